@@ -1,0 +1,143 @@
+/*
+ * wdx_b200.h — C ABI of the B200-native WarpDemuX classification path.
+ *
+ * Drop-in boundary: these entry points are what a ctypes/cffi binding inside
+ * the reference would call instead of its CPU code.  Plain pointers and sizes,
+ * no torch / numpy / C++ types.  Every data pointer may be HOST memory
+ * (pageable or pinned) or DEVICE memory of the model's device; the library
+ * asks the driver (cudaPointerGetAttributes) and stages copies itself.
+ *
+ * Return value: 0 on success, a negative wdx_status otherwise; the message is
+ * available from wdx_last_error() (thread-local).  The library never aborts
+ * and never falls back to a CPU implementation: without a usable CUDA device
+ * every compute entry point returns WDX_ERR_CUDA.
+ *
+ * Thread-safety: a wdx_model handle owns device buffers and one internal
+ * stream; calls on the SAME handle are serialised by an internal mutex, calls
+ * on different handles run concurrently.  (The reference is re-entrant and is
+ * called from worker processes / 4 live threads: one handle per worker.)
+ */
+#ifndef WDX_B200_H
+#define WDX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wdx_model wdx_model;
+
+typedef enum {
+    WDX_OK = 0,
+    WDX_ERR_INVALID = -1, /* bad argument (shape, dtype, NULL, k out of range) */
+    WDX_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+    WDX_ERR_NOMEM = -3,
+    WDX_ERR_UNSUPPORTED = -4
+} wdx_status;
+
+/* dtype tags for untyped buffers */
+enum { WDX_F64 = 0, WDX_F32 = 1 };
+
+/* Arithmetic mode of the DTW recurrence.
+ *  EXACT_F64        float64, no FMA contraction: distances bit-identical to the
+ *                   CPU restatement of dtaidistance's dtw_distance.
+ *  FAST_F32         float32 with FMA: distances within 1e-5 relative.
+ *  FAST_F32_GUARDED FAST_F32, then every read whose confidence margin lies
+ *                   within `guard` of its threshold, or whose top-2 class
+ *                   probabilities are within `guard`, is recomputed in
+ *                   EXACT_F64 — labels/threshold decisions equal EXACT's. */
+enum { WDX_MODE_EXACT_F64 = 0, WDX_MODE_FAST_F32 = 1, WDX_MODE_FAST_F32_GUARDED = 2 };
+
+/* per-read status bits written to `flags` */
+enum {
+    WDX_FLAG_NONFINITE = 1, /* fingerprint or a kernel value was NaN/inf (sklearn would raise) */
+    WDX_FLAG_RECOMPUTED = 2 /* GUARDED mode: this read was redone in EXACT_F64 */
+};
+
+/* ---- model -------------------------------------------------------------
+ * Replaces the state the reference keeps in a pickled DTW_SVM:
+ *   warpdemux/models/dtw_base.py:13-25 (model, _X, label_mapper, thresholds,
+ *   window, penalty), warpdemux/models/dtw_svm.py:26-30 (gamma, pwr_dist),
+ *   sklearn SVC arrays walked by svm.cpp:2868-2896.
+ *
+ *   sv          [n_sv, L]        float64, support vectors, class-sorted (DTW_SVM._X)
+ *   n_sv_class  [k]              SVC._n_support
+ *   dual_coef   [k-1, n_sv]      SVC._dual_coef_, row-major
+ *   rho         [k(k-1)/2]       -SVC._intercept_
+ *   probA/probB [k(k-1)/2]       Platt coefficients
+ *   thresholds  [k]              per-class confidence thresholds (DTW_SVM.thresholds)
+ *   label_map   [k]              class index -> barcode label (noise = -1)
+ *   window      Sakoe-Chiba window as dtaidistance defines it (|i-j| <= window-1); 0 = none
+ *   penalty     NOT squared here (the library squares it, like dtaidistance)
+ * All arrays are HOST pointers and are copied.  2 <= k <= 16, 1 <= L <= 64. */
+int wdx_model_create(const double* sv, int n_sv, int L, const int32_t* n_sv_class, int k,
+                     const double* dual_coef, const double* rho, const double* probA,
+                     const double* probB, const double* thresholds, const int64_t* label_map,
+                     int window, double penalty, double gamma, int pwr_dist, int device,
+                     wdx_model** out);
+
+void wdx_model_destroy(wdx_model* m);
+
+/* Guard band of WDX_MODE_FAST_F32_GUARDED (default 2e-3). */
+int wdx_model_set_guard(wdx_model* m, double guard);
+
+/* Reads per internal launch (default 2^22); bounds the scratch for the
+ * one-vs-one decision sums (k(k-1)/2 doubles per read). */
+int wdx_model_set_chunk_reads(wdx_model* m, int64_t chunk_reads);
+
+/* How many contiguous ranges the support-vector list is cut into (grid.y).
+ * 0 (default) = automatic: 1 for large batches, more for small ones so that a
+ * 512-read live batch still fills the GPU.  With 1 the one-vs-one decision
+ * sums are accumulated in exactly libsvm's order. */
+int wdx_model_set_sv_splits(wdx_model* m, int splits);
+
+/* ---- predict -------------------------------------------------------------
+ * Replaces DTW_SVM.predict (warpdemux/models/dtw_svm.py:54-98):
+ * distance_matrix_to (parallel_distances.py:58-67) -> pdist_kernel
+ * (dtw_svm.py:21-22) -> SVC.predict_proba (svm.cpp:2921-2964) -> process_probs
+ * (models/utils.py:45-61), fused on the device; the distance matrix is never
+ * written to HBM unless `dist` is given.
+ *
+ *   X       [n, L]     fingerprints, x_dtype WDX_F64 or WDX_F32
+ *   labels  [n]        int64 barcode labels (-1 = below threshold / noise)    (required)
+ *   conf    [n]        float64 top1-top2 probability margin                    (or NULL)
+ *   prob    [n, k]     float64 class probabilities                             (or NULL)
+ *   flags   [n]        uint8 WDX_FLAG_* bits                                   (or NULL)
+ *   dist    [n, n_sv]  float32 DTW distances as the reference casts them       (or NULL; debug/secondary seam)
+ *   stream  cudaStream_t to launch on, or NULL for the handle's own stream.
+ * The call returns after the results are complete, except when EVERY buffer
+ * is device memory and `stream` is non-NULL: then the work is only enqueued
+ * on `stream` (no host synchronisation).  Host input is staged through pinned
+ * memory in chunks, the copy of chunk c+1 overlapping the kernels of chunk c. */
+int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode,
+                int64_t* labels, double* conf, double* prob, uint8_t* flags,
+                float* dist, void* stream);
+
+/* ---- distance matrix (secondary seam) ------------------------------------
+ * Replaces warpdemux.parallel_distances.distance_matrix_to
+ * (parallel_distances.py:48-84): DTW between every row of X [nX,L] and every
+ * row of Y [nY,L] (float64 in), window/penalty as above.
+ *   out_dtype WDX_F32: float32 [nX,nY], the reference's return dtype;
+ *   out_dtype WDX_F64: float64 [nX,nY], the values before that cast
+ *                      (bit-exact vs the CPU restatement in EXACT mode). */
+int wdx_distance_matrix_to(const double* X, int64_t nX, const double* Y, int64_t nY, int L,
+                           int window, double penalty, int mode, void* out, int out_dtype,
+                           int device, void* stream);
+
+/* ---- introspection -------------------------------------------------------- */
+const char* wdx_last_error(void);
+int wdx_device_count(void);
+/* Kernels launched by this library in this process so far (for bench accounting). */
+int64_t wdx_kernel_launch_count(void);
+/* Device time (ms) the dominant fused DTW+SVC kernel took in the last
+ * wdx_predict on this handle, and how many launches that covered; measured
+ * with CUDA events on the handle's stream when timing is enabled. */
+int wdx_model_enable_timing(wdx_model* m, int on);
+int wdx_model_last_kernel_ms(wdx_model* m, double* ms, int* launches);
+const char* wdx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WDX_B200_H */

@@ -1,0 +1,76 @@
+"""CPU-side checks of the boundary: the C-ABI library builds/loads and exports
+every symbol include/wdx_b200.h declares; without a GPU it fails loudly instead
+of computing on the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "wdx_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(wdx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported():
+    from warpdemux_b200 import _lib
+
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert "wdx_predict" in declared and "wdx_model_create" in declared
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/wdx_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert b"sm_100a" in lib.wdx_version()
+
+
+def test_no_cpu_fallback_without_gpu(models):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from warpdemux_b200 import _lib
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    assert _lib.device_count() == 0
+    mdl = DTW_SVM(models["WDX4_rna004_v1_0"])
+    with pytest.raises(_lib.WdxError, match="no CUDA device"):
+        mdl.predict(np.zeros((2, 25)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "warpdemux_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_argument_validation_precedes_device_use(models):
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    mdl = DTW_SVM(models["WDX4_rna004_v1_0"])
+    with pytest.raises(ValueError, match="same number of columns"):
+        mdl.predict(np.zeros((3, 24)))
+    with pytest.raises(ValueError, match="Model not trained yet."):
+        DTW_SVM(None).predict(np.zeros((1, 25)))
+    with pytest.raises(ValueError):
+        DTW_SVM(models["WDX4_rna004_v1_0"], mode="bogus")
+
+
+def test_sharding_is_contiguous_and_complete():
+    from warpdemux_b200.sharding import shard_bounds, shard_of
+
+    for n, w in [(10, 3), (100, 8), (7, 8), (0, 2), (100_000_000, 8), (1, 1)]:
+        b = shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[g][1] == b[g + 1][0] for g in range(w - 1))
+        for g, (s, e) in enumerate(b):
+            if e > s:
+                assert shard_of(s, n, w) == g and shard_of(e - 1, n, w) == g

@@ -1,0 +1,226 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the
+golden outputs of the reference's own DTW_SVM.predict.
+
+Bars: EXACT_F64 distances bit-identical to the oracle; float32 casts identical;
+labels / threshold decisions identical; probabilities within 2e-6 (the float32
+exp of the kernel is not bit-reproducible across implementations);
+FAST_F32 distances within 1e-5 relative (BASELINE.json north_star)."""
+import pickle
+
+import numpy as np
+import pytest
+
+from tests.conftest import synth_fingerprints
+
+pytestmark = pytest.mark.gpu
+
+PROB_ATOL = 2e-6
+FAST_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev_models(models):
+    from warpdemux_b200.device_model import DeviceModel
+
+    out = {n: DeviceModel(m, 0) for n, m in models.items()}
+    yield out
+    for d in out.values():
+        d.close()
+
+
+def test_distance_matrix_exact_is_bitwise(models):
+    from oracle import wdx_oracle as o
+    from warpdemux_b200.device_model import distance_matrix
+
+    m = models["WDX4_rna004_v1_0"]
+    X = synth_fingerprints(m.sv, 300, seed=3)
+    want = o.dtw_matrix(X, m.sv, m.window, m.penalty)
+    got = distance_matrix(X, m.sv, m.window, m.penalty, mode="exact", out_dtype=np.float64)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    got32 = distance_matrix(X, m.sv, m.window, m.penalty, mode="exact", out_dtype=np.float32)
+    assert np.array_equal(got32, want.astype(np.float32))
+    fast = distance_matrix(X, m.sv, m.window, m.penalty, mode="fast", out_dtype=np.float64)
+    rel = np.abs(fast - want) / np.maximum(want, 1e-30)
+    assert rel.max() <= FAST_RTOL, rel.max()
+
+
+def test_distance_matrix_to_seam(models):
+    """drop-in `distance_matrix_to` (parallel_distances.py:48-84): float32 out."""
+    from oracle import wdx_oracle as o
+    from warpdemux_b200.parallel_distances import distance_matrix_to
+
+    m = models["WDX6_rna004_v1_0"]
+    X = synth_fingerprints(m.sv, 130, seed=4)
+    got = distance_matrix_to(X, m.sv, window=m.window, penalty=m.penalty, block_size=500, n_jobs=1)
+    assert got.dtype == np.float32
+    assert np.array_equal(got, o.distance_matrix_to(X, m.sv, m.window, m.penalty))
+    # symmetric use (SV vs SV): zero diagonal, bit-wise symmetric
+    D = distance_matrix_to(m.sv[:200], m.sv[:200], window=m.window, penalty=m.penalty)
+    assert np.all(np.diag(D) == 0) and np.array_equal(D, D.T)
+
+
+@pytest.mark.parametrize("shape", [(12, 5, 0.1), (30, 0, 0.0), (25, 25, 0.3), (25, 14, 0.1), (1, 1, 0.1), (64, 20, 0.05)])
+def test_distance_matrix_generic_shapes(shape):
+    from oracle import wdx_oracle as o
+    from warpdemux_b200.device_model import distance_matrix
+
+    L, w, pen = shape
+    rng = np.random.default_rng(L * 100 + w)
+    X, Y = rng.standard_normal((70, L)), rng.standard_normal((150, L))
+    want = o.dtw_matrix(X, Y, w, pen)
+    got = distance_matrix(X, Y, w, pen, mode="exact", out_dtype=np.float64)
+    assert np.array_equal(got, want)
+    fast = distance_matrix(X, Y, w, pen, mode="fast", out_dtype=np.float64)
+    assert np.allclose(fast, want, rtol=FAST_RTOL, atol=1e-12)
+
+
+def test_golden_predict_exact(models, dev_models, golden_predict):
+    """Same inputs the reference's DTW_SVM.predict was run on (oracle/make_golden.py)."""
+    for name, g in golden_predict.items():
+        labels, prob, conf, flags, dist = dev_models[name].predict(g["X"], mode="exact", want_dist=True)
+        assert np.array_equal(labels, g["y_pred"]), name
+        np.testing.assert_allclose(prob, g["y_prob"], rtol=0, atol=PROB_ATOL)
+        nd = g["D"].shape[0]
+        assert np.array_equal(dist[:nd], g["D"]), name  # float32 distances bit-identical
+        assert not flags.any()
+        np.testing.assert_allclose(prob.sum(1), 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,splits", [(1, 0), (37, 0), (1000, 0), (1000, 1), (513, 7), (2500, 3)])
+def test_predict_matches_oracle_across_split_geometries(models, dev_models, n, splits):
+    from oracle import wdx_oracle as o
+
+    for name in ("WDX4_rna004_v1_0", "WDX10_rna004_v1_0"):
+        if name.startswith("WDX10") and n > 1000:
+            continue
+        m, d = models[name], dev_models[name]
+        X = synth_fingerprints(m.sv, n, seed=n + splits)
+        want_pred, want_prob, want_conf, want_D = o.predict(m, X)
+        d.set_sv_splits(splits)
+        try:
+            labels, prob, conf, flags, dist = d.predict(X, mode="exact", want_dist=True)
+        finally:
+            d.set_sv_splits(0)
+        assert np.array_equal(dist, want_D)
+        np.testing.assert_allclose(prob, want_prob, rtol=0, atol=PROB_ATOL)
+        np.testing.assert_allclose(conf, want_conf, rtol=0, atol=2 * PROB_ATOL)
+        # labels identical except where the oracle itself is within float32-exp noise of a boundary
+        diff = labels != want_pred
+        if diff.any():
+            thr = m.thresholds[np.argmax(want_prob, 1)]
+            assert np.all(np.minimum(np.abs(want_conf - thr), want_conf)[diff] < 4 * PROB_ATOL)
+
+
+def test_fast_and_guarded_modes(models, dev_models):
+    name = "WDX4_rna004_v1_0"
+    m, d = models[name], dev_models[name]
+    X = synth_fingerprints(m.sv, 30000, seed=11)
+    le, pe, ce, _ = d.predict(X, mode="exact")
+    lf, pf, cf, _, = d.predict(X, mode="fast")
+    lg, pg, cg, fg = d.predict(X, mode="guarded")
+    # fast: probabilities close, a few boundary labels may differ
+    assert np.abs(pf - pe).max() < 5e-4
+    assert (lf != le).mean() < 2e-3
+    # guarded: decisions identical to exact; recomputed reads carry exact values
+    assert np.array_equal(lg, le)
+    rec = (fg & 2) != 0
+    assert 0 < rec.sum() < 0.05 * len(X)
+    assert np.array_equal(pg[rec], pe[rec]) and np.array_equal(cg[rec], ce[rec])
+    assert np.array_equal(pg[~rec], pf[~rec])
+
+
+def test_dropin_class_api(models, golden_predict):
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    name = "WDX4_rna004_v1_0"
+    g = golden_predict[name]
+    mdl = DTW_SVM(models[name], mode="exact")
+    y_pred, y_prob = mdl.predict(g["X"], nproc=1, return_df=False)
+    assert y_pred.dtype == np.int64 and y_prob.dtype == np.float64 and y_prob.shape == (len(g["X"]), 5)
+    assert np.array_equal(y_pred, g["y_pred"])
+    df = mdl.predict(g["X"], pbar=False, nproc=1, return_df=True)  # the call file_proc.py:445-450 makes
+    assert list(df.columns) == list(g["df_columns"])
+    assert np.array_equal(df["predicted_barcode"].to_numpy(), g["y_pred"])
+    np.testing.assert_allclose(df.to_numpy(dtype=np.float64)[:, 1:], g["df_values"][:, 1:], atol=1.01e-3)
+    # 1-D input is one read (dtw_svm.py:70-71), the live caller's shape (worker.py:117-120)
+    y1, p1 = mdl.predict(g["X"][5])
+    assert y1.shape == (1,) and p1.shape == (1, 5) and y1[0] == g["y_pred"][5]
+    # error behaviour (dtw_svm.py:65-77)
+    with pytest.raises(ValueError, match="same number of columns"):
+        mdl.predict(np.zeros((3, 24)))
+    with pytest.raises(ValueError, match="Model not trained yet."):
+        DTW_SVM(None).predict(np.zeros((1, 25)))
+    # picklable like the reference model that is shipped to every worker (file_proc.py:1232-1243)
+    clone = pickle.loads(pickle.dumps(mdl))
+    y2, p2 = clone.predict(g["X"][:16], nproc=1)
+    assert np.array_equal(y2, g["y_pred"][:16])
+    # empty batch
+    y0, p0 = mdl.predict(np.zeros((0, 25)))
+    assert y0.shape == (0,) and p0.shape == (0, 5)
+
+
+def test_nonfinite_fingerprints(models):
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    m = models["WDX4_rna004_v1_0"]
+    X = synth_fingerprints(m.sv, 40, seed=1)
+    X[7, 3] = np.nan
+    with pytest.raises(ValueError, match="NaN"):  # sklearn's check in predict_proba raises in the reference
+        DTW_SVM(m, mode="exact").predict(X)
+    y, p = DTW_SVM(m, mode="exact", on_nonfinite="noise").predict(X)
+    assert y[7] == -1 and np.isnan(p[7]).all()
+    ok = np.ones(40, bool)
+    ok[7] = False
+    y_ref, p_ref = DTW_SVM(m, mode="exact").predict(X[ok])
+    assert np.array_equal(y[ok], y_ref) and np.array_equal(p[ok], p_ref)
+    # +inf gives distance inf, kernel 0: finite probabilities, like the reference
+    X2 = synth_fingerprints(m.sv, 8, seed=2)
+    X2[3, 0] = np.inf
+    y2, p2 = DTW_SVM(m, mode="exact").predict(X2)
+    assert np.isfinite(p2).all()
+
+
+def test_float32_input_and_device_pointers(models, dev_models):
+    import torch
+
+    from warpdemux_b200 import _lib
+
+    name = "WDX6_rna004_v1_0"
+    m, d = models[name], dev_models[name]
+    X = synth_fingerprints(m.sv, 700, seed=5)
+    l64, p64, c64, _ = d.predict(X, mode="exact")
+    X32 = X.astype(np.float32)
+    l32, p32, _, _ = d.predict(X32, mode="exact")
+    l32b, p32b, _, _ = d.predict(X32.astype(np.float64), mode="exact")
+    assert np.array_equal(l32, l32b) and np.array_equal(p32, p32b)  # f32 input widened exactly
+    # device-resident buffers (torch only as the allocator)
+    Xd = torch.from_numpy(X).cuda()
+    lab = torch.empty(len(X), dtype=torch.int64, device="cuda")
+    prob = torch.empty((len(X), m.k), dtype=torch.float64, device="cuda")
+    conf = torch.empty(len(X), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    d.predict_raw(Xd, len(X), _lib.WDX_F64, _lib.MODE_EXACT_F64, lab, conf, prob, None, None, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(lab.cpu().numpy(), l64) and np.array_equal(prob.cpu().numpy(), p64)
+
+
+def test_synthetic_model_shapes(models):
+    """Shapes beyond the shipped ones: 13 classes (deprecated WDX12 shape), tiny classes, L != 25."""
+    from oracle import wdx_oracle as o
+    from warpdemux_b200 import model_io
+    from warpdemux_b200.device_model import DeviceModel
+
+    for n_sv_class, L, w in [([40] * 13, 25, 15), ([3, 1, 70, 2], 25, 15), ([30, 50, 20], 16, 6), ([5, 5], 25, 15),
+                             ([20] * 16, 25, 15)]:
+        m = model_io.synthetic_model(n_sv_class, L=L, window=w, seed=len(n_sv_class))
+        X = synth_fingerprints(m.sv, 300, seed=9, sigma=0.5)
+        want_pred, want_prob, want_conf, want_D = o.predict(m, X)
+        d = DeviceModel(m, 0)
+        for splits in (0, 1, 5):
+            d.set_sv_splits(splits)
+            labels, prob, conf, flags, dist = d.predict(X, mode="exact", want_dist=True)
+            assert np.array_equal(dist, want_D)
+            np.testing.assert_allclose(prob, want_prob, rtol=0, atol=PROB_ATOL)
+            diff = labels != want_pred
+            assert diff.mean() < 0.01
+        d.close()

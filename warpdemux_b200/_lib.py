@@ -1,0 +1,100 @@
+"""ctypes binding of libwdx_b200.so (C ABI in include/wdx_b200.h).
+
+The CUDA library is the only compute path: if it cannot be loaded this module
+raises — there is no CPU or PyTorch fallback behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwdx_b200.so")
+
+WDX_F64, WDX_F32 = 0, 1
+MODE_EXACT_F64, MODE_FAST_F32, MODE_FAST_F32_GUARDED = 0, 1, 2
+MODES = {"exact": MODE_EXACT_F64, "fast": MODE_FAST_F32, "guarded": MODE_FAST_F32_GUARDED}
+FLAG_NONFINITE, FLAG_RECOMPUTED = 1, 2
+
+# every symbol include/wdx_b200.h declares
+EXPORTS = [
+    "wdx_model_create", "wdx_model_destroy", "wdx_model_set_guard", "wdx_model_set_chunk_reads", "wdx_model_set_sv_splits",
+    "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
+    "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_version",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class WdxError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc is present)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            try:
+                from . import build as _build
+
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise WdxError(
+                    f"libwdx_b200.so is not built ({LIB_PATH}) and could not be built here: {e}. "
+                    "Run `python -m warpdemux_b200.build`. There is no CPU fallback."
+                ) from e
+        try:
+            L = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise WdxError(f"cannot load {LIB_PATH}: {e}. There is no CPU fallback.") from e
+        vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.wdx_model_create.restype = i32
+        L.wdx_model_create.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, i32, f64, f64, i32, i32,
+                                       C.POINTER(vp)]
+        L.wdx_model_destroy.restype = None
+        L.wdx_model_destroy.argtypes = [vp]
+        L.wdx_model_set_guard.restype = i32
+        L.wdx_model_set_guard.argtypes = [vp, f64]
+        L.wdx_model_set_chunk_reads.restype = i32
+        L.wdx_model_set_chunk_reads.argtypes = [vp, i64]
+        L.wdx_model_set_sv_splits.restype = i32
+        L.wdx_model_set_sv_splits.argtypes = [vp, i32]
+        L.wdx_predict.restype = i32
+        L.wdx_predict.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.wdx_distance_matrix_to.restype = i32
+        L.wdx_distance_matrix_to.argtypes = [vp, i64, vp, i64, i32, i32, f64, i32, vp, i32, i32, vp]
+        L.wdx_last_error.restype = C.c_char_p
+        L.wdx_device_count.restype = i32
+        L.wdx_kernel_launch_count.restype = i64
+        L.wdx_model_enable_timing.restype = i32
+        L.wdx_model_enable_timing.argtypes = [vp, i32]
+        L.wdx_model_last_kernel_ms.restype = i32
+        L.wdx_model_last_kernel_ms.argtypes = [vp, C.POINTER(f64), C.POINTER(i32)]
+        L.wdx_version.restype = C.c_char_p
+        if hasattr(L, "wdx_fingerprint"):
+            L.wdx_fingerprint.restype = i32
+        _lib = L
+        return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().wdx_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        if rc == -3:
+            raise MemoryError(f"{what}: {msg}")
+        raise WdxError(f"{what}: {msg} (status {rc})")
+
+
+def device_count() -> int:
+    return int(load().wdx_device_count())
+
+
+def kernel_launch_count() -> int:
+    return int(load().wdx_kernel_launch_count())

@@ -1,0 +1,505 @@
+// fused_kernels.cuh — the fused DTW + SVC-decision kernel and the probability
+// finishing kernel (sm_100a).
+//
+// Mapping: one thread owns one read for the whole launch; its
+// fingerprint lives in registers.  The CTA walks the model's support vectors in
+// class-sorted order, TILE_SV at a time, each tile brought into shared memory
+// by one TMA bulk copy (cp.async.bulk + mbarrier, double-buffered).  A support
+// vector is warp-uniform, so its 25 values reach the registers of all 32 lanes
+// by broadcast LDS.128.  After each (read, SV) DTW the distance goes straight
+// into the libsvm one-vs-one decision sums — exp kernel, then k-1 multiply-adds
+// with that SV's dual coefficients — so the distance matrix never exists in HBM.
+// The k-1 running sums of the CURRENT class stay in registers; at a class
+// boundary they are parked in / fetched from a small per-read scratch array in
+// global memory (k-1 doubles per read per class: noise next to 1.3 M DTW cells).
+//
+// Summation order is libsvm's (svm.cpp:2868-2896): for pair (i<j) first class-i
+// SVs ascending, then class-j SVs ascending — exactly the order a walk over the
+// class-sorted SV list produces, so with one SV split the decision values are
+// formed in the same order as the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dtw_band.cuh"
+
+namespace wdx {
+
+constexpr int CTA_THREADS = 128;
+constexpr int TILE_SV = 64;
+constexpr int MAXK = 16;
+constexpr int MAXL = 64;
+
+struct ModelDev {
+    // support vectors, tile-friendly rows (16-byte multiples for TMA bulk copies)
+    const float* sv_f32;    // [n_sv][ldf]   ldf = roundup(L,4)
+    const double* sv_f64;   // [n_sv][ldd]   ldd = roundup(L,2)
+    const double* coef;     // [n_sv][ldc]   coef[s][r] = dual_coef[r][s], ldc = roundup(k-1,2)
+    const double* rho;      // [n_pairs]
+    const double* probA;    // [n_pairs]
+    const double* probB;    // [n_pairs]
+    const double* thresholds;  // [k]
+    const int64_t* label_map;  // [k]
+    int class_start[MAXK + 1];
+    int n_sv, L, k, n_pairs, ldf, ldd, ldc;
+    int window;
+    double p2;      // penalty^2
+    double gamma;
+    int pwr_dist;
+};
+
+struct PredictArgs {
+    const void* X;        // [n][L] row-major, f64 or f32
+    int x_is_f32;
+    const int* read_idx;  // optional indirection (GUARDED recompute list) or nullptr
+    const int* n_idx;     // device count for read_idx (nullptr => n)
+    int64_t n;            // reads in this launch (upper bound when n_idx != nullptr)
+    int64_t part_stride;  // elements between consecutive (split,pair) planes (>= n)
+    double* part;         // [n_splits][n_pairs][part_stride] partial decision sums
+    float* dist;          // optional [n][n_sv] float32 distances (debug / secondary seam), or nullptr
+    int n_splits, sv_per_split;
+};
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copy (global -> shared)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ inline int pair_index(int i, int j, int k) {  // i < j
+    return i * k - i * (i + 1) / 2 + (j - i - 1);
+}
+
+// Does SV range [b,e) contain any SV of class c?
+__device__ __forceinline__ bool range_touches(const ModelDev& m, int b, int e, int c) {
+    const int lo = max(b, m.class_start[c]), hi = min(e, m.class_start[c + 1]);
+    return lo < hi;
+}
+
+template <typename T>
+__device__ __forceinline__ T kernel_value(T d2, const ModelDev& m);
+
+// K = float32(exp(-gamma * float32(d)^pwr)) as the reference forms it
+// (parallel_distances.py:67 casts d to float32; dtw_svm.py:21-22 evaluates the
+// kernel in float32); returned widened to double like sklearn's upcast.
+__device__ __forceinline__ double kernel_from_dist_f32(float d, float gamma, int pwr) {
+    float pw = d;
+    if (pwr != 1) {
+        pw = 1.0f;
+        for (int q = 0; q < pwr; q++) pw *= d;
+    }
+    return (double)expf(-gamma * pw);
+}
+// EXACT mode: exp evaluated in double and rounded once to float32 — the
+// correctly rounded float32 exp except in double-rounding corner cases.
+__device__ __forceinline__ double kernel_from_dist_f32_exact(float d, float gamma, int pwr) {
+    float pw = d;
+    if (pwr != 1) {
+        pw = 1.0f;
+        for (int q = 0; q < pwr; q++) pw = __fmul_rn(pw, d);
+    }
+    const float x = __fmul_rn(-gamma, pw);
+    return (double)(float)exp((double)x);
+}
+
+// ---------------------------------------------------------------------------
+// Fused DTW + SVC decision-sum kernel.
+//   EXACT : DTW in float64 (bit-exact), decision sums with separate mul/add
+//   !EXACT: DTW in float32, decision sums with DFMA
+//   L_, W_: compile-time fingerprint length / window (25 / 15 for every shipped
+//           model); L_ == 0 selects the generic runtime-shape fallback.
+//   KM1   : compile-time bound on k-1 (accumulators in registers)
+// grid = (ceil(n / CTA_THREADS), n_splits)
+// ---------------------------------------------------------------------------
+template <bool EXACT, int L_, int W_, int KM1>
+__global__ void __launch_bounds__(CTA_THREADS, EXACT ? 3 : 4)
+dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ PredictArgs a) {
+    using T = typename std::conditional<EXACT, double, float>::type;
+    constexpr bool GENERIC = (L_ == 0);
+    constexpr int LR = GENERIC ? MAXL : L_;             // register/local array length
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int L = GENERIC ? m.L : L_;
+    const int ldsv = EXACT ? m.ldd : m.ldf;             // elements per SV row in the tile
+    const int sv_row_bytes = ldsv * (int)sizeof(T);
+    const int coef_row_bytes = m.ldc * 8;
+    const int tile_sv_bytes = TILE_SV * sv_row_bytes;
+    const int tile_coef_bytes = TILE_SV * coef_row_bytes;
+    const int stage_bytes = tile_sv_bytes + tile_coef_bytes;   // multiple of 16
+    unsigned char* stage0 = smem_raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * stage_bytes);
+
+    const int64_t n_eff = a.n_idx ? (int64_t)(*a.n_idx) : a.n;
+    const int64_t cta_first = (int64_t)blockIdx.x * CTA_THREADS;
+    if (cta_first >= n_eff) return;                     // whole CTA idle (uniform)
+    const int64_t slot = cta_first + tid;               // position in this launch
+    const bool active = slot < n_eff;
+    const int64_t row = active ? (a.read_idx ? (int64_t)a.read_idx[slot] : slot) : 0;
+
+    const int split = blockIdx.y;
+    const int sv_begin = split * a.sv_per_split;
+    const int sv_end = min(m.n_sv, sv_begin + a.sv_per_split);
+    if (sv_begin >= sv_end) return;
+
+    // ---- fingerprints: coalesced 16-byte loads into shared memory, then each
+    // thread lifts its own row into registers.
+    T x[LR];
+    {
+        const int esz = a.x_is_f32 ? 4 : 8;
+        const int row_bytes = L * esz;
+        unsigned char* xs = smem_raw;  // aliases the SV stages; released before the pipeline starts
+        if (a.read_idx == nullptr) {
+            const int64_t rows_here = min((int64_t)CTA_THREADS, n_eff - cta_first);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.X) + cta_first * row_bytes;
+            const int64_t total = rows_here * row_bytes;
+            const bool al16 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+            if (al16) {
+                const int64_t n16 = total >> 4;
+                for (int64_t q = tid; q < n16; q += CTA_THREADS)
+                    reinterpret_cast<uint4*>(xs)[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                for (int64_t q = (n16 << 4) + tid; q < total; q += CTA_THREADS) xs[q] = src[q];
+            } else {
+                const int64_t n4 = total >> 2;  // rows are at least 4-byte aligned
+                for (int64_t q = tid; q < n4; q += CTA_THREADS)
+                    reinterpret_cast<uint32_t*>(xs)[q] = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
+            }
+        } else if (active) {  // gathered rows (recompute list): per-thread copy
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.X) + row * row_bytes;
+            for (int q = 0; q < row_bytes; q += 4)
+                *reinterpret_cast<uint32_t*>(xs + (int64_t)tid * row_bytes + q) = *reinterpret_cast<const uint32_t*>(src + q);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LR; j++) {
+            if (j < L && active) {
+                if (a.x_is_f32) x[j] = (T) reinterpret_cast<const float*>(xs)[tid * L + j];
+                else x[j] = (T) reinterpret_cast<const double*>(xs)[tid * L + j];
+            } else {
+                x[j] = (T)0;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- TMA pipeline over SV tiles
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();  // generic writes to the staging area above precede async-proxy writes
+    }
+    __syncthreads();
+    const int n_tiles = (sv_end - sv_begin + TILE_SV - 1) / TILE_SV;
+    auto issue_tile = [&](int t) {
+        const int base = sv_begin + t * TILE_SV;
+        const int cnt = min(TILE_SV, sv_end - base);
+        unsigned char* st = stage0 + (t & 1) * stage_bytes;
+        const uint32_t b_sv = cnt * sv_row_bytes, b_cf = cnt * coef_row_bytes;
+        mbar_expect_tx(&bars[t & 1], b_sv + b_cf);
+        const unsigned char* gsv = EXACT ? reinterpret_cast<const unsigned char*>(m.sv_f64) : reinterpret_cast<const unsigned char*>(m.sv_f32);
+        tma_load_1d(st, gsv + (size_t)base * sv_row_bytes, b_sv, &bars[t & 1]);
+        tma_load_1d(st + tile_sv_bytes, reinterpret_cast<const unsigned char*>(m.coef) + (size_t)base * coef_row_bytes, b_cf, &bars[t & 1]);
+    };
+    if (tid == 0) {
+        issue_tile(0);
+        if (n_tiles > 1) issue_tile(1);
+    }
+
+    const T p2 = (T)m.p2;
+    const float gamma_f = (float)m.gamma;
+    const int k = m.k, km1 = k - 1;
+    double acc[KM1];
+#pragma unroll
+    for (int r = 0; r < KM1; r++) acc[r] = 0.0;
+
+    // class of the first SV of this split
+    int cls = 0;
+    while (m.class_start[cls + 1] <= sv_begin) cls++;
+    int next_boundary = m.class_start[cls + 1];
+
+    double* part = a.part + (size_t)split * m.n_pairs * a.part_stride + slot;
+    auto pidx = [&](int c, int r) {
+        const int o = (r < c) ? r : r + 1;
+        return (c < o) ? pair_index(c, o, k) : pair_index(o, c, k);
+    };
+    auto park = [&](int c) {  // store the running sums of class c
+        if (!active) return;
+#pragma unroll
+        for (int r = 0; r < KM1; r++)
+            if (r < km1) part[(size_t)pidx(c, r) * a.part_stride] = acc[r];
+    };
+    auto fetch = [&](int c) {  // resume (or start) the running sums of class c
+#pragma unroll
+        for (int r = 0; r < KM1; r++) {
+            acc[r] = 0.0;
+            if (r < km1 && active) {
+                const int o = (r < c) ? r : r + 1;
+                // pair (o,c), o<c, already holds class o's contribution iff class o intersects this split
+                if (o < c && range_touches(m, sv_begin, sv_end, o)) acc[r] = part[(size_t)pidx(c, r) * a.part_stride];
+            }
+        }
+    };
+
+    // A NaN fingerprint gives NaN distances, NaN kernel values and therefore NaN
+    // decision sums (0 * NaN = NaN too); the finishing kernel flags the read.
+    for (int t = 0; t < n_tiles; t++) {
+        const unsigned char* st = stage0 + (t & 1) * stage_bytes;
+        mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
+        const int base = sv_begin + t * TILE_SV;
+        const int cnt = min(TILE_SV, sv_end - base);
+        for (int q = 0; q < cnt; q++) {
+            const int s_glob = base + q;
+            if (s_glob == next_boundary) {  // warp-uniform
+                park(cls);
+                do { cls++; } while (m.class_start[cls + 1] <= s_glob);
+                next_boundary = m.class_start[cls + 1];
+                fetch(cls);
+            }
+            // support vector -> registers (broadcast 16-byte shared loads)
+            T s[LR];
+            const T* srow = reinterpret_cast<const T*>(st + q * sv_row_bytes);
+            T d2;
+            if constexpr (!GENERIC) {
+                constexpr int VEC = 16 / sizeof(T);
+#pragma unroll
+                for (int j = 0; j < L_; j += VEC) {
+                    if constexpr (EXACT) {
+                        const double2 w = *reinterpret_cast<const double2*>(srow + j);
+                        s[j] = w.x;
+                        if (j + 1 < L_) s[j + 1] = w.y;
+                    } else {
+                        const float4 w = *reinterpret_cast<const float4*>(srow + j);
+                        s[j] = w.x;
+                        if (j + 1 < L_) s[j + 1] = w.y;
+                        if (j + 2 < L_) s[j + 2] = w.z;
+                        if (j + 3 < L_) s[j + 3] = w.w;
+                    }
+                }
+                if constexpr (EXACT) d2 = dtw_band_f64<L_, W_>(x, s, p2);
+                else d2 = dtw_band_f32<L_, W_>(x, s, p2);
+            } else {
+                for (int j = 0; j < L; j++) s[j] = srow[j];
+                d2 = dtw_generic<T, MAXL>(x, s, L, m.window, p2);
+            }
+            // distance -> float32 (the reference's cast) -> kernel value
+            float d32;
+            if constexpr (EXACT) d32 = (float)__dsqrt_rn(d2);
+            else d32 = sqrtf(d2);
+            if (a.dist && active) a.dist[(size_t)row * m.n_sv + s_glob] = d32;
+            double Kd;
+            if constexpr (EXACT) Kd = kernel_from_dist_f32_exact(d32, gamma_f, m.pwr_dist);
+            else Kd = kernel_from_dist_f32(d32, gamma_f, m.pwr_dist);
+            // decision sums of the current class (svm.cpp:2880-2884)
+            const double* crow = reinterpret_cast<const double*>(st + tile_sv_bytes + q * coef_row_bytes);
+#pragma unroll
+            for (int r = 0; r < KM1; r += 2) {
+                if (r < km1) {  // ldc is even, so the 16-byte load stays inside the row
+                    const double2 c2 = *reinterpret_cast<const double2*>(crow + r);
+                    if constexpr (EXACT) acc[r] = __dadd_rn(acc[r], __dmul_rn(c2.x, Kd));
+                    else acc[r] = __fma_rn(c2.x, Kd, acc[r]);
+                    if (r + 1 < km1) {
+                        if constexpr (EXACT) acc[r + 1] = __dadd_rn(acc[r + 1], __dmul_rn(c2.y, Kd));
+                        else acc[r + 1] = __fma_rn(c2.y, Kd, acc[r + 1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with this stage
+        if (tid == 0 && t + 2 < n_tiles) issue_tile(t + 2);
+    }
+    park(cls);
+}
+
+// ---------------------------------------------------------------------------
+// Finishing kernel: decision sums -> Platt sigmoid -> pairwise coupling
+// (Wu-Lin-Weng method 2) -> argmax / margin / threshold.  One thread per read,
+// float64, no FMA contraction (this TU is compiled with -fmad=false).
+// Restates svm.cpp:2035-2104, 2921-2964 and models/utils.py:45-61.
+// ---------------------------------------------------------------------------
+struct FinishArgs {
+    const double* part;
+    int64_t part_stride;
+    int n_splits, sv_per_split;
+    const int* read_idx;   // optional: slot -> output row
+    const int* n_idx;      // optional device count
+    int64_t n;
+    int64_t* labels;
+    double* conf;
+    double* prob;          // [n][k] or nullptr
+    uint8_t* flags;        // or nullptr
+    // GUARDED: collect reads close to a decision boundary
+    int* near_idx;         // or nullptr
+    int* near_count;
+    double guard;
+    uint8_t flag_or;       // bits OR-ed into flags (WDX_FLAG_RECOMPUTED on the exact re-run)
+};
+
+__global__ void __launch_bounds__(128) svc_finish_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ FinishArgs a) {
+    const int64_t n_eff = a.n_idx ? (int64_t)(*a.n_idx) : a.n;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_eff) return;
+    const int64_t row = a.read_idx ? (int64_t)a.read_idx[slot] : slot;
+    const int k = m.k;
+
+    double R[MAXK][MAXK];
+    double Q[MAXK][MAXK];
+    double Qp[MAXK], p[MAXK];
+    bool bad = false;
+    int pi = 0;
+    for (int i = 0; i < k; i++)
+        for (int j = i + 1; j < k; j++, pi++) {
+            double sum = 0.0;
+            for (int s = 0; s < a.n_splits; s++) {
+                const int b = s * a.sv_per_split, e = min(m.n_sv, b + a.sv_per_split);
+                if (b < e && (range_touches(m, b, e, i) || range_touches(m, b, e, j)))
+                    sum += a.part[((size_t)s * m.n_pairs + pi) * a.part_stride + slot];
+            }
+            const double dec = sum - m.rho[pi];
+            bad |= !(fabs(dec) <= 1.7e308);
+            const double fApB = dec * m.probA[pi] + m.probB[pi];
+            double r = (fApB >= 0) ? exp(-fApB) / (1.0 + exp(-fApB)) : 1.0 / (1 + exp(fApB));
+            const double min_prob = 1e-7;
+            r = (r < min_prob) ? min_prob : r;            // max(r, min_prob)
+            r = ((1 - min_prob) < r) ? (1 - min_prob) : r;  // min(r, 1-min_prob)
+            R[i][j] = r;
+            R[j][i] = 1 - r;
+        }
+
+    int best = k - 1;
+    double top1 = 0.0, top2 = 0.0;
+    if (!bad) {
+        // multiclass_probability (svm.cpp:2046-2104)
+        const int max_iter = (k > 100) ? k : 100;
+        const double eps = 0.005 / k;
+        for (int t = 0; t < k; t++) {
+            p[t] = 1.0 / k;
+            Q[t][t] = 0;
+            for (int j = 0; j < t; j++) { Q[t][t] += R[j][t] * R[j][t]; Q[t][j] = Q[j][t]; }
+            for (int j = t + 1; j < k; j++) { Q[t][t] += R[j][t] * R[j][t]; Q[t][j] = -R[j][t] * R[t][j]; }
+        }
+        for (int iter = 0; iter < max_iter; iter++) {
+            double pQp = 0;
+            for (int t = 0; t < k; t++) {
+                Qp[t] = 0;
+                for (int j = 0; j < k; j++) Qp[t] += Q[t][j] * p[j];
+                pQp += p[t] * Qp[t];
+            }
+            double max_error = 0;
+            for (int t = 0; t < k; t++) {
+                const double err = fabs(Qp[t] - pQp);
+                if (err > max_error) max_error = err;
+            }
+            if (max_error < eps) break;
+            for (int t = 0; t < k; t++) {
+                const double diff = (-Qp[t] + pQp) / Q[t][t];
+                p[t] += diff;
+                pQp = (pQp + diff * (diff * Q[t][t] + 2 * Qp[t])) / (1 + diff) / (1 + diff);
+                for (int j = 0; j < k; j++) {
+                    Qp[j] = (Qp[j] + diff * Q[t][j]) / (1 + diff);
+                    p[j] /= (1 + diff);
+                }
+            }
+        }
+        // process_probs (models/utils.py:45-61): first maximum, top1 - top2
+        best = 0;
+        for (int c = 1; c < k; c++)
+            if (p[c] > p[best]) best = c;
+        top1 = p[best];
+        top2 = -INFINITY;
+        for (int c = 0; c < k; c++)
+            if (c != best && p[c] > top2) top2 = p[c];
+    }
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double conf = bad ? nan : (top1 - top2);
+    const double thr = m.thresholds[best];
+    int64_t label = m.label_map[best];
+    if (bad || conf < thr) label = -1;
+    a.labels[row] = label;
+    if (a.conf) a.conf[row] = conf;
+    if (a.prob)
+        for (int c = 0; c < k; c++) a.prob[(size_t)row * k + c] = bad ? nan : p[c];
+    if (a.flags) a.flags[row] = (uint8_t)((bad ? 1 : 0) | a.flag_or);
+    if (a.near_idx && !bad) {
+        const bool near = (fabs(conf - thr) < a.guard) || (conf < a.guard);
+        if (near) {
+            const int pos = atomicAdd(a.near_count, 1);
+            a.near_idx[pos] = (int)row;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Plain distance-matrix kernel (secondary seam, parallel_distances.py:48-84):
+// thread = row of X, loop over the rows of Y staged through shared memory.
+// ---------------------------------------------------------------------------
+template <bool EXACT, int L_, int W_, typename OutT>
+__global__ void __launch_bounds__(CTA_THREADS) dtw_matrix_kernel(const double* __restrict__ X, int64_t nX,
+                                                                  const double* __restrict__ Y, int64_t nY, int L,
+                                                                  int window, double p2d, OutT* __restrict__ out,
+                                                                  int y_per_split) {
+    using T = typename std::conditional<EXACT, double, float>::type;
+    constexpr bool GENERIC = (L_ == 0);
+    constexpr int LR = GENERIC ? MAXL : L_;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* ys = reinterpret_cast<T*>(smem_raw);  // [TILE_SV][L]
+    const int tid = threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.x * CTA_THREADS + tid;
+    const bool active = row < nX;
+    const int64_t y_begin = (int64_t)blockIdx.y * y_per_split;
+    const int64_t y_end = min(nY, y_begin + (int64_t)y_per_split);
+    T x[LR];
+#pragma unroll
+    for (int j = 0; j < LR; j++) x[j] = (j < L && active) ? (T)X[row * L + j] : (T)0;
+    const T p2 = (T)p2d;
+    for (int64_t base = y_begin; base < y_end; base += TILE_SV) {
+        const int cnt = (int)min((int64_t)TILE_SV, y_end - base);
+        __syncthreads();
+        for (int q = tid; q < cnt * L; q += CTA_THREADS) ys[q] = (T)Y[base * L + q];
+        __syncthreads();
+        for (int q = 0; q < cnt; q++) {
+            T s[LR];
+            T d2;
+            if constexpr (!GENERIC) {
+#pragma unroll
+                for (int j = 0; j < L_; j++) s[j] = ys[q * L_ + j];
+                if constexpr (EXACT) d2 = dtw_band_f64<L_, W_>(x, s, p2);
+                else d2 = dtw_band_f32<L_, W_>(x, s, p2);
+            } else {
+                for (int j = 0; j < L; j++) s[j] = ys[q * L + j];
+                d2 = dtw_generic<T, MAXL>(x, s, L, window, p2);
+            }
+            if (active) {
+                if constexpr (EXACT) out[(size_t)row * nY + base + q] = (OutT)__dsqrt_rn(d2);
+                else out[(size_t)row * nY + base + q] = (OutT)sqrtf(d2);
+            }
+        }
+    }
+}
+
+}  // namespace wdx

@@ -1,0 +1,640 @@
+// wdx_b200.cu — C-ABI implementation (include/wdx_b200.h): model handle,
+// staging, launch plumbing.  All arithmetic is in the kernels
+// (fused_kernels.cuh, dtw_band.cuh).  There is no CPU compute path here: if
+// CUDA is unavailable every entry point returns WDX_ERR_CUDA.
+#include "../../include/wdx_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "fused_kernels.cuh"
+
+using namespace wdx;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(WDX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return WDX_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(WDX_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return WDX_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return WDX_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(WDX_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return WDX_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+bool is_device_ptr(const void* p, int device) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    (void)device;
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct wdx_model {
+    ModelDev dev{};
+    int device = 0;
+    int sm_count = 148;
+    int k = 0, L = 0, n_sv = 0, n_pairs = 0;
+    bool specialised = false;  // L == 25 && window == 15
+    double guard = 2e-3;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
+    std::vector<void*> owned;            // model arrays on the device
+    // workspaces (grow-only)
+    DevBuf part, part2, near_idx, counters;
+    DevBuf xdev[2], lab_dev, conf_dev, prob_dev, flag_dev, dist_dev;
+    HostBuf xpin[2], lab_pin, conf_pin, prob_pin, flag_pin;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
+    // timing of the fused kernel
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;
+    size_t tev_used = 0;
+    int64_t chunk_reads = (int64_t)1 << 22;
+    int forced_splits = 0;
+};
+
+namespace {
+
+template <typename T>
+int upload(wdx_model* m, const std::vector<T>& h, const T** out) {
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(h.size() * sizeof(T), 16)));
+    m->owned.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(d);
+    return WDX_OK;
+}
+
+size_t fused_smem_bytes(const wdx_model* m, bool exact, bool x_f32) {
+    const size_t sv_row = exact ? (size_t)m->dev.ldd * 8 : (size_t)m->dev.ldf * 4;
+    const size_t stage = TILE_SV * (sv_row + (size_t)m->dev.ldc * 8);
+    const size_t pipe = 2 * stage + 16;
+    const size_t xs = (size_t)CTA_THREADS * m->L * (x_f32 ? 4 : 8);
+    return std::max(pipe, xs);
+}
+
+using FusedFn = void (*)(const ModelDev, const PredictArgs);
+
+template <bool EXACT, int L_, int W_>
+FusedFn pick_km1(int km1) {
+    if (km1 <= 4) return dtw_svc_kernel<EXACT, L_, W_, 4>;
+    if (km1 <= 6) return dtw_svc_kernel<EXACT, L_, W_, 6>;
+    if (km1 <= 8) return dtw_svc_kernel<EXACT, L_, W_, 8>;
+    if (km1 <= 10) return dtw_svc_kernel<EXACT, L_, W_, 10>;
+    if (km1 <= 12) return dtw_svc_kernel<EXACT, L_, W_, 12>;
+    return dtw_svc_kernel<EXACT, L_, W_, 16>;
+}
+
+FusedFn pick_fused(const wdx_model* m, bool exact) {
+    const int km1 = m->k - 1;
+    if (m->specialised) return exact ? pick_km1<true, 25, 15>(km1) : pick_km1<false, 25, 15>(km1);
+    return exact ? (FusedFn)dtw_svc_kernel<true, 0, 0, 16> : (FusedFn)dtw_svc_kernel<false, 0, 0, 16>;
+}
+
+int launch_fused(wdx_model* m, bool exact, const PredictArgs& pa, int64_t grid_rows, cudaStream_t st) {
+    FusedFn fn = pick_fused(m, exact);
+    const size_t smem = fused_smem_bytes(m, exact, pa.x_is_f32 != 0);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((grid_rows + CTA_THREADS - 1) / CTA_THREADS), (unsigned)pa.n_splits);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (m->timing) {
+        if (m->tev_used == m->tev.size()) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            m->tev.emplace_back(a, b);
+        }
+        e0 = m->tev[m->tev_used].first;
+        e1 = m->tev[m->tev_used].second;
+        m->tev_used++;
+        CUDA_TRY(cudaEventRecord(e0, st));
+    }
+    fn<<<grid, CTA_THREADS, smem, st>>>(m->dev, pa);
+    CUDA_TRY(cudaGetLastError());
+    if (m->timing) CUDA_TRY(cudaEventRecord(e1, st));
+    g_launches++;
+    return WDX_OK;
+}
+
+int launch_finish(wdx_model* m, const FinishArgs& fa, int64_t grid_rows, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((grid_rows + 127) / 128);
+    svc_finish_kernel<<<blocks, 128, 0, st>>>(m->dev, fa);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return WDX_OK;
+}
+
+void choose_splits(const wdx_model* m, int64_t n, int* n_splits, int* sv_per_split) {
+    const int64_t ctas_x = (n + CTA_THREADS - 1) / CTA_THREADS;
+    const int64_t target = (int64_t)m->sm_count * 4 * 2;  // two full waves of 4 CTAs/SM
+    int splits = 1;
+    if (ctas_x < target) splits = (int)std::min<int64_t>(64, (target + ctas_x - 1) / ctas_x);
+    if (m->forced_splits > 0) splits = m->forced_splits;
+    splits = std::max(1, std::min(splits, m->n_sv));
+    int per = (m->n_sv + splits - 1) / splits;
+    splits = (m->n_sv + per - 1) / per;
+    *n_splits = splits;
+    *sv_per_split = per;
+}
+
+// One chunk, everything on the device: Xd [n][L] -> labels/conf/prob/flags (device).
+int predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, int mode, int64_t* labels_d,
+                         double* conf_d, double* prob_d, uint8_t* flags_d, float* dist_d, cudaStream_t st) {
+    int n_splits, per;
+    choose_splits(m, n, &n_splits, &per);
+    const int64_t stride = (n + 31) & ~(int64_t)31;
+    int rc = m->part.reserve((size_t)n_splits * m->n_pairs * stride * sizeof(double));
+    if (rc) return rc;
+    const bool exact_first = (mode == WDX_MODE_EXACT_F64);
+    const bool guarded = (mode == WDX_MODE_FAST_F32_GUARDED);
+
+    PredictArgs pa{};
+    pa.X = Xd;
+    pa.x_is_f32 = x_is_f32;
+    pa.read_idx = nullptr;
+    pa.n_idx = nullptr;
+    pa.n = n;
+    pa.part_stride = stride;
+    pa.part = (double*)m->part.p;
+    pa.dist = dist_d;
+    pa.n_splits = n_splits;
+    pa.sv_per_split = per;
+    rc = launch_fused(m, exact_first, pa, n, st);
+    if (rc) return rc;
+
+    FinishArgs fa{};
+    fa.part = (const double*)m->part.p;
+    fa.part_stride = stride;
+    fa.n_splits = n_splits;
+    fa.sv_per_split = per;
+    fa.n = n;
+    fa.labels = labels_d;
+    fa.conf = conf_d;
+    fa.prob = prob_d;
+    fa.flags = flags_d;
+    fa.guard = m->guard;
+    if (guarded) {
+        rc = m->near_idx.reserve((size_t)n * sizeof(int));
+        if (rc) return rc;
+        rc = m->counters.reserve(64);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(m->counters.p, 0, 64, st));
+        fa.near_idx = (int*)m->near_idx.p;
+        fa.near_count = (int*)m->counters.p;
+    }
+    rc = launch_finish(m, fa, n, st);
+    if (rc) return rc;
+
+    if (guarded) {
+        // Re-run the flagged reads in EXACT_F64.  The count stays on the device:
+        // the grid is sized for the worst case and idle CTAs exit at once.  The
+        // first pass's decision sums have been consumed by the finishing kernel,
+        // so the recompute reuses the same scratch with the same split geometry.
+        const int64_t cap = n;
+        PredictArgs pb = pa;
+        pb.read_idx = (const int*)m->near_idx.p;
+        pb.n_idx = (const int*)m->counters.p;
+        pb.n = cap;
+        pb.dist = nullptr;
+        rc = launch_fused(m, true, pb, cap, st);
+        if (rc) return rc;
+        FinishArgs fb = fa;
+        fb.read_idx = (const int*)m->near_idx.p;
+        fb.n_idx = (const int*)m->counters.p;
+        fb.n = cap;
+        fb.near_idx = nullptr;
+        fb.near_count = nullptr;
+        fb.flag_or = WDX_FLAG_RECOMPUTED;
+        rc = launch_finish(m, fb, cap, st);
+        if (rc) return rc;
+    }
+    return WDX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wdx_last_error(void) { return g_err; }
+const char* wdx_version(void) { return "wdx_b200 0.1 (sm_100a)"; }
+int64_t wdx_kernel_launch_count(void) { return g_launches.load(); }
+
+int wdx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int wdx_model_create(const double* sv, int n_sv, int L, const int32_t* n_sv_class, int k, const double* dual_coef,
+                     const double* rho, const double* probA, const double* probB, const double* thresholds,
+                     const int64_t* label_map, int window, double penalty, double gamma, int pwr_dist, int device,
+                     wdx_model** out) {
+    if (!out) return fail(WDX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!sv || !n_sv_class || !dual_coef || !rho || !probA || !probB || !thresholds || !label_map)
+        return fail(WDX_ERR_INVALID, "NULL model array");
+    if (k < 2 || k > MAXK) return fail(WDX_ERR_INVALID, "k=%d outside [2,%d]", k, MAXK);
+    if (L < 1 || L > MAXL) return fail(WDX_ERR_INVALID, "L=%d outside [1,%d]", L, MAXL);
+    if (n_sv < 1) return fail(WDX_ERR_INVALID, "n_sv=%d", n_sv);
+    if (pwr_dist < 0) return fail(WDX_ERR_INVALID, "pwr_dist=%d", pwr_dist);
+    if (window < 0) return fail(WDX_ERR_INVALID, "window=%d", window);
+    long tot = 0;
+    for (int c = 0; c < k; c++) {
+        if (n_sv_class[c] < 0) return fail(WDX_ERR_INVALID, "negative n_sv_class");
+        tot += n_sv_class[c];
+    }
+    if (tot != n_sv) return fail(WDX_ERR_INVALID, "n_sv_class sums to %ld, n_sv=%d", tot, n_sv);
+    int ndev = wdx_device_count();
+    if (ndev <= 0) return fail(WDX_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(WDX_ERR_INVALID, "device %d of %d", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+
+    wdx_model* m = new (std::nothrow) wdx_model();
+    if (!m) return fail(WDX_ERR_NOMEM, "host allocation failed");
+    m->device = device;
+    m->k = k;
+    m->L = L;
+    m->n_sv = n_sv;
+    m->n_pairs = k * (k - 1) / 2;
+    const int w_eff = (window <= 0 || window > L) ? L : window;
+    m->specialised = (L == 25 && w_eff == 15);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+
+    ModelDev& d = m->dev;
+    d.n_sv = n_sv;
+    d.L = L;
+    d.k = k;
+    d.n_pairs = m->n_pairs;
+    d.ldf = (L + 3) & ~3;
+    d.ldd = (L + 1) & ~1;
+    d.ldc = (k - 1 + 1) & ~1;
+    d.window = w_eff;
+    d.p2 = penalty * penalty;
+    d.gamma = gamma;
+    d.pwr_dist = pwr_dist;
+    d.class_start[0] = 0;
+    for (int c = 0; c < k; c++) d.class_start[c + 1] = d.class_start[c] + n_sv_class[c];
+    for (int c = k + 1; c <= MAXK; c++) d.class_start[c] = n_sv;
+
+    std::vector<float> svf((size_t)n_sv * d.ldf, 0.f);
+    std::vector<double> svd((size_t)n_sv * d.ldd, 0.0);
+    std::vector<double> coef((size_t)n_sv * d.ldc, 0.0);
+    for (int s = 0; s < n_sv; s++) {
+        for (int j = 0; j < L; j++) {
+            svf[(size_t)s * d.ldf + j] = (float)sv[(size_t)s * L + j];
+            svd[(size_t)s * d.ldd + j] = sv[(size_t)s * L + j];
+        }
+        for (int r = 0; r < k - 1; r++) coef[(size_t)s * d.ldc + r] = dual_coef[(size_t)r * n_sv + s];
+    }
+    int rc = WDX_OK;
+    auto bail = [&](int code) {
+        wdx_model_destroy(m);
+        return code;
+    };
+    if ((rc = upload(m, svf, &d.sv_f32))) return bail(rc);
+    if ((rc = upload(m, svd, &d.sv_f64))) return bail(rc);
+    if ((rc = upload(m, coef, &d.coef))) return bail(rc);
+    if ((rc = upload(m, std::vector<double>(rho, rho + m->n_pairs), &d.rho))) return bail(rc);
+    if ((rc = upload(m, std::vector<double>(probA, probA + m->n_pairs), &d.probA))) return bail(rc);
+    if ((rc = upload(m, std::vector<double>(probB, probB + m->n_pairs), &d.probB))) return bail(rc);
+    if ((rc = upload(m, std::vector<double>(thresholds, thresholds + k), &d.thresholds))) return bail(rc);
+    if ((rc = upload(m, std::vector<int64_t>(label_map, label_map + k), &d.label_map))) return bail(rc);
+
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(WDX_ERR_CUDA, "cudaStreamCreate failed"));
+    for (int i = 0; i < 2; i++) {
+        if (cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(WDX_ERR_CUDA, "cudaEventCreate failed"));
+    }
+    if (cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(WDX_ERR_CUDA, "cudaEventCreate failed"));
+    *out = m;
+    return WDX_OK;
+}
+
+void wdx_model_destroy(wdx_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+    for (void* p : m->owned) cudaFree(p);
+    m->part.release();
+    m->part2.release();
+    m->near_idx.release();
+    m->counters.release();
+    for (int i = 0; i < 2; i++) {
+        m->xdev[i].release();
+        m->xpin[i].release();
+        if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+        if (m->ev_free[i]) cudaEventDestroy(m->ev_free[i]);
+    }
+    if (m->ev_done) cudaEventDestroy(m->ev_done);
+    m->lab_dev.release();
+    m->conf_dev.release();
+    m->prob_dev.release();
+    m->flag_dev.release();
+    m->dist_dev.release();
+    m->lab_pin.release();
+    m->conf_pin.release();
+    m->prob_pin.release();
+    m->flag_pin.release();
+    for (auto& e : m->tev) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    delete m;
+}
+
+int wdx_model_set_guard(wdx_model* m, double guard) {
+    if (!m || !(guard >= 0)) return fail(WDX_ERR_INVALID, "bad guard");
+    m->guard = guard;
+    return WDX_OK;
+}
+
+int wdx_model_set_chunk_reads(wdx_model* m, int64_t chunk) {
+    if (!m || chunk < 1) return fail(WDX_ERR_INVALID, "bad chunk");
+    m->chunk_reads = chunk;
+    return WDX_OK;
+}
+
+int wdx_model_set_sv_splits(wdx_model* m, int splits) {
+    if (!m || splits < 0) return fail(WDX_ERR_INVALID, "bad splits");
+    m->forced_splits = splits;
+    return WDX_OK;
+}
+
+int wdx_model_enable_timing(wdx_model* m, int on) {
+    if (!m) return fail(WDX_ERR_INVALID, "NULL model");
+    m->timing = on != 0;
+    return WDX_OK;
+}
+
+int wdx_model_last_kernel_ms(wdx_model* m, double* ms, int* launches) {
+    if (!m || !ms) return fail(WDX_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    CUDA_TRY(cudaSetDevice(m->device));
+    double tot = 0;
+    for (size_t i = 0; i < m->tev_used; i++) {
+        CUDA_TRY(cudaEventSynchronize(m->tev[i].second));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, m->tev[i].first, m->tev[i].second));
+        tot += t;
+    }
+    *ms = tot;
+    if (launches) *launches = (int)m->tev_used;
+    return WDX_OK;
+}
+
+int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, int64_t* labels, double* conf,
+                double* prob, uint8_t* flags, float* dist, void* stream) {
+    if (!m) return fail(WDX_ERR_INVALID, "NULL model");
+    if (n < 0) return fail(WDX_ERR_INVALID, "n=%lld", (long long)n);
+    if (n == 0) return WDX_OK;
+    if (!X || !labels) return fail(WDX_ERR_INVALID, "X and labels are required");
+    if (x_dtype != WDX_F64 && x_dtype != WDX_F32) return fail(WDX_ERR_INVALID, "x_dtype=%d", x_dtype);
+    if (mode < WDX_MODE_EXACT_F64 || mode > WDX_MODE_FAST_F32_GUARDED) return fail(WDX_ERR_INVALID, "mode=%d", mode);
+    std::lock_guard<std::mutex> lk(m->mu);
+    CUDA_TRY(cudaSetDevice(m->device));
+    m->tev_used = 0;
+
+    const int esz = (x_dtype == WDX_F32) ? 4 : 8;
+    const int L = m->L, k = m->k;
+    const bool x_dev = is_device_ptr(X, m->device);
+    const bool lab_dev = is_device_ptr(labels, m->device);
+    const bool conf_devp = conf && is_device_ptr(conf, m->device);
+    const bool prob_devp = prob && is_device_ptr(prob, m->device);
+    const bool flag_devp = flags && is_device_ptr(flags, m->device);
+    const bool dist_devp = dist && is_device_ptr(dist, m->device);
+    const bool any_host = !x_dev || !lab_dev || (conf && !conf_devp) || (prob && !prob_devp) || (flags && !flag_devp) ||
+                          (dist && !dist_devp);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+
+    const int64_t chunk = std::min<int64_t>(n, dist ? std::min<int64_t>(m->chunk_reads, 1 << 16) : m->chunk_reads);
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    int rc;
+    // device-side result buffers for whatever lives on the host
+    if (!lab_dev && (rc = m->lab_dev.reserve((size_t)chunk * 8))) return rc;
+    if (conf && !conf_devp && (rc = m->conf_dev.reserve((size_t)chunk * 8))) return rc;
+    if (prob && !prob_devp && (rc = m->prob_dev.reserve((size_t)chunk * k * 8))) return rc;
+    if (flags && !flag_devp && (rc = m->flag_dev.reserve((size_t)chunk))) return rc;
+    if (dist && !dist_devp && (rc = m->dist_dev.reserve((size_t)chunk * m->n_sv * 4))) return rc;
+    if (!x_dev) {
+        const int nb = n_chunks > 1 ? 2 : 1;
+        for (int b = 0; b < nb; b++) {
+            if ((rc = m->xdev[b].reserve((size_t)chunk * L * esz))) return rc;
+            if ((rc = m->xpin[b].reserve((size_t)chunk * L * esz))) return rc;
+        }
+    }
+
+    // Host-resident input: chunk c+1 is copied (user memory -> pinned -> device
+    // on the copy stream) while chunk c computes.
+    auto stage_in = [&](int64_t c) -> int {
+        const int b = (int)(c & 1);
+        const int64_t r0 = c * chunk, cn = std::min(chunk, n - r0);
+        const size_t bytes = (size_t)cn * L * esz;
+        CUDA_TRY(cudaEventSynchronize(m->ev_free[b]));  // compute on this buffer (2 chunks ago) finished
+        std::memcpy(m->xpin[b].p, (const char*)X + (size_t)r0 * L * esz, bytes);
+        CUDA_TRY(cudaMemcpyAsync(m->xdev[b].p, m->xpin[b].p, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+        CUDA_TRY(cudaEventRecord(m->ev_h2d[b], m->copy_stream));
+        return WDX_OK;
+    };
+    if (!x_dev) {
+        CUDA_TRY(cudaEventRecord(m->ev_free[0], st));
+        CUDA_TRY(cudaEventRecord(m->ev_free[1], st));
+        if ((rc = stage_in(0))) return rc;
+    }
+
+    for (int64_t c = 0; c < n_chunks; c++) {
+        const int64_t r0 = c * chunk, cn = std::min(chunk, n - r0);
+        const void* Xd;
+        if (x_dev) {
+            Xd = (const char*)X + (size_t)r0 * L * esz;
+        } else {
+            Xd = m->xdev[c & 1].p;
+            CUDA_TRY(cudaStreamWaitEvent(st, m->ev_h2d[c & 1], 0));
+        }
+        int64_t* lab_d = lab_dev ? labels + r0 : (int64_t*)m->lab_dev.p;
+        double* conf_d = conf ? (conf_devp ? conf + r0 : (double*)m->conf_dev.p) : nullptr;
+        double* prob_d = prob ? (prob_devp ? prob + (size_t)r0 * k : (double*)m->prob_dev.p) : nullptr;
+        uint8_t* flag_d = flags ? (flag_devp ? flags + r0 : (uint8_t*)m->flag_dev.p) : nullptr;
+        float* dist_d = dist ? (dist_devp ? dist + (size_t)r0 * m->n_sv : (float*)m->dist_dev.p) : nullptr;
+        rc = predict_chunk_device(m, Xd, esz == 4, cn, mode, lab_d, conf_d, prob_d, flag_d, dist_d, st);
+        if (rc) return rc;
+        if (!x_dev) {
+            CUDA_TRY(cudaEventRecord(m->ev_free[c & 1], st));
+            if (c + 1 < n_chunks && (rc = stage_in(c + 1))) return rc;  // overlaps the kernels just enqueued
+        }
+        // results back to host buffers (stream-ordered; small)
+        if (!lab_dev) CUDA_TRY(cudaMemcpyAsync(labels + r0, lab_d, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
+        if (conf && !conf_devp) CUDA_TRY(cudaMemcpyAsync(conf + r0, conf_d, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
+        if (prob && !prob_devp)
+            CUDA_TRY(cudaMemcpyAsync(prob + (size_t)r0 * k, prob_d, (size_t)cn * k * 8, cudaMemcpyDeviceToHost, st));
+        if (flags && !flag_devp) CUDA_TRY(cudaMemcpyAsync(flags + r0, flag_d, (size_t)cn, cudaMemcpyDeviceToHost, st));
+        if (dist && !dist_devp)
+            CUDA_TRY(cudaMemcpyAsync(dist + (size_t)r0 * m->n_sv, dist_d, (size_t)cn * m->n_sv * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (any_host || !stream) CUDA_TRY(cudaStreamSynchronize(st));
+    return WDX_OK;
+}
+
+int wdx_distance_matrix_to(const double* X, int64_t nX, const double* Y, int64_t nY, int L, int window,
+                           double penalty, int mode, void* out, int out_dtype, int device, void* stream) {
+    if (!X || !Y || !out) return fail(WDX_ERR_INVALID, "NULL argument");
+    if (nX < 0 || nY < 0) return fail(WDX_ERR_INVALID, "negative size");
+    if (L < 1 || L > MAXL) return fail(WDX_ERR_INVALID, "L=%d outside [1,%d]", L, MAXL);
+    if (out_dtype != WDX_F32 && out_dtype != WDX_F64) return fail(WDX_ERR_INVALID, "out_dtype=%d", out_dtype);
+    if (mode != WDX_MODE_EXACT_F64 && mode != WDX_MODE_FAST_F32) return fail(WDX_ERR_INVALID, "mode=%d", mode);
+    if (nX == 0 || nY == 0) return WDX_OK;
+    int ndev = wdx_device_count();
+    if (ndev <= 0) return fail(WDX_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(WDX_ERR_INVALID, "device %d of %d", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool xd = is_device_ptr(X, device), yd = is_device_ptr(Y, device), od = is_device_ptr(out, device);
+    const size_t osz = out_dtype == WDX_F32 ? 4 : 8;
+    DevBuf bx, by, bo;
+    int rc = WDX_OK;
+    const double *Xd = X, *Yd = Y;
+    void* Od = out;
+    auto cleanup = [&](int code) {
+        bx.release();
+        by.release();
+        bo.release();
+        return code;
+    };
+    if (!xd) {
+        if ((rc = bx.reserve((size_t)nX * L * 8))) return cleanup(rc);
+        if (cudaMemcpyAsync(bx.p, X, (size_t)nX * L * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return cleanup(fail(WDX_ERR_CUDA, "H2D copy of X failed"));
+        Xd = (const double*)bx.p;
+    }
+    if (!yd) {
+        if ((rc = by.reserve((size_t)nY * L * 8))) return cleanup(rc);
+        if (cudaMemcpyAsync(by.p, Y, (size_t)nY * L * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return cleanup(fail(WDX_ERR_CUDA, "H2D copy of Y failed"));
+        Yd = (const double*)by.p;
+    }
+    if (!od) {
+        if ((rc = bo.reserve((size_t)nX * nY * osz))) return cleanup(rc);
+        Od = bo.p;
+    }
+    const int w_eff = (window <= 0 || window > L) ? L : window;
+    const bool spec = (L == 25 && w_eff == 15);
+    const bool exact = mode == WDX_MODE_EXACT_F64;
+    const int64_t ctas_x = (nX + CTA_THREADS - 1) / CTA_THREADS;
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>((nY + TILE_SV - 1) / TILE_SV, (148 * 8 + ctas_x - 1) / ctas_x));
+    int per = (int)((nY + splits - 1) / splits);
+    per = ((per + TILE_SV - 1) / TILE_SV) * TILE_SV;
+    splits = (int)((nY + per - 1) / per);
+    dim3 grid((unsigned)ctas_x, (unsigned)splits);
+    const size_t smem = (size_t)TILE_SV * L * (exact ? 8 : 4);
+    const double p2 = penalty * penalty;
+#define WDX_LAUNCH_DM(EX, LL, WW, OT)                                                                              \
+    dtw_matrix_kernel<EX, LL, WW, OT><<<grid, CTA_THREADS, smem, st>>>(Xd, nX, Yd, nY, L, w_eff, p2, (OT*)Od, per)
+    if (spec) {
+        if (exact && out_dtype == WDX_F64) WDX_LAUNCH_DM(true, 25, 15, double);
+        else if (exact) WDX_LAUNCH_DM(true, 25, 15, float);
+        else if (out_dtype == WDX_F64) WDX_LAUNCH_DM(false, 25, 15, double);
+        else WDX_LAUNCH_DM(false, 25, 15, float);
+    } else {
+        if (exact && out_dtype == WDX_F64) WDX_LAUNCH_DM(true, 0, 0, double);
+        else if (exact) WDX_LAUNCH_DM(true, 0, 0, float);
+        else if (out_dtype == WDX_F64) WDX_LAUNCH_DM(false, 0, 0, double);
+        else WDX_LAUNCH_DM(false, 0, 0, float);
+    }
+#undef WDX_LAUNCH_DM
+    if (cudaGetLastError() != cudaSuccess) return cleanup(fail(WDX_ERR_CUDA, "dtw_matrix_kernel launch failed"));
+    g_launches++;
+    if (!od && cudaMemcpyAsync(out, Od, (size_t)nX * nY * osz, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return cleanup(fail(WDX_ERR_CUDA, "D2H copy failed"));
+    if (!xd || !yd || !od || !stream) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cleanup(fail(WDX_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e)));
+    }
+    return cleanup(WDX_OK);
+}
+
+}  // extern "C"

@@ -5,8 +5,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
@@ -55,10 +56,3 @@ def golden_predict():
 def golden_fingerprint():
     with np.load(os.path.join(GOLD, "fingerprint_rna004.npz")) as z:
         return {k: z[k] for k in z.files}
-
-
-def synth_fingerprints(sv, n, seed=0, sigma=0.35):
-    """S1 of SURVEY.md §8(d)."""
-    rng = np.random.default_rng(seed)
-    idx = rng.integers(0, sv.shape[0], size=n)
-    return sv[idx] + sigma * rng.standard_normal((n, sv.shape[1]))

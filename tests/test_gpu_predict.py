@@ -10,7 +10,7 @@ import pickle
 import numpy as np
 import pytest
 
-from tests.conftest import synth_fingerprints
+from wdx_testutil import synth_fingerprints
 
 pytestmark = pytest.mark.gpu
 
@@ -71,7 +71,8 @@ def test_distance_matrix_generic_shapes(shape):
     got = distance_matrix(X, Y, w, pen, mode="exact", out_dtype=np.float64)
     assert np.array_equal(got, want)
     fast = distance_matrix(X, Y, w, pen, mode="fast", out_dtype=np.float64)
-    assert np.allclose(fast, want, rtol=FAST_RTOL, atol=1e-12)
+    # float32 rounding of the inputs bounds the absolute error (cancellation when L is tiny)
+    assert np.allclose(fast, want, rtol=FAST_RTOL, atol=2e-6)
 
 
 def test_golden_predict_exact(models, dev_models, golden_predict):

@@ -135,6 +135,9 @@ int64_t wdx_kernel_launch_count(void);
  * with CUDA events on the handle's stream when timing is enabled. */
 int wdx_model_enable_timing(wdx_model* m, int on);
 int wdx_model_last_kernel_ms(wdx_model* m, double* ms, int* launches);
+/* Same, restricted to the launches of one arithmetic (exact != 0: EXACT_F64
+ * launches, e.g. the GUARDED re-run; exact == 0: FAST_F32 launches). */
+int wdx_model_last_kernel_ms_mode(wdx_model* m, int exact, double* ms, int* launches);
 const char* wdx_version(void);
 
 #ifdef __cplusplus

@@ -21,7 +21,7 @@ FLAG_NONFINITE, FLAG_RECOMPUTED = 1, 2
 EXPORTS = [
     "wdx_model_create", "wdx_model_destroy", "wdx_model_set_guard", "wdx_model_set_chunk_reads", "wdx_model_set_sv_splits",
     "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
-    "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_version",
+    "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_model_last_kernel_ms_mode", "wdx_version",
 ]
 
 _lib = None
@@ -75,6 +75,8 @@ def load():
         L.wdx_model_enable_timing.argtypes = [vp, i32]
         L.wdx_model_last_kernel_ms.restype = i32
         L.wdx_model_last_kernel_ms.argtypes = [vp, C.POINTER(f64), C.POINTER(i32)]
+        L.wdx_model_last_kernel_ms_mode.restype = i32
+        L.wdx_model_last_kernel_ms_mode.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(i32)]
         L.wdx_version.restype = C.c_char_p
         if hasattr(L, "wdx_fingerprint"):
             L.wdx_fingerprint.restype = i32

@@ -117,12 +117,14 @@ struct wdx_model {
     std::vector<void*> owned;            // model arrays on the device
     // workspaces (grow-only)
     DevBuf part, part2, near_idx, counters;
-    DevBuf xdev[2], lab_dev, conf_dev, prob_dev, flag_dev, dist_dev;
-    HostBuf xpin[2], lab_pin, conf_pin, prob_pin, flag_pin;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
+    DevBuf xdev[2], lab_dev[2], conf_dev[2], prob_dev[2], flag_dev[2], dist_dev[2];
+    HostBuf xpin[2];
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+                ev_d2h[2] = {nullptr, nullptr};
     // timing of the fused kernel
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;
+    std::vector<char> tev_exact;
     size_t tev_used = 0;
     int64_t chunk_reads = (int64_t)1 << 22;
     int forced_splits = 0;
@@ -178,9 +180,11 @@ int launch_fused(wdx_model* m, bool exact, const PredictArgs& pa, int64_t grid_r
             CUDA_TRY(cudaEventCreate(&a));
             CUDA_TRY(cudaEventCreate(&b));
             m->tev.emplace_back(a, b);
+            m->tev_exact.push_back(0);
         }
         e0 = m->tev[m->tev_used].first;
         e1 = m->tev[m->tev_used].second;
+        m->tev_exact[m->tev_used] = exact ? 1 : 0;
         m->tev_used++;
         CUDA_TRY(cudaEventRecord(e0, st));
     }
@@ -384,11 +388,11 @@ int wdx_model_create(const double* sv, int n_sv, int L, const int32_t* n_sv_clas
         return bail(fail(WDX_ERR_CUDA, "cudaStreamCreate failed"));
     for (int i = 0; i < 2; i++) {
         if (cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
+            cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming) != cudaSuccess)
             return bail(fail(WDX_ERR_CUDA, "cudaEventCreate failed"));
     }
-    if (cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming) != cudaSuccess)
-        return bail(fail(WDX_ERR_CUDA, "cudaEventCreate failed"));
     *out = m;
     return WDX_OK;
 }
@@ -408,17 +412,14 @@ void wdx_model_destroy(wdx_model* m) {
         m->xpin[i].release();
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
         if (m->ev_free[i]) cudaEventDestroy(m->ev_free[i]);
+        if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+        if (m->ev_d2h[i]) cudaEventDestroy(m->ev_d2h[i]);
+        m->lab_dev[i].release();
+        m->conf_dev[i].release();
+        m->prob_dev[i].release();
+        m->flag_dev[i].release();
+        m->dist_dev[i].release();
     }
-    if (m->ev_done) cudaEventDestroy(m->ev_done);
-    m->lab_dev.release();
-    m->conf_dev.release();
-    m->prob_dev.release();
-    m->flag_dev.release();
-    m->dist_dev.release();
-    m->lab_pin.release();
-    m->conf_pin.release();
-    m->prob_pin.release();
-    m->flag_pin.release();
     for (auto& e : m->tev) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -452,20 +453,29 @@ int wdx_model_enable_timing(wdx_model* m, int on) {
     return WDX_OK;
 }
 
-int wdx_model_last_kernel_ms(wdx_model* m, double* ms, int* launches) {
+static int kernel_ms_impl(wdx_model* m, int which, double* ms, int* launches) {
     if (!m || !ms) return fail(WDX_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(m->mu);
     CUDA_TRY(cudaSetDevice(m->device));
     double tot = 0;
+    int cnt = 0;
     for (size_t i = 0; i < m->tev_used; i++) {
+        if (which >= 0 && (int)m->tev_exact[i] != which) continue;
         CUDA_TRY(cudaEventSynchronize(m->tev[i].second));
         float t = 0;
         CUDA_TRY(cudaEventElapsedTime(&t, m->tev[i].first, m->tev[i].second));
         tot += t;
+        cnt++;
     }
     *ms = tot;
-    if (launches) *launches = (int)m->tev_used;
+    if (launches) *launches = cnt;
     return WDX_OK;
+}
+
+int wdx_model_last_kernel_ms(wdx_model* m, double* ms, int* launches) { return kernel_ms_impl(m, -1, ms, launches); }
+
+int wdx_model_last_kernel_ms_mode(wdx_model* m, int exact, double* ms, int* launches) {
+    return kernel_ms_impl(m, exact ? 1 : 0, ms, launches);
 }
 
 int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, int64_t* labels, double* conf,
@@ -482,43 +492,84 @@ int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, i
 
     const int esz = (x_dtype == WDX_F32) ? 4 : 8;
     const int L = m->L, k = m->k;
-    const bool x_dev = is_device_ptr(X, m->device);
-    const bool lab_dev = is_device_ptr(labels, m->device);
-    const bool conf_devp = conf && is_device_ptr(conf, m->device);
-    const bool prob_devp = prob && is_device_ptr(prob, m->device);
-    const bool flag_devp = flags && is_device_ptr(flags, m->device);
-    const bool dist_devp = dist && is_device_ptr(dist, m->device);
-    const bool any_host = !x_dev || !lab_dev || (conf && !conf_devp) || (prob && !prob_devp) || (flags && !flag_devp) ||
+    auto mem_kind = [&](const void* p) -> int {  // 0 pageable host, 1 pinned host, 2 device
+        if (!p) return 0;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 2;
+        if (at.type == cudaMemoryTypeHost) return 1;
+        return 0;
+    };
+    const int x_kind = mem_kind(X);
+    const bool x_dev = x_kind == 2;
+    const bool lab_dev = mem_kind(labels) == 2;
+    const bool conf_devp = conf && mem_kind(conf) == 2;
+    const bool prob_devp = prob && mem_kind(prob) == 2;
+    const bool flag_devp = flags && mem_kind(flags) == 2;
+    const bool dist_devp = dist && mem_kind(dist) == 2;
+    const bool out_host = !lab_dev || (conf && !conf_devp) || (prob && !prob_devp) || (flags && !flag_devp) ||
                           (dist && !dist_devp);
+    const bool any_host = !x_dev || out_host;
     cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
 
-    const int64_t chunk = std::min<int64_t>(n, dist ? std::min<int64_t>(m->chunk_reads, 1 << 16) : m->chunk_reads);
+    int64_t chunk = m->chunk_reads;
+    if (any_host) chunk = std::min<int64_t>(chunk, (int64_t)1 << 20);  // finer pipeline when copies are involved
+    if (dist) chunk = std::min<int64_t>(chunk, (int64_t)1 << 16);
+    chunk = std::min<int64_t>(chunk, n);
     const int64_t n_chunks = (n + chunk - 1) / chunk;
+    const int nb = n_chunks > 1 ? 2 : 1;
     int rc;
-    // device-side result buffers for whatever lives on the host
-    if (!lab_dev && (rc = m->lab_dev.reserve((size_t)chunk * 8))) return rc;
-    if (conf && !conf_devp && (rc = m->conf_dev.reserve((size_t)chunk * 8))) return rc;
-    if (prob && !prob_devp && (rc = m->prob_dev.reserve((size_t)chunk * k * 8))) return rc;
-    if (flags && !flag_devp && (rc = m->flag_dev.reserve((size_t)chunk))) return rc;
-    if (dist && !dist_devp && (rc = m->dist_dev.reserve((size_t)chunk * m->n_sv * 4))) return rc;
-    if (!x_dev) {
-        const int nb = n_chunks > 1 ? 2 : 1;
-        for (int b = 0; b < nb; b++) {
+    // device-side result buffers (double-buffered) for whatever lives on the host
+    for (int b = 0; b < nb; b++) {
+        if (!lab_dev && (rc = m->lab_dev[b].reserve((size_t)chunk * 8))) return rc;
+        if (conf && !conf_devp && (rc = m->conf_dev[b].reserve((size_t)chunk * 8))) return rc;
+        if (prob && !prob_devp && (rc = m->prob_dev[b].reserve((size_t)chunk * k * 8))) return rc;
+        if (flags && !flag_devp && (rc = m->flag_dev[b].reserve((size_t)chunk))) return rc;
+        if (dist && !dist_devp && (rc = m->dist_dev[b].reserve((size_t)chunk * m->n_sv * 4))) return rc;
+        if (!x_dev) {
             if ((rc = m->xdev[b].reserve((size_t)chunk * L * esz))) return rc;
-            if ((rc = m->xpin[b].reserve((size_t)chunk * L * esz))) return rc;
+            if (x_kind == 0 && (rc = m->xpin[b].reserve((size_t)chunk * L * esz))) return rc;
         }
     }
 
-    // Host-resident input: chunk c+1 is copied (user memory -> pinned -> device
-    // on the copy stream) while chunk c computes.
+    // Host-resident input: chunk c+1 goes user memory -> (pinned staging ->) device
+    // on the copy stream while chunk c computes.
     auto stage_in = [&](int64_t c) -> int {
         const int b = (int)(c & 1);
         const int64_t r0 = c * chunk, cn = std::min(chunk, n - r0);
         const size_t bytes = (size_t)cn * L * esz;
-        CUDA_TRY(cudaEventSynchronize(m->ev_free[b]));  // compute on this buffer (2 chunks ago) finished
-        std::memcpy(m->xpin[b].p, (const char*)X + (size_t)r0 * L * esz, bytes);
-        CUDA_TRY(cudaMemcpyAsync(m->xdev[b].p, m->xpin[b].p, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+        const char* src = (const char*)X + (size_t)r0 * L * esz;
+        CUDA_TRY(cudaEventSynchronize(m->ev_free[b]));  // the kernels that read this buffer (2 chunks ago) are done
+        if (x_kind == 0) {
+            std::memcpy(m->xpin[b].p, src, bytes);
+            src = (const char*)m->xpin[b].p;
+        }
+        CUDA_TRY(cudaMemcpyAsync(m->xdev[b].p, src, bytes, cudaMemcpyHostToDevice, m->copy_stream));
         CUDA_TRY(cudaEventRecord(m->ev_h2d[b], m->copy_stream));
+        return WDX_OK;
+    };
+    // Results of chunk c back to the caller's host buffers on the copy stream,
+    // issued after chunk c+1's kernels are already queued.
+    auto drain = [&](int64_t c) -> int {
+        const int b = (int)(c & 1);
+        const int64_t r0 = c * chunk, cn = std::min(chunk, n - r0);
+        CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
+        if (!lab_dev)
+            CUDA_TRY(cudaMemcpyAsync(labels + r0, m->lab_dev[b].p, (size_t)cn * 8, cudaMemcpyDeviceToHost, m->copy_stream));
+        if (conf && !conf_devp)
+            CUDA_TRY(cudaMemcpyAsync(conf + r0, m->conf_dev[b].p, (size_t)cn * 8, cudaMemcpyDeviceToHost, m->copy_stream));
+        if (prob && !prob_devp)
+            CUDA_TRY(cudaMemcpyAsync(prob + (size_t)r0 * k, m->prob_dev[b].p, (size_t)cn * k * 8, cudaMemcpyDeviceToHost,
+                                     m->copy_stream));
+        if (flags && !flag_devp)
+            CUDA_TRY(cudaMemcpyAsync(flags + r0, m->flag_dev[b].p, (size_t)cn, cudaMemcpyDeviceToHost, m->copy_stream));
+        if (dist && !dist_devp)
+            CUDA_TRY(cudaMemcpyAsync(dist + (size_t)r0 * m->n_sv, m->dist_dev[b].p, (size_t)cn * m->n_sv * 4,
+                                     cudaMemcpyDeviceToHost, m->copy_stream));
+        CUDA_TRY(cudaEventRecord(m->ev_d2h[b], m->copy_stream));
         return WDX_OK;
     };
     if (!x_dev) {
@@ -526,35 +577,39 @@ int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, i
         CUDA_TRY(cudaEventRecord(m->ev_free[1], st));
         if ((rc = stage_in(0))) return rc;
     }
+    if (out_host) {
+        CUDA_TRY(cudaEventRecord(m->ev_d2h[0], m->copy_stream));
+        CUDA_TRY(cudaEventRecord(m->ev_d2h[1], m->copy_stream));
+    }
 
     for (int64_t c = 0; c < n_chunks; c++) {
+        const int b = (int)(c & 1);
         const int64_t r0 = c * chunk, cn = std::min(chunk, n - r0);
         const void* Xd;
         if (x_dev) {
             Xd = (const char*)X + (size_t)r0 * L * esz;
         } else {
-            Xd = m->xdev[c & 1].p;
-            CUDA_TRY(cudaStreamWaitEvent(st, m->ev_h2d[c & 1], 0));
+            Xd = m->xdev[b].p;
+            CUDA_TRY(cudaStreamWaitEvent(st, m->ev_h2d[b], 0));
         }
-        int64_t* lab_d = lab_dev ? labels + r0 : (int64_t*)m->lab_dev.p;
-        double* conf_d = conf ? (conf_devp ? conf + r0 : (double*)m->conf_dev.p) : nullptr;
-        double* prob_d = prob ? (prob_devp ? prob + (size_t)r0 * k : (double*)m->prob_dev.p) : nullptr;
-        uint8_t* flag_d = flags ? (flag_devp ? flags + r0 : (uint8_t*)m->flag_dev.p) : nullptr;
-        float* dist_d = dist ? (dist_devp ? dist + (size_t)r0 * m->n_sv : (float*)m->dist_dev.p) : nullptr;
+        if (out_host) CUDA_TRY(cudaStreamWaitEvent(st, m->ev_d2h[b], 0));  // result buffers b were drained
+        int64_t* lab_d = lab_dev ? labels + r0 : (int64_t*)m->lab_dev[b].p;
+        double* conf_d = conf ? (conf_devp ? conf + r0 : (double*)m->conf_dev[b].p) : nullptr;
+        double* prob_d = prob ? (prob_devp ? prob + (size_t)r0 * k : (double*)m->prob_dev[b].p) : nullptr;
+        uint8_t* flag_d = flags ? (flag_devp ? flags + r0 : (uint8_t*)m->flag_dev[b].p) : nullptr;
+        float* dist_d = dist ? (dist_devp ? dist + (size_t)r0 * m->n_sv : (float*)m->dist_dev[b].p) : nullptr;
         rc = predict_chunk_device(m, Xd, esz == 4, cn, mode, lab_d, conf_d, prob_d, flag_d, dist_d, st);
         if (rc) return rc;
+        if (out_host) CUDA_TRY(cudaEventRecord(m->ev_done[b], st));
         if (!x_dev) {
-            CUDA_TRY(cudaEventRecord(m->ev_free[c & 1], st));
+            CUDA_TRY(cudaEventRecord(m->ev_free[b], st));
             if (c + 1 < n_chunks && (rc = stage_in(c + 1))) return rc;  // overlaps the kernels just enqueued
         }
-        // results back to host buffers (stream-ordered; small)
-        if (!lab_dev) CUDA_TRY(cudaMemcpyAsync(labels + r0, lab_d, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
-        if (conf && !conf_devp) CUDA_TRY(cudaMemcpyAsync(conf + r0, conf_d, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
-        if (prob && !prob_devp)
-            CUDA_TRY(cudaMemcpyAsync(prob + (size_t)r0 * k, prob_d, (size_t)cn * k * 8, cudaMemcpyDeviceToHost, st));
-        if (flags && !flag_devp) CUDA_TRY(cudaMemcpyAsync(flags + r0, flag_d, (size_t)cn, cudaMemcpyDeviceToHost, st));
-        if (dist && !dist_devp)
-            CUDA_TRY(cudaMemcpyAsync(dist + (size_t)r0 * m->n_sv, dist_d, (size_t)cn * m->n_sv * 4, cudaMemcpyDeviceToHost, st));
+        if (out_host && c >= 1 && (rc = drain(c - 1))) return rc;
+    }
+    if (out_host) {
+        if ((rc = drain(n_chunks - 1))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
     }
     if (any_host || !stream) CUDA_TRY(cudaStreamSynchronize(st));
     return WDX_OK;

@@ -70,6 +70,12 @@ class DeviceModel:
         _lib.check(_lib.load().wdx_model_last_kernel_ms(self._h, C.byref(ms), C.byref(n)), "wdx_model_last_kernel_ms")
         return ms.value, n.value
 
+    def last_kernel_ms_mode(self, exact: bool) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int()
+        _lib.check(_lib.load().wdx_model_last_kernel_ms_mode(self._h, int(exact), C.byref(ms), C.byref(n)),
+                   "wdx_model_last_kernel_ms_mode")
+        return ms.value, n.value
+
     def predict_raw(self, X, n: int, x_dtype: int, mode: int, labels, conf=None, prob=None, flags=None,
                     dist=None, stream: int = 0) -> None:
         """Pointer-level call: every buffer may be a numpy array, a torch tensor

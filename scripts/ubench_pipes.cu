@@ -1,0 +1,119 @@
+// Instruction-throughput microbenchmarks for the ops of the DTW cell (sm_100a).
+#include <cstdio>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+#define NCH 8
+#define ITERS 2000
+#define BODY_REPEAT 8
+
+#define DEF_KERNEL(NAME, DECL, INIT, BODY, FINI)                                  \
+    __global__ void __launch_bounds__(256) NAME(float* out, float seed) {         \
+        DECL;                                                                     \
+        INIT;                                                                     \
+        for (int it = 0; it < ITERS; it++) {                                      \
+            _Pragma("unroll") for (int r = 0; r < BODY_REPEAT; r++) { BODY; }     \
+        }                                                                         \
+        FINI;                                                                     \
+    }
+
+#define FDECL float a[NCH], b = seed, c = seed * 0.5f
+#define FINIT _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = seed + i + threadIdx.x
+#define FFINI float s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = s
+
+DEF_KERNEL(k_ffma, FDECL, FINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)), FFINI)
+DEF_KERNEL(k_fadd, FDECL, FINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b)), FFINI)
+DEF_KERNEL(k_fmnmx, FDECL, FINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("min.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b)), FFINI)
+DEF_KERNEL(k_fmnmx3, FDECL, FINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)), FFINI)
+DEF_KERNEL(k_imnmx, int a[NCH]; int b = (int)seed; int c = b + 3, _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = b + i + threadIdx.x,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("min.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)),
+           int s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(s + c))
+DEF_KERNEL(k_iadd, int a[NCH]; int b = (int)seed; int c = b + 3, _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = b + i + threadIdx.x,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("add.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)),
+           int s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(s + c))
+
+#define PDECL u64 a[NCH], b, c
+#define PINIT b = __float_as_uint(seed) | ((u64)__float_as_uint(seed * 2) << 32); c = b + 5; _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = b + i + threadIdx.x
+#define PFINI u64 s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s
+DEF_KERNEL(k_ffma2, PDECL, PINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c)), PFINI)
+DEF_KERNEL(k_fadd2, PDECL, PINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b)), PFINI)
+
+// mixes (independent chains so only throughput matters)
+DEF_KERNEL(k_mix_scalar, FDECL; float m[NCH], FINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = a[i] * 2,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) {
+               asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+               asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+               asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(c));
+               asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m[i]) : "f"(b), "f"(c));
+           },
+           FFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
+DEF_KERNEL(k_mix_fma_min3, FDECL; float m[NCH], FINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = a[i] * 2,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) {
+               asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+               asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m[i]) : "f"(b), "f"(c));
+           },
+           FFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
+DEF_KERNEL(k_mix_fma_min2, FDECL; float m[NCH], FINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = a[i] * 2,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) {
+               asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+               asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(b));
+           },
+           FFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
+DEF_KERNEL(k_mix_3fma_min3, FDECL; float m[NCH], FINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = a[i] * 2,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) {
+               asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+               asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(c), "f"(b));
+               asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+               asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m[i]) : "f"(b), "f"(c));
+           },
+           FFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
+DEF_KERNEL(k_mix_x2, PDECL; float m[NCH]; float fb = seed; float fc = seed * 3, PINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = seed * i,
+           _Pragma("unroll") for (int i = 0; i < NCH; i += 2) {
+               asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
+               asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c));
+               asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(c));
+               asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m[i]) : "f"(fb), "f"(fc));
+               asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m[i + 1]) : "f"(fb), "f"(fc));
+           },
+           PFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
+DEF_KERNEL(k_mix_x2_min2, PDECL; float m[NCH]; float fb = seed; float fc = seed * 3, PINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = seed * i,
+           _Pragma("unroll") for (int i = 0; i < NCH; i += 2) {
+               asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
+               asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c));
+               asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(c));
+               asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(fb));
+               asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i + 1]) : "f"(fc));
+           },
+           PFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
+
+template <typename K>
+void run(const char* name, K kern, double instr_per_body, float* out) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = 148 * 4, threads = 256;   // 8 warps/SMSP... 4 CTAs x 8 warps = 32 warps/SM
+    kern<<<blocks, threads>>>(out, 1.5f);
+    cudaEventRecord(e0);
+    kern<<<blocks, threads>>>(out, 1.5f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double winstr = (double)blocks * (threads / 32) * ITERS * BODY_REPEAT * instr_per_body;
+    double per_smsp_per_clk = winstr / (148.0 * 4) / (ms * 1e-3 * 1.965e9);
+    printf("%-18s %7.3f ms  warp-instr/clk/SMSP = %.3f   (%s)\n", name, ms, per_smsp_per_clk, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    float* out; cudaMalloc(&out, 148 * 4 * 256 * 4);
+    run("FFMA", k_ffma, NCH, out);
+    run("FADD", k_fadd, NCH, out);
+    run("FMNMX", k_fmnmx, NCH, out);
+    run("FMNMX3", k_fmnmx3, NCH, out);
+    run("IMNMX", k_imnmx, NCH, out);
+    run("IADD", k_iadd, NCH, out);
+    run("FFMA2", k_ffma2, NCH, out);
+    run("FADD2", k_fadd2, NCH, out);
+    run("mix FADD,FFMA,FADD,MIN3", k_mix_scalar, NCH * 4, out);
+    run("mix FFMA,MIN3", k_mix_fma_min3, NCH * 2, out);
+    run("mix FFMA,MIN2", k_mix_fma_min2, NCH * 2, out);
+    run("mix 3FFMA,MIN3", k_mix_3fma_min3, NCH * 4, out);
+    run("mix x2 (5 per 2 cells)", k_mix_x2, NCH / 2 * 5, out);
+    run("mix x2 min2", k_mix_x2_min2, NCH / 2 * 5, out);
+    return 0;
+}

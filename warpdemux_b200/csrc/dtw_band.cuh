@@ -34,9 +34,38 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// 3-input minimum, selectable implementation (chosen by measurement, see
+// DESIGN.md "min3"): 0 = FMNMX3 (float), 1 = VIMNMX3 on the bit patterns (all DP
+// values are non-negative floats, for which integer order == float order; a NaN
+// pattern compares above +inf and is ignored exactly like fminf ignores it),
+// 2 = two FMNMX, 3 = two VIMNMX.
+template <int MI>
+__device__ __forceinline__ float min3sel(float a, float b, float c) {
+    if constexpr (MI == 0) {
+        return fmin3(a, b, c);
+    } else if constexpr (MI == 1) {
+        return __int_as_float(min(min(__float_as_int(a), __float_as_int(b)), __float_as_int(c)));
+    } else if constexpr (MI == 2) {
+        float t, d;  // volatile: keep ptxas from re-fusing the pair into FMNMX3
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(t) : "f"(b), "f"(c));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(t));
+        return d;
+    } else {
+        int t, d;
+        asm("min.s32 %0, %1, %2;" : "=r"(t) : "r"(__float_as_int(b)), "r"(__float_as_int(c)));
+        asm("min.s32 %0, %1, %2;" : "=r"(d) : "r"(__float_as_int(a)), "r"(t));
+        return __int_as_float(d);
+    }
+}
+template <int MI>
+__device__ __forceinline__ float min2sel(float a, float b) {
+    if constexpr (MI == 1 || MI == 3) return __int_as_float(min(__float_as_int(a), __float_as_int(b)));
+    else return fminf(a, b);
+}
+
 // ---- FAST: float32, FMA, v and v+p2 both kept so each cell is 4 instructions.
 // Returns D[L-1][L-1] (squared-cost sum; caller takes the sqrt).
-template <int L, int W>
+template <int L, int W, int MI = 0>
 __device__ __forceinline__ float dtw_band_f32(const float (&a)[L], const float (&s)[L], const float p2) {
     using B = Band<L, W>;
     float v[L];   // D[i][j]       of the row being overwritten in place
@@ -57,10 +86,10 @@ __device__ __forceinline__ float dtw_band_f32(const float (&a)[L], const float (
                 float old = 0.f;
                 if (has_up) old = v[j];
                 float m;
-                if (has_diag && has_up && has_left) m = fmin3(diag, vp[j], vp[j - 1]);
-                else if (has_diag && has_up) m = fminf(diag, vp[j]);
-                else if (has_diag && has_left) m = fminf(diag, vp[j - 1]);
-                else if (has_up && has_left) m = fminf(vp[j], vp[j - 1]);
+                if (has_diag && has_up && has_left) m = min3sel<MI>(diag, vp[j], vp[j - 1]);
+                else if (has_diag && has_up) m = min2sel<MI>(diag, vp[j]);
+                else if (has_diag && has_left) m = min2sel<MI>(diag, vp[j - 1]);
+                else if (has_up && has_left) m = min2sel<MI>(vp[j], vp[j - 1]);
                 else if (has_diag) m = diag;
                 else if (has_up) m = vp[j];
                 else m = vp[j - 1];

@@ -22,17 +22,19 @@
 #include <stdint.h>
 
 #include "dtw_band.cuh"
+#include "dtw_band_x2.cuh"
 
 namespace wdx {
 
 constexpr int CTA_THREADS = 128;
-constexpr int TILE_SV = 64;
+constexpr int TILE_SV = 32;
 constexpr int MAXK = 16;
 constexpr int MAXL = 64;
 
 struct ModelDev {
     // support vectors, tile-friendly rows (16-byte multiples for TMA bulk copies)
     const float* sv_f32;    // [n_sv][ldf]   ldf = roundup(L,4)
+    const float* sv_x2;     // [n_sv][ldp]   pre-paired rows (s[t], s[t-1]), t = 1..L-1; ldp = roundup(2(L-1),4)
     const double* sv_f64;   // [n_sv][ldd]   ldd = roundup(L,2)
     const double* coef;     // [n_sv][ldc]   coef[s][r] = dual_coef[r][s], ldc = roundup(k-1,2)
     const double* rho;      // [n_pairs]
@@ -41,7 +43,7 @@ struct ModelDev {
     const double* thresholds;  // [k]
     const int64_t* label_map;  // [k]
     int class_start[MAXK + 1];
-    int n_sv, L, k, n_pairs, ldf, ldd, ldc;
+    int n_sv, L, k, n_pairs, ldf, ldd, ldc, ldp;
     int window;
     double p2;      // penalty^2
     double gamma;
@@ -58,6 +60,7 @@ struct PredictArgs {
     double* part;         // [n_splits][n_pairs][part_stride] partial decision sums
     float* dist;          // optional [n][n_sv] float32 distances (debug / secondary seam), or nullptr
     int n_splits, sv_per_split;
+    int acc_smem_offset;  // byte offset of the shared-memory accumulator block (ACCS kernels)
 };
 
 // ---------------------------------------------------------------------------
@@ -133,20 +136,24 @@ __device__ __forceinline__ double kernel_from_dist_f32_exact(float d, float gamm
 //   !EXACT: DTW in float32, decision sums with DFMA
 //   L_, W_: compile-time fingerprint length / window (25 / 15 for every shipped
 //           model); L_ == 0 selects the generic runtime-shape fallback.
-//   KM1   : compile-time bound on k-1 (accumulators in registers)
+//   KM1   : compile-time bound on k-1 (number of running decision sums)
+//   X2    : FAST only — packed f32x2 recurrence (dtw_band_x2.cuh) instead of scalar
+//   MINB  : CTAs per SM the register allocation is bounded for
+//   ACCS  : running decision sums live in shared memory instead of registers
 // grid = (ceil(n / CTA_THREADS), n_splits)
 // ---------------------------------------------------------------------------
-template <bool EXACT, int L_, int W_, int KM1>
-__global__ void __launch_bounds__(CTA_THREADS, EXACT ? 3 : 4)
+template <bool EXACT, int L_, int W_, int KM1, bool X2, int MINB, bool ACCS>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
 dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ PredictArgs a) {
     using T = typename std::conditional<EXACT, double, float>::type;
+    static_assert(!(X2 && (EXACT || L_ == 0)), "packed recurrence is FAST + specialised shape only");
     constexpr bool GENERIC = (L_ == 0);
     constexpr int LR = GENERIC ? MAXL : L_;             // register/local array length
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
     const int L = GENERIC ? m.L : L_;
-    const int ldsv = EXACT ? m.ldd : m.ldf;             // elements per SV row in the tile
+    const int ldsv = EXACT ? m.ldd : (X2 ? m.ldp : m.ldf);  // elements per SV row in the tile
     const int sv_row_bytes = ldsv * (int)sizeof(T);
     const int coef_row_bytes = m.ldc * 8;
     const int tile_sv_bytes = TILE_SV * sv_row_bytes;
@@ -154,6 +161,8 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
     const int stage_bytes = tile_sv_bytes + tile_coef_bytes;   // multiple of 16
     unsigned char* stage0 = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * stage_bytes);
+    // [ACCS] per-thread column of running sums, after the stage/staging area (offset passed by the host)
+    double* acc_s = reinterpret_cast<double*>(smem_raw + a.acc_smem_offset) + threadIdx.x;
 
     const int64_t n_eff = a.n_idx ? (int64_t)(*a.n_idx) : a.n;
     const int64_t cta_first = (int64_t)blockIdx.x * CTA_THREADS;
@@ -169,7 +178,8 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
 
     // ---- fingerprints: coalesced 16-byte loads into shared memory, then each
     // thread lifts its own row into registers.
-    T x[LR];
+    T x[X2 ? 1 : LR];
+    u64 ap[X2 ? (LR + 1) / 2 : 1];
     {
         const int esz = a.x_is_f32 ? 4 : 8;
         const int row_bytes = L * esz;
@@ -195,14 +205,17 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
                 *reinterpret_cast<uint32_t*>(xs + (int64_t)tid * row_bytes + q) = *reinterpret_cast<const uint32_t*>(src + q);
         }
         __syncthreads();
+        auto xin = [&](int j) -> T {
+            if (j >= L || !active) return (T)0;
+            if (a.x_is_f32) return (T) reinterpret_cast<const float*>(xs)[tid * L + j];
+            return (T) reinterpret_cast<const double*>(xs)[tid * L + j];
+        };
+        if constexpr (X2) {
 #pragma unroll
-        for (int j = 0; j < LR; j++) {
-            if (j < L && active) {
-                if (a.x_is_f32) x[j] = (T) reinterpret_cast<const float*>(xs)[tid * L + j];
-                else x[j] = (T) reinterpret_cast<const double*>(xs)[tid * L + j];
-            } else {
-                x[j] = (T)0;
-            }
+            for (int q = 0; q < (LR + 1) / 2; q++) ap[q] = pack2((float)xin(2 * q), (float)xin(2 * q + 1));
+        } else {
+#pragma unroll
+            for (int j = 0; j < LR; j++) x[j] = xin(j);
         }
         __syncthreads();
     }
@@ -222,7 +235,8 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
         unsigned char* st = stage0 + (t & 1) * stage_bytes;
         const uint32_t b_sv = cnt * sv_row_bytes, b_cf = cnt * coef_row_bytes;
         mbar_expect_tx(&bars[t & 1], b_sv + b_cf);
-        const unsigned char* gsv = EXACT ? reinterpret_cast<const unsigned char*>(m.sv_f64) : reinterpret_cast<const unsigned char*>(m.sv_f32);
+        const unsigned char* gsv = EXACT ? reinterpret_cast<const unsigned char*>(m.sv_f64)
+                                         : (X2 ? reinterpret_cast<const unsigned char*>(m.sv_x2) : reinterpret_cast<const unsigned char*>(m.sv_f32));
         tma_load_1d(st, gsv + (size_t)base * sv_row_bytes, b_sv, &bars[t & 1]);
         tma_load_1d(st + tile_sv_bytes, reinterpret_cast<const unsigned char*>(m.coef) + (size_t)base * coef_row_bytes, b_cf, &bars[t & 1]);
     };
@@ -234,9 +248,11 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
     const T p2 = (T)m.p2;
     const float gamma_f = (float)m.gamma;
     const int k = m.k, km1 = k - 1;
-    double acc[KM1];
+    double acc[ACCS ? 1 : KM1];
+    auto acc_get = [&](int r) -> double { if constexpr (ACCS) return acc_s[r * CTA_THREADS]; else return acc[r]; };
+    auto acc_set = [&](int r, double v) { if constexpr (ACCS) acc_s[r * CTA_THREADS] = v; else acc[r] = v; };
 #pragma unroll
-    for (int r = 0; r < KM1; r++) acc[r] = 0.0;
+    for (int r = 0; r < KM1; r++) acc_set(r, 0.0);
 
     // class of the first SV of this split
     int cls = 0;
@@ -252,17 +268,18 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
         if (!active) return;
 #pragma unroll
         for (int r = 0; r < KM1; r++)
-            if (r < km1) part[(size_t)pidx(c, r) * a.part_stride] = acc[r];
+            if (r < km1) part[(size_t)pidx(c, r) * a.part_stride] = acc_get(r);
     };
     auto fetch = [&](int c) {  // resume (or start) the running sums of class c
 #pragma unroll
         for (int r = 0; r < KM1; r++) {
-            acc[r] = 0.0;
+            double v0 = 0.0;
             if (r < km1 && active) {
                 const int o = (r < c) ? r : r + 1;
                 // pair (o,c), o<c, already holds class o's contribution iff class o intersects this split
-                if (o < c && range_touches(m, sv_begin, sv_end, o)) acc[r] = part[(size_t)pidx(c, r) * a.part_stride];
+                if (o < c && range_touches(m, sv_begin, sv_end, o)) v0 = part[(size_t)pidx(c, r) * a.part_stride];
             }
+            acc_set(r, v0);
         }
     };
 
@@ -282,10 +299,20 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
                 fetch(cls);
             }
             // support vector -> registers (broadcast 16-byte shared loads)
-            T s[LR];
             const T* srow = reinterpret_cast<const T*>(st + q * sv_row_bytes);
             T d2;
-            if constexpr (!GENERIC) {
+            if constexpr (X2) {
+                u64 sp[LR];
+                sp[0] = 0;
+#pragma unroll
+                for (int t = 1; t < L_; t += 2) {  // (s[t],s[t-1],s[t+1],s[t]) per 16-byte load
+                    const float4 w = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(srow) + (t - 1) * 2);
+                    sp[t] = pack2(w.x, w.y);
+                    if (t + 1 < L_) sp[t + 1] = pack2(w.z, w.w);
+                }
+                d2 = dtw_band_f32_x2<L_, W_>(ap, sp, p2);
+            } else if constexpr (!GENERIC) {
+                T s[LR];
                 constexpr int VEC = 16 / sizeof(T);
 #pragma unroll
                 for (int j = 0; j < L_; j += VEC) {
@@ -304,6 +331,7 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
                 if constexpr (EXACT) d2 = dtw_band_f64<L_, W_>(x, s, p2);
                 else d2 = dtw_band_f32<L_, W_>(x, s, p2);
             } else {
+                T s[LR];
                 for (int j = 0; j < L; j++) s[j] = srow[j];
                 d2 = dtw_generic<T, MAXL>(x, s, L, m.window, p2);
             }
@@ -321,11 +349,11 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
             for (int r = 0; r < KM1; r += 2) {
                 if (r < km1) {  // ldc is even, so the 16-byte load stays inside the row
                     const double2 c2 = *reinterpret_cast<const double2*>(crow + r);
-                    if constexpr (EXACT) acc[r] = __dadd_rn(acc[r], __dmul_rn(c2.x, Kd));
-                    else acc[r] = __fma_rn(c2.x, Kd, acc[r]);
+                    if constexpr (EXACT) acc_set(r, __dadd_rn(acc_get(r), __dmul_rn(c2.x, Kd)));
+                    else acc_set(r, __fma_rn(c2.x, Kd, acc_get(r)));
                     if (r + 1 < km1) {
-                        if constexpr (EXACT) acc[r + 1] = __dadd_rn(acc[r + 1], __dmul_rn(c2.y, Kd));
-                        else acc[r + 1] = __fma_rn(c2.y, Kd, acc[r + 1]);
+                        if constexpr (EXACT) acc_set(r + 1, __dadd_rn(acc_get(r + 1), __dmul_rn(c2.y, Kd)));
+                        else acc_set(r + 1, __fma_rn(c2.y, Kd, acc_get(r + 1)));
                     }
                 }
             }

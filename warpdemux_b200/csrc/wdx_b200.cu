@@ -10,12 +10,17 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "fused_kernels.cuh"
+
+#ifndef WDX_DEFAULT_FAST_VARIANT
+#define WDX_DEFAULT_FAST_VARIANT 2
+#endif
 
 using namespace wdx;
 
@@ -142,35 +147,74 @@ int upload(wdx_model* m, const std::vector<T>& h, const T** out) {
     return WDX_OK;
 }
 
-size_t fused_smem_bytes(const wdx_model* m, bool exact, bool x_f32) {
-    const size_t sv_row = exact ? (size_t)m->dev.ldd * 8 : (size_t)m->dev.ldf * 4;
+using FusedFn = void (*)(const ModelDev, const PredictArgs);
+
+struct FusedChoice {
+    FusedFn fn;
+    bool x2, accs;
+    int km1_cap;
+};
+
+// FAST-path variants (selected by measurement; WDX_FAST_VARIANT overrides for experiments):
+//   0 scalar recurrence, 4 CTAs/SM, sums in registers
+//   1 packed f32x2,      2 CTAs/SM, sums in registers
+//   2 packed f32x2,      3 CTAs/SM, sums in shared memory
+//   3 scalar recurrence, 5 CTAs/SM, sums in shared memory
+//   4 scalar recurrence, 6 CTAs/SM, sums in shared memory
+int fast_variant() {
+    static int v = [] {
+        const char* e = getenv("WDX_FAST_VARIANT");
+        return e ? atoi(e) : WDX_DEFAULT_FAST_VARIANT;
+    }();
+    return v;
+}
+
+template <bool EXACT, int L_, int W_, bool X2, int MINB, bool ACCS>
+FusedChoice pick_km1(int km1) {
+    FusedFn f;
+    int cap;
+    if (km1 <= 4) { f = dtw_svc_kernel<EXACT, L_, W_, 4, X2, MINB, ACCS>; cap = 4; }
+    else if (km1 <= 6) { f = dtw_svc_kernel<EXACT, L_, W_, 6, X2, MINB, ACCS>; cap = 6; }
+    else if (km1 <= 10) { f = dtw_svc_kernel<EXACT, L_, W_, 10, X2, MINB, ACCS>; cap = 10; }
+    else { f = dtw_svc_kernel<EXACT, L_, W_, 16, X2, MINB, ACCS>; cap = 16; }
+    return FusedChoice{f, X2, ACCS, cap};
+}
+
+FusedChoice pick_fused(const wdx_model* m, bool exact) {
+    const int km1 = m->k - 1;
+    if (!m->specialised) {
+        if (exact) return FusedChoice{dtw_svc_kernel<true, 0, 0, 16, false, 3, false>, false, false, 16};
+        return FusedChoice{dtw_svc_kernel<false, 0, 0, 16, false, 4, false>, false, false, 16};
+    }
+    if (exact) return pick_km1<true, 25, 15, false, 3, false>(km1);
+    switch (fast_variant()) {
+        case 1: return pick_km1<false, 25, 15, true, 2, false>(km1);
+        case 2: return pick_km1<false, 25, 15, true, 3, true>(km1);
+        case 3: return pick_km1<false, 25, 15, false, 5, true>(km1);
+        case 4: return pick_km1<false, 25, 15, false, 6, true>(km1);
+        default: return pick_km1<false, 25, 15, false, 4, false>(km1);
+    }
+}
+
+// dynamic shared memory: [ SV/coef stages x2 + mbarriers | aliased fingerprint staging ][ running sums ]
+size_t fused_smem_bytes(const wdx_model* m, bool exact, bool x_f32, const FusedChoice& ch, int* acc_off) {
+    const size_t sv_row = exact ? (size_t)m->dev.ldd * 8 : (ch.x2 ? (size_t)m->dev.ldp * 4 : (size_t)m->dev.ldf * 4);
     const size_t stage = TILE_SV * (sv_row + (size_t)m->dev.ldc * 8);
     const size_t pipe = 2 * stage + 16;
     const size_t xs = (size_t)CTA_THREADS * m->L * (x_f32 ? 4 : 8);
-    return std::max(pipe, xs);
+    size_t base = (std::max(pipe, xs) + 15) & ~(size_t)15;
+    *acc_off = (int)base;
+    if (ch.accs) base += (size_t)ch.km1_cap * CTA_THREADS * 8;
+    return base;
 }
 
-using FusedFn = void (*)(const ModelDev, const PredictArgs);
-
-template <bool EXACT, int L_, int W_>
-FusedFn pick_km1(int km1) {
-    if (km1 <= 4) return dtw_svc_kernel<EXACT, L_, W_, 4>;
-    if (km1 <= 6) return dtw_svc_kernel<EXACT, L_, W_, 6>;
-    if (km1 <= 8) return dtw_svc_kernel<EXACT, L_, W_, 8>;
-    if (km1 <= 10) return dtw_svc_kernel<EXACT, L_, W_, 10>;
-    if (km1 <= 12) return dtw_svc_kernel<EXACT, L_, W_, 12>;
-    return dtw_svc_kernel<EXACT, L_, W_, 16>;
-}
-
-FusedFn pick_fused(const wdx_model* m, bool exact) {
-    const int km1 = m->k - 1;
-    if (m->specialised) return exact ? pick_km1<true, 25, 15>(km1) : pick_km1<false, 25, 15>(km1);
-    return exact ? (FusedFn)dtw_svc_kernel<true, 0, 0, 16> : (FusedFn)dtw_svc_kernel<false, 0, 0, 16>;
-}
-
-int launch_fused(wdx_model* m, bool exact, const PredictArgs& pa, int64_t grid_rows, cudaStream_t st) {
-    FusedFn fn = pick_fused(m, exact);
-    const size_t smem = fused_smem_bytes(m, exact, pa.x_is_f32 != 0);
+int launch_fused(wdx_model* m, bool exact, const PredictArgs& pa_in, int64_t grid_rows, cudaStream_t st) {
+    const FusedChoice ch = pick_fused(m, exact);
+    FusedFn fn = ch.fn;
+    PredictArgs pa = pa_in;
+    int acc_off = 0;
+    const size_t smem = fused_smem_bytes(m, exact, pa.x_is_f32 != 0, ch, &acc_off);
+    pa.acc_smem_offset = acc_off;
     CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((grid_rows + CTA_THREADS - 1) / CTA_THREADS), (unsigned)pa.n_splits);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -351,6 +395,7 @@ int wdx_model_create(const double* sv, int n_sv, int L, const int32_t* n_sv_clas
     d.ldf = (L + 3) & ~3;
     d.ldd = (L + 1) & ~1;
     d.ldc = (k - 1 + 1) & ~1;
+    d.ldp = (std::max(2 * (L - 1), 4) + 3) & ~3;
     d.window = w_eff;
     d.p2 = penalty * penalty;
     d.gamma = gamma;
@@ -362,7 +407,12 @@ int wdx_model_create(const double* sv, int n_sv, int L, const int32_t* n_sv_clas
     std::vector<float> svf((size_t)n_sv * d.ldf, 0.f);
     std::vector<double> svd((size_t)n_sv * d.ldd, 0.0);
     std::vector<double> coef((size_t)n_sv * d.ldc, 0.0);
+    std::vector<float> svp((size_t)n_sv * d.ldp, 0.f);
     for (int s = 0; s < n_sv; s++) {
+        for (int t = 1; t < L; t++) {  // pre-paired layout of the packed recurrence: (s[t], s[t-1])
+            svp[(size_t)s * d.ldp + 2 * (t - 1)] = (float)sv[(size_t)s * L + t];
+            svp[(size_t)s * d.ldp + 2 * (t - 1) + 1] = (float)sv[(size_t)s * L + t - 1];
+        }
         for (int j = 0; j < L; j++) {
             svf[(size_t)s * d.ldf + j] = (float)sv[(size_t)s * L + j];
             svd[(size_t)s * d.ldd + j] = sv[(size_t)s * L + j];
@@ -376,6 +426,7 @@ int wdx_model_create(const double* sv, int n_sv, int L, const int32_t* n_sv_clas
     };
     if ((rc = upload(m, svf, &d.sv_f32))) return bail(rc);
     if ((rc = upload(m, svd, &d.sv_f64))) return bail(rc);
+    if ((rc = upload(m, svp, &d.sv_x2))) return bail(rc);
     if ((rc = upload(m, coef, &d.coef))) return bail(rc);
     if ((rc = upload(m, std::vector<double>(rho, rho + m->n_pairs), &d.rho))) return bail(rc);
     if ((rc = upload(m, std::vector<double>(probA, probA + m->n_pairs), &d.probA))) return bail(rc);

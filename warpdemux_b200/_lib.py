@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libwdx_b200.so")
 WDX_F64, WDX_F32 = 0, 1
 MODE_EXACT_F64, MODE_FAST_F32, MODE_FAST_F32_GUARDED = 0, 1, 2
 MODES = {"exact": MODE_EXACT_F64, "fast": MODE_FAST_F32, "guarded": MODE_FAST_F32_GUARDED}
-FLAG_NONFINITE, FLAG_RECOMPUTED = 1, 2
+FLAG_NONFINITE, FLAG_RECOMPUTED, FLAG_GUARD_OVERFLOW = 1, 2, 4
 
 # every symbol include/wdx_b200.h declares
 EXPORTS = [

@@ -164,7 +164,7 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
     // [ACCS] per-thread column of running sums, after the stage/staging area (offset passed by the host)
     double* acc_s = reinterpret_cast<double*>(smem_raw + a.acc_smem_offset) + threadIdx.x;
 
-    const int64_t n_eff = a.n_idx ? (int64_t)(*a.n_idx) : a.n;
+    const int64_t n_eff = a.n_idx ? min((int64_t)(*a.n_idx), a.n) : a.n;
     const int64_t cta_first = (int64_t)blockIdx.x * CTA_THREADS;
     if (cta_first >= n_eff) return;                     // whole CTA idle (uniform)
     const int64_t slot = cta_first + tid;               // position in this launch
@@ -383,13 +383,14 @@ struct FinishArgs {
     uint8_t* flags;        // or nullptr
     // GUARDED: collect reads close to a decision boundary
     int* near_idx;         // or nullptr
-    int* near_count;
+    int* near_count;       // [0] = list length (clamped by the consumer), [1] = reads that did not fit
+    int near_cap;
     double guard;
     uint8_t flag_or;       // bits OR-ed into flags (WDX_FLAG_RECOMPUTED on the exact re-run)
 };
 
 __global__ void __launch_bounds__(128) svc_finish_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ FinishArgs a) {
-    const int64_t n_eff = a.n_idx ? (int64_t)(*a.n_idx) : a.n;
+    const int64_t n_eff = a.n_idx ? min((int64_t)(*a.n_idx), a.n) : a.n;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_eff) return;
     const int64_t row = a.read_idx ? (int64_t)a.read_idx[slot] : slot;
@@ -477,7 +478,12 @@ __global__ void __launch_bounds__(128) svc_finish_kernel(const __grid_constant__
         const bool near = (fabs(conf - thr) < a.guard) || (conf < a.guard);
         if (near) {
             const int pos = atomicAdd(a.near_count, 1);
-            a.near_idx[pos] = (int)row;
+            if (pos < a.near_cap) {
+                a.near_idx[pos] = (int)row;
+            } else {  // list full: keep the FAST result, tell the caller
+                atomicAdd(a.near_count + 1, 1);
+                if (a.flags) a.flags[row] |= 4;  // WDX_FLAG_GUARD_OVERFLOW
+            }
         }
     }
 }

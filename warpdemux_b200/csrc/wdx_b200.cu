@@ -115,7 +115,7 @@ struct wdx_model {
     int sm_count = 148;
     int k = 0, L = 0, n_sv = 0, n_pairs = 0;
     bool specialised = false;  // L == 25 && window == 15
-    double guard = 2e-3;
+    double guard = 5e-5;
     std::mutex mu;
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
@@ -296,32 +296,48 @@ int predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, 
     fa.prob = prob_d;
     fa.flags = flags_d;
     fa.guard = m->guard;
+    // GUARDED: reads close to a decision boundary are listed by the finishing
+    // kernel (count stays on the device) and re-run in EXACT_F64.  The list is
+    // capped at max(4096, n/64) entries; the re-run is sized for that worst case
+    // (idle CTAs exit at once) and cut into SV ranges so that a handful of reads
+    // still fills the GPU.  Reads that do not fit keep their FAST result and get
+    // WDX_FLAG_GUARD_OVERFLOW.
+    const int64_t cap = std::min<int64_t>(n, std::max<int64_t>(4096, n / 64));
     if (guarded) {
-        rc = m->near_idx.reserve((size_t)n * sizeof(int));
+        rc = m->near_idx.reserve((size_t)cap * sizeof(int));
         if (rc) return rc;
         rc = m->counters.reserve(64);
         if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(m->counters.p, 0, 64, st));
         fa.near_idx = (int*)m->near_idx.p;
         fa.near_count = (int*)m->counters.p;
+        fa.near_cap = (int)cap;
     }
     rc = launch_finish(m, fa, n, st);
     if (rc) return rc;
 
     if (guarded) {
-        // Re-run the flagged reads in EXACT_F64.  The count stays on the device:
-        // the grid is sized for the worst case and idle CTAs exit at once.  The
-        // first pass's decision sums have been consumed by the finishing kernel,
-        // so the recompute reuses the same scratch with the same split geometry.
-        const int64_t cap = n;
+        int s2, per2;
+        choose_splits(m, std::max<int64_t>(1, cap / 16), &s2, &per2);  // expect the list to be mostly empty
+        const int64_t stride2 = (cap + 31) & ~(int64_t)31;
+        rc = m->part2.reserve((size_t)s2 * m->n_pairs * stride2 * sizeof(double));
+        if (rc) return rc;
         PredictArgs pb = pa;
         pb.read_idx = (const int*)m->near_idx.p;
         pb.n_idx = (const int*)m->counters.p;
         pb.n = cap;
         pb.dist = nullptr;
+        pb.part = (double*)m->part2.p;
+        pb.part_stride = stride2;
+        pb.n_splits = s2;
+        pb.sv_per_split = per2;
         rc = launch_fused(m, true, pb, cap, st);
         if (rc) return rc;
         FinishArgs fb = fa;
+        fb.part = (const double*)m->part2.p;
+        fb.part_stride = stride2;
+        fb.n_splits = s2;
+        fb.sv_per_split = per2;
         fb.read_idx = (const int*)m->near_idx.p;
         fb.n_idx = (const int*)m->counters.p;
         fb.n = cap;
@@ -567,7 +583,7 @@ int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, i
     cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
 
     int64_t chunk = m->chunk_reads;
-    if (any_host) chunk = std::min<int64_t>(chunk, (int64_t)1 << 20);  // finer pipeline when copies are involved
+    if (any_host) chunk = std::min<int64_t>(chunk, (int64_t)1 << 21);  // finer pipeline when copies are involved
     if (dist) chunk = std::min<int64_t>(chunk, (int64_t)1 << 16);
     chunk = std::min<int64_t>(chunk, n);
     const int64_t n_chunks = (n + chunk - 1) / chunk;

@@ -102,6 +102,16 @@ class DeviceModel:
         dist = np.empty((n, self.params.n_sv), dtype=np.float32) if want_dist else None
         if n:
             self.predict_raw(X, n, xd, _lib.MODES[mode], labels, conf, prob, flags, dist)
+            over = np.flatnonzero(flags & _lib.FLAG_GUARD_OVERFLOW)
+            if over.size:
+                # GUARDED: the device-side list of boundary reads was full; finish the
+                # guarantee here by re-running exactly those reads in EXACT_F64.
+                Xo = np.ascontiguousarray(X[over])
+                lo, co = np.empty(over.size, np.int64), np.empty(over.size, np.float64)
+                po, fo = np.empty((over.size, k), np.float64), np.zeros(over.size, np.uint8)
+                self.predict_raw(Xo, over.size, xd, _lib.MODE_EXACT_F64, lo, co, po, fo, None)
+                labels[over], conf[over], prob[over] = lo, co, po
+                flags[over] = fo | _lib.FLAG_RECOMPUTED
         if want_dist:
             return labels, prob, conf, flags, dist
         return labels, prob, conf, flags

@@ -1,0 +1,569 @@
+// fingerprint_kernel.cuh — barcode fingerprint extraction, one CTA per read (sm_100a).
+//
+// Restates, for the configuration every shipped DTW-SVM model uses
+// (rna004_130bps@v1.0.toml), the reference's per-read Python/Cython chain
+//   detect_results_to_fpt                       warpdemux/sig_proc.py:394-605
+//     extract_adapter                           sig_proc.py:382-391
+//     nanmedian / MAD winsorisation (float32)   sig_proc.py:421-431
+//     segment_signal                            sig_proc.py:201-254
+//       c_windowed_t_test (float64)             segmentation/_c_segmentation.pyx:124-161
+//       scipy find_peaks(distance=...)          sig_proc.py:183  (local maxima + greedy distance suppression)
+//       top num_events peaks by score, sorted   sig_proc.py:188-198
+//       c_new_means (float64)                   _c_segmentation.pyx:41-53
+//     normalize(..., "mean") (numpy pairwise)   sig_proc.py:99-111, 546-552
+//     six adapter statistics                    sig_proc.py:562-567
+//     keep the last barcode_num_events          sig_proc.py:569-594
+// as ONE kernel: the adapter slice is read from HBM exactly once (coalesced)
+// into shared memory and everything else happens on-chip; 200 B of fingerprint
+// (+ optional dwell times / statistics) go back.  HBM-bound by construction:
+// algorithmic bytes per read = 4 * n_adapter in + 8 * barcode_num_events out.
+//
+// Exactness: every float operation is issued in the reference's order and
+// precision (float32 for the winsorisation, float64 for scores and means; this
+// TU is compiled with -fmad=false), so change points — integer work — are
+// identical and the float64 outputs are bit-identical to the CPU chain.
+// The sequential pieces are replaced by order-independent equivalents:
+//   * medians: exact radix selection on order-preserving integer keys;
+//   * find_peaks distance suppression (highest first, sequential): fixed point of
+//     "a peak stays iff no STAYING higher peak lies within distance" — unique, and
+//     equal to the greedy result, for any total priority order;
+//   * top-k by score: radix selection of the k-th largest score.
+// Ties between EQUAL scores are broken towards the higher index (what a stable
+// argsort would do); numpy's default argsort leaves them unspecified.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wdx {
+
+constexpr int FP_THREADS = 256;
+constexpr int FP_WARPS = FP_THREADS / 32;
+constexpr int FP_MAX_EVENTS = 254;   // num_events bound (cpts has num_events + 2 entries)
+constexpr int FP_MAX_LEN = 16384;    // longest adapter slice a CTA can hold in shared memory
+
+enum { FP_OK = 0, FP_FAIL_SEGMENTATION = 1, FP_FAIL_DETECT = 2, FP_FAIL_NORMALIZE = 3, FP_FAIL_TOO_LONG = 4 };
+
+struct FpConfig {
+    int padding;             // sig_extract.padding
+    float outlier_thresh;    // core.sig_norm_outlier_thresh (numpy 2: weak Python float * float32 -> float32)
+    int min_obs_per_base;    // segmentation.min_obs_per_base
+    int running_stat_width;  // segmentation.running_stat_width
+    int num_events;          // segmentation.num_events
+    int barcode_num_events;  // segmentation.barcode_num_events
+};
+
+struct FpArgs {
+    const float* signals;       // [n][stride]
+    float* signals_mut;         // == signals when the winsorised slice is to be written back, else nullptr
+    int64_t stride;
+    const int32_t* sig_len;     // [n] valid samples per row, or nullptr (trailing NaN padding is detected)
+    const int64_t* adapter_start;
+    const int64_t* adapter_end;
+    const uint8_t* detect_ok;   // [n] DetectResults.success, or nullptr (all true)
+    int64_t n;
+    int cap;                    // samples of shared memory per CTA
+    double* fpt;                // [n][barcode_num_events]
+    int64_t* dwell;             // [n][barcode_num_events] or nullptr
+    double* stats;              // [n][6] or nullptr
+    int32_t* status;            // [n]
+};
+
+// ---- order-preserving keys ---------------------------------------------------
+__device__ __forceinline__ uint32_t f32_key(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unkey(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---- block helpers -------------------------------------------------------------
+struct FpScratch {
+    uint32_t hist[256];
+    uint32_t warp_tmp[FP_WARPS];
+    uint32_t sel_prefix;   // radix select: key prefix found so far
+    uint32_t sel_k;        // radix select: rank still to resolve inside the prefix
+    unsigned long long sel_prefix64;
+    int flag;
+    int first_nan;
+    int n_kept;
+};
+
+// Exclusive prefix sum of one value per thread over the CTA; returns the exclusive
+// prefix, *total receives the CTA sum.  Contains __syncthreads.
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, FpScratch& s, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // warp_tmp free
+    if (lane == 31) s.warp_tmp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < FP_WARPS; w++) {
+        const uint32_t t = s.warp_tmp[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+// Histogram add with warp aggregation (the top bytes of signal samples are
+// nearly identical, so naive shared atomics would serialise).
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, bool valid) {
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned peers = __match_any_sync(act, bin);
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+
+// k-th smallest (0-based) of key(i), i in [0,n), by 4 passes of 8-bit radix
+// selection.  KEY is a functor int -> uint32_t.  All threads get the result.
+template <typename KEY>
+__device__ uint32_t block_select_u32(int n, uint32_t k, KEY key, FpScratch& s) {
+    uint32_t prefix = 0, mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        __syncthreads();
+        s.hist[threadIdx.x] = 0;  // FP_THREADS == 256
+        __syncthreads();
+        const int n_round = (n + 31) & ~31;  // keep whole warps in the loop for the ballot
+        for (int i = threadIdx.x; i < n_round; i += FP_THREADS) {
+            uint32_t kv = 0;
+            bool ok = false;
+            if (i < n) {
+                kv = key(i);
+                ok = (kv & mask) == prefix;
+            }
+            hist_add(s.hist, (kv >> shift) & 255u, ok);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // warp 0 scans the 256 bins (8 per lane)
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                c[q] = s.hist[threadIdx.x * 8 + q];
+                sum += c[q];
+            }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += t;
+            }
+            uint32_t run = inc - sum;  // elements in lower bins
+            if (k >= run && k < inc) {  // exactly one lane
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (k >= run && k < run + c[q]) {
+                        s.sel_prefix = prefix | ((uint32_t)(threadIdx.x * 8 + q) << shift);
+                        s.sel_k = k - run;
+                    }
+                    run += c[q];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = s.sel_prefix;
+        k = s.sel_k;
+        mask |= 255u << shift;
+    }
+    return prefix;
+}
+
+// numpy median of n float32 values given through KEY (np.median / np.nanmedian on
+// a NaN-free 1-D float32 array): middle element, or fl32(fl32(a+b)/2) for even n.
+template <typename KEY>
+__device__ float block_median_f32(int n, KEY key, FpScratch& s) {
+    const uint32_t k_lo = (uint32_t)((n - 1) / 2);
+    const uint32_t key_lo = block_select_u32(n, k_lo, key, s);
+    const float v_lo = f32_unkey(key_lo);
+    if (n & 1) return v_lo;
+    // the next order statistic: v_lo again if enough copies, else the smallest key above it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.hist[0] = 0;            // count(key <= key_lo)
+        s.hist[1] = 0xffffffffu;  // min key > key_lo
+    }
+    __syncthreads();
+    uint32_t cnt = 0, mn = 0xffffffffu;
+    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
+        const uint32_t kv = key(i);
+        if (kv <= key_lo) cnt++;
+        else mn = min(mn, kv);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s.hist[0], cnt);
+        atomicMin(&s.hist[1], mn);
+    }
+    __syncthreads();
+    const float v_hi = (s.hist[0] >= k_lo + 2) ? v_lo : f32_unkey(s.hist[1]);
+    return __fdiv_rn(__fadd_rn(v_lo, v_hi), 2.0f);  // np.mean of two float32: float32 add, then /2
+}
+
+// numpy's pairwise summation for n <= 128 contiguous float64 (np.add.reduce):
+// 8 strided accumulators, fixed combination tree, sequential tail.
+template <typename F>
+__device__ double np_pairwise_sum(int n, F at) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r = __dadd_rn(r, at(i));
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = at(j);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], at(i + j));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; i++) res = __dadd_rn(res, at(i));
+    return res;
+}
+
+// Python round() of a non-negative double: round half to even.
+__device__ __forceinline__ int py_round(double x) { return (int)rint(x); }
+
+// Middle element (rank (n-1)/2, n odd) or mean of the two middle elements of
+// v[0..n) (n <= 256), by rank counting; the CTA cooperates, result in *out.
+__device__ void small_median(const double* v, int n, double* out, double* tmp2) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < n) {
+        const double x = v[t];
+        int rank = 0;
+        for (int r = 0; r < n; r++) {
+            const double y = v[r];
+            rank += (y < x) || (y == x && r < t);
+        }
+        if (rank == (n - 1) / 2) tmp2[0] = x;
+        if (rank == n / 2) tmp2[1] = x;
+    }
+    __syncthreads();
+    if (t == 0) *out = (n & 1) ? tmp2[0] : __ddiv_rn(__dadd_rn(tmp2[0], tmp2[1]), 2.0);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_constant__ FpConfig c,
+                                                                   const __grid_constant__ FpArgs a) {
+    extern __shared__ __align__(16) unsigned char fp_smem[];
+    const int cap = a.cap;
+    double* score = reinterpret_cast<double*>(fp_smem);                       // [cap]
+    float* sig = reinterpret_cast<float*>(fp_smem + (size_t)cap * 8);         // [cap]
+    uint16_t* kp = reinterpret_cast<uint16_t*>(fp_smem + (size_t)cap * 12);   // [cap/2 + 8] kept peak positions
+    uint8_t* state = fp_smem + (size_t)cap * 12 + ((size_t)(cap / 2 + 8) * 2);  // [cap]
+    __shared__ FpScratch s;
+    __shared__ int cpts[FP_MAX_EVENTS + 2];
+    __shared__ double ev[FP_MAX_EVENTS + 2];   // event means, later normalised
+    __shared__ double dv[FP_MAX_EVENTS + 2];   // scratch for the statistics
+    __shared__ double red[8];
+
+    const int tid = threadIdx.x;
+    const int64_t read = blockIdx.x;
+    if (read >= a.n) return;
+    const int nb = c.barcode_num_events;
+    double* fpt_out = a.fpt + read * nb;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    auto fail = [&](int code) {  // whole CTA calls this (uniform)
+        for (int q = tid; q < nb; q += FP_THREADS) {
+            fpt_out[q] = qnan;
+            if (a.dwell) a.dwell[read * nb + q] = 0;
+        }
+        if (a.stats && tid < 6) a.stats[read * 6 + tid] = qnan;
+        if (tid == 0) a.status[read] = code;
+    };
+
+    if (a.detect_ok && !a.detect_ok[read]) {  // sig_proc.py:400-407
+        fail(FP_FAIL_DETECT);
+        return;
+    }
+
+    // ---- extract_adapter (sig_proc.py:382-391) --------------------------------
+    const int64_t len_row = a.sig_len ? (int64_t)a.sig_len[read] : a.stride;
+    int64_t start = a.adapter_start[read] - c.padding;
+    if (start < 0) start = 0;
+    int64_t stop = a.adapter_end[read] + c.padding;
+    if (stop > len_row) stop = len_row;
+    int64_t n64 = stop - start;
+    if (n64 < 0) n64 = 0;
+    if (n64 > cap) {
+        fail(FP_FAIL_TOO_LONG);
+        return;
+    }
+    int n = (int)n64;
+    const float* src = a.signals + read * a.stride + start;
+    if (tid == 0) s.first_nan = n;
+    __syncthreads();
+    for (int i = tid; i < n; i += FP_THREADS) {  // the one HBM read of the slice, coalesced
+        const float x = __ldg(src + i);
+        sig[i] = x;
+        if (x != x) atomicMin(&s.first_nan, i);
+    }
+    __syncthreads();
+    n = min(n, s.first_nan);  // NaN padding of the minibatch row ends the signal (file_proc.py:333-354)
+
+    // ---- segmentation parameters (sig_proc.py:526-533; Python round = half to even)
+    const int m_obs = min(c.min_obs_per_base, py_round((double)n / (double)c.num_events / 2.0));
+    const int w = min(c.running_stat_width, py_round((double)n / (double)c.num_events));
+    const int nc = n - 2 * w;  // number of t-test positions
+    if (m_obs < 1 || w < 1 || nc < 3) {  // find_peaks(distance < 1) raises -> the reference reports a failed read
+        fail(FP_FAIL_SEGMENTATION);
+        return;
+    }
+
+    // ---- winsorise at med +- thresh * MAD, float32 (sig_proc.py:421-431) --------
+    const float med = block_median_f32(n, [&](int i) { return f32_key(sig[i]); }, s);
+    const float mad = block_median_f32(n, [&](int i) { return f32_key(fabsf(__fsub_rn(sig[i], med))); }, s);
+    const float tm = __fmul_rn(c.outlier_thresh, mad);
+    const float lo = __fsub_rn(med, tm), hi = __fadd_rn(med, tm);
+    __syncthreads();
+    for (int i = tid; i < n; i += FP_THREADS) {
+        float x = sig[i];
+        x = (x < lo) ? lo : x;  // np.clip = min(max(x, lo), hi)
+        x = (x > hi) ? hi : x;
+        sig[i] = x;
+        if (a.signals_mut) a.signals_mut[read * a.stride + start + i] = x;  // the reference clips its view in place
+    }
+    __syncthreads();
+
+    // ---- c_windowed_t_test (_c_segmentation.pyx:124-161), float64, reference order
+    const double wd = (double)w;
+    for (int pos = tid; pos < nc; pos += FP_THREADS) {
+        double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;
+        for (int i = 0; i < w; i++) m1 = __dadd_rn(m1, (double)sig[pos + i]);
+        m1 = __ddiv_rn(m1, wd);
+        for (int i = 0; i < w; i++) m2 = __dadd_rn(m2, (double)sig[pos + w + i]);
+        m2 = __ddiv_rn(m2, wd);
+        for (int i = 0; i < w; i++) {
+            const double pd = __dsub_rn((double)sig[pos + i], m1);
+            var1 = __dadd_rn(var1, __dmul_rn(pd, pd));
+        }
+        for (int i = 0; i < w; i++) {
+            const double pd = __dsub_rn((double)sig[pos + w + i], m2);
+            var2 = __dadd_rn(var2, __dmul_rn(pd, pd));
+        }
+        const double vs = __dadd_rn(var1, var2);
+        double sc;
+        if (vs == 0.0) sc = 0.0;
+        else if (m1 > m2) sc = __ddiv_rn(__dsub_rn(m1, m2), __dsqrt_rn(vs));
+        else sc = __ddiv_rn(__dsub_rn(m2, m1), __dsqrt_rn(vs));
+        score[pos] = sc;
+        state[pos] = 0;
+    }
+    __syncthreads();
+
+    // ---- scipy _local_maxima_1d: strict maxima, plateaus -> midpoint --------------
+    for (int i = tid + 1; i < nc - 1; i += FP_THREADS) {
+        const double x = score[i];
+        if (score[i - 1] < x) {
+            int ahead = i + 1;
+            while (ahead < nc - 1 && score[ahead] == x) ahead++;
+            if (score[ahead] < x) state[(i + ahead - 1) >> 1] = 1;  // 1 = peak, undecided
+        }
+    }
+    __syncthreads();
+
+    // ---- scipy _select_by_peak_distance as a fixed point -------------------------
+    // states: 0 none, 1 undecided, 2 kept, 3 removed.  Priority = (score, index).
+    if (m_obs > 1) {
+        for (;;) {
+            int undecided = 0;
+            // phase 1: decide from the current states (low nibble); the verdict is parked in the
+            // high nibble of the peak's own byte, which no other thread interprets
+            for (int p = tid; p < nc; p += FP_THREADS) {
+                if ((state[p] & 15) != 1) continue;
+                const double x = score[p];
+                bool killed = false, blocked = false;
+                const int q0 = max(0, p - (m_obs - 1)), q1 = min(nc - 1, p + (m_obs - 1));
+                for (int q = q0; q <= q1; q++) {
+                    const int st = state[q] & 15;
+                    if (q == p || st == 0 || st == 3) continue;
+                    const double y = score[q];
+                    const bool higher = (y > x) || (y == x && q > p);
+                    if (!higher) continue;
+                    if (st == 2) killed = true;
+                    else blocked = true;  // an undecided higher peak
+                }
+                const int ns = killed ? 3 : (blocked ? 1 : 2);
+                if (ns == 1) undecided = 1;
+                state[p] = (uint8_t)(1 | (ns << 4));
+            }
+            const int any = __syncthreads_or(undecided);
+            // phase 2: publish
+            for (int p = tid; p < nc; p += FP_THREADS)
+                if (state[p] >> 4) state[p] = state[p] >> 4;
+            __syncthreads();
+            if (!any) break;
+        }
+    } else {
+        for (int p = tid; p < nc; p += FP_THREADS)
+            if (state[p] == 1) state[p] = 2;
+        __syncthreads();
+    }
+
+    // ---- ordered compaction of the kept peaks -------------------------------------
+    const int chunk = (nc + FP_THREADS - 1) / FP_THREADS;
+    const int p_begin = min(nc, tid * chunk), p_end = min(nc, p_begin + chunk);
+    uint32_t my = 0;
+    for (int p = p_begin; p < p_end; p++) my += (state[p] == 2);
+    uint32_t total = 0;
+    uint32_t off = block_exscan(my, s, &total);
+    for (int p = p_begin; p < p_end; p++)
+        if (state[p] == 2) kp[off++] = (uint16_t)p;
+    __syncthreads();
+    const int P = (int)total;
+    if (P < c.num_events) {  // sig_proc.py:185-186 -> "event segmentation failed"
+        fail(FP_FAIL_SEGMENTATION);
+        return;
+    }
+
+    // ---- the num_events highest scores (sig_proc.py:188): radix-select the threshold
+    // scores are >= 0, so their bit patterns order like the values
+    unsigned long long thr_key;
+    {
+        unsigned long long prefix = 0, mask = 0;
+        uint32_t k = (uint32_t)c.num_events - 1;  // 0-based rank from the top
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            __syncthreads();
+            s.hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < P; i += FP_THREADS) {
+                const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
+                if ((kv & mask) == prefix) atomicAdd(&s.hist[(uint32_t)(kv >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0;
+                int b = 255;
+                for (; b > 0; b--) {
+                    if (k < run + s.hist[b]) break;
+                    run += s.hist[b];
+                }
+                s.sel_prefix64 = prefix | ((unsigned long long)b << shift);
+                s.sel_k = k - run;
+            }
+            __syncthreads();
+            prefix = s.sel_prefix64;
+            k = s.sel_k;
+            mask |= 255ull << shift;
+        }
+        thr_key = prefix;
+        // k = how many elements EQUAL to the threshold rank above the selected one, i.e.
+        // (k + 1) of the ties are taken; ties -> the higher indices
+    }
+    const uint32_t ties_needed = s.sel_k + 1;
+    __syncthreads();
+    // mark the selection in `state` (4 = selected), then compact in order
+    {
+        const int pchunk = (P + FP_THREADS - 1) / FP_THREADS;
+        const int i0 = min(P, tid * pchunk), i1 = min(P, i0 + pchunk);
+        // ties: count the ties at higher list index than each tie (only needed if more ties than wanted)
+        uint32_t my_ties = 0;
+        for (int i = i0; i < i1; i++)
+            my_ties += ((unsigned long long)__double_as_longlong(score[kp[i]]) == thr_key);
+        uint32_t tot_ties = 0;
+        uint32_t tie_off = block_exscan(my_ties, s, &tot_ties);  // ties before this thread's chunk
+        uint32_t mysel = 0;
+        for (int i = i0; i < i1; i++) {
+            const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
+            bool sel = kv > thr_key;
+            if (kv == thr_key) {
+                const uint32_t ties_after = tot_ties - tie_off - 1;  // ties at higher index
+                sel = ties_after < ties_needed;
+                tie_off++;
+            }
+            if (sel) {
+                state[kp[i]] = 4;
+                mysel++;
+            }
+        }
+        uint32_t tot_sel = 0;
+        uint32_t so = block_exscan(mysel, s, &tot_sel);
+        for (int i = i0; i < i1; i++)
+            if (state[kp[i]] == 4) cpts[1 + so++] = (int)kp[i] + w;  // + running_stat_width, already sorted
+        if (tid == 0) {
+            cpts[0] = 0;                      // peaks lie in [1, nc-2] and w >= 1: 0 and n are never present
+            cpts[c.num_events + 1] = n;
+        }
+    }
+    __syncthreads();
+    const int n_seg = c.num_events + 1;
+
+    // ---- c_new_means (_c_segmentation.pyx:41-53): sequential float64 sums ----------
+    for (int q = tid; q < n_seg; q += FP_THREADS) {
+        double sum = 0.0;
+        const int b = cpts[q], e = cpts[q + 1];
+        for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)sig[i]);
+        ev[q] = __ddiv_rn(sum, (double)(e - b));
+    }
+    __syncthreads();
+
+    // ---- mean_normalize (sig_proc.py:99-111) with numpy's summation order -----------
+    if (tid == 0) {
+        const double mean = __ddiv_rn(np_pairwise_sum(n_seg, [&](int i) { return ev[i]; }), (double)n_seg);
+        const double ss = np_pairwise_sum(n_seg, [&](int i) {
+            const double d = __dsub_rn(ev[i], mean);
+            return __dmul_rn(d, d);
+        });
+        red[0] = mean;
+        red[1] = __dsqrt_rn(__ddiv_rn(ss, (double)n_seg));
+    }
+    __syncthreads();
+    const double ev_mean = red[0], ev_std = red[1];
+
+    // ---- statistics (sig_proc.py:562-567) ----------------------------------------------
+    if (a.stats) {
+        double* st = a.stats + read * 6;
+        if (tid < n_seg) dv[tid] = (double)(cpts[tid + 1] - cpts[tid]);
+        small_median(dv, n_seg, &red[2], &red[6]);  // adapter_dt_med
+        const double dt_med = red[2];
+        if (tid < n_seg) dv[tid] = fabs(__dsub_rn((double)(cpts[tid + 1] - cpts[tid]), dt_med));
+        small_median(dv, n_seg, &red[3], &red[6]);  // adapter_dt_mad
+        small_median(ev, n_seg, &red[4], &red[6]);  // adapter_event_med
+        const double e_med = red[4];
+        if (tid < n_seg) dv[tid] = fabs(__dsub_rn(ev[tid], e_med));
+        small_median(dv, n_seg, &red[5], &red[6]);  // adapter_event_mad
+        if (tid == 0) {
+            st[0] = red[2];
+            st[1] = red[3];
+            st[2] = ev_mean;
+            st[3] = ev_std;
+            st[4] = red[4];
+            st[5] = red[5];
+        }
+    }
+
+    // ---- keep the last barcode_num_events (sig_proc.py:569-594) -------------------------
+    const int keep = min(nb, n_seg);
+    for (int q = tid; q < nb; q += FP_THREADS) {
+        const int srcq = n_seg - keep + (q - (nb - keep));
+        double v = qnan;  // front NaN padding if fewer events than asked (unreachable with accept_less_cpts=false)
+        int64_t dw = 0;
+        if (q >= nb - keep) {
+            v = __ddiv_rn(__dsub_rn(ev[srcq], ev_mean), ev_std);
+            dw = (int64_t)(cpts[srcq + 1] - cpts[srcq]);
+        }
+        fpt_out[q] = v;
+        if (a.dwell) a.dwell[read * nb + q] = dw;
+    }
+    if (tid == 0) a.status[read] = FP_OK;
+}
+
+inline size_t fingerprint_smem_bytes(int cap) {
+    return (size_t)cap * 12 + (size_t)(cap / 2 + 8) * 2 + (size_t)cap;
+}
+
+}  // namespace wdx

@@ -127,6 +127,77 @@ int wdx_distance_matrix_to(const double* X, int64_t nX, const double* Y, int64_t
                            int window, double penalty, int mode, void* out, int out_dtype,
                            int device, void* stream);
 
+/* ---- fingerprint extraction ------------------------------------------------
+ * Replaces, for a whole minibatch at once, the reference's per-read loop over
+ * barcode_fpt_wrapper -> detect_results_to_fpt (warpdemux/file_proc.py:418-428,
+ * 188-224; warpdemux/sig_proc.py:394-605, non-consensus path): extract_adapter
+ * (sig_proc.py:382-391), MAD winsorisation (:421-431), windowed t-test
+ * (segmentation/_c_segmentation.pyx:124-161), scipy find_peaks + top-num_events
+ * change points (sig_proc.py:176-198), segment means (_c_segmentation.pyx:41-53),
+ * mean/std normalisation (sig_proc.py:99-111, 546-552), last barcode_num_events
+ * (:569-594) and the six adapter statistics (:562-567).
+ *
+ * Configuration = the keys of the reference's SigProcConfig this path reads
+ * (config/config_files/rna004_130bps@v1.0.toml:5-14; adapted
+ * rna004_130bps@v0.2.4.toml:7).  Only sig_extract.normalization = "none",
+ * segmentation.normalization = "mean", accept_less_cpts = false and
+ * consensus_refinement = false are implemented (every shipped DTW-SVM model). */
+typedef struct {
+    int32_t padding;            /* sig_extract.padding                 (100) */
+    double outlier_thresh;      /* core.sig_norm_outlier_thresh        (5.0) */
+    int32_t min_obs_per_base;   /* segmentation.min_obs_per_base       (6)   */
+    int32_t running_stat_width; /* segmentation.running_stat_width     (12)  */
+    int32_t num_events;         /* segmentation.num_events             (110), <= 254 */
+    int32_t barcode_num_events; /* segmentation.barcode_num_events     (25)  */
+    int32_t max_slice_len;      /* longest adapter slice (adapter_end - adapter_start + 2*padding) to size the
+                                   per-read shared memory for; 0 = derive it from the batch (host arrays) or from
+                                   the row stride (device arrays).  Hard limit 16000 samples. */
+} wdx_fp_config;
+
+/* per-read status written to `status` (0 = ReadResult.success) */
+enum {
+    WDX_FP_OK = 0,
+    WDX_FP_FAIL_SEGMENTATION = 1, /* "event segmentation failed" (sig_proc.py:537-544): < num_events peaks */
+    WDX_FP_FAIL_DETECT = 2,       /* detect_ok[r] == 0 (sig_proc.py:400-407) */
+    WDX_FP_FAIL_NORMALIZE = 3,    /* reserved: "segment normalization failed" (sig_proc.py:553-560) */
+    WDX_FP_FAIL_TOO_LONG = 4      /* adapter slice longer than the shared-memory limit */
+};
+
+typedef struct wdx_fp wdx_fp;
+
+int wdx_fp_create(const wdx_fp_config* cfg, int device, wdx_fp** out);
+void wdx_fp_destroy(wdx_fp* f);
+
+/*   signals        [n, stride] float32 calibrated pA signal, one read per row (the reference's minibatch,
+ *                  file_proc.py:333-354).  Rows may be NaN-padded at the end; the first NaN ends the read.
+ *   sig_len        [n] int32 valid samples per row, or NULL
+ *   adapter_start/adapter_end [n] int64   DetectResults.adapter_start / adapter_end
+ *   detect_ok      [n] uint8 DetectResults.success, or NULL (all true)
+ *   clip_in_place  != 0: write the winsorised adapter slice back into `signals`, as the reference's
+ *                  in-place np.clip on its view does (sig_proc.py:426-431)
+ *   fpt            [n, barcode_num_events] float64 (NaN rows for failed reads)           (required)
+ *   dwell          [n, barcode_num_events] int64 dwell times of the kept events          (or NULL)
+ *   stats          [n, 6] float64 adapter_dt_med, adapter_dt_mad, adapter_event_mean,
+ *                  adapter_event_std, adapter_event_med, adapter_event_mad                (or NULL)
+ *   status         [n] int32 WDX_FP_*                                                     (required)
+ * Buffers may be host or device memory, as for wdx_predict. */
+int wdx_fp_extract(wdx_fp* f, const float* signals, int64_t n, int64_t stride, const int32_t* sig_len,
+                   const int64_t* adapter_start, const int64_t* adapter_end, const uint8_t* detect_ok,
+                   int clip_in_place, double* fpt, int64_t* dwell, double* stats, int32_t* status,
+                   void* stream);
+
+/* Fused minibatch step (file_proc.py:418-450): fingerprints never leave the
+ * device between extraction and wdx_predict.  Failed reads get label -1, NaN
+ * confidence/probabilities and WDX_FLAG_NONFINITE.  `fpt` may be NULL. */
+int wdx_fp_predict(wdx_fp* f, wdx_model* m, const float* signals, int64_t n, int64_t stride,
+                   const int32_t* sig_len, const int64_t* adapter_start, const int64_t* adapter_end,
+                   const uint8_t* detect_ok, int mode, int64_t* labels, double* conf, double* prob,
+                   uint8_t* flags, double* fpt, int32_t* status, void* stream);
+
+/* Device time (ms) and launch count of the fingerprint kernel in the last call on this handle. */
+int wdx_fp_enable_timing(wdx_fp* f, int on);
+int wdx_fp_last_kernel_ms(wdx_fp* f, double* ms, int* launches);
+
 /* ---- introspection -------------------------------------------------------- */
 const char* wdx_last_error(void);
 int wdx_device_count(void);

@@ -1,0 +1,149 @@
+"""GPU parity of the fingerprint stage (wdx_fp_extract / wdx_fp_predict through
+the C ABI) against the golden outputs of the reference's own
+`detect_results_to_fpt` and against the CPU oracle on seeded synthetic signals.
+
+Bars: status and dwell times (integer work) identical; float64 fingerprints and
+adapter statistics bit-identical (the kernel issues the reference's float
+operations in the reference's order, no FMA contraction)."""
+import json
+import pickle
+
+import numpy as np
+import pytest
+
+from wdx_testutil import oracle_fingerprints, synth_adapter_signals
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fp():
+    from warpdemux_b200.sig_proc import Fingerprinter
+
+    f = Fingerprinter(device=0)
+    yield f
+    f.close()
+
+
+def _same(b, status, fpt, dwell, stats):
+    assert np.array_equal(b.status, status), (b.status, status)
+    ok = status == 0
+    assert np.array_equal(b.dwell[ok], dwell[ok])
+    assert np.array_equal(b.fpt[ok], fpt[ok]), np.abs(b.fpt[ok] - fpt[ok]).max()
+    assert np.array_equal(b.stats[ok], stats[ok]), np.abs(b.stats[ok] - stats[ok]).max()
+    assert np.isnan(b.fpt[~ok]).all()
+
+
+def test_golden_reference_fingerprints(fp, golden_fingerprint):
+    g = golden_fingerprint
+    cfg = json.loads(str(g["cfg"]))
+    assert cfg["num_events"] == fp.config.num_events and cfg["padding"] == fp.config.padding
+    b = fp.extract(g["signals"], g["adapter_start"], g["adapter_end"])
+    _same(b, g["status"], g["fpt"], g["dwell"], g["stats"])
+
+
+@pytest.mark.parametrize("seed,short", [(11, 0.0), (12, 0.5)])
+def test_synthetic_signals_match_oracle(fp, seed, short):
+    """300 reads incl. short adapters (window < 12, distance < 6) and failures."""
+    sig, a0, a1 = synth_adapter_signals(300, seed=seed, width=9000, short_frac=short)
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1)
+    assert (status == 0).sum() > 100
+    if short:
+        assert (status != 0).sum() > 1
+    b = fp.extract(sig, a0, a1)
+    _same(b, status, fpt, dwell, stats)
+
+
+def test_sig_len_detect_ok_and_row_end(fp):
+    sig, a0, a1 = synth_adapter_signals(40, seed=13, width=8000)
+    lens = (~np.isnan(sig)).sum(axis=1).astype(np.int32)
+    # rows without NaN padding, explicit lengths; adapter_end beyond the read end; failed detections
+    dense = np.where(np.isnan(sig), np.float32(77.0), sig)
+    a1 = a1.copy()
+    a1[5] = 10**7
+    ok = np.ones(40, dtype=np.uint8)
+    ok[[3, 9]] = 0
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1)
+    status[[3, 9]] = 2
+    b = fp.extract(dense, a0, a1, sig_len=lens, detect_ok=ok)
+    _same(b, status, fpt, dwell, stats)
+    # same through NaN padding alone
+    b2 = fp.extract(sig, a0, a1, detect_ok=ok)
+    _same(b2, status, fpt, dwell, stats)
+
+
+def test_in_place_winsorisation_matches_numpy(fp):
+    sig, a0, a1 = synth_adapter_signals(8, seed=14, width=8000)
+    work = sig.copy()
+    fp.extract(work, a0, a1, clip_in_place=True)
+    for r in range(8):
+        n = int((~np.isnan(sig[r])).sum())
+        lo, hi = max(0, a0[r] - 100), min(n, a1[r] + 100)
+        sl = sig[r, lo:hi].copy()
+        med = np.nanmedian(sl)
+        mad = np.nanmedian(np.abs(sl - med))
+        want = sig[r].copy()
+        want[lo:hi] = np.clip(sl, med - 5.0 * mad, med + 5.0 * mad)
+        assert np.array_equal(work[r], want, equal_nan=True), r
+
+
+def test_reference_shaped_api(fp, golden_fingerprint):
+    from warpdemux_b200.sig_proc import (DetectResults, FingerprintConfig, batch_detect_results_to_fpt,
+                                         detect_results_to_fpt)
+
+    g = golden_fingerprint
+    cfg = FingerprintConfig()
+    drs = [DetectResults(True, int(a), int(b)) for a, b in zip(g["adapter_start"], g["adapter_end"])]
+    drs[4] = DetectResults(False, None, None, fail_reason="no adapter")
+    res = batch_detect_results_to_fpt(g["signals"], cfg, drs)
+    assert not res[4].success and res[4].fail_reason == "no adapter" and res[4].barcode_fpt.size == 0
+    assert not res[0].success and res[0].fail_reason == "event segmentation failed"
+    for r in (1, 2, 17, 31):
+        assert res[r].success and np.array_equal(res[r].barcode_fpt, g["fpt"][r])
+        assert np.array_equal(res[r].dwell_times, g["dwell"][r])
+        assert res[r].adapter_event_std == g["stats"][r, 3]
+    # per-read signature; the reference clips its input view in place
+    row = g["signals"][2]
+    valid = row[~np.isnan(row)].copy()
+    one = detect_results_to_fpt(valid, cfg, drs[2])
+    assert one.success and np.array_equal(one.barcode_fpt, g["fpt"][2])
+    assert not np.array_equal(valid, row[~np.isnan(row)])  # spikes were winsorised in the caller's buffer
+    assert "adapter_dt_med" in one.to_summary_dict()
+    pickle.loads(pickle.dumps(fp))
+
+
+def test_fused_extract_and_predict(fp, models):
+    from oracle import wdx_oracle as o
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    m = models["WDX4_rna004_v1_0"]
+    sig, a0, a1 = synth_adapter_signals(64, seed=15, width=9000)
+    status, fpt, _, _ = oracle_fingerprints(sig, a0, a1)
+    ok = status == 0
+    want_pred, want_prob, want_conf, _ = o.predict(m, fpt[ok])
+    for mode in ("exact", "guarded"):
+        mdl = DTW_SVM(m, device=0, mode=mode)
+        labels, prob, conf, st, got_fpt = fp.extract_and_predict(mdl, sig, a0, a1, want_fpt=True)
+        assert np.array_equal(st, status)
+        assert np.array_equal(got_fpt[ok], fpt[ok])
+        assert np.array_equal(labels[ok], want_pred)
+        assert np.abs(prob[ok] - want_prob).max() < (2e-6 if mode == "exact" else 1e-3)
+        assert (labels[~ok] == -1).all() and np.isnan(conf[~ok]).all()
+
+
+def test_device_buffers_and_empty_batch(fp):
+    import torch
+
+    sig, a0, a1 = synth_adapter_signals(50, seed=16, width=8000)
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1)
+    sd = torch.from_numpy(sig).cuda()
+    a0d, a1d = torch.from_numpy(a0).cuda(), torch.from_numpy(a1).cuda()
+    out = torch.empty((50, 25), dtype=torch.float64, device="cuda")
+    st = torch.empty(50, dtype=torch.int32, device="cuda")
+    fp.extract_raw(sd, 50, sig.shape[1], a0d, a1d, out, st, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(st.cpu().numpy(), status)
+    okm = status == 0
+    assert np.array_equal(out.cpu().numpy()[okm], fpt[okm])
+    b = fp.extract(np.zeros((0, 100), dtype=np.float32), [], [])
+    assert b.fpt.shape == (0, 25)

@@ -22,6 +22,7 @@ EXPORTS = [
     "wdx_model_create", "wdx_model_destroy", "wdx_model_set_guard", "wdx_model_set_chunk_reads", "wdx_model_set_sv_splits",
     "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
     "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_model_last_kernel_ms_mode", "wdx_version",
+    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms",
 ]
 
 _lib = None
@@ -78,8 +79,18 @@ def load():
         L.wdx_model_last_kernel_ms_mode.restype = i32
         L.wdx_model_last_kernel_ms_mode.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(i32)]
         L.wdx_version.restype = C.c_char_p
-        if hasattr(L, "wdx_fingerprint"):
-            L.wdx_fingerprint.restype = i32
+        L.wdx_fp_create.restype = i32
+        L.wdx_fp_create.argtypes = [vp, i32, C.POINTER(vp)]
+        L.wdx_fp_destroy.restype = None
+        L.wdx_fp_destroy.argtypes = [vp]
+        L.wdx_fp_extract.restype = i32
+        L.wdx_fp_extract.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+        L.wdx_fp_predict.restype = i32
+        L.wdx_fp_predict.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.wdx_fp_enable_timing.restype = i32
+        L.wdx_fp_enable_timing.argtypes = [vp, i32]
+        L.wdx_fp_last_kernel_ms.restype = i32
+        L.wdx_fp_last_kernel_ms.argtypes = [vp, C.POINTER(f64), C.POINTER(i32)]
         _lib = L
         return L
 

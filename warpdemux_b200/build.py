@@ -15,8 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libwdx_b200.so")
-SOURCES = ["wdx_b200.cu"]
-HEADERS = ["fused_kernels.cuh", "dtw_band.cuh", os.path.join("..", "..", "include", "wdx_b200.h")]
+SOURCES = ["wdx_b200.cu", "wdx_fp.cu"]
+HEADERS = ["wdx_types.cuh", "fused_kernels.cuh", "dtw_band.cuh", "dtw_band_x2.cuh", "fingerprint_kernel.cuh", "wdx_internal.cuh",
+           os.path.join("..", "..", "include", "wdx_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -24,7 +25,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",          # no implicit FMA contraction: FP64 paths must round like the x86-64 CPU build;
                             # the FP32 fast path asks for FMA explicitly (__fmaf_rn)
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
 
@@ -48,16 +49,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    # the image's default CC may point at a wrapper without a full toolchain
-    if os.path.exists("/usr/bin/g++"):
-        cmd += ["-ccbin", "/usr/bin/g++"]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    nvcc = _nvcc()
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []  # the image's default CC may be a wrapper
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    # one translation unit per process, in parallel; then one link step
+    procs, objs, log = [], [], ""
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ccbin + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    ok = True
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        log += " ".join(cmd) + "\n" + out
+        ok = ok and pr.returncode == 0
+    if ok:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + ccbin + ["-o", LIB] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        ok = res.returncode == 0
     with open(os.path.join(LIBDIR, "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        fh.write(log)
+    if not ok:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libwdx_b200.so")
     if verbose:

@@ -39,7 +39,7 @@ namespace wdx {
 constexpr int FP_THREADS = 256;
 constexpr int FP_WARPS = FP_THREADS / 32;
 constexpr int FP_MAX_EVENTS = 254;   // num_events bound (cpts has num_events + 2 entries)
-constexpr int FP_MAX_LEN = 16384;    // longest adapter slice a CTA can hold in shared memory
+constexpr int FP_MAX_LEN = 16000;    // longest adapter slice a CTA can hold in shared memory (14 B per sample)
 
 enum { FP_OK = 0, FP_FAIL_SEGMENTATION = 1, FP_FAIL_DETECT = 2, FP_FAIL_NORMALIZE = 3, FP_FAIL_TOO_LONG = 4 };
 

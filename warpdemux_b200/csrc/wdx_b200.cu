@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "fused_kernels.cuh"
+#include "wdx_internal.cuh"
 
 #ifndef WDX_DEFAULT_FAST_VARIANT
 #define WDX_DEFAULT_FAST_VARIANT 2
@@ -24,7 +25,7 @@
 
 using namespace wdx;
 
-namespace {
+namespace wdx {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
@@ -37,103 +38,66 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t e__ = (expr);                                                              \
-        if (e__ != cudaSuccess)                                                                \
-            return fail(WDX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
-                        __FILE__, __LINE__);                                                   \
-    } while (0)
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return WDX_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return fail(WDX_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return WDX_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes) {
-        if (bytes <= cap) return WDX_OK;
-        if (p) cudaFree(p);
+int HostBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return WDX_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) {
         p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            want = bytes;
-            e = cudaMalloc(&p, want);
-        }
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return fail(WDX_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
-        }
-        cap = want;
-        return WDX_OK;
+        return fail(WDX_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
     }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
+    cap = bytes;
+    return WDX_OK;
+}
+void HostBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
 
-struct HostBuf {  // pinned
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes) {
-        if (bytes <= cap) return WDX_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMallocHost(&p, bytes);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return fail(WDX_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
-        }
-        cap = bytes;
-        return WDX_OK;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-bool is_device_ptr(const void* p, int device) {
-    if (!p) return false;
+int mem_kind(const void* p) {
+    if (!p) return 0;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        return 0;
     }
-    (void)device;
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 2;
+    if (at.type == cudaMemoryTypeHost) return 1;
+    return 0;
 }
 
-}  // namespace
+}  // namespace wdx
 
-struct wdx_model {
-    ModelDev dev{};
-    int device = 0;
-    int sm_count = 148;
-    int k = 0, L = 0, n_sv = 0, n_pairs = 0;
-    bool specialised = false;  // L == 25 && window == 15
-    double guard = 5e-5;
-    std::mutex mu;
-    cudaStream_t stream = nullptr;       // compute
-    cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
-    std::vector<void*> owned;            // model arrays on the device
-    // workspaces (grow-only)
-    DevBuf part, part2, near_idx, counters;
-    DevBuf xdev[2], lab_dev[2], conf_dev[2], prob_dev[2], flag_dev[2], dist_dev[2];
-    HostBuf xpin[2];
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
-                ev_d2h[2] = {nullptr, nullptr};
-    // timing of the fused kernel
-    bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;
-    std::vector<char> tev_exact;
-    size_t tev_used = 0;
-    int64_t chunk_reads = (int64_t)1 << 22;
-    int forced_splits = 0;
-};
+namespace {
+bool is_device_ptr(const void* p, int) { return wdx::mem_kind(p) == 2; }
+}  // namespace
 
 namespace {
 
@@ -260,8 +224,10 @@ void choose_splits(const wdx_model* m, int64_t n, int* n_splits, int* sv_per_spl
     *sv_per_split = per;
 }
 
+}  // namespace
+
 // One chunk, everything on the device: Xd [n][L] -> labels/conf/prob/flags (device).
-int predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, int mode, int64_t* labels_d,
+int wdx::predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, int mode, int64_t* labels_d,
                          double* conf_d, double* prob_d, uint8_t* flags_d, float* dist_d, cudaStream_t st) {
     int n_splits, per;
     choose_splits(m, n, &n_splits, &per);
@@ -349,8 +315,6 @@ int predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, 
     }
     return WDX_OK;
 }
-
-}  // namespace
 
 extern "C" {
 
@@ -559,17 +523,6 @@ int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, i
 
     const int esz = (x_dtype == WDX_F32) ? 4 : 8;
     const int L = m->L, k = m->k;
-    auto mem_kind = [&](const void* p) -> int {  // 0 pageable host, 1 pinned host, 2 device
-        if (!p) return 0;
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 2;
-        if (at.type == cudaMemoryTypeHost) return 1;
-        return 0;
-    };
     const int x_kind = mem_kind(X);
     const bool x_dev = x_kind == 2;
     const bool lab_dev = mem_kind(labels) == 2;

@@ -37,6 +37,14 @@ DEF_KERNEL(k_iadd, int a[NCH]; int b = (int)seed; int c = b + 3, _Pragma("unroll
 DEF_KERNEL(k_ffma2, PDECL, PINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c)), PFINI)
 DEF_KERNEL(k_fadd2, PDECL, PINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b)), PFINI)
 
+#define DDECL double a[NCH], b = seed, c = seed * 0.5
+#define DINIT _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = seed + i + threadIdx.x
+#define DFINI double s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s
+DEF_KERNEL(k_dadd, DDECL, DINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(a[i]) : "d"(b)), DFINI)
+DEF_KERNEL(k_dmul, DDECL, DINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(a[i]) : "d"(b)), DFINI)
+DEF_KERNEL(k_dfma, DDECL, DINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[i]) : "d"(b), "d"(c)), DFINI)
+DEF_KERNEL(k_dmin, DDECL, DINIT, _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("{.reg .pred p; setp.lt.f64 p, %1, %0; selp.f64 %0, %1, %0, p;}" : "+d"(a[i]) : "d"(b)), DFINI)
+
 // mixes (independent chains so only throughput matters)
 DEF_KERNEL(k_mix_scalar, FDECL; float m[NCH], FINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = a[i] * 2,
            _Pragma("unroll") for (int i = 0; i < NCH; i++) {
@@ -109,6 +117,10 @@ int main() {
     run("IADD", k_iadd, NCH, out);
     run("FFMA2", k_ffma2, NCH, out);
     run("FADD2", k_fadd2, NCH, out);
+    run("DADD", k_dadd, NCH, out);
+    run("DMUL", k_dmul, NCH, out);
+    run("DFMA", k_dfma, NCH, out);
+    run("DSETP+SELx2 (as 1)", k_dmin, NCH, out);
     run("mix FADD,FFMA,FADD,MIN3", k_mix_scalar, NCH * 4, out);
     run("mix FFMA,MIN3", k_mix_fma_min3, NCH * 2, out);
     run("mix FFMA,MIN2", k_mix_fma_min2, NCH * 2, out);

@@ -106,9 +106,30 @@ __device__ __forceinline__ float dtw_band_f32(const float (&a)[L], const float (
 // min(up+p2, left+p2) == min(up,left)+p2 bit-for-bit (rounding is monotone),
 // which saves keeping a second row.  Strict-'<' update order of the reference
 // only matters for ties, and ties are value-equal.
-__device__ __forceinline__ double dmin_(double a, double b) { return (b < a) ? b : a; }
+//
+// The minimum is selectable (chosen by measurement, scripts/ubench_dtw64.cu):
+//   0  (b < a) ? b : a on doubles      -> DSETP (FP64 pipe) + 2 SEL
+//   1  the same comparison on the 64-bit patterns as unsigned integers -> 2 ISETP + 2 SEL on the
+//      ALU pipe, leaving the FP64 pipe to the four arithmetic ops of the cell.  All DP values are
+//      non-negative (sums of squares, +0, +inf), for which unsigned order == numeric order; a NaN
+//      pattern compares above +inf, and a row that contains one NaN is NaN throughout (every
+//      cell's cost term is NaN), exactly as with the floating-point comparison.
+//   2  fmin()
+// Measured (profiles/r01_ubench_instruction_mix.txt): 0 is fastest; DSETP + 2 SEL cost 5.3 cycles per
+// minimum, the four arithmetic ops 2 cycles each: 18.6 cycles per cell is the FP64 ceiling of this cell.
+template <int MI>
+__device__ __forceinline__ double dmin_(double a, double b) {
+    if constexpr (MI == 1) {
+        const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+        return __longlong_as_double((long long)((ub < ua) ? ub : ua));
+    } else if constexpr (MI == 2) {
+        return fmin(a, b);
+    } else {
+        return (b < a) ? b : a;
+    }
+}
 
-template <int L, int W>
+template <int L, int W, int MI = 0>
 __device__ __forceinline__ double dtw_band_f64(const double (&a)[L], const double (&s)[L], const double p2) {
     using B = Band<L, W>;
     double v[L];
@@ -129,10 +150,10 @@ __device__ __forceinline__ double dtw_band_f64(const double (&a)[L], const doubl
                 double old = 0.0;
                 if (has_up) old = v[j];
                 double m;
-                if (has_up && has_left) m = __dadd_rn(dmin_(v[j], v[j - 1]), p2);
+                if (has_up && has_left) m = __dadd_rn(dmin_<MI>(v[j], v[j - 1]), p2);
                 else if (has_up) m = __dadd_rn(v[j], p2);
                 else if (has_left) m = __dadd_rn(v[j - 1], p2);
-                if (has_diag && (has_up || has_left)) m = dmin_(diag, m);
+                if (has_diag && (has_up || has_left)) m = dmin_<MI>(diag, m);
                 else if (has_diag) m = diag;
                 v[j] = __dadd_rn(d, m);
                 diag = old;

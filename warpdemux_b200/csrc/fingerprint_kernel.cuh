@@ -87,7 +87,15 @@ struct FpScratch {
     int flag;
     int first_nan;
     int n_kept;
+    uint32_t vmin_key, vmax_key;      // order keys of the slice minimum / maximum
+    int sel_bin;                       // linear-bin median: bin holding the wanted rank
+    uint32_t sel_below, sel_count;     //   elements in lower bins / in that bin
+    uint32_t ncand;                    //   gathered candidates
+    uint32_t key_lo, key_hi;
 };
+
+constexpr int FP_MED_BINS = 2048;      // histogram bins of the linear-bin median (aliases the score array)
+constexpr int FP_MED_CAND = 512;       // candidate keys kept from the bin that holds the median
 
 // Exclusive prefix sum of one value per thread over the CTA; returns the exclusive
 // prefix, *total receives the CTA sum.  Contains __syncthreads.
@@ -210,6 +218,134 @@ __device__ float block_median_f32(int n, KEY key, FpScratch& s) {
     return __fdiv_rn(__fadd_rn(v_lo, v_hi), 2.0f);  // np.mean of two float32: float32 add, then /2
 }
 
+// Same result as block_median_f32, found with two light passes instead of five
+// heavy ones: values are binned linearly over [vmin, vmax] (a monotone map, so
+// every element of a lower bin is <= every element of a higher bin), the bin that
+// holds rank (n-1)/2 is located by a scan of the histogram, its few members are
+// gathered and ranked exactly on their order keys.  Falls back to the radix
+// selection when the bin is crowded (degenerate signals).
+//   hist: FP_MED_BINS uint32,  cand: FP_MED_CAND uint32  (scratch in shared memory)
+template <typename VAL>
+__device__ float block_median_f32_linear(int n, VAL val, float vmin, float vmax, uint32_t* hist, uint32_t* cand,
+                                         FpScratch& s) {
+    if (!(vmax > vmin)) return vmin;  // all values equal
+    const float scale = __fdiv_rn((float)FP_MED_BINS, __fsub_rn(vmax, vmin));
+    auto key_of = [&](int i) { return f32_key(val(i)); };
+    if (!(scale < 1e30f)) return block_median_f32(n, key_of, s);
+    auto bin_of = [&](float x) { return min(FP_MED_BINS - 1, (int)__fmul_rn(__fsub_rn(x, vmin), scale)); };
+    const int tid = threadIdx.x;
+    const uint32_t k_lo = (uint32_t)((n - 1) / 2);
+    __syncthreads();
+    for (int b = tid; b < FP_MED_BINS; b += FP_THREADS) hist[b] = 0;
+    if (tid == 0) s.ncand = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += FP_THREADS) atomicAdd(&hist[bin_of(val(i))], 1u);
+    __syncthreads();
+    {   // thread t owns bins [t*B, (t+1)*B)
+        constexpr int B = FP_MED_BINS / FP_THREADS;
+        uint32_t c[B], sum = 0;
+#pragma unroll
+        for (int q = 0; q < B; q++) {
+            c[q] = hist[tid * B + q];
+            sum += c[q];
+        }
+        uint32_t total;
+        uint32_t run = block_exscan(sum, s, &total);
+        if (k_lo >= run && k_lo < run + sum) {  // exactly one thread
+#pragma unroll
+            for (int q = 0; q < B; q++) {
+                if (k_lo >= run && k_lo < run + c[q]) {
+                    s.sel_bin = tid * B + q;
+                    s.sel_below = run;
+                    s.sel_count = c[q];
+                }
+                run += c[q];
+            }
+        }
+    }
+    __syncthreads();
+    const int sel_bin = s.sel_bin;
+    const uint32_t below = s.sel_below, m = s.sel_count;
+    if (m > (uint32_t)FP_MED_CAND) return block_median_f32(n, key_of, s);  // uniform decision
+    for (int i = tid; i < n; i += FP_THREADS) {
+        const float x = val(i);
+        if (bin_of(x) == sel_bin) cand[atomicAdd(&s.ncand, 1u)] = f32_key(x);
+    }
+    __syncthreads();
+    const uint32_t r = k_lo - below;  // wanted rank inside the bin
+    const bool even = (n & 1) == 0;
+    for (uint32_t t = tid; t < m; t += FP_THREADS) {
+        const uint32_t x = cand[t];
+        uint32_t rank = 0;
+        for (uint32_t u = 0; u < m; u++) {
+            const uint32_t y = cand[u];
+            rank += (y < x) || (y == x && u < t);
+        }
+        if (rank == r) s.key_lo = x;
+        if (rank == r + 1) s.key_hi = x;
+    }
+    __syncthreads();
+    const float v_lo = f32_unkey(s.key_lo);
+    if (!even) return v_lo;
+    float v_hi;
+    if (r + 1 < m) {
+        v_hi = f32_unkey(s.key_hi);
+    } else {  // the upper middle element is the smallest member of the following bins
+        if (tid == 0) s.hist[1] = 0xffffffffu;
+        __syncthreads();
+        uint32_t mn = 0xffffffffu;
+        for (int i = tid; i < n; i += FP_THREADS) {
+            const float x = val(i);
+            if (bin_of(x) > sel_bin) mn = min(mn, f32_key(x));
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if ((tid & 31) == 0) atomicMin(&s.hist[1], mn);
+        __syncthreads();
+        v_hi = f32_unkey(s.hist[1]);
+    }
+    return __fdiv_rn(__fadd_rn(v_lo, v_hi), 2.0f);
+}
+
+// x / w for a small positive integer w, correctly rounded, in three FP64 operations
+// (Markstein: with r = RN(1/w) and q0 = RN(x*r), q0 + RN(x - w*q0)*r rounds to RN(x/w);
+// checked against IEEE division on 4.8e8 operands per w in 1..12).  Bit-identical to
+// the reference's `m1 /= running_stat_width`.
+__device__ __forceinline__ double div_small_int(double x, double w, double r) {
+    const double q0 = __dmul_rn(x, r);
+    const double rem = __fma_rn(-w, q0, x);
+    return __fma_rn(rem, r, q0);
+}
+
+// One t-test score (_c_segmentation.pyx:132-159) from the 2*W window samples at p.
+template <int W>
+__device__ __forceinline__ double ttest_score_fixed(const float* p, double wd, double wr) {
+    double x[2 * W];
+#pragma unroll
+    for (int i = 0; i < 2 * W; i++) x[i] = (double)p[i];
+    double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < W; i++) m1 = __dadd_rn(m1, x[i]);
+    m1 = div_small_int(m1, wd, wr);
+#pragma unroll
+    for (int i = 0; i < W; i++) m2 = __dadd_rn(m2, x[W + i]);
+    m2 = div_small_int(m2, wd, wr);
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double pd = __dsub_rn(x[i], m1);
+        var1 = __dadd_rn(var1, __dmul_rn(pd, pd));
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double pd = __dsub_rn(x[W + i], m2);
+        var2 = __dadd_rn(var2, __dmul_rn(pd, pd));
+    }
+    const double vs = __dadd_rn(var1, var2);
+    if (vs == 0.0) return 0.0;
+    const double num = (m1 > m2) ? __dsub_rn(m1, m2) : __dsub_rn(m2, m1);
+    return __ddiv_rn(num, __dsqrt_rn(vs));
+}
+
 // numpy's pairwise summation for n <= 128 contiguous float64 (np.add.reduce):
 // 8 strided accumulators, fixed combination tree, sequential tail.
 template <typename F>
@@ -305,15 +441,38 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
     }
     int n = (int)n64;
     const float* src = a.signals + read * a.stride + start;
-    if (tid == 0) s.first_nan = n;
-    __syncthreads();
-    for (int i = tid; i < n; i += FP_THREADS) {  // the one HBM read of the slice, coalesced
-        const float x = __ldg(src + i);
-        sig[i] = x;
-        if (x != x) atomicMin(&s.first_nan, i);
+    if (tid == 0) {
+        s.first_nan = n;
+        s.vmin_key = 0xffffffffu;
+        s.vmax_key = 0u;
     }
     __syncthreads();
-    n = min(n, s.first_nan);  // NaN padding of the minibatch row ends the signal (file_proc.py:333-354)
+    {   // the one HBM read of the slice, coalesced; minimum / maximum on the way
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+        for (int i = tid; i < n; i += FP_THREADS) {
+            const float x = __ldg(src + i);
+            sig[i] = x;
+            if (x != x) {
+                atomicMin(&s.first_nan, i);
+            } else {
+                const uint32_t kx = f32_key(x);
+                kmin = min(kmin, kx);
+                kmax = max(kmax, kx);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&s.vmin_key, kmin);
+            atomicMax(&s.vmax_key, kmax);
+        }
+    }
+    __syncthreads();
+    const bool trimmed = s.first_nan < n;  // NaN padding of the minibatch row ends the signal (file_proc.py:333-354)
+    n = min(n, s.first_nan);
 
     // ---- segmentation parameters (sig_proc.py:526-533; Python round = half to even)
     const int m_obs = min(c.min_obs_per_base, py_round((double)n / (double)c.num_events / 2.0));
@@ -325,8 +484,20 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
     }
 
     // ---- winsorise at med +- thresh * MAD, float32 (sig_proc.py:421-431) --------
-    const float med = block_median_f32(n, [&](int i) { return f32_key(sig[i]); }, s);
-    const float mad = block_median_f32(n, [&](int i) { return f32_key(fabsf(__fsub_rn(sig[i], med))); }, s);
+    uint32_t* med_hist = reinterpret_cast<uint32_t*>(score);  // the score array is idle until the t-test
+    uint32_t* med_cand = med_hist + FP_MED_BINS;
+    const bool lin = !trimmed && cap >= (FP_MED_BINS + FP_MED_CAND) / 2;  // min/max cover exactly the slice; scratch fits
+    float med, mad;
+    if (lin) {
+        const float vmin = f32_unkey(s.vmin_key), vmax = f32_unkey(s.vmax_key);
+        med = block_median_f32_linear(n, [&](int i) { return sig[i]; }, vmin, vmax, med_hist, med_cand, s);
+        const float ymax = fmaxf(__fsub_rn(vmax, med), __fsub_rn(med, vmin));  // >= every |x - med| (rounding is monotone)
+        mad = block_median_f32_linear(n, [&](int i) { return fabsf(__fsub_rn(sig[i], med)); }, 0.0f, ymax, med_hist,
+                                      med_cand, s);
+    } else {
+        med = block_median_f32(n, [&](int i) { return f32_key(sig[i]); }, s);
+        mad = block_median_f32(n, [&](int i) { return f32_key(fabsf(__fsub_rn(sig[i], med))); }, s);
+    }
     const float tm = __fmul_rn(c.outlier_thresh, mad);
     const float lo = __fsub_rn(med, tm), hi = __fadd_rn(med, tm);
     __syncthreads();
@@ -341,88 +512,115 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
 
     // ---- c_windowed_t_test (_c_segmentation.pyx:124-161), float64, reference order
     const double wd = (double)w;
-    for (int pos = tid; pos < nc; pos += FP_THREADS) {
-        double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;
-        for (int i = 0; i < w; i++) m1 = __dadd_rn(m1, (double)sig[pos + i]);
-        m1 = __ddiv_rn(m1, wd);
-        for (int i = 0; i < w; i++) m2 = __dadd_rn(m2, (double)sig[pos + w + i]);
-        m2 = __ddiv_rn(m2, wd);
-        for (int i = 0; i < w; i++) {
-            const double pd = __dsub_rn((double)sig[pos + i], m1);
-            var1 = __dadd_rn(var1, __dmul_rn(pd, pd));
+    if (w == 12) {  // the capped width (every adapter of >= 1265 samples): unrolled, window in registers
+        const double wr = 1.0 / 12.0;
+        for (int pos = tid; pos < nc; pos += FP_THREADS) score[pos] = ttest_score_fixed<12>(sig + pos, 12.0, wr);
+    } else {
+        for (int pos = tid; pos < nc; pos += FP_THREADS) {
+            double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;
+            for (int i = 0; i < w; i++) m1 = __dadd_rn(m1, (double)sig[pos + i]);
+            m1 = __ddiv_rn(m1, wd);
+            for (int i = 0; i < w; i++) m2 = __dadd_rn(m2, (double)sig[pos + w + i]);
+            m2 = __ddiv_rn(m2, wd);
+            for (int i = 0; i < w; i++) {
+                const double pd = __dsub_rn((double)sig[pos + i], m1);
+                var1 = __dadd_rn(var1, __dmul_rn(pd, pd));
+            }
+            for (int i = 0; i < w; i++) {
+                const double pd = __dsub_rn((double)sig[pos + w + i], m2);
+                var2 = __dadd_rn(var2, __dmul_rn(pd, pd));
+            }
+            const double vs = __dadd_rn(var1, var2);
+            double sc;
+            if (vs == 0.0) sc = 0.0;
+            else if (m1 > m2) sc = __ddiv_rn(__dsub_rn(m1, m2), __dsqrt_rn(vs));
+            else sc = __ddiv_rn(__dsub_rn(m2, m1), __dsqrt_rn(vs));
+            score[pos] = sc;
         }
-        for (int i = 0; i < w; i++) {
-            const double pd = __dsub_rn((double)sig[pos + w + i], m2);
-            var2 = __dadd_rn(var2, __dmul_rn(pd, pd));
-        }
-        const double vs = __dadd_rn(var1, var2);
-        double sc;
-        if (vs == 0.0) sc = 0.0;
-        else if (m1 > m2) sc = __ddiv_rn(__dsub_rn(m1, m2), __dsqrt_rn(vs));
-        else sc = __ddiv_rn(__dsub_rn(m2, m1), __dsqrt_rn(vs));
-        score[pos] = sc;
-        state[pos] = 0;
     }
     __syncthreads();
 
-    // ---- scipy _local_maxima_1d: strict maxima, plateaus -> midpoint --------------
-    for (int i = tid + 1; i < nc - 1; i += FP_THREADS) {
+    // ---- scipy _local_maxima_1d (strict maxima, plateaus -> midpoint), compacted in order
+    // thread t scans the contiguous positions [t*chunk, (t+1)*chunk); a plateau belongs to the
+    // thread that owns its first sample, which keeps the list sorted by position.
+    const int chunk = (nc + FP_THREADS - 1) / FP_THREADS;
+    const int p_begin = min(nc - 1, max(1, tid * chunk)), p_end = min(nc - 1, (tid + 1) * chunk);
+    auto peak_at = [&](int i) -> int {  // midpoint of the maximum that starts at i, or -1
         const double x = score[i];
-        if (score[i - 1] < x) {
-            int ahead = i + 1;
-            while (ahead < nc - 1 && score[ahead] == x) ahead++;
-            if (score[ahead] < x) state[(i + ahead - 1) >> 1] = 1;  // 1 = peak, undecided
+        if (!(score[i - 1] < x)) return -1;
+        int ahead = i + 1;
+        while (ahead < nc - 1 && score[ahead] == x) ahead++;
+        return (score[ahead] < x) ? ((i + ahead - 1) >> 1) : -1;
+    };
+    uint32_t my = 0;
+    for (int i = p_begin; i < p_end; i++) my += (peak_at(i) >= 0);
+    uint32_t total = 0;
+    uint32_t off = block_exscan(my, s, &total);
+    for (int i = p_begin; i < p_end; i++) {
+        const int pk = peak_at(i);
+        if (pk >= 0) {
+            kp[off] = (uint16_t)pk;
+            state[off] = 1;  // per-peak state: 1 undecided, 2 kept, 3 removed
+            off++;
         }
     }
     __syncthreads();
+    const int P0 = (int)total;
 
-    // ---- scipy _select_by_peak_distance as a fixed point -------------------------
-    // states: 0 none, 1 undecided, 2 kept, 3 removed.  Priority = (score, index).
+    // ---- scipy _select_by_peak_distance as a fixed point over the peak list ---------
+    // A peak stays iff no STAYING peak of higher priority (score, then index) lies closer than
+    // m_obs samples; the greedy highest-first sweep of scipy computes exactly this set.
     if (m_obs > 1) {
         for (;;) {
             int undecided = 0;
-            // phase 1: decide from the current states (low nibble); the verdict is parked in the
-            // high nibble of the peak's own byte, which no other thread interprets
-            for (int p = tid; p < nc; p += FP_THREADS) {
-                if ((state[p] & 15) != 1) continue;
-                const double x = score[p];
+            for (int j = tid; j < P0; j += FP_THREADS) {
+                if ((state[j] & 15) != 1) continue;
+                const int pj = kp[j];
+                const double x = score[pj];
                 bool killed = false, blocked = false;
-                const int q0 = max(0, p - (m_obs - 1)), q1 = min(nc - 1, p + (m_obs - 1));
-                for (int q = q0; q <= q1; q++) {
+                for (int q = j - 1; q >= 0 && pj - (int)kp[q] < m_obs; q--) {
                     const int st = state[q] & 15;
-                    if (q == p || st == 0 || st == 3) continue;
-                    const double y = score[q];
-                    const bool higher = (y > x) || (y == x && q > p);
-                    if (!higher) continue;
-                    if (st == 2) killed = true;
-                    else blocked = true;  // an undecided higher peak
+                    if (st == 3) continue;
+                    if (score[kp[q]] > x) {  // equal scores: the higher index wins, q < j loses
+                        if (st == 2) killed = true;
+                        else blocked = true;
+                    }
+                }
+                for (int q = j + 1; q < P0 && (int)kp[q] - pj < m_obs; q++) {
+                    const int st = state[q] & 15;
+                    if (st == 3) continue;
+                    if (score[kp[q]] >= x) {
+                        if (st == 2) killed = true;
+                        else blocked = true;
+                    }
                 }
                 const int ns = killed ? 3 : (blocked ? 1 : 2);
                 if (ns == 1) undecided = 1;
-                state[p] = (uint8_t)(1 | (ns << 4));
+                state[j] = (uint8_t)(1 | (ns << 4));  // verdict parked in the high nibble (nobody else reads it)
             }
             const int any = __syncthreads_or(undecided);
-            // phase 2: publish
-            for (int p = tid; p < nc; p += FP_THREADS)
-                if (state[p] >> 4) state[p] = state[p] >> 4;
+            for (int j = tid; j < P0; j += FP_THREADS)
+                if (state[j] >> 4) state[j] = state[j] >> 4;
             __syncthreads();
             if (!any) break;
         }
     } else {
-        for (int p = tid; p < nc; p += FP_THREADS)
-            if (state[p] == 1) state[p] = 2;
+        for (int j = tid; j < P0; j += FP_THREADS) state[j] = 2;
         __syncthreads();
     }
 
-    // ---- ordered compaction of the kept peaks -------------------------------------
-    const int chunk = (nc + FP_THREADS - 1) / FP_THREADS;
-    const int p_begin = min(nc, tid * chunk), p_end = min(nc, p_begin + chunk);
-    uint32_t my = 0;
-    for (int p = p_begin; p < p_end; p++) my += (state[p] == 2);
-    uint32_t total = 0;
-    uint32_t off = block_exscan(my, s, &total);
-    for (int p = p_begin; p < p_end; p++)
-        if (state[p] == 2) kp[off++] = (uint16_t)p;
+    // ---- kept peaks, in order (in place: the write index never passes the read index)
+    const int pchunk0 = (P0 + FP_THREADS - 1) / FP_THREADS;
+    const int j0 = min(P0, tid * pchunk0), j1 = min(P0, j0 + pchunk0);
+    uint32_t mk = 0;
+    for (int j = j0; j < j1; j++) mk += (state[j] == 2);
+    uint32_t koff = block_exscan(mk, s, &total);
+    uint16_t keep_local[FP_MAX_LEN / 2 / FP_THREADS + 2];
+    int nk = 0;
+    for (int j = j0; j < j1; j++)
+        if (state[j] == 2) keep_local[nk++] = kp[j];
+    __syncthreads();  // everybody has read its part of the list
+    for (int q = 0; q < nk; q++) kp[koff + q] = keep_local[q];
     __syncthreads();
     const int P = (int)total;
     if (P < c.num_events) {  // sig_proc.py:185-186 -> "event segmentation failed"
@@ -445,15 +643,30 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
                 if ((kv & mask) == prefix) atomicAdd(&s.hist[(uint32_t)(kv >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                uint32_t run = 0;
-                int b = 255;
-                for (; b > 0; b--) {
-                    if (k < run + s.hist[b]) break;
-                    run += s.hist[b];
+            if (tid < 32) {  // warp 0 scans the 256 bins from the top, 8 per lane (lane 0 = bins 255..248)
+                uint32_t cnt[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    cnt[q] = s.hist[255 - (tid * 8 + q)];
+                    sum += cnt[q];
                 }
-                s.sel_prefix64 = prefix | ((unsigned long long)b << shift);
-                s.sel_k = k - run;
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (tid >= o) inc += t;
+                }
+                uint32_t run = inc - sum;  // elements in higher bins
+                if (k >= run && k < inc) {  // exactly one lane
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (k >= run && k < run + cnt[q]) {
+                            s.sel_prefix64 = prefix | ((unsigned long long)(255 - (tid * 8 + q)) << shift);
+                            s.sel_k = k - run;
+                        }
+                        run += cnt[q];
+                    }
+                }
             }
             __syncthreads();
             prefix = s.sel_prefix64;
@@ -466,11 +679,10 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
     }
     const uint32_t ties_needed = s.sel_k + 1;
     __syncthreads();
-    // mark the selection in `state` (4 = selected), then compact in order
+    // mark the selection, then compact in order into the change points
     {
         const int pchunk = (P + FP_THREADS - 1) / FP_THREADS;
         const int i0 = min(P, tid * pchunk), i1 = min(P, i0 + pchunk);
-        // ties: count the ties at higher list index than each tie (only needed if more ties than wanted)
         uint32_t my_ties = 0;
         for (int i = i0; i < i1; i++)
             my_ties += ((unsigned long long)__double_as_longlong(score[kp[i]]) == thr_key);
@@ -485,15 +697,13 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
                 sel = ties_after < ties_needed;
                 tie_off++;
             }
-            if (sel) {
-                state[kp[i]] = 4;
-                mysel++;
-            }
+            state[i] = sel ? 4 : 0;
+            mysel += sel;
         }
         uint32_t tot_sel = 0;
         uint32_t so = block_exscan(mysel, s, &tot_sel);
         for (int i = i0; i < i1; i++)
-            if (state[kp[i]] == 4) cpts[1 + so++] = (int)kp[i] + w;  // + running_stat_width, already sorted
+            if (state[i] == 4) cpts[1 + so++] = (int)kp[i] + w;  // + running_stat_width, already sorted
         if (tid == 0) {
             cpts[0] = 0;                      // peaks lie in [1, nc-2] and w >= 1: 0 and n are never present
             cpts[c.num_events + 1] = n;

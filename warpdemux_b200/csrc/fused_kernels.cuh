@@ -101,12 +101,13 @@ __device__ __forceinline__ double kernel_from_dist_f32_exact(float d, float gamm
 //   L_, W_: compile-time fingerprint length / window (25 / 15 for every shipped
 //           model); L_ == 0 selects the generic runtime-shape fallback.
 //   KM1   : compile-time bound on k-1 (number of running decision sums)
-//   X2    : FAST only — packed f32x2 recurrence (dtw_band_x2.cuh) instead of scalar
+//   X2    : FAST only — 0 scalar recurrence, 1 packed f32x2 (dtw_band_x2.cuh), 2 packed f32x2 in
+//           offset ("E") form with a plain-recurrence redo of near-zero distances
 //   MINB  : CTAs per SM the register allocation is bounded for
 //   ACCS  : running decision sums live in shared memory instead of registers
 // grid = (ceil(n / CTA_THREADS), n_splits)
 // ---------------------------------------------------------------------------
-template <bool EXACT, int L_, int W_, int KM1, bool X2, int MINB, bool ACCS>
+template <bool EXACT, int L_, int W_, int KM1, int X2, int MINB, bool ACCS>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
 dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ PredictArgs a) {
     using T = typename std::conditional<EXACT, double, float>::type;
@@ -274,7 +275,19 @@ dtw_svc_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ Predi
                     sp[t] = pack2(w.x, w.y);
                     if (t + 1 < L_) sp[t + 1] = pack2(w.z, w.w);
                 }
-                d2 = dtw_band_f32_x2<L_, W_>(ap, sp, p2);
+                if constexpr (X2 == 2) {
+                    d2 = dtw_band_f32_x2e<L_, W_>(ap, sp, p2);
+                    if (d2 < DTW_E_FORM_MIN_D2) {  // rare: cancellation would cost relative accuracy
+                        float xa[MAXL], sa[MAXL];
+#pragma unroll
+                        for (int j = 0; j < L_; j++) xa[j] = (j & 1) ? hi2(ap[j >> 1]) : lo2(ap[j >> 1]);
+                        sa[0] = reinterpret_cast<const float*>(srow)[1];
+                        for (int j = 1; j < L_; j++) sa[j] = reinterpret_cast<const float*>(srow)[2 * (j - 1)];
+                        d2 = dtw_generic<float, MAXL>(xa, sa, L_, m.window, p2);
+                    }
+                } else {
+                    d2 = dtw_band_f32_x2<L_, W_>(ap, sp, p2);
+                }
             } else if constexpr (!GENERIC) {
                 T s[LR];
                 constexpr int VEC = 16 / sizeof(T);

@@ -19,8 +19,11 @@
 #include "fused_kernels.cuh"
 #include "wdx_internal.cuh"
 
+#ifndef WDX_DEFAULT_EXACT_VARIANT
+#define WDX_DEFAULT_EXACT_VARIANT 2
+#endif
 #ifndef WDX_DEFAULT_FAST_VARIANT
-#define WDX_DEFAULT_FAST_VARIANT 2
+#define WDX_DEFAULT_FAST_VARIANT 9
 #endif
 
 using namespace wdx;
@@ -119,12 +122,13 @@ struct FusedChoice {
     int km1_cap;
 };
 
-// FAST-path variants (selected by measurement; WDX_FAST_VARIANT overrides for experiments):
-//   0 scalar recurrence, 4 CTAs/SM, sums in registers
-//   1 packed f32x2,      2 CTAs/SM, sums in registers
-//   2 packed f32x2,      3 CTAs/SM, sums in shared memory
-//   3 scalar recurrence, 5 CTAs/SM, sums in shared memory
-//   4 scalar recurrence, 6 CTAs/SM, sums in shared memory
+// FAST-path variants (selected by measurement, profiles/r01_fast_variants.jsonl and
+// profiles/r01_ubench_instruction_mix.txt; WDX_FAST_VARIANT overrides for experiments):
+//   0 scalar recurrence,               4 CTAs/SM, sums in registers
+//   2 packed f32x2,                    3 CTAs/SM, sums in shared memory
+//   6 packed f32x2 in offset (E) form, 4 CTAs/SM, sums in shared memory
+//   7 packed f32x2 in offset (E) form, 5 CTAs/SM, sums in shared memory (spills once k-1 > 4)
+//   9 (default) 7 for models with at most 5 classes, else 6
 int fast_variant() {
     static int v = [] {
         const char* e = getenv("WDX_FAST_VARIANT");
@@ -133,7 +137,7 @@ int fast_variant() {
     return v;
 }
 
-template <bool EXACT, int L_, int W_, bool X2, int MINB, bool ACCS>
+template <bool EXACT, int L_, int W_, int X2, int MINB, bool ACCS>
 FusedChoice pick_km1(int km1) {
     FusedFn f;
     int cap;
@@ -141,22 +145,29 @@ FusedChoice pick_km1(int km1) {
     else if (km1 <= 6) { f = dtw_svc_kernel<EXACT, L_, W_, 6, X2, MINB, ACCS>; cap = 6; }
     else if (km1 <= 10) { f = dtw_svc_kernel<EXACT, L_, W_, 10, X2, MINB, ACCS>; cap = 10; }
     else { f = dtw_svc_kernel<EXACT, L_, W_, 16, X2, MINB, ACCS>; cap = 16; }
-    return FusedChoice{f, X2, ACCS, cap};
+    return FusedChoice{f, X2 != 0, ACCS, cap};
 }
 
 FusedChoice pick_fused(const wdx_model* m, bool exact) {
     const int km1 = m->k - 1;
     if (!m->specialised) {
-        if (exact) return FusedChoice{dtw_svc_kernel<true, 0, 0, 16, false, 3, false>, false, false, 16};
-        return FusedChoice{dtw_svc_kernel<false, 0, 0, 16, false, 4, false>, false, false, 16};
+        if (exact) return FusedChoice{dtw_svc_kernel<true, 0, 0, 16, 0, 3, false>, false, false, 16};
+        return FusedChoice{dtw_svc_kernel<false, 0, 0, 16, 0, 4, false>, false, false, 16};
     }
-    if (exact) return pick_km1<true, 25, 15, false, 3, false>(km1);
+    if (exact) {  // WDX_EXACT_VARIANT: 0 = 3 CTAs/SM, sums in registers; 1 = 4 CTAs/SM, sums in shared memory;
+                  // 2 (default) = 0 for models with at most 5 classes, else 1 (measured: WDX4 1930 vs 1876, WDX10 1806 vs 1892 GCUPS)
+        static const int ev = [] { const char* e = getenv("WDX_EXACT_VARIANT"); return e ? atoi(e) : WDX_DEFAULT_EXACT_VARIANT; }();
+        if (ev == 0 || (ev == 2 && km1 <= 4)) return pick_km1<true, 25, 15, 0, 3, false>(km1);
+        return pick_km1<true, 25, 15, 0, 4, true>(km1);
+    }
     switch (fast_variant()) {
-        case 1: return pick_km1<false, 25, 15, true, 2, false>(km1);
-        case 2: return pick_km1<false, 25, 15, true, 3, true>(km1);
-        case 3: return pick_km1<false, 25, 15, false, 5, true>(km1);
-        case 4: return pick_km1<false, 25, 15, false, 6, true>(km1);
-        default: return pick_km1<false, 25, 15, false, 4, false>(km1);
+        case 0: return pick_km1<false, 25, 15, 0, 4, false>(km1);
+        case 2: return pick_km1<false, 25, 15, 1, 3, true>(km1);
+        case 6: return pick_km1<false, 25, 15, 2, 4, true>(km1);
+        case 7: return pick_km1<false, 25, 15, 2, 5, true>(km1);
+        default:
+            if (km1 <= 4) return FusedChoice{dtw_svc_kernel<false, 25, 15, 4, 2, 5, true>, true, true, 4};
+            return pick_km1<false, 25, 15, 2, 4, true>(km1);
     }
 }
 

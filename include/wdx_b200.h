@@ -150,8 +150,10 @@ typedef struct {
     int32_t num_events;         /* segmentation.num_events             (110), <= 254 */
     int32_t barcode_num_events; /* segmentation.barcode_num_events     (25)  */
     int32_t max_slice_len;      /* longest adapter slice (adapter_end - adapter_start + 2*padding) to size the
-                                   per-read shared memory for; 0 = derive it from the batch (host arrays) or from
-                                   the row stride (device arrays).  Hard limit 16000 samples. */
+                                   per-read shared memory for (14 B per sample; smaller = more reads per SM);
+                                   0 = derive it from the batch: a host loop over host-resident bounds, or a
+                                   small device reduction + 4-byte read back (a host sync) for device-resident
+                                   bounds.  Hard limit 16000 samples. */
 } wdx_fp_config;
 
 /* per-read status written to `status` (0 = ReadResult.success) */

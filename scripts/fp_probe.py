@@ -25,7 +25,8 @@ def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
     bytes_alg = int(sl.sum()) * 4 * reps + n * 25 * 8
     fpt = torch.empty((n, 25), dtype=torch.float64, device="cuda")
     st = torch.empty(n, dtype=torch.int32, device="cuda")
-    fp = Fingerprinter(device=0)
+    from warpdemux_b200.sig_proc import FingerprintConfig
+    fp = Fingerprinter(FingerprintConfig(max_slice_len=int(os.environ.get("FP_MAX_SLICE", "7040"))), device=0)
     fp.enable_timing(True)
     stream = torch.cuda.current_stream().cuda_stream
     best = 1e30

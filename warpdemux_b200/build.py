@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ccbin + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("WDX_NVCC_EXTRA", "").split() + ccbin + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True
     for cmd, pr in procs:

@@ -36,7 +36,10 @@
 
 namespace wdx {
 
-constexpr int FP_THREADS = 256;
+#ifndef WDX_FP_THREADS
+#define WDX_FP_THREADS 512
+#endif
+constexpr int FP_THREADS = WDX_FP_THREADS;  // 512 x 2 CTAs/SM = 32 warps/SM at <= 64 registers
 constexpr int FP_WARPS = FP_THREADS / 32;
 constexpr int FP_MAX_EVENTS = 254;   // num_events bound (cpts has num_events + 2 entries)
 constexpr int FP_MAX_LEN = 16000;    // longest adapter slice a CTA can hold in shared memory (14 B per sample)
@@ -137,7 +140,7 @@ __device__ uint32_t block_select_u32(int n, uint32_t k, KEY key, FpScratch& s) {
     uint32_t prefix = 0, mask = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
         __syncthreads();
-        s.hist[threadIdx.x] = 0;  // FP_THREADS == 256
+        if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
         __syncthreads();
         const int n_round = (n + 31) & ~31;  // keep whole warps in the loop for the ballot
         for (int i = threadIdx.x; i < n_round; i += FP_THREADS) {
@@ -392,7 +395,7 @@ __device__ void small_median(const double* v, int n, double* out, double* tmp2) 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_constant__ FpConfig c,
+__global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_kernel(const __grid_constant__ FpConfig c,
                                                                    const __grid_constant__ FpArgs a) {
     extern __shared__ __align__(16) unsigned char fp_smem[];
     const int cap = a.cap;
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
         uint32_t k = (uint32_t)c.num_events - 1;  // 0-based rank from the top
         for (int shift = 56; shift >= 0; shift -= 8) {
             __syncthreads();
-            s.hist[tid] = 0;
+            if (tid < 256) s.hist[tid] = 0;
             __syncthreads();
             for (int i = tid; i < P; i += FP_THREADS) {
                 const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
@@ -770,6 +773,22 @@ __global__ void __launch_bounds__(FP_THREADS) fingerprint_kernel(const __grid_co
         if (a.dwell) a.dwell[read * nb + q] = dw;
     }
     if (tid == 0) a.status[read] = FP_OK;
+}
+
+// Longest adapter slice of a batch whose bounds live in device memory (sizes the shared memory).
+__global__ void max_slice_kernel(const int64_t* __restrict__ a0, const int64_t* __restrict__ a1, const int32_t* __restrict__ sig_len,
+                                 int64_t n, int64_t stride, int padding, int* __restrict__ out) {
+    int best = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t len_row = sig_len ? (int64_t)sig_len[r] : stride;
+        int64_t b = a0[r] - padding, e = a1[r] + padding;
+        if (b < 0) b = 0;
+        if (e > len_row) e = len_row;
+        if (e - b > best) best = (int)min((int64_t)0x7fffffff, e - b);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, best);
 }
 
 inline size_t fingerprint_smem_bytes(int cap) {

@@ -19,7 +19,7 @@ struct wdx_fp {
     cudaStream_t stream = nullptr;       // kernels + result copies
     cudaStream_t copy_stream = nullptr;  // H2D of the next chunk
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    DevBuf sig[2], len[2], a0[2], a1[2], ok[2];
+    DevBuf sig[2], len[2], a0[2], a1[2], ok[2], maxlen;
     DevBuf fpt[2], dwell[2], stats[2], status[2], lab[2], conf[2], prob[2], flags[2];
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;
@@ -123,6 +123,20 @@ int run(wdx_fp* f, const FpCall& c) {
                 if (e > c.stride) e = c.stride;
                 cap64 = std::max(cap64, e - b);
             }
+        } else if (a0_dev && a1_dev && (!c.sig_len || len_dev)) {
+            // bounds live on the device: one small reduction + a 4-byte read back (a host sync; give
+            // wdx_fp_config.max_slice_len to stay asynchronous)
+            int rc0 = f->maxlen.reserve(sizeof(int));
+            if (rc0) return rc0;
+            CUDA_TRY(cudaMemsetAsync(f->maxlen.p, 0, sizeof(int), st));
+            const unsigned blocks = (unsigned)std::min<int64_t>(1184, (c.n + 255) / 256);
+            max_slice_kernel<<<blocks, 256, 0, st>>>(c.a0, c.a1, c.sig_len, c.n, c.stride, f->cfg.padding, (int*)f->maxlen.p);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
+            int h = 0;
+            CUDA_TRY(cudaMemcpyAsync(&h, f->maxlen.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cap64 = h;
         } else {
             cap64 = c.stride;
         }
@@ -304,6 +318,7 @@ void wdx_fp_destroy(wdx_fp* f) {
         if (f->ev_h2d[i]) cudaEventDestroy(f->ev_h2d[i]);
         if (f->ev_free[i]) cudaEventDestroy(f->ev_free[i]);
     }
+    f->maxlen.release();
     for (auto& e : f->tev) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);

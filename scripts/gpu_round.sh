@@ -32,12 +32,16 @@ cat $OUT/${TAG}_bench_ref.json
 
 echo "== ncu launch list (same bench command, smaller step count; times are cold-cache/serialised)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-modes \
+    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-modes --no-extras \
     > $OUT/${TAG}_bench_under_ncu.log 2>&1
 tail -2 $OUT/${TAG}_launches.csv
 
 echo "== ncu --set full on the fused kernel (1 M reads so one replay pass stays short)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dtw_svc_kernel -s 2 -c 2 \
     -o $OUT/${TAG}_prof -f python bench.py --steps 1 --warmup 3 --reads-per-gpu 1000000 --mode fast \
-    --no-cpu-baseline --no-extra-modes > $OUT/${TAG}_prof.log 2>&1
+    --no-cpu-baseline --no-extra-modes --no-extras > $OUT/${TAG}_prof.log 2>&1
 ls -la $OUT | tail -20
+echo "== ncu --set full on the fingerprint kernel"
+FP_REPS=4 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fingerprint_kernel -s 1 -c 1 \
+    -o $OUT/${TAG}_fpprof -f python scripts/fp_probe.py > $OUT/${TAG}_fpprof.log 2>&1
+tail -2 $OUT/${TAG}_fpprof.log

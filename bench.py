@@ -101,7 +101,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_arm(params, threads, seconds_target, steps=1, warmup=0):
+def cpu_arm(params, threads, seconds_target, steps=1, warmup=0, want_outputs=False):
     """The reference's CPU path as restated in oracle/ (kind "port"): production
     style minibatches of 1000 reads over `threads` single-threaded workers."""
     from oracle import wdx_oracle as o
@@ -119,8 +119,10 @@ def cpu_arm(params, threads, seconds_target, steps=1, warmup=0):
         o.predict_threaded(params, X[: max(threads, n // 8)], threads, mb)
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.predict_threaded(params, X, threads, mb)
+        res = o.predict_threaded(params, X, threads, mb)
     dt = (time.perf_counter() - t0) / steps
+    if want_outputs:
+        return n / dt, n, dt, X, res
     return n / dt, n, dt
 
 
@@ -237,6 +239,36 @@ def fingerprint_stage(params_small, local, stream, seconds_cpu=6.0):
     return out
 
 
+def config2_wdx4(params4, local, stream, n):
+    """BASELINE.json configs[1]: WDX4 on n synthetic fingerprints, 1 B200, EXACT_F64 vs FAST_F32 (and GUARDED);
+    label identity of GUARDED vs EXACT over the whole set."""
+    import torch
+    from warpdemux_b200 import _lib
+    from warpdemux_b200.device_model import DeviceModel
+
+    X = torch.from_numpy(synth_host(params4, n, seed=4242)).cuda()
+    dm = DeviceModel(params4, local)
+    dm.enable_timing(True)
+    labs, out = {}, {"model": "WDX4_rna004_v1_0", "reads": n}
+    cells = params4.n_sv * params4.band_cells()
+    for mode in ("exact", "fast", "guarded"):
+        lab = torch.empty(n, dtype=torch.int64, device="cuda")
+        dm.predict_raw(X, min(n, 1 << 20), _lib.WDX_F64, _lib.MODES[mode], lab, None, None, None, None, stream=stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dm.predict_raw(X, n, _lib.WDX_F64, _lib.MODES[mode], lab, None, None, None, None, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        labs[mode] = lab
+        out[mode] = {"reads_per_s": n / (ms * 1e-3), "gcups": n * cells / (ms * 1e-3) / 1e9, "ms": ms}
+    out["label_mismatches_fast_vs_exact"] = int((labs["fast"] != labs["exact"]).sum().item())
+    out["label_mismatches_guarded_vs_exact"] = int((labs["guarded"] != labs["exact"]).sum().item())
+    dm.close()
+    return out
+
+
 def streaming_latency(mdl, params, batches=(1, 8, 64, 512), iters=300):
     """BASELINE.json configs[4]: per-batch latency of DTW_SVM.predict on host
     arrays (H2D + kernels + D2H), model resident, batches of a 512-channel
@@ -284,6 +316,17 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # Rank 0 prints exactly ONE line on stdout: anything a library writes there (e.g. the NCCL
+    # version banner) is sent to stderr instead by pointing fd 1 at fd 2 until the JSON line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     import torch
     import torch.distributed as dist
 
@@ -421,8 +464,12 @@ def run_ours(args):
         try:
             from warpdemux_b200 import model_io as _mio
             small = _mio.load_npz(os.path.join(ROOT, "tests", "golden", "models", "WDX4_rna004_v1_0.npz"))
-            del X_dev, prob_d  # make room for the signal batch
+            del X_dev, prob_d  # make room
             torch.cuda.empty_cache()
+            extras["wdx4_10M_exact_vs_fast"] = config2_wdx4(small, local, stream, args.config2_reads)
+        except Exception as e:  # noqa: BLE001
+            extras["wdx4_10M_exact_vs_fast"] = {"error": repr(e)}
+        try:
             extras["fingerprint_stage"] = fingerprint_stage(small, local, stream)
         except Exception as e:  # noqa: BLE001
             extras["fingerprint_stage"] = {"error": repr(e)}
@@ -481,10 +528,14 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rps, ns, dt = cpu_arm(params, threads, 15.0)
+        rps, ns, dt, Xc, (cpu_pred, cpu_prob, cpu_conf) = cpu_arm(params, threads, 15.0, want_outputs=True)
+        # the same reads through the GPU path: the parity statement that goes with the speed-up
+        gpu_pred, gpu_prob = mdl.predict(Xc, nproc=1)
         cpu = {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
                "sample": f"{ns} S1 reads of the same workload, minibatches of <=1000 over {threads} single-threaded "
-                         f"workers, {dt:.1f} s (oracle/wdx_oracle.c)"}
+                         f"workers, {dt:.1f} s (oracle/wdx_oracle.c)",
+               "gpu_label_mismatches_on_sample": int((gpu_pred != cpu_pred).sum()),
+               "gpu_max_abs_prob_diff_on_sample": float(np.abs(gpu_prob - cpu_prob).max())}
 
     line = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -497,8 +548,8 @@ def run_ours(args):
                    "cache": f"input {n * params.L * 8 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
         "gcups": value * cells_per_read / 1e9,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n * params.L * 8),
-                "d2h_bytes_per_step": int(n * (8 + 8 + 8 * k + 1)), "steps": e2e_steps,
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n_total * params.L * 8),
+                "d2h_bytes_per_step": int(n_total * (8 + 8 + 8 * k + 1)), "steps": e2e_steps,
                 "api": "DTW_SVM.predict(X_host, nproc=1) -> (y_pred, y_prob); pinned host input, "
                        "host perf_counter around the blocking calls, max over ranks",
                 "labels_equal_device_run": e2e_match},
@@ -509,7 +560,7 @@ def run_ours(args):
         "label_histogram": {str(int(a)): int(b) for a, b in zip(*np.unique(label_sample, return_counts=True))},
     }
     line.update(extras)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -525,6 +576,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-modes", dest="extra_modes", action="store_false")
+    ap.add_argument("--config2-reads", type=int, default=10_000_000)
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the secondary measurements (streaming latency, fingerprint stage)")
     args = ap.parse_args()

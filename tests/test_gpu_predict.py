@@ -254,3 +254,29 @@ def test_synthetic_model_shapes(models):
             diff = labels != want_pred
             assert diff.mean() < 0.01
         d.close()
+
+
+def test_fast_distances_tolerance_through_fused_kernel(models, dev_models):
+    """FAST_F32 distances as the fused kernel forms them (packed recurrence in offset form) stay
+    within 1e-5 relative of the float64 oracle for ordinary reads AND for reads (almost) identical
+    to a support vector, where the kernel redoes the pair with the plain recurrence."""
+    from oracle import wdx_oracle as o
+
+    for name in ("WDX4_rna004_v1_0", "WDX10_rna004_v1_0"):
+        m, d = models[name], dev_models[name]
+        rng = np.random.default_rng(5)
+        parts = [synth_fingerprints(m.sv, 200, seed=21)]
+        for sigma in (0.0, 1e-4, 1e-3, 1e-2, 5e-2, 0.15):
+            idx = rng.integers(0, m.n_sv, 60)
+            parts.append(m.sv[idx] + sigma * rng.standard_normal((60, m.L)))
+        X = np.vstack(parts)
+        # inputs representable in float32, so that the comparison isolates the recurrence
+        X = X.astype(np.float32).astype(np.float64)
+        want = o.dtw_matrix(X, m.sv.astype(np.float32).astype(np.float64), m.window, m.penalty)
+        _, _, _, _, dist = d.predict(X, mode="fast", want_dist=True)
+        got = dist.astype(np.float64)
+        ref32 = want.astype(np.float32).astype(np.float64)
+        rel = np.abs(got - ref32) / np.maximum(ref32, 1e-30)
+        rel[ref32 == 0] = np.where(got[ref32 == 0] == 0, 0.0, np.inf)
+        assert rel.max() <= FAST_RTOL + 1.2e-7, (name, rel.max())   # + one float32 rounding of the stored distance
+        assert (want < 0.25).sum() > 50                               # the near-zero branch was exercised

@@ -366,6 +366,34 @@ struct FinishArgs {
     uint8_t flag_or;       // bits OR-ed into flags (WDX_FLAG_RECOMPUTED on the exact re-run)
 };
 
+// Small batches cut the support-vector list into ranges (grid.y) so that the GPU is filled; this
+// kernel folds the per-range partial decision sums into range 0's plane — one thread per
+// (pair, read), ranges in ascending order — so that the finishing kernel (one thread per read)
+// does not walk n_splits x n_pairs dependent loads on its own.
+__global__ void __launch_bounds__(256) svc_fold_splits_kernel(const __grid_constant__ ModelDev m, double* __restrict__ part,
+                                                              int64_t part_stride, int n_splits, int sv_per_split,
+                                                              const int* __restrict__ n_idx, int64_t n) {
+    const int64_t n_eff = n_idx ? min((int64_t)(*n_idx), n) : n;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pi = blockIdx.y;
+    if (slot >= n_eff) return;
+    int i = 0, rem = pi;  // pair index -> (i, j), i < j
+    while (rem >= m.k - 1 - i) {
+        rem -= m.k - 1 - i;
+        i++;
+    }
+    const int j = i + 1 + rem;
+    double sum = 0.0;
+#pragma unroll 8
+    for (int s = 0; s < n_splits; s++) {
+        const int b = s * sv_per_split, e = min(m.n_sv, b + sv_per_split);
+        const bool live = b < e && (range_touches(m, b, e, i) || range_touches(m, b, e, j));
+        const double v = live ? part[((size_t)s * m.n_pairs + pi) * part_stride + slot] : 0.0;
+        if (live) sum += v;
+    }
+    part[(size_t)pi * part_stride + slot] = sum;
+}
+
 __global__ void __launch_bounds__(128) svc_finish_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ FinishArgs a) {
     const int64_t n_eff = a.n_idx ? min((int64_t)(*a.n_idx), a.n) : a.n;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

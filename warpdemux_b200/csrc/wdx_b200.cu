@@ -214,7 +214,17 @@ int launch_fused(wdx_model* m, bool exact, const PredictArgs& pa_in, int64_t gri
     return WDX_OK;
 }
 
-int launch_finish(wdx_model* m, const FinishArgs& fa, int64_t grid_rows, cudaStream_t st) {
+int launch_finish(wdx_model* m, const FinishArgs& fa_in, int64_t grid_rows, cudaStream_t st) {
+    FinishArgs fa = fa_in;
+    if (fa.n_splits > 1) {  // fold the SV ranges first (parallel over pairs x reads), then finish as one range
+        dim3 grid((unsigned)((grid_rows + 255) / 256), (unsigned)m->n_pairs);
+        svc_fold_splits_kernel<<<grid, 256, 0, st>>>(m->dev, const_cast<double*>(fa.part), fa.part_stride, fa.n_splits,
+                                                    fa.sv_per_split, fa.n_idx, fa.n);
+        CUDA_TRY(cudaGetLastError());
+        g_launches++;
+        fa.n_splits = 1;
+        fa.sv_per_split = m->n_sv;
+    }
     const unsigned blocks = (unsigned)((grid_rows + 127) / 128);
     svc_finish_kernel<<<blocks, 128, 0, st>>>(m->dev, fa);
     CUDA_TRY(cudaGetLastError());

@@ -3,6 +3,7 @@
 // the fused minibatch step fingerprint -> DTW+SVC with the fingerprints kept on
 // the device.  No CPU compute path.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -49,6 +50,11 @@ struct FpCall {
     cudaStream_t user_stream;
 };
 
+bool zero_copy_disabled() {
+    static const bool off = [] { const char* e = getenv("WDX_FP_NO_ZERO_COPY"); return e && e[0] == '1'; }();
+    return off;
+}
+
 int launch_fp(wdx_fp* f, const FpArgs& fa, cudaStream_t st) {
     const size_t smem = fingerprint_smem_bytes(fa.cap);
     if ((int)smem > f->smem_max) return fail(WDX_ERR_UNSUPPORTED, "adapter slice of %d samples needs %zu B of shared memory, device allows %d", fa.cap, smem, f->smem_max);
@@ -94,7 +100,19 @@ int run(wdx_fp* f, const FpCall& c) {
     cudaStream_t st = c.user_stream ? c.user_stream : f->stream;
 
     const int k = c.m ? c.m->k : 0;
-    const int sig_kind = mem_kind(c.signals);
+    // Signals in PINNED host memory are read by the kernel straight over PCIe (zero copy): each CTA
+    // touches only its adapter slice, so about half the bytes of the NaN-padded rows never move.
+    const float* signals = c.signals;
+    int sig_kind = mem_kind(c.signals);
+    if (sig_kind == 1 && !zero_copy_disabled()) {
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, const_cast<float*>(c.signals), 0) == cudaSuccess && dptr) {
+            signals = (const float*)dptr;
+            sig_kind = 2;
+        } else {
+            cudaGetLastError();
+        }
+    }
     const bool sig_dev = sig_kind == 2;
     const bool len_dev = c.sig_len && mem_kind(c.sig_len) == 2;
     const bool a0_dev = mem_kind(c.a0) == 2, a1_dev = mem_kind(c.a1) == 2;
@@ -172,7 +190,7 @@ int run(wdx_fp* f, const FpCall& c) {
         const int64_t r0 = ci * chunk, cn = std::min(chunk, c.n - r0);
         CUDA_TRY(cudaEventSynchronize(f->ev_free[b]));  // the chunk that used these buffers is finished
         if (!sig_dev)
-            CUDA_TRY(cudaMemcpyAsync(f->sig[b].p, c.signals + (size_t)r0 * c.stride, (size_t)cn * c.stride * 4,
+            CUDA_TRY(cudaMemcpyAsync(f->sig[b].p, signals + (size_t)r0 * c.stride, (size_t)cn * c.stride * 4,
                                      cudaMemcpyHostToDevice, f->copy_stream));
         if (c.sig_len && !len_dev)
             CUDA_TRY(cudaMemcpyAsync(f->len[b].p, c.sig_len + r0, (size_t)cn * 4, cudaMemcpyHostToDevice, f->copy_stream));
@@ -193,7 +211,7 @@ int run(wdx_fp* f, const FpCall& c) {
         const int64_t r0 = ci * chunk, cn = std::min(chunk, c.n - r0);
         if (stage_any) CUDA_TRY(cudaStreamWaitEvent(st, f->ev_h2d[b], 0));
         FpArgs fa{};
-        float* sig_d = sig_dev ? const_cast<float*>(c.signals) + (size_t)r0 * c.stride : (float*)f->sig[b].p;
+        float* sig_d = sig_dev ? const_cast<float*>(signals) + (size_t)r0 * c.stride : (float*)f->sig[b].p;
         fa.signals = sig_d;
         fa.signals_mut = c.clip_in_place ? sig_d : nullptr;
         fa.stride = c.stride;

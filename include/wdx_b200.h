@@ -161,7 +161,7 @@ enum {
     WDX_FP_OK = 0,
     WDX_FP_FAIL_SEGMENTATION = 1, /* "event segmentation failed" (sig_proc.py:537-544): < num_events peaks */
     WDX_FP_FAIL_DETECT = 2,       /* detect_ok[r] == 0 (sig_proc.py:400-407) */
-    WDX_FP_FAIL_NORMALIZE = 3,    /* reserved: "segment normalization failed" (sig_proc.py:553-560) */
+    WDX_FP_FAIL_NORMALIZE = 3,    /* "segment normalization failed" (sig_proc.py:553-560): NaN inside the adapter slice */
     WDX_FP_FAIL_TOO_LONG = 4      /* adapter slice longer than the shared-memory limit */
 };
 

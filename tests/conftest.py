@@ -56,3 +56,9 @@ def golden_predict():
 def golden_fingerprint():
     with np.load(os.path.join(GOLD, "fingerprint_rna004.npz")) as z:
         return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden_real():
+    with np.load(os.path.join(GOLD, "real_rna004_WDX4.npz")) as z:
+        return {k: z[k] for k in z.files}

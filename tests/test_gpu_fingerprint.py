@@ -61,13 +61,20 @@ def test_sig_len_detect_ok_and_row_end(fp):
     dense = np.where(np.isnan(sig), np.float32(77.0), sig)
     a1 = a1.copy()
     a1[5] = 10**7
+    a1[6] = lens[6] - 30          # the padded slice ends 70 samples into the NaN padding
     ok = np.ones(40, dtype=np.uint8)
     ok[[3, 9]] = 0
-    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1)
+    # explicit lengths = "signal without NaNs" (file_proc.py:194): the slice stops at the read end
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1, padded_rows=False)
     status[[3, 9]] = 2
+    assert status[5] == 0 and status[6] == 0
     b = fp.extract(dense, a0, a1, sig_len=lens, detect_ok=ok)
     _same(b, status, fpt, dwell, stats)
-    # same through NaN padding alone
+    # NaN-padded rows handed over whole, as the reference's worker does: a slice that reaches into
+    # the padding fails with "segment normalization failed" (status 3)
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1, padded_rows=True)
+    status[[3, 9]] = 2
+    assert status[5] == 3 and status[6] == 3
     b2 = fp.extract(sig, a0, a1, detect_ok=ok)
     _same(b2, status, fpt, dwell, stats)
 

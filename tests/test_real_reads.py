@@ -1,0 +1,117 @@
+"""BASELINE.json configs[0]: real reads of the reference's own test file
+(test_data/demux/4000_rna004.pod5), boundaries from the reference's own adapter detection,
+expected fingerprints / barcode calls from the reference's own sig_proc and DTW_SVM
+(tests/golden/real_rna004_WDX4.npz, oracle/make_golden_real.py).  CPU: the oracle against that
+fixture.  GPU: the CUDA path against it, through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from wdx_testutil import oracle_fingerprints, real_fixture_rows
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(g):
+    cfg = json.loads(str(g["cfg"]))
+    cfg.pop("model")
+    return cfg
+
+
+def test_oracle_matches_reference_on_real_reads(golden_real, models):
+    from oracle import wdx_oracle as o
+
+    g = golden_real
+    rows = real_fixture_rows(g)
+    ok_det = g["detect_ok"].astype(bool)
+    assert ok_det.sum() >= 450
+    status, fpt, dwell, stats = oracle_fingerprints(rows[ok_det], g["adapter_start"][ok_det], g["adapter_end"][ok_det],
+                                                    **_cfg(g))
+    assert np.array_equal(status, g["status"][ok_det])
+    good = status == 0
+    assert np.array_equal(fpt[good], g["fpt"][ok_det][good]), "fingerprints of real reads must be bit-identical"
+    assert np.array_equal(dwell[good], g["dwell"][ok_det][good])
+    assert np.array_equal(stats[good], g["stats"][ok_det][good])
+    m = models["WDX4_rna004_v1_0"]
+    pred, prob, conf, _ = o.predict(m, g["fpt"][g["status"] == 0])
+    assert np.array_equal(pred, g["y_pred"])
+    assert np.abs(prob - g["y_prob"]).max() < 2e-6
+    assert (pred != -1).mean() > 0.6          # real barcodes are being called, not noise
+
+
+@pytest.mark.gpu
+def test_gpu_path_matches_reference_on_real_reads(golden_real, models):
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import Fingerprinter, FingerprintConfig
+
+    g = golden_real
+    rows = real_fixture_rows(g)
+    cfg = _cfg(g)
+    fp = Fingerprinter(FingerprintConfig(**cfg), device=0)
+    b = fp.extract(rows, g["adapter_start"], g["adapter_end"], detect_ok=g["detect_ok"])
+    assert np.array_equal(b.status, g["status"])
+    good = g["status"] == 0
+    assert np.array_equal(b.fpt[good], g["fpt"][good])
+    assert np.array_equal(b.dwell[good], g["dwell"][good])
+    assert np.array_equal(b.stats[good], g["stats"][good])
+    # barcode calls: separate predict and the fused signals -> calls step
+    for mode in ("exact", "guarded"):
+        mdl = DTW_SVM(models["WDX4_rna004_v1_0"], device=0, mode=mode)
+        y_pred, y_prob = mdl.predict(b.fpt[good], nproc=1)
+        assert np.array_equal(y_pred, g["y_pred"]), mode
+        assert np.abs(y_prob - g["y_prob"]).max() < (2e-6 if mode == "exact" else 1e-3)
+        labels, prob, conf, status = fp.extract_and_predict(mdl, rows, g["adapter_start"], g["adapter_end"],
+                                                            detect_ok=g["detect_ok"])
+        assert np.array_equal(status, g["status"])
+        assert np.array_equal(labels[good], g["y_pred"]) and (labels[~good] == -1).all()
+    fp.close()
+
+
+def test_pod5_reader_self_check():
+    """Minimal pod5 reader (warpdemux_b200/io/pod5_min.py) on a synthetic VBZ chunk: the decoder
+    inverts an independently written encoder (zig-zag delta -> 1/2-byte stream with key bits -> zstd)."""
+    import pyarrow as pa
+
+    from warpdemux_b200.io.pod5_min import decode_vbz
+
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.integers(-40, 40, 5000)).astype(np.int16)
+    x[100] = 3000
+    x[101] = -2000
+    d = np.diff(np.concatenate([[0], x.astype(np.int32)])).astype(np.int32)
+    d = ((d + 32768) % 65536 - 32768).astype(np.int32)                   # int16 wrap-around of the deltas
+    u = ((d << 1) ^ (d >> 31)).astype(np.uint32) & 0xFFFF
+    keys = (u > 255).astype(np.uint8)
+    data = bytearray()
+    for v, k in zip(u.tolist(), keys.tolist()):
+        data.append(v & 255)
+        if k:
+            data.append(v >> 8)
+    raw = np.packbits(keys, bitorder="little").tobytes() + bytes(data)
+    chunk = pa.Codec("zstd").compress(raw, asbytes=True)
+    assert np.array_equal(decode_vbz(chunk, x.size), x)
+    assert decode_vbz(pa.Codec("zstd").compress(b"", asbytes=True), 0).size == 0
+
+
+def test_pod5_reader_on_reference_file_if_present(golden_real):
+    path = "/root/reference/test_data/demux/4000_rna004.pod5"
+    if not os.path.exists(path):
+        pytest.skip("reference test data not present (GPU box)")
+    from warpdemux_b200.io.pod5_min import Pod5File
+
+    f = Pod5File(path)
+    assert len(f) == 4000
+    g = golden_real
+    off = g["adc_offsets"]
+    for i, r in enumerate(f.reads()):
+        if i >= 25:
+            break
+        assert r.read_id == str(g["read_ids"][i])
+        s = r.signal
+        assert s.size == r.num_samples and s.dtype == np.int16
+        a = int(g["slice_start"][i])
+        stored = g["adc"][off[i]:off[i + 1]]
+        assert np.array_equal(s[a:a + stored.size], stored)
+        assert r.signal_pa.dtype == np.float32

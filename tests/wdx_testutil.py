@@ -42,8 +42,11 @@ def synth_adapter_signals(n, seed=2, width=9000, short_frac=0.0):
     return sig, a0, a1
 
 
-def oracle_fingerprints(sig, a0, a1, **cfg):
-    """Row-by-row CPU oracle over a NaN-padded minibatch -> (status, fpt, dwell, stats)."""
+def oracle_fingerprints(sig, a0, a1, padded_rows=True, **cfg):
+    """Row-by-row CPU oracle over a NaN-padded minibatch -> (status, fpt, dwell, stats).
+    padded_rows=True hands the whole padded row to the oracle, as the reference's worker does
+    (file_proc.py:418-428); False strips the padding first (the "signal without NaNs" contract of
+    barcode_fpt_wrapper, file_proc.py:194 — what an explicit `sig_len` means on the GPU path)."""
     from oracle import wdx_oracle as o
 
     n = sig.shape[0]
@@ -55,10 +58,25 @@ def oracle_fingerprints(sig, a0, a1, **cfg):
     keys = ["adapter_dt_med", "adapter_dt_mad", "adapter_event_mean", "adapter_event_std", "adapter_event_med",
             "adapter_event_mad"]
     for r in range(n):
-        valid = sig[r][~np.isnan(sig[r])]
-        st, f, d, s = o.fingerprint(valid, int(a0[r]), int(a1[r]), **cfg)
+        row = sig[r] if padded_rows else sig[r][~np.isnan(sig[r])]
+        with np.errstate(all="ignore"):
+            st, f, d, s = o.fingerprint(row, int(a0[r]), int(a1[r]), **cfg)
         status[r] = st
         if st == 0:
             fpt[r], dwell[r] = f, d
             stats[r] = [s[k] for k in keys]
     return status, fpt, dwell, stats
+
+
+def real_fixture_rows(g):
+    """Rebuild the float32 pA minibatch rows of tests/golden/real_rna004_WDX4.npz
+    (oracle/make_golden_real.py): NaN everywhere except the stored adapter slice;
+    pA = (adc + calibration_offset) * calibration_scale in float32."""
+    n, m = g["adapter_start"].size, int(g["preload_size"])
+    rows = np.full((n, m), np.nan, dtype=np.float32)
+    off = g["adc_offsets"]
+    for r in range(n):
+        adc = g["adc"][off[r]:off[r + 1]]
+        s = int(g["slice_start"][r])
+        rows[r, s:s + adc.size] = (adc.astype(np.float32) + g["calibration_offset"][r]) * g["calibration_scale"][r]
+    return rows

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     }
 
     // ---- extract_adapter (sig_proc.py:382-391) --------------------------------
-    const int64_t len_row = a.sig_len ? (int64_t)a.sig_len[read] : a.stride;
+    const int64_t len_row = a.sig_len ? min((int64_t)a.sig_len[read], a.stride) : a.stride;
     int64_t start = a.adapter_start[read] - c.padding;
     if (start < 0) start = 0;
     int64_t stop = a.adapter_end[read] + c.padding;
@@ -474,13 +474,19 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         }
     }
     __syncthreads();
-    const bool trimmed = s.first_nan < n;  // NaN padding of the minibatch row ends the signal (file_proc.py:333-354)
+    // NaN padding inside the slice (a read that ends less than `padding` samples after its adapter):
+    // the reference hands the padded minibatch row to detect_results_to_fpt (file_proc.py:418-428), so
+    // the slice keeps its full length for the segmentation parameters, medians ignore the NaNs
+    // (np.nanmedian), scores next to the NaNs are NaN and never peaks, and the last event mean is NaN:
+    // the read fails with "segment normalization failed" unless it already failed for too few peaks.
+    const int n_total = n;
+    const bool trimmed = s.first_nan < n;
     n = min(n, s.first_nan);
 
     // ---- segmentation parameters (sig_proc.py:526-533; Python round = half to even)
-    const int m_obs = min(c.min_obs_per_base, py_round((double)n / (double)c.num_events / 2.0));
-    const int w = min(c.running_stat_width, py_round((double)n / (double)c.num_events));
-    const int nc = n - 2 * w;  // number of t-test positions
+    const int m_obs = min(c.min_obs_per_base, py_round((double)n_total / (double)c.num_events / 2.0));
+    const int w = min(c.running_stat_width, py_round((double)n_total / (double)c.num_events));
+    const int nc = n - 2 * w;  // number of finite t-test positions
     if (m_obs < 1 || w < 1 || nc < 3) {  // find_peaks(distance < 1) raises -> the reference reports a failed read
         fail(FP_FAIL_SEGMENTATION);
         return;
@@ -628,6 +634,10 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     const int P = (int)total;
     if (P < c.num_events) {  // sig_proc.py:185-186 -> "event segmentation failed"
         fail(FP_FAIL_SEGMENTATION);
+        return;
+    }
+    if (trimmed) {  // the last event would reach into the NaN padding (sig_proc.py:553-560)
+        fail(FP_FAIL_NORMALIZE);
         return;
     }
 
@@ -780,7 +790,7 @@ __global__ void max_slice_kernel(const int64_t* __restrict__ a0, const int64_t* 
                                  int64_t n, int64_t stride, int padding, int* __restrict__ out) {
     int best = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t len_row = sig_len ? (int64_t)sig_len[r] : stride;
+        const int64_t len_row = sig_len ? min((int64_t)sig_len[r], stride) : stride;
         int64_t b = a0[r] - padding, e = a1[r] + padding;
         if (b < 0) b = 0;
         if (e > len_row) e = len_row;

@@ -284,11 +284,13 @@ def _read_result(b: FingerprintBatch, r: int, dr) -> ReadResult:
 
 
 def batch_detect_results_to_fpt(signals: np.ndarray, spc, detect_results: Sequence[Any],
-                                full_signal_lens: Optional[Sequence[int]] = None,
+                                sig_len: Optional[Sequence[int]] = None,
                                 clip_in_place: bool = False) -> List[ReadResult]:
     """Batched `detect_results_to_fpt`: signals float32 [n, m] (NaN-padded rows
-    as `file_proc.yield_signals_from_pod5` builds them, file_proc.py:333-354),
-    one DetectResults per row -> one ReadResult per row."""
+    as `file_proc.yield_signals_from_pod5` builds them, file_proc.py:227-279),
+    one DetectResults per row -> one ReadResult per row.  Like the reference's
+    worker (file_proc.py:418-428) each padded row IS the signal; pass `sig_len`
+    (samples per row) only to get the "signal without NaNs" behaviour instead."""
     fp = _fingerprinter_for(spc)
     n = len(detect_results)
     ok = np.array([bool(d.success) for d in detect_results], dtype=np.uint8)
@@ -301,7 +303,7 @@ def batch_detect_results_to_fpt(signals: np.ndarray, spc, detect_results: Sequen
         signals = signals.reshape(1, -1)
     if signals.shape[0] != n:
         raise ValueError("one DetectResults per signal row is required")
-    b = fp.extract(signals, a0, a1, sig_len=full_signal_lens, detect_ok=ok, clip_in_place=clip_in_place)
+    b = fp.extract(signals, a0, a1, sig_len=sig_len, detect_ok=ok, clip_in_place=clip_in_place)
     return [_read_result(b, r, detect_results[r]) for r in range(n)]
 
 

@@ -200,6 +200,74 @@ int wdx_fp_predict(wdx_fp* f, wdx_model* m, const float* signals, int64_t n, int
 int wdx_fp_enable_timing(wdx_fp* f, int on);
 int wdx_fp_last_kernel_ms(wdx_fp* f, double* ms, int* launches);
 
+/* ---- adapter / poly(A) boundary CNN ("next" row: the step before the fingerprint stage) -------------
+ * Replaces adapted.detect.cnn.cnn_detect (warpdemux/adapted/adapted/detect/cnn.py:165-183) for a whole
+ * minibatch: prepare_data (cnn.py:71-85: zero-padded block-mean downscaling, downscale.py:4-41; float32
+ * nanmedian / MAD normalisation; NaN -> -5), the BoundariesCNN forward (cnn.py:16-52) and cnn_predict
+ * (cnn.py:104-162: argmax of channel 0 over the adapter range, masked argmax of channel 1, scipy
+ * find_peaks(distance=5) on the FLATTENED batch, top polya_cand_k peaks per read, including the
+ * reference's row shift when a read has no peak).
+ *
+ * Weights are the tensors of the reference's torch state dict (adapted/models/rna004_130bps@v0.2.4.pth),
+ * float32, torch layouts, HOST pointers (copied):
+ *   w0 [64,1,7] b0 [64]   Conv1d(1,64,7,stride 3,padding 3)
+ *   w1 [64,64,7] b1 [64]  Conv1d(64,64,7,padding 3)
+ *   w2 [64,64,7] b2 [64]  Conv1d(64,64,7,padding 3)
+ *   w3 [64,2,7] b3 [2]    ConvTranspose1d(64,2,7,stride 3,padding 3)
+ * Only this architecture (channels 64, kernel 7) is implemented. */
+typedef struct {
+    int32_t min_obs_adapter;   /* core.min_obs_adapter            (1000) */
+    int32_t max_obs_adapter;   /* core.max_obs_adapter            (6500) */
+    int32_t downscale_factor;  /* core.downscale_factor           (10), <= 128 */
+    int32_t polya_cand_k;      /* cnn_boundaries.polya_cand_k     (5 for WarpDemuX, 10 for ADAPTed), 2..16 */
+    int32_t channels;          /* 64 */
+    int32_t kernel_size;       /* 7  */
+} wdx_cnn_config;
+
+/* Arithmetic of the two 64->64 convolutions (97 % of the work):
+ *  EXACT_F32   float32 FMA on the CUDA cores (the reference computes in float32 on the CPU; results
+ *              agree to summation order).
+ *  FAST_TC     tcgen05 tensor cores: activations and weights split into fp16 high + low parts, three
+ *              products per term accumulated in float32 (error ~2^-21 relative, float32-class).
+ *  GUARDED     FAST_TC, then every read whose argmax decisions have a top-2 margin below the guard, or
+ *              whose activations left the fp16 range, is recomputed in EXACT_F32. */
+enum { WDX_CNN_EXACT_F32 = 0, WDX_CNN_FAST_TC = 1, WDX_CNN_GUARDED = 2 };
+
+/* per-read bits written to `flags` */
+enum {
+    WDX_CNN_FLAG_NONFINITE = 1,  /* a score was NaN/inf (degenerate input, e.g. MAD = 0) */
+    WDX_CNN_FLAG_RECOMPUTED = 2, /* GUARDED: redone in EXACT_F32 */
+    WDX_CNN_FLAG_CHAIN = 4,      /* peak-distance suppression depended on samples beyond the 64-sample halo
+                                    around the read; candidates of this read may differ from scipy's */
+    WDX_CNN_FLAG_RANGE = 8       /* FAST_TC: an activation exceeded the fp16 range (re-run in EXACT_F32) */
+};
+
+typedef struct wdx_cnn wdx_cnn;
+
+int wdx_cnn_create(const wdx_cnn_config* cfg, const float* w0, const float* b0, const float* w1, const float* b1,
+                   const float* w2, const float* b2, const float* w3, const float* b3, int device, wdx_cnn** out);
+void wdx_cnn_destroy(wdx_cnn* c);
+
+/*   signals [n, stride] float32 calibrated pA rows, NaN padded (the reference's minibatch, file_proc.py:241-262)
+ *   preds   [n, 1 + polya_cand_k] int64: adapter end, poly(A) end candidates (samples; 0 = none)   (required)
+ *   scores  [n, 2, To] float32 raw CNN output, To = 3*((T-1)/3+1)-2, T = ceil((stride-min_obs_adapter)/factor)  (or NULL)
+ *   flags   [n] uint8 WDX_CNN_FLAG_*                                                               (or NULL)
+ * Buffers may be host or device memory.  The whole call is ONE flattened batch for the peak search. */
+int wdx_cnn_detect(wdx_cnn* c, const float* signals, int64_t n, int64_t stride, int mode, int64_t* preds,
+                   float* scores, uint8_t* flags, void* stream);
+/* prepare_data alone (cnn.py:71-85): x [n, T] float32, the CNN input (bit-identical to the numpy chain). */
+int wdx_cnn_prepare(wdx_cnn* c, const float* signals, int64_t n, int64_t stride, float* x, void* stream);
+/* cnn_predict alone (cnn.py:104-162) on given scores [n, 2, t_out] float32.  scaled == 0: downscaled positions as
+ * cnn_predict returns them; scaled != 0: samples, with the == min_obs_adapter -> 0 rule of cnn_detect (cnn.py:176-181). */
+int wdx_cnn_predict(wdx_cnn* c, const float* scores, int64_t n, int32_t t_out, int scaled, int64_t* preds, uint8_t* flags,
+                    void* stream);
+/* Length To of the score rows for a given row stride. */
+int wdx_cnn_score_len(wdx_cnn* c, int64_t stride, int32_t* t_in, int32_t* t_out);
+int wdx_cnn_set_guard(wdx_cnn* c, double guard);
+/* Device time (ms) of the convolution kernels in the last wdx_cnn_detect on this handle, and their launch count. */
+int wdx_cnn_enable_timing(wdx_cnn* c, int on);
+int wdx_cnn_last_kernel_ms(wdx_cnn* c, double* ms, int* launches);
+
 /* ---- introspection -------------------------------------------------------- */
 const char* wdx_last_error(void);
 int wdx_device_count(void);

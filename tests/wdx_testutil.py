@@ -80,3 +80,16 @@ def real_fixture_rows(g):
         s = int(g["slice_start"][r])
         rows[r, s:s + adc.size] = (adc.astype(np.float32) + g["calibration_offset"][r]) * g["calibration_scale"][r]
     return rows
+
+
+def cnn_golden_signals(gold):
+    """Rebuild the float32 NaN-padded minibatch rows of tests/golden/cnn_detect_rna004.npz
+    (pA = (adc + offset) * scale in float32, file_proc.py:241-262)."""
+    m = int(gold["preload_size"])
+    offs = gold["adc_offsets"]
+    n = len(offs) - 1
+    sig = np.full((n, m), np.nan, dtype=np.float32)
+    for i in range(n):
+        adc = gold["adc"][offs[i]:offs[i + 1]].astype(np.float32)
+        sig[i, : adc.size] = (adc + gold["calibration_offset"][i]) * gold["calibration_scale"][i]
+    return sig

@@ -23,6 +23,8 @@ EXPORTS = [
     "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
     "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_model_last_kernel_ms_mode", "wdx_version",
     "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms",
+    "wdx_cnn_create", "wdx_cnn_destroy", "wdx_cnn_detect", "wdx_cnn_prepare", "wdx_cnn_predict", "wdx_cnn_score_len", "wdx_cnn_set_guard", "wdx_cnn_enable_timing",
+    "wdx_cnn_last_kernel_ms",
 ]
 
 _lib = None
@@ -91,6 +93,24 @@ def load():
         L.wdx_fp_enable_timing.argtypes = [vp, i32]
         L.wdx_fp_last_kernel_ms.restype = i32
         L.wdx_fp_last_kernel_ms.argtypes = [vp, C.POINTER(f64), C.POINTER(i32)]
+        L.wdx_cnn_create.restype = i32
+        L.wdx_cnn_create.argtypes = [vp] + [vp] * 8 + [i32, C.POINTER(vp)]
+        L.wdx_cnn_destroy.restype = None
+        L.wdx_cnn_destroy.argtypes = [vp]
+        L.wdx_cnn_detect.restype = i32
+        L.wdx_cnn_detect.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
+        L.wdx_cnn_prepare.restype = i32
+        L.wdx_cnn_prepare.argtypes = [vp, vp, i64, i64, vp, vp]
+        L.wdx_cnn_predict.restype = i32
+        L.wdx_cnn_predict.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+        L.wdx_cnn_score_len.restype = i32
+        L.wdx_cnn_score_len.argtypes = [vp, i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.wdx_cnn_set_guard.restype = i32
+        L.wdx_cnn_set_guard.argtypes = [vp, f64]
+        L.wdx_cnn_enable_timing.restype = i32
+        L.wdx_cnn_enable_timing.argtypes = [vp, i32]
+        L.wdx_cnn_last_kernel_ms.restype = i32
+        L.wdx_cnn_last_kernel_ms.argtypes = [vp, C.POINTER(f64), C.POINTER(i32)]
         _lib = L
         return L
 

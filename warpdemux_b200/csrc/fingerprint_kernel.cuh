@@ -164,29 +164,29 @@ __device__ __forceinline__ double div_small_int(double x, double w, double r) {
     return __fma_rn(rem, r, q0);
 }
 
-// One t-test score (_c_segmentation.pyx:132-159) from the 2*W window samples at p.
+// Mean and sum of squared deviations of the W samples at p, in the reference's order
+// (_c_segmentation.pyx:133-149).  The statistics of window [pos+W, pos+2W) at position pos are
+// bit for bit those of window [pos', pos'+W) at pos' = pos + W (same operands, same sequential
+// order), so a thread that walks pos, pos+W, pos+2W, ... computes every window once.
 template <int W>
-__device__ __forceinline__ double ttest_score_fixed(const float* p, double wd, double wr) {
-    double x[2 * W];
+__device__ __forceinline__ void window_stat_fixed(const float* p, double wd, double wr, double& m, double& v) {
+    double x[W];
 #pragma unroll
-    for (int i = 0; i < 2 * W; i++) x[i] = (double)p[i];
-    double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;
+    for (int i = 0; i < W; i++) x[i] = (double)p[i];
+    m = 0.0;
 #pragma unroll
-    for (int i = 0; i < W; i++) m1 = __dadd_rn(m1, x[i]);
-    m1 = div_small_int(m1, wd, wr);
-#pragma unroll
-    for (int i = 0; i < W; i++) m2 = __dadd_rn(m2, x[W + i]);
-    m2 = div_small_int(m2, wd, wr);
+    for (int i = 0; i < W; i++) m = __dadd_rn(m, x[i]);
+    m = div_small_int(m, wd, wr);
+    v = 0.0;
 #pragma unroll
     for (int i = 0; i < W; i++) {
-        const double pd = __dsub_rn(x[i], m1);
-        var1 = __dadd_rn(var1, __dmul_rn(pd, pd));
+        const double pd = __dsub_rn(x[i], m);
+        v = __dadd_rn(v, __dmul_rn(pd, pd));
     }
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        const double pd = __dsub_rn(x[W + i], m2);
-        var2 = __dadd_rn(var2, __dmul_rn(pd, pd));
-    }
+}
+
+// One t-test score (_c_segmentation.pyx:151-156) from the statistics of its two windows.
+__device__ __forceinline__ double ttest_combine(double m1, double var1, double m2, double var2) {
     const double vs = __dadd_rn(var1, var2);
     if (vs == 0.0) return 0.0;
     const double num = (m1 > m2) ? __dsub_rn(m1, m2) : __dsub_rn(m2, m1);
@@ -366,8 +366,26 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     // ---- c_windowed_t_test (_c_segmentation.pyx:124-161), float64, reference order
     const double wd = (double)w;
     if (w == 12) {  // the capped width (every adapter of >= 1265 samples): unrolled, window in registers
+        // Positions r, r+12, r+24, ... share windows: a thread owns `seg_len` consecutive positions of one
+        // residue class r and carries the second window's statistics over as the next position's first.
         const double wr = 1.0 / 12.0;
-        for (int pos = tid; pos < nc; pos += FP_THREADS) score[pos] = ttest_score_fixed<12>(sig + pos, 12.0, wr);
+        const int chain_len = (nc + 11) / 12;
+        const int seg_len = (chain_len + FP_THREADS / 12 - 1) / (FP_THREADS / 12);
+        const int n_seg = (chain_len + seg_len - 1) / seg_len;  // <= FP_THREADS / 12: one item per thread
+        if (tid < 12 * n_seg) {
+            int pos = tid % 12 + 12 * seg_len * (tid / 12);
+            if (pos < nc) {
+                double m1, v1;
+                window_stat_fixed<12>(sig + pos, 12.0, wr, m1, v1);
+                for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
+                    double m2, v2;
+                    window_stat_fixed<12>(sig + pos + 12, 12.0, wr, m2, v2);
+                    score[pos] = ttest_combine(m1, v1, m2, v2);
+                    m1 = m2;
+                    v1 = v2;
+                }
+            }
+        }
     } else {
         for (int pos = tid; pos < nc; pos += FP_THREADS) {
             double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;

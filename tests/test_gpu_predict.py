@@ -75,6 +75,58 @@ def test_distance_matrix_generic_shapes(shape):
     assert np.allclose(fast, want, rtol=FAST_RTOL, atol=2e-6)
 
 
+# (L, window, penalty): strips of 4 / 8 / 16 columns per lane, one and several column chunks, windows
+# narrower than a strip, wider than a chunk, absent (0 = no window), and L at the chunk boundaries
+WAVEFRONT_SHAPES = [(57, 0, 0.1), (60, 9, 0.2), (64, 64, 0.0), (65, 15, 0.1), (65, 0, 0.1), (100, 30, 0.0), (128, 128, 0.3), (129, 0, 0.1), (130, 7, 0.1),
+                    (257, 1, 0.1), (300, 40, 0.05), (300, 0, 0.1), (530, 50, 0.1), (530, 0, 0.2), (700, 3, 0.1),
+                    (1024, 0, 0.1), (1500, 200, 0.1)]
+
+
+@pytest.mark.parametrize("shape", WAVEFRONT_SHAPES)
+def test_distance_matrix_wavefront_long_series(shape):
+    """Series longer than a register row (L > 64) take the warp-wide anti-diagonal wavefront
+    (dtw_wavefront.cuh): EXACT bit-identical to the oracle, FAST within 1e-5 relative."""
+    from oracle import wdx_oracle as o
+    from warpdemux_b200.device_model import distance_matrix
+
+    L, w, pen = shape
+    rng = np.random.default_rng(L * 1000 + w)
+    nX, nY = (23, 37) if L <= 600 else (5, 9)
+    X, Y = rng.standard_normal((nX, L)), rng.standard_normal((nY, L))
+    Y[0] = X[0]  # distance exactly 0
+    X[1, ::7] += 25.0  # spikes: large cell costs next to small ones
+    want = o.dtw_matrix(X, Y, w, pen)
+    got = distance_matrix(X, Y, w, pen, mode="exact", out_dtype=np.float64)
+    assert np.array_equal(got, want)
+    assert got[0, 0] == 0.0
+    got32 = distance_matrix(X, Y, w, pen, mode="exact", out_dtype=np.float32)
+    assert np.array_equal(got32, want.astype(np.float32))
+    fast = distance_matrix(X, Y, w, pen, mode="fast", out_dtype=np.float64)
+    assert np.allclose(fast, want, rtol=FAST_RTOL, atol=2e-6)
+
+
+def test_distance_matrix_wavefront_nonfinite_and_limits():
+    from oracle import wdx_oracle as o
+    from warpdemux_b200.device_model import distance_matrix
+
+    rng = np.random.default_rng(5)
+    L = 200
+    X, Y = rng.standard_normal((6, L)), rng.standard_normal((4, L))
+    X[2, 50] = np.nan
+    X[3, 10] = np.inf
+    Y[1, 199] = np.nan
+    want = o.dtw_matrix(X, Y, 25, 0.1)
+    got = distance_matrix(X, Y, 25, 0.1, mode="exact", out_dtype=np.float64)
+    assert np.array_equal(got, want, equal_nan=True)
+    # the same pair through both code paths (thread-per-pair for L <= 64, wavefront above): pad with a
+    # constant tail that adds zero cost along the diagonal
+    Xs, Ys = rng.standard_normal((9, 60)), rng.standard_normal((11, 60))
+    Xl, Yl = np.hstack([Xs, np.zeros((9, 40))]), np.hstack([Ys, np.zeros((11, 40))])
+    assert np.array_equal(distance_matrix(Xl, Yl, 0, 0.1, mode="exact", out_dtype=np.float64), o.dtw_matrix(Xl, Yl, 0, 0.1))
+    with pytest.raises(ValueError):
+        distance_matrix(np.zeros((1, 16385)), np.zeros((1, 16385)), 10, 0.1)
+
+
 def test_golden_predict_exact(models, dev_models, golden_predict):
     """Same inputs the reference's DTW_SVM.predict was run on (oracle/make_golden.py)."""
     for name, g in golden_predict.items():

@@ -16,6 +16,7 @@
 #include <new>
 #include <vector>
 
+#include "dtw_wavefront.cuh"
 #include "fused_kernels.cuh"
 #include "wdx_internal.cuh"
 
@@ -660,7 +661,7 @@ int wdx_distance_matrix_to(const double* X, int64_t nX, const double* Y, int64_t
                            double penalty, int mode, void* out, int out_dtype, int device, void* stream) {
     if (!X || !Y || !out) return fail(WDX_ERR_INVALID, "NULL argument");
     if (nX < 0 || nY < 0) return fail(WDX_ERR_INVALID, "negative size");
-    if (L < 1 || L > MAXL) return fail(WDX_ERR_INVALID, "L=%d outside [1,%d]", L, MAXL);
+    if (L < 1 || L > WF_MAX_L) return fail(WDX_ERR_INVALID, "L=%d outside [1,%d]", L, WF_MAX_L);
     if (out_dtype != WDX_F32 && out_dtype != WDX_F64) return fail(WDX_ERR_INVALID, "out_dtype=%d", out_dtype);
     if (mode != WDX_MODE_EXACT_F64 && mode != WDX_MODE_FAST_F32) return fail(WDX_ERR_INVALID, "mode=%d", mode);
     if (nX == 0 || nY == 0) return WDX_OK;
@@ -700,6 +701,60 @@ int wdx_distance_matrix_to(const double* X, int64_t nX, const double* Y, int64_t
     const int w_eff = (window <= 0 || window > L) ? L : window;
     const bool spec = (L == 25 && w_eff == 15);
     const bool exact = mode == WDX_MODE_EXACT_F64;
+    const double p2 = penalty * penalty;
+    // Series longer than a register row (L > MAXL) take the warp-wide anti-diagonal wavefront (dtw_wavefront.cuh);
+    // so do non-specialised shapes from L = 57: there the thread-per-pair kernel keeps its rows in local memory
+    // and is 2.3x slower (profiles/r01h_wavefront_probe.jsonl).  WDX_WAVEFRONT_MIN_L overrides (probing only).
+    int wf_min_l = 57;
+    if (const char* ev = getenv("WDX_WAVEFRONT_MIN_L")) wf_min_l = std::max(1, std::min(MAXL + 1, atoi(ev)));
+    if (L >= wf_min_l && !spec) {
+        // strip width C: the one with the fewest issue slots, ~7 (14 in float64) per cell plus the per-step
+        // shuffles and bookkeeping; 2 columns per lane only when one chunk of 64 columns covers the series
+        int best_c = 4;
+        double best_cost = 0;
+        for (int c : {2, 4, 8, 16}) {
+            if (c == 2 && L > 64) continue;
+            const int W = 32 * c;
+            double cost = 0;
+            for (int jb = 0; jb < L; jb += W) {
+                const int ib = std::max(0, jb - w_eff + 1), ie = std::min(L, jb + W + w_eff - 1);
+                cost += (double)(ie - ib + 31) * (c * (exact ? 14.0 : 7.0) + (exact ? 45.0 : 30.0));
+            }
+            if (best_cost == 0 || cost < best_cost) best_cost = cost, best_c = c;
+        }
+        const int n_chunks = (L + 32 * best_c - 1) / (32 * best_c);
+        const int64_t pairs = nX * nY;
+        const int64_t max_ctas = n_chunks > 1 ? 148 * 2 : 148 * 8;
+        const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>((pairs + WF_WARPS - 1) / WF_WARPS, max_ctas));
+        DevBuf be;
+        auto cleanup_wf = [&](int code) {
+            be.release();
+            return cleanup(code);
+        };
+        if (n_chunks > 1 && (rc = be.reserve((size_t)ctas * WF_WARPS * 2 * L * (exact ? 8 : 4)))) return cleanup_wf(rc);
+#define WDX_LAUNCH_WF(EX, CC, OT) \
+    dtw_wavefront_kernel<EX, CC, OT><<<ctas, WF_THREADS, 0, st>>>(Xd, nX, Yd, nY, L, w_eff, p2, (OT*)Od, be.p)
+#define WDX_LAUNCH_WF_C(EX, OT)                      \
+    do {                                             \
+        if (best_c == 2) WDX_LAUNCH_WF(EX, 2, OT);   \
+        else if (best_c == 4) WDX_LAUNCH_WF(EX, 4, OT); \
+        else if (best_c == 8) WDX_LAUNCH_WF(EX, 8, OT); \
+        else WDX_LAUNCH_WF(EX, 16, OT);              \
+    } while (0)
+        if (exact && out_dtype == WDX_F64) WDX_LAUNCH_WF_C(true, double);
+        else if (exact) WDX_LAUNCH_WF_C(true, float);
+        else if (out_dtype == WDX_F64) WDX_LAUNCH_WF_C(false, double);
+        else WDX_LAUNCH_WF_C(false, float);
+#undef WDX_LAUNCH_WF_C
+#undef WDX_LAUNCH_WF
+        if (cudaGetLastError() != cudaSuccess) return cleanup_wf(fail(WDX_ERR_CUDA, "dtw_wavefront_kernel launch failed"));
+        g_launches++;
+        if (!od && cudaMemcpyAsync(out, Od, (size_t)nX * nY * osz, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            return cleanup_wf(fail(WDX_ERR_CUDA, "D2H copy failed"));
+        cudaError_t e = cudaStreamSynchronize(st);  // the scratch is released on return
+        if (e != cudaSuccess) return cleanup_wf(fail(WDX_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e)));
+        return cleanup_wf(WDX_OK);
+    }
     const int64_t ctas_x = (nX + CTA_THREADS - 1) / CTA_THREADS;
     int splits = (int)std::max<int64_t>(1, std::min<int64_t>((nY + TILE_SV - 1) / TILE_SV, (148 * 8 + ctas_x - 1) / ctas_x));
     int per = (int)((nY + splits - 1) / splits);
@@ -707,7 +762,6 @@ int wdx_distance_matrix_to(const double* X, int64_t nX, const double* Y, int64_t
     splits = (int)((nY + per - 1) / per);
     dim3 grid((unsigned)ctas_x, (unsigned)splits);
     const size_t smem = (size_t)TILE_SV * L * (exact ? 8 : 4);
-    const double p2 = penalty * penalty;
 #define WDX_LAUNCH_DM(EX, LL, WW, OT)                                                                              \
     dtw_matrix_kernel<EX, LL, WW, OT><<<grid, CTA_THREADS, smem, st>>>(Xd, nX, Yd, nY, L, w_eff, p2, (OT*)Od, per)
     if (spec) {

@@ -1,7 +1,7 @@
 // dtw_wavefront.cuh — windowed DTW for series longer than a register row (L > MAXL): one WARP per
 // (x, y) pair, anti-diagonal wavefront over column strips, neighbours exchanged with __shfl_sync.
 //
-// Same recurrence, band and minimum order as dtw_generic (dtw_band.cuh) and as the oracle's restatement
+// Same recurrence, band and minimum order as dtw_generic (dtw_band.cuh) i.e. the published algorithm
 // of dtaidistance 2.3.13 `dtw_distance` (call sites warpdemux/parallel_distances.py:34,59):
 //   D[i+1][j+1] = (x_i - y_j)^2 + min(D[i][j], D[i][j+1] + p^2, D[i+1][j] + p^2)   for |i - j| < window
 // EXACT: float64, no contraction, bit-identical to the thread-per-pair kernels.  FAST: float32, FMA.
@@ -45,7 +45,7 @@ __device__ __forceinline__ T wf_add(T a, T b) {
     else return __fadd_rn(a, b);
 }
 
-// One row of one strip: C cells, left to right.  EXACT keeps the oracle's compare-and-replace minimum
+// One row of one strip: C cells, left to right.  EXACT keeps the reference's compare-and-replace minimum
 // (diagonal, then vertical, then horizontal; a NaN never replaces) so non-finite inputs propagate
 // identically; FAST uses one 3-input minimum.  CHECK = some strip of the warp straddles a band edge:
 // bit c of `valid` says whether column j0 + c is inside the band (one LOP3 + select per cell).

@@ -32,5 +32,30 @@ def distance_matrix(s, max_dist=None, use_pruning=False, max_length_diff=None, w
     return out
 
 
-def warping_paths_fast(*a, **k):  # imported by sig_proc.py:16 (tRNA path only)
-    raise NotImplementedError("dtaidistance shim: warping_paths_fast not restated")
+def warping_paths_fast(s1, s2, window=None, max_dist=None, use_pruning=False, max_step=None,
+                       max_length_diff=None, penalty=None, psi=None, psi_neg=True, compact=False,
+                       inner_dist="squared euclidean", **kwargs):
+    """`dtaidistance.dtw.warping_paths_fast` for the one call the reference makes (sig_proc.py:298-305:
+    penalty, psi = (b1, 0, b2, 0), compact=False, psi_neg=False): (distance, sqrt'ed paths matrix),
+    computed by the C restatement in oracle/wdx_oracle.c (PARITY UNPINNED, see its header)."""
+    from oracle import wdx_oracle as _o
+
+    if any(v not in (None, 0) for v in (window, max_dist, max_step, max_length_diff)) or use_pruning or compact:
+        raise NotImplementedError("shim supports only penalty/psi (what the reference passes)")
+    if inner_dist != "squared euclidean" or psi_neg:
+        raise NotImplementedError
+    if psi is None:
+        psi = (0, 0, 0, 0)
+    elif isinstance(psi, int):
+        psi = (psi, psi, psi, psi)
+    elif len(psi) == 2:
+        psi = (psi[0], psi[0], psi[1], psi[1])
+    return _o.warping_paths(np.asarray(s1, dtype=np.float64), np.asarray(s2, dtype=np.float64), penalty or 0.0, psi)
+
+
+def best_path(paths, row=None, col=None, use_max=False):
+    from oracle import wdx_oracle as _o
+
+    if use_max:
+        raise NotImplementedError
+    return _o.best_path(paths, row=row, col=col)

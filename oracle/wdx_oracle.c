@@ -339,3 +339,44 @@ void wdx_oracle_new_means(const double *x, const int64_t *segs, int64_t n_segs, 
         means[q] = s / (double)(segs[q + 1] - segs[q]);
     }
 }
+
+/* ------------------------------------------------------------------------
+ * Warping-paths matrix for the consensus-guided (tRNA) fingerprint.
+ * Follows dtaidistance 2.3.13 `dtw.warping_paths` / `dtw_cc.warping_paths`
+ * (dd_dtw.c: dtw_warping_paths, expanded by dtw_expand_wps) as called from
+ * warpdemux/sig_proc.py:298-305:
+ *     warping_paths_fast(query, norm_series, penalty=..., psi=(b1, 0, b2, 0),
+ *                        compact=False, psi_neg=False)
+ * i.e. no window (window = max(r, c) covers the whole matrix), no max_step /
+ * max_dist, squared-Euclidean inner distance, squared penalty on the two
+ * non-diagonal moves, start relaxation only:
+ *     P[0][0..psi_2b] = 0,  P[0..psi_1b][0] = 0,  +inf elsewhere on the border
+ *     P[i+1][j+1] = (s1[i]-s2[j])^2 + min(P[i][j], P[i][j+1] + pen^2, P[i+1][j] + pen^2)
+ * and the WHOLE matrix goes through sqrt at the end.  out: (r+1) x (c+1), row-major.
+ * PARITY UNPINNED: dtaidistance is absent from /root/reference and this image;
+ * the reference ships no vectors for this call.
+ * ---------------------------------------------------------------------- */
+void wdx_oracle_warping_paths(const double *s1, int r, const double *s2, int c,
+                              double penalty, int psi_1b, int psi_2b, double *out)
+{
+    const int W = c + 1;
+    const double pen = penalty * penalty;
+    for (int64_t t = 0; t < (int64_t)(r + 1) * W; t++) out[t] = INFINITY;
+    for (int j = 0; j <= psi_2b && j <= c; j++) out[j] = 0.0;
+    for (int i = 0; i <= psi_1b && i <= r; i++) out[(int64_t)i * W] = 0.0;
+    for (int i = 0; i < r; i++) {
+        const double *p0 = out + (int64_t)i * W;
+        double *p1 = out + (int64_t)(i + 1) * W;
+        for (int j = 0; j < c; j++) {
+            const double df = s1[i] - s2[j];
+            const double d = df * df;
+            double m = p0[j];
+            double t = p0[j + 1] + pen;
+            if (t < m) m = t;
+            t = p1[j] + pen;
+            if (t < m) m = t;
+            p1[j + 1] = d + m;
+        }
+    }
+    for (int64_t t = 0; t < (int64_t)(r + 1) * W; t++) out[t] = sqrt(out[t]);
+}

@@ -55,6 +55,8 @@ def lib():
         L.wdx_oracle_svc_predict_proba.argtypes = [_fp, C.c_int64, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp]
         L.wdx_oracle_process_probs.restype = None
         L.wdx_oracle_process_probs.argtypes = [_dp, C.c_int64, C.c_int, _lp, _dp, _lp, _dp]
+        L.wdx_oracle_warping_paths.restype = None
+        L.wdx_oracle_warping_paths.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_double, C.c_int, C.c_int, _dp]
         L.wdx_oracle_predict.restype = C.c_int
         L.wdx_oracle_predict.argtypes = [_dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp, _lp, _dp, _lp, _dp, _dp]
@@ -290,3 +292,155 @@ def fingerprint(signal: np.ndarray, adapter_start: int, adapter_end: int, *, pad
     )
     keep = min(barcode_num_events, norm.size)
     return FP_OK, norm[-keep:], dwell[-keep:].astype(np.int64), stats
+
+
+# --------------------------------------------------------------------------
+# Consensus-guided barcode refinement (tRNA configs; sig_proc.py:257-378, 451-521)
+# PARITY UNPINNED for the dtaidistance pieces (warping_paths, SubsequenceAlignment,
+# best_path): restated from the published 2.3.13 algorithm, no upstream source,
+# wheel or reference vector is available here.
+# --------------------------------------------------------------------------
+FP_FAIL_TOO_LONG = 4
+FP_FAIL_CONSENSUS = 5     # "consensus query outlier" (sig_proc.py:500-521)
+
+
+def warping_paths(s1: np.ndarray, s2: np.ndarray, penalty: float, psi) -> Tuple[float, np.ndarray]:
+    """dtaidistance `dtw.warping_paths_fast(s1, s2, penalty=, psi=(b1, e1, b2, e2), compact=False,
+    psi_neg=False)` for e1 = e2 = 0 (the reference's call, sig_proc.py:298-305): (distance, paths) with
+    paths the sqrt'ed (len(s1)+1) x (len(s2)+1) cumulative-cost matrix."""
+    s1 = _c64(s1)
+    s2 = _c64(s2)
+    psi_1b, psi_1e, psi_2b, psi_2e = (int(v) for v in psi)
+    if psi_1e or psi_2e:
+        raise NotImplementedError("end relaxation is not used by the reference")
+    out = np.empty((s1.size + 1, s2.size + 1), dtype=np.float64)
+    lib().wdx_oracle_warping_paths(_d(s1), s1.size, _d(s2), s2.size, float(penalty), psi_1b, psi_2b, _d(out))
+    return float(out[s1.size, s2.size]), out
+
+
+def best_path(paths: np.ndarray, row: Optional[int] = None, col: Optional[int] = None):
+    """dtaidistance `dtw.best_path(paths, row, col)`: walk back from (row, col) to the border, at
+    every step to the FIRST minimum of (diagonal, up, left); returns [(i-1, j-1), ...] in forward
+    order without the border cell."""
+    i = paths.shape[0] - 1 if row is None else row
+    j = paths.shape[1] - 1 if col is None else col
+    p = []
+    if paths[i, j] != -1:
+        p.append((i - 1, j - 1))
+    while i > 0 and j > 0:
+        c, vmin = 0, float("inf")
+        for q, v in enumerate((paths[i - 1, j - 1], paths[i - 1, j], paths[i, j - 1])):
+            if v < vmin:
+                c, vmin = q, v
+        if c == 0:
+            i, j = i - 1, j - 1
+        elif c == 1:
+            i = i - 1
+        else:
+            j = j - 1
+        if paths[i, j] != -1:
+            p.append((i - 1, j - 1))
+    p.pop()
+    p.reverse()
+    return p
+
+
+def subsequence_best_match(query: np.ndarray, series: np.ndarray, penalty: float, psi) -> Tuple[int, int]:
+    """`_get_subseq_match` (sig_proc.py:288-312): SubsequenceAlignment with externally computed paths,
+    `_compute_matching` (last row / len(query), trimmed to len(series)), `best_match().segment`
+    = [start of best_path(paths, col=idx+1), idx]."""
+    _, paths = warping_paths(query, series, penalty, psi)
+    matching = paths[-1, :]
+    if matching.size > series.size:
+        matching = matching[-series.size:]
+    matching = np.array(matching) / len(query)
+    best_idx = int(np.argmin(matching))
+    path = best_path(paths, col=best_idx + 1)
+    return int(path[0][1]), best_idx
+
+
+def _cpts_from_scores(scores, num_events, min_obs, w):
+    """discrepenacy_curve_to_cpts (sig_proc.py:176-198), accept_less_cpts=False; None on failure."""
+    from scipy.signal import find_peaks
+
+    try:
+        peaks, _ = find_peaks(scores, distance=min_obs)
+    except ValueError:
+        return None
+    if peaks.size < num_events:
+        return None
+    cpts = peaks[np.argsort(scores[peaks])[-num_events:]] + w
+    cpts.sort()
+    signal_len = scores.size + 2 * w
+    if cpts[0] != 0:
+        cpts = np.insert(cpts, 0, 0)
+    if cpts[-1] != signal_len:
+        cpts = np.append(cpts, signal_len)
+    return cpts
+
+
+def fingerprint_consensus(signal: np.ndarray, adapter_start: int, adapter_end: int, consensus: np.ndarray, *,
+                          padding: int = 100, outlier_thresh: float = 5.0, min_obs_per_base: int = 9,
+                          running_stat_width: int = 18, num_events: int = 120, barcode_num_events=(25, 25),
+                          penalty: float = 1.5, psi=(5, 0, 40, 0), ub_start: int = 18, lb_end: int = 69,
+                          ub_end: int = 97, mutate: bool = False):
+    """`detect_results_to_fpt` with `consensus_refinement = true` (sig_proc.py:451-521 ->
+    segment_signal_with_consensus_guided_barcode_refinement :257-378), defaults of
+    rna004_130bps@v1.0_tRNA.toml:13-29 (sig_extract normalization "none", segmentation and
+    consensus normalization "mean", refinement_optimal_cpts false).
+
+    Returns (status, fpt[retain], dwell[retain], stats dict, (seg_query_start, seg_query_end,
+    sig_barcode_start)).  Two inputs on which the reference itself does not return are given a
+    status instead: NaN padding inside the slice (normalize() raises inside _get_subseq_match ->
+    FP_FAIL_NORMALIZE) and adapters so short that the adapter window is narrower than
+    running_stat_width (compute_base_means is handed change points beyond the signal end, an
+    out-of-bounds read in the reference -> FP_FAIL_SEGMENTATION).
+    """
+    seg_events, retain = int(barcode_num_events[0]), int(barcode_num_events[1])
+    signal = np.asarray(signal)
+    start = max(0, adapter_start - padding)
+    stop = min(signal.size, adapter_end + padding)
+    sig = signal[start:stop]
+    if not mutate:
+        sig = sig.copy()
+    med = np.nanmedian(sig)
+    mad = np.nanmedian(np.abs(sig - med))
+    np.clip(sig, med - outlier_thresh * mad, med + outlier_thresh * mad, out=sig)
+    n = sig.size
+    empty = (np.full(retain, np.nan), np.zeros(retain, dtype=np.int64), {}, (0, 0, 0))
+    m_obs = min(min_obs_per_base, int(round(n / num_events / 2)))          # :315-318
+    w = min(running_stat_width, int(round(n / num_events)))                # :319-322
+    scores = windowed_t_test(sig, w)
+    cpts = _cpts_from_scores(scores, num_events, m_obs, w)
+    if cpts is None:
+        return (FP_FAIL_SEGMENTATION,) + empty
+    a_dwell = cpts[1:] - cpts[:-1]
+    a_ev = new_means(sig, cpts)
+    if np.isnan(a_ev).any():
+        return (FP_FAIL_NORMALIZE,) + empty
+    if w != running_stat_width:
+        return (FP_FAIL_SEGMENTATION,) + empty
+    norm_series = (a_ev - np.mean(a_ev, axis=-1, keepdims=True)) / np.std(a_ev, axis=-1, keepdims=True)
+    q_start, q_end = subsequence_best_match(np.asarray(consensus, dtype=np.float64), norm_series, penalty, psi)
+    sig_bc_start = int(np.sum(a_dwell[:q_end]))                            # :334
+    bc_scores = scores[sig_bc_start:]                                      # :336
+    bc_cpts = _cpts_from_scores(bc_scores, seg_events, min_obs_per_base, running_stat_width)   # :359-365
+    if bc_cpts is None:
+        return (FP_FAIL_SEGMENTATION,) + empty
+    bc_dwell = bc_cpts[1:] - bc_cpts[:-1]
+    bc_ev = new_means(sig[sig_bc_start:], bc_cpts)                         # :371
+    norm = ((bc_ev[:, None] - np.mean(a_ev)) / np.std(a_ev)).squeeze(-1)   # normalize_wrt :139-168
+    dmed = float(np.median(a_dwell))
+    stats = dict(
+        adapter_dt_med=dmed,
+        adapter_dt_mad=float(np.median(np.abs(a_dwell - dmed))),
+        adapter_event_mean=float(a_ev.mean()),
+        adapter_event_std=float(a_ev.std()),
+        adapter_event_med=float(np.median(a_ev)),
+        adapter_event_mad=float(np.median(np.abs(a_ev - np.median(a_ev)))),
+    )
+    cons = (q_start, q_end, sig_bc_start)
+    if q_start > ub_start or q_end < lb_end or q_end > ub_end:             # :500-521
+        return FP_FAIL_CONSENSUS, empty[0], empty[1], stats, cons
+    keep = min(retain, norm.size)
+    return FP_OK, norm[-keep:], bc_dwell[-keep:].astype(np.int64), stats, cons

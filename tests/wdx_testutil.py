@@ -93,3 +93,75 @@ def cnn_golden_signals(gold):
         adc = gold["adc"][offs[i]:offs[i + 1]].astype(np.float32)
         sig[i, : adc.size] = (adc + gold["calibration_offset"][i]) * gold["calibration_scale"][i]
     return sig
+
+
+def synth_trna_signals(consensus, n, seed=5, width=9000):
+    """Consensus-shaped adapter signals for the consensus-guided (tRNA) fingerprint
+    (BASELINE.json configs[3]): `lead` random events, the constant adapter region (the
+    consensus levels, some events dropped or split, level noise), then the barcode events; pA scale,
+    float32, NaN-padded rows, adapter boundaries.  Rows 0..4 are edge cases: tiny adapter, adapter at
+    the start of the read, a long lead (consensus found too late -> "consensus query outlier"), too
+    few barcode events (second segmentation fails), NaN padding inside the slice."""
+    rng = np.random.default_rng(seed)
+    consensus = np.asarray(consensus, dtype=np.float64)
+    sig = np.full((n, width), np.nan, dtype=np.float32)
+    a0 = np.zeros(n, dtype=np.int64)
+    a1 = np.zeros(n, dtype=np.int64)
+    for r in range(n):
+        n_lead = int(rng.integers(0, 22))
+        n_bc = int(rng.integers(27, 42))
+        if r == 2:
+            n_lead = 45
+        if r == 3:
+            n_bc = 12
+        keep = rng.random(consensus.size) > 0.04
+        z = consensus[keep] + 0.08 * rng.standard_normal(int(keep.sum()))
+        split = rng.random(z.size) < 0.04
+        z = np.repeat(z, 1 + split.astype(int))
+        levels = np.concatenate([rng.standard_normal(n_lead), z, rng.standard_normal(n_bc) * 1.1]) * 12.0 + 80.0
+        dwell = 10 + rng.geometric(1.0 / 20.0, size=levels.size)
+        x = np.repeat(levels, dwell)
+        x = x + rng.normal(0.0, 1.5, size=x.size)
+        spikes = rng.random(x.size) < 0.005
+        x[spikes] += rng.choice([-60.0, 60.0], size=int(spikes.sum()))
+        lead = int(rng.integers(0, 300))
+        tail = 40 if r == 4 else int(rng.integers(200, 1500))
+        full = np.concatenate([rng.normal(110.0, 3.0, lead), x, rng.normal(95.0, 6.0, tail)])[:width]
+        sig[r, : full.size] = full.astype(np.float32)
+        a0[r] = lead
+        a1[r] = min(lead + x.size, full.size)
+    a1[0] = a0[0] + 40
+    if n > 1:
+        a0[1] = 0
+    return sig, a0, a1
+
+
+def oracle_fingerprints_consensus(sig, a0, a1, consensus, detect_ok=None, **cfg):
+    """Row-by-row CPU oracle of the consensus-guided fingerprint over a NaN-padded minibatch ->
+    (status, fpt, dwell, stats, cons[n,3])."""
+    from oracle import wdx_oracle as o
+
+    cfg = dict(cfg)
+    cfg.pop("consensus_model", None)
+    n = sig.shape[0]
+    nb = int(cfg.get("barcode_num_events", (25, 25))[1])
+    status = np.zeros(n, dtype=np.int32)
+    fpt = np.full((n, nb), np.nan)
+    dwell = np.zeros((n, nb), dtype=np.int64)
+    stats = np.full((n, 6), np.nan)
+    cons = np.zeros((n, 3), dtype=np.int32)
+    keys = ["adapter_dt_med", "adapter_dt_mad", "adapter_event_mean", "adapter_event_std", "adapter_event_med",
+            "adapter_event_mad"]
+    for r in range(n):
+        if detect_ok is not None and not detect_ok[r]:
+            status[r] = o.FP_FAIL_DETECT
+            continue
+        with np.errstate(all="ignore"):
+            st, f, d, s, c = o.fingerprint_consensus(sig[r], int(a0[r]), int(a1[r]), consensus, **cfg)
+        status[r] = st
+        if st == 0:
+            fpt[r], dwell[r] = f, d
+        if s:
+            stats[r] = [s[k] for k in keys]
+            cons[r] = c
+    return status, fpt, dwell, stats, cons

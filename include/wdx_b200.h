@@ -162,7 +162,8 @@ enum {
     WDX_FP_FAIL_SEGMENTATION = 1, /* "event segmentation failed" (sig_proc.py:537-544): < num_events peaks */
     WDX_FP_FAIL_DETECT = 2,       /* detect_ok[r] == 0 (sig_proc.py:400-407) */
     WDX_FP_FAIL_NORMALIZE = 3,    /* "segment normalization failed" (sig_proc.py:553-560): NaN inside the adapter slice */
-    WDX_FP_FAIL_TOO_LONG = 4      /* adapter slice longer than the shared-memory limit */
+    WDX_FP_FAIL_TOO_LONG = 4,     /* adapter slice longer than the shared-memory limit */
+    WDX_FP_FAIL_CONSENSUS = 5     /* "consensus query outlier" (sig_proc.py:500-521), consensus-guided mode only */
 };
 
 typedef struct wdx_fp wdx_fp;
@@ -187,6 +188,42 @@ int wdx_fp_extract(wdx_fp* f, const float* signals, int64_t n, int64_t stride, c
                    const int64_t* adapter_start, const int64_t* adapter_end, const uint8_t* detect_ok,
                    int clip_in_place, double* fpt, int64_t* dwell, double* stats, int32_t* status,
                    void* stream);
+
+/* ---- consensus-guided barcode refinement ("next" row: the tRNA fingerprint, BASELINE configs[3]) ----
+ * Replaces `segment_signal_with_consensus_guided_barcode_refinement` + the consensus branch of
+ * `detect_results_to_fpt` (warpdemux/sig_proc.py:257-378, 451-521; configuration
+ * rna004_130bps@v1.0_tRNA.toml:13-29, refinement_optimal_cpts = false): adapter segmentation into
+ * num_events + 1 events -> sub-sequence alignment of the consensus query against the mean-normalised
+ * event means (dtaidistance warping_paths with penalty and start relaxation psi = (q, 0, s, 0), no
+ * window; SubsequenceAlignment.best_match) -> sig_barcode_start -> second change-point selection on
+ * the tail of the t-test scores (barcode_segm_events points, uncapped min_obs_per_base /
+ * running_stat_width) -> event means normalised with the ADAPTER events' mean / std (normalize_wrt)
+ * -> the last wdx_fp_config.barcode_num_events (= barcode_num_events[1]) -> outlier filter on the
+ * match position.  After wdx_fp_set_consensus every wdx_fp_extract* / wdx_fp_predict call on the
+ * handle runs this variant; query_len = 0 (or NULL) switches back.
+ * Two inputs on which the reference itself raises instead of returning are reported as failed reads:
+ * NaN padding inside the slice (WDX_FP_FAIL_NORMALIZE) and adapters so short that the adapter window
+ * is narrower than running_stat_width (WDX_FP_FAIL_SEGMENTATION). */
+typedef struct {
+    const double* query;         /* warpdemux._consensus.ALL[consensus_model], HOST pointer (copied) */
+    int32_t query_len;           /* <= 128 (84 for rna004_130bps_v1_0) */
+    int32_t barcode_segm_events; /* segmentation.barcode_num_events[0]               (25)  */
+    double penalty;              /* consensus_subseq_match_penalty                   (1.5) */
+    int32_t psi_query_begin;     /* consensus_subseq_match_psi[0]                    (5)   */
+    int32_t psi_series_begin;    /* consensus_subseq_match_psi[2]                    (40)  */
+    int32_t ub_start;            /* consensus_subseq_match_ub_start                  (18)  */
+    int32_t lb_end;              /* consensus_subseq_match_lb_end                    (69)  */
+    int32_t ub_end;              /* consensus_subseq_match_ub_end                    (97)  */
+} wdx_fp_consensus;
+
+int wdx_fp_set_consensus(wdx_fp* f, const wdx_fp_consensus* c);
+
+/* wdx_fp_extract plus `cons` [n, 3] int32: seg_cons_query_start, seg_cons_query_end, sig_barcode_start
+ * (ReadResult fields, sig_proc.py:595-604); NULL unless the handle is in consensus-guided mode. */
+int wdx_fp_extract_ex(wdx_fp* f, const float* signals, int64_t n, int64_t stride, const int32_t* sig_len,
+                      const int64_t* adapter_start, const int64_t* adapter_end, const uint8_t* detect_ok,
+                      int clip_in_place, double* fpt, int64_t* dwell, double* stats, int32_t* status,
+                      int32_t* cons, void* stream);
 
 /* Fused minibatch step (file_proc.py:418-450): fingerprints never leave the
  * device between extraction and wdx_predict.  Failed reads get label -1, NaN

@@ -22,7 +22,7 @@ EXPORTS = [
     "wdx_model_create", "wdx_model_destroy", "wdx_model_set_guard", "wdx_model_set_chunk_reads", "wdx_model_set_sv_splits",
     "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
     "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_model_last_kernel_ms_mode", "wdx_version",
-    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms",
+    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_extract_ex", "wdx_fp_set_consensus", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms",
     "wdx_cnn_create", "wdx_cnn_destroy", "wdx_cnn_detect", "wdx_cnn_prepare", "wdx_cnn_predict", "wdx_cnn_score_len", "wdx_cnn_set_guard", "wdx_cnn_enable_timing",
     "wdx_cnn_last_kernel_ms",
 ]
@@ -87,6 +87,10 @@ def load():
         L.wdx_fp_destroy.argtypes = [vp]
         L.wdx_fp_extract.restype = i32
         L.wdx_fp_extract.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+        L.wdx_fp_extract_ex.restype = i32
+        L.wdx_fp_extract_ex.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.wdx_fp_set_consensus.restype = i32
+        L.wdx_fp_set_consensus.argtypes = [vp, vp]
         L.wdx_fp_predict.restype = i32
         L.wdx_fp_predict.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.wdx_fp_enable_timing.restype = i32

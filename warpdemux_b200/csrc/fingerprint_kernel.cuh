@@ -38,7 +38,8 @@
 
 namespace wdx {
 
-enum { FP_OK = 0, FP_FAIL_SEGMENTATION = 1, FP_FAIL_DETECT = 2, FP_FAIL_NORMALIZE = 3, FP_FAIL_TOO_LONG = 4 };
+enum { FP_OK = 0, FP_FAIL_SEGMENTATION = 1, FP_FAIL_DETECT = 2, FP_FAIL_NORMALIZE = 3, FP_FAIL_TOO_LONG = 4, FP_FAIL_CONSENSUS = 5 };
+constexpr int FP_MAX_QUERY = 128;  // longest consensus query (4 rows per lane of one warp)
 
 struct FpConfig {
     int padding;             // sig_extract.padding
@@ -46,7 +47,13 @@ struct FpConfig {
     int min_obs_per_base;    // segmentation.min_obs_per_base
     int running_stat_width;  // segmentation.running_stat_width
     int num_events;          // segmentation.num_events
-    int barcode_num_events;  // segmentation.barcode_num_events
+    int barcode_num_events;  // segmentation.barcode_num_events (consensus mode: barcode_num_events[1], events kept)
+    // consensus-guided barcode refinement (segmentation.consensus_refinement, sig_proc.py:257-378, 451-521)
+    int cons_len;            // length of the consensus query; 0 = refinement off
+    int cons_seg_events;     // barcode_num_events[0]: change points of the second segmentation
+    double cons_pen2;        // consensus_subseq_match_penalty squared
+    int cons_psi_q, cons_psi_s;              // consensus_subseq_match_psi[0], [2] (start relaxation: query, series)
+    int cons_ub_start, cons_lb_end, cons_ub_end;
 };
 
 struct FpArgs {
@@ -63,6 +70,8 @@ struct FpArgs {
     int64_t* dwell;             // [n][barcode_num_events] or nullptr
     double* stats;              // [n][6] or nullptr
     int32_t* status;            // [n]
+    const double* cons_query;   // [cons_len] consensus query (device), consensus mode only
+    int32_t* cons;              // [n][3] seg_cons_query_start, seg_cons_query_end, sig_barcode_start, or nullptr
 };
 
 // Same result as block_median_f32, found with two light passes instead of five
@@ -239,6 +248,288 @@ __device__ void small_median(const double* v, int n, double* out, double* tmp2) 
     __syncthreads();
 }
 
+
+// ---- scipy find_peaks(scores[lo:nc], distance=m_obs): local maxima + distance suppression ----------
+// Works on the positions (lo, nc - 1) of score[] (find_peaks of the sub-array scores[lo:]: its first
+// and last samples are never peaks and a plateau is judged by the same neighbours, so the maxima of
+// the sub-array are the maxima of the full array whose plateau starts after lo).  Leaves the kept
+// peaks, in order, in kp[0..P) and returns P.  kp / state: scratch of (nc - lo)/2 + 8 entries.
+__device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint8_t* state,
+                               FpScratch& s) {
+    const int tid = threadIdx.x;
+    // scipy _local_maxima_1d (strict maxima, plateaus -> midpoint), compacted in order:
+    // thread t scans the contiguous positions [lo + t*chunk, lo + (t+1)*chunk); a plateau belongs to the
+    // thread that owns its first sample, which keeps the list sorted by position.
+    const int chunk = (nc - lo + FP_THREADS - 1) / FP_THREADS;
+    const int p_begin = min(nc - 1, max(lo + 1, lo + tid * chunk)), p_end = min(nc - 1, lo + (tid + 1) * chunk);
+    auto peak_at = [&](int i) -> int {  // midpoint of the maximum that starts at i, or -1
+        const double x = score[i];
+        if (!(score[i - 1] < x)) return -1;
+        int ahead = i + 1;
+        while (ahead < nc - 1 && score[ahead] == x) ahead++;
+        return (score[ahead] < x) ? ((i + ahead - 1) >> 1) : -1;
+    };
+    uint32_t my = 0;
+    for (int i = p_begin; i < p_end; i++) my += (peak_at(i) >= 0);
+    uint32_t total = 0;
+    uint32_t off = block_exscan(my, s, &total);
+    for (int i = p_begin; i < p_end; i++) {
+        const int pk = peak_at(i);
+        if (pk >= 0) {
+            kp[off] = (uint16_t)pk;
+            state[off] = 1;  // per-peak state: 1 undecided, 2 kept, 3 removed
+            off++;
+        }
+    }
+    __syncthreads();
+    const int P0 = (int)total;
+
+    // ---- scipy _select_by_peak_distance as a fixed point over the peak list ---------
+    // A peak stays iff no STAYING peak of higher priority (score, then index) lies closer than
+    // m_obs samples; the greedy highest-first sweep of scipy computes exactly this set.
+    if (m_obs > 1) {
+        for (;;) {
+            int undecided = 0;
+            for (int j = tid; j < P0; j += FP_THREADS) {
+                if ((state[j] & 15) != 1) continue;
+                const int pj = kp[j];
+                const double x = score[pj];
+                bool killed = false, blocked = false;
+                for (int q = j - 1; q >= 0 && pj - (int)kp[q] < m_obs; q--) {
+                    const int st = state[q] & 15;
+                    if (st == 3) continue;
+                    if (score[kp[q]] > x) {  // equal scores: the higher index wins, q < j loses
+                        if (st == 2) killed = true;
+                        else blocked = true;
+                    }
+                }
+                for (int q = j + 1; q < P0 && (int)kp[q] - pj < m_obs; q++) {
+                    const int st = state[q] & 15;
+                    if (st == 3) continue;
+                    if (score[kp[q]] >= x) {
+                        if (st == 2) killed = true;
+                        else blocked = true;
+                    }
+                }
+                const int ns = killed ? 3 : (blocked ? 1 : 2);
+                if (ns == 1) undecided = 1;
+                state[j] = (uint8_t)(1 | (ns << 4));  // verdict parked in the high nibble (nobody else reads it)
+            }
+            const int any = __syncthreads_or(undecided);
+            for (int j = tid; j < P0; j += FP_THREADS)
+                if (state[j] >> 4) state[j] = state[j] >> 4;
+            __syncthreads();
+            if (!any) break;
+        }
+    } else {
+        for (int j = tid; j < P0; j += FP_THREADS) state[j] = 2;
+        __syncthreads();
+    }
+
+    // ---- kept peaks, in order (in place: the write index never passes the read index)
+    const int pchunk0 = (P0 + FP_THREADS - 1) / FP_THREADS;
+    const int j0 = min(P0, tid * pchunk0), j1 = min(P0, j0 + pchunk0);
+    uint32_t mk = 0;
+    for (int j = j0; j < j1; j++) mk += (state[j] == 2);
+    uint32_t koff = block_exscan(mk, s, &total);
+    uint16_t keep_local[FP_MAX_LEN / 2 / FP_THREADS + 2];
+    int nk = 0;
+    for (int j = j0; j < j1; j++)
+        if (state[j] == 2) keep_local[nk++] = kp[j];
+    __syncthreads();  // everybody has read its part of the list
+    for (int q = 0; q < nk; q++) kp[koff + q] = keep_local[q];
+    __syncthreads();
+    return (int)total;
+}
+
+// ---- the k highest-scoring of the P kept peaks (sig_proc.py:188), in position order ---------------
+// out[0..k) = kp[i] + add for the selected peaks.  Radix-selects the k-th largest score (scores are
+// >= 0, so their bit patterns order like the values); ties -> the higher indices.  Requires P >= k.
+__device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* state, int P, int k_events, int add,
+                             int* out, FpScratch& s) {
+    const int tid = threadIdx.x;
+    unsigned long long thr_key;
+    {
+        unsigned long long prefix = 0, mask = 0;
+        uint32_t k = (uint32_t)k_events - 1;  // 0-based rank from the top
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            __syncthreads();
+            if (tid < 256) s.hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < P; i += FP_THREADS) {
+                const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
+                if ((kv & mask) == prefix) atomicAdd(&s.hist[(uint32_t)(kv >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {  // warp 0 scans the 256 bins from the top, 8 per lane (lane 0 = bins 255..248)
+                uint32_t cnt[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    cnt[q] = s.hist[255 - (tid * 8 + q)];
+                    sum += cnt[q];
+                }
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (tid >= o) inc += t;
+                }
+                uint32_t run = inc - sum;  // elements in higher bins
+                if (k >= run && k < inc) {  // exactly one lane
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (k >= run && k < run + cnt[q]) {
+                            s.sel_prefix64 = prefix | ((unsigned long long)(255 - (tid * 8 + q)) << shift);
+                            s.sel_k = k - run;
+                        }
+                        run += cnt[q];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = s.sel_prefix64;
+            k = s.sel_k;
+            mask |= 255ull << shift;
+        }
+        thr_key = prefix;
+        // k = how many elements EQUAL to the threshold rank above the selected one, i.e.
+        // (k + 1) of the ties are taken; ties -> the higher indices
+    }
+    const uint32_t ties_needed = s.sel_k + 1;
+    __syncthreads();
+    // mark the selection, then compact in order
+    const int pchunk = (P + FP_THREADS - 1) / FP_THREADS;
+    const int i0 = min(P, tid * pchunk), i1 = min(P, i0 + pchunk);
+    uint32_t my_ties = 0;
+    for (int i = i0; i < i1; i++) my_ties += ((unsigned long long)__double_as_longlong(score[kp[i]]) == thr_key);
+    uint32_t tot_ties = 0;
+    uint32_t tie_off = block_exscan(my_ties, s, &tot_ties);  // ties before this thread's chunk
+    uint32_t mysel = 0;
+    for (int i = i0; i < i1; i++) {
+        const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
+        bool sel = kv > thr_key;
+        if (kv == thr_key) {
+            const uint32_t ties_after = tot_ties - tie_off - 1;  // ties at higher index
+            sel = ties_after < ties_needed;
+            tie_off++;
+        }
+        state[i] = sel ? 4 : 0;
+        mysel += sel;
+    }
+    uint32_t tot_sel = 0;
+    uint32_t so = block_exscan(mysel, s, &tot_sel);
+    for (int i = i0; i < i1; i++)
+        if (state[i] == 4) out[so++] = (int)kp[i] + add;  // already sorted
+    __syncthreads();
+}
+
+// ---- consensus sub-sequence match (sig_proc.py:288-312) by ONE warp ---------------------------------
+// dtaidistance warping_paths(query, series, penalty, psi = (psi_q, 0, psi_s, 0)) without window:
+//     P[0][0..psi_s] = 0, P[0..psi_q][0] = 0, +inf elsewhere on the border,
+//     P[i+1][j+1] = (q[i] - x[j])^2 + min(P[i][j], P[i][j+1] + pen2, P[i+1][j] + pen2),
+// then SubsequenceAlignment: matching[j] = sqrt(P[Q][j+1]) / Q, end = first argmin, start = column of the
+// first cell of best_path(paths, col = end + 1) (walk back to the FIRST minimum of sqrt(diagonal),
+// sqrt(up), sqrt(left), no penalty).  The matrix is never stored: lane l owns rows [l*R, (l+1)*R) and
+// sweeps the columns as an anti-diagonal wavefront (values handed down the lanes by __shfl_up_sync);
+// the start column of the walk-back travels FORWARD with every cell (origin of a cell = origin of the
+// predecessor the walk-back would choose, or the cell's own column when that predecessor lies on the
+// border), so the answer for every end column is known when the last row is reached.
+// sqrt(a) < sqrt(b) as the walk-back compares them (correctly rounded square roots can collide):
+__device__ __forceinline__ bool lt_sqrt(double a, double b) {
+    if (!(a < b)) return false;
+    if (__dsub_rn(b, a) > __dmul_rn(b, 1.7763568394002505e-15 /* 2^-49 */)) return true;  // more than 8 ulp apart: the roots differ
+    return __dsqrt_rn(a) < __dsqrt_rn(b);
+}
+
+template <int RMAX>
+__device__ void consensus_match_warp(const double* __restrict__ query, int Q, const double* series, int Cn, double pen2,
+                                     int psi_q, int psi_s, double* lastrow, int* lastorg, int* result /*[2] start, end*/) {
+    const int lane = threadIdx.x & 31;
+    const int R = (Q + 31) >> 5;            // rows per lane (<= RMAX)
+    const int n_lanes = (Q + R - 1) / R;    // lanes that own rows
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double qv[RMAX], left[RMAX];
+    int lorg[RMAX];
+#pragma unroll
+    for (int rr = 0; rr < RMAX; rr++) {
+        const int i = lane * R + rr;
+        qv[rr] = (rr < R && i < Q) ? query[i] : 0.0;
+        left[rr] = (i + 1 <= psi_q) ? 0.0 : inf;   // P[i+1][0]
+        lorg[rr] = -1;
+    }
+    const int i_first = lane * R;
+    double diag_in = (i_first <= psi_q) ? 0.0 : inf;  // P[i_first][0]
+    int diag_org = -1;
+    double pass_v = inf;
+    int pass_o = -1;
+    const int steps = Cn + n_lanes - 1;
+    for (int st = 0; st < steps; st++) {
+        double up_in = __shfl_up_sync(0xffffffffu, pass_v, 1);
+        int up_org = __shfl_up_sync(0xffffffffu, pass_o, 1);
+        const int j = st - lane;
+        if (lane == 0) {
+            up_in = (j + 1 <= psi_s) ? 0.0 : inf;  // P[0][j+1]
+            up_org = -1;
+        }
+        if (j >= 0 && j < Cn && lane < n_lanes) {
+            const double x = series[j];
+            double up = up_in, dg = diag_in;
+            int uo = up_org, dgo = diag_org;
+#pragma unroll
+            for (int rr = 0; rr < RMAX; rr++) {
+                const int i = i_first + rr;
+                if (rr < R && i < Q) {
+                    const double lf = left[rr];
+                    const int lfo = lorg[rr];
+                    const double df = __dsub_rn(qv[rr], x);
+                    const double d = __dmul_rn(df, df);
+                    double m = dg;
+                    double t = __dadd_rn(up, pen2);
+                    if (t < m) m = t;
+                    t = __dadd_rn(lf, pen2);
+                    if (t < m) m = t;
+                    const double val = __dadd_rn(d, m);
+                    // walk-back choice at this cell
+                    double best = dg;
+                    int po = dgo;
+                    if (lt_sqrt(up, best)) { best = up; po = uo; }
+                    if (lt_sqrt(lf, best)) { best = lf; po = lfo; }
+                    const int org = (po < 0) ? j : po;
+                    // hand down: this row's old value is the next row's diagonal, its new value the next row's up
+                    dg = lf; dgo = lfo;
+                    up = val; uo = org;
+                    left[rr] = val; lorg[rr] = org;
+                    if (i == Q - 1) { lastrow[j] = val; lastorg[j] = org; }
+                }
+            }
+            pass_v = up; pass_o = uo;
+            diag_in = up_in; diag_org = up_org;
+        }
+    }
+    __syncwarp();
+    // matching = sqrt(last row) / Q; first minimum (np.argmin)
+    const double Qd = (double)Q;
+    double bv = inf;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < Cn; j += 32) {
+        const double v = __ddiv_rn(__dsqrt_rn(lastrow[j]), Qd);
+        if (v < bv) { bv = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;  // every entry +inf/NaN: argmin returns 0
+    if (lane == 0) {
+        result[0] = lastorg[bi];
+        result[1] = bi;
+    }
+}
+
+// CONS = consensus-guided barcode refinement (tRNA configurations, sig_proc.py:257-378, 451-521).
+template <bool CONS>
 __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_kernel(const __grid_constant__ FpConfig c,
                                                                    const __grid_constant__ FpArgs a) {
     extern __shared__ __align__(16) unsigned char fp_smem[];
@@ -266,6 +557,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
             if (a.dwell) a.dwell[read * nb + q] = 0;
         }
         if (a.stats && tid < 6) a.stats[read * 6 + tid] = qnan;
+        if (CONS && a.cons && tid < 3) a.cons[read * 3 + tid] = 0;
         if (tid == 0) a.status[read] = code;
     };
 
@@ -411,89 +703,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     }
     __syncthreads();
 
-    // ---- scipy _local_maxima_1d (strict maxima, plateaus -> midpoint), compacted in order
-    // thread t scans the contiguous positions [t*chunk, (t+1)*chunk); a plateau belongs to the
-    // thread that owns its first sample, which keeps the list sorted by position.
-    const int chunk = (nc + FP_THREADS - 1) / FP_THREADS;
-    const int p_begin = min(nc - 1, max(1, tid * chunk)), p_end = min(nc - 1, (tid + 1) * chunk);
-    auto peak_at = [&](int i) -> int {  // midpoint of the maximum that starts at i, or -1
-        const double x = score[i];
-        if (!(score[i - 1] < x)) return -1;
-        int ahead = i + 1;
-        while (ahead < nc - 1 && score[ahead] == x) ahead++;
-        return (score[ahead] < x) ? ((i + ahead - 1) >> 1) : -1;
-    };
-    uint32_t my = 0;
-    for (int i = p_begin; i < p_end; i++) my += (peak_at(i) >= 0);
-    uint32_t total = 0;
-    uint32_t off = block_exscan(my, s, &total);
-    for (int i = p_begin; i < p_end; i++) {
-        const int pk = peak_at(i);
-        if (pk >= 0) {
-            kp[off] = (uint16_t)pk;
-            state[off] = 1;  // per-peak state: 1 undecided, 2 kept, 3 removed
-            off++;
-        }
-    }
-    __syncthreads();
-    const int P0 = (int)total;
 
-    // ---- scipy _select_by_peak_distance as a fixed point over the peak list ---------
-    // A peak stays iff no STAYING peak of higher priority (score, then index) lies closer than
-    // m_obs samples; the greedy highest-first sweep of scipy computes exactly this set.
-    if (m_obs > 1) {
-        for (;;) {
-            int undecided = 0;
-            for (int j = tid; j < P0; j += FP_THREADS) {
-                if ((state[j] & 15) != 1) continue;
-                const int pj = kp[j];
-                const double x = score[pj];
-                bool killed = false, blocked = false;
-                for (int q = j - 1; q >= 0 && pj - (int)kp[q] < m_obs; q--) {
-                    const int st = state[q] & 15;
-                    if (st == 3) continue;
-                    if (score[kp[q]] > x) {  // equal scores: the higher index wins, q < j loses
-                        if (st == 2) killed = true;
-                        else blocked = true;
-                    }
-                }
-                for (int q = j + 1; q < P0 && (int)kp[q] - pj < m_obs; q++) {
-                    const int st = state[q] & 15;
-                    if (st == 3) continue;
-                    if (score[kp[q]] >= x) {
-                        if (st == 2) killed = true;
-                        else blocked = true;
-                    }
-                }
-                const int ns = killed ? 3 : (blocked ? 1 : 2);
-                if (ns == 1) undecided = 1;
-                state[j] = (uint8_t)(1 | (ns << 4));  // verdict parked in the high nibble (nobody else reads it)
-            }
-            const int any = __syncthreads_or(undecided);
-            for (int j = tid; j < P0; j += FP_THREADS)
-                if (state[j] >> 4) state[j] = state[j] >> 4;
-            __syncthreads();
-            if (!any) break;
-        }
-    } else {
-        for (int j = tid; j < P0; j += FP_THREADS) state[j] = 2;
-        __syncthreads();
-    }
-
-    // ---- kept peaks, in order (in place: the write index never passes the read index)
-    const int pchunk0 = (P0 + FP_THREADS - 1) / FP_THREADS;
-    const int j0 = min(P0, tid * pchunk0), j1 = min(P0, j0 + pchunk0);
-    uint32_t mk = 0;
-    for (int j = j0; j < j1; j++) mk += (state[j] == 2);
-    uint32_t koff = block_exscan(mk, s, &total);
-    uint16_t keep_local[FP_MAX_LEN / 2 / FP_THREADS + 2];
-    int nk = 0;
-    for (int j = j0; j < j1; j++)
-        if (state[j] == 2) keep_local[nk++] = kp[j];
-    __syncthreads();  // everybody has read its part of the list
-    for (int q = 0; q < nk; q++) kp[koff + q] = keep_local[q];
-    __syncthreads();
-    const int P = (int)total;
+    // ---- change points: find_peaks + the num_events highest scores (sig_proc.py:176-198) ------------
+    const int P = find_kept_peaks(score, 0, nc, m_obs, kp, state, s);
     if (P < c.num_events) {  // sig_proc.py:185-186 -> "event segmentation failed"
         fail(FP_FAIL_SEGMENTATION);
         return;
@@ -502,87 +714,10 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         fail(FP_FAIL_NORMALIZE);
         return;
     }
-
-    // ---- the num_events highest scores (sig_proc.py:188): radix-select the threshold
-    // scores are >= 0, so their bit patterns order like the values
-    unsigned long long thr_key;
-    {
-        unsigned long long prefix = 0, mask = 0;
-        uint32_t k = (uint32_t)c.num_events - 1;  // 0-based rank from the top
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            __syncthreads();
-            if (tid < 256) s.hist[tid] = 0;
-            __syncthreads();
-            for (int i = tid; i < P; i += FP_THREADS) {
-                const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
-                if ((kv & mask) == prefix) atomicAdd(&s.hist[(uint32_t)(kv >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (tid < 32) {  // warp 0 scans the 256 bins from the top, 8 per lane (lane 0 = bins 255..248)
-                uint32_t cnt[8], sum = 0;
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    cnt[q] = s.hist[255 - (tid * 8 + q)];
-                    sum += cnt[q];
-                }
-                uint32_t inc = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (tid >= o) inc += t;
-                }
-                uint32_t run = inc - sum;  // elements in higher bins
-                if (k >= run && k < inc) {  // exactly one lane
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (k >= run && k < run + cnt[q]) {
-                            s.sel_prefix64 = prefix | ((unsigned long long)(255 - (tid * 8 + q)) << shift);
-                            s.sel_k = k - run;
-                        }
-                        run += cnt[q];
-                    }
-                }
-            }
-            __syncthreads();
-            prefix = s.sel_prefix64;
-            k = s.sel_k;
-            mask |= 255ull << shift;
-        }
-        thr_key = prefix;
-        // k = how many elements EQUAL to the threshold rank above the selected one, i.e.
-        // (k + 1) of the ties are taken; ties -> the higher indices
-    }
-    const uint32_t ties_needed = s.sel_k + 1;
-    __syncthreads();
-    // mark the selection, then compact in order into the change points
-    {
-        const int pchunk = (P + FP_THREADS - 1) / FP_THREADS;
-        const int i0 = min(P, tid * pchunk), i1 = min(P, i0 + pchunk);
-        uint32_t my_ties = 0;
-        for (int i = i0; i < i1; i++)
-            my_ties += ((unsigned long long)__double_as_longlong(score[kp[i]]) == thr_key);
-        uint32_t tot_ties = 0;
-        uint32_t tie_off = block_exscan(my_ties, s, &tot_ties);  // ties before this thread's chunk
-        uint32_t mysel = 0;
-        for (int i = i0; i < i1; i++) {
-            const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
-            bool sel = kv > thr_key;
-            if (kv == thr_key) {
-                const uint32_t ties_after = tot_ties - tie_off - 1;  // ties at higher index
-                sel = ties_after < ties_needed;
-                tie_off++;
-            }
-            state[i] = sel ? 4 : 0;
-            mysel += sel;
-        }
-        uint32_t tot_sel = 0;
-        uint32_t so = block_exscan(mysel, s, &tot_sel);
-        for (int i = i0; i < i1; i++)
-            if (state[i] == 4) cpts[1 + so++] = (int)kp[i] + w;  // + running_stat_width, already sorted
-        if (tid == 0) {
-            cpts[0] = 0;                      // peaks lie in [1, nc-2] and w >= 1: 0 and n are never present
-            cpts[c.num_events + 1] = n;
-        }
+    select_top_k(score, kp, state, P, c.num_events, w, cpts + 1, s);  // + running_stat_width
+    if (tid == 0) {
+        cpts[0] = 0;                      // peaks lie in [1, nc-2] and w >= 1: 0 and n are never present
+        cpts[c.num_events + 1] = n;
     }
     __syncthreads();
     const int n_seg = c.num_events + 1;
@@ -609,9 +744,8 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     __syncthreads();
     const double ev_mean = red[0], ev_std = red[1];
 
-    // ---- statistics (sig_proc.py:562-567) ----------------------------------------------
+    // ---- statistics (sig_proc.py:562-567 / 490-498: always over the ADAPTER events) ---------------
     if (a.stats) {
-        double* st = a.stats + read * 6;
         if (tid < n_seg) dv[tid] = (double)(cpts[tid + 1] - cpts[tid]);
         small_median(dv, n_seg, &red[2], &red[6]);  // adapter_dt_med
         const double dt_med = red[2];
@@ -621,7 +755,10 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         const double e_med = red[4];
         if (tid < n_seg) dv[tid] = fabs(__dsub_rn(ev[tid], e_med));
         small_median(dv, n_seg, &red[5], &red[6]);  // adapter_event_mad
-        if (tid == 0) {
+    }
+    auto write_stats = [&]() {
+        if (a.stats && tid == 0) {
+            double* st = a.stats + read * 6;
             st[0] = red[2];
             st[1] = red[3];
             st[2] = ev_mean;
@@ -629,12 +766,75 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
             st[4] = red[4];
             st[5] = red[5];
         }
-    }
+    };
 
-    // ---- keep the last barcode_num_events (sig_proc.py:569-594) -------------------------
-    const int keep = min(nb, n_seg);
+    int n_out_seg = n_seg;   // segments the fingerprint is cut from (their bounds in cpts, means in ev)
+    if constexpr (CONS) {
+        // ---- consensus-guided barcode refinement (sig_proc.py:257-378) ------------------------------
+        // The second segmentation hands compute_base_means change points up to scores.size + 2 *
+        // running_stat_width; with a narrower adapter window that lies beyond the signal (the
+        // reference's bounds-checked Cython raises): such reads fail.
+        if (w != c.running_stat_width) {
+            fail(FP_FAIL_SEGMENTATION);
+            return;
+        }
+        __shared__ double lastrow[FP_MAX_EVENTS + 2];
+        __shared__ int lastorg[FP_MAX_EVENTS + 2];
+        __shared__ int match[2];
+        __syncthreads();
+        if (tid < n_seg) dv[tid] = __ddiv_rn(__dsub_rn(ev[tid], ev_mean), ev_std);  // normalize(series, "mean")
+        __syncthreads();
+        if (tid < 32)
+            consensus_match_warp<FP_MAX_QUERY / 32>(a.cons_query, c.cons_len, dv, n_seg, c.cons_pen2, c.cons_psi_q,
+                                                    c.cons_psi_s, lastrow, lastorg, match);
+        __syncthreads();
+        const int q_start = match[0], q_end = match[1];
+        const int sbs = cpts[q_end];  // sig_barcode_start = sum(adapter_dwell_times[:q_end]) (sig_proc.py:334)
+        __syncthreads();              // cpts / ev are rewritten below
+        // second segmentation on barcode_scores = adapter_scores[sbs:] with the UNCAPPED min_obs_per_base
+        // and running_stat_width (sig_proc.py:336-365)
+        const int ke = c.cons_seg_events;
+        const int P2 = (nc - sbs >= 3) ? find_kept_peaks(score, sbs, nc, c.min_obs_per_base, kp, state, s) : 0;
+        if (P2 < ke) {
+            fail(FP_FAIL_SEGMENTATION);
+            return;
+        }
+        select_top_k(score, kp, state, P2, ke, w - sbs, cpts + 1, s);  // relative to raw_signal[sbs:]
+        if (tid == 0) {
+            cpts[0] = 0;
+            cpts[ke + 1] = n - sbs;   // scores.size + 2 * running_stat_width = (nc - sbs) + 2 w
+        }
+        __syncthreads();
+        for (int q = tid; q < ke + 1; q += FP_THREADS) {  // compute_base_means(raw_signal[sbs:], cpts) (:368)
+            double sum = 0.0;
+            const int b = cpts[q], e = cpts[q + 1];
+            for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)sig[sbs + i]);
+            ev[q] = __ddiv_rn(sum, (double)(e - b));
+        }
+        __syncthreads();
+        n_out_seg = ke + 1;
+        if (a.cons && tid == 0) {
+            a.cons[read * 3 + 0] = q_start;
+            a.cons[read * 3 + 1] = q_end;
+            a.cons[read * 3 + 2] = sbs;
+        }
+        if (q_start > c.cons_ub_start || q_end < c.cons_lb_end || q_end > c.cons_ub_end) {  // sig_proc.py:500-521
+            for (int q = tid; q < nb; q += FP_THREADS) {
+                fpt_out[q] = qnan;
+                if (a.dwell) a.dwell[read * nb + q] = 0;
+            }
+            write_stats();
+            if (tid == 0) a.status[read] = FP_FAIL_CONSENSUS;
+            return;
+        }
+    }
+    write_stats();
+
+    // ---- keep the last barcode_num_events (sig_proc.py:569-594); normalised by the mean / std of the
+    // adapter events (normalize "mean" :546-552, or normalize_wrt for the refined barcode events :482-484)
+    const int keep = min(nb, n_out_seg);
     for (int q = tid; q < nb; q += FP_THREADS) {
-        const int srcq = n_seg - keep + (q - (nb - keep));
+        const int srcq = n_out_seg - keep + (q - (nb - keep));
         double v = qnan;  // front NaN padding if fewer events than asked (unreachable with accept_less_cpts=false)
         int64_t dw = 0;
         if (q >= nb - keep) {

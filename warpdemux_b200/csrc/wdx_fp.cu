@@ -21,7 +21,8 @@ struct wdx_fp {
     cudaStream_t copy_stream = nullptr;  // H2D of the next chunk
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     DevBuf sig[2], len[2], a0[2], a1[2], ok[2], maxlen;
-    DevBuf fpt[2], dwell[2], stats[2], status[2], lab[2], conf[2], prob[2], flags[2];
+    DevBuf fpt[2], dwell[2], stats[2], status[2], lab[2], conf[2], prob[2], flags[2], cons[2];
+    DevBuf cons_query;                   // consensus query (consensus-guided mode)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;
     size_t tev_used = 0;
@@ -41,6 +42,7 @@ struct FpCall {
     int64_t* dwell;
     double* stats;
     int32_t* status;
+    int32_t* cons;
     // fused predict (m == nullptr: extraction only)
     wdx_model* m;
     int mode;
@@ -71,7 +73,8 @@ int launch_fp(wdx_fp* f, const FpArgs& fa, cudaStream_t st) {
         f->tev_used++;
         CUDA_TRY(cudaEventRecord(e0, st));
     }
-    fingerprint_kernel<<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
+    if (f->cfg.cons_len > 0) fingerprint_kernel<true><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
+    else fingerprint_kernel<false><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
     CUDA_TRY(cudaGetLastError());
     if (f->timing) CUDA_TRY(cudaEventRecord(e1, st));
     g_launches++;
@@ -125,10 +128,11 @@ int run(wdx_fp* f, const FpCall& c) {
     const bool conf_dev = c.conf && mem_kind(c.conf) == 2;
     const bool prob_dev = c.prob && mem_kind(c.prob) == 2;
     const bool flags_dev = c.flags && mem_kind(c.flags) == 2;
+    const bool cons_dev = c.cons && mem_kind(c.cons) == 2;
     const bool any_host = !sig_dev || (c.sig_len && !len_dev) || !a0_dev || !a1_dev || (c.ok && !ok_dev) ||
                           (c.fpt && !fpt_dev) || (c.dwell && !dwell_dev) || (c.stats && !stats_dev) || !status_dev ||
                           (c.labels && !lab_dev) || (c.conf && !conf_dev) || (c.prob && !prob_dev) ||
-                          (c.flags && !flags_dev);
+                          (c.flags && !flags_dev) || (c.cons && !cons_dev);
 
     // shared-memory capacity per read
     int64_t cap64 = f->max_slice_len;
@@ -182,6 +186,7 @@ int run(wdx_fp* f, const FpCall& c) {
         if (c.conf && !conf_dev && (rc = f->conf[b].reserve((size_t)chunk * 8))) return rc;
         if (c.prob && !prob_dev && (rc = f->prob[b].reserve((size_t)chunk * k * 8))) return rc;
         if (c.flags && !flags_dev && (rc = f->flags[b].reserve((size_t)chunk))) return rc;
+        if (c.cons && !cons_dev && (rc = f->cons[b].reserve((size_t)chunk * 3 * 4))) return rc;
     }
 
     const bool stage_any = !sig_dev || (c.sig_len && !len_dev) || !a0_dev || !a1_dev || (c.ok && !ok_dev);
@@ -226,6 +231,8 @@ int run(wdx_fp* f, const FpCall& c) {
         fa.dwell = c.dwell ? (dwell_dev ? c.dwell + (size_t)r0 * nb : (int64_t*)f->dwell[b].p) : nullptr;
         fa.stats = c.stats ? (stats_dev ? c.stats + (size_t)r0 * 6 : (double*)f->stats[b].p) : nullptr;
         fa.status = status_dev ? c.status + r0 : (int32_t*)f->status[b].p;
+        fa.cons_query = (const double*)f->cons_query.p;
+        fa.cons = c.cons ? (cons_dev ? c.cons + (size_t)r0 * 3 : (int32_t*)f->cons[b].p) : nullptr;
         if ((rc = launch_fp(f, fa, st))) return rc;
 
         int64_t* lab_d = nullptr;
@@ -248,6 +255,8 @@ int run(wdx_fp* f, const FpCall& c) {
         if (c.stats && !stats_dev)
             CUDA_TRY(cudaMemcpyAsync(c.stats + (size_t)r0 * 6, fa.stats, (size_t)cn * 6 * 8, cudaMemcpyDeviceToHost, st));
         if (!status_dev) CUDA_TRY(cudaMemcpyAsync(c.status + r0, fa.status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+        if (c.cons && !cons_dev)
+            CUDA_TRY(cudaMemcpyAsync(c.cons + (size_t)r0 * 3, fa.cons, (size_t)cn * 3 * 4, cudaMemcpyDeviceToHost, st));
         if (c.m) {
             if (!lab_dev) CUDA_TRY(cudaMemcpyAsync(c.labels + r0, lab_d, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
             if (c.conf && !conf_dev) CUDA_TRY(cudaMemcpyAsync(c.conf + r0, conf_d, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
@@ -299,13 +308,17 @@ int wdx_fp_create(const wdx_fp_config* cfg, int device, wdx_fp** out) {
         // device maximum so that handles cannot shrink each other's limit.
         cudaFuncAttributes fa;
         int optin = 0;
-        if (cudaFuncGetAttributes(&fa, (const void*)fingerprint_kernel) != cudaSuccess ||
+        cudaFuncAttributes fb;
+        if (cudaFuncGetAttributes(&fa, (const void*)fingerprint_kernel<false>) != cudaSuccess ||
+            cudaFuncGetAttributes(&fb, (const void*)fingerprint_kernel<true>) != cudaSuccess ||
             cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) {
             delete f;
             return fail(WDX_ERR_CUDA, "cannot query shared-memory limits: %s", cudaGetErrorString(cudaGetLastError()));
         }
-        f->smem_max = optin - (int)fa.sharedSizeBytes;
-        if (cudaFuncSetAttribute((const void*)fingerprint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        f->smem_max = optin - (int)std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);
+        if (cudaFuncSetAttribute((const void*)fingerprint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 f->smem_max) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)fingerprint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  f->smem_max) != cudaSuccess) {
             delete f;
             return fail(WDX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -331,12 +344,13 @@ void wdx_fp_destroy(wdx_fp* f) {
     if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
     for (int i = 0; i < 2; i++) {
         for (DevBuf* b : {&f->sig[i], &f->len[i], &f->a0[i], &f->a1[i], &f->ok[i], &f->fpt[i], &f->dwell[i], &f->stats[i],
-                          &f->status[i], &f->lab[i], &f->conf[i], &f->prob[i], &f->flags[i]})
+                          &f->status[i], &f->lab[i], &f->conf[i], &f->prob[i], &f->flags[i], &f->cons[i]})
             b->release();
         if (f->ev_h2d[i]) cudaEventDestroy(f->ev_h2d[i]);
         if (f->ev_free[i]) cudaEventDestroy(f->ev_free[i]);
     }
     f->maxlen.release();
+    f->cons_query.release();
     for (auto& e : f->tev) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -346,14 +360,52 @@ void wdx_fp_destroy(wdx_fp* f) {
     delete f;
 }
 
-int wdx_fp_extract(wdx_fp* f, const float* signals, int64_t n, int64_t stride, const int32_t* sig_len,
-                   const int64_t* adapter_start, const int64_t* adapter_end, const uint8_t* detect_ok,
-                   int clip_in_place, double* fpt, int64_t* dwell, double* stats, int32_t* status, void* stream) {
+int wdx_fp_set_consensus(wdx_fp* f, const wdx_fp_consensus* cc) {
+    if (!f) return fail(WDX_ERR_INVALID, "NULL fingerprint handle");
+    std::lock_guard<std::mutex> lk(f->mu);
+    if (!cc || cc->query_len == 0) {  // back to the plain segmentation
+        f->cfg.cons_len = 0;
+        return WDX_OK;
+    }
+    if (!cc->query || cc->query_len < 1 || cc->query_len > FP_MAX_QUERY)
+        return fail(WDX_ERR_INVALID, "consensus query of %d values outside [1,%d]", cc->query_len, FP_MAX_QUERY);
+    if (cc->barcode_segm_events < 1 || cc->barcode_segm_events > FP_MAX_EVENTS)
+        return fail(WDX_ERR_INVALID, "barcode_segm_events=%d outside [1,%d]", cc->barcode_segm_events, FP_MAX_EVENTS);
+    if (!(cc->penalty >= 0) || cc->psi_query_begin < 0 || cc->psi_series_begin < 0)
+        return fail(WDX_ERR_INVALID, "bad consensus penalty / psi");
+    CUDA_TRY(cudaSetDevice(f->device));
+    int rc = f->cons_query.reserve((size_t)cc->query_len * sizeof(double));
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    CUDA_TRY(cudaMemcpy(f->cons_query.p, cc->query, (size_t)cc->query_len * sizeof(double), cudaMemcpyHostToDevice));
+    f->cfg.cons_len = cc->query_len;
+    f->cfg.cons_seg_events = cc->barcode_segm_events;
+    f->cfg.cons_pen2 = cc->penalty * cc->penalty;
+    f->cfg.cons_psi_q = cc->psi_query_begin;
+    f->cfg.cons_psi_s = cc->psi_series_begin;
+    f->cfg.cons_ub_start = cc->ub_start;
+    f->cfg.cons_lb_end = cc->lb_end;
+    f->cfg.cons_ub_end = cc->ub_end;
+    return WDX_OK;
+}
+
+int wdx_fp_extract_ex(wdx_fp* f, const float* signals, int64_t n, int64_t stride, const int32_t* sig_len,
+                      const int64_t* adapter_start, const int64_t* adapter_end, const uint8_t* detect_ok,
+                      int clip_in_place, double* fpt, int64_t* dwell, double* stats, int32_t* status, int32_t* cons,
+                      void* stream) {
+    if (cons && f && f->cfg.cons_len == 0) return fail(WDX_ERR_INVALID, "`cons` needs wdx_fp_set_consensus first");
     FpCall c{};
     c.signals = signals; c.n = n; c.stride = stride; c.sig_len = sig_len; c.a0 = adapter_start; c.a1 = adapter_end;
     c.ok = detect_ok; c.clip_in_place = clip_in_place; c.fpt = fpt; c.dwell = dwell; c.stats = stats; c.status = status;
-    c.m = nullptr; c.user_stream = (cudaStream_t)stream;
+    c.cons = cons; c.m = nullptr; c.user_stream = (cudaStream_t)stream;
     return run(f, c);
+}
+
+int wdx_fp_extract(wdx_fp* f, const float* signals, int64_t n, int64_t stride, const int32_t* sig_len,
+                   const int64_t* adapter_start, const int64_t* adapter_end, const uint8_t* detect_ok,
+                   int clip_in_place, double* fpt, int64_t* dwell, double* stats, int32_t* status, void* stream) {
+    return wdx_fp_extract_ex(f, signals, n, stride, sig_len, adapter_start, adapter_end, detect_ok, clip_in_place, fpt,
+                             dwell, stats, status, nullptr, stream);
 }
 
 int wdx_fp_predict(wdx_fp* f, wdx_model* m, const float* signals, int64_t n, int64_t stride, const int32_t* sig_len,
@@ -364,7 +416,7 @@ int wdx_fp_predict(wdx_fp* f, wdx_model* m, const float* signals, int64_t n, int
     FpCall c{};
     c.signals = signals; c.n = n; c.stride = stride; c.sig_len = sig_len; c.a0 = adapter_start; c.a1 = adapter_end;
     c.ok = detect_ok; c.clip_in_place = 0; c.fpt = fpt; c.dwell = nullptr; c.stats = nullptr; c.status = status;
-    c.m = m; c.mode = mode; c.labels = labels; c.conf = conf; c.prob = prob; c.flags = flags;
+    c.cons = nullptr; c.m = m; c.mode = mode; c.labels = labels; c.conf = conf; c.prob = prob; c.flags = flags;
     c.user_stream = (cudaStream_t)stream;
     return run(f, c);
 }

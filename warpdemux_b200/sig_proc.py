@@ -1,6 +1,7 @@
 """Fingerprint extraction — host-side mirror of the reference's
-`warpdemux/sig_proc.py` for the path the shipped DTW-SVM models use
-(`detect_results_to_fpt`, sig_proc.py:394-605; non-consensus branch).
+`warpdemux/sig_proc.py`: `detect_results_to_fpt` (sig_proc.py:394-605), both the
+plain branch every shipped DTW-SVM model uses and the consensus-guided barcode
+refinement of the tRNA configurations (sig_proc.py:257-378, 451-521).
 
 The reference calls `detect_results_to_fpt` once per read inside a Python loop
 (file_proc.py:418-428).  Here a whole minibatch goes to the GPU in one call of
@@ -13,15 +14,16 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
 from .sharding import default_device
 
-FP_OK, FP_FAIL_SEGMENTATION, FP_FAIL_DETECT, FP_FAIL_NORMALIZE, FP_FAIL_TOO_LONG = 0, 1, 2, 3, 4
+FP_OK, FP_FAIL_SEGMENTATION, FP_FAIL_DETECT, FP_FAIL_NORMALIZE, FP_FAIL_TOO_LONG, FP_FAIL_CONSENSUS = 0, 1, 2, 3, 4, 5
 _FAIL_REASON = {
+    FP_FAIL_CONSENSUS: "consensus query outlier",               # sig_proc.py:500-521
     FP_FAIL_SEGMENTATION: "event segmentation failed",          # sig_proc.py:537-544
     FP_FAIL_NORMALIZE: "segment normalization failed",          # sig_proc.py:553-560
     FP_FAIL_TOO_LONG: "adapter slice exceeds the GPU shared-memory limit",
@@ -87,16 +89,53 @@ class FingerprintConfig:
     min_obs_per_base: int = 6
     running_stat_width: int = 12
     num_events: int = 110
-    barcode_num_events: int = 25
+    barcode_num_events: int = 25      # events kept (barcode_num_events, or barcode_num_events[1] with a consensus)
     max_slice_len: int = 0
+    # consensus-guided barcode refinement (segmentation.consensus_refinement; rna004_130bps@v1.0_tRNA.toml:13-29)
+    consensus: Optional[Tuple[float, ...]] = None   # warpdemux._consensus.ALL[consensus_model]; None = off
+    barcode_segm_events: int = 25                    # barcode_num_events[0]
+    consensus_penalty: float = 1.5
+    consensus_psi: Tuple[int, int, int, int] = (5, 0, 40, 0)
+    consensus_ub_start: int = 18
+    consensus_lb_end: int = 69
+    consensus_ub_end: int = 97
 
     @classmethod
-    def from_spc(cls, spc) -> "FingerprintConfig":
+    def trna(cls, consensus, **kw) -> "FingerprintConfig":
+        """rna004_130bps@v1.0_tRNA.toml (WDX4_tRNA / WDX4b_tRNA) with the given consensus query."""
+        base = dict(min_obs_per_base=9, running_stat_width=18, num_events=120, barcode_num_events=25)
+        base.update(kw)
+        return cls(consensus=tuple(float(v) for v in np.asarray(consensus).reshape(-1)), **base)
+
+    @classmethod
+    def from_spc(cls, spc, consensus_query=None) -> "FingerprintConfig":
         """From a reference `SigProcConfig` (or any object with the same attribute
         tree).  Raises for settings the GPU path does not implement."""
         seg, ext = spc.segmentation, spc.sig_extract
         if getattr(seg, "consensus_refinement", False):
-            raise NotImplementedError("consensus_refinement (tRNA fingerprints) is not on the GPU path")
+            if getattr(seg, "refinement_optimal_cpts", False):
+                raise NotImplementedError("refinement_optimal_cpts (ruptures KernelCPD) is not on the GPU path")
+            if getattr(seg, "consensus_subseq_match_normalization", "mean") != "mean":
+                raise NotImplementedError("consensus_subseq_match_normalization must be 'mean'")
+            if consensus_query is None or not np.size(consensus_query):
+                raise ValueError("consensus_refinement needs the consensus query (warpdemux._consensus.ALL[consensus_model])")
+            nb = seg.barcode_num_events
+            if isinstance(nb, (int, np.integer)):        # sig_proc.py:453-458
+                raise ValueError("barcode_num_events is an integer in consensus refinement mode, use a tuple instead")
+            psi = tuple(int(v) for v in seg.consensus_subseq_match_psi)
+            if len(psi) != 4 or psi[1] or psi[3]:
+                raise NotImplementedError("consensus_subseq_match_psi must be (begin_query, 0, begin_series, 0)")
+            if getattr(ext, "normalization", "none") != "none" or getattr(seg, "normalization", "mean") != "mean" \
+                    or getattr(seg, "accept_less_cpts", False):
+                raise NotImplementedError("only normalization none/mean and accept_less_cpts=false are on the GPU path")
+            return cls(padding=int(ext.padding), outlier_thresh=float(spc.core.sig_norm_outlier_thresh),
+                       min_obs_per_base=int(seg.min_obs_per_base), running_stat_width=int(seg.running_stat_width),
+                       num_events=int(seg.num_events), barcode_num_events=int(nb[1]),
+                       consensus=tuple(float(v) for v in np.asarray(consensus_query).reshape(-1)),
+                       barcode_segm_events=int(nb[0]), consensus_penalty=float(seg.consensus_subseq_match_penalty),
+                       consensus_psi=psi, consensus_ub_start=int(seg.consensus_subseq_match_ub_start),
+                       consensus_lb_end=int(seg.consensus_subseq_match_lb_end),
+                       consensus_ub_end=int(seg.consensus_subseq_match_ub_end))
         if getattr(ext, "normalization", "none") != "none":
             raise NotImplementedError("sig_extract.normalization must be 'none'")
         if getattr(seg, "normalization", "mean") != "mean":
@@ -117,6 +156,12 @@ class _CConfig(C.Structure):
                 ("max_slice_len", C.c_int32)]
 
 
+class _CConsensus(C.Structure):
+    _fields_ = [("query", C.c_void_p), ("query_len", C.c_int32), ("barcode_segm_events", C.c_int32),
+                ("penalty", C.c_double), ("psi_query_begin", C.c_int32), ("psi_series_begin", C.c_int32),
+                ("ub_start", C.c_int32), ("lb_end", C.c_int32), ("ub_end", C.c_int32)]
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -135,6 +180,7 @@ class FingerprintBatch:
     status: np.ndarray              # int32 [n]
     dwell: Optional[np.ndarray] = None   # int64 [n, barcode_num_events]
     stats: Optional[np.ndarray] = None   # float64 [n, 6]
+    cons: Optional[np.ndarray] = None    # int32 [n, 3] seg_cons_query_start, seg_cons_query_end, sig_barcode_start
 
 
 class Fingerprinter:
@@ -155,6 +201,14 @@ class Fingerprinter:
             h = C.c_void_p()
             dev = default_device() if self.device is None else int(self.device)
             _lib.check(lib.wdx_fp_create(C.byref(cc), dev, C.byref(h)), "wdx_fp_create")
+            if c.consensus is not None:
+                q = np.ascontiguousarray(c.consensus, dtype=np.float64)
+                cs = _CConsensus(q.ctypes.data, q.size, c.barcode_segm_events, c.consensus_penalty, c.consensus_psi[0],
+                                 c.consensus_psi[2], c.consensus_ub_start, c.consensus_lb_end, c.consensus_ub_end)
+                rc = lib.wdx_fp_set_consensus(h, C.byref(cs))
+                if rc != 0:
+                    lib.wdx_fp_destroy(h)
+                    _lib.check(rc, "wdx_fp_set_consensus")
             self._h = h
         return self._h
 
@@ -185,11 +239,11 @@ class Fingerprinter:
 
     # -- pointer-level calls (numpy arrays, torch tensors or addresses) --------
     def extract_raw(self, signals, n, stride, adapter_start, adapter_end, fpt, status, sig_len=None, detect_ok=None,
-                    dwell=None, stats=None, clip_in_place=False, stream: int = 0) -> None:
-        rc = _lib.load().wdx_fp_extract(self._handle(), _ptr(signals), int(n), int(stride), _ptr(sig_len),
-                                        _ptr(adapter_start), _ptr(adapter_end), _ptr(detect_ok), int(clip_in_place),
-                                        _ptr(fpt), _ptr(dwell), _ptr(stats), _ptr(status), stream or None)
-        _lib.check(rc, "wdx_fp_extract")
+                    dwell=None, stats=None, clip_in_place=False, stream: int = 0, cons=None) -> None:
+        rc = _lib.load().wdx_fp_extract_ex(self._handle(), _ptr(signals), int(n), int(stride), _ptr(sig_len),
+                                           _ptr(adapter_start), _ptr(adapter_end), _ptr(detect_ok), int(clip_in_place),
+                                           _ptr(fpt), _ptr(dwell), _ptr(stats), _ptr(status), _ptr(cons), stream or None)
+        _lib.check(rc, "wdx_fp_extract_ex")
 
     def predict_raw(self, device_model, signals, n, stride, adapter_start, adapter_end, mode, labels, status,
                     conf=None, prob=None, flags=None, fpt=None, sig_len=None, detect_ok=None, stream: int = 0) -> None:
@@ -228,10 +282,11 @@ class Fingerprinter:
         status = np.zeros(n, dtype=np.int32)
         dwell = np.zeros((n, nb), dtype=np.int64) if want_dwell else None
         stats = np.full((n, 6), np.nan, dtype=np.float64) if want_stats else None
+        cons = np.zeros((n, 3), dtype=np.int32) if self.config.consensus is not None else None
         if n:
             self.extract_raw(signals, n, signals.shape[1], a0, a1, fpt, status, sig_len=sl, detect_ok=ok, dwell=dwell,
-                             stats=stats, clip_in_place=clip_in_place)
-        return FingerprintBatch(fpt=fpt, status=status, dwell=dwell, stats=stats)
+                             stats=stats, clip_in_place=clip_in_place, cons=cons)
+        return FingerprintBatch(fpt=fpt, status=status, dwell=dwell, stats=stats, cons=cons)
 
     def extract_and_predict(self, model, signals, adapter_start, adapter_end, sig_len=None, detect_ok=None,
                             mode: Optional[str] = None, want_fpt: bool = False):
@@ -260,8 +315,8 @@ class Fingerprinter:
 _default_fp: Dict[Any, Fingerprinter] = {}
 
 
-def _fingerprinter_for(spc) -> Fingerprinter:
-    cfg = spc if isinstance(spc, FingerprintConfig) else FingerprintConfig.from_spc(spc)
+def _fingerprinter_for(spc, consensus_query=None) -> Fingerprinter:
+    cfg = spc if isinstance(spc, FingerprintConfig) else FingerprintConfig.from_spc(spc, consensus_query)
     key = (cfg, default_device())
     if key not in _default_fp:
         _default_fp[key] = Fingerprinter(cfg)
@@ -273,25 +328,31 @@ def _read_result(b: FingerprintBatch, r: int, dr) -> ReadResult:
     if st == FP_FAIL_DETECT:  # sig_proc.py:400-407
         return ReadResult(success=False, fail_reason=getattr(dr, "fail_reason", None), barcode_fpt=np.array([]),
                           dwell_times=np.array([]), detect_results=dr)
-    if st != FP_OK:
+    if st not in (FP_OK, FP_FAIL_CONSENSUS):
         return ReadResult(success=False, fail_reason=_FAIL_REASON.get(st, "unknown"), barcode_fpt=np.array([]),
                           dwell_times=np.array([]), detect_results=dr)
     s = b.stats[r]
+    extra = dict(adapter_dt_med=float(s[0]), adapter_dt_mad=float(s[1]), adapter_event_mean=float(s[2]),
+                 adapter_event_std=float(s[3]), adapter_event_med=float(s[4]), adapter_event_mad=float(s[5]))
+    if b.cons is not None:
+        extra.update(seg_cons_query_start=int(b.cons[r, 0]), seg_cons_query_end=int(b.cons[r, 1]),
+                     sig_barcode_start=int(b.cons[r, 2]))
+    if st == FP_FAIL_CONSENSUS:  # sig_proc.py:500-521: reported with the adapter statistics
+        return ReadResult(success=False, fail_reason=_FAIL_REASON[st], barcode_fpt=np.array([]),
+                          dwell_times=np.array([]), detect_results=dr, **extra)
     return ReadResult(success=True, fail_reason="", barcode_fpt=b.fpt[r].copy(), dwell_times=b.dwell[r].copy(),
-                      detect_results=dr, adapter_dt_med=float(s[0]), adapter_dt_mad=float(s[1]),
-                      adapter_event_mean=float(s[2]), adapter_event_std=float(s[3]), adapter_event_med=float(s[4]),
-                      adapter_event_mad=float(s[5]))
+                      detect_results=dr, **extra)
 
 
 def batch_detect_results_to_fpt(signals: np.ndarray, spc, detect_results: Sequence[Any],
                                 sig_len: Optional[Sequence[int]] = None,
-                                clip_in_place: bool = False) -> List[ReadResult]:
+                                clip_in_place: bool = False, consensus_query=None) -> List[ReadResult]:
     """Batched `detect_results_to_fpt`: signals float32 [n, m] (NaN-padded rows
     as `file_proc.yield_signals_from_pod5` builds them, file_proc.py:227-279),
     one DetectResults per row -> one ReadResult per row.  Like the reference's
     worker (file_proc.py:418-428) each padded row IS the signal; pass `sig_len`
     (samples per row) only to get the "signal without NaNs" behaviour instead."""
-    fp = _fingerprinter_for(spc)
+    fp = _fingerprinter_for(spc, consensus_query)
     n = len(detect_results)
     ok = np.array([bool(d.success) for d in detect_results], dtype=np.uint8)
     a0 = np.array([d.adapter_start if (d.success and d.adapter_start is not None) else 0 for d in detect_results],
@@ -313,8 +374,7 @@ def detect_results_to_fpt(calibrated_signal: np.ndarray, spc, detect_results,
     not contain NaNs (file_proc.py:194).  Like the reference, the winsorised
     adapter slice is written back into `calibrated_signal` when it is a
     C-contiguous float32 array."""
-    if np.size(consensus_query):
-        raise NotImplementedError("consensus-guided (tRNA) fingerprints are not on the GPU path")
     sig = np.asarray(calibrated_signal)
     in_place = sig.dtype == np.float32 and sig.ndim == 1 and sig.flags.c_contiguous and sig.flags.writeable
-    return batch_detect_results_to_fpt(sig.reshape(1, -1), spc, [detect_results], clip_in_place=in_place)[0]
+    return batch_detect_results_to_fpt(sig.reshape(1, -1), spc, [detect_results], clip_in_place=in_place,
+                                       consensus_query=consensus_query if np.size(consensus_query) else None)[0]

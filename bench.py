@@ -239,6 +239,64 @@ def fingerprint_stage(params_small, local, stream, seconds_cpu=6.0):
     return out
 
 
+def trna_stage(params_small, local, stream):
+    """BASELINE.json configs[3] (rank 0, N=1): consensus-guided (tRNA) fingerprint batch — the
+    rna004_130bps@v1.0_tRNA segmentation (120 events, sub-sequence alignment of the consensus,
+    second change-point pass, normalize_wrt) on consensus-shaped synthetic adapter signals, alone and
+    fused with DTW+SVC (WDX4 as the DTW-SVM shape proxy: the shipped tRNA classifier is CatBoost, out of scope)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from wdx_testutil import synth_trna_signals
+    from warpdemux_b200 import _lib
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import Fingerprinter, FingerprintConfig
+
+    with np.load(os.path.join(ROOT, "tests", "golden", "fingerprint_trna.npz")) as z:
+        consensus = z["consensus"].astype(np.float64)
+    base, reps, width = 512, 64, 9000
+    sig, a0, a1 = synth_trna_signals(consensus, base, seed=23, width=width)
+    lens = (~np.isnan(sig)).sum(axis=1)
+    sl = np.minimum(lens, a1 + 100) - np.maximum(0, a0 - 100)
+    n = base * reps
+    sd = torch.from_numpy(np.tile(sig, (reps, 1))).cuda()
+    a0d, a1d = torch.from_numpy(np.tile(a0, reps)).cuda(), torch.from_numpy(np.tile(a1, reps)).cuda()
+    fpt = torch.empty((n, 25), dtype=torch.float64, device="cuda")
+    st = torch.empty(n, dtype=torch.int32, device="cuda")
+    cap = int((sl.max() + 63) // 64 * 64)
+    fp = Fingerprinter(FingerprintConfig.trna(consensus, max_slice_len=cap), device=local)
+    fp.enable_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, it=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(it):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / it
+
+    ms = timed(lambda: fp.extract_raw(sd, n, width, a0d, a1d, fpt, st, stream=stream))
+    kms, kl = fp.last_kernel_ms()
+    ok = float((st == 0).float().mean().item())
+    bytes_alg = int(sl.sum()) * 4 * reps + n * 25 * 8
+    out = {"workload": f"consensus-shaped synthetic adapter signals: {n} reads x {width} samples float32 (mean adapter slice "
+                       f"{sl.mean():.0f}), rna004_130bps@v1.0_tRNA segmentation config, consensus of {consensus.size} events",
+           "reads_per_s": n / (ms * 1e-3), "kernel_ms": kms, "kernel_launches": kl, "ok_fraction": ok,
+           "algorithmic_GBps": bytes_alg / (kms * 1e-3) / 1e9}
+    mdl = DTW_SVM(params_small, device=local, mode="guarded")
+    lab = torch.empty(n, dtype=torch.int64, device="cuda")
+    dm = mdl._device_model()
+    ms2 = timed(lambda: fp.predict_raw(dm, sd, n, width, a0d, a1d, _lib.MODES["guarded"], lab, st, stream=stream))
+    out["fused_signals_to_calls"] = {"model": "WDX4_rna004_v1_0 (DTW-SVM shape proxy)", "reads_per_s": n / (ms2 * 1e-3),
+                                     "mode": "guarded"}
+    fp.close()
+    return out
+
+
 def config2_wdx4(params4, local, stream, n):
     """BASELINE.json configs[1]: WDX4 on n synthetic fingerprints, 1 B200, EXACT_F64 vs FAST_F32 (and GUARDED);
     label identity of GUARDED vs EXACT over the whole set."""
@@ -473,6 +531,10 @@ def run_ours(args):
             extras["fingerprint_stage"] = fingerprint_stage(small, local, stream)
         except Exception as e:  # noqa: BLE001
             extras["fingerprint_stage"] = {"error": repr(e)}
+        try:
+            extras["trna_consensus_stage"] = trna_stage(small, local, stream)
+        except Exception as e:  # noqa: BLE001
+            extras["trna_consensus_stage"] = {"error": repr(e)}
     barrier()
 
     if rank != 0:

@@ -305,6 +305,76 @@ int wdx_cnn_set_guard(wdx_cnn* c, double guard);
 int wdx_cnn_enable_timing(wdx_cnn* c, int on);
 int wdx_cnn_last_kernel_ms(wdx_cnn* c, double* ms, int* launches);
 
+/* ---- validation of the CNN's boundary predictions (the step between wdx_cnn_detect and wdx_fp_extract) ----
+ * Replaces adapted.detect.combined.validate_boundaries (warpdemux/adapted/adapted/detect/combined.py:409-683)
+ * as combined_detect_cnn calls it for every read of a minibatch (combined.py:211-221):
+ *   validate_boundaries(signal[:full_signal_len], Boundaries(0, pred[0], pred[1], pred[1:]), spc, full_signal_len)
+ * i.e. adapter median / MAD range check, open-pore detection (anomalies.py:16-35: adapter_start moves to the last
+ * open-pore sample), real_range_check (real_range.py:34-63), mean_var_shift_polyA_check over the poly(A)
+ * candidates (mvs.py:42-159) and the optional median-shift check.  mvs_detect_overwrite = true is not implemented
+ * (WDX_ERR_UNSUPPORTED); the partition statistics of DetectResults (signal_partitions.py:80-96) are not computed.
+ * Reads that fail are the ones the reference hands to its LLR fallback (combined.py:222-290) - that stays with the
+ * caller.  Ranges are [lo, hi] with -INFINITY / INFINITY for "None". */
+typedef struct {
+    int32_t min_obs_adapter;          /* core.min_obs_adapter                     (1000) */
+    int32_t detect_open_pores;        /* real_range.detect_open_pores             (1) */
+    int32_t real_signal_check;        /* real_range.real_signal_check             (1) */
+    int32_t mean_window;              /* real_range.mean_window                   (300) */
+    int32_t max_obs_local_range;      /* real_range.max_obs_local_range           (5000) */
+    int32_t open_pore_min_obs_diff;   /* find_open_pores(min_obs_diff)            (10) */
+    double open_pore_min;             /* find_open_pores(sig_range[0])            (200.0) */
+    double mean_start_range[2], mean_end_range[2], local_range[2], adapter_mad_range[2];
+    int32_t mvs_detect_check;         /* mvs_polya.mvs_detect_check               (1) */
+    int32_t mvs_detect_overwrite;     /* must be 0 */
+    int32_t pA_mean_window;           /* (20) */
+    int32_t pA_var_window;            /* (100) */
+    int32_t median_shift_window;      /* (1000) */
+    int32_t detect_med_shift;         /* med_shift.detect_med_shift               (0) */
+    int32_t med_shift_window;         /* (2000) */
+    int32_t reserved;
+    double pA_var_range[2], median_shift_range[2], polyA_med_range[2], polyA_local_range[2];
+    double pA_mean_range[2];                     /* used when not (-inf, inf) */
+    double pA_mean_adapter_med_scale_range[2];   /* else this range times the adapter median (combined.py:505-519) */
+    double med_shift_range[2];
+} wdx_validate_config;
+
+/* info[.][0]: 0 = success, else the reference's fail_reason */
+enum {
+    WDX_VAL_OK = 0,
+    WDX_VAL_NO_ADAPTER = 1,     /* "No adapter detected (primary)" */
+    WDX_VAL_ADAPTER_MAD = 2,    /* "adapter MAD check failed" */
+    WDX_VAL_OPEN_PORE = 3,      /* "Open pore too close to boundary" */
+    WDX_VAL_REAL_RANGE = 4,     /* "Real signal check failed" */
+    WDX_VAL_NO_POLYA = 5,       /* "No polya detected (primary)" */
+    WDX_VAL_MVS_NO_SIGNAL = 6,  /* "MVS polya check failed: not enough signal" */
+    WDX_VAL_MVS_CHECKS = 7,     /* "MVS polya check failed: " + names of the checks whose bit in info[.][1] is clear */
+    WDX_VAL_MED_SHIFT = 8,      /* "Median shift check failed" */
+    WDX_VAL_HAS_NAN = 9         /* the ValueError of combined.py:416-418 ("Signal contains nan values") */
+};
+#define WDX_VAL_NVALS 12
+
+typedef struct wdx_validate wdx_validate;
+
+int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate** out);
+void wdx_validate_destroy(wdx_validate* v);
+/*   signals  [n, stride] float32 calibrated pA rows, NaN padded (file_proc.py:241-262)
+ *   full_len [n] int32 full_signal_lens (may exceed stride)
+ *   preds    [n, ld] int64 wdx_cnn_detect's output: adapter end, poly(A) end candidates (0 = none)
+ *   success  [n] uint8 DetectResults.success
+ *   info     [n, 4] int32: fail code (WDX_VAL_*), check bits (bit0 mean, 1 var, 2 med, 3 range, 4 shift: set = passed),
+ *            number of open pores kept, 0
+ *   bounds   [n, 3] int64 adapter_start, adapter_end, polya_end (DetectResults fields)
+ *   vals     [n, WDX_VAL_NVALS] float64 or NULL: adapter median, adapter MAD (as thresholded), real_adapter_mean_start,
+ *            real_adapter_mean_end, real_adapter_local_range, mvs_detect_mean_at_loc, mvs_detect_var_at_loc,
+ *            mvs_detect_polya_med, mvs_detect_polya_local_range, mvs_detect_med_shift, adapter_rna_median_shift, NaN;
+ *            NaN where the reference leaves None
+ * Buffers may be host or device memory; stride * 4 bytes must fit in shared memory (<= ~54 000 samples). */
+int wdx_validate_run(wdx_validate* v, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
+                     const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
+                     void* stream);
+int wdx_validate_enable_timing(wdx_validate* v, int on);
+int wdx_validate_last_kernel_ms(wdx_validate* v, double* ms, int* launches);
+
 /* ---- introspection -------------------------------------------------------- */
 const char* wdx_last_error(void);
 int wdx_device_count(void);

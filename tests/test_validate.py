@@ -1,0 +1,144 @@
+"""Boundary validation (reference combined.py:409-683).
+CPU: the numpy restatement (oracle/wdx_oracle_validate.py) against the fixture produced by the reference's
+own validate_boundaries (tests/golden/validate_rna004.npz: 64 real reads + 540 synthetic rows that reach
+every fail_reason).  GPU: validate_kernel through the C ABI against the same fixture and the oracle.
+Bar: success flags, fail reasons, boundaries and open-pore counts identical; the float statistics
+bit-identical (they are float32 order statistics / numpy-ordered sums), float64 tolerance 0."""
+import dataclasses
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD
+from wdx_testutil import pack_rows, validate_golden_inputs
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with np.load(os.path.join(GOLD, "validate_rna004.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def gold_cnn():
+    with np.load(os.path.join(GOLD, "cnn_detect_rna004.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def inputs(gold, gold_cnn):
+    return validate_golden_inputs(gold, gold_cnn)
+
+
+def _ocfg(gold):
+    from oracle import wdx_oracle_validate as ov
+
+    d = json.loads(str(gold["cfg"]))
+    return ov.ValidateConfig(**{k: tuple(v) if isinstance(v, list) else v for k, v in d.items()})
+
+
+def test_oracle_matches_reference_validate_boundaries(gold, inputs):
+    from oracle import wdx_oracle_validate as ov
+
+    rows, lens, preds = inputs
+    cfg = _ocfg(gold)
+    assert len(set(gold["reasons"].tolist())) >= 12          # every fail_reason of the config is in the fixture
+    assert gold["success"][: int(gold["n_real"])].sum() >= 40  # most real reads validate
+    for i in range(len(rows)):
+        r = ov.validate_one(rows[i], int(lens[i]), int(preds[i, 0]), preds[i, 1:], cfg)
+        assert bool(r["success"]) == bool(gold["success"][i]), i
+        assert (ov.fail_reason(r["code"], r["checks"]) or "") == str(gold["reasons"][i]), i
+        if gold["success"][i]:
+            assert (r["adapter_start"], r["adapter_end"], r["polya_end"]) == tuple(gold["bounds"][i]), i
+        assert np.array_equal(r["vals"][2:11], gold["vals"][i, 2:11], equal_nan=True), i
+        assert r["n_open_pores"] == gold["n_open_pores"][i], i
+
+
+def test_config_mirror_matches_oracle_config(gold):
+    """The product's ValidateConfig carries the same fields and defaults as the oracle's."""
+    from warpdemux_b200.detect import combined
+
+    want = json.loads(str(gold["cfg"]))
+    got = dataclasses.asdict(combined.ValidateConfig())
+    for k, v in want.items():
+        g = got[k]
+        assert (list(g) if isinstance(g, tuple) else g) == v, k
+    assert combined.fail_reason(7, 0b10100) == "MVS polya check failed: mean var range"
+    assert combined.fail_reason(2) == "adapter MAD check failed"
+
+
+@pytest.mark.gpu
+def test_gpu_validate_matches_reference_and_oracle(gold, inputs):
+    from oracle import wdx_oracle_validate as ov
+    from warpdemux_b200.detect import combined
+
+    rows, lens, preds = inputs
+    sig = pack_rows(rows)
+    cfg = _ocfg(gold)
+    v = combined.Validator(combined.ValidateConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)}), device=0)
+    vb = v.validate(sig, lens, preds)
+    n = len(rows)
+    bad = []
+    for i in range(n):
+        reason = vb.fail_reason(i) or ""
+        ok = (bool(vb.success[i]) == bool(gold["success"][i]) and reason == str(gold["reasons"][i])
+              and (not gold["success"][i] or tuple(vb.bounds[i]) == tuple(gold["bounds"][i]))
+              and vb.n_open_pores[i] == gold["n_open_pores"][i]
+              and np.array_equal(vb.vals[i, 2:11], gold["vals"][i, 2:11], equal_nan=True))
+        if not ok:
+            bad.append((i, reason, str(gold["reasons"][i]), vb.bounds[i].tolist(), gold["bounds"][i].tolist(),
+                        vb.vals[i, 2:11].tolist(), gold["vals"][i, 2:11].tolist()))
+    assert not bad, bad[:5]
+    # against the oracle: also the thresholded adapter median / MAD and the boundaries of failed reads
+    osuc, ocode, ochk, obounds, ovals, opores = ov.validate_batch(sig, lens, preds, cfg)
+    assert np.array_equal(vb.success, osuc) and np.array_equal(vb.code, ocode) and np.array_equal(vb.checks, ochk)
+    assert np.array_equal(vb.bounds, obounds) and np.array_equal(vb.n_open_pores, opores)
+    assert np.array_equal(vb.vals, ovals, equal_nan=True)
+    v.close()
+
+
+@pytest.mark.gpu
+def test_gpu_validate_device_buffers_and_variants(gold, inputs):
+    """Device-resident buffers (the chained CNN -> validation -> fingerprint use), a config with the median-shift
+    check on and explicit pA_mean_range, empty batch, oversize rows."""
+    import torch
+
+    from oracle import wdx_oracle_validate as ov
+    from warpdemux_b200 import _lib
+    from warpdemux_b200.detect import combined
+
+    rows, lens, preds = inputs
+    sel = list(range(0, len(rows), 3))
+    sig = pack_rows([rows[i] for i in sel])
+    lens, preds = lens[sel], preds[sel]
+    ocfg = dataclasses.replace(_ocfg(gold), detect_med_shift=True, med_shift_window=700, med_shift_range=(8.0, ov.INF),
+                               pA_mean_range=(95.0, 160.0), polyA_local_range=(2.0, 14.0), polyA_med_range=(90.0, 150.0),
+                               mean_start_range=(60.0, 100.0), max_obs_local_range=1500, mean_window=250)
+    v = combined.Validator(combined.ValidateConfig(**{f.name: getattr(ocfg, f.name) for f in dataclasses.fields(ocfg)}), device=0)
+    n = sig.shape[0]
+    d_sig = torch.from_numpy(sig).cuda()
+    d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
+    d_preds = torch.from_numpy(preds).cuda()
+    d_suc = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_info = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    d_bounds = torch.zeros((n, 3), dtype=torch.int64, device="cuda")
+    d_vals = torch.zeros((n, combined.N_VALS), dtype=torch.float64, device="cuda")
+    v.run_raw(d_sig, n, sig.shape[1], d_len, d_preds, preds.shape[1], d_suc, d_info, d_bounds, d_vals,
+              stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    osuc, ocode, ochk, obounds, ovals, opores = ov.validate_batch(sig, lens, preds, ocfg)
+    assert len(set(ocode.tolist())) >= 7
+    assert np.array_equal(d_suc.cpu().numpy(), osuc)
+    info = d_info.cpu().numpy()
+    assert np.array_equal(info[:, 0], ocode) and np.array_equal(info[:, 1], ochk) and np.array_equal(info[:, 2], opores)
+    assert np.array_equal(d_bounds.cpu().numpy(), obounds)
+    assert np.array_equal(d_vals.cpu().numpy(), ovals, equal_nan=True)
+    # empty batch is a no-op; rows too long for shared memory are refused, not truncated
+    v.run_raw(d_sig, 0, sig.shape[1], d_len, d_preds, preds.shape[1], d_suc, d_info, d_bounds)
+    with pytest.raises(_lib.WdxError):
+        v.run_raw(d_sig, 1, 100000, d_len, d_preds, preds.shape[1], d_suc, d_info, d_bounds)
+    v.close()
+    with pytest.raises(_lib.WdxError):
+        combined.Validator(combined.ValidateConfig(mvs_detect_overwrite=True), device=0)._handle()

@@ -165,3 +165,30 @@ def oracle_fingerprints_consensus(sig, a0, a1, consensus, detect_ok=None, **cfg)
             stats[r] = [s[k] for k in keys]
             cons[r] = c
     return status, fpt, dwell, stats, cons
+
+
+def validate_golden_inputs(gold_val, gold_cnn):
+    """Inputs of tests/golden/validate_rna004.npz (oracle/make_golden_validate.py): the real reads of the CNN
+    fixture with the reference CNN's own predictions, then synthetic rows rebuilt from their seeds.
+    Returns (list of float32 rows, full_lens int64[n], preds int64[n, 1 + k])."""
+    from oracle import wdx_oracle_validate as ov
+
+    n_real, n_syn, k = int(gold_val["n_real"]), int(gold_val["n_syn"]), int(gold_val["k"])
+    real = cnn_golden_signals(gold_cnn)
+    assert real.shape[0] == n_real
+    rows = [real[i] for i in range(n_real)]
+    preds = [gold_cnn["preds"][i] for i in range(n_real)]
+    for s in range(n_syn):
+        row, _fl, pr = ov.synthetic_case(s, k=k)
+        rows.append(row)
+        preds.append(pr)
+    return rows, gold_val["full_lens"].astype(np.int64), np.array(preds, dtype=np.int64)
+
+
+def pack_rows(rows, fill=np.nan):
+    """Ragged float32 rows -> one NaN-padded [n, max_len] minibatch."""
+    m = max(r.size for r in rows)
+    out = np.full((len(rows), m), fill, dtype=np.float32)
+    for i, r in enumerate(rows):
+        out[i, : r.size] = r
+    return out

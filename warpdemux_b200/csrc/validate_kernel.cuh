@@ -1,0 +1,389 @@
+// validate_kernel.cuh — validation of CNN boundary predictions, one CTA per read (sm_100a).
+//
+// The step between the boundary CNN and the fingerprint stage.  Restates, for
+// mvs_detect_overwrite = false (every shipped configuration), the reference's per-read Python chain
+//   validate_boundaries                 warpdemux/adapted/adapted/detect/combined.py:409-683
+//     adapter median / MAD (float32)    combined.py:452-467
+//     find_open_pores                   adapted/detect/anomalies.py:16-35
+//     real_range_check                  adapted/detect/real_range.py:34-63   (np.mean float32, np.percentile)
+//     mean_var_shift_polyA_check        adapted/detect/mvs.py:42-159          (moving mean / variance medians,
+//                                                                              median, percentiles, median shift)
+//     median-shift check                combined.py:612-629
+// as ONE persistent kernel: a CTA stages the row of one read in shared memory (read from HBM once,
+// coalesced) and evaluates every check on-chip; per read 1 byte of verdict, three boundaries and a few
+// statistics go back.  HBM-bound by construction: algorithmic bytes per read = 4 * min(len, stride).
+//
+// Exactness (this TU is compiled with -fmad=false): medians and percentiles are exact order statistics
+// found by radix selection on order-preserving keys; float32 / float64 sums follow numpy's pairwise
+// summation order; np.percentile's linear interpolation is evaluated in float64 as numpy does.  The
+// sequential open-pore scan is replaced by its closed form: position i is kept iff an earlier open-pore
+// sample exists and none lies within min_obs_diff - 1 samples before i.
+// bottleneck.move_mean / move_var (third-party, float32 out) are computed per window in float64
+// (exact window mean; two-pass variance), as documented — not bottleneck's running update.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "block_select.cuh"
+
+namespace wdx {
+
+enum {
+    VAL_OK = 0, VAL_NO_ADAPTER = 1, VAL_ADAPTER_MAD = 2, VAL_OPEN_PORE = 3, VAL_REAL_RANGE = 4, VAL_NO_POLYA = 5,
+    VAL_MVS_NO_SIGNAL = 6, VAL_MVS_CHECKS = 7, VAL_MED_SHIFT = 8, VAL_HAS_NAN = 9
+};
+constexpr int VAL_NVALS = 12;
+
+struct ValCfg {
+    int min_obs_adapter;
+    int detect_open_pores, real_signal_check, mean_window, max_obs_local_range;
+    double mean_start_lo, mean_start_hi, mean_end_lo, mean_end_hi, local_range_lo, local_range_hi, mad_lo, mad_hi;
+    float open_pore_min;
+    int open_pore_min_obs_diff;
+    int mvs_detect_check, pa_mean_window, pa_var_window, median_shift_window;
+    double var_lo, var_hi, shift_lo, shift_hi, pmed_lo, pmed_hi, plr_lo, plr_hi, mean_lo, mean_hi, scale_lo, scale_hi;
+    int mean_from_scale;  // pA_mean_range empty and pA_mean_adapter_med_scale_range set (combined.py:505-519)
+    int detect_med_shift, med_shift_window;
+    double ms_lo, ms_hi;
+};
+
+struct ValArgs {
+    const float* signals;      // [n][stride] calibrated pA, NaN padded
+    int64_t stride;
+    const int32_t* full_len;   // [n] full_signal_lens (may exceed stride)
+    const int64_t* preds;      // [n][ld] adapter end, poly(A) end candidates (cnn_detect's output)
+    int ld;
+    int64_t n;
+    uint8_t* success;          // [n]
+    int32_t* info;             // [n][4] fail code, check bits (bit i = check i passed), open pores kept, 0
+    int64_t* bounds;           // [n][3] adapter_start, adapter_end, polya_end
+    double* vals;              // [n][VAL_NVALS] or nullptr
+    float* scratch;            // [gridDim.x][stride] moving-window statistics
+};
+
+// numpy's pairwise summation (np.add.reduce on a contiguous 1-D array), any n.
+template <typename T, typename F>
+__device__ T np_pairwise(int lo, int n, F at) {
+    if (n < 8) {
+        T r = (T)0;
+        for (int i = 0; i < n; i++) r = r + at(lo + i);
+        return r;
+    }
+    if (n <= 128) {
+        T r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = at(lo + j);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = r[j] + at(lo + i + j);
+        }
+        T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res = res + at(lo + i);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const T a = np_pairwise<T>(lo, n2, at);
+    const T b = np_pairwise<T>(lo + n2, n - n2, at);
+    return a + b;
+}
+
+// k-th and (k+1)-th smallest (0-based) of n float32 values given through VAL.  All threads get both.
+template <typename VAL>
+__device__ void block_order2(int n, uint32_t k, VAL val, FpScratch& s, float* v_k, float* v_k1) {
+    auto key = [&](int i) { return f32_key(val(i)); };
+    const uint32_t key_lo = block_select_u32(n, k, key, s);
+    *v_k = f32_unkey(key_lo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.hist[0] = 0;            // count(key <= key_lo)
+        s.hist[1] = 0xffffffffu;  // min key > key_lo
+    }
+    __syncthreads();
+    uint32_t cnt = 0, mn = 0xffffffffu;
+    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
+        const uint32_t kv = key(i);
+        if (kv <= key_lo) cnt++;
+        else mn = min(mn, kv);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s.hist[0], cnt);
+        atomicMin(&s.hist[1], mn);
+    }
+    __syncthreads();
+    const uint32_t c = s.hist[0], m = s.hist[1];
+    *v_k1 = (c >= k + 2 || m == 0xffffffffu) ? *v_k : f32_unkey(m);
+    __syncthreads();
+}
+
+// np.median / np.nanmedian of n NaN-free float32 values (NaN for n == 0, as numpy returns for an empty slice).
+template <typename VAL>
+__device__ float val_median(int n, VAL val, FpScratch& s) {
+    if (n <= 0) return __int_as_float(0x7fc00000);
+    float a, b;
+    block_order2(n, (uint32_t)((n - 1) / 2), val, s, &a, &b);
+    if (n & 1) return a;
+    return __fdiv_rn(__fadd_rn(a, b), 2.0f);
+}
+
+// np.percentile(x, q) of n >= 1 float32 values, method "linear": float64 result.
+template <typename VAL>
+__device__ double val_percentile(int n, double q, VAL val, FpScratch& s) {
+    const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(q, 100.0));
+    int prev = (int)floor(vi);
+    prev = max(0, min(prev, n - 1));
+    const double g = __dsub_rn(vi, (double)prev);
+    float a, b;
+    block_order2(n, (uint32_t)prev, val, s, &a, &b);
+    if (prev + 1 > n - 1) b = a;
+    const double d = (double)__fsub_rn(b, a);   // subtract(b, a) on float32
+    double r = (g >= 0.5) ? __dsub_rn((double)b, __dmul_rn(d, __dsub_rn(1.0, g))) : __dadd_rn((double)a, __dmul_rn(d, g));
+    if (b == a) r = (double)a;                  // _lerp: where(b == a, a, lerp)
+    return r;
+}
+
+__device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
+
+__global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, const ValCfg c) {
+    extern __shared__ float vsig[];
+    __shared__ FpScratch s;
+    __shared__ int sh_i[6];
+    __shared__ double sh_d[4];
+    const int tid = threadIdx.x;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    float* scratch = a.scratch + (size_t)blockIdx.x * a.stride;
+
+    for (int64_t r = blockIdx.x; r < a.n; r += gridDim.x) {
+        __syncthreads();
+        const float* row = a.signals + (size_t)r * a.stride;
+        const int64_t fl = a.full_len[r];
+        const int L = (int)max((int64_t)0, min(fl, a.stride));
+        int has_nan = 0;
+        for (int i = tid; i < L; i += FP_THREADS) {
+            const float x = row[i];
+            vsig[i] = x;
+            has_nan |= (x != x);
+        }
+        has_nan = __syncthreads_or(has_nan);
+
+        const int64_t* pr = a.preds + (size_t)r * a.ld;
+        const int64_t a1 = pr[0];
+        int64_t a0 = 0;
+        int64_t pe_best = a.ld > 1 ? pr[1] : 0;
+        int code = VAL_OK, checks = 0, n_pores = 0;
+        double v[VAL_NVALS];
+#pragma unroll
+        for (int j = 0; j < VAL_NVALS; j++) v[j] = qnan;
+
+        if (has_nan) code = VAL_HAS_NAN;
+        const int hi = (int)max((int64_t)0, min(a1, (int64_t)L));   // sig[a0:a1] ends here
+        float med = 0.f, mad = 0.f;
+        if (code == VAL_OK) {
+            if (a1 == 0) code = VAL_NO_ADAPTER;
+            else {
+                med = val_median(hi, [&](int i) { return vsig[i]; }, s);
+                mad = val_median(hi, [&](int i) { return fabsf(__fsub_rn(vsig[i], med)); }, s);
+                v[0] = (double)med;
+                v[1] = (double)mad;
+            }
+        }
+        if (code == VAL_OK && mad != 0.f && !val_in_range((double)mad, c.mad_lo, c.mad_hi)) code = VAL_ADAPTER_MAD;
+
+        if (code == VAL_OK && c.detect_open_pores) {
+            __syncthreads();
+            if (tid == 0) {
+                sh_i[0] = 0;           // open-pore samples
+                sh_i[1] = 0x7fffffff;  // first
+                sh_i[2] = -1;          // last
+                sh_i[3] = -1;          // last kept
+                sh_i[4] = 0;           // kept
+            }
+            __syncthreads();
+            const float lo = c.open_pore_min;
+            for (int i = tid; i < hi; i += FP_THREADS) {
+                if (vsig[i] >= lo) {
+                    atomicAdd(&sh_i[0], 1);
+                    atomicMin(&sh_i[1], i);
+                    atomicMax(&sh_i[2], i);
+                }
+            }
+            __syncthreads();
+            const int first = sh_i[1];
+            const int D = c.open_pore_min_obs_diff;
+            for (int i = tid; i < hi; i += FP_THREADS) {
+                if (vsig[i] >= lo && first < i) {
+                    bool near = false;
+                    for (int q = max(0, i - D + 1); q < i; q++) near |= (vsig[q] >= lo);
+                    if (!near) {
+                        atomicMax(&sh_i[3], i);
+                        atomicAdd(&sh_i[4], 1);
+                    }
+                }
+            }
+            __syncthreads();
+            const int cnt = sh_i[0];
+            if (cnt > 1) {
+                n_pores = sh_i[4] > 0 ? sh_i[4] : 1;
+                a0 = sh_i[4] > 0 ? sh_i[3] : sh_i[2];
+            } else if (cnt == 1) {
+                n_pores = 1;
+                a0 = first;
+            }
+            if (cnt > 0 && a1 - a0 < c.min_obs_adapter) code = VAL_OPEN_PORE;
+        }
+
+        if (code == VAL_OK && c.real_signal_check) {
+            const int b0 = (int)min(a0, (int64_t)hi);
+            const int nseg = hi - b0;
+            bool ok = false;
+            if (nseg >= 2 * c.mean_window) {
+                __syncthreads();
+                if (tid == 0 || tid == 32) {
+                    const int base = tid == 0 ? b0 : hi - c.mean_window;
+                    const float sm = np_pairwise<float>(base, c.mean_window, [&](int i) { return vsig[i]; });
+                    sh_d[tid == 0 ? 0 : 1] = (double)__fdiv_rn(sm, (float)c.mean_window);
+                }
+                __syncthreads();
+                v[2] = sh_d[0];
+                v[3] = sh_d[1];
+                if (val_in_range(v[2], c.mean_start_lo, c.mean_start_hi) && val_in_range(v[3], c.mean_end_lo, c.mean_end_hi)) {
+                    const int nn = min(c.max_obs_local_range, nseg);
+                    const int base = hi - nn;
+                    const double p85 = val_percentile(nn, 85.0, [&](int i) { return vsig[base + i]; }, s);
+                    const double p15 = val_percentile(nn, 15.0, [&](int i) { return vsig[base + i]; }, s);
+                    v[4] = __dsub_rn(p85, p15);
+                    ok = val_in_range(v[4], c.local_range_lo, c.local_range_hi);
+                }
+            }
+            if (!ok) code = VAL_REAL_RANGE;
+        }
+
+        if (code == VAL_OK && c.mvs_detect_check) {
+            if (pe_best == 0) code = VAL_NO_POLYA;
+            else {
+                double mlo = c.mean_lo, mhi = c.mean_hi;
+                if (c.mean_from_scale) {
+                    mlo = __dmul_rn(c.scale_lo, (double)med);
+                    mhi = __dmul_rn(c.scale_hi, (double)med);
+                }
+                const int e = (int)a1;   // a1 <= L here or the size test below fails first
+                for (int j = 1; j < a.ld; j++) {
+                    const int64_t pe = pr[j];
+                    if (pe == 0) break;
+                    double r_mean = 0.0, r_var = 0.0, r_med = 0.0, r_lr = 0.0, r_shift = 0.0;
+                    bool okc = false;
+                    int bits = 0;
+                    const bool early = pe < a1 || pe - a1 <= 2 || (int64_t)L < a1 + c.median_shift_window;
+                    if (!early) {
+                        const int pend = (int)min(pe, (int64_t)L);
+                        const int m = pend - e;
+                        const int64_t nominal = pe - a1;
+                        // variance
+                        if (nominal <= c.pa_var_window + 2) {
+                            __syncthreads();
+                            if (tid == 0) {
+                                const float mu = __fdiv_rn(np_pairwise<float>(e, m, [&](int i) { return vsig[i]; }), (float)m);
+                                const float ss = np_pairwise<float>(e, m, [&](int i) {
+                                    const float d = __fsub_rn(vsig[i], mu);
+                                    return __fmul_rn(d, d);
+                                });
+                                sh_d[0] = (double)__fdiv_rn(ss, (float)m);
+                            }
+                            __syncthreads();
+                            r_var = sh_d[0];
+                        } else {
+                            const int w = c.pa_var_window, cnt = m - w + 1;
+                            __syncthreads();
+                            for (int p = tid; p < cnt; p += FP_THREADS) {
+                                const double mu = __ddiv_rn(np_pairwise<double>(e + p, w, [&](int i) { return (double)vsig[i]; }), (double)w);
+                                const double ss = np_pairwise<double>(e + p, w, [&](int i) {
+                                    const double d = __dsub_rn((double)vsig[i], mu);
+                                    return __dmul_rn(d, d);
+                                });
+                                scratch[p] = (float)__ddiv_rn(ss, (double)w);
+                            }
+                            __syncthreads();
+                            r_var = (double)val_median(cnt, [&](int i) { return scratch[i]; }, s);
+                        }
+                        // mean
+                        if (nominal <= c.pa_mean_window + 2) {
+                            __syncthreads();
+                            if (tid == 0)
+                                sh_d[0] = (double)__fdiv_rn(np_pairwise<float>(e, m, [&](int i) { return vsig[i]; }), (float)m);
+                            __syncthreads();
+                            r_mean = sh_d[0];
+                        } else {
+                            const int w = c.pa_mean_window, cnt = m - w + 1;
+                            __syncthreads();
+                            for (int p = tid; p < cnt; p += FP_THREADS)
+                                scratch[p] = (float)__ddiv_rn(np_pairwise<double>(e + p, w, [&](int i) { return (double)vsig[i]; }), (double)w);
+                            __syncthreads();
+                            r_mean = (double)val_median(cnt, [&](int i) { return scratch[i]; }, s);
+                        }
+                        r_med = (double)val_median(m, [&](int i) { return vsig[e + i]; }, s);
+                        const double p85 = val_percentile(m, 85.0, [&](int i) { return vsig[e + i]; }, s);
+                        const double p15 = val_percentile(m, 15.0, [&](int i) { return vsig[e + i]; }, s);
+                        r_lr = __dsub_rn(p85, p15);
+                        const int up = min(e + c.median_shift_window, L), dn = max(e - c.median_shift_window, 0);
+                        const float m_after = val_median(up - e, [&](int i) { return vsig[e + i]; }, s);
+                        const float m_before = val_median(e - dn, [&](int i) { return vsig[dn + i]; }, s);
+                        r_shift = (double)__fsub_rn(m_after, m_before);
+                        bits = (val_in_range(r_mean, mlo, mhi) ? 1 : 0) | (val_in_range(r_var, c.var_lo, c.var_hi) ? 2 : 0) |
+                               (val_in_range(r_med, c.pmed_lo, c.pmed_hi) ? 4 : 0) | (val_in_range(r_lr, c.plr_lo, c.plr_hi) ? 8 : 0) |
+                               (val_in_range(r_shift, c.shift_lo, c.shift_hi) ? 16 : 0);
+                        okc = bits == 31;
+                    }
+                    v[5] = r_mean;
+                    v[6] = r_var;
+                    v[7] = r_med;
+                    v[8] = r_lr;
+                    v[9] = r_shift;
+                    if (!okc) {   // `success` is never set back to True: later candidates only overwrite the report
+                        if (r_mean == 0.0) {
+                            code = VAL_MVS_NO_SIGNAL;
+                            checks = 0;
+                        } else {
+                            code = VAL_MVS_CHECKS;
+                            checks = bits;
+                        }
+                    }
+                    if (code == VAL_OK) {
+                        pe_best = pe;
+                        break;
+                    }
+                }
+            }
+        }
+
+        if (code == VAL_OK && c.detect_med_shift) {
+            const int e = (int)min(a1, (int64_t)L);
+            const int up = (int)min(min(a1 + c.med_shift_window, fl), (int64_t)L), dn = (int)max(a1 - c.med_shift_window, (int64_t)0);
+            const float m_after = val_median(max(0, up - e), [&](int i) { return vsig[e + i]; }, s);
+            const float m_before = val_median(max(0, e - min(dn, e)), [&](int i) { return vsig[min(dn, e) + i]; }, s);
+            v[10] = (double)__fsub_rn(m_after, m_before);
+            if (!val_in_range(v[10], c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
+        }
+
+        if (tid == 0) {
+            a.success[r] = code == VAL_OK;
+            a.info[r * 4 + 0] = code;
+            a.info[r * 4 + 1] = checks;
+            a.info[r * 4 + 2] = n_pores;
+            a.info[r * 4 + 3] = 0;
+            a.bounds[r * 3 + 0] = a0;
+            a.bounds[r * 3 + 1] = a1;
+            a.bounds[r * 3 + 2] = pe_best;
+            if (a.vals)
+                for (int j = 0; j < VAL_NVALS; j++) a.vals[r * VAL_NVALS + j] = v[j];
+        }
+    }
+}
+
+}  // namespace wdx

@@ -1,0 +1,223 @@
+// wdx_validate.cu — C-ABI entry points of the boundary validation step (include/wdx_b200.h:
+// wdx_validate_*): handle, staging of host buffers, launch of validate_kernel.  No CPU compute path.
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "validate_kernel.cuh"
+#include "wdx_internal.cuh"
+
+using namespace wdx;
+
+struct wdx_validate {
+    ValCfg cfg{};
+    int device = 0;
+    int sm_count = 148;
+    int smem_max = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    DevBuf sig, len, preds, success, info, bounds, vals, scratch;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+bool range_empty(const double* r) { return r[0] == -INFINITY && r[1] == INFINITY; }
+}  // namespace
+
+extern "C" {
+
+int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate** out) {
+    if (!cfg || !out) return fail(WDX_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (cfg->mvs_detect_overwrite) return fail(WDX_ERR_UNSUPPORTED, "mvs_detect_overwrite = true is not implemented");
+    if (cfg->mean_window < 1 || cfg->max_obs_local_range < 1 || cfg->pA_mean_window < 1 || cfg->pA_var_window < 1 ||
+        cfg->median_shift_window < 1 || cfg->med_shift_window < 1 || cfg->min_obs_adapter < 0 || cfg->open_pore_min_obs_diff < 1)
+        return fail(WDX_ERR_INVALID, "window sizes must be positive");
+    const bool from_scale = range_empty(cfg->pA_mean_range) && !range_empty(cfg->pA_mean_adapter_med_scale_range);
+    if (cfg->mvs_detect_check && !from_scale && range_empty(cfg->pA_mean_range))
+        return fail(WDX_ERR_INVALID, "pA_mean_range is not specified");   // combined.py:521-522 raises the same
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(WDX_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(WDX_ERR_INVALID, "device %d of %d", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    wdx_validate* h = new (std::nothrow) wdx_validate();
+    if (!h) return fail(WDX_ERR_NOMEM, "out of host memory");
+    h->device = device;
+    ValCfg& c = h->cfg;
+    c.min_obs_adapter = cfg->min_obs_adapter;
+    c.detect_open_pores = cfg->detect_open_pores;
+    c.real_signal_check = cfg->real_signal_check;
+    c.mean_window = cfg->mean_window;
+    c.max_obs_local_range = cfg->max_obs_local_range;
+    c.mean_start_lo = cfg->mean_start_range[0];
+    c.mean_start_hi = cfg->mean_start_range[1];
+    c.mean_end_lo = cfg->mean_end_range[0];
+    c.mean_end_hi = cfg->mean_end_range[1];
+    c.local_range_lo = cfg->local_range[0];
+    c.local_range_hi = cfg->local_range[1];
+    c.mad_lo = cfg->adapter_mad_range[0];
+    c.mad_hi = cfg->adapter_mad_range[1];
+    c.open_pore_min = (float)cfg->open_pore_min;
+    c.open_pore_min_obs_diff = cfg->open_pore_min_obs_diff;
+    c.mvs_detect_check = cfg->mvs_detect_check;
+    c.pa_mean_window = cfg->pA_mean_window;
+    c.pa_var_window = cfg->pA_var_window;
+    c.median_shift_window = cfg->median_shift_window;
+    c.var_lo = cfg->pA_var_range[0];
+    c.var_hi = cfg->pA_var_range[1];
+    c.shift_lo = cfg->median_shift_range[0];
+    c.shift_hi = cfg->median_shift_range[1];
+    c.pmed_lo = cfg->polyA_med_range[0];
+    c.pmed_hi = cfg->polyA_med_range[1];
+    c.plr_lo = cfg->polyA_local_range[0];
+    c.plr_hi = cfg->polyA_local_range[1];
+    c.mean_lo = cfg->pA_mean_range[0];
+    c.mean_hi = cfg->pA_mean_range[1];
+    c.scale_lo = cfg->pA_mean_adapter_med_scale_range[0];
+    c.scale_hi = cfg->pA_mean_adapter_med_scale_range[1];
+    c.mean_from_scale = from_scale;
+    c.detect_med_shift = cfg->detect_med_shift;
+    c.med_shift_window = cfg->med_shift_window;
+    c.ms_lo = cfg->med_shift_range[0];
+    c.ms_hi = cfg->med_shift_range[1];
+    if ((double)c.open_pore_min != cfg->open_pore_min) {
+        delete h;
+        return fail(WDX_ERR_UNSUPPORTED, "open_pore_min must be representable in float32");
+    }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_max = (int)prop.sharedMemPerBlockOptin - 8192;
+    CUDA_TRY(cudaFuncSetAttribute(validate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_max));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    *out = h;
+    return WDX_OK;
+}
+
+void wdx_validate_destroy(wdx_validate* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->scratch}) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int wdx_validate_enable_timing(wdx_validate* h, int on) {
+    if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
+    h->timing = on != 0;
+    return WDX_OK;
+}
+
+int wdx_validate_last_kernel_ms(wdx_validate* h, double* ms, int* launches) {
+    if (!h || !ms) return fail(WDX_ERR_INVALID, "NULL argument");
+    *ms = 0.0;
+    if (launches) *launches = 0;
+    if (!h->timed) return WDX_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    float t = 0.f;
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+    *ms = t;
+    if (launches) *launches = 1;
+    return WDX_OK;
+}
+
+int wdx_validate_run(wdx_validate* h, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
+                     const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
+                     void* stream) {
+    if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
+    if (n < 0 || stride < 1 || ld < 1) return fail(WDX_ERR_INVALID, "n=%lld stride=%lld ld=%d", (long long)n, (long long)stride, ld);
+    if (n == 0) return WDX_OK;
+    if (!signals || !full_len || !preds || !success || !info || !bounds)
+        return fail(WDX_ERR_INVALID, "signals, full_len, preds, success, info and bounds are required");
+    const size_t smem = (size_t)stride * 4;
+    if ((int64_t)smem > h->smem_max)
+        return fail(WDX_ERR_UNSUPPORTED, "rows of %lld samples need %zu B of shared memory, device allows %d", (long long)stride, smem, h->smem_max);
+    std::lock_guard<std::mutex> lk(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc;
+    h->timed = false;
+
+    const float* sig_d = signals;
+    int sig_kind = mem_kind(signals);
+    if (sig_kind == 1) {   // pinned host rows: read once by the kernel, straight over PCIe
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, const_cast<float*>(signals), 0) == cudaSuccess && dptr) {
+            sig_d = (const float*)dptr;
+            sig_kind = 2;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (sig_kind != 2) {
+        if ((rc = h->sig.reserve((size_t)n * stride * 4))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->sig.p, signals, (size_t)n * stride * 4, cudaMemcpyHostToDevice, st));
+        sig_d = (const float*)h->sig.p;
+    }
+    const int32_t* len_d = full_len;
+    if (mem_kind(full_len) != 2) {
+        if ((rc = h->len.reserve((size_t)n * 4))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->len.p, full_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        len_d = (const int32_t*)h->len.p;
+    }
+    const int64_t* preds_d = preds;
+    if (mem_kind(preds) != 2) {
+        if ((rc = h->preds.reserve((size_t)n * ld * 8))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->preds.p, preds, (size_t)n * ld * 8, cudaMemcpyHostToDevice, st));
+        preds_d = (const int64_t*)h->preds.p;
+    }
+    const bool suc_dev = mem_kind(success) == 2, info_dev = mem_kind(info) == 2, bnd_dev = mem_kind(bounds) == 2,
+               val_dev = vals && mem_kind(vals) == 2;
+    if (!suc_dev && (rc = h->success.reserve((size_t)n))) return rc;
+    if (!info_dev && (rc = h->info.reserve((size_t)n * 16))) return rc;
+    if (!bnd_dev && (rc = h->bounds.reserve((size_t)n * 24))) return rc;
+    if (vals && !val_dev && (rc = h->vals.reserve((size_t)n * VAL_NVALS * 8))) return rc;
+
+    // persistent grid: as many CTAs as fit (shared memory bound), each owning one scratch row
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, validate_kernel, FP_THREADS, smem));
+    per_sm = std::max(1, per_sm);
+    const int grid = (int)std::min<int64_t>(n, (int64_t)per_sm * h->sm_count);
+    if ((rc = h->scratch.reserve((size_t)grid * stride * 4))) return rc;
+
+    ValArgs a{};
+    a.signals = sig_d;
+    a.stride = stride;
+    a.full_len = len_d;
+    a.preds = preds_d;
+    a.ld = ld;
+    a.n = n;
+    a.success = suc_dev ? success : (uint8_t*)h->success.p;
+    a.info = info_dev ? info : (int32_t*)h->info.p;
+    a.bounds = bnd_dev ? bounds : (int64_t*)h->bounds.p;
+    a.vals = vals ? (val_dev ? vals : (double*)h->vals.p) : nullptr;
+    a.scratch = (float*)h->scratch.p;
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    validate_kernel<<<grid, FP_THREADS, smem, st>>>(a, h->cfg);
+    CUDA_TRY(cudaGetLastError());
+    if (h->timing) {
+        CUDA_TRY(cudaEventRecord(h->ev1, st));
+        h->timed = true;
+    }
+    g_launches++;
+    bool any_host = false;
+    if (!suc_dev) { CUDA_TRY(cudaMemcpyAsync(success, a.success, (size_t)n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+    if (!info_dev) { CUDA_TRY(cudaMemcpyAsync(info, a.info, (size_t)n * 16, cudaMemcpyDeviceToHost, st)); any_host = true; }
+    if (!bnd_dev) { CUDA_TRY(cudaMemcpyAsync(bounds, a.bounds, (size_t)n * 24, cudaMemcpyDeviceToHost, st)); any_host = true; }
+    if (vals && !val_dev) { CUDA_TRY(cudaMemcpyAsync(vals, a.vals, (size_t)n * VAL_NVALS * 8, cudaMemcpyDeviceToHost, st)); any_host = true; }
+    // host buffers (inputs staged from pageable memory, results) are only safe to touch after the stream drained
+    if (any_host || sig_kind != 2 || len_d != full_len || preds_d != preds) CUDA_TRY(cudaStreamSynchronize(st));
+    return WDX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+"""Boundary validation and the CNN detection workflow — host-side mirror of the reference's
+`adapted.detect.combined` (warpdemux/adapted/adapted/detect/combined.py) on top of the CUDA library
+(include/wdx_b200.h: wdx_validate_*, wdx_cnn_*).
+
+    validate_boundaries_batch(signals, full_signal_lens, preds, spc)   combined.py:409-683, whole minibatch
+    combined_detect_cnn(batch_of_signals, full_signal_lens, model, spc) combined.py:198-296 without the LLR
+                                                                        fallback -> List[DetectResults]
+
+`spc` is the reference's `SigProcConfig` or anything with the same attributes (`ValidateConfig.from_spc`).
+Reads whose validation fails carry `needs_llr_fallback = True`: the reference re-detects those with its
+LLR detector on the CPU (combined.py:222-290); that stays with the caller.  All arithmetic is in
+warpdemux_b200/csrc/validate_kernel.cuh; there is no CPU implementation in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from .. import _lib
+from ..sharding import default_device
+from . import cnn as _cnn
+
+INF = float("inf")
+N_VALS = 12
+FAIL_REASONS = {
+    0: None,
+    1: "No adapter detected (primary)",
+    2: "adapter MAD check failed",
+    3: "Open pore too close to boundary",
+    4: "Real signal check failed",
+    5: "No polya detected (primary)",
+    6: "MVS polya check failed: not enough signal",
+    7: "MVS polya check failed: ",
+    8: "Median shift check failed",
+    9: "Validate boundaries failed: Signal contains nan values",
+}
+_CHECK_NAMES = ("mean", "var", "med", "range", "shift")
+HAS_NAN = 9
+
+
+def _rng(t):
+    lo, hi = t
+    return (-INF if lo is None else float(lo), INF if hi is None else float(hi))
+
+
+@dataclass
+class ValidateConfig:
+    """The SigProcConfig fields validate_boundaries reads (defaults: adapted rna004_130bps@v0.2.4.toml)."""
+    min_obs_adapter: int = 1000
+    detect_open_pores: bool = True
+    real_signal_check: bool = True
+    mean_window: int = 300
+    mean_start_range: tuple = (-INF, INF)
+    mean_end_range: tuple = (-INF, INF)
+    max_obs_local_range: int = 5000
+    local_range: tuple = (7.0, 35.0)
+    adapter_mad_range: tuple = (3.0, 12.0)
+    open_pore_min: float = 200.0
+    open_pore_min_obs_diff: int = 10
+    mvs_detect_check: bool = True
+    mvs_detect_overwrite: bool = False
+    pA_mean_window: int = 20
+    pA_var_window: int = 100
+    pA_var_range: tuple = (-INF, 30.0)
+    median_shift_range: tuple = (5.0, INF)
+    median_shift_window: int = 1000
+    polyA_med_range: tuple = (-INF, INF)
+    polyA_local_range: tuple = (-INF, INF)
+    pA_mean_range: tuple = (-INF, INF)
+    pA_mean_adapter_med_scale_range: tuple = (1.3, INF)
+    detect_med_shift: bool = False
+    med_shift_window: int = 2000
+    med_shift_range: tuple = (5.0, INF)
+    primary_method: str = "cnn"
+
+    @classmethod
+    def from_spc(cls, spc) -> "ValidateConfig":
+        if isinstance(spc, cls):
+            return spc
+        rr, mv, ms = spc.real_range, spc.mvs_polya, spc.med_shift
+        return cls(
+            min_obs_adapter=int(spc.core.min_obs_adapter),
+            detect_open_pores=bool(rr.detect_open_pores), real_signal_check=bool(rr.real_signal_check),
+            mean_window=int(rr.mean_window), mean_start_range=_rng(rr.mean_start_range), mean_end_range=_rng(rr.mean_end_range),
+            max_obs_local_range=int(rr.max_obs_local_range), local_range=_rng(rr.local_range),
+            adapter_mad_range=_rng(rr.adapter_mad_range),
+            mvs_detect_check=bool(mv.mvs_detect_check), mvs_detect_overwrite=bool(mv.mvs_detect_overwrite),
+            pA_mean_window=int(mv.pA_mean_window), pA_var_window=int(mv.pA_var_window), pA_var_range=_rng(mv.pA_var_range),
+            median_shift_range=_rng(mv.median_shift_range), median_shift_window=int(mv.median_shift_window),
+            polyA_med_range=_rng(mv.polyA_med_range), polyA_local_range=_rng(mv.polyA_local_range),
+            pA_mean_range=_rng(mv.pA_mean_range), pA_mean_adapter_med_scale_range=_rng(mv.pA_mean_adapter_med_scale_range),
+            detect_med_shift=bool(ms.detect_med_shift), med_shift_window=int(ms.med_shift_window),
+            med_shift_range=_rng(ms.med_shift_range), primary_method=str(getattr(spc, "primary_method", "cnn")),
+        )
+
+
+class _CValidateConfig(C.Structure):
+    _fields_ = [
+        ("min_obs_adapter", C.c_int32), ("detect_open_pores", C.c_int32), ("real_signal_check", C.c_int32),
+        ("mean_window", C.c_int32), ("max_obs_local_range", C.c_int32), ("open_pore_min_obs_diff", C.c_int32),
+        ("open_pore_min", C.c_double),
+        ("mean_start_range", C.c_double * 2), ("mean_end_range", C.c_double * 2), ("local_range", C.c_double * 2),
+        ("adapter_mad_range", C.c_double * 2),
+        ("mvs_detect_check", C.c_int32), ("mvs_detect_overwrite", C.c_int32), ("pA_mean_window", C.c_int32),
+        ("pA_var_window", C.c_int32), ("median_shift_window", C.c_int32), ("detect_med_shift", C.c_int32),
+        ("med_shift_window", C.c_int32), ("reserved", C.c_int32),
+        ("pA_var_range", C.c_double * 2), ("median_shift_range", C.c_double * 2), ("polyA_med_range", C.c_double * 2),
+        ("polyA_local_range", C.c_double * 2), ("pA_mean_range", C.c_double * 2),
+        ("pA_mean_adapter_med_scale_range", C.c_double * 2), ("med_shift_range", C.c_double * 2),
+    ]
+
+
+def _c_config(cfg: ValidateConfig) -> _CValidateConfig:
+    c = _CValidateConfig()
+    for name, _typ in _CValidateConfig._fields_:
+        if name == "reserved":
+            continue
+        v = getattr(cfg, name)
+        if isinstance(v, (tuple, list)):
+            setattr(c, name, (C.c_double * 2)(float(v[0]), float(v[1])))
+        elif isinstance(v, float):
+            setattr(c, name, v)
+        else:
+            setattr(c, name, int(v))
+    return c
+
+
+@dataclass
+class DetectResults:
+    """The fields of adapted/container_types.py:17-89 that validate_boundaries fills (partition statistics excepted)."""
+    success: bool
+    signal_len: Optional[int] = None
+    preloaded: Optional[int] = None
+    adapter_start: Optional[int] = None
+    adapter_end: Optional[int] = None
+    polya_end: Optional[int] = None
+    polya_candidates: Optional[np.ndarray] = None
+    cnn_adapter_end: Optional[int] = None
+    cnn_polya_end: Optional[int] = None
+    mvs_detect_mean_at_loc: Optional[float] = None
+    mvs_detect_var_at_loc: Optional[float] = None
+    mvs_detect_polya_med: Optional[float] = None
+    mvs_detect_polya_local_range: Optional[float] = None
+    mvs_detect_med_shift: Optional[float] = None
+    adapter_rna_median_shift: Optional[float] = None
+    real_adapter_mean_start: Optional[float] = None
+    real_adapter_mean_end: Optional[float] = None
+    real_adapter_local_range: Optional[float] = None
+    n_open_pores: int = 0
+    fail_reason: Optional[str] = None
+    needs_llr_fallback: bool = False
+
+
+@dataclass
+class ValidationBatch:
+    success: np.ndarray        # uint8 [n]
+    code: np.ndarray           # int32 [n] WDX_VAL_*
+    checks: np.ndarray         # int32 [n] bit i set = MVS check i passed
+    n_open_pores: np.ndarray   # int32 [n]
+    bounds: np.ndarray         # int64 [n, 3] adapter_start, adapter_end, polya_end
+    vals: np.ndarray           # float64 [n, N_VALS]
+    kernel_ms: Optional[float] = field(default=None)
+
+    def fail_reason(self, i: int) -> Optional[str]:
+        return fail_reason(int(self.code[i]), int(self.checks[i]))
+
+
+def fail_reason(code: int, checks: int = 0) -> Optional[str]:
+    if code == 7:
+        return FAIL_REASONS[7] + " ".join(n for i, n in enumerate(_CHECK_NAMES) if not (checks >> i) & 1)
+    return FAIL_REASONS[code]
+
+
+class Validator:
+    """Device handle of the validation step (`wdx_validate*`), created lazily in the process that uses it."""
+
+    def __init__(self, spc=None, device: Optional[int] = None):
+        self.cfg = ValidateConfig.from_spc(spc) if spc is not None else ValidateConfig()
+        self.device = device
+        self._h = None
+
+    def _handle(self):
+        if self._h is None:
+            h = C.c_void_p()
+            c = _c_config(self.cfg)
+            dev = default_device() if self.device is None else int(self.device)
+            _lib.check(_lib.load().wdx_validate_create(C.byref(c), dev, C.byref(h)), "wdx_validate_create")
+            self._h = h
+        return self._h
+
+    def run_raw(self, signals, n: int, stride: int, full_lens, preds, ld: int, success, info, bounds, vals=None, stream: int = 0):
+        """Pointer-level call (numpy arrays, torch tensors or addresses; host or device memory)."""
+        p = _cnn._ptr
+        rc = _lib.load().wdx_validate_run(self._handle(), p(signals), int(n), int(stride), p(full_lens), p(preds), int(ld),
+                                          p(success), p(info), p(bounds), p(vals), stream or None)
+        _lib.check(rc, "wdx_validate_run")
+
+    def enable_timing(self, on: bool = True):
+        _lib.check(_lib.load().wdx_validate_enable_timing(self._handle(), int(on)), "wdx_validate_enable_timing")
+
+    def last_kernel_ms(self) -> float:
+        ms, k = C.c_double(), C.c_int()
+        _lib.check(_lib.load().wdx_validate_last_kernel_ms(self._handle(), C.byref(ms), C.byref(k)), "wdx_validate_last_kernel_ms")
+        return ms.value
+
+    def validate(self, batch_of_signals, full_signal_lens, preds) -> ValidationBatch:
+        sig = _cnn._as_batch(batch_of_signals)
+        n, stride = sig.shape
+        lens = np.ascontiguousarray(np.minimum(np.asarray(full_signal_lens, dtype=np.int64), np.iinfo(np.int32).max), dtype=np.int32)
+        pr = np.ascontiguousarray(preds, dtype=np.int64)
+        if pr.ndim != 2 or pr.shape[0] != n or lens.shape != (n,):
+            raise ValueError("preds must be [n, 1 + k] and full_signal_lens [n]")
+        success = np.zeros(n, np.uint8)
+        info = np.zeros((n, 4), np.int32)
+        bounds = np.zeros((n, 3), np.int64)
+        vals = np.full((n, N_VALS), np.nan)
+        if n:
+            self.run_raw(sig, n, stride, lens, pr, pr.shape[1], success, info, bounds, vals)
+        return ValidationBatch(success, info[:, 0].copy(), info[:, 1].copy(), info[:, 2].copy(), bounds, vals)
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().wdx_validate_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __getstate__(self):
+        return {"cfg": self.cfg, "device": self.device}
+
+    def __setstate__(self, st):
+        self.cfg, self.device, self._h = st["cfg"], st["device"], None
+
+
+def validate_boundaries_batch(batch_of_signals, full_signal_lens, preds, spc, validator: Optional[Validator] = None) -> ValidationBatch:
+    v = validator or Validator(spc)
+    try:
+        return v.validate(batch_of_signals, full_signal_lens, preds)
+    finally:
+        if validator is None:
+            v.close()
+
+
+def _opt(x: float) -> Optional[float]:
+    return None if x != x else float(x)
+
+
+def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, stride: int, primary_method: str = "cnn") -> List[DetectResults]:
+    out = []
+    for i in range(len(vb.success)):
+        code = int(vb.code[i])
+        if code == HAS_NAN:     # the reference's validate_boundaries raises; combined_detect_cnn records str(e) (combined.py:293-294)
+            out.append(DetectResults(success=False, fail_reason=FAIL_REASONS[HAS_NAN]))
+            continue
+        fl = int(full_signal_lens[i])
+        v = vb.vals[i]
+        d = DetectResults(
+            success=bool(vb.success[i]), signal_len=fl, preloaded=min(fl, int(stride)),
+            adapter_start=int(vb.bounds[i, 0]), adapter_end=int(vb.bounds[i, 1]), polya_end=int(vb.bounds[i, 2]),
+            polya_candidates=np.asarray(preds[i, 1:]).copy(),
+            mvs_detect_mean_at_loc=_opt(v[5]), mvs_detect_var_at_loc=_opt(v[6]), mvs_detect_polya_med=_opt(v[7]),
+            mvs_detect_polya_local_range=_opt(v[8]), mvs_detect_med_shift=_opt(v[9]), adapter_rna_median_shift=_opt(v[10]),
+            real_adapter_mean_start=_opt(v[2]), real_adapter_mean_end=_opt(v[3]), real_adapter_local_range=_opt(v[4]),
+            n_open_pores=int(vb.n_open_pores[i]), fail_reason=vb.fail_reason(i), needs_llr_fallback=not bool(vb.success[i]),
+        )
+        setattr(d, f"{primary_method}_adapter_end", int(preds[i, 0]))
+        setattr(d, f"{primary_method}_polya_end", int(preds[i, 1]) if preds.shape[1] > 1 else 0)
+        out.append(d)
+    return out
+
+
+def combined_detect_cnn(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, model: "_cnn.BoundariesCNN", spc,
+                        validator: Optional[Validator] = None, mode: Optional[str] = None) -> List[DetectResults]:
+    """CNN boundaries + validation for a minibatch, both on the GPU (combined.py:198-221).  Reads with
+    `needs_llr_fallback` are the ones the reference retries with its CPU LLR detector (combined.py:222-290)."""
+    sig = _cnn._as_batch(batch_of_signals)
+    preds = _cnn.cnn_detect(sig, model, spc.cnn_boundaries, spc.core, mode=mode)
+    vb = validate_boundaries_batch(sig, full_signal_lens, preds, spc, validator=validator)
+    return to_detect_results(vb, preds, full_signal_lens, sig.shape[1], str(getattr(spc, "primary_method", "cnn")))

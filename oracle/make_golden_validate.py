@@ -90,7 +90,7 @@ def main():
         preds.append(g["preds"][i])
     k = g["preds"].shape[1] - 1
     for s in range(N_SYN):
-        row, fl, pr = ov.synthetic_case(s, k=k)
+        row, fl, pr = ov.synthetic_case(s, stride=m, k=k)
         rows.append(row)
         lens.append(int(fl))
         preds.append(pr)

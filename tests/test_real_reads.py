@@ -115,3 +115,55 @@ def test_pod5_reader_on_reference_file_if_present(golden_real):
         stored = g["adc"][off[i]:off[i + 1]]
         assert np.array_equal(s[a:a + stored.size], stored)
         assert r.signal_pa.dtype == np.float32
+
+
+@pytest.mark.gpu
+def test_gpu_chain_raw_signal_to_barcode_calls(golden_real, models):
+    """BASELINE.json configs[0] end to end on the device: calibrated pA rows of the first reads of
+    4000_rna004.pod5 -> boundary CNN -> boundary validation -> fingerprint -> DTW+SVC, against what the
+    reference's own chain (combined_detect_cnn -> detect_results_to_fpt -> DTW_SVM.predict) produced for the
+    same reads.  Reads whose validation fails are the reference's LLR-fallback reads (stay with the caller)."""
+    from types import SimpleNamespace
+
+    from conftest import GOLD
+    from warpdemux_b200.detect import cnn, combined
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import Fingerprinter, FingerprintConfig
+    from wdx_testutil import cnn_golden_signals
+
+    g = golden_real
+    with np.load(os.path.join(GOLD, "cnn_detect_rna004.npz")) as z:
+        gc = {k: z[k] for k in z.files}
+    with np.load(os.path.join(GOLD, "validate_rna004.npz")) as z:
+        full_lens = z["full_lens"][: int(z["n_real"])]
+    m = int(g["preload_size"])            # production preload (parser.py:515 update_sig_preload_size): 11 500 samples
+    sig = np.ascontiguousarray(cnn_golden_signals(gc)[:, :m])
+    n = sig.shape[0]
+    ccfg = json.loads(str(gc["cfg"]))
+    spc = SimpleNamespace(core=cnn.CoreConfig(min_obs_adapter=ccfg["min_obs_adapter"], max_obs_adapter=ccfg["max_obs_adapter"],
+                                              downscale_factor=ccfg["downscale_factor"]),
+                          cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=ccfg["polya_cand_k"]), primary_method="cnn")
+    model = cnn.load_cnn_model(os.path.join(GOLD, "models", "cnn_rna004_130bps_v0.2.4.npz"), device=0)
+    val = combined.Validator(device=0)
+    dets = combined.combined_detect_cnn(sig, full_lens, model, spc, validator=val)
+    ok = np.array([d.success for d in dets])
+    assert ok.sum() >= n - 3
+    a0 = np.array([d.adapter_start if d.success else 0 for d in dets], dtype=np.int64)
+    a1 = np.array([d.adapter_end if d.success else 0 for d in dets], dtype=np.int64)
+    ref_ok = g["detect_ok"][:n].astype(bool)
+    assert not (ok & ~ref_ok).any()                       # a read the CNN path validates is validated by the reference too
+    assert np.array_equal(a0[ok], g["adapter_start"][:n][ok]) and np.array_equal(a1[ok], g["adapter_end"][:n][ok])
+    assert dets[0].cnn_adapter_end == int(gc["preds"][0, 0])
+
+    fp = Fingerprinter(FingerprintConfig(**_cfg(g)), device=0)
+    mdl = DTW_SVM(models["WDX4_rna004_v1_0"], device=0, mode="guarded")
+    labels, prob, conf, status = fp.extract_and_predict(mdl, sig, a0, a1, detect_ok=ok.astype(np.uint8))
+    assert np.array_equal(status[ok], g["status"][:n][ok])
+    good_all = g["status"] == 0
+    pos = np.cumsum(good_all) - 1                         # row of y_pred for each read with a fingerprint
+    chk = ok & good_all[:n]
+    assert chk.sum() >= n - 5
+    assert np.array_equal(labels[chk], g["y_pred"][pos[:n][chk]])
+    fp.close()
+    val.close()
+    model.close()

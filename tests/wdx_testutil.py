@@ -179,7 +179,7 @@ def validate_golden_inputs(gold_val, gold_cnn):
     rows = [real[i] for i in range(n_real)]
     preds = [gold_cnn["preds"][i] for i in range(n_real)]
     for s in range(n_syn):
-        row, _fl, pr = ov.synthetic_case(s, k=k)
+        row, _fl, pr = ov.synthetic_case(s, stride=real.shape[1], k=k)
         rows.append(row)
         preds.append(pr)
     return rows, gold_val["full_lens"].astype(np.int64), np.array(preds, dtype=np.int64)

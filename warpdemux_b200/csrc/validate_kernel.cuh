@@ -14,7 +14,7 @@
 // statistics go back.  HBM-bound by construction: algorithmic bytes per read = 4 * min(len, stride).
 //
 // Exactness (this TU is compiled with -fmad=false): medians and percentiles are exact order statistics
-// found by radix selection on order-preserving keys; float32 / float64 sums follow numpy's pairwise
+// found by histogram / radix selection on order-preserving keys; float32 / float64 sums follow numpy's pairwise
 // summation order; np.percentile's linear interpolation is evaluated in float64 as numpy does.  The
 // sequential open-pore scan is replaced by its closed form: position i is kept iff an earlier open-pore
 // sample exists and none lies within min_obs_diff - 1 samples before i.
@@ -90,63 +90,187 @@ __device__ T np_pairwise(int lo, int n, F at) {
     return a + b;
 }
 
-// k-th and (k+1)-th smallest (0-based) of n float32 values given through VAL.  All threads get both.
+// ---- order statistics ---------------------------------------------------------------------------------
+// Several exact order statistics of the same n float32 values in three light passes (instead of five
+// radix passes per statistic): (1) min / max, (2) a 2048-bin histogram over [min, max] — a monotone map,
+// so every element of a lower bin is <= every element of a higher bin, (3) the few members of the bins
+// that hold the wanted ranks are gathered and ranked exactly on their order keys.  A crowded bin
+// (degenerate data) falls back to radix selection for that rank.
+constexpr int VAL_BINS = 2048;
+constexpr int VAL_MAXQ = 6;      // ranks per call
+constexpr int VAL_CAND = 320;    // members kept per selected bin
+
+struct ValSel {
+    uint32_t hist[VAL_BINS];
+    uint32_t cand[VAL_MAXQ][VAL_CAND];
+    uint32_t slot_n[VAL_MAXQ];
+    int q_bin[VAL_MAXQ];
+    uint32_t q_r[VAL_MAXQ], q_cnt[VAL_MAXQ], q_key[VAL_MAXQ];
+    uint32_t mnk, mxk;
+};
+
+// out[q] = the ranks[q]-th smallest (0-based) value, q < nq <= VAL_MAXQ; ranks < n, n >= 1.  All threads get all results.
 template <typename VAL>
-__device__ void block_order2(int n, uint32_t k, VAL val, FpScratch& s, float* v_k, float* v_k1) {
-    auto key = [&](int i) { return f32_key(val(i)); };
-    const uint32_t key_lo = block_select_u32(n, k, key, s);
-    *v_k = f32_unkey(key_lo);
+__device__ void block_ranks(int n, VAL val, int nq, const uint32_t* ranks, float* out, ValSel& vs, FpScratch& s) {
+    const int tid = threadIdx.x;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        s.hist[0] = 0;            // count(key <= key_lo)
-        s.hist[1] = 0xffffffffu;  // min key > key_lo
+    if (tid == 0) {
+        vs.mnk = 0xffffffffu;
+        vs.mxk = 0u;
     }
+    if (tid < VAL_MAXQ) vs.slot_n[tid] = 0;
+    for (int b = tid; b < VAL_BINS; b += FP_THREADS) vs.hist[b] = 0;
     __syncthreads();
-    uint32_t cnt = 0, mn = 0xffffffffu;
-    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
-        const uint32_t kv = key(i);
-        if (kv <= key_lo) cnt++;
-        else mn = min(mn, kv);
-    }
+    {
+        uint32_t mn = 0xffffffffu, mx = 0u;
+        for (int i = tid; i < n; i += FP_THREADS) {
+            const uint32_t kv = f32_key(val(i));
+            mn = min(mn, kv);
+            mx = max(mx, kv);
+        }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s.hist[0], cnt);
-        atomicMin(&s.hist[1], mn);
+        for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&vs.mnk, mn);
+            atomicMax(&vs.mxk, mx);
+        }
     }
     __syncthreads();
-    const uint32_t c = s.hist[0], m = s.hist[1];
-    *v_k1 = (c >= k + 2 || m == 0xffffffffu) ? *v_k : f32_unkey(m);
+    const float vmin = f32_unkey(vs.mnk), vmax = f32_unkey(vs.mxk);
+    if (!(vmax > vmin)) {   // all values equal
+        for (int q = 0; q < nq; q++) out[q] = vmin;
+        return;
+    }
+    const float scale = __fdiv_rn((float)VAL_BINS, __fsub_rn(vmax, vmin));
+    auto key_of = [&](int i) { return f32_key(val(i)); };
+    if (!(scale < 1e30f)) {
+        for (int q = 0; q < nq; q++) out[q] = f32_unkey(block_select_u32(n, ranks[q], key_of, s));
+        return;
+    }
+    auto bin_of = [&](float x) { return min(VAL_BINS - 1, (int)__fmul_rn(__fsub_rn(x, vmin), scale)); };
+    for (int i = tid; i < n; i += FP_THREADS) atomicAdd(&vs.hist[bin_of(val(i))], 1u);
     __syncthreads();
+    {   // thread t owns bins [t*B, (t+1)*B)
+        constexpr int B = VAL_BINS / FP_THREADS;
+        uint32_t c[B], sum = 0;
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            c[j] = vs.hist[tid * B + j];
+            sum += c[j];
+        }
+        uint32_t total;
+        const uint32_t run0 = block_exscan(sum, s, &total);
+        for (int q = 0; q < nq; q++) {
+            const uint32_t k = ranks[q];
+            if (k >= run0 && k < run0 + sum) {  // exactly one thread per rank
+                uint32_t run = run0;
+#pragma unroll
+                for (int j = 0; j < B; j++) {
+                    if (k >= run && k < run + c[j]) {
+                        vs.q_bin[q] = tid * B + j;
+                        vs.q_r[q] = k - run;
+                        vs.q_cnt[q] = c[j];
+                    }
+                    run += c[j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // distinct selected bins -> slots (every thread derives the same mapping)
+    int slot_of[VAL_MAXQ], slot_bin[VAL_MAXQ], n_slots = 0;
+    bool crowded = false;
+    for (int q = 0; q < nq; q++) {
+        const int b = vs.q_bin[q];
+        int sl = -1;
+        for (int j = 0; j < n_slots; j++)
+            if (slot_bin[j] == b) sl = j;
+        if (vs.q_cnt[q] > (uint32_t)VAL_CAND) {
+            crowded = true;
+            slot_of[q] = -1;
+            continue;
+        }
+        if (sl < 0) {
+            sl = n_slots++;
+            slot_bin[sl] = b;
+        }
+        slot_of[q] = sl;
+    }
+    for (int i = tid; i < n; i += FP_THREADS) {
+        const float x = val(i);
+        const int b = bin_of(x);
+        for (int j = 0; j < n_slots; j++)
+            if (b == slot_bin[j]) vs.cand[j][atomicAdd(&vs.slot_n[j], 1u)] = f32_key(x);
+    }
+    __syncthreads();
+    for (int q = 0; q < nq; q++) {
+        const int sl = slot_of[q];
+        if (sl < 0) continue;
+        const uint32_t m = vs.q_cnt[q], r = vs.q_r[q];
+        for (uint32_t t = tid; t < m; t += FP_THREADS) {
+            const uint32_t x = vs.cand[sl][t];
+            uint32_t rank = 0;
+            for (uint32_t u = 0; u < m; u++) {
+                const uint32_t y = vs.cand[sl][u];
+                rank += (y < x) || (y == x && u < t);
+            }
+            if (rank == r) vs.q_key[q] = x;
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < nq; q++)
+        if (slot_of[q] >= 0) out[q] = f32_unkey(vs.q_key[q]);
+    if (crowded) {   // uniform decision
+        for (int q = 0; q < nq; q++)
+            if (slot_of[q] < 0) out[q] = f32_unkey(block_select_u32(n, ranks[q], key_of, s));
+    }
 }
 
-// np.median / np.nanmedian of n NaN-free float32 values (NaN for n == 0, as numpy returns for an empty slice).
-template <typename VAL>
-__device__ float val_median(int n, VAL val, FpScratch& s) {
-    if (n <= 0) return __int_as_float(0x7fc00000);
-    float a, b;
-    block_order2(n, (uint32_t)((n - 1) / 2), val, s, &a, &b);
-    if (n & 1) return a;
-    return __fdiv_rn(__fadd_rn(a, b), 2.0f);
-}
+// np.median / np.nanmedian of NaN-free float32 values from their two middle order statistics.
+__device__ __forceinline__ float median_of(int n, float lo, float hi) { return (n & 1) ? lo : __fdiv_rn(__fadd_rn(lo, hi), 2.0f); }
 
-// np.percentile(x, q) of n >= 1 float32 values, method "linear": float64 result.
-template <typename VAL>
-__device__ double val_percentile(int n, double q, VAL val, FpScratch& s) {
+// np.percentile(x, q), method "linear": the two ranks it interpolates between, and the float64 result.
+__device__ __forceinline__ void pct_ranks(int n, double q, uint32_t* r0, uint32_t* r1, double* g) {
     const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(q, 100.0));
     int prev = (int)floor(vi);
     prev = max(0, min(prev, n - 1));
-    const double g = __dsub_rn(vi, (double)prev);
-    float a, b;
-    block_order2(n, (uint32_t)prev, val, s, &a, &b);
-    if (prev + 1 > n - 1) b = a;
+    *g = __dsub_rn(vi, (double)prev);
+    *r0 = (uint32_t)prev;
+    *r1 = (uint32_t)min(prev + 1, n - 1);
+}
+__device__ __forceinline__ double pct_lerp(float a, float b, double g) {
     const double d = (double)__fsub_rn(b, a);   // subtract(b, a) on float32
     double r = (g >= 0.5) ? __dsub_rn((double)b, __dmul_rn(d, __dsub_rn(1.0, g))) : __dadd_rn((double)a, __dmul_rn(d, g));
     if (b == a) r = (double)a;                  // _lerp: where(b == a, a, lerp)
     return r;
+}
+
+// np.median of n NaN-free float32 values (NaN for n == 0, as numpy returns for an empty slice).
+template <typename VAL>
+__device__ float val_median(int n, VAL val, ValSel& vs, FpScratch& s) {
+    if (n <= 0) return __int_as_float(0x7fc00000);
+    const uint32_t rk[2] = {(uint32_t)((n - 1) / 2), (uint32_t)(n / 2)};
+    float o[2];
+    block_ranks(n, val, 2, rk, o, vs, s);
+    return median_of(n, o[0], o[1]);
+}
+
+// p85 - p15 of n >= 1 values (np.subtract(*np.percentile(x, (85, 15)))), optionally with the median.
+template <typename VAL>
+__device__ double val_local_range(int n, VAL val, ValSel& vs, FpScratch& s, float* median) {
+    uint32_t rk[6];
+    double g85, g15;
+    pct_ranks(n, 85.0, &rk[0], &rk[1], &g85);
+    pct_ranks(n, 15.0, &rk[2], &rk[3], &g15);
+    rk[4] = (uint32_t)((n - 1) / 2);
+    rk[5] = (uint32_t)(n / 2);
+    float o[6];
+    block_ranks(n, val, median ? 6 : 4, rk, o, vs, s);
+    if (median) *median = median_of(n, o[4], o[5]);
+    return __dsub_rn(pct_lerp(o[0], o[1], g85), pct_lerp(o[2], o[3], g15));
 }
 
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
@@ -154,6 +278,7 @@ __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { r
 __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, const ValCfg c) {
     extern __shared__ float vsig[];
     __shared__ FpScratch s;
+    __shared__ ValSel vs;
     __shared__ int sh_i[6];
     __shared__ double sh_d[4];
     const int tid = threadIdx.x;
@@ -188,8 +313,8 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
         if (code == VAL_OK) {
             if (a1 == 0) code = VAL_NO_ADAPTER;
             else {
-                med = val_median(hi, [&](int i) { return vsig[i]; }, s);
-                mad = val_median(hi, [&](int i) { return fabsf(__fsub_rn(vsig[i], med)); }, s);
+                med = val_median(hi, [&](int i) { return vsig[i]; }, vs, s);
+                mad = val_median(hi, [&](int i) { return fabsf(__fsub_rn(vsig[i], med)); }, vs, s);
                 v[0] = (double)med;
                 v[1] = (double)mad;
             }
@@ -256,9 +381,7 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
                 if (val_in_range(v[2], c.mean_start_lo, c.mean_start_hi) && val_in_range(v[3], c.mean_end_lo, c.mean_end_hi)) {
                     const int nn = min(c.max_obs_local_range, nseg);
                     const int base = hi - nn;
-                    const double p85 = val_percentile(nn, 85.0, [&](int i) { return vsig[base + i]; }, s);
-                    const double p15 = val_percentile(nn, 15.0, [&](int i) { return vsig[base + i]; }, s);
-                    v[4] = __dsub_rn(p85, p15);
+                    v[4] = val_local_range(nn, [&](int i) { return vsig[base + i]; }, vs, s, nullptr);
                     ok = val_in_range(v[4], c.local_range_lo, c.local_range_hi);
                 }
             }
@@ -274,6 +397,8 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
                     mhi = __dmul_rn(c.scale_hi, (double)med);
                 }
                 const int e = (int)a1;   // a1 <= L here or the size test below fails first
+                bool have_shift = false;
+                double shift_cached = 0.0;
                 for (int j = 1; j < a.ld; j++) {
                     const int64_t pe = pr[j];
                     if (pe == 0) break;
@@ -310,7 +435,7 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
                                 scratch[p] = (float)__ddiv_rn(ss, (double)w);
                             }
                             __syncthreads();
-                            r_var = (double)val_median(cnt, [&](int i) { return scratch[i]; }, s);
+                            r_var = (double)val_median(cnt, [&](int i) { return scratch[i]; }, vs, s);
                         }
                         // mean
                         if (nominal <= c.pa_mean_window + 2) {
@@ -325,16 +450,19 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
                             for (int p = tid; p < cnt; p += FP_THREADS)
                                 scratch[p] = (float)__ddiv_rn(np_pairwise<double>(e + p, w, [&](int i) { return (double)vsig[i]; }), (double)w);
                             __syncthreads();
-                            r_mean = (double)val_median(cnt, [&](int i) { return scratch[i]; }, s);
+                            r_mean = (double)val_median(cnt, [&](int i) { return scratch[i]; }, vs, s);
                         }
-                        r_med = (double)val_median(m, [&](int i) { return vsig[e + i]; }, s);
-                        const double p85 = val_percentile(m, 85.0, [&](int i) { return vsig[e + i]; }, s);
-                        const double p15 = val_percentile(m, 15.0, [&](int i) { return vsig[e + i]; }, s);
-                        r_lr = __dsub_rn(p85, p15);
-                        const int up = min(e + c.median_shift_window, L), dn = max(e - c.median_shift_window, 0);
-                        const float m_after = val_median(up - e, [&](int i) { return vsig[e + i]; }, s);
-                        const float m_before = val_median(e - dn, [&](int i) { return vsig[dn + i]; }, s);
-                        r_shift = (double)__fsub_rn(m_after, m_before);
+                        float pmed;
+                        r_lr = val_local_range(m, [&](int i) { return vsig[e + i]; }, vs, s, &pmed);
+                        r_med = (double)pmed;
+                        if (!have_shift) {   // depends on the adapter end only: once per read, not per candidate
+                            const int up = min(e + c.median_shift_window, L), dn = max(e - c.median_shift_window, 0);
+                            const float m_after = val_median(up - e, [&](int i) { return vsig[e + i]; }, vs, s);
+                            const float m_before = val_median(e - dn, [&](int i) { return vsig[dn + i]; }, vs, s);
+                            shift_cached = (double)__fsub_rn(m_after, m_before);
+                            have_shift = true;
+                        }
+                        r_shift = shift_cached;
                         bits = (val_in_range(r_mean, mlo, mhi) ? 1 : 0) | (val_in_range(r_var, c.var_lo, c.var_hi) ? 2 : 0) |
                                (val_in_range(r_med, c.pmed_lo, c.pmed_hi) ? 4 : 0) | (val_in_range(r_lr, c.plr_lo, c.plr_hi) ? 8 : 0) |
                                (val_in_range(r_shift, c.shift_lo, c.shift_hi) ? 16 : 0);
@@ -365,8 +493,8 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
         if (code == VAL_OK && c.detect_med_shift) {
             const int e = (int)min(a1, (int64_t)L);
             const int up = (int)min(min(a1 + c.med_shift_window, fl), (int64_t)L), dn = (int)max(a1 - c.med_shift_window, (int64_t)0);
-            const float m_after = val_median(max(0, up - e), [&](int i) { return vsig[e + i]; }, s);
-            const float m_before = val_median(max(0, e - min(dn, e)), [&](int i) { return vsig[min(dn, e) + i]; }, s);
+            const float m_after = val_median(max(0, up - e), [&](int i) { return vsig[e + i]; }, vs, s);
+            const float m_before = val_median(max(0, e - min(dn, e)), [&](int i) { return vsig[min(dn, e) + i]; }, vs, s);
             v[10] = (double)__fsub_rn(m_after, m_before);
             if (!val_in_range(v[10], c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
         }

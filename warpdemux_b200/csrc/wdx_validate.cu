@@ -92,7 +92,9 @@ int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    h->smem_max = (int)prop.sharedMemPerBlockOptin - 8192;
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, validate_kernel));
+    h->smem_max = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes - 1024;
     CUDA_TRY(cudaFuncSetAttribute(validate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_max));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&h->ev0));

@@ -167,3 +167,72 @@ def test_gpu_chain_raw_signal_to_barcode_calls(golden_real, models):
     fp.close()
     val.close()
     model.close()
+
+
+@pytest.mark.gpu
+def test_gpu_minibatch_step_matches_reference_worker(golden_real, models):
+    """warpdemux_b200.file_proc.MinibatchDemuxer = the compute core of the reference's
+    worker_detect_and_predict_on_preloaded_signals (file_proc.py:380-455) on the device; the reads the CNN path
+    rejects get their boundaries from an `llr_fallback` callback (here: the reference's own results)."""
+    from types import SimpleNamespace
+
+    import torch
+
+    from conftest import GOLD
+    from warpdemux_b200.detect import cnn, combined
+    from warpdemux_b200.file_proc import MinibatchDemuxer, detect_and_predict_on_preloaded_signals
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import FingerprintConfig
+    from wdx_testutil import cnn_golden_signals
+
+    g = golden_real
+    with np.load(os.path.join(GOLD, "cnn_detect_rna004.npz")) as z:
+        gc = {k: z[k] for k in z.files}
+    with np.load(os.path.join(GOLD, "validate_rna004.npz")) as z:
+        full_lens = z["full_lens"][: int(z["n_real"])]
+    m = int(g["preload_size"])
+    sig = np.ascontiguousarray(cnn_golden_signals(gc)[:, :m])
+    n = sig.shape[0]
+    ccfg = json.loads(str(gc["cfg"]))
+    core = cnn.CoreConfig(min_obs_adapter=ccfg["min_obs_adapter"], max_obs_adapter=ccfg["max_obs_adapter"],
+                          downscale_factor=ccfg["downscale_factor"])
+    model_detect = cnn.load_cnn_model(os.path.join(GOLD, "models", "cnn_rna004_130bps_v0.2.4.npz"), device=0)
+    model_predict = DTW_SVM(models["WDX4_rna004_v1_0"], device=0, mode="guarded")
+    read_ids = g["read_ids"][:n]
+    calls = []
+
+    def llr_fallback(row, full_len):
+        # identify the read by its samples (rows are unique)
+        i = next(j for j in range(n) if np.array_equal(sig[j], row, equal_nan=True))
+        calls.append(i)
+        if not g["detect_ok"][i]:
+            return SimpleNamespace(success=False)
+        return SimpleNamespace(success=True, adapter_start=int(g["adapter_start"][i]), adapter_end=int(g["adapter_end"][i]), polya_end=0)
+
+    dmx = MinibatchDemuxer(model_predict, model_detect, core=core, cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=ccfg["polya_cand_k"]),
+                           validate_config=combined.ValidateConfig(), fp_config=FingerprintConfig(**_cfg(g)), device=0,
+                           llr_fallback=llr_fallback)
+    res = dmx.run(sig, full_lens, read_ids, want_fpt=True)
+    assert np.array_equal(res.fp_status, g["status"][:n])
+    good_all = g["status"] == 0
+    pos = np.cumsum(good_all) - 1
+    good = good_all[:n]
+    assert np.array_equal(res.labels[good], g["y_pred"][pos[:n][good]]) and (res.labels[~good] == -1).all()
+    assert np.abs(res.prob[good] - g["y_prob"][pos[:n][good]]).max() < 1e-3
+    assert np.array_equal(res.fpt[good], g["fpt"][:n][good])           # fingerprints bit-identical through the chain
+    assert sorted(calls) == sorted(np.flatnonzero(res.detect_code != 0).tolist()) and res.llr_rescued.sum() == len(
+        [i for i in calls if g["detect_ok"][i]])
+    df = res.predictions
+    assert list(df.columns[:3]) == ["#read_id", "predicted_barcode", "confidence_score"] and df.columns[-1] == "p-1"
+    assert list(df["#read_id"]) == list(read_ids[good]) and np.array_equal(df["predicted_barcode"].to_numpy(), res.labels[good])
+    # device-resident input, no callback, reference argument order
+    dmx2 = MinibatchDemuxer(model_predict, model_detect, core=core, cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=ccfg["polya_cand_k"]),
+                            fp_config=FingerprintConfig(**_cfg(g)), device=0)
+    res2 = detect_and_predict_on_preloaded_signals((torch.from_numpy(sig).cuda(), None, full_lens, read_ids), model_predict, model_detect,
+                                                   SimpleNamespace(primary_method="cnn"), demuxer=dmx2)
+    ok2 = res2.detect_success.astype(bool)
+    assert np.array_equal(res2.labels[ok2], res.labels[ok2]) and (res2.labels[~ok2] == -1).all()
+    assert all(res2.fail_reason(i) == combined.fail_reason(int(res2.detect_code[i]), int(res2.detect_checks[i])) for i in np.flatnonzero(~ok2))
+    dmx.close()
+    dmx2.close()
+    model_detect.close()

@@ -1,0 +1,211 @@
+"""The production minibatch step on the GPU — compute core of the reference's
+`worker_detect_and_predict_on_preloaded_signals` (warpdemux/file_proc.py:380-455):
+
+    combined_detect_cnn          boundary CNN + validation            wdx_cnn_detect, wdx_validate_run
+    barcode_fpt_wrapper (x n)    fingerprint per read                 } wdx_fp_predict (fingerprints stay
+    model_predict.predict        DTW distances + SVC + thresholds     }  on the device)
+    add_read_id_col_to_predictions                                    host (pandas)
+
+One upload of the NaN-padded float32 minibatch (none when a CUDA tensor is given; asynchronous from a pinned
+torch tensor), three kernel stages chained on ONE stream through device-resident buffers (boundaries, verdicts, fingerprints never visit the host), one download of the per-read results.
+The queues / counters of the reference worker are orchestration and stay with the caller.
+
+Reads whose CNN boundaries fail validation are the ones the reference retries with its CPU LLR detector
+(adapted/detect/combined.py:222-290).  `llr_fallback`, if given, is called for the minibatch rows of those
+reads between validation and fingerprinting (one host round trip of n verdict bytes); without it they are
+reported as failed with the validation's fail_reason and `needs_llr_fallback` set.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from .detect import cnn as _cnn
+from .detect import combined as _combined
+from .models.utils import predictions_to_df
+from .sharding import default_device
+from .sig_proc import Fingerprinter, FingerprintConfig
+
+FP_STATUS_REASON = {1: "segmentation failed", 2: "detection failed", 3: "segment normalization failed",
+                    4: "adapter slice too long", 5: "consensus query outlier"}
+
+
+def add_read_id_col_to_predictions(predictions: pd.DataFrame, read_ids) -> pd.DataFrame:
+    """file_proc.py:769-780."""
+    cols = predictions.columns.tolist()
+    if "#read_id" in cols:
+        raise ValueError("'#read_id' already in dataframe")
+    predictions["#read_id"] = read_ids
+    return predictions[["#read_id", *cols]]
+
+
+@dataclass
+class MinibatchResult:
+    labels: np.ndarray            # int64 [n] predicted barcode, -1 = unclassified or no fingerprint
+    conf: np.ndarray              # float64 [n] confidence margin (NaN without a fingerprint)
+    prob: np.ndarray              # float64 [n, k]
+    fp_status: np.ndarray         # int32 [n] 0 = fingerprint ok, else the fingerprint stage's status
+    detect_success: np.ndarray    # uint8 [n]
+    detect_code: np.ndarray       # int32 [n] validation fail code (detect.combined.FAIL_REASONS)
+    detect_checks: np.ndarray     # int32 [n]
+    bounds: np.ndarray            # int64 [n, 3] adapter_start, adapter_end, polya_end
+    preds: np.ndarray             # int64 [n, 1 + k] raw CNN boundaries
+    llr_rescued: np.ndarray       # bool [n] boundaries came from the llr_fallback callback
+    predictions: Optional[pd.DataFrame]   # reads with a fingerprint: '#read_id', predicted_barcode, confidence_score, pXX..
+    fpt: Optional[np.ndarray] = None      # float64 [n, L] when asked for
+
+    @property
+    def passed(self) -> np.ndarray:
+        return self.fp_status == 0
+
+    def fail_reason(self, i: int) -> Optional[str]:
+        if self.fp_status[i] == 0:
+            return None
+        if not self.detect_success[i]:
+            return _combined.fail_reason(int(self.detect_code[i]), int(self.detect_checks[i]))
+        return FP_STATUS_REASON.get(int(self.fp_status[i]), "fingerprint failed")
+
+
+class MinibatchDemuxer:
+    """`model_predict`: warpdemux_b200 DTW_SVM; `model_detect`: detect.cnn.BoundariesCNN; `spc`: the reference's
+    SigProcConfig (or the three config mirrors given explicitly)."""
+
+    def __init__(self, model_predict, model_detect: "_cnn.BoundariesCNN", spc=None, *, core=None, cnn_boundaries=None,
+                 validate_config: Optional["_combined.ValidateConfig"] = None, fp_config: Optional[FingerprintConfig] = None,
+                 device: Optional[int] = None, mode: Optional[str] = None, cnn_mode: Optional[str] = None,
+                 llr_fallback: Optional[Callable] = None, consensus_query=None):
+        import torch  # device memory and streams only
+
+        self._torch = torch
+        self.device = default_device() if device is None else int(device)
+        self.model_predict, self.model_detect = model_predict, model_detect
+        self.core = core if core is not None else (spc.core if spc is not None else _cnn.CoreConfig())
+        self.cnn_boundaries = cnn_boundaries if cnn_boundaries is not None else (
+            spc.cnn_boundaries if spc is not None else _cnn.CNNBoundariesConfig())
+        vcfg = validate_config if validate_config is not None else (
+            _combined.ValidateConfig.from_spc(spc) if spc is not None else _combined.ValidateConfig())
+        fcfg = fp_config if fp_config is not None else (
+            FingerprintConfig.from_spc(spc, consensus_query) if spc is not None else FingerprintConfig())
+        self.validator = _combined.Validator(vcfg, device=self.device)
+        self.fingerprinter = Fingerprinter(fcfg, device=self.device)
+        self.mode = mode or model_predict.mode
+        self.cnn_mode = cnn_mode or model_detect.mode
+        self.llr_fallback = llr_fallback
+        self.k_cand = int(self.cnn_boundaries.polya_cand_k)
+        self._stream = None
+        self._buf = {}
+
+    # -- device plumbing ---------------------------------------------------------
+    def _dev(self):
+        return self._torch.device("cuda", self.device)
+
+    def _get(self, name, shape, dtype):
+        t = self._buf.get(name)
+        need = int(np.prod(shape))
+        if t is None or t.numel() < need or t.dtype != dtype:
+            t = self._torch.empty(max(need, 1), dtype=dtype, device=self._dev())
+            self._buf[name] = t
+        return t[:need].view(*shape)
+
+    def run(self, signals, full_lengths, read_ids: Optional[Sequence] = None, return_df: bool = True,
+            want_fpt: bool = False) -> MinibatchResult:
+        """signals: float32 [n, stride] NaN-padded minibatch (numpy, pinned or not; or a CUDA tensor);
+        full_lengths: [n] full read lengths (file_proc.py:241-262)."""
+        torch = self._torch
+        dm = self.model_predict._device_model()
+        k, L = self.model_predict.params.k, self.model_predict.params.L
+        with torch.cuda.device(self.device):
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=self._dev())
+            st = self._stream
+            if isinstance(signals, torch.Tensor):
+                if signals.dtype != torch.float32 or signals.dim() != 2 or not signals.is_contiguous():
+                    raise ValueError("signals tensor must be contiguous float32 [n, stride]")
+                st.wait_stream(torch.cuda.current_stream())   # the caller produced the tensor on its current stream
+                d_sig = signals if signals.is_cuda else None
+                h_sig = None if signals.is_cuda else signals
+            else:
+                h_sig = torch.from_numpy(_cnn._as_batch(signals))
+                d_sig = None
+            n, stride = (d_sig if d_sig is not None else h_sig).shape
+            lens = np.ascontiguousarray(np.minimum(np.asarray(full_lengths, dtype=np.int64).reshape(-1), np.iinfo(np.int32).max), dtype=np.int32)
+            if lens.shape[0] != n:
+                raise ValueError("full_lengths must have one entry per signal row")
+            ld = 1 + self.k_cand
+            with torch.cuda.stream(st):
+                if d_sig is None:   # one upload; pinned memory makes it asynchronous
+                    d_sig = self._get("sig", (n, stride), torch.float32)
+                    d_sig.copy_(h_sig, non_blocking=True)
+                d_len = self._get("len", (n,), torch.int32)
+                d_len.copy_(torch.from_numpy(lens), non_blocking=True)
+                d_preds = self._get("preds", (n, ld), torch.int64)
+                d_suc = self._get("suc", (n,), torch.uint8)
+                d_info = self._get("info", (n, 4), torch.int32)
+                d_bounds = self._get("bounds", (n, 3), torch.int64)
+                d_a0 = self._get("a0", (n,), torch.int64)
+                d_a1 = self._get("a1", (n,), torch.int64)
+                d_lab = self._get("lab", (n,), torch.int64)
+                d_conf = self._get("conf", (n,), torch.float64)
+                d_prob = self._get("prob", (n, k), torch.float64)
+                d_status = self._get("status", (n,), torch.int32)
+                d_fpt = self._get("fpt", (n, L), torch.float64) if want_fpt else None
+                sp = st.cuda_stream
+                rescued = np.zeros(n, dtype=bool)
+                if n:
+                    _cnn.detect_raw(self.model_detect, self.core, self.k_cand, d_sig, n, stride, d_preds, mode=self.cnn_mode, stream=sp)
+                    self.validator.run_raw(d_sig, n, stride, d_len, d_preds, ld, d_suc, d_info, d_bounds, None, stream=sp)
+                    if self.llr_fallback is not None:
+                        suc_h = d_suc.cpu().numpy()            # synchronises this stream: n bytes
+                        failed = np.flatnonzero(suc_h == 0)
+                        if failed.size:
+                            rows = d_sig[torch.from_numpy(failed).to(self._dev())].cpu().numpy() if h_sig is None else h_sig.numpy()[failed]
+                            b_h = d_bounds.cpu().numpy()
+                            for j, i in enumerate(failed):
+                                res = self.llr_fallback(rows[j], int(lens[i]))
+                                if res is not None and getattr(res, "success", False):
+                                    b_h[i] = (int(res.adapter_start or 0), int(res.adapter_end), int(res.polya_end or 0))
+                                    suc_h[i] = 1
+                                    rescued[i] = True
+                            d_bounds.copy_(torch.from_numpy(b_h))
+                            d_suc.copy_(torch.from_numpy(suc_h))
+                    d_a0.copy_(d_bounds[:, 0])
+                    d_a1.copy_(d_bounds[:, 1])
+                    self.fingerprinter.predict_raw(dm, d_sig, n, stride, d_a0, d_a1, _lib.MODES[self.mode], d_lab, d_status,
+                                                   conf=d_conf, prob=d_prob, fpt=d_fpt, detect_ok=d_suc, stream=sp)
+                out = [t.cpu() for t in (d_lab, d_conf, d_prob, d_status, d_suc, d_info, d_bounds, d_preds)]
+                fpt = d_fpt.cpu().numpy() if want_fpt else None
+            st.synchronize()
+        labels, conf, prob, status, suc, info, bounds, preds = [t.numpy() for t in out]
+        predictions = None
+        if return_df:
+            good = status == 0
+            predictions = predictions_to_df(labels[good], prob[good], conf[good], self.model_predict.label_mapper)
+            ids = np.asarray(read_ids if read_ids is not None else np.arange(n))[good]
+            predictions = add_read_id_col_to_predictions(predictions, ids)
+        return MinibatchResult(labels, conf, prob, status, suc, info[:, 0].copy(), info[:, 1].copy(), bounds, preds, rescued,
+                               predictions, fpt)
+
+    def close(self):
+        self.validator.close()
+        self.fingerprinter.close()
+        self._buf = {}
+
+
+def detect_and_predict_on_preloaded_signals(preloaded_minibatch, model_predict, model_detect, config,
+                                            demuxer: Optional[MinibatchDemuxer] = None) -> MinibatchResult:
+    """Argument order of the reference worker (file_proc.py:380-390) without its queues: `preloaded_minibatch` =
+    (signals, _, full_lengths, read_ids); `config.sig_proc` is the SigProcConfig."""
+    signals, _, full_lengths, read_ids = preloaded_minibatch
+    spc = config.sig_proc if hasattr(config, "sig_proc") else config
+    if getattr(spc, "primary_method", "cnn") != "cnn":
+        raise NotImplementedError("only primary_method = 'cnn' is on the GPU path (llr / start_peak detection stay with the reference)")
+    d = demuxer or MinibatchDemuxer(model_predict, model_detect, spc)
+    try:
+        return d.run(signals, full_lengths, read_ids, return_df=True)
+    finally:
+        if demuxer is None:
+            d.close()

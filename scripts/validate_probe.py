@@ -70,6 +70,8 @@ def main(n_base=256, reps=int(os.environ.get("VAL_REPS", "32")), stride=int(os.e
     print(json.dumps(dict(stage="validate", reads=n, stride=stride, kernel_ms=round(best, 3), reads_per_s=round(n / best * 1e3),
                           alg_GBps=round(alg / best / 1e6, 1), codes=dict(zip(codes.tolist(), cnt.tolist())))), flush=True)
 
+    if os.environ.get("VAL_ONLY") == "1":
+        return
     # chained pipeline on the same rows: CNN (guarded) -> validation -> fingerprint + DTW/SVC (guarded)
     model = cnn.load_cnn_model(os.path.join(GOLD, "models", "cnn_rna004_130bps_v0.2.4.npz"), device=0)
     core, cb = cnn.CoreConfig(), cnn.CNNBoundariesConfig(polya_cand_k=k)

@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwdx_b200.so")
+LIB_PATH = os.environ.get("WDX_B200_LIB") or os.path.join(_HERE, "lib", "libwdx_b200.so")  # override: kernel-variant experiments
 
 WDX_F64, WDX_F32 = 0, 1
 MODE_EXACT_F64, MODE_FAST_F32, MODE_FAST_F32_GUARDED = 0, 1, 2

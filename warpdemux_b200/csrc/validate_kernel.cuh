@@ -25,6 +25,14 @@
 #include <math.h>
 #include <stdint.h>
 
+// CTA shape of this translation unit (block_select.cuh helpers follow WDX_FP_THREADS)
+#ifndef WDX_VAL_THREADS
+#define WDX_VAL_THREADS 512
+#endif
+#ifndef WDX_VAL_MIN_CTAS
+#define WDX_VAL_MIN_CTAS 2
+#endif
+#define WDX_FP_THREADS WDX_VAL_THREADS
 #include "block_select.cuh"
 
 namespace wdx {
@@ -62,32 +70,66 @@ struct ValArgs {
     float* scratch;            // [gridDim.x][stride] moving-window statistics
 };
 
-// numpy's pairwise summation (np.add.reduce on a contiguous 1-D array), any n.
+// numpy's pairwise summation (np.add.reduce on a contiguous 1-D array): a block of n <= 128 elements is
+// summed with 8 strided accumulators, a fixed combination tree and a sequential tail ...
 template <typename T, typename F>
-__device__ T np_pairwise(int lo, int n, F at) {
+__device__ __forceinline__ T np_pairwise_leaf(int lo, int n, F at) {
     if (n < 8) {
         T r = (T)0;
         for (int i = 0; i < n; i++) r = r + at(lo + i);
         return r;
     }
-    if (n <= 128) {
-        T r[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) r[j] = at(lo + j);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = r[j] + at(lo + i + j);
-        }
-        T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; i++) res = res + at(lo + i);
-        return res;
+    T r0 = at(lo), r1 = at(lo + 1), r2 = at(lo + 2), r3 = at(lo + 3), r4 = at(lo + 4), r5 = at(lo + 5), r6 = at(lo + 6),
+      r7 = at(lo + 7);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 = r0 + at(lo + i);
+        r1 = r1 + at(lo + i + 1);
+        r2 = r2 + at(lo + i + 2);
+        r3 = r3 + at(lo + i + 3);
+        r4 = r4 + at(lo + i + 4);
+        r5 = r5 + at(lo + i + 5);
+        r6 = r6 + at(lo + i + 6);
+        r7 = r7 + at(lo + i + 7);
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    const T a = np_pairwise<T>(lo, n2, at);
-    const T b = np_pairwise<T>(lo + n2, n - n2, at);
-    return a + b;
+    T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; i++) res = res + at(lo + i);
+    return res;
+}
+
+// ... and longer arrays are halved recursively (left half rounded down to a multiple of 8); the recursion
+// is unrolled onto an explicit stack here.
+template <typename T, typename F>
+__device__ T np_pairwise(int lo, int n, F at) {
+    if (n <= 128) return np_pairwise_leaf<T>(lo, n, at);
+    struct Frame {
+        int lo, n, state;
+        T left;
+    };
+    Frame st[24];
+    int sp = 0;
+    st[sp++] = Frame{lo, n, 0, (T)0};
+    T result = (T)0;
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        int n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.n <= 128) {
+            result = np_pairwise_leaf<T>(f.lo, f.n, at);
+            sp--;
+        } else if (f.state == 0) {
+            f.state = 1;
+            st[sp++] = Frame{f.lo, n2, 0, (T)0};
+        } else if (f.state == 1) {
+            f.left = result;
+            f.state = 2;
+            st[sp++] = Frame{f.lo + n2, f.n - n2, 0, (T)0};
+        } else {
+            result = f.left + result;
+            sp--;
+        }
+    }
+    return result;
 }
 
 // ---- order statistics ---------------------------------------------------------------------------------
@@ -275,12 +317,13 @@ __device__ double val_local_range(int n, VAL val, ValSel& vs, FpScratch& s, floa
 
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
 
-__global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, const ValCfg c) {
+__global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(const ValArgs a, const ValCfg c) {
     extern __shared__ float vsig[];
     __shared__ FpScratch s;
     __shared__ ValSel vs;
     __shared__ int sh_i[6];
     __shared__ double sh_d[4];
+    __shared__ double sh_v[VAL_NVALS];
     const int tid = threadIdx.x;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     float* scratch = a.scratch + (size_t)blockIdx.x * a.stride;
@@ -291,6 +334,7 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
         const int64_t fl = a.full_len[r];
         const int L = (int)max((int64_t)0, min(fl, a.stride));
         int has_nan = 0;
+        if (tid < VAL_NVALS) sh_v[tid] = qnan;
         for (int i = tid; i < L; i += FP_THREADS) {
             const float x = row[i];
             vsig[i] = x;
@@ -303,9 +347,8 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
         int64_t a0 = 0;
         int64_t pe_best = a.ld > 1 ? pr[1] : 0;
         int code = VAL_OK, checks = 0, n_pores = 0;
-        double v[VAL_NVALS];
-#pragma unroll
-        for (int j = 0; j < VAL_NVALS; j++) v[j] = qnan;
+        // reported statistics live in shared memory (thread 0 writes them as they are found); the fill above is
+        // ordered before those writes by the barrier of the NaN vote
 
         if (has_nan) code = VAL_HAS_NAN;
         const int hi = (int)max((int64_t)0, min(a1, (int64_t)L));   // sig[a0:a1] ends here
@@ -315,8 +358,10 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
             else {
                 med = val_median(hi, [&](int i) { return vsig[i]; }, vs, s);
                 mad = val_median(hi, [&](int i) { return fabsf(__fsub_rn(vsig[i], med)); }, vs, s);
-                v[0] = (double)med;
-                v[1] = (double)mad;
+                if (tid == 0) {
+                    sh_v[0] = (double)med;
+                    sh_v[1] = (double)mad;
+                }
             }
         }
         if (code == VAL_OK && mad != 0.f && !val_in_range((double)mad, c.mad_lo, c.mad_hi)) code = VAL_ADAPTER_MAD;
@@ -376,13 +421,17 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
                     sh_d[tid == 0 ? 0 : 1] = (double)__fdiv_rn(sm, (float)c.mean_window);
                 }
                 __syncthreads();
-                v[2] = sh_d[0];
-                v[3] = sh_d[1];
-                if (val_in_range(v[2], c.mean_start_lo, c.mean_start_hi) && val_in_range(v[3], c.mean_end_lo, c.mean_end_hi)) {
+                const double mean_start = sh_d[0], mean_end = sh_d[1];
+                if (tid == 0) {
+                    sh_v[2] = mean_start;
+                    sh_v[3] = mean_end;
+                }
+                if (val_in_range(mean_start, c.mean_start_lo, c.mean_start_hi) && val_in_range(mean_end, c.mean_end_lo, c.mean_end_hi)) {
                     const int nn = min(c.max_obs_local_range, nseg);
                     const int base = hi - nn;
-                    v[4] = val_local_range(nn, [&](int i) { return vsig[base + i]; }, vs, s, nullptr);
-                    ok = val_in_range(v[4], c.local_range_lo, c.local_range_hi);
+                    const double lr = val_local_range(nn, [&](int i) { return vsig[base + i]; }, vs, s, nullptr);
+                    if (tid == 0) sh_v[4] = lr;
+                    ok = val_in_range(lr, c.local_range_lo, c.local_range_hi);
                 }
             }
             if (!ok) code = VAL_REAL_RANGE;
@@ -468,11 +517,13 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
                                (val_in_range(r_shift, c.shift_lo, c.shift_hi) ? 16 : 0);
                         okc = bits == 31;
                     }
-                    v[5] = r_mean;
-                    v[6] = r_var;
-                    v[7] = r_med;
-                    v[8] = r_lr;
-                    v[9] = r_shift;
+                    if (tid == 0) {
+                        sh_v[5] = r_mean;
+                        sh_v[6] = r_var;
+                        sh_v[7] = r_med;
+                        sh_v[8] = r_lr;
+                        sh_v[9] = r_shift;
+                    }
                     if (!okc) {   // `success` is never set back to True: later candidates only overwrite the report
                         if (r_mean == 0.0) {
                             code = VAL_MVS_NO_SIGNAL;
@@ -495,8 +546,9 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
             const int up = (int)min(min(a1 + c.med_shift_window, fl), (int64_t)L), dn = (int)max(a1 - c.med_shift_window, (int64_t)0);
             const float m_after = val_median(max(0, up - e), [&](int i) { return vsig[e + i]; }, vs, s);
             const float m_before = val_median(max(0, e - min(dn, e)), [&](int i) { return vsig[min(dn, e) + i]; }, vs, s);
-            v[10] = (double)__fsub_rn(m_after, m_before);
-            if (!val_in_range(v[10], c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
+            const double ms = (double)__fsub_rn(m_after, m_before);
+            if (tid == 0) sh_v[10] = ms;
+            if (!val_in_range(ms, c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
         }
 
         if (tid == 0) {
@@ -509,7 +561,7 @@ __global__ void __launch_bounds__(FP_THREADS) validate_kernel(const ValArgs a, c
             a.bounds[r * 3 + 1] = a1;
             a.bounds[r * 3 + 2] = pe_best;
             if (a.vals)
-                for (int j = 0; j < VAL_NVALS; j++) a.vals[r * VAL_NVALS + j] = v[j];
+                for (int j = 0; j < VAL_NVALS; j++) a.vals[r * VAL_NVALS + j] = sh_v[j];
         }
     }
 }

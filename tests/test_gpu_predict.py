@@ -332,3 +332,50 @@ def test_fast_distances_tolerance_through_fused_kernel(models, dev_models):
         rel[ref32 == 0] = np.where(got[ref32 == 0] == 0, 0.0, np.inf)
         assert rel.max() <= FAST_RTOL + 1.2e-7, (name, rel.max())   # + one float32 rounding of the stored distance
         assert (want < 0.25).sum() > 50                               # the near-zero branch was exercised
+
+
+def test_small_batch_host_path_equals_chunked_path(models, dev_models):
+    """Live-sized batches with host buffers take the one-copy-each-way path (<= 8192 reads); larger ones the
+    pipelined chunk path.  Same kernels, so labels are identical and probabilities agree to summation geometry."""
+    import torch
+
+    from warpdemux_b200 import _lib
+
+    name = "WDX4_rna004_v1_0"
+    m, d = models[name], dev_models[name]
+    X = synth_fingerprints(m.sv, 8300, seed=9)
+    for mode in ("exact", "guarded"):
+        la, pa, ca, _ = d.predict(X, mode=mode)                 # chunk path
+        lb, pb, cb, _ = d.predict(X[:8192], mode=mode)          # small path at its upper edge
+        lc, pc, cc, _ = d.predict(X[:3], mode=mode)
+        assert np.array_equal(la[:8192], lb) and np.array_equal(la[:3], lc)
+        assert np.abs(pa[:8192] - pb).max() < 2e-6 and np.abs(pa[:3] - pc).max() < 2e-6
+        assert np.abs(ca[:8192] - cb).max() < 4e-6
+    # labels only (conf / prob / flags NULL), pinned and float32 inputs
+    lab = np.empty(100, dtype=np.int64)
+    Xp = torch.from_numpy(X[:100].copy()).pin_memory()
+    d.predict_raw(Xp, 100, _lib.WDX_F64, _lib.MODE_FAST_F32_GUARDED, lab)
+    assert np.array_equal(lab, la[:100])
+    lab32 = np.empty(100, dtype=np.int64)
+    d.predict_raw(X[:100].astype(np.float32), 100, _lib.WDX_F32, _lib.MODE_EXACT_F64, lab32)
+    want, _, _, _ = d.predict(X[:100].astype(np.float32).astype(np.float64), mode="exact")
+    assert np.array_equal(lab32, want)
+
+
+def test_warp_finish_is_bit_identical_to_thread_finish(models, dev_models):
+    """Batches <= 16384 reads finish with one warp per read (latency), larger ones with one thread per read
+    (throughput).  With the same SV-range geometry the two must agree to the last bit."""
+    for name in ("WDX4_rna004_v1_0", "WDX10_rna004_v1_0"):
+        m, d = models[name], dev_models[name]
+        X = synth_fingerprints(m.sv, 16500, seed=11)
+        X[5] = np.nan                      # non-finite fingerprint -> label -1, NaN probabilities on both paths
+        X[7] = m.sv[3]                     # zero distance to a support vector
+        d.set_sv_splits(8)
+        try:
+            for mode in ("exact", "fast"):
+                lb, pb, cb, fb = d.predict(X, mode=mode)            # thread-per-read finish
+                ls, ps, cs, fs = d.predict(X[:4000], mode=mode)     # warp-per-read finish
+                assert np.array_equal(lb[:4000], ls) and np.array_equal(fb[:4000], fs)
+                assert np.array_equal(pb[:4000], ps, equal_nan=True) and np.array_equal(cb[:4000], cs, equal_nan=True)
+        finally:
+            d.set_sv_splits(0)

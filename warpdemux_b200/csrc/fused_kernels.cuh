@@ -394,6 +394,134 @@ __global__ void __launch_bounds__(256) svc_fold_splits_kernel(const __grid_const
     part[(size_t)pi * part_stride + slot] = sum;
 }
 
+// Same arithmetic as svc_finish_kernel below, one WARP per read: for live-sized batches the single-thread
+// coupling iteration (up to 100 sweeps over a k x k system with a division per element) is the latency of the
+// whole call (150 us at k = 11).  Lane t owns row t of Q, p[t] and Qp[t]; every sum runs in the serial order
+// (operands fetched with shuffles), the Gauss-Seidel sweep stays sequential in t but its k-wide updates and
+// divisions run across the lanes - bit-identical results, ~k times shorter dependency chain.
+constexpr int FINISH_WARPS = 4;
+__global__ void __launch_bounds__(FINISH_WARPS * 32) svc_finish_warp_kernel(const __grid_constant__ ModelDev m,
+                                                                            const __grid_constant__ FinishArgs a) {
+    __shared__ double Rs[FINISH_WARPS][MAXK][MAXK];
+    __shared__ double Qs[FINISH_WARPS][MAXK][MAXK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n_eff = a.n_idx ? min((int64_t)(*a.n_idx), a.n) : a.n;
+    const int64_t slot = (int64_t)blockIdx.x * FINISH_WARPS + w;
+    if (slot >= n_eff) return;   // whole warp
+    const int64_t row = a.read_idx ? (int64_t)a.read_idx[slot] : slot;
+    const int k = m.k;
+    const unsigned full = 0xffffffffu;
+    double (*R)[MAXK] = Rs[w];
+    double (*Q)[MAXK] = Qs[w];
+
+    bool bad = false;
+    {
+        int pi = 0;
+        for (int i = 0; i < k; i++)
+            for (int j = i + 1; j < k; j++, pi++) {
+                if ((pi & 31) != lane) continue;
+                double sum = 0.0;
+                for (int sp = 0; sp < a.n_splits; sp++) {
+                    const int b = sp * a.sv_per_split, e = min(m.n_sv, b + a.sv_per_split);
+                    if (b < e && (range_touches(m, b, e, i) || range_touches(m, b, e, j)))
+                        sum += a.part[((size_t)sp * m.n_pairs + pi) * a.part_stride + slot];
+                }
+                const double dec = sum - m.rho[pi];
+                bad |= !(fabs(dec) <= 1.7e308);
+                const double fApB = dec * m.probA[pi] + m.probB[pi];
+                double r = (fApB >= 0) ? exp(-fApB) / (1.0 + exp(-fApB)) : 1.0 / (1 + exp(fApB));
+                const double min_prob = 1e-7;
+                r = (r < min_prob) ? min_prob : r;
+                r = ((1 - min_prob) < r) ? (1 - min_prob) : r;
+                R[i][j] = r;
+                R[j][i] = 1 - r;
+            }
+    }
+    bad = __any_sync(full, bad);
+    __syncwarp();
+
+    const bool act = lane < k;
+    const int t_own = act ? lane : 0;
+    double p = 0.0, Qp = 0.0;
+    if (!bad) {
+        const int max_iter = (k > 100) ? k : 100;
+        const double eps = 0.005 / k;
+        if (act) {
+            const int t = lane;
+            double qtt = 0;
+            for (int j = 0; j < t; j++) { qtt += R[j][t] * R[j][t]; Q[t][j] = -R[j][t] * R[t][j]; }
+            for (int j = t + 1; j < k; j++) { qtt += R[j][t] * R[j][t]; Q[t][j] = -R[j][t] * R[t][j]; }
+            Q[t][t] = qtt;
+        }
+        p = 1.0 / k;
+        __syncwarp();
+        for (int iter = 0; iter < max_iter; iter++) {
+            Qp = 0;
+            for (int j = 0; j < k; j++) {
+                const double pj = __shfl_sync(full, p, j);
+                Qp += Q[t_own][j] * pj;
+            }
+            double pQp = 0;
+            for (int t = 0; t < k; t++) pQp += __shfl_sync(full, p, t) * __shfl_sync(full, Qp, t);
+            double err = act ? fabs(Qp - pQp) : 0.0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) err = fmax(err, __shfl_xor_sync(full, err, o));
+            if (err < eps) break;
+            for (int t = 0; t < k; t++) {
+                const double Qp_t = __shfl_sync(full, Qp, t);
+                const double qtt = Q[t][t];
+                const double diff = (-Qp_t + pQp) / qtt;
+                if (lane == t) p += diff;
+                pQp = (pQp + diff * (diff * qtt + 2 * Qp_t)) / (1 + diff) / (1 + diff);
+                if (act) {
+                    Qp = (Qp + diff * Q[t][lane]) / (1 + diff);
+                    p /= (1 + diff);
+                }
+            }
+        }
+    }
+    // process_probs (models/utils.py:45-61): first maximum, top1 - top2 — every lane walks the classes in order
+    int best = k - 1;
+    double top1 = 0.0, top2 = 0.0;
+    if (!bad) {
+        best = 0;
+        double pb = __shfl_sync(full, p, 0);
+        for (int c = 1; c < k; c++) {
+            const double pc = __shfl_sync(full, p, c);
+            if (pc > pb) { pb = pc; best = c; }
+        }
+        top1 = pb;
+        top2 = -INFINITY;
+        for (int c = 0; c < k; c++) {
+            const double pc = __shfl_sync(full, p, c);
+            if (c != best && pc > top2) top2 = pc;
+        }
+    }
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double conf = bad ? nan : (top1 - top2);
+    const double thr = m.thresholds[best];
+    if (a.prob && act) a.prob[(size_t)row * k + lane] = bad ? nan : p;
+    if (lane == 0) {
+        int64_t label = m.label_map[best];
+        if (bad || conf < thr) label = -1;
+        a.labels[row] = label;
+        if (a.conf) a.conf[row] = conf;
+        if (a.flags) a.flags[row] = (uint8_t)((bad ? 1 : 0) | a.flag_or);
+        if (a.near_idx && !bad) {
+            const bool near = (fabs(conf - thr) < a.guard) || (conf < a.guard);
+            if (near) {
+                const int pos = atomicAdd(a.near_count, 1);
+                if (pos < a.near_cap) {
+                    a.near_idx[pos] = (int)row;
+                } else {
+                    atomicAdd(a.near_count + 1, 1);
+                    if (a.flags) a.flags[row] |= 4;  // WDX_FLAG_GUARD_OVERFLOW
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) svc_finish_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ FinishArgs a) {
     const int64_t n_eff = a.n_idx ? min((int64_t)(*a.n_idx), a.n) : a.n;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

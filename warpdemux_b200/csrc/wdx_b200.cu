@@ -215,6 +215,12 @@ int launch_fused(wdx_model* m, bool exact, const PredictArgs& pa_in, int64_t gri
     return WDX_OK;
 }
 
+constexpr int64_t FINISH_WARP_MAX_ROWS = 16384;
+bool finish_warp_disabled() {
+    static const bool off = [] { const char* e = getenv("WDX_NO_FINISH_WARP"); return e && e[0] == '1'; }();
+    return off;
+}
+
 int launch_finish(wdx_model* m, const FinishArgs& fa_in, int64_t grid_rows, cudaStream_t st) {
     FinishArgs fa = fa_in;
     if (fa.n_splits > 1) {  // fold the SV ranges first (parallel over pairs x reads), then finish as one range
@@ -226,18 +232,26 @@ int launch_finish(wdx_model* m, const FinishArgs& fa_in, int64_t grid_rows, cuda
         fa.n_splits = 1;
         fa.sv_per_split = m->n_sv;
     }
-    const unsigned blocks = (unsigned)((grid_rows + 127) / 128);
-    svc_finish_kernel<<<blocks, 128, 0, st>>>(m->dev, fa);
+    if (grid_rows <= FINISH_WARP_MAX_ROWS && !finish_warp_disabled()) {   // live-sized batch: one warp per read (latency)
+        const unsigned blocks = (unsigned)((grid_rows + FINISH_WARPS - 1) / FINISH_WARPS);
+        svc_finish_warp_kernel<<<blocks, FINISH_WARPS * 32, 0, st>>>(m->dev, fa);
+    } else {
+        const unsigned blocks = (unsigned)((grid_rows + 127) / 128);
+        svc_finish_kernel<<<blocks, 128, 0, st>>>(m->dev, fa);
+    }
     CUDA_TRY(cudaGetLastError());
     g_launches++;
     return WDX_OK;
 }
 
-void choose_splits(const wdx_model* m, int64_t n, int* n_splits, int* sv_per_split) {
+// A thread walks its SV range serially, so for a live-sized batch the range length IS the latency of the call:
+// 41 SVs per range (64 ranges of WDX10) cost 74 us in FAST and 330 us in EXACT arithmetic, measured; shorter
+// ranges are paid for by the fold over the partial sums (profiles/r01o_latency_sweep.jsonl: best at 128 / 512).
+void choose_splits(const wdx_model* m, int64_t n, bool exact, int* n_splits, int* sv_per_split) {
     const int64_t ctas_x = (n + CTA_THREADS - 1) / CTA_THREADS;
     const int64_t target = (int64_t)m->sm_count * 4 * 2;  // two full waves of 4 CTAs/SM
     int splits = 1;
-    if (ctas_x < target) splits = (int)std::min<int64_t>(64, (target + ctas_x - 1) / ctas_x);
+    if (ctas_x < target) splits = (int)std::min<int64_t>(exact ? 512 : 128, (target + ctas_x - 1) / ctas_x);
     if (m->forced_splits > 0) splits = m->forced_splits;
     splits = std::max(1, std::min(splits, m->n_sv));
     int per = (m->n_sv + splits - 1) / splits;
@@ -252,7 +266,7 @@ void choose_splits(const wdx_model* m, int64_t n, int* n_splits, int* sv_per_spl
 int wdx::predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, int mode, int64_t* labels_d,
                          double* conf_d, double* prob_d, uint8_t* flags_d, float* dist_d, cudaStream_t st) {
     int n_splits, per;
-    choose_splits(m, n, &n_splits, &per);
+    choose_splits(m, n, mode == WDX_MODE_EXACT_F64, &n_splits, &per);
     const int64_t stride = (n + 31) & ~(int64_t)31;
     int rc = m->part.reserve((size_t)n_splits * m->n_pairs * stride * sizeof(double));
     if (rc) return rc;
@@ -306,7 +320,7 @@ int wdx::predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_
 
     if (guarded) {
         int s2, per2;
-        choose_splits(m, std::max<int64_t>(1, cap / 16), &s2, &per2);  // expect the list to be mostly empty
+        choose_splits(m, std::max<int64_t>(1, cap / 16), true, &s2, &per2);  // expect the list to be mostly empty
         const int64_t stride2 = (cap + 31) & ~(int64_t)31;
         rc = m->part2.reserve((size_t)s2 * m->n_pairs * stride2 * sizeof(double));
         if (rc) return rc;
@@ -460,6 +474,8 @@ void wdx_model_destroy(wdx_model* m) {
     m->part2.release();
     m->near_idx.release();
     m->counters.release();
+    m->small_dev.release();
+    m->small_pin.release();
     for (int i = 0; i < 2; i++) {
         m->xdev[i].release();
         m->xpin[i].release();
@@ -531,6 +547,46 @@ int wdx_model_last_kernel_ms_mode(wdx_model* m, int exact, double* ms, int* laun
     return kernel_ms_impl(m, exact ? 1 : 0, ms, launches);
 }
 
+namespace {
+constexpr int64_t SMALL_BATCH_MAX = 8192;
+
+bool small_path_disabled() {
+    static const bool off = [] { const char* e = getenv("WDX_NO_SMALL_PATH"); return e && e[0] == '1'; }();
+    return off;
+}
+
+// Live-sized batch with every buffer in host memory (the read-until caller, live_balancing/worker.py:117-120):
+// input and results share ONE device block mirrored by ONE pinned block, so the call costs one H2D, the
+// kernels, one D2H and one stream synchronisation instead of a copy and a wait per output array.
+int predict_small_host(wdx_model* m, const void* X, int64_t n, int esz, int x_kind, int mode, int64_t* labels, double* conf,
+                       double* prob, uint8_t* flags, cudaStream_t st) {
+    const int L = m->L, k = m->k;
+    const size_t x_bytes = ((size_t)n * L * esz + 15) & ~(size_t)15;
+    const size_t o_lab = x_bytes, o_conf = o_lab + (size_t)n * 8, o_prob = o_conf + (size_t)n * 8,
+                 o_flag = o_prob + (size_t)n * k * 8, total = (o_flag + (size_t)n + 15) & ~(size_t)15;
+    int rc;
+    if ((rc = m->small_dev.reserve(total)) || (rc = m->small_pin.reserve(total))) return rc;
+    char* d = (char*)m->small_dev.p;
+    char* h = (char*)m->small_pin.p;
+    const void* src = X;
+    if (x_kind == 0) {   // pageable: stage through the pinned block
+        std::memcpy(h, X, (size_t)n * L * esz);
+        src = h;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d, src, (size_t)n * L * esz, cudaMemcpyHostToDevice, st));
+    rc = wdx::predict_chunk_device(m, d, esz == 4, n, mode, (int64_t*)(d + o_lab), (double*)(d + o_conf), (double*)(d + o_prob),
+                                   (uint8_t*)(d + o_flag), nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h + o_lab, d + o_lab, total - o_lab, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::memcpy(labels, h + o_lab, (size_t)n * 8);
+    if (conf) std::memcpy(conf, h + o_conf, (size_t)n * 8);
+    if (prob) std::memcpy(prob, h + o_prob, (size_t)n * k * 8);
+    if (flags) std::memcpy(flags, h + o_flag, (size_t)n);
+    return WDX_OK;
+}
+}  // namespace
+
 int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, int64_t* labels, double* conf,
                 double* prob, uint8_t* flags, float* dist, void* stream) {
     if (!m) return fail(WDX_ERR_INVALID, "NULL model");
@@ -556,6 +612,8 @@ int wdx_predict(wdx_model* m, const void* X, int64_t n, int x_dtype, int mode, i
                           (dist && !dist_devp);
     const bool any_host = !x_dev || out_host;
     cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    if (n <= SMALL_BATCH_MAX && !x_dev && !lab_dev && !conf_devp && !prob_devp && !flag_devp && !dist && !small_path_disabled())
+        return predict_small_host(m, X, n, esz, x_kind, mode, labels, conf, prob, flags, st);
 
     int64_t chunk = m->chunk_reads;
     if (any_host) chunk = std::min<int64_t>(chunk, (int64_t)1 << 21);  // finer pipeline when copies are involved

@@ -64,6 +64,8 @@ struct wdx_model {
     DevBuf part, part2, near_idx, counters;
     DevBuf xdev[2], lab_dev[2], conf_dev[2], prob_dev[2], flag_dev[2], dist_dev[2];
     HostBuf xpin[2];
+    DevBuf small_dev;   // live-sized batches: input and all results in one device block ...
+    HostBuf small_pin;  // ... mirrored by one pinned block (one copy each way, one synchronisation)
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
                 ev_d2h[2] = {nullptr, nullptr};
     // timing of the fused kernel

@@ -122,6 +122,18 @@ def main(n_base=256, reps=int(os.environ.get("VAL_REPS", "32")), stride=int(os.e
     print(json.dumps(dict(stage="MinibatchDemuxer.run from pinned host rows (e2e)", reads=n, ms=round(best * 1e3, 2),
                           reads_per_s=round(n / best), h2d_GBps=round(h_sig.numel() * 4 / best / 1e9, 1),
                           validated=int(r.detect_success.sum()), fp_ok=int((r.fp_status == 0).sum()))), flush=True)
+    mb = 1000
+    mbs = [(h_sig[a:a + mb], h_len[a:a + mb]) for a in range(0, n - mb + 1, mb)] * 4
+    for it in range(2):
+        t0 = time.perf_counter()
+        got = sum(int(x.labels.size) for x in dmx.stream(mbs, return_df=False))
+        dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    got2 = sum(int(dmx.run(a, b, return_df=False).labels.size) for a, b in mbs)
+    dt2 = time.perf_counter() - t0
+    print(json.dumps(dict(stage="1000-read minibatches from pinned host rows", minibatches=len(mbs), stream_reads_per_s=round(got / dt),
+                          stream_ms_per_minibatch=round(dt / len(mbs) * 1e3, 3), run_reads_per_s=round(got2 / dt2),
+                          run_ms_per_minibatch=round(dt2 / len(mbs) * 1e3, 3))), flush=True)
 
 
 if __name__ == "__main__":

@@ -233,6 +233,18 @@ def test_gpu_minibatch_step_matches_reference_worker(golden_real, models):
     ok2 = res2.detect_success.astype(bool)
     assert np.array_equal(res2.labels[ok2], res.labels[ok2]) and (res2.labels[~ok2] == -1).all()
     assert all(res2.fail_reason(i) == combined.fail_reason(int(res2.detect_code[i]), int(res2.detect_checks[i])) for i in np.flatnonzero(~ok2))
+    # pipelined stream of minibatches (upload of i+1 overlaps the kernels of i) == one run() per minibatch
+    cuts = [(0, 20), (20, 21), (21, n)]
+    mbs = [(sig[a:b], full_lens[a:b], read_ids[a:b]) for a, b in cuts]
+    streamed = list(dmx2.stream(mbs, want_fpt=True))
+    assert len(streamed) == len(cuts)
+    for (a, b), r_s in zip(cuts, streamed):
+        r_1 = dmx2.run(sig[a:b], full_lens[a:b], read_ids[a:b], want_fpt=True)
+        assert np.array_equal(r_s.labels, r_1.labels) and np.array_equal(r_s.fp_status, r_1.fp_status)
+        assert np.array_equal(r_s.bounds, r_1.bounds) and np.array_equal(r_s.preds, r_1.preds)
+        assert np.array_equal(r_s.fpt, r_1.fpt, equal_nan=True) and np.array_equal(r_s.prob, r_1.prob, equal_nan=True)
+        assert list(r_s.predictions["#read_id"]) == list(r_1.predictions["#read_id"])
+    assert list(dmx2.stream([])) == []
     dmx.close()
     dmx2.close()
     model_detect.close()

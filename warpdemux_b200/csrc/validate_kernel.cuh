@@ -68,6 +68,8 @@ struct ValArgs {
     int64_t* bounds;           // [n][3] adapter_start, adapter_end, polya_end
     double* vals;              // [n][VAL_NVALS] or nullptr
     float* scratch;            // [gridDim.x][stride] moving-window statistics
+    unsigned long long* next;  // work counter (zeroed before the launch): reads are handed out dynamically, because a
+                               // read whose first poly(A) candidate fails costs several times a read that validates
 };
 
 // numpy's pairwise summation (np.add.reduce on a contiguous 1-D array): a block of n <= 128 elements is
@@ -328,8 +330,13 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     float* scratch = a.scratch + (size_t)blockIdx.x * a.stride;
 
-    for (int64_t r = blockIdx.x; r < a.n; r += gridDim.x) {
+    __shared__ unsigned long long sh_next;
+    for (;;) {
         __syncthreads();
+        if (tid == 0) sh_next = atomicAdd(a.next, 1ULL);
+        __syncthreads();
+        const int64_t r = (int64_t)sh_next;
+        if (r >= a.n) break;
         const float* row = a.signals + (size_t)r * a.stride;
         const int64_t fl = a.full_len[r];
         const int L = (int)max((int64_t)0, min(fl, a.stride));

@@ -16,7 +16,7 @@ struct wdx_validate {
     int smem_max = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr;
-    DevBuf sig, len, preds, success, info, bounds, vals, scratch;
+    DevBuf sig, len, preds, success, info, bounds, vals, scratch, counter;
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -106,7 +106,7 @@ int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate
 void wdx_validate_destroy(wdx_validate* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->scratch}) b->release();
+    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->scratch, &h->counter}) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -204,6 +204,9 @@ int wdx_validate_run(wdx_validate* h, const float* signals, int64_t n, int64_t s
     a.bounds = bnd_dev ? bounds : (int64_t*)h->bounds.p;
     a.vals = vals ? (val_dev ? vals : (double*)h->vals.p) : nullptr;
     a.scratch = (float*)h->scratch.p;
+    if ((rc = h->counter.reserve(16))) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, 8, st));
+    a.next = (unsigned long long*)h->counter.p;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     validate_kernel<<<grid, FP_THREADS, smem, st>>>(a, h->cfg);
     CUDA_TRY(cudaGetLastError());

@@ -97,7 +97,9 @@ class MinibatchDemuxer:
         self.llr_fallback = llr_fallback
         self.k_cand = int(self.cnn_boundaries.polya_cand_k)
         self._stream = None
+        self._copy_stream = None
         self._buf = {}
+        self._pin = {}
 
     # -- device plumbing ---------------------------------------------------------
     def _dev(self):
@@ -111,88 +113,175 @@ class MinibatchDemuxer:
             self._buf[name] = t
         return t[:need].view(*shape)
 
-    def run(self, signals, full_lengths, read_ids: Optional[Sequence] = None, return_df: bool = True,
-            want_fpt: bool = False) -> MinibatchResult:
-        """signals: float32 [n, stride] NaN-padded minibatch (numpy, pinned or not; or a CUDA tensor);
-        full_lengths: [n] full read lengths (file_proc.py:241-262)."""
+    # -- the three phases of one minibatch (slot = one set of device / pinned buffers) -----------------------
+    def _streams(self):
         torch = self._torch
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=self._dev())        # kernels + result download
+            self._copy_stream = torch.cuda.Stream(device=self._dev())   # minibatch upload
+        return self._stream, self._copy_stream
+
+    def _upload(self, slot: int, signals, full_lengths, read_ids) -> dict:
+        """Phase 1 (copy stream): the minibatch goes to the device.  Pageable rows are first copied into the slot's
+        pinned staging block so that the H2D transfer itself is asynchronous."""
+        torch = self._torch
+        st, cst = self._streams()
+        job = {"slot": slot, "read_ids": read_ids}
+        if isinstance(signals, torch.Tensor):
+            if signals.dtype != torch.float32 or signals.dim() != 2 or not signals.is_contiguous():
+                raise ValueError("signals tensor must be contiguous float32 [n, stride]")
+            h_sig = None if signals.is_cuda else signals
+            d_sig = signals if signals.is_cuda else None
+        else:
+            h_sig, d_sig = torch.from_numpy(_cnn._as_batch(signals)), None
+        n, stride = (d_sig if d_sig is not None else h_sig).shape
+        lens = np.ascontiguousarray(np.minimum(np.asarray(full_lengths, dtype=np.int64).reshape(-1), np.iinfo(np.int32).max), dtype=np.int32)
+        if lens.shape[0] != n:
+            raise ValueError("full_lengths must have one entry per signal row")
+        job.update(n=n, stride=stride, lens=lens, h_sig=h_sig)
+        if d_sig is not None:
+            cst.wait_stream(torch.cuda.current_stream())   # the caller produced the tensor on its current stream
+        with torch.cuda.stream(cst):
+            if d_sig is None:
+                if not h_sig.is_pinned():
+                    pin = self._pinned(f"{slot}:sig", n * stride, torch.float32).view(n, stride)
+                    pin.copy_(h_sig)
+                    h_sig = pin
+                d_sig = self._get(f"{slot}:sig", (n, stride), torch.float32)
+                d_sig.copy_(h_sig, non_blocking=True)
+            d_len = self._get(f"{slot}:len", (n,), torch.int32)
+            pin_len = self._pinned(f"{slot}:len", n, torch.int32)
+            pin_len.copy_(torch.from_numpy(lens))
+            d_len.copy_(pin_len, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cst)
+        job.update(d_sig=d_sig, d_len=d_len, ev_h2d=ev)
+        return job
+
+    def _launch(self, job: dict, want_fpt: bool) -> None:
+        """Phase 2 (compute stream): CNN -> validation -> fingerprint + DTW/SVC, then the result download."""
+        torch = self._torch
+        st, _ = self._streams()
         dm = self.model_predict._device_model()
         k, L = self.model_predict.params.k, self.model_predict.params.L
-        with torch.cuda.device(self.device):
-            if self._stream is None:
-                self._stream = torch.cuda.Stream(device=self._dev())
-            st = self._stream
-            if isinstance(signals, torch.Tensor):
-                if signals.dtype != torch.float32 or signals.dim() != 2 or not signals.is_contiguous():
-                    raise ValueError("signals tensor must be contiguous float32 [n, stride]")
-                st.wait_stream(torch.cuda.current_stream())   # the caller produced the tensor on its current stream
-                d_sig = signals if signals.is_cuda else None
-                h_sig = None if signals.is_cuda else signals
-            else:
-                h_sig = torch.from_numpy(_cnn._as_batch(signals))
-                d_sig = None
-            n, stride = (d_sig if d_sig is not None else h_sig).shape
-            lens = np.ascontiguousarray(np.minimum(np.asarray(full_lengths, dtype=np.int64).reshape(-1), np.iinfo(np.int32).max), dtype=np.int32)
-            if lens.shape[0] != n:
-                raise ValueError("full_lengths must have one entry per signal row")
-            ld = 1 + self.k_cand
-            with torch.cuda.stream(st):
-                if d_sig is None:   # one upload; pinned memory makes it asynchronous
-                    d_sig = self._get("sig", (n, stride), torch.float32)
-                    d_sig.copy_(h_sig, non_blocking=True)
-                d_len = self._get("len", (n,), torch.int32)
-                d_len.copy_(torch.from_numpy(lens), non_blocking=True)
-                d_preds = self._get("preds", (n, ld), torch.int64)
-                d_suc = self._get("suc", (n,), torch.uint8)
-                d_info = self._get("info", (n, 4), torch.int32)
-                d_bounds = self._get("bounds", (n, 3), torch.int64)
-                d_a0 = self._get("a0", (n,), torch.int64)
-                d_a1 = self._get("a1", (n,), torch.int64)
-                d_lab = self._get("lab", (n,), torch.int64)
-                d_conf = self._get("conf", (n,), torch.float64)
-                d_prob = self._get("prob", (n, k), torch.float64)
-                d_status = self._get("status", (n,), torch.int32)
-                d_fpt = self._get("fpt", (n, L), torch.float64) if want_fpt else None
-                sp = st.cuda_stream
-                rescued = np.zeros(n, dtype=bool)
-                if n:
-                    _cnn.detect_raw(self.model_detect, self.core, self.k_cand, d_sig, n, stride, d_preds, mode=self.cnn_mode, stream=sp)
-                    self.validator.run_raw(d_sig, n, stride, d_len, d_preds, ld, d_suc, d_info, d_bounds, None, stream=sp)
-                    if self.llr_fallback is not None:
-                        suc_h = d_suc.cpu().numpy()            # synchronises this stream: n bytes
-                        failed = np.flatnonzero(suc_h == 0)
-                        if failed.size:
-                            rows = d_sig[torch.from_numpy(failed).to(self._dev())].cpu().numpy() if h_sig is None else h_sig.numpy()[failed]
-                            b_h = d_bounds.cpu().numpy()
-                            for j, i in enumerate(failed):
-                                res = self.llr_fallback(rows[j], int(lens[i]))
-                                if res is not None and getattr(res, "success", False):
-                                    b_h[i] = (int(res.adapter_start or 0), int(res.adapter_end), int(res.polya_end or 0))
-                                    suc_h[i] = 1
-                                    rescued[i] = True
-                            d_bounds.copy_(torch.from_numpy(b_h))
-                            d_suc.copy_(torch.from_numpy(suc_h))
-                    d_a0.copy_(d_bounds[:, 0])
-                    d_a1.copy_(d_bounds[:, 1])
-                    self.fingerprinter.predict_raw(dm, d_sig, n, stride, d_a0, d_a1, _lib.MODES[self.mode], d_lab, d_status,
-                                                   conf=d_conf, prob=d_prob, fpt=d_fpt, detect_ok=d_suc, stream=sp)
-                out = [t.cpu() for t in (d_lab, d_conf, d_prob, d_status, d_suc, d_info, d_bounds, d_preds)]
-                fpt = d_fpt.cpu().numpy() if want_fpt else None
-            st.synchronize()
-        labels, conf, prob, status, suc, info, bounds, preds = [t.numpy() for t in out]
+        n, stride, slot, lens = job["n"], job["stride"], job["slot"], job["lens"]
+        ld = 1 + self.k_cand
+        d_sig, d_len = job["d_sig"], job["d_len"]
+        g = lambda name, shape, dt: self._get(f"{slot}:{name}", shape, dt)
+        with torch.cuda.stream(st):
+            st.wait_event(job["ev_h2d"])
+            # every per-read result lives in ONE device block (8-byte aligned sections) mirrored by one pinned block
+            spec = [("preds", (n, ld), torch.int64), ("bounds", (n, 3), torch.int64), ("lab", (n,), torch.int64),
+                    ("conf", (n,), torch.float64), ("prob", (n, k), torch.float64), ("info", (n, 4), torch.int32),
+                    ("status", (n,), torch.int32), ("suc", (n,), torch.uint8)]
+            if want_fpt:
+                spec.insert(0, ("fpt", (n, L), torch.float64))
+            sizes = [(int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size() + 7) // 8 * 8 for _, shape, dt in spec]
+            total = sum(sizes)
+            d_block = g("results", (max(total, 8),), torch.uint8)
+            h_block = self._pinned(f"{slot}:results", max(total, 8), torch.uint8)
+            views, hviews, off = {}, {}, 0
+            for (name, shape, dt), sz in zip(spec, sizes):
+                nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size()
+                views[name] = d_block[off:off + nbytes].view(dt).view(*shape)
+                hviews[name] = h_block[off:off + nbytes].view(dt).view(*shape)
+                off += sz
+            d_preds, d_bounds, d_lab, d_conf, d_prob = views["preds"], views["bounds"], views["lab"], views["conf"], views["prob"]
+            d_info, d_status, d_suc = views["info"], views["status"], views["suc"]
+            d_fpt = views.get("fpt")
+            d_a0, d_a1 = g("a0", (n,), torch.int64), g("a1", (n,), torch.int64)
+            sp = st.cuda_stream
+            rescued = np.zeros(n, dtype=bool)
+            if n:
+                _cnn.detect_raw(self.model_detect, self.core, self.k_cand, d_sig, n, stride, d_preds, mode=self.cnn_mode, stream=sp)
+                self.validator.run_raw(d_sig, n, stride, d_len, d_preds, ld, d_suc, d_info, d_bounds, None, stream=sp)
+                if self.llr_fallback is not None:
+                    suc_h = d_suc.cpu().numpy()            # synchronises this stream: n bytes
+                    failed = np.flatnonzero(suc_h == 0)
+                    if failed.size:
+                        h_sig = job["h_sig"]
+                        rows = d_sig[torch.from_numpy(failed).to(self._dev())].cpu().numpy() if h_sig is None else h_sig.numpy()[failed]
+                        b_h = d_bounds.cpu().numpy()
+                        for j, i in enumerate(failed):
+                            res = self.llr_fallback(rows[j], int(lens[i]))
+                            if res is not None and getattr(res, "success", False):
+                                b_h[i] = (int(res.adapter_start or 0), int(res.adapter_end), int(res.polya_end or 0))
+                                suc_h[i] = 1
+                                rescued[i] = True
+                        d_bounds.copy_(torch.from_numpy(b_h))
+                        d_suc.copy_(torch.from_numpy(suc_h))
+                d_a0.copy_(d_bounds[:, 0])
+                d_a1.copy_(d_bounds[:, 1])
+                self.fingerprinter.predict_raw(dm, d_sig, n, stride, d_a0, d_a1, _lib.MODES[self.mode], d_lab, d_status,
+                                               conf=d_conf, prob=d_prob, fpt=d_fpt, detect_ok=d_suc, stream=sp)
+            h_block[:max(total, 8)].copy_(d_block, non_blocking=True)      # one download, does not block the host
+            host = hviews
+            ev = torch.cuda.Event()
+            ev.record(st)
+        job.update(host=host, ev_done=ev, rescued=rescued)
+
+    def _finalize(self, job: dict, return_df: bool) -> MinibatchResult:
+        """Phase 3 (host): wait for the download, copy out of the pinned blocks, build the DataFrame."""
+        job["ev_done"].synchronize()
+        h = {k: v.numpy().copy() for k, v in job["host"].items()}
+        labels, conf, prob, status = h["lab"], h["conf"], h["prob"], h["status"]
         predictions = None
         if return_df:
             good = status == 0
             predictions = predictions_to_df(labels[good], prob[good], conf[good], self.model_predict.label_mapper)
-            ids = np.asarray(read_ids if read_ids is not None else np.arange(n))[good]
+            rid = job["read_ids"]
+            ids = np.asarray(rid if rid is not None else np.arange(job["n"]))[good]
             predictions = add_read_id_col_to_predictions(predictions, ids)
-        return MinibatchResult(labels, conf, prob, status, suc, info[:, 0].copy(), info[:, 1].copy(), bounds, preds, rescued,
-                               predictions, fpt)
+        return MinibatchResult(labels, conf, prob, status, h["suc"], h["info"][:, 0].copy(), h["info"][:, 1].copy(), h["bounds"],
+                               h["preds"], job["rescued"], predictions, h.get("fpt"))
+
+    def _pinned(self, name, numel, dtype):
+        t = self._pin.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = self._torch.empty(max(int(numel), 1), dtype=dtype).pin_memory()
+            self._pin[name] = t
+        return t[:numel]
+
+    def run(self, signals, full_lengths, read_ids: Optional[Sequence] = None, return_df: bool = True,
+            want_fpt: bool = False) -> MinibatchResult:
+        """One minibatch.  signals: float32 [n, stride] NaN-padded rows (numpy; torch CPU tensor, pinned or not; or a CUDA
+        tensor); full_lengths: [n] full read lengths (file_proc.py:241-262)."""
+        with self._torch.cuda.device(self.device):
+            job = self._upload(0, signals, full_lengths, read_ids)
+            self._launch(job, want_fpt)
+            return self._finalize(job, return_df)
+
+    def stream(self, minibatches, return_df: bool = True, want_fpt: bool = False):
+        """Generator over an iterable of minibatches `(signals, full_lengths[, read_ids])`, results in order.
+        Two buffer slots: the upload of minibatch i+1 (copy stream) overlaps the kernels of minibatch i — the reference
+        overlaps the same way with a loader process feeding a queue (file_proc.py:333-377)."""
+        with self._torch.cuda.device(self.device):
+            it = iter(minibatches)
+
+            def up(slot, mb):
+                return self._upload(slot, mb[0], mb[1], mb[2] if len(mb) > 2 else None)
+
+            nxt = next(it, None)
+            job = up(0, nxt) if nxt is not None else None
+            if job is not None:
+                self._launch(job, want_fpt)
+            i = 0
+            while job is not None:
+                # minibatch i is in flight: upload and launch i+1 behind it (other slot), THEN collect i — the host-side
+                # work of collecting overlaps the kernels of i+1
+                nxt = next(it, None)
+                njob = up((i + 1) & 1, nxt) if nxt is not None else None
+                if njob is not None:
+                    self._launch(njob, want_fpt)
+                yield self._finalize(job, return_df)
+                job = njob
+                i += 1
 
     def close(self):
         self.validator.close()
         self.fingerprinter.close()
         self._buf = {}
+        self._pin = {}
 
 
 def detect_and_predict_on_preloaded_signals(preloaded_minibatch, model_predict, model_detect, config,

@@ -372,6 +372,11 @@ void wdx_validate_destroy(wdx_validate* v);
 int wdx_validate_run(wdx_validate* v, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
                      const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
                      void* stream);
+/* on != 0: stop at the first failing poly(A) candidate.  success and bounds are unchanged (the reference never sets
+ * `success` back to True after a failed candidate, combined.py:540-610); the fail code, check bits and mvs_* values are
+ * those of the FIRST failing candidate instead of the last one evaluated.  For callers that only need the verdict (the
+ * fingerprint stage); default off = reference-identical report. */
+int wdx_validate_set_verdict_only(wdx_validate* v, int on);
 int wdx_validate_enable_timing(wdx_validate* v, int on);
 int wdx_validate_last_kernel_ms(wdx_validate* v, double* ms, int* launches);
 

@@ -187,7 +187,7 @@ def _mvs_check(sig: np.ndarray, adapter_end: int, polya_end: int, cfg: ValidateC
 
 
 def validate_one(row: np.ndarray, full_signal_len: int, adapter_end: int, polya_topk, cfg: ValidateConfig,
-                 adapter_start: int = 0):
+                 adapter_start: int = 0, verdict_only: bool = False):
     """validate_boundaries(signal[:full_signal_len], Boundaries(adapter_start, adapter_end, topk[0], topk), spc,
     full_signal_len) as combined_detect_cnn calls it (combined.py:215-221), for one minibatch row.
     Returns dict(success, code, checks (bit i set = check i passed), adapter_start, adapter_end, polya_end,
@@ -260,6 +260,8 @@ def validate_one(row: np.ndarray, full_signal_len: int, adapter_end: int, polya_
                     if code == OK:
                         polya_best = pe
                         break
+                    if verdict_only:      # NOT the reference's behaviour: report the first failing candidate and stop
+                        break
         if code == OK and cfg.detect_med_shift:                     # :612-629
             shift = float(np.median(sig[a1:min(a1 + cfg.med_shift_window, full_signal_len)])
                           - np.median(sig[max(a1 - cfg.med_shift_window, 0):a1]))
@@ -276,7 +278,7 @@ def fail_reason(code: int, checks: int):
     return FAIL_REASON[code]
 
 
-def validate_batch(signals: np.ndarray, full_lens, preds: np.ndarray, cfg: ValidateConfig):
+def validate_batch(signals: np.ndarray, full_lens, preds: np.ndarray, cfg: ValidateConfig, verdict_only: bool = False):
     """Batch form: signals [n, stride] float32 (NaN padded), full_lens [n], preds [n, 1+k] (cnn_detect's output:
     adapter end, poly(A) end candidates).  Returns arrays success u8[n], code i32[n], checks i32[n],
     bounds i64[n,3] (adapter_start, adapter_end, polya_end), vals f64[n,N_VALS], n_open_pores i32[n]."""
@@ -288,7 +290,7 @@ def validate_batch(signals: np.ndarray, full_lens, preds: np.ndarray, cfg: Valid
     vals = np.full((n, N_VALS), np.nan)
     pores = np.zeros(n, np.int32)
     for i in range(n):
-        r = validate_one(signals[i], int(full_lens[i]), int(preds[i, 0]), preds[i, 1:], cfg)
+        r = validate_one(signals[i], int(full_lens[i]), int(preds[i, 0]), preds[i, 1:], cfg, verdict_only=verdict_only)
         success[i], code[i], checks[i] = r["success"], r["code"], r["checks"]
         bounds[i] = (r["adapter_start"], r["adapter_end"], r["polya_end"])
         vals[i] = r["vals"]

@@ -72,6 +72,8 @@ def main(n_base=256, reps=int(os.environ.get("VAL_REPS", "32")), stride=int(os.e
 
     if os.environ.get("VAL_ONLY") == "1":
         return
+    v.close()
+    v = combined.Validator(device=0, verdict_only=True)     # what MinibatchDemuxer uses: stop at the first failing candidate
     # chained pipeline on the same rows: CNN (guarded) -> validation -> fingerprint + DTW/SVC (guarded)
     model = cnn.load_cnn_model(os.path.join(GOLD, "models", "cnn_rna004_130bps_v0.2.4.npz"), device=0)
     core, cb = cnn.CoreConfig(), cnn.CNNBoundariesConfig(polya_cand_k=k)
@@ -122,12 +124,40 @@ def main(n_base=256, reps=int(os.environ.get("VAL_REPS", "32")), stride=int(os.e
     print(json.dumps(dict(stage="MinibatchDemuxer.run from pinned host rows (e2e)", reads=n, ms=round(best * 1e3, 2),
                           reads_per_s=round(n / best), h2d_GBps=round(h_sig.numel() * 4 / best / 1e9, 1),
                           validated=int(r.detect_success.sum()), fp_ok=int((r.fp_status == 0).sum()))), flush=True)
+    # raw pinned-host -> device copy rate of this box (the bound of the end-to-end numbers above and below)
+    d_tmp = torch.empty_like(h_sig, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rates = {}
+    for label, rows in (("whole", n), ("1000_rows", min(1000, n))):
+        bestc = 1e30
+        for it in range(4):
+            e0.record()
+            d_tmp[:rows].copy_(h_sig[:rows], non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            bestc = min(bestc, e0.elapsed_time(e1))
+        rates[label] = round(rows * stride * 4 / bestc / 1e6, 1)
+    print(json.dumps(dict(stage="pinned H2D copy rate (GB/s)", **rates)), flush=True)
+    del d_tmp
+    if os.environ.get("VAL_PHASES") == "1":     # host time spent in each phase of the pipelined stream
+        acc = {"_upload": 0.0, "_launch": 0.0, "_finalize": 0.0}
+        for name in acc:
+            orig = getattr(dmx, name)
+
+            def wrap(*a, _o=orig, _n=name, **k):
+                t0 = time.perf_counter()
+                r_ = _o(*a, **k)
+                acc[_n] += time.perf_counter() - t0
+                return r_
+            setattr(dmx, name, wrap)
     mb = 1000
     mbs = [(h_sig[a:a + mb], h_len[a:a + mb]) for a in range(0, n - mb + 1, mb)] * 4
     for it in range(2):
         t0 = time.perf_counter()
         got = sum(int(x.labels.size) for x in dmx.stream(mbs, return_df=False))
         dt = time.perf_counter() - t0
+    if os.environ.get("VAL_PHASES") == "1":
+        print(json.dumps({"host_ms_per_minibatch_in_phase (2 passes of the stream)": {k: round(v / (2 * len(mbs)) * 1e3, 3) for k, v in acc.items()}}), flush=True)
     t0 = time.perf_counter()
     got2 = sum(int(dmx.run(a, b, return_df=False).labels.size) for a, b in mbs)
     dt2 = time.perf_counter() - t0

@@ -379,3 +379,37 @@ def test_warp_finish_is_bit_identical_to_thread_finish(models, dev_models):
                 assert np.array_equal(pb[:4000], ps, equal_nan=True) and np.array_equal(cb[:4000], cs, equal_nan=True)
         finally:
             d.set_sv_splits(0)
+
+
+def test_concurrent_predict_from_four_threads(models):
+    """The live path classifies from 4 threads (live_balancing/session.py:165-167): calls on ONE model object are
+    serialised by the handle's mutex, calls on per-thread objects run concurrently; both give the single-thread result."""
+    import threading
+
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    m = models["WDX6_rna004_v1_0"]
+    X = synth_fingerprints(m.sv, 64 * 24, seed=13)
+    shared = DTW_SVM(m, device=0, mode="guarded")
+    want, want_p = shared.predict(X, nproc=1)
+    for per_thread in (False, True):
+        out, errs = {}, []
+
+        def work(t):
+            try:
+                mdl = DTW_SVM(m, device=0, mode="guarded") if per_thread else shared
+                for r in range(6):
+                    lo = (t * 6 + r) * 64
+                    y, p = mdl.predict(X[lo:lo + 64], nproc=1)
+                    out[(t, r)] = (lo, y, p)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        assert not errs, errs
+        assert len(out) == 24
+        for lo, y, p in out.values():
+            assert np.array_equal(y, want[lo:lo + 64])
+            assert np.abs(p - want_p[lo:lo + 64]).max() < 2e-6

@@ -97,6 +97,14 @@ def test_gpu_validate_matches_reference_and_oracle(gold, inputs):
     assert np.array_equal(vb.bounds, obounds) and np.array_equal(vb.n_open_pores, opores)
     assert np.array_equal(vb.vals, ovals, equal_nan=True)
     v.close()
+    # verdict-only mode (what the chained pipeline uses): same success and boundaries, report of the first failing candidate
+    v1 = combined.Validator(v.cfg, device=0, verdict_only=True)
+    vb1 = v1.validate(sig, lens, preds)
+    assert np.array_equal(vb1.success, vb.success) and np.array_equal(vb1.bounds, vb.bounds)
+    o1 = ov.validate_batch(sig, lens, preds, cfg, verdict_only=True)
+    assert np.array_equal(vb1.code, o1[1]) and np.array_equal(vb1.checks, o1[2]) and np.array_equal(vb1.vals, o1[4], equal_nan=True)
+    assert (vb1.code != vb.code).sum() + (vb1.checks != vb.checks).sum() > 0      # the fixture does exercise the difference
+    v1.close()
 
 
 @pytest.mark.gpu

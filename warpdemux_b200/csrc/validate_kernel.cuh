@@ -68,6 +68,8 @@ struct ValArgs {
     int64_t* bounds;           // [n][3] adapter_start, adapter_end, polya_end
     double* vals;              // [n][VAL_NVALS] or nullptr
     float* scratch;            // [gridDim.x][stride] moving-window statistics
+    int verdict_only;          // stop at the first failing poly(A) candidate: same success / boundaries (success is never
+                               // set back once a candidate failed), fail code and statistics of THAT candidate instead of the last
     unsigned long long* next;  // work counter (zeroed before the launch): reads are handed out dynamically, because a
                                // read whose first poly(A) candidate fails costs several times a read that validates
 };
@@ -544,6 +546,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                         pe_best = pe;
                         break;
                     }
+                    if (a.verdict_only) break;
                 }
             }
         }

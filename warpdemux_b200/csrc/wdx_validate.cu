@@ -18,6 +18,7 @@ struct wdx_validate {
     cudaStream_t stream = nullptr;
     DevBuf sig, len, preds, success, info, bounds, vals, scratch, counter;
     bool timing = false;
+    bool verdict_only = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
 };
@@ -113,6 +114,12 @@ void wdx_validate_destroy(wdx_validate* h) {
     delete h;
 }
 
+int wdx_validate_set_verdict_only(wdx_validate* h, int on) {
+    if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
+    h->verdict_only = on != 0;
+    return WDX_OK;
+}
+
 int wdx_validate_enable_timing(wdx_validate* h, int on) {
     if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
     h->timing = on != 0;
@@ -204,6 +211,7 @@ int wdx_validate_run(wdx_validate* h, const float* signals, int64_t n, int64_t s
     a.bounds = bnd_dev ? bounds : (int64_t*)h->bounds.p;
     a.vals = vals ? (val_dev ? vals : (double*)h->vals.p) : nullptr;
     a.scratch = (float*)h->scratch.p;
+    a.verdict_only = h->verdict_only ? 1 : 0;
     if ((rc = h->counter.reserve(16))) return rc;
     CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, 8, st));
     a.next = (unsigned long long*)h->counter.p;

@@ -177,9 +177,12 @@ def fail_reason(code: int, checks: int = 0) -> Optional[str]:
 class Validator:
     """Device handle of the validation step (`wdx_validate*`), created lazily in the process that uses it."""
 
-    def __init__(self, spc=None, device: Optional[int] = None):
+    def __init__(self, spc=None, device: Optional[int] = None, verdict_only: bool = False):
+        """verdict_only: stop at the first failing poly(A) candidate — same `success` and boundaries, fail reason and
+        mvs_* values of that candidate instead of the last one the reference goes on to evaluate."""
         self.cfg = ValidateConfig.from_spc(spc) if spc is not None else ValidateConfig()
         self.device = device
+        self.verdict_only = bool(verdict_only)
         self._h = None
 
     def _handle(self):
@@ -188,6 +191,7 @@ class Validator:
             c = _c_config(self.cfg)
             dev = default_device() if self.device is None else int(self.device)
             _lib.check(_lib.load().wdx_validate_create(C.byref(c), dev, C.byref(h)), "wdx_validate_create")
+            _lib.check(_lib.load().wdx_validate_set_verdict_only(h, int(self.verdict_only)), "wdx_validate_set_verdict_only")
             self._h = h
         return self._h
 
@@ -233,10 +237,11 @@ class Validator:
             pass
 
     def __getstate__(self):
-        return {"cfg": self.cfg, "device": self.device}
+        return {"cfg": self.cfg, "device": self.device, "verdict_only": self.verdict_only}
 
     def __setstate__(self, st):
         self.cfg, self.device, self._h = st["cfg"], st["device"], None
+        self.verdict_only = st.get("verdict_only", False)
 
 
 def validate_boundaries_batch(batch_of_signals, full_signal_lens, preds, spc, validator: Optional[Validator] = None) -> ValidationBatch:

@@ -77,7 +77,7 @@ class MinibatchDemuxer:
     def __init__(self, model_predict, model_detect: "_cnn.BoundariesCNN", spc=None, *, core=None, cnn_boundaries=None,
                  validate_config: Optional["_combined.ValidateConfig"] = None, fp_config: Optional[FingerprintConfig] = None,
                  device: Optional[int] = None, mode: Optional[str] = None, cnn_mode: Optional[str] = None,
-                 llr_fallback: Optional[Callable] = None, consensus_query=None):
+                 llr_fallback: Optional[Callable] = None, consensus_query=None, full_detect_report: bool = False):
         import torch  # device memory and streams only
 
         self._torch = torch
@@ -90,7 +90,16 @@ class MinibatchDemuxer:
             _combined.ValidateConfig.from_spc(spc) if spc is not None else _combined.ValidateConfig())
         fcfg = fp_config if fp_config is not None else (
             FingerprintConfig.from_spc(spc, consensus_query) if spc is not None else FingerprintConfig())
-        self.validator = _combined.Validator(vcfg, device=self.device)
+        # the fingerprint stage needs the verdict and the boundaries only; full_detect_report=True also reproduces the
+        # reference's fail_reason / mvs_* values of reads whose first poly(A) candidate fails (all candidates evaluated)
+        self.validator = _combined.Validator(vcfg, device=self.device, verdict_only=not full_detect_report)
+        if fcfg.max_slice_len <= 0:
+            # a fixed shared-memory capacity keeps the fingerprint call free of its host synchronisation (the read-back of
+            # the longest slice): the CNN's adapter end is < max_obs_adapter, the slice adds the padding on both sides
+            import dataclasses
+
+            cap = (int(self.core.max_obs_adapter) + 2 * int(fcfg.padding) + 63) // 64 * 64
+            fcfg = dataclasses.replace(fcfg, max_slice_len=min(cap, 16000))
         self.fingerprinter = Fingerprinter(fcfg, device=self.device)
         self.mode = mode or model_predict.mode
         self.cnn_mode = cnn_mode or model_detect.mode
@@ -253,29 +262,39 @@ class MinibatchDemuxer:
 
     def stream(self, minibatches, return_df: bool = True, want_fpt: bool = False):
         """Generator over an iterable of minibatches `(signals, full_lengths[, read_ids])`, results in order.
-        Two buffer slots: the upload of minibatch i+1 (copy stream) overlaps the kernels of minibatch i — the reference
-        overlaps the same way with a loader process feeding a queue (file_proc.py:333-377)."""
+        Three buffer slots: while the kernels of minibatch i run, minibatch i+1 is already launched behind them and
+        minibatch i+2 is uploading on the copy stream — the reference overlaps loading and computing with a loader
+        process feeding a queue (file_proc.py:333-377)."""
         with self._torch.cuda.device(self.device):
             it = iter(minibatches)
 
             def up(slot, mb):
                 return self._upload(slot, mb[0], mb[1], mb[2] if len(mb) > 2 else None)
 
-            nxt = next(it, None)
-            job = up(0, nxt) if nxt is not None else None
-            if job is not None:
-                self._launch(job, want_fpt)
-            i = 0
-            while job is not None:
-                # minibatch i is in flight: upload and launch i+1 behind it (other slot), THEN collect i — the host-side
-                # work of collecting overlaps the kernels of i+1
-                nxt = next(it, None)
-                njob = up((i + 1) & 1, nxt) if nxt is not None else None
-                if njob is not None:
-                    self._launch(njob, want_fpt)
-                yield self._finalize(job, return_df)
-                job = njob
+            SLOTS = 3
+            pending = []          # uploaded or launched jobs, oldest first
+            i = 0                 # minibatches uploaded so far
+
+            def upload_next():
+                nonlocal i
+                mb = next(it, None)
+                if mb is None:
+                    return False
+                pending.append([up(i % SLOTS, mb), False])
                 i += 1
+                return True
+
+            more = upload_next() and upload_next()      # two uploads in flight before the first launch
+            while pending:
+                for pj in pending[:2]:                  # keep two minibatches launched (the CNN call blocks the host
+                    if not pj[1]:                       # until its own kernels are done; the next upload is already queued)
+                        self._launch(pj[0], want_fpt)
+                        pj[1] = True
+                done = pending.pop(0)
+                res = self._finalize(done[0], return_df)    # frees the oldest slot ...
+                if more:
+                    more = upload_next()                    # ... for the upload of minibatch i+2
+                yield res
 
     def close(self):
         self.validator.close()

@@ -150,3 +150,67 @@ def test_gpu_validate_device_buffers_and_variants(gold, inputs):
     v.close()
     with pytest.raises(_lib.WdxError):
         combined.Validator(combined.ValidateConfig(mvs_detect_overwrite=True), device=0)._handle()
+
+
+@pytest.mark.gpu
+def test_gpu_validate_fuzz_against_oracle():
+    """Randomised rows, boundaries and configurations (incl. degenerate ones: constant signals, duplicates, rows
+    shorter than the windows, adapter ends beyond the signal, candidates at / before the adapter end, a single
+    candidate column): kernel == oracle on every output, both report modes."""
+    from oracle import wdx_oracle_validate as ov
+    from warpdemux_b200.detect import combined
+
+    rng = np.random.default_rng(123)
+    stride = 9000
+    n = 160
+    sig = np.full((n, stride), np.nan, dtype=np.float32)
+    lens = np.zeros(n, dtype=np.int64)
+    k = 4
+    preds = np.zeros((n, 1 + k), dtype=np.int64)
+    for i in range(n):
+        L = int(rng.choice([0, 1, 5, 150, 700, 1300, 2500, 6000, stride]))
+        kind = i % 8
+        if kind == 0:
+            x = np.full(L, 80.0)                                          # constant
+        elif kind == 1:
+            x = rng.integers(70, 90, L).astype(np.float64)                # heavy duplicates (crowded bins, ties)
+        elif kind == 2:
+            x = rng.normal(80, 6, L)
+            x[rng.random(L) < 0.02] = rng.choice([1e6, -1e6, 250.0])      # outliers stretch the histogram range
+        else:
+            a = int(L * rng.uniform(0.3, 0.7))
+            x = np.concatenate([rng.normal(80, rng.uniform(3, 12), a), rng.normal(115, rng.uniform(1, 7), L - a)])
+        sig[i, :L] = x.astype(np.float32)
+        lens[i] = L if rng.random() < 0.8 else L + int(rng.integers(0, 3000))
+        if lens[i] > L:
+            sig[i, L:min(stride, lens[i])] = 81.5                         # the row really holds full_len samples
+        a_end = int(rng.choice([0, 3, 600, 1000, 1200, 2000, 4000, 8000, 12000]))
+        preds[i, 0] = a_end
+        c = [a_end + int(rng.choice([-50, 0, 1, 2, 3, 30, 101, 102, 103, 400, 2000, 6000])) for _ in range(k)]
+        c = [max(0, v) for v in c]
+        if rng.random() < 0.3:
+            c[int(rng.integers(0, k))] = 0
+        preds[i, 1:] = c
+    cfgs = [ov.ValidateConfig(),
+            ov.ValidateConfig(min_obs_adapter=100, mean_window=40, max_obs_local_range=333, local_range=(0.0, 1e9),
+                              adapter_mad_range=(0.0, 1e9), pA_mean_window=5, pA_var_window=17, median_shift_window=64,
+                              pA_var_range=(-ov.INF, 1e9), median_shift_range=(-1e9, ov.INF), open_pore_min=90.0,
+                              open_pore_min_obs_diff=3, detect_med_shift=True, med_shift_window=77, med_shift_range=(-5.0, 60.0)),
+            ov.ValidateConfig(detect_open_pores=False, real_signal_check=False, min_obs_adapter=0, adapter_mad_range=(0.0, 1e9),
+                              pA_mean_adapter_med_scale_range=(0.5, ov.INF), median_shift_window=200)]
+    for ci, cfg in enumerate(cfgs):
+        pcfg = combined.ValidateConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)})
+        for verdict_only in (False, True):
+            v = combined.Validator(pcfg, device=0, verdict_only=verdict_only)
+            for cols in ((1 + k), 2):
+                pr = np.ascontiguousarray(preds[:, :cols])
+                vb = v.validate(sig, lens, pr)
+                o = ov.validate_batch(sig, lens, pr, cfg, verdict_only=verdict_only)
+                tag = (ci, verdict_only, cols)
+                assert np.array_equal(vb.success, o[0]), tag
+                assert np.array_equal(vb.code, o[1]) and np.array_equal(vb.checks, o[2]), tag
+                assert np.array_equal(vb.bounds, o[3]) and np.array_equal(vb.n_open_pores, o[5]), tag
+                bad = np.flatnonzero(~np.all((vb.vals == o[4]) | (np.isnan(vb.vals) & np.isnan(o[4])), axis=1))
+                assert bad.size == 0, (tag, bad[:5], vb.vals[bad[:2]], o[4][bad[:2]])
+            v.close()
+    assert len(set(o[1].tolist())) >= 3

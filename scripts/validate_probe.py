@@ -111,7 +111,7 @@ def main(n_base=256, reps=int(os.environ.get("VAL_REPS", "32")), stride=int(os.e
     from warpdemux_b200.file_proc import MinibatchDemuxer
 
     torch.cuda.set_stream(torch.cuda.default_stream())
-    dmx = MinibatchDemuxer(mdl, model, core=core, cnn_boundaries=cb, device=0)
+    dmx = MinibatchDemuxer(mdl, model, core=core, cnn_boundaries=cb, device=0, cnn_mode=os.environ.get("CNN_MODE") or None)
     h_sig = torch.from_numpy(np.tile(sig, (reps, 1))).pin_memory()
     h_len = np.tile(lens, reps)
     best = 1e30

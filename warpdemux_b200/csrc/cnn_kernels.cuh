@@ -127,9 +127,13 @@ __global__ void __launch_bounds__(FP_THREADS) cnn_prepare_kernel(const float* __
 
 // ---- EXACT mode: float32 CUDA-core convolutions ------------------------------------------------
 // conv1: x [n][T] -> h [n][T1][64], stride 3, padding 3, ReLU.   w0 [64][7], b0 [64]
+// n_dev (all EXACT kernels): optional read count on the device; reads at or beyond it are skipped, so a launch sized for
+// the worst case needs no host round trip to learn how many reads there really are (GUARDED re-run).
 __global__ void __launch_bounds__(256) cnn_conv1_f32_kernel(const float* __restrict__ x, const float* __restrict__ w0,
-                                                            const float* __restrict__ b0, CnnDims d, float* __restrict__ h) {
+                                                            const float* __restrict__ b0, CnnDims d, float* __restrict__ h,
+                                                            const int32_t* __restrict__ n_dev = nullptr) {
     __shared__ float ws[CNN_C * CNN_K], bs[CNN_C];
+    if (n_dev && (int64_t)blockIdx.y >= (int64_t)*n_dev) return;
     const int tid = threadIdx.x;
     for (int i = tid; i < CNN_C * CNN_K; i += 256) ws[i] = w0[i];
     if (tid < CNN_C) bs[tid] = b0[tid];
@@ -158,8 +162,11 @@ inline size_t cnn_conv64_smem_bytes() { return (size_t)(CNN_K * CNN_C * CNN_C + 
 
 __global__ void __launch_bounds__(256) cnn_conv64_f32_kernel(const float* __restrict__ hin, float* __restrict__ hout,
                                                              const float* __restrict__ wt, const float* __restrict__ bias,
-                                                             int T1, int tiles_per_read, int64_t n_tiles) {
+                                                             int T1, int tiles_per_read, int64_t n_tiles,
+                                                             const int32_t* __restrict__ n_dev = nullptr) {
     extern __shared__ __align__(16) float cv_sm[];
+    if (n_dev) n_tiles = min(n_tiles, (int64_t)*n_dev * tiles_per_read);
+    if ((int64_t)blockIdx.x >= n_tiles) return;
     float* w_s = cv_sm;                          // [7][64][64]
     float* in_s = cv_sm + CNN_K * CNN_C * CNN_C;  // [70][CV_LD]
     const int tid = threadIdx.x;
@@ -233,8 +240,10 @@ __device__ __forceinline__ void cnn_convT_point(HAT hat, int T1, int u, const fl
 }
 
 __global__ void __launch_bounds__(128) cnn_convT_f32_kernel(const float* __restrict__ h3, const float* __restrict__ wT,
-                                                            const float* __restrict__ b3, CnnDims d, float* __restrict__ scores) {
+                                                            const float* __restrict__ b3, CnnDims d, float* __restrict__ scores,
+                                                            const int32_t* __restrict__ n_dev = nullptr) {
     __shared__ float w_s[CNN_K * CNN_C * 2];
+    if (n_dev && (int64_t)blockIdx.y >= (int64_t)*n_dev) return;
     for (int i = threadIdx.x; i < CNN_K * CNN_C * 2; i += 128) w_s[i] = wT[i];
     __syncthreads();
     const int64_t read = blockIdx.y;
@@ -314,8 +323,9 @@ __global__ void __launch_bounds__(128) cnn_argmax_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) cnn_argmax_idx_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int64_t m,
                                                              CnnDims d, float* __restrict__ masked, int32_t* __restrict__ a_end,
                                                              int32_t* __restrict__ p_end, uint8_t* __restrict__ flags,
-                                                             float* __restrict__ scores_out) {
+                                                             float* __restrict__ scores_out, const int32_t* __restrict__ n_dev = nullptr) {
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (n_dev) m = min(m, (int64_t)*n_dev);
     if (q >= m) return;
     const int64_t read = idx[q];
     const float* c0 = scores + (q * 2 + 0) * d.To;
@@ -341,7 +351,9 @@ __global__ void cnn_guard_list_kernel(const float* __restrict__ margin, const ui
     }
 }
 
-__global__ void cnn_gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int T, float* __restrict__ out) {
+__global__ void cnn_gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int T, float* __restrict__ out,
+                                       const int32_t* __restrict__ n_dev = nullptr) {
+    if (n_dev && (int64_t)blockIdx.x >= (int64_t)*n_dev) return;
     const float* src = x + (int64_t)idx[blockIdx.x] * T;
     float* dst = out + (int64_t)blockIdx.x * T;
     for (int i = threadIdx.x; i < T; i += blockDim.x) dst[i] = src[i];

@@ -83,7 +83,14 @@ int make_dims(const wdx_cnn* c, int64_t stride, CnnDims* d) {
 }
 
 // x [cn][T] -> scores [cn][2][To], float32 CUDA-core path
-int forward_exact(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, float* scores, cudaStream_t st) {
+constexpr int64_t ASYNC_REDO_MAX_READS = 4096;
+bool async_redo_disabled() {
+    static const bool off = [] { const char* e = getenv("WDX_CNN_SYNC_REDO"); return e && e[0] == '1'; }();
+    return off;
+}
+
+int forward_exact(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, float* scores, cudaStream_t st,
+                  const int32_t* n_dev = nullptr) {
     int rc;
     if ((rc = c->hA.reserve((size_t)cn * d.T1 * CNN_C * 4))) return rc;
     if ((rc = c->hB.reserve((size_t)cn * d.T1 * CNN_C * 4))) return rc;
@@ -92,22 +99,22 @@ int forward_exact(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, floa
     Timer tm{c, st};
     if ((rc = tm.begin())) return rc;
     {
-        dim3 grid((unsigned)std::min(64, (d.T1 + 3) / 4), (unsigned)cn);
-        cnn_conv1_f32_kernel<<<grid, 256, 0, st>>>(x, (const float*)c->w0.p, (const float*)c->b0.p, d, hA);
+        dim3 grid((unsigned)std::min(n_dev ? 8 : 64, (d.T1 + 3) / 4), (unsigned)cn);   // few, mostly idle CTAs in the device-counted re-run
+        cnn_conv1_f32_kernel<<<grid, 256, 0, st>>>(x, (const float*)c->w0.p, (const float*)c->b0.p, d, hA, n_dev);
         CUDA_TRY(cudaGetLastError());
     }
     const int tiles_per_read = (d.T1 + CV_TT - 1) / CV_TT;
     const int64_t n_tiles = cn * tiles_per_read;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, c->sm_count);
     cnn_conv64_f32_kernel<<<grid, 256, cnn_conv64_smem_bytes(), st>>>(hA, hB, (const float*)c->wt1.p, (const float*)c->b1.p, d.T1,
-                                                                     tiles_per_read, n_tiles);
+                                                                     tiles_per_read, n_tiles, n_dev);
     CUDA_TRY(cudaGetLastError());
     cnn_conv64_f32_kernel<<<grid, 256, cnn_conv64_smem_bytes(), st>>>(hB, hA, (const float*)c->wt2.p, (const float*)c->b2.p, d.T1,
-                                                                     tiles_per_read, n_tiles);
+                                                                     tiles_per_read, n_tiles, n_dev);
     CUDA_TRY(cudaGetLastError());
     {
         dim3 g2((unsigned)((d.To + 127) / 128), (unsigned)cn);
-        cnn_convT_f32_kernel<<<g2, 128, 0, st>>>(hA, (const float*)c->wT.p, (const float*)c->b3.p, d, scores);
+        cnn_convT_f32_kernel<<<g2, 128, 0, st>>>(hA, (const float*)c->wT.p, (const float*)c->b3.p, d, scores, n_dev);
         CUDA_TRY(cudaGetLastError());
     }
     g_launches += 4;
@@ -382,8 +389,24 @@ int wdx_cnn_detect(wdx_cnn* c, const float* signals, int64_t n, int64_t stride, 
         CUDA_TRY(cudaGetLastError());
         g_launches++;
         int m = 0;
-        CUDA_TRY(cudaMemcpyAsync(&m, c->redo_cnt.p, 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        const bool counted_on_device = n <= ASYNC_REDO_MAX_READS && (!scores || scores_dev) && !async_redo_disabled();
+        if (counted_on_device) {
+            // minibatch-sized call: the re-run is launched for the worst case (every read listed) and the kernels skip
+            // what lies beyond the device-side count - no host synchronisation, the call stays asynchronous
+            const int32_t* cnt = (const int32_t*)c->redo_cnt.p;
+            if ((rc = c->xg.reserve((size_t)n * d.T * 4)) || (rc = c->sg.reserve((size_t)n * 2 * d.To * 4))) return rc;
+            cnn_gather_rows_kernel<<<(unsigned)n, 256, 0, st>>>((const float*)c->x.p, (const int32_t*)c->redo_idx.p, d.T, (float*)c->xg.p, cnt);
+            CUDA_TRY(cudaGetLastError());
+            if ((rc = forward_exact(c, (const float*)c->xg.p, n, d, (float*)c->sg.p, st, cnt))) return rc;
+            cnn_argmax_idx_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>((const float*)c->sg.p, (const int32_t*)c->redo_idx.p, n, d,
+                                                                          (float*)c->masked.p, (int32_t*)c->a_end.p, (int32_t*)c->p_end.p,
+                                                                          flags_d, scores_dev ? scores : nullptr, cnt);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 2;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(&m, c->redo_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
         for (int64_t g0 = 0; g0 < m; g0 += chunk) {
             const int64_t gn = std::min<int64_t>(chunk, m - g0);
             if ((rc = c->xg.reserve((size_t)gn * d.T * 4)) || (rc = c->sg.reserve((size_t)gn * 2 * d.To * 4))) return rc;

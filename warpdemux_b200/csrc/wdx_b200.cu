@@ -224,7 +224,7 @@ bool finish_warp_disabled() {
 int launch_finish(wdx_model* m, const FinishArgs& fa_in, int64_t grid_rows, cudaStream_t st) {
     FinishArgs fa = fa_in;
     if (fa.n_splits > 1) {  // fold the SV ranges first (parallel over pairs x reads), then finish as one range
-        dim3 grid((unsigned)((grid_rows + 255) / 256), (unsigned)m->n_pairs);
+        dim3 grid((unsigned)((grid_rows + 31) / 32), (unsigned)m->n_pairs);   // 32 reads x FOLD_SUB sub-sums per CTA
         svc_fold_splits_kernel<<<grid, 256, 0, st>>>(m->dev, const_cast<double*>(fa.part), fa.part_stride, fa.n_splits,
                                                     fa.sv_per_split, fa.n_idx, fa.n);
         CUDA_TRY(cudaGetLastError());

@@ -375,6 +375,23 @@ def raw_signal_chain(params_small, local):
                               "validate_reads_per_s": n / (res[1] * 1e-3),
                               "validate_roofline": {"bound": "hbm", "achieved": alg / (res[1] * 1e-3) / 1e9, "unit": "GB/s",
                                                     "note": "algorithmic bytes = 4 x valid samples per row, read once"}}
+    # CPU beside it (bounded sample, one core): the numpy restatement of validate_boundaries on the same rows and the
+    # boundaries the GPU CNN produced for them - the only stage of this chain whose CPU port is timed here (the
+    # fingerprint and DTW/SVC stages have their own cpu_baseline entries above)
+    try:
+        from oracle import wdx_oracle_validate as ov
+
+        m_cpu = 96
+        pr = d_preds[:m_cpu].cpu().numpy()
+        t0 = time.perf_counter()
+        o = ov.validate_batch(sig[:m_cpu], h_len[:m_cpu], pr, ov.ValidateConfig())
+        dt = time.perf_counter() - t0
+        gpu_ok = d_suc[:m_cpu].cpu().numpy()
+        out["validate_cpu_baseline"] = {"value": m_cpu / dt, "unit": "reads/s", "cores": 1, "kind": "port",
+                                        "sample": f"{m_cpu} of the same reads, oracle/wdx_oracle_validate.py (numpy), one process",
+                                        "gpu_verdict_mismatches_on_sample": int((o[0] != gpu_ok).sum())}
+    except Exception as e:  # noqa: BLE001
+        out["validate_cpu_baseline"] = {"error": repr(e)}
     dmx.close()
     model.close()
     return out

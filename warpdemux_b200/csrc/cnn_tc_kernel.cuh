@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const CnnDims d = a.d;
     const int T1 = d.T1;
+    const int m_tiles = (T1 + 127) >> 7;   // 128-row M tiles that hold hidden positions (3 of 5 at the CLI's preload size)
 
     // ---- one-time setup ------------------------------------------------------------------------------
     for (int i = tid; i < CNN_C * CNN_K; i += TC_THREADS) w0_s[i] = a.w0[i];
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     if (tc_elect_one()) {
                         const uint64_t bd0 = b_desc0 + (uint64_t)(s * (TC_W_TAP / 16));
 #pragma unroll 1
-                        for (int m = 0; m < TC_TILES; m++) {
+                        for (int m = 0; m < m_tiles; m++) {
                             const uint64_t ad0 = a_desc0 + (uint64_t)(m * 128 + tap);
                             const uint32_t dcol = tmem + m * CNN_C;
 #pragma unroll
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
             const float* bias = (layer == 0 ? b1_s : b2_s) + hc * 32;
             const float sc = a.inv_wscale;
 #pragma unroll 1
-            for (int m = 0; m < TC_TILES; m++) {
+            for (int m = 0; m < m_tiles; m++) {
                 uint32_t r[32];
                 tc_ld32(tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(m * CNN_C + hc * 32), r);
                 const int t = m * 128 + g * 32 + lane;

@@ -57,6 +57,15 @@ def test_distance_matrix_to_seam(models):
     # symmetric use (SV vs SV): zero diagonal, bit-wise symmetric
     D = distance_matrix_to(m.sv[:200], m.sv[:200], window=m.window, penalty=m.penalty)
     assert np.all(np.diag(D) == 0) and np.array_equal(D, D.T)
+    # the block-parallel variants of the reference (parallel_distances.py:24-45, 87-198) give the same numbers
+    from warpdemux_b200.parallel_distances import compute_block_distance, parallel_distance_matrix, parallel_distance_matrix_to
+
+    assert np.array_equal(parallel_distance_matrix_to(X, m.sv, block_size=50, n_jobs=3, window=m.window, penalty=m.penalty), got)
+    Z = np.vstack([X, m.sv])
+    sub = parallel_distance_matrix(Z, block_size=64, subset=((0, len(X)), (len(X), len(Z))), window=m.window, penalty=m.penalty)
+    assert np.array_equal(sub, got)
+    i, j, blk = compute_block_distance((np.arange(5, 25), np.arange(len(X), len(X) + 40)), Z, window=m.window, penalty=m.penalty)
+    assert np.array_equal(blk, got[5:25, :40]) and blk.dtype == np.float32
 
 
 @pytest.mark.parametrize("shape", [(12, 5, 0.1), (30, 0, 0.0), (25, 25, 0.3), (25, 14, 0.1), (1, 1, 0.1), (64, 20, 0.05)])

@@ -438,6 +438,9 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
 __device__ __forceinline__ bool lt_sqrt(double a, double b) {
     if (!(a < b)) return false;
     if (__dsub_rn(b, a) > __dmul_rn(b, 1.7763568394002505e-15 /* 2^-49 */)) return true;  // more than 8 ulp apart: the roots differ
+    // a finite, b = +inf (border cells: every anti-diagonal of the first Q steps has one): inf - a > inf * 2^-49 is false, and
+    // without this line the whole warp would take the two software square roots below for it; sqrt(a) < inf holds exactly
+    if (b == __longlong_as_double(0x7ff0000000000000LL)) return true;
     return __dsqrt_rn(a) < __dsqrt_rn(b);
 }
 
@@ -525,6 +528,99 @@ __device__ void consensus_match_warp(const double* __restrict__ query, int Q, co
     if (lane == 0) {
         result[0] = lastorg[bi];
         result[1] = bi;
+    }
+}
+
+// The same recurrence with ONE ROW PER LANE over NW warps (Q <= 32 * NW): the single-warp version walks
+// ceil(Q / 32) dependent rows per lane and step, and with one warp per CTA at work that dependency chain was 60 % of
+// the consensus kernel's time.  Lane g owns row g; inside a warp the hand-down is the same __shfl_up_sync, between
+// warps lane 31 leaves its value in a double-buffered shared slot and the NW warps meet at a named barrier once per
+// anti-diagonal step.  Cell arithmetic, walk-back origin and the final argmin are unchanged (bit-identical results).
+template <int NW>
+__device__ void consensus_match_rows(const double* __restrict__ query, int Q, const double* series, int Cn, double pen2,
+                                     int psi_q, int psi_s, double* lastrow, int* lastorg, int* result /*[2] start, end*/,
+                                     double* hand_v /*[2][NW]*/, int* hand_o /*[2][NW]*/) {
+    const int g = threadIdx.x;   // caller: threadIdx.x < 32 * NW
+    const int lane = g & 31, warp = g >> 5;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const bool own = g < Q;
+    const double qv = own ? query[g] : 0.0;
+    double left = (g + 1 <= psi_q) ? 0.0 : inf;   // P[g+1][0]
+    int lorg = -1;
+    double diag_in = (g <= psi_q) ? 0.0 : inf;    // P[g][0]
+    int diag_org = -1;
+    double pass_v = inf;
+    int pass_o = -1;
+    if (lane == 31) {
+        hand_v[warp] = inf;
+        hand_o[warp] = -1;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
+    const int steps = Cn + Q - 1;
+    for (int st = 0; st < steps; st++) {
+        double up_in = __shfl_up_sync(0xffffffffu, pass_v, 1);
+        int up_org = __shfl_up_sync(0xffffffffu, pass_o, 1);
+        if (lane == 0 && warp > 0) {
+            up_in = hand_v[(st & 1) * NW + warp - 1];
+            up_org = hand_o[(st & 1) * NW + warp - 1];
+        }
+        const int j = st - g;
+        if (g == 0) {
+            up_in = (j + 1 <= psi_s) ? 0.0 : inf;  // P[0][j+1]
+            up_org = -1;
+        }
+        if (j >= 0 && j < Cn && own) {
+            const double x = series[j];
+            const double up = up_in, dg = diag_in, lf = left;
+            const int uo = up_org, dgo = diag_org, lfo = lorg;
+            const double df = __dsub_rn(qv, x);
+            const double d = __dmul_rn(df, df);
+            double m = dg;
+            double t = __dadd_rn(up, pen2);
+            if (t < m) m = t;
+            t = __dadd_rn(lf, pen2);
+            if (t < m) m = t;
+            const double val = __dadd_rn(d, m);
+            // walk-back choice at this cell
+            double best = dg;
+            int po = dgo;
+            if (lt_sqrt(up, best)) { best = up; po = uo; }
+            if (lt_sqrt(lf, best)) { best = lf; po = lfo; }
+            const int org = (po < 0) ? j : po;
+            left = val;
+            lorg = org;
+            if (g == Q - 1) { lastrow[j] = val; lastorg[j] = org; }
+            pass_v = val;
+            pass_o = org;
+            diag_in = up_in;
+            diag_org = up_org;
+        }
+        if (lane == 31) {
+            hand_v[((st + 1) & 1) * NW + warp] = pass_v;
+            hand_o[((st + 1) & 1) * NW + warp] = pass_o;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
+    }
+    if (warp == 0) {
+        // matching = sqrt(last row) / Q; first minimum (np.argmin)
+        const double Qd = (double)Q;
+        double bv = inf;
+        int bi = 0x7fffffff;
+        for (int j = lane; j < Cn; j += 32) {
+            const double v = __ddiv_rn(__dsqrt_rn(lastrow[j]), Qd);
+            if (v < bv) { bv = v; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (bi == 0x7fffffff) bi = 0;  // every entry +inf/NaN: argmin returns 0
+        if (lane == 0) {
+            result[0] = lastorg[bi];
+            result[1] = bi;
+        }
     }
 }
 
@@ -784,9 +880,11 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         __syncthreads();
         if (tid < n_seg) dv[tid] = __ddiv_rn(__dsub_rn(ev[tid], ev_mean), ev_std);  // normalize(series, "mean")
         __syncthreads();
-        if (tid < 32)
-            consensus_match_warp<FP_MAX_QUERY / 32>(a.cons_query, c.cons_len, dv, n_seg, c.cons_pen2, c.cons_psi_q,
-                                                    c.cons_psi_s, lastrow, lastorg, match);
+        __shared__ double hand_v[2 * (FP_MAX_QUERY / 32)];
+        __shared__ int hand_o[2 * (FP_MAX_QUERY / 32)];
+        if (tid < FP_MAX_QUERY)   // FP_MAX_QUERY / 32 warps, one query row per lane
+            consensus_match_rows<FP_MAX_QUERY / 32>(a.cons_query, c.cons_len, dv, n_seg, c.cons_pen2, c.cons_psi_q, c.cons_psi_s,
+                                                    lastrow, lastorg, match, hand_v, hand_o);
         __syncthreads();
         const int q_start = match[0], q_end = match[1];
         const int sbs = cpts[q_end];  // sig_barcode_start = sum(adapter_dwell_times[:q_end]) (sig_proc.py:334)

@@ -423,7 +423,7 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
     __syncthreads();
 }
 
-// ---- consensus sub-sequence match (sig_proc.py:288-312) by ONE warp ---------------------------------
+// ---- consensus sub-sequence match (sig_proc.py:288-312) ----------------------------------------------
 // dtaidistance warping_paths(query, series, penalty, psi = (psi_q, 0, psi_s, 0)) without window:
 //     P[0][0..psi_s] = 0, P[0..psi_q][0] = 0, +inf elsewhere on the border,
 //     P[i+1][j+1] = (q[i] - x[j])^2 + min(P[i][j], P[i][j+1] + pen2, P[i+1][j] + pen2),
@@ -444,96 +444,9 @@ __device__ __forceinline__ bool lt_sqrt(double a, double b) {
     return __dsqrt_rn(a) < __dsqrt_rn(b);
 }
 
-template <int RMAX>
-__device__ void consensus_match_warp(const double* __restrict__ query, int Q, const double* series, int Cn, double pen2,
-                                     int psi_q, int psi_s, double* lastrow, int* lastorg, int* result /*[2] start, end*/) {
-    const int lane = threadIdx.x & 31;
-    const int R = (Q + 31) >> 5;            // rows per lane (<= RMAX)
-    const int n_lanes = (Q + R - 1) / R;    // lanes that own rows
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double qv[RMAX], left[RMAX];
-    int lorg[RMAX];
-#pragma unroll
-    for (int rr = 0; rr < RMAX; rr++) {
-        const int i = lane * R + rr;
-        qv[rr] = (rr < R && i < Q) ? query[i] : 0.0;
-        left[rr] = (i + 1 <= psi_q) ? 0.0 : inf;   // P[i+1][0]
-        lorg[rr] = -1;
-    }
-    const int i_first = lane * R;
-    double diag_in = (i_first <= psi_q) ? 0.0 : inf;  // P[i_first][0]
-    int diag_org = -1;
-    double pass_v = inf;
-    int pass_o = -1;
-    const int steps = Cn + n_lanes - 1;
-    for (int st = 0; st < steps; st++) {
-        double up_in = __shfl_up_sync(0xffffffffu, pass_v, 1);
-        int up_org = __shfl_up_sync(0xffffffffu, pass_o, 1);
-        const int j = st - lane;
-        if (lane == 0) {
-            up_in = (j + 1 <= psi_s) ? 0.0 : inf;  // P[0][j+1]
-            up_org = -1;
-        }
-        if (j >= 0 && j < Cn && lane < n_lanes) {
-            const double x = series[j];
-            double up = up_in, dg = diag_in;
-            int uo = up_org, dgo = diag_org;
-#pragma unroll
-            for (int rr = 0; rr < RMAX; rr++) {
-                const int i = i_first + rr;
-                if (rr < R && i < Q) {
-                    const double lf = left[rr];
-                    const int lfo = lorg[rr];
-                    const double df = __dsub_rn(qv[rr], x);
-                    const double d = __dmul_rn(df, df);
-                    double m = dg;
-                    double t = __dadd_rn(up, pen2);
-                    if (t < m) m = t;
-                    t = __dadd_rn(lf, pen2);
-                    if (t < m) m = t;
-                    const double val = __dadd_rn(d, m);
-                    // walk-back choice at this cell
-                    double best = dg;
-                    int po = dgo;
-                    if (lt_sqrt(up, best)) { best = up; po = uo; }
-                    if (lt_sqrt(lf, best)) { best = lf; po = lfo; }
-                    const int org = (po < 0) ? j : po;
-                    // hand down: this row's old value is the next row's diagonal, its new value the next row's up
-                    dg = lf; dgo = lfo;
-                    up = val; uo = org;
-                    left[rr] = val; lorg[rr] = org;
-                    if (i == Q - 1) { lastrow[j] = val; lastorg[j] = org; }
-                }
-            }
-            pass_v = up; pass_o = uo;
-            diag_in = up_in; diag_org = up_org;
-        }
-    }
-    __syncwarp();
-    // matching = sqrt(last row) / Q; first minimum (np.argmin)
-    const double Qd = (double)Q;
-    double bv = inf;
-    int bi = 0x7fffffff;
-    for (int j = lane; j < Cn; j += 32) {
-        const double v = __ddiv_rn(__dsqrt_rn(lastrow[j]), Qd);
-        if (v < bv) { bv = v; bi = j; }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (bi == 0x7fffffff) bi = 0;  // every entry +inf/NaN: argmin returns 0
-    if (lane == 0) {
-        result[0] = lastorg[bi];
-        result[1] = bi;
-    }
-}
-
-// The same recurrence with ONE ROW PER LANE over NW warps (Q <= 32 * NW): the single-warp version walks
-// ceil(Q / 32) dependent rows per lane and step, and with one warp per CTA at work that dependency chain was 60 % of
-// the consensus kernel's time.  Lane g owns row g; inside a warp the hand-down is the same __shfl_up_sync, between
+// ONE ROW PER LANE over NW warps (Q <= 32 * NW): a single warp would walk ceil(Q / 32) dependent rows per lane and
+// step, and with one warp per CTA at work that dependency chain was 60 % of the consensus kernel's time
+// (profiles/r01z_ncu_trna_lines.txt).  Lane g owns row g; inside a warp the hand-down is the same __shfl_up_sync, between
 // warps lane 31 leaves its value in a double-buffered shared slot and the NW warps meet at a named barrier once per
 // anti-diagonal step.  Cell arithmetic, walk-back origin and the final argmin are unchanged (bit-identical results).
 template <int NW>

@@ -312,7 +312,7 @@ int wdx_cnn_last_kernel_ms(wdx_cnn* c, double* ms, int* launches);
  * i.e. adapter median / MAD range check, open-pore detection (anomalies.py:16-35: adapter_start moves to the last
  * open-pore sample), real_range_check (real_range.py:34-63), mean_var_shift_polyA_check over the poly(A)
  * candidates (mvs.py:42-159) and the optional median-shift check.  mvs_detect_overwrite = true is not implemented
- * (WDX_ERR_UNSUPPORTED); the partition statistics of DetectResults (signal_partitions.py:80-96) are not computed.
+ * (WDX_ERR_UNSUPPORTED); the partition statistics of DetectResults come from wdx_validate_run_ex.
  * Reads that fail are the ones the reference hands to its LLR fallback (combined.py:222-290) - that stays with the
  * caller.  Ranges are [lo, hi] with -INFINITY / INFINITY for "None". */
 typedef struct {
@@ -372,6 +372,15 @@ void wdx_validate_destroy(wdx_validate* v);
 int wdx_validate_run(wdx_validate* v, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
                      const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
                      void* stream);
+/* As wdx_validate_run, plus the partition statistics of DetectResults (adapted/partition/signal_partitions.py:65-96,
+ * combined.py:631-636) when `parts` is not NULL:
+ *   parts [n, WDX_VAL_NPART] float64: for the adapter [adapter_start, adapter_end), poly(A) [adapter_end, polya_end) and
+ *   preloaded-RNA [polya_end, len) partitions: start, len, mean, std, med, mad (float32 numpy arithmetic, widened);
+ *   NaN where the reference leaves None (empty partition, or the NaN-signal error). */
+#define WDX_VAL_NPART 18
+int wdx_validate_run_ex(wdx_validate* v, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
+                        const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
+                        double* parts, void* stream);
 /* on != 0: stop at the first failing poly(A) candidate.  success and bounds are unchanged (the reference never sets
  * `success` back to True after a failed candidate, combined.py:540-610); the fail code, check bits and mvs_* values are
  * those of the FIRST failing candidate instead of the last one evaluated.  For callers that only need the verdict (the

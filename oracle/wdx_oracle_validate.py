@@ -13,8 +13,8 @@ its documented semantics are restated here the same way as in oracle/shim/bottle
 min_count = window, ddof = 0, float32 in -> float32 out, float64 accumulation) -> **parity unpinned**
 for those two statistics; everything else is pinned on the reference's own validate_boundaries
 (tests/golden/validate_rna004.npz, oracle/make_golden_validate.py).
-The partition statistics (adapted/partition/signal_partitions.py:80-96: mean/std/med/mad of the three
-partitions, reporting only) are not part of the restatement.
+The partition statistics of DetectResults (adapted/partition/signal_partitions.py:65-96: start, len, mean, std, med,
+mad of the adapter / poly(A) / preloaded-RNA partitions, reporting only) are restated in `partitions()`.
 """
 from __future__ import annotations
 
@@ -195,7 +195,7 @@ def validate_one(row: np.ndarray, full_signal_len: int, adapter_end: int, polya_
     sig = np.asarray(row)[:full_signal_len]
     vals = np.full(N_VALS, np.nan)
     out = dict(success=False, code=OK, checks=0, adapter_start=int(adapter_start), adapter_end=int(adapter_end),
-               polya_end=int(polya_topk[0]) if len(polya_topk) else 0, vals=vals, n_open_pores=0)
+               polya_end=int(polya_topk[0]) if len(polya_topk) else 0, vals=vals, n_open_pores=0, parts=np.full(N_PART, np.nan))
     if np.isnan(sig).any():                                         # combined.py:416-418 (raises; caller records it)
         out["code"] = HAS_NAN
         return out
@@ -269,7 +269,31 @@ def validate_one(row: np.ndarray, full_signal_len: int, adapter_end: int, polya_
             if not in_range(shift, *cfg.med_shift_range):
                 code = MED_SHIFT
     out.update(success=code == OK, code=code, adapter_start=a0, adapter_end=a1, polya_end=polya_best)
+    out["parts"] = partitions(row, full_signal_len, a0, a1, polya_best)
     return out
+
+
+N_PART = 18   # adapter, polya, rna_preloaded x (start, len, mean, std, med, mad); NaN = None
+
+
+def _partition_stats(sig: np.ndarray, start, end):
+    """calc_partition_stats (signal_partitions.py:80-96)."""
+    if end <= start:
+        return [float(start)] + [np.nan] * 5
+    seg = sig[start:end]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean, std, med = float(np.mean(seg)), float(np.std(seg)), float(np.median(seg))
+        mad = float(np.median(np.abs(seg - med)))
+    return [float(start), float(end - start), mean, std, med, mad]
+
+
+def partitions(row: np.ndarray, full_signal_len: int, adapter_start: int, adapter_end: int, polya_end: int) -> np.ndarray:
+    """calc_partitions_from_vals(signal[:full_signal_len], adapter_start, adapter_end, polya_end) as validate_boundaries
+    calls it (combined.py:631-636): float64 [N_PART]."""
+    sig = np.asarray(row)[:full_signal_len]
+    return np.array(_partition_stats(sig, adapter_start, adapter_end) + _partition_stats(sig, adapter_end, polya_end)
+                    + _partition_stats(sig, polya_end, sig.size))
 
 
 def fail_reason(code: int, checks: int):

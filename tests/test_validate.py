@@ -78,8 +78,13 @@ def test_gpu_validate_matches_reference_and_oracle(gold, inputs):
     sig = pack_rows(rows)
     cfg = _ocfg(gold)
     v = combined.Validator(combined.ValidateConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)}), device=0)
-    vb = v.validate(sig, lens, preds)
+    vb = v.validate(sig, lens, preds, partitions=True)
     n = len(rows)
+    # partition statistics of DetectResults against the reference's own values (start, len, mean, std, med, mad x 3)
+    has = np.array([not str(r).startswith("Validate boundaries failed") for r in gold["reasons"]])
+    pbad = np.flatnonzero(~np.all((vb.parts == gold["partitions"]) | (np.isnan(vb.parts) & np.isnan(gold["partitions"])), axis=1) & has)
+    assert pbad.size == 0, (pbad[:5], vb.parts[pbad[:2]], gold["partitions"][pbad[:2]])
+    assert np.isnan(vb.parts[~has]).all()
     bad = []
     for i in range(n):
         reason = vb.fail_reason(i) or ""
@@ -204,8 +209,12 @@ def test_gpu_validate_fuzz_against_oracle():
             v = combined.Validator(pcfg, device=0, verdict_only=verdict_only)
             for cols in ((1 + k), 2):
                 pr = np.ascontiguousarray(preds[:, :cols])
-                vb = v.validate(sig, lens, pr)
+                vb = v.validate(sig, lens, pr, partitions=True)
                 o = ov.validate_batch(sig, lens, pr, cfg, verdict_only=verdict_only)
+                oparts = np.array([ov.validate_one(sig[i], int(lens[i]), int(pr[i, 0]), pr[i, 1:], cfg, verdict_only=verdict_only)["parts"]
+                                   for i in range(n)])
+                pb = np.flatnonzero(~np.all((vb.parts == oparts) | (np.isnan(vb.parts) & np.isnan(oparts)), axis=1))
+                assert pb.size == 0, ("partitions", (ci, verdict_only, cols), pb[:5], vb.parts[pb[:2]], oparts[pb[:2]])
                 tag = (ci, verdict_only, cols)
                 assert np.array_equal(vb.success, o[0]), tag
                 assert np.array_equal(vb.code, o[1]) and np.array_equal(vb.checks, o[2]), tag

@@ -42,6 +42,7 @@ enum {
     VAL_MVS_NO_SIGNAL = 6, VAL_MVS_CHECKS = 7, VAL_MED_SHIFT = 8, VAL_HAS_NAN = 9
 };
 constexpr int VAL_NVALS = 12;
+constexpr int VAL_NPART = 18;  // adapter, polya, rna_preloaded x (start, len, mean, std, med, mad)
 
 struct ValCfg {
     int min_obs_adapter;
@@ -67,6 +68,7 @@ struct ValArgs {
     int32_t* info;             // [n][4] fail code, check bits (bit i = check i passed), open pores kept, 0
     int64_t* bounds;           // [n][3] adapter_start, adapter_end, polya_end
     double* vals;              // [n][VAL_NVALS] or nullptr
+    double* parts;             // [n][VAL_NPART] partition statistics (signal_partitions.py:65-96) or nullptr
     float* scratch;            // [gridDim.x][stride] moving-window statistics
     int verdict_only;          // stop at the first failing poly(A) candidate: same success / boundaries (success is never
                                // set back once a candidate failed), fail code and statistics of THAT candidate instead of the last
@@ -319,12 +321,133 @@ __device__ double val_local_range(int n, VAL val, ValSel& vs, FpScratch& s, floa
     return __dsub_rn(pct_lerp(o[0], o[1], g85), pct_lerp(o[2], o[3], g15));
 }
 
+// ---- numpy's pairwise sum of a long float32 array, in parallel ---------------------------------------------
+// np.add.reduce halves the array recursively (left half rounded down to a multiple of 8) until a block has <= 128
+// elements.  Thread 0 lists the leaf blocks in order (VAL_MAX_LEAVES covers any row that fits in shared memory), the
+// CTA sums the leaves with the 8-accumulator block routine, thread 0 adds the leaf sums up the same tree.
+constexpr int VAL_MAX_LEAVES = 1024;
+struct ValTree {
+    int off[VAL_MAX_LEAVES];
+    float sum[VAL_MAX_LEAVES];
+    short len[VAL_MAX_LEAVES];
+    int n_leaves;
+    float result;
+};
+
+__device__ void val_tree_build(int n, ValTree& t) {   // one thread
+    int lo_s[24], n_s[24], sp = 0, nl = 0;
+    lo_s[sp] = 0;
+    n_s[sp++] = n;
+    while (sp > 0) {
+        const int lo = lo_s[--sp], m = n_s[sp];
+        if (m <= 128) {
+            if (nl < VAL_MAX_LEAVES) {
+                t.off[nl] = lo;
+                t.len[nl] = (short)m;
+            }
+            nl++;
+        } else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            lo_s[sp] = lo + n2;      // right half (popped second)
+            n_s[sp++] = m - n2;
+            lo_s[sp] = lo;           // left half (popped first)
+            n_s[sp++] = n2;
+        }
+    }
+    t.n_leaves = nl;
+}
+
+__device__ float val_tree_combine(int n, const ValTree& t) {   // one thread; same walk, leaf sums consumed in order
+    struct Frame {
+        int n, state;
+        float left;
+    };
+    Frame st[24];
+    int sp = 0, next = 0;
+    st[sp++] = Frame{n, 0, 0.f};
+    float result = 0.f;
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        int n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.n <= 128) {
+            result = t.sum[next++];
+            sp--;
+        } else if (f.state == 0) {
+            f.state = 1;
+            st[sp++] = Frame{n2, 0, 0.f};
+        } else if (f.state == 1) {
+            f.left = result;
+            f.state = 2;
+            st[sp++] = Frame{f.n - n2, 0, 0.f};
+        } else {
+            result = __fadd_rn(f.left, result);
+            sp--;
+        }
+    }
+    return result;
+}
+
+// Sum of f(lo + i), i < n, in numpy's order; the tree for this n must have been built (val_tree_build + barrier).
+template <typename F>
+__device__ float block_np_sum_f32(int lo, int n, F f, ValTree& t) {
+    const int nl = t.n_leaves;
+    for (int k = threadIdx.x; k < nl; k += FP_THREADS) t.sum[k] = np_pairwise_leaf<float>(lo + t.off[k], (int)t.len[k], f);
+    __syncthreads();
+    if (threadIdx.x == 0) t.result = val_tree_combine(n, t);
+    __syncthreads();
+    const float r = t.result;
+    __syncthreads();
+    return r;
+}
+
+// calc_partition_stats (signal_partitions.py:80-96) of sig[start:end] for a row of L samples -> out[6] (thread 0 writes).
+__device__ void val_partition(const float* vsig, int L, int64_t start, int64_t end, double* out, ValTree& t, ValSel& vs, FpScratch& s) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const int tid = threadIdx.x;
+    if (end <= start) {
+        if (tid == 0) {
+            out[0] = (double)start;
+            for (int j = 1; j < 6; j++) out[j] = qnan;
+        }
+        return;
+    }
+    const int b = (int)max((int64_t)0, min(start, (int64_t)L)), e = (int)max((int64_t)0, min(end, (int64_t)L));
+    const int n = max(0, e - b);
+    float mean, sd, med, mad;
+    if (n == 0 || n > VAL_MAX_LEAVES * 64) {   // empty slice: numpy returns NaN for all four
+        mean = sd = med = mad = __int_as_float(0x7fc00000);
+    } else {
+        __syncthreads();
+        if (tid == 0) val_tree_build(n, t);
+        __syncthreads();
+        mean = __fdiv_rn(block_np_sum_f32(b, n, [&](int i) { return vsig[i]; }, t), (float)n);
+        const float ss = block_np_sum_f32(b, n, [&](int i) {
+            const float d = __fsub_rn(vsig[i], mean);
+            return __fmul_rn(d, d);
+        }, t);
+        sd = __fsqrt_rn(__fdiv_rn(ss, (float)n));
+        med = val_median(n, [&](int i) { return vsig[b + i]; }, vs, s);
+        mad = val_median(n, [&](int i) { return fabsf(__fsub_rn(vsig[b + i], med)); }, vs, s);
+    }
+    if (tid == 0) {
+        out[0] = (double)start;
+        out[1] = (double)(end - start);
+        out[2] = (double)mean;
+        out[3] = (double)sd;
+        out[4] = (double)med;
+        out[5] = (double)mad;
+    }
+}
+
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
 
 __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(const ValArgs a, const ValCfg c) {
     extern __shared__ float vsig[];
     __shared__ FpScratch s;
     __shared__ ValSel vs;
+    __shared__ ValTree tree;
     __shared__ int sh_i[6];
     __shared__ double sh_d[4];
     __shared__ double sh_v[VAL_NVALS];
@@ -561,6 +684,16 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             if (!val_in_range(ms, c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
         }
 
+        if (a.parts) {   // calc_partitions_from_vals(signal, adapter_start, adapter_end, polya_end_best), combined.py:631-636
+            double* po = a.parts + r * VAL_NPART;
+            if (code == VAL_HAS_NAN) {
+                if (tid < VAL_NPART) po[tid] = qnan;
+            } else {
+                val_partition(vsig, L, a0, a1, po, tree, vs, s);
+                val_partition(vsig, L, a1, pe_best, po + 6, tree, vs, s);
+                val_partition(vsig, L, pe_best, (int64_t)L, po + 12, tree, vs, s);
+            }
+        }
         if (tid == 0) {
             a.success[r] = code == VAL_OK;
             a.info[r * 4 + 0] = code;

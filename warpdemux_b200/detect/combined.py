@@ -25,6 +25,8 @@ from . import cnn as _cnn
 
 INF = float("inf")
 N_VALS = 12
+N_PART = 18
+PART_FIELDS = tuple(f"{p}_{f}" for p in ("adapter", "polya", "rna_preloaded") for f in ("start", "len", "mean", "std", "med", "mad"))
 FAIL_REASONS = {
     0: None,
     1: "No adapter detected (primary)",
@@ -130,7 +132,7 @@ def _c_config(cfg: ValidateConfig) -> _CValidateConfig:
 
 @dataclass
 class DetectResults:
-    """The fields of adapted/container_types.py:17-89 that validate_boundaries fills (partition statistics excepted)."""
+    """The fields of adapted/container_types.py:17-89 that validate_boundaries fills."""
     success: bool
     signal_len: Optional[int] = None
     preloaded: Optional[int] = None
@@ -152,6 +154,24 @@ class DetectResults:
     n_open_pores: int = 0
     fail_reason: Optional[str] = None
     needs_llr_fallback: bool = False
+    # partition statistics (adapted/partition/signal_partitions.py:17-35), filled when asked for
+    adapter_len: Optional[int] = None
+    adapter_mean: Optional[float] = None
+    adapter_std: Optional[float] = None
+    adapter_med: Optional[float] = None
+    adapter_mad: Optional[float] = None
+    polya_start: Optional[int] = None
+    polya_len: Optional[int] = None
+    polya_mean: Optional[float] = None
+    polya_std: Optional[float] = None
+    polya_med: Optional[float] = None
+    polya_mad: Optional[float] = None
+    rna_preloaded_start: Optional[int] = None
+    rna_preloaded_len: Optional[int] = None
+    rna_preloaded_mean: Optional[float] = None
+    rna_preloaded_std: Optional[float] = None
+    rna_preloaded_med: Optional[float] = None
+    rna_preloaded_mad: Optional[float] = None
 
 
 @dataclass
@@ -163,6 +183,7 @@ class ValidationBatch:
     bounds: np.ndarray         # int64 [n, 3] adapter_start, adapter_end, polya_end
     vals: np.ndarray           # float64 [n, N_VALS]
     kernel_ms: Optional[float] = field(default=None)
+    parts: Optional[np.ndarray] = field(default=None)   # float64 [n, N_PART] partition statistics (PART_FIELDS), NaN = None
 
     def fail_reason(self, i: int) -> Optional[str]:
         return fail_reason(int(self.code[i]), int(self.checks[i]))
@@ -195,12 +216,13 @@ class Validator:
             self._h = h
         return self._h
 
-    def run_raw(self, signals, n: int, stride: int, full_lens, preds, ld: int, success, info, bounds, vals=None, stream: int = 0):
+    def run_raw(self, signals, n: int, stride: int, full_lens, preds, ld: int, success, info, bounds, vals=None, stream: int = 0,
+                parts=None):
         """Pointer-level call (numpy arrays, torch tensors or addresses; host or device memory)."""
         p = _cnn._ptr
-        rc = _lib.load().wdx_validate_run(self._handle(), p(signals), int(n), int(stride), p(full_lens), p(preds), int(ld),
-                                          p(success), p(info), p(bounds), p(vals), stream or None)
-        _lib.check(rc, "wdx_validate_run")
+        rc = _lib.load().wdx_validate_run_ex(self._handle(), p(signals), int(n), int(stride), p(full_lens), p(preds), int(ld),
+                                             p(success), p(info), p(bounds), p(vals), p(parts), stream or None)
+        _lib.check(rc, "wdx_validate_run_ex")
 
     def enable_timing(self, on: bool = True):
         _lib.check(_lib.load().wdx_validate_enable_timing(self._handle(), int(on)), "wdx_validate_enable_timing")
@@ -210,7 +232,7 @@ class Validator:
         _lib.check(_lib.load().wdx_validate_last_kernel_ms(self._handle(), C.byref(ms), C.byref(k)), "wdx_validate_last_kernel_ms")
         return ms.value
 
-    def validate(self, batch_of_signals, full_signal_lens, preds) -> ValidationBatch:
+    def validate(self, batch_of_signals, full_signal_lens, preds, partitions: bool = False) -> ValidationBatch:
         sig = _cnn._as_batch(batch_of_signals)
         n, stride = sig.shape
         lens = np.ascontiguousarray(np.minimum(np.asarray(full_signal_lens, dtype=np.int64), np.iinfo(np.int32).max), dtype=np.int32)
@@ -221,9 +243,10 @@ class Validator:
         info = np.zeros((n, 4), np.int32)
         bounds = np.zeros((n, 3), np.int64)
         vals = np.full((n, N_VALS), np.nan)
+        parts = np.full((n, N_PART), np.nan) if partitions else None
         if n:
-            self.run_raw(sig, n, stride, lens, pr, pr.shape[1], success, info, bounds, vals)
-        return ValidationBatch(success, info[:, 0].copy(), info[:, 1].copy(), info[:, 2].copy(), bounds, vals)
+            self.run_raw(sig, n, stride, lens, pr, pr.shape[1], success, info, bounds, vals, parts=parts)
+        return ValidationBatch(success, info[:, 0].copy(), info[:, 1].copy(), info[:, 2].copy(), bounds, vals, parts=parts)
 
     def close(self):
         if self._h is not None:
@@ -244,10 +267,11 @@ class Validator:
         self.verdict_only = st.get("verdict_only", False)
 
 
-def validate_boundaries_batch(batch_of_signals, full_signal_lens, preds, spc, validator: Optional[Validator] = None) -> ValidationBatch:
+def validate_boundaries_batch(batch_of_signals, full_signal_lens, preds, spc, validator: Optional[Validator] = None,
+                              partitions: bool = False) -> ValidationBatch:
     v = validator or Validator(spc)
     try:
-        return v.validate(batch_of_signals, full_signal_lens, preds)
+        return v.validate(batch_of_signals, full_signal_lens, preds, partitions=partitions)
     finally:
         if validator is None:
             v.close()
@@ -275,6 +299,12 @@ def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, 
             real_adapter_mean_start=_opt(v[2]), real_adapter_mean_end=_opt(v[3]), real_adapter_local_range=_opt(v[4]),
             n_open_pores=int(vb.n_open_pores[i]), fail_reason=vb.fail_reason(i), needs_llr_fallback=not bool(vb.success[i]),
         )
+        if vb.parts is not None:
+            for name, x in zip(PART_FIELDS, vb.parts[i]):
+                if name == "adapter_start":
+                    continue   # already set from the boundaries
+                val = None if x != x else (int(x) if name.endswith(("_start", "_len")) else float(x))
+                setattr(d, name, val)
         setattr(d, f"{primary_method}_adapter_end", int(preds[i, 0]))
         setattr(d, f"{primary_method}_polya_end", int(preds[i, 1]) if preds.shape[1] > 1 else 0)
         out.append(d)
@@ -282,10 +312,10 @@ def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, 
 
 
 def combined_detect_cnn(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, model: "_cnn.BoundariesCNN", spc,
-                        validator: Optional[Validator] = None, mode: Optional[str] = None) -> List[DetectResults]:
+                        validator: Optional[Validator] = None, mode: Optional[str] = None, partitions: bool = True) -> List[DetectResults]:
     """CNN boundaries + validation for a minibatch, both on the GPU (combined.py:198-221).  Reads with
     `needs_llr_fallback` are the ones the reference retries with its CPU LLR detector (combined.py:222-290)."""
     sig = _cnn._as_batch(batch_of_signals)
     preds = _cnn.cnn_detect(sig, model, spc.cnn_boundaries, spc.core, mode=mode)
-    vb = validate_boundaries_batch(sig, full_signal_lens, preds, spc, validator=validator)
+    vb = validate_boundaries_batch(sig, full_signal_lens, preds, spc, validator=validator, partitions=partitions)
     return to_detect_results(vb, preds, full_signal_lens, sig.shape[1], str(getattr(spc, "primary_method", "cnn")))

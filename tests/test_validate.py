@@ -223,3 +223,32 @@ def test_gpu_validate_fuzz_against_oracle():
                 assert bad.size == 0, (tag, bad[:5], vb.vals[bad[:2]], o[4][bad[:2]])
             v.close()
     assert len(set(o[1].tolist())) >= 3
+
+
+def test_detect_results_mirror_has_the_reference_fields():
+    """DetectResults of the mirror lists the reference's fields in the reference's order (container_types.py:14-77), so
+    to_dict() yields the columns of its detected_boundaries table."""
+    from warpdemux_b200.detect import combined
+
+    ref = ["success", "signal_len", "preloaded", "adapter_start", "adapter_end", "adapter_len", "adapter_mean", "adapter_std",
+           "adapter_med", "adapter_mad", "polya_start", "polya_end", "polya_len", "polya_mean", "polya_std", "polya_med", "polya_mad",
+           "polya_candidates", "rna_preloaded_start", "rna_preloaded_len", "rna_preloaded_mean", "rna_preloaded_std",
+           "rna_preloaded_med", "rna_preloaded_mad", "start_peak_idx", "start_peak_pa", "start_peak_next_max_idx",
+           "start_peak_next_max_pa", "start_peak_open_pore_idx", "adapter_rna_median_shift", "llr_adapter_end", "llr_polya_end",
+           "cnn_adapter_end", "cnn_polya_end", "start_peak_adapter_end", "start_peak_polya_end", "llr_trace", "mvs_adapter_end",
+           "mvs_detect_mean_at_loc", "mvs_detect_var_at_loc", "mvs_detect_polya_med", "mvs_detect_polya_local_range",
+           "mvs_detect_med_shift", "real_adapter_mean_start", "real_adapter_mean_end", "real_adapter_local_range", "open_pores",
+           "fail_reason"]
+    assert list(combined.DetectResults(success=True).to_dict().keys()) == ref
+    # to_detect_results fills them from a batch (host-only logic)
+    n = 2
+    vb = combined.ValidationBatch(success=np.array([1, 0], np.uint8), code=np.array([0, 7], np.int32), checks=np.array([0, 0b11100], np.int32),
+                                  n_open_pores=np.array([1, 0], np.int32), bounds=np.array([[644, 4247, 5672], [0, 3000, 3500]]),
+                                  vals=np.full((n, combined.N_VALS), np.nan), parts=np.arange(36, dtype=np.float64).reshape(2, 18))
+    vb.parts[1, 1:6] = np.nan
+    preds = np.array([[4247, 5672, 0], [3000, 3500, 3600]])
+    ds = combined.to_detect_results(vb, preds, [20000, 9000], 11500)
+    assert ds[0].success and ds[0].adapter_start == 644 and ds[0].cnn_adapter_end == 4247 and ds[0].preloaded == 11500
+    assert ds[0].adapter_len == 1 and ds[0].polya_start == 6 and ds[0].rna_preloaded_mad == 17.0 and ds[0].open_pores.tolist() == [644]
+    assert not ds[1].success and ds[1].fail_reason == "MVS polya check failed: mean var" and ds[1].needs_llr_fallback
+    assert ds[1].adapter_len is None and ds[1].adapter_mean is None and ds[1].preloaded == 9000 and ds[1].open_pores is None

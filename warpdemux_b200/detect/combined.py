@@ -132,46 +132,85 @@ def _c_config(cfg: ValidateConfig) -> _CValidateConfig:
 
 @dataclass
 class DetectResults:
-    """The fields of adapted/container_types.py:17-89 that validate_boundaries fills."""
+    """adapted/container_types.py:14-77: the reference's fields in the reference's order (so `to_dict()` yields the
+    columns of its detected_boundaries table), then this package's extras.  Not reproduced: `open_pores` holds only the
+    position adapter_start moved to (the reference lists every kept open-pore sample), `llr_trace` / start-peak fields
+    belong to detectors that are not on the GPU path."""
     success: bool
+
     signal_len: Optional[int] = None
     preloaded: Optional[int] = None
+
     adapter_start: Optional[int] = None
     adapter_end: Optional[int] = None
-    polya_end: Optional[int] = None
-    polya_candidates: Optional[np.ndarray] = None
-    cnn_adapter_end: Optional[int] = None
-    cnn_polya_end: Optional[int] = None
-    mvs_detect_mean_at_loc: Optional[float] = None
-    mvs_detect_var_at_loc: Optional[float] = None
-    mvs_detect_polya_med: Optional[float] = None
-    mvs_detect_polya_local_range: Optional[float] = None
-    mvs_detect_med_shift: Optional[float] = None
-    adapter_rna_median_shift: Optional[float] = None
-    real_adapter_mean_start: Optional[float] = None
-    real_adapter_mean_end: Optional[float] = None
-    real_adapter_local_range: Optional[float] = None
-    n_open_pores: int = 0
-    fail_reason: Optional[str] = None
-    needs_llr_fallback: bool = False
-    # partition statistics (adapted/partition/signal_partitions.py:17-35), filled when asked for
     adapter_len: Optional[int] = None
     adapter_mean: Optional[float] = None
     adapter_std: Optional[float] = None
     adapter_med: Optional[float] = None
     adapter_mad: Optional[float] = None
+
     polya_start: Optional[int] = None
+    polya_end: Optional[int] = None
     polya_len: Optional[int] = None
     polya_mean: Optional[float] = None
     polya_std: Optional[float] = None
     polya_med: Optional[float] = None
     polya_mad: Optional[float] = None
+    polya_candidates: Optional[np.ndarray] = None
+
     rna_preloaded_start: Optional[int] = None
     rna_preloaded_len: Optional[int] = None
     rna_preloaded_mean: Optional[float] = None
     rna_preloaded_std: Optional[float] = None
     rna_preloaded_med: Optional[float] = None
     rna_preloaded_mad: Optional[float] = None
+
+    start_peak_idx: Optional[int] = None
+    start_peak_pa: Optional[float] = None
+    start_peak_next_max_idx: Optional[int] = None
+    start_peak_next_max_pa: Optional[float] = None
+    start_peak_open_pore_idx: Optional[int] = None
+
+    adapter_rna_median_shift: Optional[float] = None
+
+    llr_adapter_end: Optional[int] = None
+    llr_polya_end: Optional[int] = None
+
+    cnn_adapter_end: Optional[int] = None
+    cnn_polya_end: Optional[int] = None
+
+    start_peak_adapter_end: Optional[int] = None
+    start_peak_polya_end: Optional[int] = None
+
+    llr_trace: Optional[np.ndarray] = None
+
+    mvs_adapter_end: Optional[int] = None
+    mvs_detect_mean_at_loc: Optional[float] = None
+    mvs_detect_var_at_loc: Optional[float] = None
+    mvs_detect_polya_med: Optional[float] = None
+    mvs_detect_polya_local_range: Optional[float] = None
+    mvs_detect_med_shift: Optional[float] = None
+
+    real_adapter_mean_start: Optional[float] = None
+    real_adapter_mean_end: Optional[float] = None
+    real_adapter_local_range: Optional[float] = None
+
+    open_pores: Optional[np.ndarray] = None
+
+    fail_reason: Optional[str] = None
+
+    # extras of this package
+    n_open_pores: int = 0
+    needs_llr_fallback: bool = False
+
+    def to_dict(self):
+        d = dict(self.__dict__)
+        d.pop("n_open_pores", None)
+        d.pop("needs_llr_fallback", None)
+        return d
+
+    def update(self, d: dict):
+        self.__dict__.update(d)
 
 
 @dataclass
@@ -298,6 +337,7 @@ def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, 
             mvs_detect_polya_local_range=_opt(v[8]), mvs_detect_med_shift=_opt(v[9]), adapter_rna_median_shift=_opt(v[10]),
             real_adapter_mean_start=_opt(v[2]), real_adapter_mean_end=_opt(v[3]), real_adapter_local_range=_opt(v[4]),
             n_open_pores=int(vb.n_open_pores[i]), fail_reason=vb.fail_reason(i), needs_llr_fallback=not bool(vb.success[i]),
+            open_pores=np.array([int(vb.bounds[i, 0])]) if vb.n_open_pores[i] > 0 else None,
         )
         if vb.parts is not None:
             for name, x in zip(PART_FIELDS, vb.parts[i]):

@@ -248,3 +248,40 @@ def test_gpu_minibatch_step_matches_reference_worker(golden_real, models):
     dmx.close()
     dmx2.close()
     model_detect.close()
+
+
+@pytest.mark.gpu
+def test_gpu_minibatch_step_on_second_device(golden_real, models):
+    """One process per GPU in production, but nothing in the chain may assume device 0: the same minibatch on cuda:1
+    (when the box has one) gives the results of cuda:0."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from conftest import GOLD
+    from warpdemux_b200.detect import cnn
+    from warpdemux_b200.file_proc import MinibatchDemuxer
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import FingerprintConfig
+    from wdx_testutil import cnn_golden_signals
+
+    g = golden_real
+    with np.load(os.path.join(GOLD, "cnn_detect_rna004.npz")) as z:
+        gc = {k: z[k] for k in z.files}
+    with np.load(os.path.join(GOLD, "validate_rna004.npz")) as z:
+        full_lens = z["full_lens"][: int(z["n_real"])]
+    sig = np.ascontiguousarray(cnn_golden_signals(gc)[:, : int(g["preload_size"])])
+    res = []
+    for dev in (0, 1):
+        md = cnn.load_cnn_model(os.path.join(GOLD, "models", "cnn_rna004_130bps_v0.2.4.npz"), device=dev)
+        mp = DTW_SVM(models["WDX4_rna004_v1_0"], device=dev, mode="guarded")
+        dmx = MinibatchDemuxer(mp, md, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=5),
+                               fp_config=FingerprintConfig(**_cfg(g)), device=dev)
+        res.append(dmx.run(sig, full_lens, want_fpt=True))
+        res.append(list(dmx.stream([(sig[:30], full_lens[:30]), (sig[30:], full_lens[30:])], return_df=False)))
+        dmx.close()
+        md.close()
+    a, sa, b, sb = res
+    assert np.array_equal(a.labels, b.labels) and np.array_equal(a.bounds, b.bounds) and np.array_equal(a.fpt, b.fpt, equal_nan=True)
+    assert np.array_equal(np.concatenate([x.labels for x in sb]), b.labels)
+    assert np.array_equal(np.concatenate([x.labels for x in sa]), a.labels)

@@ -74,9 +74,35 @@ template <typename KEY>
 __device__ float block_nanmedian_f32(int T, int n_valid, KEY key, FpScratch& s) {
     if (n_valid <= 0) return __uint_as_float(0x7fc00000u);
     const uint32_t k_lo = (uint32_t)((n_valid - 1) / 2);
-    const float v_lo = f32_unkey(block_select_u32(T, k_lo, key, s));
+    const uint32_t key_lo = block_select_u32(T, k_lo, key, s);
+    const float v_lo = f32_unkey(key_lo);
     if (n_valid & 1) return v_lo;
-    const float v_hi = f32_unkey(block_select_u32(T, k_lo + 1, key, s));
+    // the next order statistic without a second radix selection: v_lo again if enough copies, else the smallest key
+    // above it (rank k_lo + 1 < n_valid, so that key belongs to a valid sample, never to a NaN)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.hist[0] = 0;            // count(key <= key_lo)
+        s.hist[1] = 0xffffffffu;  // min key > key_lo
+    }
+    __syncthreads();
+    uint32_t cnt = 0, mn = 0xffffffffu;
+    for (int i = threadIdx.x; i < T; i += FP_THREADS) {
+        const uint32_t kv = key(i);
+        if (kv <= key_lo) cnt++;
+        else mn = min(mn, kv);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s.hist[0], cnt);
+        atomicMin(&s.hist[1], mn);
+    }
+    __syncthreads();
+    const float v_hi = (s.hist[0] >= k_lo + 2) ? v_lo : f32_unkey(s.hist[1]);
+    __syncthreads();
     return __fdiv_rn(__fadd_rn(v_lo, v_hi), 2.0f);  // np.mean of the two middle float32 values
 }
 

@@ -40,26 +40,33 @@ constexpr int TC_W_HALF = CNN_C * CNN_C * 2;                 // 8 192 B: one tap
 constexpr int TC_W_TAP = 2 * TC_W_HALF;                      // 16 384 B
 constexpr int TC_STAGES = 3;
 constexpr int TC_XS = 3 * TC_MAX_T1 + 16;                    // padded input row (floats)
-constexpr int TC_TMEM_COLS = 512;                            // 5 tiles x 64 float32 columns -> next power of two
+constexpr int TC_TMEM_COLS = 512;                            // 5 tiles x (64 + 16) float32 columns -> next power of two
+constexpr int TC_CT_N = 16;                                  // ConvTranspose as an MMA: 3 residues x 2 channels = 6 columns, N >= 16 at M = 128
+constexpr int TC_CT_BLOCK = CNN_C * TC_CT_N * 2;             // 2 048 B: one row shift, one split of its operand B (K = 64, N = 16)
+constexpr int TC_CT_BYTES = 3 * 2 * TC_CT_BLOCK;             // 12 288 B: shifts j = 0..2 x (hi, lo); travels as one weight-ring item
+constexpr int TC_CT_COL0 = TC_TILES * CNN_C;                 // first TMEM column of the ConvTranspose accumulators (16 per tile)
 
 constexpr int TC_OFF_W = TC_A_BYTES;
 constexpr int TC_OFF_XS = TC_OFF_W + TC_STAGES * TC_W_TAP;
 constexpr int TC_OFF_SMALL = TC_OFF_XS + TC_XS * 4;
-// small block: w0 [64*7], b0 [64], b1 [64], b2 [64], wT [7*64*2], b3 [2 (+2 pad)], barriers 8 x u64, tmem ptr, flag
-constexpr int TC_SMALL_FLOATS = CNN_C * CNN_K + 3 * CNN_C + CNN_K * CNN_C * 2 + 4;
+// small block: w0 [64*7], b0 [64], b1 [64], b2 [64], b3 [2 (+2 pad)], barriers 8 x u64, tmem ptr, flag
+constexpr int TC_SMALL_FLOATS = CNN_C * CNN_K + 3 * CNN_C + 4;
 constexpr int TC_OFF_BARS = TC_OFF_SMALL + TC_SMALL_FLOATS * 4;
 constexpr size_t TC_SMEM_BYTES = TC_OFF_BARS + 8 * 8 + 16;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
-static_assert((size_t)TC_MAX_T1 * CNN_C * 4 <= TC_A_BYTES, "h3 must fit in the activation buffer it aliases");
+static_assert(TC_CT_BYTES <= TC_W_TAP, "the ConvTranspose operand must fit in one ring stage");
+static_assert(TC_CT_COL0 + TC_TILES * TC_CT_N <= TC_TMEM_COLS, "TMEM columns");
 static_assert(TC_OFF_BARS % 8 == 0 && TC_OFF_W % 128 == 0, "alignment");
 
 struct TcArgs {
     const float* x;      // [n][T] prepared input
     int64_t n;
     CnnDims d;
-    const float *w0, *b0, *b1, *b2, *wT, *b3;
+    const float *w0, *b0, *b1, *b2, *b3;
     const __half* wtc;   // [2 layers][7 taps][hi, lo][tc_b_offset(co, ci)] fp16, scaled by 1 / inv_wscale
     float inv_wscale;
+    const __half* wct;   // ConvTranspose operand B: [3 shifts][hi, lo][tc_ct_offset(n, ci)] fp16, scaled by 1 / inv_ctscale
+    float inv_ctscale;
     float* scores;       // [n][2][To]
     uint8_t* flags;      // [n]
 };
@@ -67,6 +74,9 @@ struct TcArgs {
 // element offset of W[co][ci] inside one 64x64 operand-B block (K-major, no swizzle: 8x8 core matrices,
 // 16-byte rows, 128 B between 8-row groups, 1024 B between k-chunks)
 __host__ __device__ inline size_t tc_b_offset(int co, int ci) { return (size_t)(ci / 8) * (CNN_C * 8) + (size_t)co * 8 + (ci % 8); }
+
+// element offset of column n (= 2 * residue + channel) and input channel ci inside one K = 64, N = 16 ConvTranspose block
+__host__ __device__ inline size_t tc_ct_offset(int n, int ci) { return (size_t)(ci / 8) * (TC_CT_N * 8) + (size_t)n * 8 + (ci % 8); }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,6 +130,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
 // instruction descriptor (InstrDescriptor): c_format F32 (1) at [4,6), a/b format F16 (0), K-major both,
 // N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(CNN_C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t TC_IDESC_CT = (1u << 4) | ((uint32_t)(TC_CT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // one lane of a converged warp (the compiler then keeps the descriptors in uniform registers)
 __device__ __forceinline__ bool tc_elect_one() {
@@ -142,6 +153,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
@@ -171,20 +190,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     float* b0_s = w0_s + CNN_C * CNN_K;
     float* b1_s = b0_s + CNN_C;
     float* b2_s = b1_s + CNN_C;
-    float* wT_s = b2_s + CNN_C;                                   // [7][64][2]
-    float* b3_s = wT_s + CNN_K * CNN_C * 2;
+    float* b3_s = b2_s + CNN_C;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_sm + TC_OFF_BARS);
     uint64_t* full = bars;             // [3] weights of a tap have landed
     uint64_t* empty = bars + 3;        // [3] the MMAs that read the stage have completed
     uint64_t* layer_done = bars + 6;   // all MMAs of a layer have completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     uint32_t* range_flag = tmem_slot + 1;
-    float* h3 = reinterpret_cast<float*>(A);                      // [T1][64] float32, channel index XOR (t & 31); aliases A after the last MMA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const CnnDims d = a.d;
     const int T1 = d.T1;
     const int m_tiles = (T1 + 127) >> 7;   // 128-row M tiles that hold hidden positions (3 of 5 at the CLI's preload size)
+    const int q_tiles = (T1 + 128) >> 7;   // tiles of the ConvTranspose rows q = 0 .. T1 (<= TC_TILES: the host requires T1 < TC_MAX_T1)
 
     // ---- one-time setup ------------------------------------------------------------------------------
     for (int i = tid; i < CNN_C * CNN_K; i += TC_THREADS) w0_s[i] = a.w0[i];
@@ -193,7 +211,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         b1_s[i] = a.b1[i];
         b2_s[i] = a.b2[i];
     }
-    for (int i = tid; i < CNN_K * CNN_C * 2; i += TC_THREADS) wT_s[i] = a.wT[i];
     if (tid < 2) b3_s[tid] = a.b3[tid];
     for (int i = tid; i < TC_A_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(A)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -322,71 +339,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                 uint32_t r[32];
                 tc_ld32(tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(m * CNN_C + hc * 32), r);
                 const int t = m * 128 + g * 32 + lane;
-                if (layer == 0) {
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        float v[8];
+                for (int c4 = 0; c4 < 4; c4++) {   // both layers: the result is the next MMA's operand A (fp16 hi + lo, in place)
+                    float v[8];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float acc = fmaf(__uint_as_float(r[c4 * 8 + q]), sc, bias[c4 * 8 + q]);
-                            v[q] = (t < T1) ? cnn_relu(acc) : 0.0f;
-                        }
-                        uint4 hi, lo;
-                        tc_split8(v, &hi, &lo, &range);
-                        unsigned char* p = A + (hc * 4 + c4) * TC_LBO + (t + CNN_P) * 16;
-                        *reinterpret_cast<uint4*>(p) = hi;
-                        *reinterpret_cast<uint4*>(p + TC_A_SPLIT) = lo;
+                    for (int q = 0; q < 8; q++) {
+                        const float acc = fmaf(__uint_as_float(r[c4 * 8 + q]), sc, bias[c4 * 8 + q]);
+                        v[q] = (t < T1) ? cnn_relu(acc) : 0.0f;
                     }
-                } else if (t < T1) {
-#pragma unroll
-                    for (int q = 0; q < 32; q++)
-                        h3[t * CNN_C + ((hc * 32 + q) ^ (t & 31))] = cnn_relu(fmaf(__uint_as_float(r[q]), sc, bias[q]));
+                    uint4 hi, lo;
+                    tc_split8(v, &hi, &lo, &range);
+                    unsigned char* p = A + (hc * 4 + c4) * TC_LBO + (t + CNN_P) * 16;
+                    *reinterpret_cast<uint4*>(p) = hi;
+                    *reinterpret_cast<uint4*>(p + TC_A_SPLIT) = lo;
                 }
             }
             tc_fence_before();
-            if (layer == 0) tc_fence_proxy_async();
+            tc_fence_proxy_async();
             __syncthreads();
         }
 
-        // ---- ConvTranspose1d on the CUDA cores, scores to HBM --------------------------------------------
+        // ---- ConvTranspose1d (64 -> 2, stride 3) on the tensor cores ---------------------------------------------
+        //   out[c][3q - 3 + r] = b[c] + sum_{j = 0..2} sum_ci h[q - j][ci] * w[ci][c][r + 3j]      (tap r + 3j <= 6)
+        // = three row-shifted GEMMs  D[q][2r + c] += A[rows q - j] * B_j  with K = 64, N = 16 (6 columns used): the operand of
+        // shift j is the activation buffer with the descriptor's start moved back j rows, exactly like a convolution tap.
+        if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t s = p_item % TC_STAGES, ph = (p_item / TC_STAGES) & 1;
+                tc_mbar_wait(&empty[s], ph ^ 1);
+                tc_mbar_expect_tx(&full[s], TC_CT_BYTES);
+                tc_bulk_load(W + s * TC_W_TAP, a.wct, TC_CT_BYTES, &full[s]);
+                p_item++;
+            }
+            __syncwarp();
+        } else if (warp == 0) {
+            tc_fence_after();
+            const uint32_t s = c_item % TC_STAGES, ph = (c_item / TC_STAGES) & 1;
+            tc_mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (tc_elect_one()) {
+                const uint64_t a_desc0 = tc_desc(a_base, TC_LBO, 128);
+                const uint64_t b_desc0 = tc_desc(w_base + s * TC_W_TAP, TC_CT_N * 16, 128);
+#pragma unroll 1
+                for (int m = 0; m < q_tiles; m++) {
+                    const uint32_t dcol = tmem + TC_CT_COL0 + m * TC_CT_N;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const uint64_t ad0 = a_desc0 + (uint64_t)(m * 128 + CNN_P - j);
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++) {  // hi*hi, lo*hi, hi*lo
+#pragma unroll
+                            for (int ks = 0; ks < CNN_C / 16; ks++) {
+                                const uint64_t ad = ad0 + (uint64_t)((prod == 1 ? TC_A_SPLIT / 16 : 0) + 2 * ks * (TC_LBO / 16));
+                                const uint64_t bd = b_desc0 + (uint64_t)(((j * 2 + (prod == 2 ? 1 : 0)) * TC_CT_BLOCK) / 16 +
+                                                                         2 * ks * (TC_CT_N * 16 / 16));
+                                tc_mma_f16(dcol, ad, bd, TC_IDESC_CT, (j | prod | ks) != 0);
+                            }
+                        }
+                    }
+                }
+                tc_commit(&empty[s]);
+                tc_commit(layer_done);
+            }
+            c_item++;
+            __syncwarp();
+        }
+        tc_mbar_wait(layer_done, done_phase);
+        done_phase ^= 1;
+        tc_fence_after();
         if (range) atomicOr(range_flag, 1u);
-        float* s0 = a.scores + (read * 2 + 0) * d.To;
-        float* s1 = a.scores + (read * 2 + 1) * d.To;
-        const float bb0 = b3_s[0], bb1 = b3_s[1];
-        // thread q produces the three outputs u = 3q - 3 + r, r = 0..2, which read hidden rows q, q-1, q-2:
-        //   out[c][3q-3+r] = b[c] + sum_j sum_ci h[q-j][ci] * w[ci][c][r+3j]        (k = r + 3j <= 6)
-        for (int q = tid; q <= T1 + 1; q += TC_THREADS) {
-            float o[3][2];
+        {
+            float* s0 = a.scores + (read * 2 + 0) * d.To;
+            float* s1 = a.scores + (read * 2 + 1) * d.To;
+            const float bb0 = b3_s[0], bb1 = b3_s[1], sct = a.inv_ctscale;
+            const int g = warp & 3;
+            for (int m = warp >> 2; m < q_tiles; m += 2) {
+                uint32_t r[8];
+                tc_ld8(tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(TC_CT_COL0 + m * TC_CT_N), r);
+                const int q = m * 128 + g * 32 + lane;
+                if (q <= T1) {
 #pragma unroll
-            for (int r = 0; r < 3; r++) { o[r][0] = bb0; o[r][1] = bb1; }
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const int t = q - j;
-                if (t < 0 || t >= T1) continue;
-                const float* hr = h3 + t * CNN_C;
-                const int sw = t & 31;
-#pragma unroll 8
-                for (int ci = 0; ci < CNN_C; ci++) {
-                    const float h = hr[ci ^ sw];
-#pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        if (r + 3 * j < CNN_K) {
-                            const float2 w = *reinterpret_cast<const float2*>(wT_s + ((r + 3 * j) * CNN_C + ci) * 2);
-                            o[r][0] = fmaf(h, w.x, o[r][0]);
-                            o[r][1] = fmaf(h, w.y, o[r][1]);
+                    for (int rr = 0; rr < 3; rr++) {
+                        const int u = 3 * q - 3 + rr;
+                        if (u >= 0 && u < d.To) {
+                            s0[u] = fmaf(__uint_as_float(r[2 * rr]), sct, bb0);
+                            s1[u] = fmaf(__uint_as_float(r[2 * rr + 1]), sct, bb1);
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const int u = 3 * q - 3 + r;
-                if (u >= 0 && u < d.To) {
-                    s0[u] = o[r][0];
-                    s1[u] = o[r][1];
-                }
-            }
         }
+        tc_fence_before();
         __syncthreads();
         if (tid == 0 && *range_flag && a.flags) a.flags[read] |= CNN_FLAG_RANGE;
     }

@@ -27,6 +27,8 @@ struct wdx_cnn {
     DevBuf w0, b0, wt1, b1, wt2, b2, wT, b3;  // float32 (EXACT mode and the first / last layer of both modes)
     DevBuf wtc;                                // fp16 hi/lo split weights of the two 64->64 layers (FAST mode)
     float tc_wscale = 1.0f;
+    DevBuf wct;                                // fp16 hi/lo split ConvTranspose operand (FAST mode), 3 row shifts
+    float tc_ctscale = 1.0f;
     // workspaces (grow-only)
     DevBuf sig[2], x, hA, hB, scores, masked, a_end, p_end, margin, cand, n_cand, flags, preds, redo_idx, redo_cnt, xg, sg;
     bool timing = false;
@@ -123,7 +125,7 @@ int forward_exact(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, floa
 
 int forward_fast(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, float* scores, uint8_t* flags, cudaStream_t st) {
     if (!c->tc_smem_ok) return fail(WDX_ERR_UNSUPPORTED, "tensor-core CNN kernel unavailable on this device");
-    if (d.T1 > TC_MAX_T1) return fail(WDX_ERR_UNSUPPORTED, "hidden length %d > %d: use WDX_CNN_EXACT_F32", d.T1, TC_MAX_T1);
+    if (d.T1 >= TC_MAX_T1) return fail(WDX_ERR_UNSUPPORTED, "hidden length %d >= %d: use WDX_CNN_EXACT_F32", d.T1, TC_MAX_T1);
     Timer tm{c, st};
     int rc;
     if ((rc = tm.begin())) return rc;
@@ -136,10 +138,11 @@ int forward_fast(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, float
     a.b0 = (const float*)c->b0.p;
     a.b1 = (const float*)c->b1.p;
     a.b2 = (const float*)c->b2.p;
-    a.wT = (const float*)c->wT.p;
     a.b3 = (const float*)c->b3.p;
     a.wtc = (const __half*)c->wtc.p;
     a.inv_wscale = 1.0f / c->tc_wscale;
+    a.wct = (const __half*)c->wct.p;
+    a.inv_ctscale = 1.0f / c->tc_ctscale;
     a.scores = scores;
     a.flags = flags;
     cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
@@ -244,6 +247,33 @@ int wdx_cnn_create(const wdx_cnn_config* cfg, const float* w0, const float* b0, 
         if (cudaMemcpy(c->wtc.p, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(WDX_ERR_CUDA, "weight upload failed"));
     }
+    {   // FAST mode ConvTranspose as three row-shifted GEMMs (cnn_tc_kernel.cuh): operand B of shift j holds, in column
+        // n = 2 * r + ch, the tap r + 3 j of torch's w3 [ci][ch][k] (zero where r + 3 j > 6 and in the padding columns)
+        float wmax = 0.f;
+        for (size_t i = 0; i < (size_t)CNN_C * 2 * CNN_K; i++) wmax = std::max(wmax, std::fabs(w3[i]));
+        int e = 0;
+        if (wmax > 0.f) e = (int)std::floor(std::log2(1024.0f / wmax));
+        e = std::max(-8, std::min(14, e));
+        c->tc_ctscale = std::ldexp(1.0f, e);
+        std::vector<__half> hc((size_t)TC_CT_BYTES / 2, __float2half_rn(0.0f));
+        for (int j = 0; j < 3; j++)
+            for (int r = 0; r < 3; r++) {
+                const int k = r + 3 * j;
+                if (k >= CNN_K) continue;
+                for (int ch = 0; ch < 2; ch++)
+                    for (int ci = 0; ci < CNN_C; ci++) {
+                        const float v = w3[((size_t)ci * 2 + ch) * CNN_K + k] * c->tc_ctscale;
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t off = tc_ct_offset(2 * r + ch, ci);
+                        hc[(size_t)(j * 2 + 0) * (TC_CT_BLOCK / 2) + off] = hi;
+                        hc[(size_t)(j * 2 + 1) * (TC_CT_BLOCK / 2) + off] = lo;
+                    }
+            }
+        if ((rc = c->wct.reserve(hc.size() * sizeof(__half)))) return bail(rc);
+        if (cudaMemcpy(c->wct.p, hc.data(), hc.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(WDX_ERR_CUDA, "weight upload failed"));
+    }
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (cudaFuncSetAttribute((const void*)cnn_conv64_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -270,7 +300,7 @@ void wdx_cnn_destroy(wdx_cnn* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    for (DevBuf* b : {&c->w0, &c->b0, &c->wt1, &c->b1, &c->wt2, &c->b2, &c->wT, &c->b3, &c->wtc, &c->sig[0], &c->sig[1], &c->x, &c->hA,
+    for (DevBuf* b : {&c->w0, &c->b0, &c->wt1, &c->b1, &c->wt2, &c->b2, &c->wT, &c->b3, &c->wtc, &c->wct, &c->sig[0], &c->sig[1], &c->x, &c->hA,
                       &c->hB, &c->scores, &c->masked, &c->a_end, &c->p_end, &c->margin, &c->cand, &c->n_cand, &c->flags, &c->preds,
                       &c->redo_idx, &c->redo_cnt, &c->xg, &c->sg})
         b->release();

@@ -247,11 +247,11 @@ int launch_finish(wdx_model* m, const FinishArgs& fa_in, int64_t grid_rows, cuda
 // A thread walks its SV range serially, so for a live-sized batch the range length IS the latency of the call:
 // 41 SVs per range (64 ranges of WDX10) cost 74 us in FAST and 330 us in EXACT arithmetic, measured; shorter
 // ranges are paid for by the fold over the partial sums (profiles/r01o_latency_sweep.jsonl: best at 128 / 512).
-void choose_splits(const wdx_model* m, int64_t n, bool exact, int* n_splits, int* sv_per_split) {
+void choose_splits(const wdx_model* m, int64_t n, int max_splits, int* n_splits, int* sv_per_split) {
     const int64_t ctas_x = (n + CTA_THREADS - 1) / CTA_THREADS;
     const int64_t target = (int64_t)m->sm_count * 4 * 2;  // two full waves of 4 CTAs/SM
     int splits = 1;
-    if (ctas_x < target) splits = (int)std::min<int64_t>(exact ? 512 : 128, (target + ctas_x - 1) / ctas_x);
+    if (ctas_x < target) splits = (int)std::min<int64_t>(max_splits, (target + ctas_x - 1) / ctas_x);
     if (m->forced_splits > 0) splits = m->forced_splits;
     splits = std::max(1, std::min(splits, m->n_sv));
     int per = (m->n_sv + splits - 1) / splits;
@@ -266,7 +266,7 @@ void choose_splits(const wdx_model* m, int64_t n, bool exact, int* n_splits, int
 int wdx::predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_t n, int mode, int64_t* labels_d,
                          double* conf_d, double* prob_d, uint8_t* flags_d, float* dist_d, cudaStream_t st) {
     int n_splits, per;
-    choose_splits(m, n, mode == WDX_MODE_EXACT_F64, &n_splits, &per);
+    choose_splits(m, n, mode == WDX_MODE_EXACT_F64 ? 512 : 128, &n_splits, &per);
     const int64_t stride = (n + 31) & ~(int64_t)31;
     int rc = m->part.reserve((size_t)n_splits * m->n_pairs * stride * sizeof(double));
     if (rc) return rc;
@@ -320,7 +320,9 @@ int wdx::predict_chunk_device(wdx_model* m, const void* Xd, int x_is_f32, int64_
 
     if (guarded) {
         int s2, per2;
-        choose_splits(m, std::max<int64_t>(1, cap / 16), true, &s2, &per2);  // expect the list to be mostly empty
+        // expect the list to be mostly empty; short ranges (latency) only for live-sized batches - the partial-sum planes
+        // of the re-run are sized splits x pairs x cap
+        choose_splits(m, std::max<int64_t>(1, cap / 16), cap <= 1024 ? 512 : (cap <= 4096 ? 256 : 64), &s2, &per2);
         const int64_t stride2 = (cap + 31) & ~(int64_t)31;
         rc = m->part2.reserve((size_t)s2 * m->n_pairs * stride2 * sizeof(double));
         if (rc) return rc;

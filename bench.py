@@ -342,6 +342,25 @@ def raw_signal_chain(params_small, local):
         dt = time.perf_counter() - t0
     out["e2e_pipelined_minibatches"] = {"reads_per_s": got / dt, "minibatch": mb, "minibatches": len(mbs), "ms_per_minibatch": dt / len(mbs) * 1e3,
                                         "api": "MinibatchDemuxer.stream(iter of (pinned rows, full_lengths)), results consumed in order"}
+    # the same stream of minibatches as raw int16 ADC samples + calibration (AdcBatch: half the bytes over PCIe, pA rows
+    # made on the device by wdx_calibrate_rows); the ADC values are the synthetic pA rows quantised with a MinION-like
+    # calibration (scale 0.1755 pA per count, offset -243)
+    from warpdemux_b200.file_proc import AdcBatch
+
+    cal_scale, cal_off = np.float32(0.1755), np.float32(-243.0)
+    sig_np = h_sig.numpy()
+    adc = np.where(np.isnan(sig_np), 0, np.rint(np.nan_to_num(sig_np) / cal_scale - cal_off)).astype(np.int16)
+    h_adc = torch.from_numpy(adc).pin_memory()
+    num = np.minimum(h_len, stride).astype(np.int64)
+    offv, scv = np.full(n, cal_off, np.float32), np.full(n, cal_scale, np.float32)
+    mbs_adc = [(AdcBatch(h_adc[a:a + mb], num[a:a + mb], offv[a:a + mb], scv[a:a + mb]), h_len[a:a + mb]) for a in range(0, n - mb + 1, mb)] * 4
+    for it in range(2):
+        t0 = time.perf_counter()
+        got = sum(int(r.labels.size) for r in dmx.stream(mbs_adc, return_df=False))
+        dt = time.perf_counter() - t0
+    out["e2e_pipelined_minibatches_adc"] = {"reads_per_s": got / dt, "minibatch": mb, "ms_per_minibatch": dt / len(mbs_adc) * 1e3,
+                                            "h2d_bytes_per_read": stride * 2,
+                                            "api": "MinibatchDemuxer.stream(iter of (AdcBatch(pinned int16 rows, calibration), full_lengths))"}
     # stage times, rows resident on the device
     side = torch.cuda.Stream()
     sp = side.cuda_stream

@@ -389,6 +389,15 @@ int wdx_validate_set_verdict_only(wdx_validate* v, int on);
 int wdx_validate_enable_timing(wdx_validate* v, int on);
 int wdx_validate_last_kernel_ms(wdx_validate* v, double* ms, int* launches);
 
+/* ---- raw ADC samples -> calibrated pA minibatch rows on the device --------------------------------------------
+ * The reference's loader hands float32 pA rows to the worker (pod5 `signal_pa` = (adc + calibration_offset) *
+ * calibration_scale in float32, rows NaN padded to sig_preload_size; file_proc.py:227-262).  Shipping the int16 ADC
+ * samples and calibrating after the upload halves the bytes that cross PCIe; results are bit-identical.
+ *   adc [n, stride_in] int16, n_valid [n] int32 samples present per row, offset / scale [n] float32,
+ *   out [n, stride_out] float32 (NaN from n_valid on).  DEVICE pointers; asynchronous on `stream`. */
+int wdx_calibrate_rows(const int16_t* adc, int64_t n, int64_t stride_in, const int32_t* n_valid, const float* offset,
+                       const float* scale, float* out, int64_t stride_out, int device, void* stream);
+
 /* ---- introspection -------------------------------------------------------- */
 const char* wdx_last_error(void);
 int wdx_device_count(void);

@@ -285,3 +285,60 @@ def test_gpu_minibatch_step_on_second_device(golden_real, models):
     assert np.array_equal(a.labels, b.labels) and np.array_equal(a.bounds, b.bounds) and np.array_equal(a.fpt, b.fpt, equal_nan=True)
     assert np.array_equal(np.concatenate([x.labels for x in sb]), b.labels)
     assert np.array_equal(np.concatenate([x.labels for x in sa]), a.labels)
+
+
+@pytest.mark.gpu
+def test_gpu_minibatch_step_from_raw_adc(golden_real, models):
+    """AdcBatch input: int16 ADC samples + calibration instead of float32 pA rows (half the PCIe bytes); the rows made on
+    the device are bit-identical to the host calibration, so every result is identical."""
+    import torch
+
+    from conftest import GOLD
+    from warpdemux_b200 import _lib
+    from warpdemux_b200.detect import cnn
+    from warpdemux_b200.file_proc import AdcBatch, MinibatchDemuxer
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import FingerprintConfig
+    from wdx_testutil import cnn_golden_signals
+
+    g = golden_real
+    with np.load(os.path.join(GOLD, "cnn_detect_rna004.npz")) as z:
+        gc = {k: z[k] for k in z.files}
+    with np.load(os.path.join(GOLD, "validate_rna004.npz")) as z:
+        full_lens = z["full_lens"][: int(z["n_real"])]
+    m = int(g["preload_size"])
+    sig = np.ascontiguousarray(cnn_golden_signals(gc)[:, :m])
+    n = sig.shape[0]
+    offs = gc["adc_offsets"]
+    adc = np.full((n, m), -7, dtype=np.int16)                         # filler beyond the read must not matter
+    num = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        row = gc["adc"][offs[i]:offs[i + 1]][:m]
+        adc[i, : row.size] = row
+        num[i] = row.size
+    batch = AdcBatch(adc, num, gc["calibration_offset"], gc["calibration_scale"])
+    # the calibration kernel alone
+    d_adc = torch.from_numpy(adc).cuda()
+    d_num = torch.from_numpy(num.astype(np.int32)).cuda()
+    d_off, d_sc = torch.from_numpy(gc["calibration_offset"]).cuda(), torch.from_numpy(gc["calibration_scale"]).cuda()
+    d_out = torch.empty((n, m), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().wdx_calibrate_rows(d_adc.data_ptr(), n, m, d_num.data_ptr(), d_off.data_ptr(), d_sc.data_ptr(), d_out.data_ptr(), m, 0,
+                                              torch.cuda.current_stream().cuda_stream), "wdx_calibrate_rows")
+    assert np.array_equal(d_out.cpu().numpy(), sig, equal_nan=True)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.load().wdx_calibrate_rows(adc.ctypes.data, n, m, d_num.data_ptr(), d_off.data_ptr(), d_sc.data_ptr(), d_out.data_ptr(), m, 0, None), "x")
+    # the whole step
+    md = cnn.load_cnn_model(os.path.join(GOLD, "models", "cnn_rna004_130bps_v0.2.4.npz"), device=0)
+    mp = DTW_SVM(models["WDX4_rna004_v1_0"], device=0, mode="guarded")
+    dmx = MinibatchDemuxer(mp, md, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=5),
+                           fp_config=FingerprintConfig(**_cfg(g)), device=0)
+    a = dmx.run(sig, full_lens, want_fpt=True)
+    b = dmx.run(batch, full_lens, want_fpt=True)
+    for f in ("labels", "fp_status", "bounds", "preds", "detect_code"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(a.fpt, b.fpt, equal_nan=True) and np.array_equal(a.prob, b.prob, equal_nan=True)
+    parts = list(dmx.stream([(AdcBatch(adc[:40], num[:40], batch.offset[:40], batch.scale[:40]), full_lens[:40]),
+                             (AdcBatch(adc[40:], num[40:], batch.offset[40:], batch.scale[40:]), full_lens[40:])], return_df=False))
+    assert np.array_equal(np.concatenate([p.labels for p in parts])[:40], dmx.run(sig[:40], full_lens[:40], return_df=False).labels)
+    dmx.close()
+    md.close()

@@ -24,10 +24,39 @@ struct wdx_validate {
 };
 
 namespace {
+// pA = (adc + offset) * scale in float32, as the pod5 reader calibrates on the host (the reference receives
+// `read_record.signal_pa`, file_proc.py:227-262); samples at or beyond n_valid become the NaN padding of a minibatch row.
+__global__ void __launch_bounds__(256) calibrate_kernel(const int16_t* __restrict__ adc, int64_t stride_in, const int32_t* __restrict__ n_valid,
+                                                        const float* __restrict__ offset, const float* __restrict__ scale,
+                                                        float* __restrict__ out, int64_t stride_out) {
+    const int64_t r = blockIdx.x;
+    const int64_t nv = min((int64_t)n_valid[r], min(stride_in, stride_out));
+    const float o = offset[r], sc = scale[r];
+    const int16_t* src = adc + r * stride_in;
+    float* dst = out + r * stride_out;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int64_t i = threadIdx.x; i < stride_out; i += 256)
+        dst[i] = (i < nv) ? __fmul_rn(__fadd_rn((float)src[i], o), sc) : qnan;
+}
+
 bool range_empty(const double* r) { return r[0] == -INFINITY && r[1] == INFINITY; }
 }  // namespace
 
 extern "C" {
+
+int wdx_calibrate_rows(const int16_t* adc, int64_t n, int64_t stride_in, const int32_t* n_valid, const float* offset,
+                       const float* scale, float* out, int64_t stride_out, int device, void* stream) {
+    if (n < 0 || stride_in < 1 || stride_out < 1) return fail(WDX_ERR_INVALID, "n=%lld strides %lld, %lld", (long long)n, (long long)stride_in, (long long)stride_out);
+    if (n == 0) return WDX_OK;
+    if (!adc || !n_valid || !offset || !scale || !out) return fail(WDX_ERR_INVALID, "NULL argument");
+    for (const void* p : {(const void*)adc, (const void*)n_valid, (const void*)offset, (const void*)scale, (const void*)out})
+        if (mem_kind(p) != 2) return fail(WDX_ERR_INVALID, "wdx_calibrate_rows takes device pointers (it is the first kernel after the upload)");
+    CUDA_TRY(cudaSetDevice(device));
+    calibrate_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(adc, stride_in, n_valid, offset, scale, out, stride_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return WDX_OK;
+}
 
 int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate** out) {
     if (!cfg || !out) return fail(WDX_ERR_INVALID, "NULL argument");

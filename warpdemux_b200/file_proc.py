@@ -44,6 +44,16 @@ def add_read_id_col_to_predictions(predictions: pd.DataFrame, read_ids) -> pd.Da
 
 
 @dataclass
+class AdcBatch:
+    """A minibatch as raw ADC samples instead of calibrated pA rows: half the bytes over PCIe, calibrated on the device
+    (`wdx_calibrate_rows`: pA = (adc + offset) * scale in float32, as pod5's `signal_pa`; bit-identical rows)."""
+    adc: np.ndarray            # int16 [n, stride] (any filler beyond num_samples), numpy or torch CPU tensor (pinned or not)
+    num_samples: np.ndarray    # [n] samples present per row (min(read length, stride))
+    offset: np.ndarray         # float32 [n] calibration_offset
+    scale: np.ndarray          # float32 [n] calibration_scale
+
+
+@dataclass
 class MinibatchResult:
     labels: np.ndarray            # int64 [n] predicted barcode, -1 = unclassified or no fingerprint
     conf: np.ndarray              # float64 [n] confidence margin (NaN without a fingerprint)
@@ -136,6 +146,8 @@ class MinibatchDemuxer:
         torch = self._torch
         st, cst = self._streams()
         job = {"slot": slot, "read_ids": read_ids}
+        if isinstance(signals, AdcBatch):
+            return self._upload_adc(job, signals, full_lengths)
         if isinstance(signals, torch.Tensor):
             if signals.dtype != torch.float32 or signals.dim() != 2 or not signals.is_contiguous():
                 raise ValueError("signals tensor must be contiguous float32 [n, stride]")
@@ -165,6 +177,48 @@ class MinibatchDemuxer:
             ev = torch.cuda.Event()
             ev.record(cst)
         job.update(d_sig=d_sig, d_len=d_len, ev_h2d=ev)
+        return job
+
+    def _upload_adc(self, job: dict, b: AdcBatch, full_lengths) -> dict:
+        """Phase 1 for raw ADC input: int16 rows + calibration go up, the float32 pA rows are made on the device."""
+        torch = self._torch
+        st, cst = self._streams()
+        slot = job["slot"]
+        adc = b.adc if isinstance(b.adc, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(b.adc, dtype=np.int16))
+        if adc.dtype != torch.int16 or adc.dim() != 2 or not adc.is_contiguous() or adc.is_cuda:
+            raise ValueError("AdcBatch.adc must be a contiguous int16 [n, stride] host array")
+        n, stride = adc.shape
+        lens = np.ascontiguousarray(np.minimum(np.asarray(full_lengths, dtype=np.int64).reshape(-1), np.iinfo(np.int32).max), dtype=np.int32)
+        small = np.empty((3, n), dtype=np.float32)            # one small upload: n_valid (as int32 bits), offset, scale
+        small[0] = np.minimum(np.asarray(b.num_samples, dtype=np.int64).reshape(-1), stride).astype(np.int32).view(np.float32)
+        small[1] = np.asarray(b.offset, dtype=np.float32).reshape(-1)
+        small[2] = np.asarray(b.scale, dtype=np.float32).reshape(-1)
+        if lens.shape[0] != n:
+            raise ValueError("full_lengths must have one entry per signal row")
+        job.update(n=n, stride=stride, lens=lens, h_sig=None)
+        with torch.cuda.stream(cst):
+            if not adc.is_pinned():
+                pin = self._pinned(f"{slot}:adc", n * stride, torch.int16).view(n, stride)
+                pin.copy_(adc)
+                adc = pin
+            d_adc = self._get(f"{slot}:adc", (n, stride), torch.int16)
+            d_adc.copy_(adc, non_blocking=True)
+            pin_small = self._pinned(f"{slot}:cal", 3 * n, torch.float32).view(3, n)
+            pin_small.copy_(torch.from_numpy(small))
+            d_small = self._get(f"{slot}:cal", (3, n), torch.float32)
+            d_small.copy_(pin_small, non_blocking=True)
+            d_len = self._get(f"{slot}:len", (n,), torch.int32)
+            pin_len = self._pinned(f"{slot}:len", n, torch.int32)
+            pin_len.copy_(torch.from_numpy(lens))
+            d_len.copy_(pin_len, non_blocking=True)
+            d_sig = self._get(f"{slot}:sig", (n, stride), torch.float32)
+            if n:
+                rc = _lib.load().wdx_calibrate_rows(d_adc.data_ptr(), n, stride, d_small[0].data_ptr(), d_small[1].data_ptr(),
+                                                    d_small[2].data_ptr(), d_sig.data_ptr(), stride, self.device, cst.cuda_stream)
+                _lib.check(rc, "wdx_calibrate_rows")
+            ev = torch.cuda.Event()
+            ev.record(cst)
+        job.update(d_sig=d_sig, d_len=d_len, ev_h2d=ev, h2d_bytes=int(n) * int(stride) * 2)
         return job
 
     def _launch(self, job: dict, want_fpt: bool) -> None:
@@ -254,7 +308,7 @@ class MinibatchDemuxer:
     def run(self, signals, full_lengths, read_ids: Optional[Sequence] = None, return_df: bool = True,
             want_fpt: bool = False) -> MinibatchResult:
         """One minibatch.  signals: float32 [n, stride] NaN-padded rows (numpy; torch CPU tensor, pinned or not; or a CUDA
-        tensor); full_lengths: [n] full read lengths (file_proc.py:241-262)."""
+        tensor), or an `AdcBatch` of raw int16 samples; full_lengths: [n] full read lengths (file_proc.py:241-262)."""
         with self._torch.cuda.device(self.device):
             job = self._upload(0, signals, full_lengths, read_ids)
             self._launch(job, want_fpt)

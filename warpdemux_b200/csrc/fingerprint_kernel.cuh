@@ -342,12 +342,39 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
     return (int)total;
 }
 
+constexpr int FP_RANK_MAX = 192;   // up to this many kept peaks the top-k is found by all-pairs ranking
+
 // ---- the k highest-scoring of the P kept peaks (sig_proc.py:188), in position order ---------------
 // out[0..k) = kp[i] + add for the selected peaks.  Radix-selects the k-th largest score (scores are
 // >= 0, so their bit patterns order like the values); ties -> the higher indices.  Requires P >= k.
 __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* state, int P, int k_events, int add,
                              int* out, FpScratch& s) {
     const int tid = threadIdx.x;
+    if (P <= FP_RANK_MAX) {
+        // A few hundred peaks: rank every peak against all others (descending score, ties -> the higher index first)
+        // and keep ranks < k - one pass and two barriers instead of the eight radix passes below.
+        __syncthreads();
+        for (int i = tid; i < P; i += FP_THREADS) {
+            const unsigned long long ki = (unsigned long long)__double_as_longlong(score[kp[i]]);
+            int rank = 0;
+            for (int j = 0; j < P; j++) {
+                const unsigned long long kj = (unsigned long long)__double_as_longlong(score[kp[j]]);
+                rank += (kj > ki) || (kj == ki && j > i);
+            }
+            state[i] = rank < k_events ? 4 : 0;
+        }
+        __syncthreads();
+        const int pchunk = (P + FP_THREADS - 1) / FP_THREADS;
+        const int i0 = min(P, tid * pchunk), i1 = min(P, i0 + pchunk);
+        uint32_t mysel = 0;
+        for (int i = i0; i < i1; i++) mysel += (state[i] == 4);
+        uint32_t tot_sel = 0;
+        uint32_t so = block_exscan(mysel, s, &tot_sel);
+        for (int i = i0; i < i1; i++)
+            if (state[i] == 4) out[so++] = (int)kp[i] + add;  // already sorted
+        __syncthreads();
+        return;
+    }
     unsigned long long thr_key;
     {
         unsigned long long prefix = 0, mask = 0;
@@ -429,7 +456,7 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
 //     P[i+1][j+1] = (q[i] - x[j])^2 + min(P[i][j], P[i][j+1] + pen2, P[i+1][j] + pen2),
 // then SubsequenceAlignment: matching[j] = sqrt(P[Q][j+1]) / Q, end = first argmin, start = column of the
 // first cell of best_path(paths, col = end + 1) (walk back to the FIRST minimum of sqrt(diagonal),
-// sqrt(up), sqrt(left), no penalty).  The matrix is never stored: lane l owns rows [l*R, (l+1)*R) and
+// sqrt(up), sqrt(left), no penalty).  The matrix is never stored: every lane owns one query row and
 // sweeps the columns as an anti-diagonal wavefront (values handed down the lanes by __shfl_up_sync);
 // the start column of the walk-back travels FORWARD with every cell (origin of a cell = origin of the
 // predecessor the walk-back would choose, or the cell's own column when that predecessor lies on the

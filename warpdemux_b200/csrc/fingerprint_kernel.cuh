@@ -342,13 +342,14 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
     return (int)total;
 }
 
-constexpr int FP_RANK_MAX = 192;   // up to this many kept peaks the top-k is found by all-pairs ranking
+constexpr int FP_RANK_MAX = 192;
+constexpr int FP_TOPK_CAND = FP_MAX_EVENTS + 2;   // keys of the threshold's histogram bin that can be ranked exactly (scratch = dv)   // up to this many kept peaks the top-k is found by all-pairs ranking
 
 // ---- the k highest-scoring of the P kept peaks (sig_proc.py:188), in position order ---------------
 // out[0..k) = kp[i] + add for the selected peaks.  Radix-selects the k-th largest score (scores are
 // >= 0, so their bit patterns order like the values); ties -> the higher indices.  Requires P >= k.
 __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* state, int P, int k_events, int add,
-                             int* out, FpScratch& s) {
+                             int* out, FpScratch& s, unsigned long long* cand /* FP_TOPK_CAND keys of scratch */) {
     const int tid = threadIdx.x;
     if (P <= FP_RANK_MAX) {
         // A few hundred peaks: rank every peak against all others (descending score, ties -> the higher index first)
@@ -376,7 +377,101 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
         return;
     }
     unsigned long long thr_key;
+    bool have_thr = false;
     {
+        // The k-th largest score in three light passes: float minimum / maximum of the peaks' scores, a 256-bin histogram
+        // over that range (float(x) and the binning are monotone, so a higher bin holds only larger scores), and the
+        // exact ranking of the few members of the bin that holds rank k on their 64-bit keys.  Falls through to the
+        // radix selection below for degenerate score sets.
+        __syncthreads();
+        if (tid < 256) s.hist[tid] = 0;
+        if (tid == 0) {
+            s.vmin_key = 0xffffffffu;
+            s.vmax_key = 0u;
+            s.ncand = 0;
+            s.flag = 0;
+        }
+        __syncthreads();
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+        for (int i = tid; i < P; i += FP_THREADS) {
+            const uint32_t kf = f32_key((float)score[kp[i]]);
+            kmin = min(kmin, kf);
+            kmax = max(kmax, kf);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&s.vmin_key, kmin);
+            atomicMax(&s.vmax_key, kmax);
+        }
+        __syncthreads();
+        const float vmin = f32_unkey(s.vmin_key), vmax = f32_unkey(s.vmax_key);
+        const float scale = __fdiv_rn(256.0f, __fsub_rn(vmax, vmin));
+        if (vmax > vmin && scale < 1e30f) {   // uniform
+            auto bin_of = [&](double x) { return min(255, (int)__fmul_rn(__fsub_rn((float)x, vmin), scale)); };
+            for (int i = tid; i < P; i += FP_THREADS) atomicAdd(&s.hist[bin_of(score[kp[i]])], 1u);
+            __syncthreads();
+            if (tid < 32) {  // warp 0 scans the 256 bins from the top, 8 per lane (lane 0 = bins 255..248)
+                const uint32_t k = (uint32_t)k_events - 1;  // 0-based rank from the top
+                uint32_t cnt[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    cnt[q] = s.hist[255 - (tid * 8 + q)];
+                    sum += cnt[q];
+                }
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (tid >= o) inc += t;
+                }
+                uint32_t run = inc - sum;  // peaks in higher bins
+                if (k >= run && k < inc) {  // exactly one lane
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (k >= run && k < run + cnt[q]) {
+                            s.sel_bin = 255 - (tid * 8 + q);
+                            s.sel_below = k - run;     // rank from the top inside the bin
+                            s.sel_count = cnt[q];
+                        }
+                        run += cnt[q];
+                    }
+                }
+            }
+            __syncthreads();
+            const int sel_bin = s.sel_bin;
+            const uint32_t r_in = s.sel_below, m = s.sel_count;
+            if (m <= (uint32_t)FP_TOPK_CAND) {   // uniform
+                for (int i = tid; i < P; i += FP_THREADS) {
+                    const double x = score[kp[i]];
+                    if (bin_of(x) == sel_bin) cand[atomicAdd(&s.ncand, 1u)] = (unsigned long long)__double_as_longlong(x);
+                }
+                __syncthreads();
+                for (uint32_t t = tid; t < m; t += FP_THREADS) {
+                    const unsigned long long x = cand[t];
+                    uint32_t g = 0, e = 0;
+                    for (uint32_t u = 0; u < m; u++) {
+                        const unsigned long long y = cand[u];
+                        g += (y > x);
+                        e += (y == x);
+                    }
+                    if (r_in >= g && r_in < g + e) {   // every copy of the threshold key writes the same values
+                        s.sel_prefix64 = x;
+                        s.sel_k = r_in - g;            // ties ranked above the selected one
+                        s.flag = 1;
+                    }
+                }
+                __syncthreads();
+                have_thr = s.flag != 0;
+            }
+        }
+    }
+    if (have_thr) {
+        thr_key = s.sel_prefix64;
+    } else {
         unsigned long long prefix = 0, mask = 0;
         uint32_t k = (uint32_t)k_events - 1;  // 0-based rank from the top
         for (int shift = 56; shift >= 0; shift -= 8) {
@@ -750,7 +845,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         fail(FP_FAIL_NORMALIZE);
         return;
     }
-    select_top_k(score, kp, state, P, c.num_events, w, cpts + 1, s);  // + running_stat_width
+    select_top_k(score, kp, state, P, c.num_events, w, cpts + 1, s, reinterpret_cast<unsigned long long*>(dv));  // + running_stat_width
     if (tid == 0) {
         cpts[0] = 0;                      // peaks lie in [1, nc-2] and w >= 1: 0 and n are never present
         cpts[c.num_events + 1] = n;
@@ -837,7 +932,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
             fail(FP_FAIL_SEGMENTATION);
             return;
         }
-        select_top_k(score, kp, state, P2, ke, w - sbs, cpts + 1, s);  // relative to raw_signal[sbs:]
+        select_top_k(score, kp, state, P2, ke, w - sbs, cpts + 1, s, reinterpret_cast<unsigned long long*>(dv));  // relative to raw_signal[sbs:]
         if (tid == 0) {
             cpts[0] = 0;
             cpts[ke + 1] = n - sbs;   // scores.size + 2 * running_stat_width = (nc - sbs) + 2 w

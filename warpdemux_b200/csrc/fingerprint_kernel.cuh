@@ -225,6 +225,26 @@ __device__ double np_pairwise_sum(int n, F at) {
     return res;
 }
 
+// The same sum by one warp (all 32 lanes call it, all get the result): lane j < 8 owns accumulator j, so the
+// dependent chain is n / 8 additions instead of n; the combination tree and the tail are those of the serial code.
+template <typename F>
+__device__ double np_pairwise_sum_warp(int n, F at) {
+    const int lane = threadIdx.x & 31;
+    if (n < 8) return np_pairwise_sum(n, at);
+    double r = 0.0;
+    const int n8 = n - (n % 8);
+    if (lane < 8) {
+        r = at(lane);
+        for (int i = 8 + lane; i < n8; i += 8) r = __dadd_rn(r, at(i));
+    }
+    const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2),
+                 r3 = __shfl_sync(0xffffffffu, r, 3), r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5),
+                 r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (int i = n8; i < n; i++) res = __dadd_rn(res, at(i));
+    return res;
+}
+
 // Python round() of a non-negative double: round half to even.
 __device__ __forceinline__ int py_round(double x) { return (int)rint(x); }
 
@@ -863,14 +883,16 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     __syncthreads();
 
     // ---- mean_normalize (sig_proc.py:99-111) with numpy's summation order -----------
-    if (tid == 0) {
-        const double mean = __ddiv_rn(np_pairwise_sum(n_seg, [&](int i) { return ev[i]; }), (double)n_seg);
-        const double ss = np_pairwise_sum(n_seg, [&](int i) {
+    if (tid < 32) {   // warp 0: the eight accumulators of numpy's block sum live in lanes 0..7
+        const double mean = __ddiv_rn(np_pairwise_sum_warp(n_seg, [&](int i) { return ev[i]; }), (double)n_seg);
+        const double ss = np_pairwise_sum_warp(n_seg, [&](int i) {
             const double d = __dsub_rn(ev[i], mean);
             return __dmul_rn(d, d);
         });
-        red[0] = mean;
-        red[1] = __dsqrt_rn(__ddiv_rn(ss, (double)n_seg));
+        if (tid == 0) {
+            red[0] = mean;
+            red[1] = __dsqrt_rn(__ddiv_rn(ss, (double)n_seg));
+        }
     }
     __syncthreads();
     const double ev_mean = red[0], ev_std = red[1];

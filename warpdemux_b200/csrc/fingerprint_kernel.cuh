@@ -739,15 +739,26 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     __syncthreads();
     {   // the one HBM read of the slice, coalesced; minimum / maximum on the way
         uint32_t kmin = 0xffffffffu, kmax = 0u;
-        for (int i = tid; i < n; i += FP_THREADS) {
-            const float x = __ldg(src + i);
-            sig[i] = x;
-            if (x != x) {
-                atomicMin(&s.first_nan, i);
-            } else {
-                const uint32_t kx = f32_key(x);
-                kmin = min(kmin, kx);
-                kmax = max(kmax, kx);
+        for (int i0 = tid; i0 < n; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * FP_THREADS;
+                xv[u] = (i < n) ? __ldg(src + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * FP_THREADS;
+                if (i >= n) break;
+                const float x = xv[u];
+                sig[i] = x;
+                if (x != x) {
+                    atomicMin(&s.first_nan, i);
+                } else {
+                    const uint32_t kx = f32_key(x);
+                    kmin = min(kmin, kx);
+                    kmax = max(kmax, kx);
+                }
             }
         }
 #pragma unroll

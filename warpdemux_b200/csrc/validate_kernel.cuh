@@ -467,10 +467,21 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         const int L = (int)max((int64_t)0, min(fl, a.stride));
         int has_nan = 0;
         if (tid < VAL_NVALS) sh_v[tid] = qnan;
-        for (int i = tid; i < L; i += FP_THREADS) {
-            const float x = row[i];
-            vsig[i] = x;
-            has_nan |= (x != x);
+        for (int i0 = tid; i0 < L; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * FP_THREADS;
+                xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * FP_THREADS;
+                if (i < L) {
+                    vsig[i] = xv[u];
+                    has_nan |= (xv[u] != xv[u]);
+                }
+            }
         }
         has_nan = __syncthreads_or(has_nan);
 

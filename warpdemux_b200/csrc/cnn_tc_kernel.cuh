@@ -238,9 +238,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     for (int64_t read = blockIdx.x; read < a.n; read += gridDim.x) {
         // ---- input row, conv1 -> activations (fp16 hi + lo) ------------------------------------------
         const float* xr = a.x + read * d.T;
-        for (int j = tid; j < 3 * T1 + 8; j += TC_THREADS) {
-            const int i = j - CNN_P;
-            xs[j] = (i >= 0 && i < d.T) ? __ldg(xr + i) : 0.0f;
+        for (int j0 = tid; j0 < 3 * T1 + 8; j0 += 4 * TC_THREADS) {   // four loads in flight per thread before the first use
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = j0 + u * TC_THREADS - CNN_P;
+                xv[u] = (i >= 0 && i < d.T) ? __ldg(xr + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u * TC_THREADS;
+                if (j < 3 * T1 + 8) xs[j] = xv[u];
+            }
         }
         if (tid == 0) *range_flag = 0;
         // padding rows (the previous read's float32 h3 aliased this buffer): rows [0,3) and [T1+3, TC_ROWS)

@@ -380,3 +380,51 @@ void wdx_oracle_warping_paths(const double *s1, int r, const double *s2, int c,
     }
     for (int64_t t = 0; t < (int64_t)(r + 1) * W; t++) out[t] = sqrt(out[t]);
 }
+
+/* ------------------------------------------------------------------------
+ * LLR change-point trace of the ADAPTed fallback detector.  Follows
+ * warpdemux/adapted/adapted/detect/_c_llr.pyx: var_c (:24-38), _gains (:66-88,
+ * stride 1, no early stopping — the only variant combined.py:39-129,232-274
+ * reaches) on the cumulative sums c = cumsum(x), c2 = cumsum(x*x) that
+ * c_llr_trace (:214-230) builds with np.cumsum (sequential float64 adds).
+ *   var(s, e)  = c2[e-1]/e - (c[e-1]/e)^2                          (s == 0)
+ *              = (c2[e-1]-c2[s-1])/(e-s) - ((c[e-1]-c[s-1])/(e-s))^2
+ *   gains[i]   = (e-s) log var(s,e) - ((i-s) log var(s,i) + (e-i) log var(i,e)),
+ *                i in [s + offset_head, e - offset_tail); 0 elsewhere.
+ * log(0) = -inf and log(<0) = NaN propagate exactly as in the reference
+ * (its callers silence the RuntimeWarnings).  Pinned against the reference's
+ * own compiled Cython (oracle/_ref/ref_c_llr, tests/test_oracle_llr.py).
+ * ---------------------------------------------------------------------- */
+void wdx_oracle_cumsums(const double *x, int64_t n, double *c, double *c2)
+{
+    double a = 0.0, b = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        a += x[i];
+        b += x[i] * x[i];
+        c[i] = a;
+        c2[i] = b;
+    }
+}
+
+static double llr_var_c(int64_t start, int64_t end, const double *c, const double *c2)
+{
+    if (start == end) return 0.0;
+    if (start == 0) {
+        const double m = c[end - 1] / (double)end;
+        return c2[end - 1] / (double)end - m * m;
+    }
+    const double m = (c[end - 1] - c[start - 1]) / (double)(end - start);
+    return (c2[end - 1] - c2[start - 1]) / (double)(end - start) - m * m;
+}
+
+void wdx_oracle_llr_gains(const double *c, const double *c2, int64_t n, int64_t start, int64_t end,
+                          int64_t offset_head, int64_t offset_tail, double *gains)
+{
+    for (int64_t i = 0; i < n; i++) gains[i] = 0.0;
+    const double var_summed = (double)(end - start) * log(llr_var_c(start, end, c, c2));
+    for (int64_t i = start + offset_head; i < end - offset_tail; i++) {
+        const double head = (double)(i - start) * log(llr_var_c(start, i, c, c2));
+        const double tail = (double)(end - i) * log(llr_var_c(i, end, c, c2));
+        gains[i] = var_summed - (head + tail);
+    }
+}

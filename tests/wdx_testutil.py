@@ -192,3 +192,30 @@ def pack_rows(rows, fill=np.nan):
     for i, r in enumerate(rows):
         out[i, : r.size] = r
     return out
+
+
+def unpack_adc_planes(lo, hi):
+    """Inverse of oracle/make_golden_real4000.py::planes: byte planes of the zig-zag coded int16 deltas -> int16 samples."""
+    z = lo.astype(np.uint32) | (hi.astype(np.uint32) << 8)
+    d = ((z >> 1).astype(np.int32) ^ -(z & 1).astype(np.int32)).astype(np.int16)
+    return np.cumsum(d.astype(np.int64)).astype(np.int16)      # int16 wrap-around like the encoder's deltas
+
+
+def real4000_rows(g, full=None):
+    """Minibatch rows (float32 pA, NaN padded to preload_size) of tests/golden/real4000_rna004_WDX4.npz.
+    full = the dict of tests/golden/_local/real4000_adc_rows.npz -> all 4000 reads, else the committed subset.
+    Returns (read indices int64 [m], rows float32 [m, preload], adc int16 [m, preload] (filler -7), num_samples int64 [m])."""
+    m = int(g["preload_size"])
+    src = full if full is not None else g
+    idx = np.arange(len(g["full_lengths"])) if full is not None else g["subset"]
+    adc_cat = unpack_adc_planes(src["adc_lo"], src["adc_hi"])
+    offs = src["adc_offsets"]
+    rows = np.full((idx.size, m), np.nan, dtype=np.float32)
+    adc = np.full((idx.size, m), -7, dtype=np.int16)
+    num = np.zeros(idx.size, dtype=np.int64)
+    for j, i in enumerate(idx):
+        a = adc_cat[offs[j]:offs[j + 1]]
+        adc[j, : a.size] = a
+        num[j] = a.size
+        rows[j, : a.size] = (a.astype(np.float32) + g["calibration_offset"][i]) * g["calibration_scale"][i]
+    return idx.astype(np.int64), rows, adc, num

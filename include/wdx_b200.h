@@ -170,6 +170,11 @@ typedef struct wdx_fp wdx_fp;
 
 int wdx_fp_create(const wdx_fp_config* cfg, int device, wdx_fp** out);
 void wdx_fp_destroy(wdx_fp* f);
+/* Second capacity for the rare long adapters (the LLR fallback can place an adapter end anywhere below
+ * core.max_obs_trace, the CNN only below core.max_obs_adapter): with wdx_fp_config.max_slice_len > 0 and
+ * len > max_slice_len, reads that do not fit the first pass are redone by a second launch with this capacity
+ * instead of failing with WDX_FP_FAIL_TOO_LONG; all other reads keep the occupancy of the small capacity.  0 = off. */
+int wdx_fp_set_long_slice_len(wdx_fp* f, int32_t len);
 
 /*   signals        [n, stride] float32 calibrated pA signal, one read per row (the reference's minibatch,
  *                  file_proc.py:333-354).  Rows may be NaN-padded at the end; the first NaN ends the read.
@@ -388,6 +393,45 @@ int wdx_validate_run_ex(wdx_validate* v, const float* signals, int64_t n, int64_
 int wdx_validate_set_verdict_only(wdx_validate* v, int on);
 int wdx_validate_enable_timing(wdx_validate* v, int on);
 int wdx_validate_last_kernel_ms(wdx_validate* v, double* ms, int* launches);
+
+/* ---- LLR fallback of the boundary detection -------------------------------------------------------------------
+ * Replaces the re-detection branch of adapted.detect.combined.combined_detect_cnn
+ * (warpdemux/adapted/adapted/detect/combined.py:222-296) for the reads whose CNN boundaries fail validation:
+ *   normalize_signal(row[:min(max_obs_trace, full_len)])                          detect/normalize.py:15-63
+ *   "hail mary" (cnn_boundaries.fallback_to_llr_short_reads, combined.py:232-274): for short reads with a long
+ *       CNN poly(A) stretch the poly(A) end is re-detected on [cnn adapter_end, cnn polya_end) by an LLR trace
+ *       (detect/llr.py:243-334, _c_llr.pyx:66-88) + detect_full_polya_trace_peak_with_spike (llr.py:385-455);
+ *       the re-validated result REPLACES the read's result, success or not
+ *   full LLR (cnn_boundaries.fallback_to_llr, combined.py:275-290): detect_llr_on_downscaled_signal
+ *       (combined.py:39-129: adapter end = first peak of the LLR trace by scipy find_peaks(width, prominence x nanstd,
+ *       rel_height), corrected for plateaus and split peaks, llr.py:124-240; poly(A) end as above); its validated
+ *       result replaces the read's result only if it SUCCEEDS.
+ * After wdx_validate_set_llr(v, cfg) every wdx_validate_run / wdx_validate_run_ex call performs this branch on the
+ * device behind the validation of the given boundaries (two llr_kernel + two masked validate_kernel launches, no
+ * host round trip); cfg = NULL switches it off again.  info[.][3] then reports, per read:
+ *   bits 0-1  which boundaries the reported result validated: 0 = the given (CNN) ones, 1 = hail mary, 2 = full LLR
+ *             (for 1 and 2 DetectResults.llr_adapter_end / llr_polya_end are bounds[.][1] / bounds[.][2] and the
+ *             reference's primary_method of that result is "llr")
+ *   bit 2     the hail-mary re-detection ran, bit 3 the full LLR detection ran.
+ * Two more fail codes appear in info[.][0]: */
+enum {
+    WDX_VAL_MAD_ZERO = 10,   /* "MAD normalization failed: scale is 0" (normalize.py:55-58), the read's whole result */
+    WDX_VAL_LLR_ERROR = 11   /* reserved: other exceptions of the fallback branch */
+};
+typedef struct {
+    int32_t max_obs_trace;             /* core.max_obs_trace                       (10000 WarpDemuX, 16000 ADAPTed) */
+    int32_t min_obs_adapter;           /* core.min_obs_adapter                     (1000) */
+    int32_t max_obs_adapter;           /* core.max_obs_adapter                     (6500) */
+    int32_t downscale_factor;          /* core.downscale_factor                    (10) */
+    double sig_norm_outlier_thresh;    /* core.sig_norm_outlier_thresh             (5.0) */
+    double adapter_peak_prominence;    /* llr_boundaries.adapter_peak_prominence   (1.0) */
+    double adapter_peak_rel_height;    /* llr_boundaries.adapter_peak_rel_height   (1.0) */
+    int32_t adapter_peak_width;        /* llr_boundaries.adapter_peak_width        (1000) */
+    int32_t fallback_to_llr;           /* cnn_boundaries.fallback_to_llr           (1) */
+    int32_t fallback_to_llr_short_reads; /* cnn_boundaries.fallback_to_llr_short_reads (1) */
+    int32_t reserved;
+} wdx_llr_config;
+int wdx_validate_set_llr(wdx_validate* v, const wdx_llr_config* cfg);
 
 /* ---- raw ADC samples -> calibrated pA minibatch rows on the device --------------------------------------------
  * The reference's loader hands float32 pA rows to the worker (pod5 `signal_pa` = (adc + calibration_offset) *

@@ -227,7 +227,31 @@ def main():
             offs.append(offs[-1] + adc_rows[i].size)
         return np.concatenate(chunks) if chunks else np.zeros(0, np.int16), np.array(offs, dtype=np.int64)
 
-    subset = np.flatnonzero((n_validate > 1) | (success == 0) | (np.arange(n) % 16 == 0))
+    # Reads whose change points depend on how numpy's (unstable) argsort orders EQUAL t-test scores: the reference's
+    # result is machine-dependent there.  The fixture keeps which reads have such ties and, where a stable sort (the CUDA
+    # kernels' rule: the later of two equal peaks wins) gives another fingerprint than this machine's numpy did, that
+    # fingerprint too (oracle/wdx_oracle.py::fingerprint(stable_ties=True)).
+    from oracle import wdx_oracle as _o
+
+    fp_keys = dict(padding=pad, outlier_thresh=float(spc.core.sig_norm_outlier_thresh), min_obs_per_base=int(spc.segmentation.min_obs_per_base),
+                   running_stat_width=int(spc.segmentation.running_stat_width), num_events=int(spc.segmentation.num_events),
+                   barcode_num_events=nb)
+    tie_reads, stable_idx, stable_fpt, stable_label = [], [], [], []
+    for i in np.flatnonzero(status == 0):
+        row = np.full(m, np.nan, dtype=np.float32)
+        a = adc_rows[i]
+        row[: a.size] = (a.astype(np.float32) + cal_off[i]) * cal_sc[i]
+        if _o.fingerprint_has_ties(row, int(bounds[i, 0]), int(bounds[i, 1]), **fp_keys):
+            tie_reads.append(i)
+            st_, f_, _, _ = _o.fingerprint(row, int(bounds[i, 0]), int(bounds[i, 1]), stable_ties=True, **fp_keys)
+            plain = _o.fingerprint(row, int(bounds[i, 0]), int(bounds[i, 1]), **fp_keys)
+            assert np.array_equal(plain[1], fpt[i]), i          # the oracle reproduces the reference on this machine
+            if st_ != 0 or not np.array_equal(f_, fpt[i]):
+                stable_idx.append(i)
+                stable_fpt.append(f_)
+                stable_label.append(int(ref_model.predict(f_[None, :], nproc=1, return_df=False)[0][0]) if st_ == 0 else -1)
+    print("reads with score ties:", len(tie_reads), "of which the stable tie rule changes the fingerprint:", stable_idx)
+    subset = np.flatnonzero((n_validate > 1) | (success == 0) | (np.arange(n) % 16 == 0) | np.isin(np.arange(n), stable_idx))
     adc_sub, offs_sub = pack(subset)
 
     def planes(adc):
@@ -257,6 +281,8 @@ def main():
         float_fields=np.array(FLOAT_FIELDS), part_fields=np.array(PART_FIELDS),
         fail_reason=np.array(fail_reason.tolist()),
         status=status, fpt=fpt, dwell=dwell, stats=stats, y_pred=y_pred.astype(np.int64), y_prob=y_prob,
+        tie_reads=np.array(tie_reads, dtype=np.int64), stable_idx=np.array(stable_idx, dtype=np.int64),
+        stable_fpt=np.array(stable_fpt, dtype=np.float64).reshape(-1, nb), stable_label=np.array(stable_label, dtype=np.int64),
         subset=subset.astype(np.int64), adc_lo=sub_lo, adc_hi=sub_hi, adc_offsets=offs_sub,
         cfg=np.array(json.dumps(cfg)),
     )

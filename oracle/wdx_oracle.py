@@ -237,9 +237,61 @@ FP_FAIL_DETECT = 2        # detect_results.success == False (sig_proc.py:400-407
 FP_FAIL_NORMALIZE = 3     # "segment normalization failed" (sig_proc.py:553-560)
 
 
+def select_by_peak_distance_stable(peaks: np.ndarray, priority: np.ndarray, distance: int) -> np.ndarray:
+    """scipy.signal._peak_finding_utils._select_by_peak_distance with a STABLE argsort: of two equally high peaks closer
+    than `distance` the later one stays.  scipy sorts with numpy's default (unstable) argsort, so which of the two stays
+    is not defined by the reference — it depends on the numpy build and the CPU's SIMD level.  Returns the keep mask."""
+    n = peaks.size
+    keep = np.ones(n, dtype=bool)
+    order = np.argsort(priority, kind="stable")
+    for i in range(n - 1, -1, -1):
+        j = order[i]
+        if not keep[j]:
+            continue
+        k = j - 1
+        while 0 <= k and peaks[j] - peaks[k] < distance:
+            keep[k] = False
+            k -= 1
+        k = j + 1
+        while k < n and peaks[k] - peaks[j] < distance:
+            keep[k] = False
+            k += 1
+    return keep
+
+
+def fingerprint_has_ties(signal: np.ndarray, adapter_start: int, adapter_end: int, *, padding: int = 100,
+                         outlier_thresh: float = 5.0, min_obs_per_base: int = 6, running_stat_width: int = 12,
+                         num_events: int = 110, **_ignored) -> bool:
+    """True when the reference's change points depend on how numpy's unstable argsort orders EQUAL t-test scores:
+    two equally high local maxima closer than the peak distance, or a tie at the num_events-th highest kept peak."""
+    from scipy.signal import find_peaks
+
+    signal = np.asarray(signal)
+    sig = signal[max(0, adapter_start - padding):min(signal.size, adapter_end + padding)].copy()
+    med = np.nanmedian(sig)
+    mad = np.nanmedian(np.abs(sig - med))
+    np.clip(sig, med - outlier_thresh * mad, med + outlier_thresh * mad, out=sig)
+    n = sig.size
+    m_obs = min(min_obs_per_base, round(n / num_events / 2))
+    w = min(running_stat_width, round(n / num_events))
+    if m_obs < 1 or w < 1 or n - 2 * w < 3:
+        return False
+    scores = windowed_t_test(sig, w)
+    pk, _ = find_peaks(scores)
+    for a in range(pk.size - 1):
+        b = a + 1
+        while b < pk.size and pk[b] - pk[a] < m_obs:
+            if scores[pk[a]] == scores[pk[b]]:
+                return True
+            b += 1
+    keep = select_by_peak_distance_stable(pk, scores[pk], m_obs)
+    h = np.sort(scores[pk[keep]])
+    return bool(h.size > num_events and h[-num_events] == h[-num_events - 1])
+
+
 def fingerprint(signal: np.ndarray, adapter_start: int, adapter_end: int, *, padding: int = 100,
                 outlier_thresh: float = 5.0, min_obs_per_base: int = 6, running_stat_width: int = 12,
-                num_events: int = 110, barcode_num_events: int = 25, mutate: bool = False):
+                num_events: int = 110, barcode_num_events: int = 25, mutate: bool = False, stable_ties: bool = False):
     """`detect_results_to_fpt` (sig_proc.py:394-605) for the configuration every
     shipped DTW-SVM model uses (rna004_130bps@v1.0.toml: sig_extract
     normalization "none", segmentation normalization "mean",
@@ -247,6 +299,9 @@ def fingerprint(signal: np.ndarray, adapter_start: int, adapter_end: int, *, pad
 
     Returns (status, fpt float64[25], dwell int64[25], stats dict).
     numpy 2 scalar semantics (NEP 50) apply to the clip bounds: float32.
+    stable_ties: equal t-test scores are ordered by a stable sort (the later peak wins) instead of by numpy's default
+    argsort, whose order of equal keys is unspecified (introsort / AVX-512 / AVX2 sorting networks depending on the numpy
+    build and the CPU) — the one point where the reference's own result is machine-dependent.
     """
     from scipy.signal import find_peaks
 
@@ -268,9 +323,12 @@ def fingerprint(signal: np.ndarray, adapter_start: int, adapter_end: int, *, pad
         peaks, _ = find_peaks(scores, distance=m_obs)            # :183
     except ValueError:                                           # distance < 1 (very short adapter)
         return (FP_FAIL_SEGMENTATION,) + empty
+    if stable_ties:      # the tie rule of the CUDA kernels (see select_by_peak_distance_stable)
+        peaks, _ = find_peaks(scores)
+        peaks = peaks[select_by_peak_distance_stable(peaks, scores[peaks], m_obs)]
     if peaks.size < num_events:                                  # :185-186
         return (FP_FAIL_SEGMENTATION,) + empty
-    cpts = peaks[np.argsort(scores[peaks])[-num_events:]] + w    # :188
+    cpts = peaks[np.argsort(scores[peaks], kind="stable" if stable_ties else None)[-num_events:]] + w    # :188
     cpts.sort()
     if cpts[0] != 0:
         cpts = np.insert(cpts, 0, 0)

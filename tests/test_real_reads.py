@@ -342,3 +342,54 @@ def test_gpu_minibatch_step_from_raw_adc(golden_real, models):
     assert np.array_equal(np.concatenate([p.labels for p in parts])[:40], dmx.run(sig[:40], full_lens[:40], return_df=False).labels)
     dmx.close()
     md.close()
+
+
+@pytest.mark.gpu
+def test_gpu_fingerprints_of_the_4000_read_subset_incl_score_ties(models):
+    """Fingerprint + barcode call of the committed subset of tests/golden/real4000_rna004_WDX4.npz from the reference's own
+    boundaries (incl. the long LLR adapters, which take the second, larger-capacity pass).  Reads where two EQUAL t-test
+    scores compete inside the peak distance are ambiguous in the reference itself (numpy's unstable argsort decides);
+    the kernel follows the stable order: expected values for those come from the oracle's stable_ties variant."""
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+    from warpdemux_b200.sig_proc import Fingerprinter, FingerprintConfig
+    from wdx_testutil import real4000_rows
+
+    with np.load(os.path.join(ROOT, "tests", "golden", "real4000_rna004_WDX4.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    idx, rows, _, _ = real4000_rows(g)
+    c = json.loads(str(g["cfg"]))
+    cfg = {k: c[k] for k in ("padding", "outlier_thresh", "min_obs_per_base", "running_stat_width", "num_events", "barcode_num_events")}
+    want_fpt = g["fpt"].copy()
+    want_fpt[g["stable_idx"]] = g["stable_fpt"]
+    assert g["stable_idx"].size >= 1 and set(g["stable_idx"].tolist()) <= set(idx.tolist())
+    for kw in (dict(), dict(max_slice_len=6720, long_slice_len=10112)):
+        fp = Fingerprinter(FingerprintConfig(**cfg, **kw), device=0)
+        b = fp.extract(rows, g["bounds"][idx, 0], g["bounds"][idx, 1], detect_ok=g["success"][idx])
+        assert np.array_equal(b.status, g["status"][idx]), kw
+        good = g["status"][idx] == 0
+        assert np.array_equal(b.fpt[good], want_fpt[idx][good]), kw
+        assert (g["bounds"][idx, 1] - g["bounds"][idx, 0] > 6600)[good].sum() >= 5      # the long pass is exercised
+        fp.close()
+    fp = Fingerprinter(FingerprintConfig(max_slice_len=6720, **cfg), device=0)             # without the long pass they fail
+    b = fp.extract(rows, g["bounds"][idx, 0], g["bounds"][idx, 1], detect_ok=g["success"][idx])
+    assert (b.status == 4).sum() >= 5
+    fp.close()
+
+
+def test_oracle_stable_tie_rule_on_the_ambiguous_read():
+    """The read of the 4000-read fixture whose change points depend on the order of two equal scores: numpy's default
+    argsort reproduces the reference (same machine, same numpy) and the stable order gives the fixture's second answer."""
+    from oracle import wdx_oracle as o
+    from wdx_testutil import real4000_rows
+
+    with np.load(os.path.join(ROOT, "tests", "golden", "real4000_rna004_WDX4.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    idx, rows, _, _ = real4000_rows(g)
+    c = json.loads(str(g["cfg"]))
+    cfg = {k: c[k] for k in ("padding", "outlier_thresh", "min_obs_per_base", "running_stat_width", "num_events", "barcode_num_events")}
+    for q, i in enumerate(g["stable_idx"]):
+        j = int(np.flatnonzero(idx == i)[0])
+        a0, a1 = int(g["bounds"][i, 0]), int(g["bounds"][i, 1])
+        assert o.fingerprint_has_ties(rows[j], a0, a1, **cfg)
+        st, f, _, _ = o.fingerprint(rows[j], a0, a1, stable_ties=True, **cfg)
+        assert st == 0 and np.array_equal(f, g["stable_fpt"][q]) and not np.array_equal(f, g["fpt"][i])

@@ -66,6 +66,7 @@ struct FpArgs {
     const uint8_t* detect_ok;   // [n] DetectResults.success, or nullptr (all true)
     int64_t n;
     int cap;                    // samples of shared memory per CTA
+    int retry_status;           // != 0: second pass with a larger `cap` — only reads whose status equals this are processed
     double* fpt;                // [n][barcode_num_events]
     int64_t* dwell;             // [n][barcode_num_events] or nullptr
     double* stats;              // [n][6] or nullptr
@@ -698,6 +699,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     const int tid = threadIdx.x;
     const int64_t read = blockIdx.x;
     if (read >= a.n) return;
+    if (a.retry_status && a.status[read] != a.retry_status) return;
     const int nb = c.barcode_num_events;
     double* fpt_out = a.fpt + read * nb;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);

@@ -74,6 +74,10 @@ struct ValArgs {
                                // set back once a candidate failed), fail code and statistics of THAT candidate instead of the last
     unsigned long long* next;  // work counter (zeroed before the launch): reads are handed out dynamically, because a
                                // read whose first poly(A) candidate fails costs several times a read that validates
+    // masked re-validation of the LLR fallback (llr_kernel.cuh; combined.py:222-290)
+    const uint8_t* todo;       // [n] or nullptr: only reads with todo[r] != 0 are validated, the others keep their results
+    int commit_on_success;     // != 0: results are written only when the validation succeeds (combined.py:288-289)
+    int src_tag;               // masked mode: written to the low two bits of info[.][3] with the results (LLR_SRC_*)
 };
 
 // numpy's pairwise summation (np.add.reduce on a contiguous 1-D array): a block of n <= 128 elements is
@@ -458,7 +462,12 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     __shared__ unsigned long long sh_next;
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh_next = atomicAdd(a.next, 1ULL);
+        if (tid == 0) {
+            unsigned long long nx = atomicAdd(a.next, 1ULL);
+            if (a.todo)
+                while (nx < (unsigned long long)a.n && !a.todo[nx]) nx = atomicAdd(a.next, 1ULL);
+            sh_next = nx;
+        }
         __syncthreads();
         const int64_t r = (int64_t)sh_next;
         if (r >= a.n) break;
@@ -695,6 +704,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             if (!val_in_range(ms, c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
         }
 
+        if (a.commit_on_success && code != VAL_OK) continue;
         if (a.parts) {   // calc_partitions_from_vals(signal, adapter_start, adapter_end, polya_end_best), combined.py:631-636
             double* po = a.parts + r * VAL_NPART;
             if (code == VAL_HAS_NAN) {
@@ -710,7 +720,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             a.info[r * 4 + 0] = code;
             a.info[r * 4 + 1] = checks;
             a.info[r * 4 + 2] = n_pores;
-            a.info[r * 4 + 3] = 0;
+            a.info[r * 4 + 3] = a.todo ? ((a.info[r * 4 + 3] & ~3) | a.src_tag) : 0;
             a.bounds[r * 3 + 0] = a0;
             a.bounds[r * 3 + 1] = a1;
             a.bounds[r * 3 + 2] = pe_best;

@@ -15,6 +15,7 @@ using namespace wdx;
 struct wdx_fp {
     FpConfig cfg{};
     int max_slice_len = 0;
+    int long_slice_len = 0;   // > max_slice_len: reads too long for the first pass are redone with this capacity
     int device = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr;       // kernels + result copies
@@ -234,6 +235,12 @@ int run(wdx_fp* f, const FpCall& c) {
         fa.cons_query = (const double*)f->cons_query.p;
         fa.cons = c.cons ? (cons_dev ? c.cons + (size_t)r0 * 3 : (int32_t*)f->cons[b].p) : nullptr;
         if ((rc = launch_fp(f, fa, st))) return rc;
+        if (f->max_slice_len > 0 && f->long_slice_len > cap) {   // the few reads longer than the first pass's capacity
+            FpArgs fl = fa;
+            fl.cap = std::min<int>(FP_MAX_LEN, (f->long_slice_len + 63) & ~63);
+            fl.retry_status = FP_FAIL_TOO_LONG;
+            if ((rc = launch_fp(f, fl, st))) return rc;
+        }
 
         int64_t* lab_d = nullptr;
         double *conf_d = nullptr, *prob_d = nullptr;
@@ -358,6 +365,14 @@ void wdx_fp_destroy(wdx_fp* f) {
     if (f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     delete f;
+}
+
+int wdx_fp_set_long_slice_len(wdx_fp* f, int32_t len) {
+    if (!f) return fail(WDX_ERR_INVALID, "NULL fingerprint handle");
+    if (len < 0 || len > FP_MAX_LEN) return fail(WDX_ERR_INVALID, "long_slice_len=%d outside [0,%d]", len, FP_MAX_LEN);
+    std::lock_guard<std::mutex> lk(f->mu);
+    f->long_slice_len = len;
+    return WDX_OK;
 }
 
 int wdx_fp_set_consensus(wdx_fp* f, const wdx_fp_consensus* cc) {

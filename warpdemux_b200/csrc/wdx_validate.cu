@@ -5,6 +5,7 @@
 #include <new>
 
 #include "validate_kernel.cuh"
+#include "llr_kernel.cuh"
 #include "wdx_internal.cuh"
 
 using namespace wdx;
@@ -17,6 +18,12 @@ struct wdx_validate {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     DevBuf sig, len, preds, success, info, bounds, vals, parts, scratch, counter;
+    // LLR fallback (wdx_validate_set_llr): proposed boundaries, mask, per-read median / MAD
+    bool llr_on = false;
+    LlrCfg llr{};
+    int llr_nmax = 0, llr_lt_max = 0;
+    size_t llr_smem = 0;
+    DevBuf preds2, todo, medmad;
     bool timing = false;
     bool verdict_only = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -136,7 +143,9 @@ int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate
 void wdx_validate_destroy(wdx_validate* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->parts, &h->scratch, &h->counter}) b->release();
+    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->parts, &h->scratch, &h->counter,
+                      &h->preds2, &h->todo, &h->medmad})
+        b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -146,6 +155,43 @@ void wdx_validate_destroy(wdx_validate* h) {
 int wdx_validate_set_verdict_only(wdx_validate* h, int on) {
     if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
     h->verdict_only = on != 0;
+    return WDX_OK;
+}
+
+int wdx_validate_set_llr(wdx_validate* h, const wdx_llr_config* cfg) {
+    if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!cfg) {
+        h->llr_on = false;
+        return WDX_OK;
+    }
+    if (cfg->downscale_factor < 1 || cfg->downscale_factor > 128 || cfg->max_obs_trace < 1 || cfg->min_obs_adapter < 0 ||
+        cfg->max_obs_adapter < 1 || cfg->adapter_peak_width < 0)
+        return fail(WDX_ERR_INVALID, "wdx_llr_config: sizes out of range (1 <= downscale_factor <= 128)");
+    LlrCfg& c = h->llr;
+    c.max_obs_trace = cfg->max_obs_trace;
+    c.min_obs_adapter = cfg->min_obs_adapter;
+    c.max_obs_adapter = cfg->max_obs_adapter;
+    c.factor = cfg->downscale_factor;
+    c.outlier_thresh = cfg->sig_norm_outlier_thresh;
+    c.peak_prominence = cfg->adapter_peak_prominence;
+    c.peak_rel_height = cfg->adapter_peak_rel_height;
+    c.peak_width = cfg->adapter_peak_width / cfg->downscale_factor;
+    c.fallback_to_llr = cfg->fallback_to_llr != 0;
+    c.fallback_short_reads = cfg->fallback_to_llr_short_reads != 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, llr_kernel));
+    const int room = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes - 1024;
+    h->llr_lt_max = cfg->max_obs_trace;
+    h->llr_nmax = (cfg->max_obs_trace + cfg->downscale_factor - 1) / cfg->downscale_factor + 8;
+    h->llr_smem = llr_smem_bytes(h->llr_nmax, h->llr_lt_max);
+    if ((int64_t)h->llr_smem > room)
+        return fail(WDX_ERR_UNSUPPORTED, "max_obs_trace = %d needs %zu B of shared memory, device allows %d", cfg->max_obs_trace, h->llr_smem, room);
+    CUDA_TRY(cudaFuncSetAttribute(llr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->llr_smem));
+    h->llr_on = c.fallback_to_llr || c.fallback_short_reads;
     return WDX_OK;
 }
 
@@ -253,17 +299,59 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
     a.parts = parts ? (part_dev ? parts : (double*)h->parts.p) : nullptr;
     a.scratch = (float*)h->scratch.p;
     a.verdict_only = h->verdict_only ? 1 : 0;
-    if ((rc = h->counter.reserve(16))) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, 8, st));
-    a.next = (unsigned long long*)h->counter.p;
+    if ((rc = h->counter.reserve(64))) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, 64, st));
+    unsigned long long* counters = (unsigned long long*)h->counter.p;
+    a.next = counters;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     validate_kernel<<<grid, FP_THREADS, smem, st>>>(a, h->cfg);
     CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    if (h->llr_on) {
+        // combined.py:222-290: the reads that failed get a poly(A) re-detection on the CNN's adapter end ("hail mary",
+        // result assigned unconditionally), then a full LLR detection (result assigned only when it validates)
+        if ((rc = h->preds2.reserve((size_t)n * ld * 8))) return rc;
+        if ((rc = h->todo.reserve((size_t)n))) return rc;
+        if ((rc = h->medmad.reserve((size_t)n * 8))) return rc;
+        LlrArgs la{};
+        la.signals = sig_d;
+        la.stride = stride;
+        la.full_len = len_d;
+        la.cnn_preds = preds_d;
+        la.ld = ld;
+        la.n = n;
+        la.success = a.success;
+        la.info = a.info;
+        la.preds_out = (int64_t*)h->preds2.p;
+        la.todo = (uint8_t*)h->todo.p;
+        la.medmad = (float*)h->medmad.p;
+        la.nmax = h->llr_nmax;
+        la.lt_max = h->llr_lt_max;
+        const int llr_grid = (int)std::min<int64_t>(n, (int64_t)2 * h->sm_count);
+        ValArgs b = a;
+        b.preds = (const int64_t*)h->preds2.p;
+        b.todo = (const uint8_t*)h->todo.p;
+        b.verdict_only = 0;   // single-candidate lists: nothing to cut short
+        for (int stage = 0; stage < 2; stage++) {
+            if (stage == 0 && !h->llr.fallback_short_reads) continue;
+            if (stage == 1 && !h->llr.fallback_to_llr) continue;
+            la.stage = stage;
+            la.next = counters + 1 + 2 * stage;
+            if (stage == 1 && !h->llr.fallback_short_reads) la.medmad = nullptr;   // stage 0 did not run: compute here
+            llr_kernel<<<llr_grid, FP_THREADS, h->llr_smem, st>>>(la, h->llr);
+            CUDA_TRY(cudaGetLastError());
+            b.next = counters + 2 + 2 * stage;
+            b.commit_on_success = stage == 1;
+            b.src_tag = stage == 0 ? LLR_SRC_HAIL_MARY : LLR_SRC_LLR;
+            validate_kernel<<<grid, FP_THREADS, smem, st>>>(b, h->cfg);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 2;
+        }
+    }
     if (h->timing) {
         CUDA_TRY(cudaEventRecord(h->ev1, st));
         h->timed = true;
     }
-    g_launches++;
     bool any_host = false;
     if (!suc_dev) { CUDA_TRY(cudaMemcpyAsync(success, a.success, (size_t)n, cudaMemcpyDeviceToHost, st)); any_host = true; }
     if (!info_dev) { CUDA_TRY(cudaMemcpyAsync(info, a.info, (size_t)n * 16, cudaMemcpyDeviceToHost, st)); any_host = true; }

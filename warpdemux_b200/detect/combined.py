@@ -3,13 +3,13 @@
 (include/wdx_b200.h: wdx_validate_*, wdx_cnn_*).
 
     validate_boundaries_batch(signals, full_signal_lens, preds, spc)   combined.py:409-683, whole minibatch
-    combined_detect_cnn(batch_of_signals, full_signal_lens, model, spc) combined.py:198-296 without the LLR
-                                                                        fallback -> List[DetectResults]
+    combined_detect_cnn(batch_of_signals, full_signal_lens, model, spc) combined.py:198-306 -> List[DetectResults]
 
-`spc` is the reference's `SigProcConfig` or anything with the same attributes (`ValidateConfig.from_spc`).
-Reads whose validation fails carry `needs_llr_fallback = True`: the reference re-detects those with its
-LLR detector on the CPU (combined.py:222-290); that stays with the caller.  All arithmetic is in
-warpdemux_b200/csrc/validate_kernel.cuh; there is no CPU implementation in this package.
+`spc` is the reference's `SigProcConfig` or anything with the same attributes (`ValidateConfig.from_spc`,
+`LLRConfig.from_spc`).  Reads whose CNN boundaries fail validation are re-detected on the device like the reference
+does on the CPU (combined.py:222-290: poly(A) re-detection on the CNN adapter end for short reads, then the full LLR
+detector; `wdx_validate_set_llr`, csrc/llr_kernel.cuh) when the config's `cnn_boundaries.fallback_to_llr*` flags ask
+for it.  All arithmetic is in warpdemux_b200/csrc/{validate,llr}_kernel.cuh; there is no CPU implementation in this package.
 """
 from __future__ import annotations
 
@@ -38,6 +38,8 @@ FAIL_REASONS = {
     7: "MVS polya check failed: ",
     8: "Median shift check failed",
     9: "Validate boundaries failed: Signal contains nan values",
+    10: "MAD normalization failed: scale is 0",       # normalize.py:55-58, raised inside the fallback branch
+    11: "LLR detection failed",
 }
 _CHECK_NAMES = ("mean", "var", "med", "range", "shift")
 HAS_NAN = 9
@@ -97,6 +99,43 @@ class ValidateConfig:
             detect_med_shift=bool(ms.detect_med_shift), med_shift_window=int(ms.med_shift_window),
             med_shift_range=_rng(ms.med_shift_range), primary_method=str(getattr(spc, "primary_method", "cnn")),
         )
+
+
+@dataclass
+class LLRConfig:
+    """The SigProcConfig fields the LLR fallback reads (WarpDemuX rna004_130bps@v1.0.toml over adapted @v0.2.4)."""
+    max_obs_trace: int = 10000
+    min_obs_adapter: int = 1000
+    max_obs_adapter: int = 6500
+    downscale_factor: int = 10
+    sig_norm_outlier_thresh: float = 5.0
+    adapter_peak_prominence: float = 1.0
+    adapter_peak_rel_height: float = 1.0
+    adapter_peak_width: int = 1000
+    fallback_to_llr: bool = True
+    fallback_to_llr_short_reads: bool = True
+
+    @classmethod
+    def from_spc(cls, spc) -> Optional["LLRConfig"]:
+        """None when the config has no llr_boundaries / cnn_boundaries sections to read the fallback from."""
+        if isinstance(spc, cls):
+            return spc
+        core, cb, lb = getattr(spc, "core", None), getattr(spc, "cnn_boundaries", None), getattr(spc, "llr_boundaries", None)
+        if core is None or cb is None or lb is None or not hasattr(cb, "fallback_to_llr"):
+            return None
+        return cls(max_obs_trace=int(core.max_obs_trace), min_obs_adapter=int(core.min_obs_adapter),
+                   max_obs_adapter=int(core.max_obs_adapter), downscale_factor=int(core.downscale_factor),
+                   sig_norm_outlier_thresh=float(core.sig_norm_outlier_thresh),
+                   adapter_peak_prominence=float(lb.adapter_peak_prominence), adapter_peak_rel_height=float(lb.adapter_peak_rel_height),
+                   adapter_peak_width=int(lb.adapter_peak_width), fallback_to_llr=bool(cb.fallback_to_llr),
+                   fallback_to_llr_short_reads=bool(getattr(cb, "fallback_to_llr_short_reads", False)))
+
+
+class _CLLRConfig(C.Structure):
+    _fields_ = [("max_obs_trace", C.c_int32), ("min_obs_adapter", C.c_int32), ("max_obs_adapter", C.c_int32),
+                ("downscale_factor", C.c_int32), ("sig_norm_outlier_thresh", C.c_double), ("adapter_peak_prominence", C.c_double),
+                ("adapter_peak_rel_height", C.c_double), ("adapter_peak_width", C.c_int32), ("fallback_to_llr", C.c_int32),
+                ("fallback_to_llr_short_reads", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _CValidateConfig(C.Structure):
@@ -201,12 +240,13 @@ class DetectResults:
 
     # extras of this package
     n_open_pores: int = 0
-    needs_llr_fallback: bool = False
+    needs_llr_fallback: bool = False     # validation failed and no device LLR fallback ran for this read
+    detect_source: int = 0               # 0 = CNN boundaries, 1 = hail-mary poly(A) re-detection, 2 = full LLR detection
 
     def to_dict(self):
         d = dict(self.__dict__)
-        d.pop("n_open_pores", None)
-        d.pop("needs_llr_fallback", None)
+        for k in ("n_open_pores", "needs_llr_fallback", "detect_source"):
+            d.pop(k, None)
         return d
 
     def update(self, d: dict):
@@ -223,6 +263,8 @@ class ValidationBatch:
     vals: np.ndarray           # float64 [n, N_VALS]
     kernel_ms: Optional[float] = field(default=None)
     parts: Optional[np.ndarray] = field(default=None)   # float64 [n, N_PART] partition statistics (PART_FIELDS), NaN = None
+    source: Optional[np.ndarray] = field(default=None)  # int32 [n] info[.][3]: bits 0-1 boundaries validated (0 cnn, 1 hail mary,
+                                                        # 2 llr), bit 2 hail mary ran, bit 3 full LLR ran
 
     def fail_reason(self, i: int) -> Optional[str]:
         return fail_reason(int(self.code[i]), int(self.checks[i]))
@@ -237,12 +279,19 @@ def fail_reason(code: int, checks: int = 0) -> Optional[str]:
 class Validator:
     """Device handle of the validation step (`wdx_validate*`), created lazily in the process that uses it."""
 
-    def __init__(self, spc=None, device: Optional[int] = None, verdict_only: bool = False):
+    def __init__(self, spc=None, device: Optional[int] = None, verdict_only: bool = False, llr="auto"):
         """verdict_only: stop at the first failing poly(A) candidate — same `success` and boundaries, fail reason and
-        mvs_* values of that candidate instead of the last one the reference goes on to evaluate."""
+        mvs_* values of that candidate instead of the last one the reference goes on to evaluate.
+        llr: an LLRConfig = re-detect the reads that fail on the device (combined.py:222-290); None = off; "auto" = what
+        `spc` says (off for a bare ValidateConfig)."""
         self.cfg = ValidateConfig.from_spc(spc) if spc is not None else ValidateConfig()
         self.device = device
         self.verdict_only = bool(verdict_only)
+        if isinstance(llr, str):
+            llr = LLRConfig.from_spc(spc) if (spc is not None and not isinstance(spc, ValidateConfig)) else None
+        if llr is not None and not (llr.fallback_to_llr or llr.fallback_to_llr_short_reads):
+            llr = None
+        self.llr = llr
         self._h = None
 
     def _handle(self):
@@ -252,6 +301,13 @@ class Validator:
             dev = default_device() if self.device is None else int(self.device)
             _lib.check(_lib.load().wdx_validate_create(C.byref(c), dev, C.byref(h)), "wdx_validate_create")
             _lib.check(_lib.load().wdx_validate_set_verdict_only(h, int(self.verdict_only)), "wdx_validate_set_verdict_only")
+            if self.llr is not None:
+                lc = _CLLRConfig()
+                for name, _t in _CLLRConfig._fields_:
+                    if name != "reserved":
+                        v = getattr(self.llr, name)
+                        setattr(lc, name, float(v) if isinstance(v, float) else int(v))
+                _lib.check(_lib.load().wdx_validate_set_llr(h, C.byref(lc)), "wdx_validate_set_llr")
             self._h = h
         return self._h
 
@@ -285,7 +341,8 @@ class Validator:
         parts = np.full((n, N_PART), np.nan) if partitions else None
         if n:
             self.run_raw(sig, n, stride, lens, pr, pr.shape[1], success, info, bounds, vals, parts=parts)
-        return ValidationBatch(success, info[:, 0].copy(), info[:, 1].copy(), info[:, 2].copy(), bounds, vals, parts=parts)
+        return ValidationBatch(success, info[:, 0].copy(), info[:, 1].copy(), info[:, 2].copy(), bounds, vals, parts=parts,
+                               source=info[:, 3].copy())
 
     def close(self):
         if self._h is not None:
@@ -299,11 +356,12 @@ class Validator:
             pass
 
     def __getstate__(self):
-        return {"cfg": self.cfg, "device": self.device, "verdict_only": self.verdict_only}
+        return {"cfg": self.cfg, "device": self.device, "verdict_only": self.verdict_only, "llr": self.llr}
 
     def __setstate__(self, st):
         self.cfg, self.device, self._h = st["cfg"], st["device"], None
         self.verdict_only = st.get("verdict_only", False)
+        self.llr = st.get("llr")
 
 
 def validate_boundaries_batch(batch_of_signals, full_signal_lens, preds, spc, validator: Optional[Validator] = None,
@@ -320,23 +378,26 @@ def _opt(x: float) -> Optional[float]:
     return None if x != x else float(x)
 
 
-def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, stride: int, primary_method: str = "cnn") -> List[DetectResults]:
+def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, stride: int, primary_method: str = "cnn",
+                      llr_ran: bool = False) -> List[DetectResults]:
     out = []
     for i in range(len(vb.success)):
         code = int(vb.code[i])
-        if code == HAS_NAN:     # the reference's validate_boundaries raises; combined_detect_cnn records str(e) (combined.py:293-294)
-            out.append(DetectResults(success=False, fail_reason=FAIL_REASONS[HAS_NAN]))
+        if code in (HAS_NAN, 10, 11):   # the reference raises; combined_detect_cnn records str(e) (combined.py:293-294)
+            out.append(DetectResults(success=False, fail_reason=FAIL_REASONS[code]))
             continue
+        src = int(vb.source[i]) & 3 if vb.source is not None else 0
         fl = int(full_signal_lens[i])
         v = vb.vals[i]
         d = DetectResults(
             success=bool(vb.success[i]), signal_len=fl, preloaded=min(fl, int(stride)),
             adapter_start=int(vb.bounds[i, 0]), adapter_end=int(vb.bounds[i, 1]), polya_end=int(vb.bounds[i, 2]),
-            polya_candidates=np.asarray(preds[i, 1:]).copy(),
+            polya_candidates=np.asarray(preds[i, 1:]).copy() if src == 0 else np.array([int(vb.bounds[i, 2])]),
             mvs_detect_mean_at_loc=_opt(v[5]), mvs_detect_var_at_loc=_opt(v[6]), mvs_detect_polya_med=_opt(v[7]),
             mvs_detect_polya_local_range=_opt(v[8]), mvs_detect_med_shift=_opt(v[9]), adapter_rna_median_shift=_opt(v[10]),
             real_adapter_mean_start=_opt(v[2]), real_adapter_mean_end=_opt(v[3]), real_adapter_local_range=_opt(v[4]),
-            n_open_pores=int(vb.n_open_pores[i]), fail_reason=vb.fail_reason(i), needs_llr_fallback=not bool(vb.success[i]),
+            n_open_pores=int(vb.n_open_pores[i]), fail_reason=vb.fail_reason(i),
+            needs_llr_fallback=not bool(vb.success[i]) and not llr_ran, detect_source=src,
             open_pores=np.array([int(vb.bounds[i, 0])]) if vb.n_open_pores[i] > 0 else None,
         )
         if vb.parts is not None:
@@ -345,17 +406,28 @@ def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, 
                     continue   # already set from the boundaries
                 val = None if x != x else (int(x) if name.endswith(("_start", "_len")) else float(x))
                 setattr(d, name, val)
-        setattr(d, f"{primary_method}_adapter_end", int(preds[i, 0]))
-        setattr(d, f"{primary_method}_polya_end", int(preds[i, 1]) if preds.shape[1] > 1 else 0)
+        if src == 0:
+            setattr(d, f"{primary_method}_adapter_end", int(preds[i, 0]))
+            setattr(d, f"{primary_method}_polya_end", int(preds[i, 1]) if preds.shape[1] > 1 else 0)
+        else:       # validated under spc_copy.primary_method = "llr" (combined.py:229-230, 638-641)
+            d.llr_adapter_end, d.llr_polya_end = int(vb.bounds[i, 1]), int(vb.bounds[i, 2])
         out.append(d)
     return out
 
 
 def combined_detect_cnn(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, model: "_cnn.BoundariesCNN", spc,
                         validator: Optional[Validator] = None, mode: Optional[str] = None, partitions: bool = True) -> List[DetectResults]:
-    """CNN boundaries + validation for a minibatch, both on the GPU (combined.py:198-221).  Reads with
-    `needs_llr_fallback` are the ones the reference retries with its CPU LLR detector (combined.py:222-290)."""
+    """CNN boundaries + validation + hail-mary / LLR re-detection of the reads that fail, for a minibatch, all on the GPU
+    (combined.py:198-306).  The LLR branch runs when `spc` carries the reference's `cnn_boundaries.fallback_to_llr*` and
+    `llr_boundaries` settings (or `validator` was built with an LLRConfig); otherwise failed reads come back with
+    `needs_llr_fallback = True`."""
     sig = _cnn._as_batch(batch_of_signals)
     preds = _cnn.cnn_detect(sig, model, spc.cnn_boundaries, spc.core, mode=mode)
-    vb = validate_boundaries_batch(sig, full_signal_lens, preds, spc, validator=validator, partitions=partitions)
-    return to_detect_results(vb, preds, full_signal_lens, sig.shape[1], str(getattr(spc, "primary_method", "cnn")))
+    v = validator or Validator(spc)
+    try:
+        vb = v.validate(sig, full_signal_lens, preds, partitions=partitions)
+    finally:
+        if validator is None:
+            v.close()
+    return to_detect_results(vb, preds, full_signal_lens, sig.shape[1], str(getattr(spc, "primary_method", "cnn")),
+                             llr_ran=v.llr is not None)

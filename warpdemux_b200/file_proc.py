@@ -10,10 +10,12 @@ One upload of the NaN-padded float32 minibatch (none when a CUDA tensor is given
 torch tensor), three kernel stages chained on ONE stream through device-resident buffers (boundaries, verdicts, fingerprints never visit the host), one download of the per-read results.
 The queues / counters of the reference worker are orchestration and stay with the caller.
 
-Reads whose CNN boundaries fail validation are the ones the reference retries with its CPU LLR detector
-(adapted/detect/combined.py:222-290).  `llr_fallback`, if given, is called for the minibatch rows of those
-reads between validation and fingerprinting (one host round trip of n verdict bytes); without it they are
-reported as failed with the validation's fail_reason and `needs_llr_fallback` set.
+Reads whose CNN boundaries fail validation are re-detected like the reference does (adapted/detect/combined.py:222-290:
+hail-mary poly(A) re-detection, then the LLR detector) — on the device, inside the validation call
+(`wdx_validate_set_llr`, csrc/llr_kernel.cuh), when the configuration asks for it (`cnn_boundaries.fallback_to_llr*`;
+`llr=` overrides).  `llr_fallback` is an optional host hook for the reads that still fail after that (or for all failed
+reads when the device fallback is off): it is called for their minibatch rows between validation and fingerprinting
+(one host round trip of n verdict bytes).
 """
 from __future__ import annotations
 
@@ -67,6 +69,8 @@ class MinibatchResult:
     llr_rescued: np.ndarray       # bool [n] boundaries came from the llr_fallback callback
     predictions: Optional[pd.DataFrame]   # reads with a fingerprint: '#read_id', predicted_barcode, confidence_score, pXX..
     fpt: Optional[np.ndarray] = None      # float64 [n, L] when asked for
+    detect_source: Optional[np.ndarray] = None   # int32 [n] bits 0-1: boundaries validated (0 CNN, 1 hail mary, 2 device LLR);
+                                                 # bit 2 / 3: the hail-mary / full LLR re-detection ran for this read
 
     @property
     def passed(self) -> np.ndarray:
@@ -87,7 +91,8 @@ class MinibatchDemuxer:
     def __init__(self, model_predict, model_detect: "_cnn.BoundariesCNN", spc=None, *, core=None, cnn_boundaries=None,
                  validate_config: Optional["_combined.ValidateConfig"] = None, fp_config: Optional[FingerprintConfig] = None,
                  device: Optional[int] = None, mode: Optional[str] = None, cnn_mode: Optional[str] = None,
-                 llr_fallback: Optional[Callable] = None, consensus_query=None, full_detect_report: bool = False):
+                 llr_fallback: Optional[Callable] = None, consensus_query=None, full_detect_report: bool = False,
+                 llr="auto"):
         import torch  # device memory and streams only
 
         self._torch = torch
@@ -102,7 +107,9 @@ class MinibatchDemuxer:
             FingerprintConfig.from_spc(spc, consensus_query) if spc is not None else FingerprintConfig())
         # the fingerprint stage needs the verdict and the boundaries only; full_detect_report=True also reproduces the
         # reference's fail_reason / mvs_* values of reads whose first poly(A) candidate fails (all candidates evaluated)
-        self.validator = _combined.Validator(vcfg, device=self.device, verdict_only=not full_detect_report)
+        if isinstance(llr, str):     # "auto": what the configuration says (the reference's defaults: both fallbacks on)
+            llr = _combined.LLRConfig.from_spc(spc) if spc is not None else None
+        self.validator = _combined.Validator(vcfg, device=self.device, verdict_only=not full_detect_report, llr=llr)
         if fcfg.max_slice_len <= 0:
             # a fixed shared-memory capacity keeps the fingerprint call free of its host synchronisation (the read-back of
             # the longest slice): the CNN's adapter end is < max_obs_adapter, the slice adds the padding on both sides
@@ -110,6 +117,11 @@ class MinibatchDemuxer:
 
             cap = (int(self.core.max_obs_adapter) + 2 * int(fcfg.padding) + 63) // 64 * 64
             fcfg = dataclasses.replace(fcfg, max_slice_len=min(cap, 16000))
+            if llr is not None:
+                # an LLR adapter end may lie anywhere below max_obs_trace: those few reads get a second, larger pass
+                cap2 = (int(llr.max_obs_trace) + int(fcfg.padding) + 63) // 64 * 64
+                if cap2 > fcfg.max_slice_len:
+                    fcfg = dataclasses.replace(fcfg, long_slice_len=min(cap2, 16000))
         self.fingerprinter = Fingerprinter(fcfg, device=self.device)
         self.mode = mode or model_predict.mode
         self.cnn_mode = cnn_mode or model_detect.mode
@@ -296,7 +308,7 @@ class MinibatchDemuxer:
             ids = np.asarray(rid if rid is not None else np.arange(job["n"]))[good]
             predictions = add_read_id_col_to_predictions(predictions, ids)
         return MinibatchResult(labels, conf, prob, status, h["suc"], h["info"][:, 0].copy(), h["info"][:, 1].copy(), h["bounds"],
-                               h["preds"], job["rescued"], predictions, h.get("fpt"))
+                               h["preds"], job["rescued"], predictions, h.get("fpt"), detect_source=h["info"][:, 3].copy())
 
     def _pinned(self, name, numel, dtype):
         t = self._pin.get(name)

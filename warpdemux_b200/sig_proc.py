@@ -91,6 +91,7 @@ class FingerprintConfig:
     num_events: int = 110
     barcode_num_events: int = 25      # events kept (barcode_num_events, or barcode_num_events[1] with a consensus)
     max_slice_len: int = 0
+    long_slice_len: int = 0           # > max_slice_len: second pass for the rare longer slices (wdx_fp_set_long_slice_len)
     # consensus-guided barcode refinement (segmentation.consensus_refinement; rna004_130bps@v1.0_tRNA.toml:13-29)
     consensus: Optional[Tuple[float, ...]] = None   # warpdemux._consensus.ALL[consensus_model]; None = off
     barcode_segm_events: int = 25                    # barcode_num_events[0]
@@ -201,6 +202,11 @@ class Fingerprinter:
             h = C.c_void_p()
             dev = default_device() if self.device is None else int(self.device)
             _lib.check(lib.wdx_fp_create(C.byref(cc), dev, C.byref(h)), "wdx_fp_create")
+            if c.long_slice_len:
+                rc = lib.wdx_fp_set_long_slice_len(h, int(c.long_slice_len))
+                if rc != 0:
+                    lib.wdx_fp_destroy(h)
+                    _lib.check(rc, "wdx_fp_set_long_slice_len")
             if c.consensus is not None:
                 q = np.ascontiguousarray(c.consensus, dtype=np.float64)
                 cs = _CConsensus(q.ctypes.data, q.size, c.barcode_segm_events, c.consensus_penalty, c.consensus_psi[0],

@@ -175,6 +175,12 @@ void wdx_fp_destroy(wdx_fp* f);
  * len > max_slice_len, reads that do not fit the first pass are redone by a second launch with this capacity
  * instead of failing with WDX_FP_FAIL_TOO_LONG; all other reads keep the occupancy of the small capacity.  0 = off. */
 int wdx_fp_set_long_slice_len(wdx_fp* f, int32_t len);
+/* Scalar promotion of the winsorisation bounds med -+ outlier_thresh * mad (warpdemux/sig_proc.py:421-431), where med and
+ * mad are np.float32 scalars and outlier_thresh a Python float.  on = 0 (default): numpy >= 2 semantics (NEP 50), every
+ * step in float32 — the numpy of this image, which the golden fixtures were written with.  on != 0: numpy < 2 semantics
+ * (the reference's environment.yml pins numpy 1.26.4): the bounds are formed in float64 and rounded to float32 once by
+ * np.clip.  The two differ by one float32 ulp of a bound for a fraction of the reads. */
+int wdx_fp_set_numpy1_promotion(wdx_fp* f, int on);
 
 /*   signals        [n, stride] float32 calibrated pA signal, one read per row (the reference's minibatch,
  *                  file_proc.py:333-354).  Rows may be NaN-padded at the end; the first NaN ends the read.

@@ -24,6 +24,7 @@ import sys
 import warnings
 
 import numpy as np
+import pandas  # noqa: F401  (before oracle/shim is on sys.path: pandas probes for the real `bottleneck`)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("WDX_REFERENCE", "/root/reference")
@@ -33,7 +34,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
 sys.path.insert(0, REF)
 sys.path.insert(0, os.path.join(REF, "warpdemux", "adapted"))
 
-MODELS = ["WDX4_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0"]
+MODELS = ["WDX4_rna004_v1_0", "WDX4b_rna004_v1_0", "WDX4c_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0"]   # every shipped DTW_SVM
+# WDX_GOLDEN_MODELS="a,b": (re)generate only those model / predict fixtures and leave everything else as it is
+ONLY = [m for m in os.environ.get("WDX_GOLDEN_MODELS", "").split(",") if m]
 
 
 def synth_fingerprints(sv: np.ndarray, n: int, seed: int = 0, sigma: float = 0.35) -> np.ndarray:
@@ -89,7 +92,10 @@ def main():
         "files": {},
     }
 
-    for name in MODELS:
+    if ONLY:
+        with open(os.path.join(GOLD, "MANIFEST.json")) as fh:
+            manifest = json.load(fh)
+    for name in (ONLY or MODELS):
         path = os.path.join(REF, "warpdemux", "models", "model_files", name + ".joblib")
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -113,6 +119,14 @@ def main():
             df_columns=np.array(list(df.columns)), df_values=df.to_numpy(dtype=np.float64),
         )
         print(name, "labels", dict(zip(*np.unique(y_pred, return_counts=True))))
+        if ONLY:
+            for rel in (os.path.join("models", name + ".npz"), f"predict_{name}.npz"):
+                p = os.path.join(GOLD, rel)
+                manifest["files"][rel] = {"sha256": hashlib.sha256(open(p, "rb").read()).hexdigest(), "bytes": os.path.getsize(p)}
+    if ONLY:
+        with open(os.path.join(GOLD, "MANIFEST.json"), "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True)
+        return
 
     # ---- fingerprints through the reference's sig_proc ------------------
     # The reference's config dataclasses use mutable defaults, which Python

@@ -291,7 +291,8 @@ def fingerprint_has_ties(signal: np.ndarray, adapter_start: int, adapter_end: in
 
 def fingerprint(signal: np.ndarray, adapter_start: int, adapter_end: int, *, padding: int = 100,
                 outlier_thresh: float = 5.0, min_obs_per_base: int = 6, running_stat_width: int = 12,
-                num_events: int = 110, barcode_num_events: int = 25, mutate: bool = False, stable_ties: bool = False):
+                num_events: int = 110, barcode_num_events: int = 25, mutate: bool = False, stable_ties: bool = False,
+                numpy1_promotion: bool = False):
     """`detect_results_to_fpt` (sig_proc.py:394-605) for the configuration every
     shipped DTW-SVM model uses (rna004_130bps@v1.0.toml: sig_extract
     normalization "none", segmentation normalization "mean",
@@ -313,7 +314,12 @@ def fingerprint(signal: np.ndarray, adapter_start: int, adapter_end: int, *, pad
         sig = sig.copy()
     med = np.nanmedian(sig)                                      # :421
     mad = np.nanmedian(np.abs(sig - med))                        # :422
-    np.clip(sig, med - outlier_thresh * mad, med + outlier_thresh * mad, out=sig)   # :426-431
+    if numpy1_promotion:   # numpy < 2 (the reference pins 1.26.4): np.float32 scalar * Python float -> float64; np.clip casts once
+        lo = np.float32(np.float64(med) - outlier_thresh * np.float64(mad))
+        hi = np.float32(np.float64(med) + outlier_thresh * np.float64(mad))
+        np.clip(sig, lo, hi, out=sig)
+    else:
+        np.clip(sig, med - outlier_thresh * mad, med + outlier_thresh * mad, out=sig)   # :426-431
     n = sig.size
     m_obs = min(min_obs_per_base, round(n / num_events / 2))     # :526-529
     w = min(running_stat_width, round(n / num_events))           # :530-533

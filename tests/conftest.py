@@ -33,7 +33,7 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
-MODEL_NAMES = ["WDX4_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0"]
+MODEL_NAMES = ["WDX4_rna004_v1_0", "WDX4b_rna004_v1_0", "WDX4c_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0"]   # every shipped DTW_SVM
 
 
 @pytest.fixture(scope="session")

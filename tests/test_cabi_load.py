@@ -74,3 +74,34 @@ def test_sharding_is_contiguous_and_complete():
         for g, (s, e) in enumerate(b):
             if e > s:
                 assert shard_of(s, n, w) == g and shard_of(e - 1, n, w) == g
+
+
+def test_model_unpickler_admits_exact_globals_only(tmp_path):
+    """load_reference_joblib resolves only an exact list of (module, name) pairs: a crafted file cannot reach a callable
+    inside an admitted package (numpy.testing._private.utils.runstring is exec), and the shipped models still load."""
+    import glob
+    import pickle
+
+    import numpy as np
+    import pytest
+
+    from warpdemux_b200 import model_io
+
+    class Evil:
+        def __reduce__(self):
+            import numpy.testing._private.utils as u
+
+            return (u.runstring, ("raise SystemExit('code ran')", {}))
+
+    for i, payload in enumerate((Evil(), np.testing.assert_equal)):
+        p = tmp_path / f"evil{i}.joblib"
+        p.write_bytes(pickle.dumps(payload, protocol=4))
+        with pytest.raises(ValueError, match="refusing to unpickle"):
+            model_io.load_reference_joblib(str(p))
+    for mod, name in model_io._ALLOWED_GLOBALS:
+        assert "testing" not in mod and not mod.startswith(("os", "subprocess", "sys"))
+    files = [f for f in glob.glob("/root/reference/warpdemux/models/model_files/WDX*_rna004_v1_0.joblib") if "tRNA" not in f]
+    for f in files:                       # build container only: the five shipped DTW_SVM files
+        m = model_io.load_reference_joblib(f)
+        g = model_io.load_npz(os.path.join(ROOT, "tests", "golden", "models", os.path.basename(f).replace(".joblib", ".npz")))
+        assert np.array_equal(m.sv, g.sv) and np.array_equal(m.dual_coef, g.dual_coef) and np.array_equal(m.thresholds, g.thresholds)

@@ -170,3 +170,34 @@ def test_pinned_host_signals_are_read_in_place(fp):
     fp.extract(work, a0, a1, clip_in_place=True)             # pageable: staged copy + copy back
     fp.extract(pinned.numpy(), a0, a1, clip_in_place=True)   # pinned: written through the mapping
     assert np.array_equal(pinned.numpy(), work, equal_nan=True)
+
+
+def test_numpy1_scalar_promotion_of_the_clip_bounds():
+    """The reference pins numpy 1.26.4, where med -+ thresh * mad (np.float32 scalars, Python float) is formed in float64
+    and rounded once; this image runs numpy 2 (every step float32), which the goldens were written with.  Both modes of the
+    kernel equal the oracle in the same mode.  On pA-scale signals the two roundings rarely differ (med and mad share the
+    ADC grid: 26 of the 3837 real reads of the 4000-read fixture get a 1-ulp different bound, none of these synthetic ones),
+    so the second half of the set is centred and rescaled to fill the float32 mantissas, where half of the reads differ."""
+    import dataclasses
+
+    from oracle import wdx_oracle as ORACLE
+    from warpdemux_b200.sig_proc import Fingerprinter, FingerprintConfig
+
+    sig, a0, a1 = synth_adapter_signals(400, seed=21, width=9000)
+    sig[200:] = (sig[200:] - np.float32(80)) * np.float32(0.737)
+    n = sig.shape[0]
+    res = {}
+    for legacy in (False, True):
+        f = Fingerprinter(dataclasses.replace(FingerprintConfig(), numpy1_promotion=legacy), device=0)
+        work = sig.copy()
+        b = f.extract(work, a0, a1, clip_in_place=True)
+        f.close()
+        for r in range(n):
+            st, fpt, dw, _ = ORACLE.fingerprint(sig[r], int(a0[r]), int(a1[r]), numpy1_promotion=legacy)
+            assert st == b.status[r], (legacy, r)
+            if st == 0:
+                assert np.array_equal(fpt, b.fpt[r]) and np.array_equal(dw, b.dwell[r]), (legacy, r)
+        res[legacy] = work
+    differ = (res[False] != res[True]) & ~np.isnan(res[False])
+    assert differ[200:].any(axis=1).sum() >= 20 and not differ[:200].any()
+    assert np.abs(res[False][differ] - res[True][differ]).max() < 1e-4          # one float32 ulp of a bound

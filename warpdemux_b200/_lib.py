@@ -22,7 +22,7 @@ EXPORTS = [
     "wdx_model_create", "wdx_model_destroy", "wdx_model_set_guard", "wdx_model_set_chunk_reads", "wdx_model_set_sv_splits",
     "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
     "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_model_last_kernel_ms_mode", "wdx_version",
-    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_extract_ex", "wdx_fp_set_consensus", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms", "wdx_fp_set_long_slice_len",
+    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_extract_ex", "wdx_fp_set_consensus", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms", "wdx_fp_set_long_slice_len", "wdx_fp_set_numpy1_promotion",
     "wdx_cnn_create", "wdx_cnn_destroy", "wdx_cnn_detect", "wdx_cnn_prepare", "wdx_cnn_predict", "wdx_cnn_score_len", "wdx_cnn_set_guard", "wdx_cnn_enable_timing",
     "wdx_cnn_last_kernel_ms",
     "wdx_validate_create", "wdx_validate_destroy", "wdx_validate_run", "wdx_validate_enable_timing", "wdx_validate_last_kernel_ms", "wdx_validate_set_verdict_only", "wdx_validate_run_ex", "wdx_calibrate_rows", "wdx_validate_set_llr",
@@ -42,6 +42,7 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
+        default_lib = "WDX_B200_LIB" not in os.environ
         if not os.path.exists(LIB_PATH):
             try:
                 from . import build as _build
@@ -52,6 +53,22 @@ def load():
                     f"libwdx_b200.so is not built ({LIB_PATH}) and could not be built here: {e}. "
                     "Run `python -m warpdemux_b200.build`. There is no CPU fallback."
                 ) from e
+        elif default_lib:
+            # a library older than its sources would silently run old kernels: rebuild where nvcc is at hand, else say so
+            from . import build as _build
+
+            try:
+                if _build.needs_build():
+                    try:
+                        _build._nvcc()
+                    except RuntimeError:
+                        import warnings
+
+                        warnings.warn(f"{LIB_PATH} is older than warpdemux_b200/csrc (no nvcc here to rebuild it)", RuntimeWarning)
+                    else:
+                        _build.build()
+            except OSError:
+                pass
         try:
             L = C.CDLL(LIB_PATH)
         except OSError as e:
@@ -92,6 +109,8 @@ def load():
         L.wdx_fp_extract_ex.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         L.wdx_fp_set_long_slice_len.restype = i32
         L.wdx_fp_set_long_slice_len.argtypes = [vp, C.c_int32]
+        L.wdx_fp_set_numpy1_promotion.restype = i32
+        L.wdx_fp_set_numpy1_promotion.argtypes = [vp, i32]
         L.wdx_fp_set_consensus.restype = i32
         L.wdx_fp_set_consensus.argtypes = [vp, vp]
         L.wdx_fp_predict.restype = i32

@@ -37,12 +37,25 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(LIBDIR, "sources.sha256")
+
+
+def _source_digest() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive copying the tree to another box)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + [os.environ.get("WDX_NVCC_EXTRA", "")]).encode())
+    for rel in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, rel), "rb") as fh:
+            h.update(rel.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -75,6 +88,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not ok:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libwdx_b200.so")
+    with open(STAMP, "w") as fh:
+        fh.write(_source_digest() + "\n")
     if verbose:
         print(log)
     return LIB

@@ -44,6 +44,9 @@ constexpr int FP_MAX_QUERY = 128;  // longest consensus query (4 rows per lane o
 struct FpConfig {
     int padding;             // sig_extract.padding
     float outlier_thresh;    // core.sig_norm_outlier_thresh (numpy 2: weak Python float * float32 -> float32)
+    double outlier_thresh_d; // the same value as given
+    int numpy1_promotion;    // winsorisation bounds as numpy < 2 forms them (the reference pins numpy 1.26.4): med -+ thresh * mad
+                             // in float64 (np.float32 scalar * Python float -> float64), cast to float32 ONCE by np.clip
     int min_obs_per_base;    // segmentation.min_obs_per_base
     int running_stat_width;  // segmentation.running_stat_width
     int num_events;          // segmentation.num_events
@@ -807,8 +810,16 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         med = block_median_f32(n, [&](int i) { return f32_key(sig[i]); }, s);
         mad = block_median_f32(n, [&](int i) { return f32_key(fabsf(__fsub_rn(sig[i], med))); }, s);
     }
-    const float tm = __fmul_rn(c.outlier_thresh, mad);
-    const float lo = __fsub_rn(med, tm), hi = __fadd_rn(med, tm);
+    float lo, hi;
+    if (c.numpy1_promotion) {
+        const double tmd = __dmul_rn(c.outlier_thresh_d, (double)mad);
+        lo = (float)__dsub_rn((double)med, tmd);
+        hi = (float)__dadd_rn((double)med, tmd);
+    } else {   // numpy >= 2 (NEP 50): every step in float32
+        const float tm = __fmul_rn(c.outlier_thresh, mad);
+        lo = __fsub_rn(med, tm);
+        hi = __fadd_rn(med, tm);
+    }
     __syncthreads();
     for (int i = tid; i < n; i += FP_THREADS) {
         float x = sig[i];

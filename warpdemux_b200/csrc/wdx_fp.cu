@@ -306,6 +306,8 @@ int wdx_fp_create(const wdx_fp_config* cfg, int device, wdx_fp** out) {
     f->device = device;
     f->cfg.padding = cfg->padding;
     f->cfg.outlier_thresh = (float)cfg->outlier_thresh;
+    f->cfg.outlier_thresh_d = cfg->outlier_thresh;
+    f->cfg.numpy1_promotion = 0;
     f->cfg.min_obs_per_base = cfg->min_obs_per_base;
     f->cfg.running_stat_width = cfg->running_stat_width;
     f->cfg.num_events = cfg->num_events;
@@ -365,6 +367,13 @@ void wdx_fp_destroy(wdx_fp* f) {
     if (f->stream) cudaStreamDestroy(f->stream);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     delete f;
+}
+
+int wdx_fp_set_numpy1_promotion(wdx_fp* f, int on) {
+    if (!f) return fail(WDX_ERR_INVALID, "NULL fingerprint handle");
+    std::lock_guard<std::mutex> lk(f->mu);
+    f->cfg.numpy1_promotion = on != 0;
+    return WDX_OK;
 }
 
 int wdx_fp_set_long_slice_len(wdx_fp* f, int32_t len) {

@@ -30,10 +30,8 @@ from .detect import cnn as _cnn
 from .detect import combined as _combined
 from .models.utils import predictions_to_df
 from .sharding import default_device
-from .sig_proc import Fingerprinter, FingerprintConfig
-
-FP_STATUS_REASON = {1: "segmentation failed", 2: "detection failed", 3: "segment normalization failed",
-                    4: "adapter slice too long", 5: "consensus query outlier"}
+from .sig_proc import FAIL_REASON as FP_STATUS_REASON   # one table, the reference's strings
+from .sig_proc import FP_NONFINITE, Fingerprinter, FingerprintConfig
 
 
 def add_read_id_col_to_predictions(predictions: pd.DataFrame, read_ids) -> pd.DataFrame:
@@ -248,7 +246,7 @@ class MinibatchDemuxer:
             # every per-read result lives in ONE device block (8-byte aligned sections) mirrored by one pinned block
             spec = [("preds", (n, ld), torch.int64), ("bounds", (n, 3), torch.int64), ("lab", (n,), torch.int64),
                     ("conf", (n,), torch.float64), ("prob", (n, k), torch.float64), ("info", (n, 4), torch.int32),
-                    ("status", (n,), torch.int32), ("suc", (n,), torch.uint8)]
+                    ("status", (n,), torch.int32), ("suc", (n,), torch.uint8), ("flags", (n,), torch.uint8)]
             if want_fpt:
                 spec.insert(0, ("fpt", (n, L), torch.float64))
             sizes = [(int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size() + 7) // 8 * 8 for _, shape, dt in spec]
@@ -264,6 +262,9 @@ class MinibatchDemuxer:
             d_preds, d_bounds, d_lab, d_conf, d_prob = views["preds"], views["bounds"], views["lab"], views["conf"], views["prob"]
             d_info, d_status, d_suc = views["info"], views["status"], views["suc"]
             d_fpt = views.get("fpt")
+            if d_fpt is None:     # kept on the device anyway: a guard-list overflow is repaired from it (_finalize)
+                d_fpt = g("fpt_dev", (n, L), torch.float64)
+            d_flags = views["flags"]
             d_a0, d_a1 = g("a0", (n,), torch.int64), g("a1", (n,), torch.int64)
             sp = st.cuda_stream
             rescued = np.zeros(n, dtype=bool)
@@ -288,18 +289,37 @@ class MinibatchDemuxer:
                 d_a0.copy_(d_bounds[:, 0])
                 d_a1.copy_(d_bounds[:, 1])
                 self.fingerprinter.predict_raw(dm, d_sig, n, stride, d_a0, d_a1, _lib.MODES[self.mode], d_lab, d_status,
-                                               conf=d_conf, prob=d_prob, fpt=d_fpt, detect_ok=d_suc, stream=sp)
+                                               conf=d_conf, prob=d_prob, fpt=d_fpt, detect_ok=d_suc, stream=sp, flags=d_flags)
             h_block[:max(total, 8)].copy_(d_block, non_blocking=True)      # one download, does not block the host
             host = hviews
             ev = torch.cuda.Event()
             ev.record(st)
-        job.update(host=host, ev_done=ev, rescued=rescued)
+        job.update(host=host, ev_done=ev, rescued=rescued, d_fpt=d_fpt, dev=views)
 
     def _finalize(self, job: dict, return_df: bool) -> MinibatchResult:
         """Phase 3 (host): wait for the download, copy out of the pinned blocks, build the DataFrame."""
         job["ev_done"].synchronize()
         h = {k: v.numpy().copy() for k, v in job["host"].items()}
         labels, conf, prob, status = h["lab"], h["conf"], h["prob"], h["status"]
+        flags = h["flags"]
+        over = np.flatnonzero((flags & _lib.FLAG_GUARD_OVERFLOW) != 0)
+        if over.size:
+            # GUARDED mode listed more boundary reads than its re-run list holds (max(4096, n/64) per launch): those kept
+            # their FAST_F32 results; redo them in EXACT_F64 from the fingerprints still on the device
+            torch = self._torch
+            sel = torch.from_numpy(over).to(self._dev())
+            with torch.cuda.stream(self._streams()[0]):
+                x = job["d_fpt"].index_select(0, sel).contiguous()
+                k = prob.shape[1]
+                lab2 = torch.empty(over.size, dtype=torch.int64, device=self._dev())
+                conf2 = torch.empty(over.size, dtype=torch.float64, device=self._dev())
+                prob2 = torch.empty((over.size, k), dtype=torch.float64, device=self._dev())
+                self.model_predict._device_model().predict_raw(x, over.size, _lib.WDX_F64, _lib.MODE_EXACT_F64, lab2, conf2, prob2,
+                                                               stream=self._streams()[0].cuda_stream)
+                labels[over], conf[over], prob[over] = lab2.cpu().numpy(), conf2.cpu().numpy(), prob2.cpu().numpy()
+        # a fingerprint whose decision values are not finite: the reference's predict raises (sklearn check_array); here the
+        # read is reported as failed with its own status instead of silently becoming "unclassified"
+        status[(status == 0) & ((flags & _lib.FLAG_NONFINITE) != 0)] = FP_NONFINITE
         predictions = None
         if return_df:
             good = status == 0

@@ -169,22 +169,38 @@ class _RefModelStub:
         self.__dict__.update(state)
 
 
-_ALLOWED_PREFIXES = (
-    "numpy",
-    "sklearn.svm",
-    "sklearn.utils",
-    "sklearn.base",
-    "joblib.numpy_pickle",
-    "collections",
-    "scipy.sparse",
-)
-_ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "slice", "complex", "bytearray", "object"}
+# Exact (module, name) pairs a DTW_SVM model file may reference.  The five shipped DTW_SVM files need only the first four
+# (recorded by instrumenting the unpickler); the rest are the data-only globals other numpy / sklearn versions emit for the
+# same objects (array reconstruction, scalars, sparse dual coefficients).  Whole packages are NOT admitted: `numpy` and
+# `sklearn.utils` contain callables that execute code given as a string (numpy.testing._private.utils.runstring, ...).
+_ALLOWED_GLOBALS = frozenset({
+    ("joblib.numpy_pickle", "NumpyArrayWrapper"),
+    ("numpy", "dtype"),
+    ("numpy", "ndarray"),
+    ("sklearn.svm._classes", "SVC"),
+    ("numpy.core.multiarray", "_reconstruct"),
+    ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "scalar"),
+    ("numpy", "float64"),
+    ("numpy", "int64"),
+    ("numpy", "int32"),
+    ("numpy", "bool_"),
+    ("scipy.sparse._csr", "csr_matrix"),
+    ("scipy.sparse._csr", "csr_array"),
+    ("scipy.sparse.csr", "csr_matrix"),
+    ("collections", "OrderedDict"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"),
+    ("builtins", "slice"), ("builtins", "complex"), ("builtins", "bytearray"), ("builtins", "object"),
+})
 
 
 def load_reference_joblib(path: str) -> ModelParams:
-    """Read a reference ``*.joblib`` model file with an allow-listing unpickler
-    (only numpy / sklearn.svm / joblib array globals; ``warpdemux.models.*``
-    classes are replaced by a state-holding stub) and convert it."""
+    """Read a reference ``*.joblib`` model file with an allow-listing unpickler: only the exact globals of
+    ``_ALLOWED_GLOBALS`` (array / dtype / SVC constructors, no package-wide admission) are resolved and
+    ``warpdemux.models.*`` classes are replaced by a state-holding stub; anything else raises.  That keeps a crafted
+    file from reaching an arbitrary callable through a REDUCE opcode; it is still the reference's trust model
+    (``joblib.load`` of files shipped with the package) — do not feed it files from untrusted sources."""
     import warnings
 
     from joblib import numpy_pickle as npk
@@ -193,9 +209,7 @@ def load_reference_joblib(path: str) -> ModelParams:
         def find_class(self, module, name):
             if module.startswith("warpdemux.models"):
                 return _RefModelStub
-            if module == "builtins" and name in _ALLOWED_BUILTINS:
-                return super().find_class(module, name)
-            if any(module == p or module.startswith(p + ".") for p in _ALLOWED_PREFIXES):
+            if (module, name) in _ALLOWED_GLOBALS:
                 return super().find_class(module, name)
             raise ValueError(f"refusing to unpickle global {module}.{name} from {path}")
 

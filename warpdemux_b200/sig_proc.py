@@ -22,12 +22,17 @@ from . import _lib
 from .sharding import default_device
 
 FP_OK, FP_FAIL_SEGMENTATION, FP_FAIL_DETECT, FP_FAIL_NORMALIZE, FP_FAIL_TOO_LONG, FP_FAIL_CONSENSUS = 0, 1, 2, 3, 4, 5
-_FAIL_REASON = {
+FP_NONFINITE = 6   # host-side status: fingerprint extracted, but a decision value was NaN / inf (sklearn raises there)
+# the ONE table of fail reasons of the fingerprint stage, in the reference's words (file_proc / detect mirrors use it too)
+FAIL_REASON = {
     FP_FAIL_CONSENSUS: "consensus query outlier",               # sig_proc.py:500-521
-    FP_FAIL_SEGMENTATION: "event segmentation failed",          # sig_proc.py:537-544
-    FP_FAIL_NORMALIZE: "segment normalization failed",          # sig_proc.py:553-560
-    FP_FAIL_TOO_LONG: "adapter slice exceeds the GPU shared-memory limit",
+    FP_FAIL_SEGMENTATION: "event segmentation failed",          # sig_proc.py:472-479, 537-544
+    FP_FAIL_DETECT: "detection failed",                         # sig_proc.py:400-407 reports detect_results.fail_reason instead
+    FP_FAIL_NORMALIZE: "segment normalization failed: Signal contains NaN values.",   # sig_proc.py:553-560 + :100-103
+    FP_FAIL_TOO_LONG: "adapter slice exceeds the GPU shared-memory limit",            # no counterpart in the reference
+    FP_NONFINITE: "Input contains NaN.",                        # sklearn's check_array inside SVC.predict_proba
 }
+_FAIL_REASON = FAIL_REASON
 
 
 # --------------------------------------------------------------------------
@@ -92,6 +97,7 @@ class FingerprintConfig:
     barcode_num_events: int = 25      # events kept (barcode_num_events, or barcode_num_events[1] with a consensus)
     max_slice_len: int = 0
     long_slice_len: int = 0           # > max_slice_len: second pass for the rare longer slices (wdx_fp_set_long_slice_len)
+    numpy1_promotion: bool = False    # winsorisation bounds as numpy < 2 forms them (wdx_fp_set_numpy1_promotion)
     # consensus-guided barcode refinement (segmentation.consensus_refinement; rna004_130bps@v1.0_tRNA.toml:13-29)
     consensus: Optional[Tuple[float, ...]] = None   # warpdemux._consensus.ALL[consensus_model]; None = off
     barcode_segm_events: int = 25                    # barcode_num_events[0]
@@ -202,6 +208,8 @@ class Fingerprinter:
             h = C.c_void_p()
             dev = default_device() if self.device is None else int(self.device)
             _lib.check(lib.wdx_fp_create(C.byref(cc), dev, C.byref(h)), "wdx_fp_create")
+            if c.numpy1_promotion:
+                _lib.check(lib.wdx_fp_set_numpy1_promotion(h, 1), "wdx_fp_set_numpy1_promotion")
             if c.long_slice_len:
                 rc = lib.wdx_fp_set_long_slice_len(h, int(c.long_slice_len))
                 if rc != 0:
@@ -307,10 +315,16 @@ class Fingerprinter:
         prob = np.full((n, k), np.nan)
         flags = np.zeros(n, dtype=np.uint8)
         status = np.zeros(n, dtype=np.int32)
-        fpt = np.full((n, self.config.barcode_num_events), np.nan) if want_fpt else None
+        fpt = np.full((n, self.config.barcode_num_events), np.nan)    # also the source of the overflow repair below
         if n:
             self.predict_raw(dm, signals, n, signals.shape[1], a0, a1, _lib.MODES[mode or model.mode], labels, status,
                              conf=conf, prob=prob, flags=flags, fpt=fpt, sig_len=sl, detect_ok=ok)
+            over = np.flatnonzero((flags & _lib.FLAG_GUARD_OVERFLOW) != 0)
+            if over.size:      # more guard-band reads than the re-run list of a launch holds: redo them in EXACT_F64
+                l2, p2, c2, _ = dm.predict(fpt[over], mode="exact")
+                labels[over], prob[over], conf[over] = l2, p2, c2
+            # non-finite decision values with a valid fingerprint: the reference's predict raises; report the read failed
+            status[(status == 0) & ((flags & _lib.FLAG_NONFINITE) != 0)] = FP_NONFINITE
         out = (labels, prob, conf, status)
         return out + (fpt,) if want_fpt else out
 

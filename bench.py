@@ -101,6 +101,69 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---- the reference's own Python (baseline/_ref: `pip install --target` of /root/reference, done by __graft_entry__.build()
+# in the build container; git-ignored, travels with the working tree) on top of the dtaidistance shim --------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+_REF_MODEL = None
+
+
+def reference_python_available():
+    return os.path.exists(os.path.join(REF_DIR, "warpdemux", "models", "dtw_svm.py")) and os.path.exists(
+        os.path.join(REF_DIR, "warpdemux", "models", "model_files", MODEL + ".joblib"))
+
+
+def _ref_init(model_name):
+    """Pool initialiser: import the UNMODIFIED reference package and load its own shipped model file."""
+    global _REF_MODEL
+    import warnings
+
+    import pandas  # noqa: F401  (before oracle/shim is importable: pandas probes for the real `bottleneck`)
+    for q in (REF_DIR, os.path.join(ROOT, "oracle", "shim"), ROOT):
+        if q not in sys.path:
+            sys.path.insert(0, q)
+    import joblib
+    from warpdemux.models.dtw_svm import DTW_SVM  # noqa: F401
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _REF_MODEL = joblib.load(os.path.join(REF_DIR, "warpdemux", "models", "model_files", model_name + ".joblib"))
+
+
+def _ref_predict(X):
+    """One production minibatch through the reference's stock call (file_proc.py:443-450)."""
+    df = _REF_MODEL.predict(X, nproc=1, return_df=True)
+    return df["predicted_barcode"].to_numpy()
+
+
+def reference_python_arm(params, workers, seconds_target, steps=1, warmup=0, want_outputs=False):
+    """`DTW_SVM.predict(X, nproc=1, return_df=True)` of the reference package, minibatches of <= 1000 reads over a
+    ProcessPoolExecutor(workers) — how production runs it (file_proc.py:1197-1245).  dtaidistance (absent third-party C)
+    is the shim backed by oracle/wdx_oracle.c; everything else (numpy/pandas glue, 104 MB scratch matrix per call,
+    float32 kernel, sklearn's libsvm predict_proba, thresholds) is the reference's own code."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    with ProcessPoolExecutor(workers, mp_context=mp.get_context("spawn"), initializer=_ref_init, initargs=(MODEL,)) as ex:
+        probe = synth_host(params, 32, seed=123)
+        list(ex.map(_ref_predict, [probe] * workers))                  # workers up, model loaded
+        t0 = time.perf_counter()
+        list(ex.map(_ref_predict, [probe] * workers))
+        per_read = (time.perf_counter() - t0) / 32
+        mb = int(max(16, min(1000, seconds_target / per_read)))
+        n = mb * workers
+        X = synth_host(params, n, seed=7)
+        chunks = [X[i:i + mb] for i in range(0, n, mb)]
+        for _ in range(warmup):
+            list(ex.map(_ref_predict, chunks))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = list(ex.map(_ref_predict, chunks))
+        dt = (time.perf_counter() - t0) / steps
+    if want_outputs:
+        return n / dt, n, dt, X, np.concatenate(res)
+    return n / dt, n, dt
+
+
 def cpu_arm(params, threads, seconds_target, steps=1, warmup=0, want_outputs=False):
     """The reference's CPU path as restated in oracle/ (kind "port"): production
     style minibatches of 1000 reads over `threads` single-threaded workers."""
@@ -297,6 +360,47 @@ def trna_stage(params_small, local, stream):
     return out
 
 
+_CHAIN_DATA = None
+
+
+def chain_dataset():
+    """Reads for the raw-signal measurements: the 4000 real reads of the reference's own test file
+    (test_data/demux/4000_rna004.pod5; first 11 500 samples each as int16 ADC + calibration, written by
+    oracle/make_golden_real4000.py into tests/golden/_local — git-ignored, travels with the working tree), where 4.95 % of
+    the reads leave the plain CNN path like in production.  Without that file: synthetic adapter + poly(A) + RNA rows
+    (scripts/validate_probe.py), on which the real-data CNN misplaces ~20 % of the poly(A) ends (far more fallback work).
+    Returns dict(kind, sig float32 [n, 11500] NaN padded, lens int32 [n] full read lengths, adc int16 [n, 11500], num int64 [n],
+    offset / scale float32 [n])."""
+    global _CHAIN_DATA
+    if _CHAIN_DATA is not None:
+        return _CHAIN_DATA
+    stride = 11500
+    local_file = os.path.join(ROOT, "tests", "golden", "_local", "real4000_adc_rows.npz")
+    if os.path.exists(local_file):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from wdx_testutil import real4000_rows
+
+        with np.load(os.path.join(ROOT, "tests", "golden", "real4000_rna004_WDX4.npz")) as z:
+            g = {k: z[k] for k in ("preload_size", "full_lengths", "subset", "calibration_offset", "calibration_scale")}
+        with np.load(local_file) as z:
+            full = {k: z[k] for k in z.files}
+        _, sig, adc, num = real4000_rows(g, full)
+        _CHAIN_DATA = dict(kind="real: the 4000 reads of test_data/demux/4000_rna004.pod5 (first 11 500 samples)", sig=sig,
+                           lens=g["full_lengths"].astype(np.int32), adc=adc, num=num, offset=g["calibration_offset"].astype(np.float32),
+                           scale=g["calibration_scale"].astype(np.float32))
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from validate_probe import synth_reads
+
+        sig, lens, _, _ = synth_reads(1024, stride)
+        cal_scale, cal_off = np.float32(0.1755), np.float32(-243.0)
+        adc = np.where(np.isnan(sig), 0, np.rint(np.nan_to_num(sig) / cal_scale - cal_off)).astype(np.int16)
+        n = sig.shape[0]
+        _CHAIN_DATA = dict(kind="synthetic adapter + poly(A) + RNA rows (tests/golden/_local absent)", sig=sig, lens=lens.astype(np.int32), adc=adc,
+                           num=np.minimum(lens, stride).astype(np.int64), offset=np.full(n, cal_off, np.float32), scale=np.full(n, cal_scale, np.float32))
+    return _CHAIN_DATA
+
+
 def raw_signal_chain(params_small, local):
     """The production minibatch step from raw signal (reference file_proc.py:380-455, BASELINE.json configs[0] shape) on
     synthetic reads (adapter + poly(A) plateau + RNA): boundary CNN -> boundary validation -> fingerprint -> DTW+SVC,
@@ -306,20 +410,22 @@ def raw_signal_chain(params_small, local):
 
     import torch
 
-    sys.path.insert(0, os.path.join(ROOT, "scripts"))
-    from validate_probe import synth_reads
     from warpdemux_b200.detect import cnn, combined
     from warpdemux_b200.file_proc import MinibatchDemuxer
     from warpdemux_b200.models.dtw_svm import DTW_SVM
 
-    base, reps, stride, k = 256, 32, 11500, 5          # 11 500 = the CLI's sig_preload_size for rna004 (parser.py:515)
-    sig, lens, _, _ = synth_reads(base, stride)
+    ds = chain_dataset()
+    stride, k = 11500, 5                               # 11 500 = the CLI's sig_preload_size for rna004 (parser.py:515)
+    sig, lens = ds["sig"], ds["lens"]
+    base = sig.shape[0]
+    reps = max(1, 8000 // base)
     n = base * reps
     h_sig = torch.from_numpy(np.tile(sig, (reps, 1))).pin_memory()
     h_len = np.tile(lens, reps)
     model = cnn.load_cnn_model(os.path.join(ROOT, "tests", "golden", "models", "cnn_rna004_130bps_v0.2.4.npz"), device=local)
     mdl = DTW_SVM(params_small, device=local, mode="guarded")
-    dmx = MinibatchDemuxer(mdl, model, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=k), device=local)
+    dmx = MinibatchDemuxer(mdl, model, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=k), device=local,
+                           llr=combined.LLRConfig())          # the reference's defaults: hail-mary + LLR fallback on (device)
     best = 1e30
     for it in range(4):
         t0 = time.perf_counter()
@@ -327,8 +433,9 @@ def raw_signal_chain(params_small, local):
         dt = time.perf_counter() - t0
         if it:
             best = min(best, dt)
-    out = {"workload": f"{n} synthetic reads x {stride} samples float32 (NaN-padded minibatch rows), rna004 configs, WDX4 model, "
-                       "CNN guarded, DTW guarded",
+    out = {"workload": f"{n} reads x {stride} samples float32 (NaN-padded minibatch rows), rna004 configs, WDX4 model, "
+                       "CNN guarded, LLR fallback on the device, DTW guarded",
+           "data": ds["kind"],
            "e2e": {"reads_per_s": n / best, "ms": best * 1e3, "h2d_bytes": int(h_sig.numel()) * 4,
                    "api": "MinibatchDemuxer.run(pinned host rows, full_lengths)"},
            "validated_fraction": float(r.detect_success.mean()), "fingerprint_ok_fraction": float((r.fp_status == 0).mean())}
@@ -343,16 +450,12 @@ def raw_signal_chain(params_small, local):
     out["e2e_pipelined_minibatches"] = {"reads_per_s": got / dt, "minibatch": mb, "minibatches": len(mbs), "ms_per_minibatch": dt / len(mbs) * 1e3,
                                         "api": "MinibatchDemuxer.stream(iter of (pinned rows, full_lengths)), results consumed in order"}
     # the same stream of minibatches as raw int16 ADC samples + calibration (AdcBatch: half the bytes over PCIe, pA rows
-    # made on the device by wdx_calibrate_rows); the ADC values are the synthetic pA rows quantised with a MinION-like
-    # calibration (scale 0.1755 pA per count, offset -243)
+    # made on the device by wdx_calibrate_rows)
     from warpdemux_b200.file_proc import AdcBatch
 
-    cal_scale, cal_off = np.float32(0.1755), np.float32(-243.0)
-    sig_np = h_sig.numpy()
-    adc = np.where(np.isnan(sig_np), 0, np.rint(np.nan_to_num(sig_np) / cal_scale - cal_off)).astype(np.int16)
-    h_adc = torch.from_numpy(adc).pin_memory()
-    num = np.minimum(h_len, stride).astype(np.int64)
-    offv, scv = np.full(n, cal_off, np.float32), np.full(n, cal_scale, np.float32)
+    h_adc = torch.from_numpy(np.tile(ds["adc"], (reps, 1))).pin_memory()
+    num = np.tile(ds["num"], reps)
+    offv, scv = np.tile(ds["offset"], reps), np.tile(ds["scale"], reps)
     mbs_adc = [(AdcBatch(h_adc[a:a + mb], num[a:a + mb], offv[a:a + mb], scv[a:a + mb]), h_len[a:a + mb]) for a in range(0, n - mb + 1, mb)] * 4
     for it in range(2):
         t0 = time.perf_counter()
@@ -390,6 +493,24 @@ def raw_signal_chain(params_small, local):
             if it and (res is None or sum(t) < sum(res)):
                 res = t
     alg = int(h_len.astype(np.int64).clip(max=stride).sum()) * 4
+    # the validation stage alone, without the LLR branch behind it
+    v0 = combined.Validator(combined.ValidateConfig(), device=local, verdict_only=True, llr=None)
+    best0 = None
+    with torch.cuda.stream(side):
+        for it in range(3):
+            ev[0].record()
+            v0.run_raw(d_sig, n, stride, d_len, d_preds, 1 + k, d_suc, d_info, d_bounds, None, stream=sp)
+            ev[1].record()
+            side.synchronize()
+            t0 = ev[0].elapsed_time(ev[1])
+            best0 = t0 if best0 is None or (it and t0 < best0) else best0
+        dmx.validator.run_raw(d_sig, n, stride, d_len, d_preds, 1 + k, d_suc, d_info, d_bounds, None, stream=sp)   # results of the chain again
+        side.synchronize()
+    v0.close()
+    src = d_info[:, 3].cpu().numpy()
+    out["llr_fallback"] = {"validate_without_llr_ms": best0, "llr_and_revalidation_ms": res[1] - best0,
+                           "reads_hail_mary_ran": int(((src & 4) != 0).sum()), "reads_llr_ran": int(((src & 8) != 0).sum()),
+                           "reads_rescued": int(((src & 3) != 0).sum())}
     out["device_resident"] = {"reads_per_s": n / (sum(res) * 1e-3), "cnn_ms": res[0], "validate_ms": res[1], "fingerprint_predict_ms": res[2],
                               "validate_reads_per_s": n / (res[1] * 1e-3),
                               "validate_roofline": {"bound": "hbm", "achieved": alg / (res[1] * 1e-3) / 1e9, "unit": "GB/s",
@@ -398,6 +519,7 @@ def raw_signal_chain(params_small, local):
     # boundaries the GPU CNN produced for them - the only stage of this chain whose CPU port is timed here (the
     # fingerprint and DTW/SVC stages have their own cpu_baseline entries above)
     try:
+        from oracle import wdx_oracle_llr as ol
         from oracle import wdx_oracle_validate as ov
 
         m_cpu = 96
@@ -405,15 +527,51 @@ def raw_signal_chain(params_small, local):
         t0 = time.perf_counter()
         o = ov.validate_batch(sig[:m_cpu], h_len[:m_cpu], pr, ov.ValidateConfig())
         dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        full_res = [ol.detect_one(sig[i], int(h_len[i]), pr[i], ol.LLRConfig(), ov.ValidateConfig())[0] for i in range(m_cpu)]
+        dt_llr = time.perf_counter() - t0
         gpu_ok = d_suc[:m_cpu].cpu().numpy()
+        gpu_b = d_bounds[:m_cpu].cpu().numpy()
         out["validate_cpu_baseline"] = {"value": m_cpu / dt, "unit": "reads/s", "cores": 1, "kind": "port",
                                         "sample": f"{m_cpu} of the same reads, oracle/wdx_oracle_validate.py (numpy), one process",
-                                        "gpu_verdict_mismatches_on_sample": int((o[0] != gpu_ok).sum())}
+                                        "with_llr_fallback_reads_per_s": m_cpu / dt_llr,
+                                        "gpu_verdict_mismatches_on_sample": int(sum(bool(r["success"]) != bool(g) for r, g in zip(full_res, gpu_ok))),
+                                        "gpu_boundary_mismatches_on_sample": int(sum(
+                                            bool(r["success"]) and (r["adapter_start"], r["adapter_end"], r["polya_end"]) != tuple(int(v) for v in b)
+                                            for r, b in zip(full_res, gpu_b)))}
     except Exception as e:  # noqa: BLE001
         out["validate_cpu_baseline"] = {"error": repr(e)}
     dmx.close()
     model.close()
     return out
+
+
+def raw_chain_stream_rank(local, minibatches=48, mb=1000, stride=11500):
+    """One rank's part of the multi-GPU raw-signal measurement: a stream of production minibatches (1000 reads x 11 500
+    int16 ADC samples + calibration, pinned host memory) through MinibatchDemuxer.stream on this rank's GPU.
+    Returns (reads, seconds) — the caller takes the max of the seconds over ranks."""
+    import torch
+
+    from warpdemux_b200 import model_io as _mio
+    from warpdemux_b200.detect import cnn, combined
+    from warpdemux_b200.file_proc import AdcBatch, MinibatchDemuxer
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    small = _mio.load_npz(os.path.join(ROOT, "tests", "golden", "models", "WDX4_rna004_v1_0.npz"))
+    ds = chain_dataset()
+    nb = ds["adc"].shape[0] // mb                      # distinct minibatches in the data set (4 for the real file)
+    h_adc = torch.from_numpy(ds["adc"][: nb * mb]).pin_memory()
+    md = cnn.load_cnn_model(os.path.join(ROOT, "tests", "golden", "models", "cnn_rna004_130bps_v0.2.4.npz"), device=local)
+    mp4 = DTW_SVM(small, device=local, mode="guarded")
+    dmx = MinibatchDemuxer(mp4, md, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=5), device=local,
+                           llr=combined.LLRConfig())
+    mbs = []
+    for i in range(minibatches):
+        a = (i % nb) * mb
+        mbs.append((AdcBatch(h_adc[a:a + mb], ds["num"][a:a + mb], ds["offset"][a:a + mb], ds["scale"][a:a + mb]), ds["lens"][a:a + mb]))
+    sum(int(r.labels.size) for r in dmx.stream(mbs[:8], return_df=False))
+    torch.cuda.synchronize()
+    return dmx, md, mbs
 
 
 def config2_wdx4(params4, local, stream, n):
@@ -467,6 +625,119 @@ def streaming_latency(mdl, params, batches=(1, 8, 64, 512), iters=300):
     return out
 
 
+def streaming_cadence(mdl, params, local, seconds=60.0, period=0.1, batches=(1, 8, 64, 512), raw_batch=512):
+    """BASELINE.json configs[4] as SURVEY.md 8(d) S5 defines it: every 100 ms (the cadence of
+    minknow_config/RNA2_seq_WDX_live_100ms.toml) a batch of b fingerprints of a 512-channel flow cell arrives, for
+    `seconds`; the GPU idles in between (clocks ramp down, L2 goes cold), unlike the back-to-back loop of
+    `streaming_latency`.  Each tick issues one DTW_SVM.predict per batch size on host arrays (H2D + kernels + D2H timed by
+    the host clock) and one MinibatchDemuxer.run on a raw-signal chunk batch of `raw_batch` reads x 11 500 samples
+    (CNN -> validation / LLR -> fingerprint -> DTW + SVC from pinned host rows)."""
+    import torch
+
+    from warpdemux_b200 import model_io as _mio
+    from warpdemux_b200.detect import cnn, combined
+    from warpdemux_b200.file_proc import MinibatchDemuxer
+    from warpdemux_b200.models.dtw_svm import DTW_SVM
+
+    X = synth_host(params, max(batches) * 8, seed=99)
+    ds = chain_dataset()
+    sig, lens = ds["sig"][:raw_batch], ds["lens"][:raw_batch]
+    h_sig = torch.from_numpy(np.ascontiguousarray(sig)).pin_memory()
+    small = _mio.load_npz(os.path.join(ROOT, "tests", "golden", "models", "WDX4_rna004_v1_0.npz"))
+    md = cnn.load_cnn_model(os.path.join(ROOT, "tests", "golden", "models", "cnn_rna004_130bps_v0.2.4.npz"), device=local)
+    mp4 = DTW_SVM(small, device=local, mode="guarded")
+    dmx = MinibatchDemuxer(mp4, md, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=5), device=local,
+                           llr=combined.LLRConfig())
+    for _ in range(3):
+        for b in batches:
+            mdl.predict(X[:b], nproc=1)
+        dmx.run(h_sig, lens, return_df=False)
+    ts = {str(b): [] for b in batches}
+    ts_raw = []
+    n_ticks = int(round(seconds / period))
+    t_start = time.perf_counter()
+    late = 0
+    for tick in range(n_ticks):
+        due = t_start + tick * period
+        now = time.perf_counter()
+        if now < due:
+            time.sleep(due - now)
+        elif now - due > period:
+            late += 1
+        for b in batches:
+            o = ((tick * 7) % 8) * b
+            t0 = time.perf_counter()
+            mdl.predict(X[o:o + b], nproc=1)
+            ts[str(b)].append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        dmx.run(h_sig, lens, return_df=False)
+        ts_raw.append(time.perf_counter() - t0)
+    out = {"cadence_ms": period * 1e3, "seconds": seconds, "ticks": n_ticks, "late_ticks": late, "model": MODEL, "mode": mdl.mode,
+           "api": "DTW_SVM.predict(host array) once per batch size per tick; the GPU idles between ticks"}
+    for b in batches:
+        a = np.array(ts[str(b)]) * 1e3
+        out[str(b)] = {"p50_ms": float(np.percentile(a, 50)), "p99_ms": float(np.percentile(a, 99)), "max_ms": float(a.max()), "samples": int(a.size)}
+    a = np.array(ts_raw) * 1e3
+    out["raw_chunk_batch"] = {"reads": raw_batch, "samples_per_read": 11500, "p50_ms": float(np.percentile(a, 50)), "p99_ms": float(np.percentile(a, 99)),
+                              "max_ms": float(a.max()), "samples": int(a.size), "model": "WDX4_rna004_v1_0", "data": ds["kind"],
+                              "api": "MinibatchDemuxer.run(pinned float32 rows, full_lengths), CNN guarded, LLR fallback on, DTW guarded"}
+    dmx.close()
+    md.close()
+    return out
+
+
+def label_identity_at_scale(dm, params, X_dev, n, lab_g, conf_g, flags_g, stream):
+    """SURVEY.md 8(c) acceptance on the headline configuration: the GUARDED results of the timed run against EXACT_F64 over
+    the whole step (every mismatch listed), and the FAST_F32 confidence error that the guard band has to cover."""
+    import torch
+    from warpdemux_b200 import _lib
+
+    k = params.k
+    lab_e = torch.empty(n, dtype=torch.int64, device="cuda")
+    conf_e = torch.empty(n, dtype=torch.float64, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dm.predict_raw(X_dev, n, _lib.WDX_F64, _lib.MODE_EXACT_F64, lab_e, conf_e, None, None, None, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_exact = e0.elapsed_time(e1)
+    lab_f = torch.empty(n, dtype=torch.int64, device="cuda")
+    conf_f = torch.empty(n, dtype=torch.float64, device="cuda")
+    dm.predict_raw(X_dev, n, _lib.WDX_F64, _lib.MODE_FAST_F32, lab_f, conf_f, None, None, None, stream=stream)
+    torch.cuda.synchronize()
+    thr = torch.from_numpy(np.asarray(params.thresholds, dtype=np.float64)).cuda()
+    lm = {int(v): i for i, v in enumerate(params.label_map)}
+
+    def listing(mask, lab_x, conf_x):
+        idx = torch.nonzero(mask).flatten()[:50].cpu().numpy()
+        return [{"read": int(i), "label": int(lab_x[i]), "label_exact": int(lab_e[i]), "conf": float(conf_x[i]), "conf_exact": float(conf_e[i])}
+                for i in idx]
+
+    d = (conf_f - conf_e).abs()
+    d = d[torch.isfinite(d)]
+    edges = [0.0, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 5e-5, 1e-4, 1e-3, 1.0]
+    hist = torch.histogram(d.cpu(), bins=torch.tensor(edges, dtype=torch.float64)).hist.to(torch.int64).tolist()
+    mism_g = lab_g != lab_e
+    mism_f = lab_f != lab_e
+    guard = 5e-5
+    out = {
+        "reads": int(n), "model": params.name if hasattr(params, "name") else MODEL,
+        "exact_reads_per_s": n / (ms_exact * 1e-3),
+        "label_mismatches_guarded_vs_exact": int(mism_g.sum().item()), "mismatch_rate_guarded": float(mism_g.sum().item()) / n,
+        "guarded_mismatch_list": listing(mism_g, lab_g, conf_g),
+        "label_mismatches_fast_vs_exact": int(mism_f.sum().item()), "fast_mismatch_list": listing(mism_f, lab_f, conf_f),
+        "max_abs_conf_fast_minus_exact": float(d.max().item()) if d.numel() else 0.0,
+        "abs_conf_error_histogram": {f"<={hi:g}": int(c) for hi, c in zip(edges[1:], hist)},
+        "guard_band": guard, "guard_over_max_error": guard / max(float(d.max().item()), 1e-300) if d.numel() else None,
+        "reads_recomputed_in_exact": int(((flags_g & 2) != 0).sum().item()),
+        "guard_overflow_flags": int(((flags_g & 4) != 0).sum().item()),
+        "nonfinite_flags": int(((flags_g & 1) != 0).sum().item()),
+        "max_abs_conf_guarded_minus_exact_on_recomputed": float((conf_g - conf_e)[(flags_g & 2) != 0].abs().max().item())
+        if bool(((flags_g & 2) != 0).any()) else 0.0,     # same arithmetic, other SV-range split: differs in summation order only
+    }
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -475,7 +746,19 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     total_budget = 120.0
     per_step = max(2.0, min(20.0, total_budget / max(1, args.steps + args.warmup)))
-    rps, n, dt = cpu_arm(params, threads, per_step, steps=args.steps, warmup=min(args.warmup, 1))
+    kind, how = "port", ("minibatches of <=1000 over %d single-threaded workers (oracle/wdx_oracle.c: restated dtaidistance DTW + "
+                         "libsvm predict_proba)" % threads)
+    if reference_python_available() and not args.port_only:
+        try:
+            rps, n, dt = reference_python_arm(params, threads, per_step, steps=args.steps, warmup=min(args.warmup, 1))
+            kind = "reference"
+            how = ("the reference package's own DTW_SVM.predict(X, nproc=1, return_df=True) (baseline/_ref, unmodified) in "
+                   "minibatches of <=1000 over a ProcessPoolExecutor(%d); dtaidistance = shim on the restated C (oracle/wdx_oracle.c)" % threads)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"reference python arm failed ({e!r}); timing the oracle port instead\n")
+            rps, n, dt = cpu_arm(params, threads, per_step, steps=args.steps, warmup=min(args.warmup, 1))
+    else:
+        rps, n, dt = cpu_arm(params, threads, per_step, steps=args.steps, warmup=min(args.warmup, 1))
     cells = params.n_sv * params.band_cells()
     line = {
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "reads/s", "n_gpus": args.gpus,
@@ -484,9 +767,8 @@ def run_reference(args):
         "config": {"workload": f"{MODEL} on synthetic S1 fingerprints; bounded sample of {n} reads per step",
                    "model": MODEL, "n_sv": params.n_sv, "classes": params.k, "L": params.L, "window": params.window},
         "gcups": rps * cells / 1e9,
-        "cpu_baseline": {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} S1 reads/step, minibatches of <=1000 over {threads} single-threaded workers "
-                                   "(oracle/wdx_oracle.c: restated dtaidistance DTW + libsvm predict_proba)"},
+        "cpu_baseline": {"value": rps, "unit": "reads/s", "cores": threads, "kind": kind,
+                         "sample": f"{n} S1 reads/step, {how}"},
         "e2e": {"value": rps, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -556,6 +838,7 @@ def run_ours(args):
     lab_d = torch.empty(n, dtype=torch.int64, device="cuda")
     conf_d = torch.empty(n, dtype=torch.float64, device="cuda")
     prob_d = torch.empty((n, k), dtype=torch.float64, device="cuda")
+    flags_d = torch.zeros(n, dtype=torch.uint8, device="cuda")
 
     dm = DeviceModel(params, local)
     dm.enable_timing(True)
@@ -563,7 +846,7 @@ def run_ours(args):
     MODE = _lib.MODES[mode]
 
     def step_device():
-        dm.predict_raw(X_dev, n, _lib.WDX_F64, MODE, lab_d, conf_d, prob_d, None, None, stream=stream)
+        dm.predict_raw(X_dev, n, _lib.WDX_F64, MODE, lab_d, conf_d, prob_d, flags_d, None, stream=stream)
 
     # ---- value: inputs resident in HBM, CUDA events on the launch stream ----
     for _ in range(args.warmup):
@@ -614,6 +897,69 @@ def run_ours(args):
     barrier()
     e2e_value = n_total / e2e_s
     e2e_match = bool(np.array_equal(y_pred, labels_host))
+    # guard bookkeeping of the timed device run (flags were written inside the timed region)
+    n_overflow = int(sum_over_ranks(float(((flags_d & 4) != 0).sum().item())))
+    n_recomputed = int(sum_over_ranks(float(((flags_d & 2) != 0).sum().item())))
+
+    # ---- e2e from PAGEABLE host memory: what the reference's call sites pass (np.vstack(fpts), file_proc.py:443-450) ----
+    X_page = np.array(X_host, copy=True)          # ordinary numpy allocation, not pinned
+    mdl.predict(X_page[: min(n, 1 << 18)], nproc=1)
+    barrier()
+    t0 = time.perf_counter()
+    yp2, _ = mdl.predict(X_page, nproc=1, return_df=False)
+    torch.cuda.synchronize()
+    e2e_page_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_pageable = {"value": n_total / e2e_page_s, "unit": "reads/s", "labels_equal_device_run": bool(np.array_equal(yp2, labels_host)),
+                    "api": "DTW_SVM.predict(X, nproc=1) with X an ordinary (pageable) numpy array, as the reference's workers pass it"}
+    del X_page
+
+    # ---- N > 1: the whole sharded call incl. the host-side label gather north_star names (sharding.predict_sharded) ----
+    sharded = None
+    if world > 1:
+        from warpdemux_b200.sharding import predict_sharded
+
+        def fn(x):
+            yp, pr = mdl.predict(x, nproc=1, return_df=False)
+            return yp, pr.max(axis=1)              # label + top probability per read: what a caller keeps per read
+
+        predict_sharded(fn, X_host[: 1 << 16], x_is_local_shard=True, dst=0)
+        barrier()
+        t0 = time.perf_counter()
+        got = predict_sharded(fn, X_host, x_is_local_shard=True, dst=0)
+        torch.cuda.synchronize()
+        sh_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        sharded = {"value": n_total / sh_s, "unit": "reads/s", "seconds": sh_s,
+                   "api": "sharding.predict_sharded(lambda x: DTW_SVM.predict(x), this rank's contiguous shard, dst=0): every rank "
+                          "classifies its shard from pinned host memory, rank 0 receives all labels + top probabilities in read order",
+                   "gathered_bytes": int(n_total * 16)}
+        if rank == 0:
+            sharded["gathered_reads"] = int(got[0].shape[0])
+            sharded["rank0_shard_equals_device_run"] = bool(np.array_equal(got[0][:n], labels_host))
+
+    # ---- raw-signal chain at N GPUs: where host memory / PCIe could break the linear scaling of the fingerprint path ----
+    chain = None
+    if args.chain_stream:
+        try:
+            dmx_c, md_c, mbs_c = raw_chain_stream_rank(local)
+            barrier()
+            t0 = time.perf_counter()
+            got_c = sum(int(r.labels.size) for r in dmx_c.stream(mbs_c, return_df=False))
+            torch.cuda.synchronize()
+            dt_c = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            tot_c = sum_over_ranks(float(got_c))
+            chain = {"value": tot_c / dt_c, "unit": "reads/s", "n_gpus": world, "reads": int(tot_c), "seconds": dt_c,
+                     "h2d_bytes_per_read": 11500 * 2, "host_to_device_gb_per_s": tot_c * 11500 * 2 / dt_c / 1e9,
+                     "data": chain_dataset()["kind"],
+                     "api": "MinibatchDemuxer.stream(AdcBatch minibatches of 1000 reads x 11 500 int16 samples from pinned host memory) on every "
+                            "rank concurrently: calibration -> CNN -> validation / LLR -> fingerprint -> DTW + SVC (WDX4, guarded); "
+                            "wall clock, max over ranks"}
+            dmx_c.close()
+            md_c.close()
+        except Exception as e:  # noqa: BLE001
+            chain = {"error": repr(e)}
 
     # ---- other arithmetic modes on a smaller batch (context for `value`) ------
     modes = {}
@@ -635,13 +981,53 @@ def run_ours(args):
     extras = {}
     if rank == 0 and world == 1 and args.extras:
         try:
+            extras["label_identity_at_scale"] = label_identity_at_scale(dm, params, X_dev, n, lab_d, conf_d, flags_d, stream)
+        except Exception as e:  # noqa: BLE001
+            extras["label_identity_at_scale"] = {"error": repr(e)}
+        try:
             extras["streaming_latency_ms"] = streaming_latency(mdl, params)
         except Exception as e:  # noqa: BLE001
             extras["streaming_latency_ms"] = {"error": repr(e)}
+        if args.cadence_seconds > 0:
+            try:
+                extras["streaming_100ms_cadence"] = streaming_cadence(mdl, params, local, seconds=args.cadence_seconds)
+            except Exception as e:  # noqa: BLE001
+                extras["streaming_100ms_cadence"] = {"error": repr(e)}
+        if args.single_call_reads > 0:
+            try:   # BASELINE.json configs[2]'s whole 100 M-read set given to ONE GPU in ONE wdx_predict call (20 GB of input)
+                del X_dev, prob_d
+                X_dev = prob_d = None
+                torch.cuda.empty_cache()
+                nb = args.single_call_reads
+                gen = torch.Generator(device="cuda").manual_seed(2024)
+                sv_d = torch.from_numpy(params.sv).cuda()
+                Xb = torch.empty((nb, params.L), dtype=torch.float64, device="cuda")
+                for r0 in range(0, nb, 1 << 22):
+                    r1 = min(nb, r0 + (1 << 22))
+                    ix = torch.randint(0, params.n_sv, (r1 - r0,), device="cuda", generator=gen)
+                    Xb[r0:r1] = sv_d[ix] + SIGMA * torch.randn((r1 - r0, params.L), dtype=torch.float64, device="cuda", generator=gen)
+                labb = torch.empty(nb, dtype=torch.int64, device="cuda")
+                flb = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+                dm.predict_raw(Xb, 1 << 20, _lib.WDX_F64, MODE, labb, None, None, flb, None, stream=stream)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                dm.predict_raw(Xb, nb, _lib.WDX_F64, MODE, labb, None, None, flb, None, stream=stream)
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b)
+                extras["single_gpu_100M_call"] = {"reads": nb, "seconds": ms * 1e-3, "reads_per_s": nb / (ms * 1e-3), "mode": mode,
+                                                  "input_gb": nb * params.L * 8 / 1e9, "guard_overflow_flags": int(((flb & 4) != 0).sum().item()),
+                                                  "data": "S1 generated on the device (torch Philox, seed 2024); one wdx_predict call, device buffers",
+                                                  "label_histogram_first_1M": {str(int(u)): int(c) for u, c in zip(*np.unique(labb[: 1 << 20].cpu().numpy(), return_counts=True))}}
+                del Xb, labb, flb
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                extras["single_gpu_100M_call"] = {"error": repr(e)}
         try:
             from warpdemux_b200 import model_io as _mio
             small = _mio.load_npz(os.path.join(ROOT, "tests", "golden", "models", "WDX4_rna004_v1_0.npz"))
-            del X_dev, prob_d  # make room
+            X_dev = prob_d = None  # make room
             torch.cuda.empty_cache()
             extras["wdx4_10M_exact_vs_fast"] = config2_wdx4(small, local, stream, args.config2_reads)
         except Exception as e:  # noqa: BLE001
@@ -700,17 +1086,29 @@ def run_ours(args):
         "kernel_share_of_step": kms / ms_per_step,
         "all_fused_launches_ms_per_step": kms_all, "all_fused_launches_per_step": kl_all,
         "traffic": None,
-        "hbm_algorithmic_bytes_per_launch": n * (params.L * 8 + 2 * (k - 1) * k * 8),
     }
+    # HBM side of the same kernel (it is compute-bound; this shows no re-reads are wasted).  Algorithmic bytes per read:
+    # the float64 fingerprint in, the k(k-1)/2 one-vs-one decision sums out (fused kernel) and back in (finishing
+    # kernel), the per-read results out (label, confidence, k probabilities, flag) - DESIGN.md 4.1.
+    n_pairs = k * (k - 1) // 2
+    alg_per_read = params.L * 8 + n_pairs * 8      # the fused kernel itself: fingerprint in, decision sums out
+    reads_per_launch = min(n, 1 << 22)          # wdx_model_set_chunk_reads default: 2^22 reads per fused launch
+    roofline["hbm_algorithmic_bytes_per_read"] = alg_per_read
+    roofline["path_hbm_algorithmic_bytes_per_read"] = params.L * 8 + 2 * n_pairs * 8 + (8 + 8 + 8 * k + 1)   # + finishing kernel
+    roofline["reads_per_launch"] = reads_per_launch
+    roofline["hbm_algorithmic_bytes_per_launch"] = alg_per_read * reads_per_launch
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
-        roofline["traffic"] = prof.get("dram_bytes_per_launch")
-        roofline["traffic_note"] = prof.get("note")
+        if prof.get("reads_in_profiled_launch") == reads_per_launch and prof.get("mode") == mode and prof.get("model") == MODEL:
+            roofline["traffic"] = prof.get("dram_bytes_per_launch")            # same variant, same launch size: comparable as printed
+        roofline["traffic_bytes_per_read"] = prof.get("dram_bytes_per_read")
+        roofline["traffic_profile"] = {k2: prof.get(k2) for k2 in ("kernel", "reads_in_profiled_launch", "mode", "model", "source", "note")}
     except Exception:  # noqa: BLE001
         pass
 
     # ---- CPU baseline on this box's host cores (bounded sample) ------------------
     cpu = None
+    cpu_ref_py = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rps, ns, dt, Xc, (cpu_pred, cpu_prob, cpu_conf) = cpu_arm(params, threads, 15.0, want_outputs=True)
@@ -721,6 +1119,25 @@ def run_ours(args):
                          f"workers, {dt:.1f} s (oracle/wdx_oracle.c)",
                "gpu_label_mismatches_on_sample": int((gpu_pred != cpu_pred).sum()),
                "gpu_max_abs_prob_diff_on_sample": float(np.abs(gpu_prob - cpu_prob).max())}
+        if reference_python_available():
+            # the reference's own Python on the shim, one worker and all cores, bounded samples
+            try:
+                r1, n1, d1 = reference_python_arm(params, 1, 4.0)
+                ra, na, da, Xr, ref_pred = reference_python_arm(params, threads, 6.0, want_outputs=True)
+                g_pred, _ = mdl.predict(Xr, nproc=1)
+                cpu_ref_py = {"unit": "reads/s", "kind": "reference",
+                              "n1": {"value": r1, "cores": 1, "sample": f"{n1} S1 reads, {d1:.1f} s"},
+                              "all_cores": {"value": ra, "cores": threads, "sample": f"{na} S1 reads in minibatches of {na // threads} over a "
+                                                                                        f"ProcessPoolExecutor({threads}), {da:.1f} s"},
+                              "gpu_label_mismatches_on_sample": int((g_pred != ref_pred).sum()),
+                              "what": "the unmodified reference package (baseline/_ref, pip --target install of /root/reference): "
+                                      "DTW_SVM.predict(X, nproc=1, return_df=True) -> parallel_distances.distance_matrix_to -> "
+                                      "dtaidistance SHIM on the restated C (oracle/wdx_oracle.c) -> pdist_kernel -> sklearn "
+                                      "SVC.predict_proba -> process_probs -> predictions_to_df"}
+            except Exception as e:  # noqa: BLE001
+                cpu_ref_py = {"error": repr(e)}
+        else:
+            cpu_ref_py = {"unavailable": "baseline/_ref not present (install: __graft_entry__.build() where /root/reference exists)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -738,9 +1155,16 @@ def run_ours(args):
                 "api": "DTW_SVM.predict(X_host, nproc=1) -> (y_pred, y_prob); pinned host input, "
                        "host perf_counter around the blocking calls, max over ranks",
                 "labels_equal_device_run": e2e_match},
+        "e2e_pageable": e2e_pageable,
+        "e2e_sharded_with_label_gather": sharded,
+        "raw_signal_chain_stream": chain,
+        "guard": {"mode": mode, "band": 5e-5, "reads_recomputed_in_exact_per_step": n_recomputed, "guard_overflow_flags_per_step": n_overflow,
+                  "note": "flags written inside the timed region; an overflow (more boundary reads than the re-run list of a launch "
+                          "holds) would leave FAST_F32 labels on the flagged reads"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "cpu_baseline_reference_python": cpu_ref_py,
         "modes": modes,
         "label_histogram": {str(int(a)): int(b) for a, b in zip(*np.unique(label_sample, return_counts=True))},
     }
@@ -762,6 +1186,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-modes", dest="extra_modes", action="store_false")
     ap.add_argument("--config2-reads", type=int, default=10_000_000)
+    ap.add_argument("--cadence-seconds", type=float, default=60.0, help="length of the 100 ms-cadence streaming measurement (0 = skip)")
+    ap.add_argument("--single-call-reads", type=int, default=100_000_000, help="reads of the one-call single-GPU run (0 = skip)")
+    ap.add_argument("--no-chain-stream", dest="chain_stream", action="store_false",
+                    help="skip the raw-signal chain stream measured on every rank (multi-GPU scaling of the ADC -> calls path)")
+    ap.add_argument("--port-only", action="store_true", help="reference arm: time the C port even if baseline/_ref is present")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the secondary measurements (streaming latency, fingerprint stage)")
     args = ap.parse_args()

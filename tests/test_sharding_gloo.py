@@ -41,6 +41,10 @@ def _worker(rank, world, port, n, q):
     full = predict_sharded(fn, X)
     lo, hi = shard_bounds(n, world)[rank]
     local = predict_sharded(fn, X[lo:hi], x_is_local_shard=True)
+    root_only = predict_sharded(fn, X, dst=0)              # the main process's label gather: rank 0 alone receives
+    assert (root_only is None) == (rank != 0)
+    if rank == 0:
+        assert all(np.array_equal(a, b) for a, b in zip(root_only, full))
     q.put((rank, calls, full[0], full[1], local[0]))
     dist.barrier()
     dist.destroy_process_group()
@@ -81,3 +85,33 @@ def test_predict_sharded_without_process_group(models):
     parts = [(np.array([1, 2]), np.zeros((2, 3))), (np.array([3]), np.ones((1, 3)))]
     a, b = gather_in_shard_order(parts)
     assert a.tolist() == [1, 2, 3] and b.shape == (3, 3)
+
+
+def _which_device(_):
+    from warpdemux_b200.sharding import default_device
+
+    return default_device()
+
+
+def test_pool_workers_spread_over_the_visible_devices(monkeypatch):
+    """The reference's ProcessPoolExecutor forks its workers with ONE environment (file_proc.py:1197-1245): handles
+    created without an explicit device are assigned round-robin by pool index; explicit settings win."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    from warpdemux_b200 import sharding
+
+    for var in ("WDX_B200_DEVICE", "LOCAL_RANK"):
+        monkeypatch.delenv(var, raising=False)
+    monkeypatch.setenv("WDX_B200_DEVICES", "0,1,2,3")
+    assert sharding.default_device() == 0 and sharding.visible_devices() == [0, 1, 2, 3]
+    with ProcessPoolExecutor(8, mp_context=mp.get_context("fork")) as ex:
+        got = sorted(set(ex.map(_which_device, range(64), chunksize=1)))
+    assert set(got) <= {0, 1, 2, 3} and len(got) >= 2          # more than one device is in use ...
+    monkeypatch.setenv("WDX_B200_DEVICES", "2,5")
+    with ProcessPoolExecutor(4, mp_context=mp.get_context("fork")) as ex:
+        assert set(ex.map(_which_device, range(32), chunksize=1)) <= {2, 5}
+    monkeypatch.setenv("LOCAL_RANK", "3")                        # ... unless torchrun / the user pinned it
+    assert sharding.default_device() == 3
+    monkeypatch.setenv("WDX_B200_DEVICE", "1")
+    assert sharding.default_device() == 1

@@ -15,8 +15,10 @@
 // (_local_maxima_1d, _select_by_peak_distance, _peak_prominences, _peak_widths), np.nanstd, np.nan_to_num,
 // stats.linregress' r value.
 //
-// The kernel only PROPOSES boundaries (preds_out, todo); they are validated by validate_kernel in masked mode, and
-// wdx_validate_run_ex commits the results the way the reference assigns `validated`.
+// The kernel only PROPOSES boundaries (preds_out, todo_list); they are validated by validate_kernel in list mode, and
+// wdx_validate_run_ex commits the results the way the reference assigns `validated`.  Which reads each launch looks at
+// comes from device-side lists filled by the launch before it (failed reads of the validation -> stage 0 -> reads with
+// a proposal / without one -> ...), so a minibatch with 5 % fallback reads costs 5 % of the work and no host round trip.
 //
 // Arithmetic: float64 without contraction in the reference's operation order, so everything except `log` is
 // bit-identical to the CPU; `log` is CUDA's (<= 1 ulp; the reference's is libm's, itself machine-dependent).  The
@@ -46,15 +48,21 @@ struct LlrArgs {
     const int64_t* cnn_preds;  // [n][ld] the CNN's boundaries
     int ld;
     int64_t n;
-    const uint8_t* success;    // [n] verdicts so far
     int32_t* info;             // [n][4]; [0] fail code (MAD_ZERO is written here), [3] source / progress bits
     int64_t* preds_out;        // [n][ld] boundaries proposed for the next validation
-    uint8_t* todo;             // [n] 1 = validate preds_out
     float* medmad;             // [n][2] median / MAD of the trace part of the row (stage 0 writes, stage 1 reads)
     int stage;                 // 0 hail mary, 1 full LLR
     int nmax;                  // capacity (downscaled samples) of the shared float64 arrays
     int lt_max;                // capacity (samples) of the shared row
-    unsigned long long* next;  // work counter
+    // device-side work lists (no host round trip, no scan over the minibatch): the reads to look at, the reads with a
+    // proposal (validated next), and - stage 0 only - the reads without one, which go straight on to the full LLR stage
+    const int* in_list;
+    const int* in_count;
+    int* todo_list;
+    int* todo_count;
+    int* pass_list;            // or nullptr
+    int* pass_count;
+    unsigned long long* next;  // cursor into in_list
 };
 
 struct LlrPeaks {       // work arrays of find_peaks, capacity nmax / 2 + 2 each
@@ -155,44 +163,82 @@ __device__ int llr_find_peaks(const double* x, int n, int distance, double pmin,
         __syncthreads();
         P = sh.count;
     }
-    // _peak_prominences (wlen = None), prominence filter, _peak_widths, width filter
-    for (int j = tid; j < P; j += FP_THREADS) {
+    // _peak_prominences (wlen = None), prominence filter, _peak_widths, width filter: one WARP per peak, the walks
+    // away from the peak advance 32 samples per step (a thread per peak would leave the CTA waiting for the one thread
+    // whose peak is the highest and walks the whole trace)
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    for (int j = warp; j < P; j += FP_WARPS) {
         const int peak = w.pk[j];
         const double xp = x[peak];
-        int i = peak, lb = peak;
-        double lmin = xp;
-        while (0 <= i && x[i] <= xp) {
-            if (x[i] < lmin) {
-                lmin = x[i];
-                lb = i;
+        // walk(dir): samples peak, peak+dir, ... while inside [0, n) and x <= xp; minimum of them and the position where it
+        // is first reached (the one closest to the peak), as the sequential loop finds it
+        double mins[2];
+        int bases[2];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const int dir = side ? 1 : -1;
+            double vmin = xp;
+            int vbase = peak;
+            for (int base = peak;; base += 32 * dir) {
+                const int idx = base + lane * dir;
+                const bool inside = idx >= 0 && idx < n;
+                const double v = inside ? x[idx] : 0.0;
+                const bool go = inside && (v <= xp);
+                const unsigned stop = __ballot_sync(full, !go);
+                const int first = stop ? (__ffs(stop) - 1) : 32;       // lanes below `first` belong to the walk
+                double cv = (lane < first) ? v : INFINITY;
+                int ci = (lane < first) ? lane : 64;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const double ov = __shfl_xor_sync(full, cv, o);
+                    const int oi = __shfl_xor_sync(full, ci, o);
+                    if (ov < cv || (ov == cv && oi < ci)) {
+                        cv = ov;
+                        ci = oi;
+                    }
+                }
+                if (cv < vmin) {   // strictly smaller than everything closer to the peak
+                    vmin = cv;
+                    vbase = base + ci * dir;
+                }
+                if (stop) break;
             }
-            i--;
+            mins[side] = vmin;
+            bases[side] = vbase;
         }
-        i = peak;
-        int rb = peak;
-        double rmin = xp;
-        while (i <= n - 1 && x[i] <= xp) {
-            if (x[i] < rmin) {
-                rmin = x[i];
-                rb = i;
-            }
-            i++;
-        }
+        const double lmin = mins[0], rmin = mins[1];
+        const int lb = bases[0], rb = bases[1];
         const double prom = __dsub_rn(xp, (lmin > rmin) ? lmin : rmin);
         bool keep = pmin <= prom;
         if (keep) {
             const double height = __dsub_rn(xp, __dmul_rn(prom, rel_height));
-            i = peak;
-            while (lb < i && height < x[i]) i--;
+            int ends[2];
+#pragma unroll
+            for (int side = 0; side < 2; side++) {   // i = peak; while (lb < i && height < x[i]) i--;   (and mirrored)
+                const int dir = side ? 1 : -1;
+                int found = peak;
+                for (int base = peak;; base += 32 * dir) {
+                    const int idx = base + lane * dir;
+                    const bool inside = side ? (idx < rb) : (lb < idx);
+                    const bool go = inside && (height < x[min(max(idx, 0), n - 1)]);
+                    const unsigned stop = __ballot_sync(full, !go);
+                    if (stop) {
+                        found = base + (__ffs(stop) - 1) * dir;
+                        break;
+                    }
+                }
+                ends[side] = found;
+            }
+            int i = ends[0];
             double left_ip = (double)i;
             if (x[i] < height) left_ip = __dadd_rn(left_ip, __ddiv_rn(__dsub_rn(height, x[i]), __dsub_rn(x[i + 1], x[i])));
-            i = peak;
-            while (i < rb && height < x[i]) i++;
+            i = ends[1];
             double right_ip = (double)i;
             if (x[i] < height) right_ip = __dsub_rn(right_ip, __ddiv_rn(__dsub_rn(height, x[i]), __dsub_rn(x[i - 1], x[i])));
             keep = wmin <= __dsub_rn(right_ip, left_ip);
         }
-        w.keep[j] = keep;
+        if (lane == 0) w.keep[j] = keep;
     }
     __syncthreads();
     if (tid == 0) {
@@ -273,7 +319,7 @@ __device__ int llr_polya_peak(const double* tr, int n, double* xn, LlrPeaks& w, 
     return res;
 }
 
-__global__ void __launch_bounds__(FP_THREADS, 1) llr_kernel(const LlrArgs a, const LlrCfg c) {
+__global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, const LlrCfg c) {
     extern __shared__ __align__(16) unsigned char llr_smem[];
     __shared__ FpScratch s;
     __shared__ ValSel vs;
@@ -297,16 +343,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1) llr_kernel(const LlrArgs a, con
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) {   // skip the reads that need no re-detection without involving the CTA
-            unsigned long long r;
-            for (;;) {
-                r = atomicAdd(a.next, 1ULL);
-                if (r >= (unsigned long long)a.n) break;
-                const int code = a.info[r * 4];
-                if (!a.success[r] && code != VAL_HAS_NAN && code != VAL_MAD_ZERO && code != VAL_LLR_ERROR) break;
-                a.todo[r] = 0;
-            }
-            sh_next = r;
+        if (tid == 0) {
+            const unsigned long long i = atomicAdd(a.next, 1ULL);
+            sh_next = (i < (unsigned long long)*a.in_count) ? (unsigned long long)a.in_list[i] : (unsigned long long)a.n;
         }
         __syncthreads();
         const int64_t r = (int64_t)sh_next;
@@ -340,7 +379,6 @@ __global__ void __launch_bounds__(FP_THREADS, 1) llr_kernel(const LlrArgs a, con
                 if (tid == 0) {
                     a.info[r * 4] = VAL_MAD_ZERO;
                     a.info[r * 4 + 1] = 0;
-                    a.todo[r] = 0;
                 }
                 continue;
             }
@@ -352,7 +390,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) llr_kernel(const LlrArgs a, con
             __syncthreads();
         }
         if (!(hm || full)) {
-            if (tid == 0) a.todo[r] = 0;
+            if (tid == 0 && a.pass_list) a.pass_list[atomicAdd(a.pass_count, 1)] = (int)r;
             continue;
         }
         // clip bounds: python floats (float64), cast once to float32 by np.clip; (clip - med) / mad in float32
@@ -372,18 +410,28 @@ __global__ void __launch_bounds__(FP_THREADS, 1) llr_kernel(const LlrArgs a, con
             xs[j] = (double)__fdiv_rn(sum, (float)c.factor);
         }
         __syncthreads();
-        // c = cumsum(x), c2 = cumsum(x * x): sequential float64 adds (two warps, one each)
-        if (tid == 0) {
+        // c = cumsum(x), c2 = cumsum(x * x): sequential float64 adds (two warps, one each); the loads of eight terms are
+        // issued before their dependent chain of adds
+        if (tid == 0 || tid == 32) {
+            const bool sq = tid == 32;
+            double* dst = sq ? c2 : cs;
             double acc = 0.0;
-            for (int i = 0; i < m; i++) {
-                acc = __dadd_rn(acc, xs[i]);
-                cs[i] = acc;
+            int i = 0;
+            for (; i + 8 <= m; i += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = xs[i + u];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    acc = __dadd_rn(acc, sq ? __dmul_rn(v[u], v[u]) : v[u]);
+                    v[u] = acc;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) dst[i + u] = v[u];
             }
-        } else if (tid == 32) {
-            double acc = 0.0;
-            for (int i = 0; i < m; i++) {
-                acc = __dadd_rn(acc, __dmul_rn(xs[i], xs[i]));
-                c2[i] = acc;
+            for (; i < m; i++) {
+                acc = __dadd_rn(acc, sq ? __dmul_rn(xs[i], xs[i]) : xs[i]);
+                dst[i] = acc;
             }
         }
         __syncthreads();
@@ -491,8 +539,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1) llr_kernel(const LlrArgs a, con
             }
         }
         if (tid == 0) {
-            a.todo[r] = (uint8_t)todo;
             a.info[r * 4 + 3] |= bits;
+            if (todo) a.todo_list[atomicAdd(a.todo_count, 1)] = (int)r;
+            else if (a.pass_list) a.pass_list[atomicAdd(a.pass_count, 1)] = (int)r;
         }
     }
 }

@@ -74,10 +74,13 @@ struct ValArgs {
                                // set back once a candidate failed), fail code and statistics of THAT candidate instead of the last
     unsigned long long* next;  // work counter (zeroed before the launch): reads are handed out dynamically, because a
                                // read whose first poly(A) candidate fails costs several times a read that validates
-    // masked re-validation of the LLR fallback (llr_kernel.cuh; combined.py:222-290)
-    const uint8_t* todo;       // [n] or nullptr: only reads with todo[r] != 0 are validated, the others keep their results
+    // re-validation of the LLR fallback's proposals (llr_kernel.cuh; combined.py:222-290): work lists on the device
+    const int* list;           // or nullptr: only the reads list[0 .. *list_count) are validated, the others keep their results
+    const int* list_count;
     int commit_on_success;     // != 0: results are written only when the validation succeeds (combined.py:288-289)
-    int src_tag;               // masked mode: written to the low two bits of info[.][3] with the results (LLR_SRC_*)
+    int src_tag;               // list mode: written to the low two bits of info[.][3] with the results (LLR_SRC_*)
+    int* fail_list;            // or nullptr: reads whose validation fails (other than by the NaN error) are appended here
+    int* fail_count;
 };
 
 // numpy's pairwise summation (np.add.reduce on a contiguous 1-D array): a block of n <= 128 elements is
@@ -448,7 +451,9 @@ __device__ void val_partition(const float* vsig, int L, int64_t start, int64_t e
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
 
 __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(const ValArgs a, const ValCfg c) {
+#ifndef WDX_VAL_GLOBAL_ROW
     extern __shared__ float vsig[];
+#endif
     __shared__ FpScratch s;
     __shared__ ValSel vs;
     __shared__ ValTree tree;
@@ -464,8 +469,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         __syncthreads();
         if (tid == 0) {
             unsigned long long nx = atomicAdd(a.next, 1ULL);
-            if (a.todo)
-                while (nx < (unsigned long long)a.n && !a.todo[nx]) nx = atomicAdd(a.next, 1ULL);
+            if (a.list) nx = (nx < (unsigned long long)*a.list_count) ? (unsigned long long)a.list[nx] : (unsigned long long)a.n;
             sh_next = nx;
         }
         __syncthreads();
@@ -476,6 +480,22 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         const int L = (int)max((int64_t)0, min(fl, a.stride));
         int has_nan = 0;
         if (tid < VAL_NVALS) sh_v[tid] = qnan;
+#ifdef WDX_VAL_GLOBAL_ROW
+        // The row stays in global memory: this NaN scan is its one trip from HBM (coalesced), every later pass finds it in
+        // L2 (46 KB per read, ~1200 reads in flight).  No shared-memory staging = small CTAs, eight per SM, and the many
+        // short barrier-separated phases of one read overlap with those of seven others.
+        const float* vsig = row;
+        for (int i0 = tid; i0 < L; i0 += 8 * FP_THREADS) {
+            float xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * FP_THREADS;
+                xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) has_nan |= (xv[u] != xv[u]);
+        }
+#else
         for (int i0 = tid; i0 < L; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
             float xv[4];
 #pragma unroll
@@ -492,6 +512,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                 }
             }
         }
+#endif
         has_nan = __syncthreads_or(has_nan);
 
         const int64_t* pr = a.preds + (size_t)r * a.ld;
@@ -704,6 +725,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             if (!val_in_range(ms, c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
         }
 
+        if (a.fail_list && tid == 0 && code != VAL_OK && code != VAL_HAS_NAN) a.fail_list[atomicAdd(a.fail_count, 1)] = (int)r;
         if (a.commit_on_success && code != VAL_OK) continue;
         if (a.parts) {   // calc_partitions_from_vals(signal, adapter_start, adapter_end, polya_end_best), combined.py:631-636
             double* po = a.parts + r * VAL_NPART;
@@ -720,7 +742,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             a.info[r * 4 + 0] = code;
             a.info[r * 4 + 1] = checks;
             a.info[r * 4 + 2] = n_pores;
-            a.info[r * 4 + 3] = a.todo ? ((a.info[r * 4 + 3] & ~3) | a.src_tag) : 0;
+            a.info[r * 4 + 3] = a.list ? ((a.info[r * 4 + 3] & ~3) | a.src_tag) : 0;
             a.bounds[r * 3 + 0] = a0;
             a.bounds[r * 3 + 1] = a1;
             a.bounds[r * 3 + 2] = pe_best;

@@ -21,7 +21,7 @@ struct wdx_validate {
     // LLR fallback (wdx_validate_set_llr): proposed boundaries, mask, per-read median / MAD
     bool llr_on = false;
     LlrCfg llr{};
-    int llr_nmax = 0, llr_lt_max = 0;
+    int llr_nmax = 0, llr_lt_max = 0, llr_ctas_per_sm = 1;
     size_t llr_smem = 0;
     DevBuf preds2, todo, medmad;
     bool timing = false;
@@ -191,6 +191,9 @@ int wdx_validate_set_llr(wdx_validate* h, const wdx_llr_config* cfg) {
     if ((int64_t)h->llr_smem > room)
         return fail(WDX_ERR_UNSUPPORTED, "max_obs_trace = %d needs %zu B of shared memory, device allows %d", cfg->max_obs_trace, h->llr_smem, room);
     CUDA_TRY(cudaFuncSetAttribute(llr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->llr_smem));
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, llr_kernel, FP_THREADS, h->llr_smem));
+    h->llr_ctas_per_sm = std::max(1, per_sm);
     h->llr_on = c.fallback_to_llr || c.fallback_short_reads;
     return WDX_OK;
 }
@@ -233,7 +236,11 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
     if (n == 0) return WDX_OK;
     if (!signals || !full_len || !preds || !success || !info || !bounds)
         return fail(WDX_ERR_INVALID, "signals, full_len, preds, success, info and bounds are required");
+#ifdef WDX_VAL_GLOBAL_ROW
+    const size_t smem = 0;
+#else
     const size_t smem = (size_t)stride * 4;
+#endif
     if ((int64_t)smem > h->smem_max)
         return fail(WDX_ERR_UNSUPPORTED, "rows of %lld samples need %zu B of shared memory, device allows %d", (long long)stride, smem, h->smem_max);
     std::lock_guard<std::mutex> lk(h->mu);
@@ -303,16 +310,28 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
     CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, 64, st));
     unsigned long long* counters = (unsigned long long*)h->counter.p;
     a.next = counters;
+    int* L[4] = {nullptr, nullptr, nullptr, nullptr};
+    int* lc = nullptr;
+    if (h->llr_on) {
+        if ((rc = h->preds2.reserve((size_t)n * ld * 8))) return rc;
+        if ((rc = h->todo.reserve((size_t)n * 4 * 4 + 64))) return rc;    // four work lists + their counters
+        if ((rc = h->medmad.reserve((size_t)n * 8))) return rc;
+        lc = (int*)h->todo.p;
+        for (int q = 0; q < 4; q++) L[q] = lc + 16 + (size_t)q * n;
+        CUDA_TRY(cudaMemsetAsync(lc, 0, 64, st));
+        a.fail_list = L[0];
+        a.fail_count = lc + 0;
+    }
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     validate_kernel<<<grid, FP_THREADS, smem, st>>>(a, h->cfg);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
     if (h->llr_on) {
         // combined.py:222-290: the reads that failed get a poly(A) re-detection on the CNN's adapter end ("hail mary",
-        // result assigned unconditionally), then a full LLR detection (result assigned only when it validates)
-        if ((rc = h->preds2.reserve((size_t)n * ld * 8))) return rc;
-        if ((rc = h->todo.reserve((size_t)n))) return rc;
-        if ((rc = h->medmad.reserve((size_t)n * 8))) return rc;
+        // result assigned unconditionally), then a full LLR detection (result assigned only when it validates).
+        // Device-side work lists chain the launches: L0 = failed reads (written by the validation above) -> llr stage 0 ->
+        // L1 (hail-mary proposal: validated next) / L2 (no proposal) -> validation of L1 appends its failures to L2 ->
+        // llr stage 1 on L2 -> L3 (LLR proposal) -> validation of L3, committed on success.
         LlrArgs la{};
         la.signals = sig_d;
         la.stride = stride;
@@ -320,30 +339,48 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
         la.cnn_preds = preds_d;
         la.ld = ld;
         la.n = n;
-        la.success = a.success;
         la.info = a.info;
         la.preds_out = (int64_t*)h->preds2.p;
-        la.todo = (uint8_t*)h->todo.p;
         la.medmad = (float*)h->medmad.p;
         la.nmax = h->llr_nmax;
         la.lt_max = h->llr_lt_max;
-        const int llr_grid = (int)std::min<int64_t>(n, (int64_t)2 * h->sm_count);
+        const int llr_grid = (int)std::min<int64_t>(n, (int64_t)h->llr_ctas_per_sm * h->sm_count);
         ValArgs b = a;
         b.preds = (const int64_t*)h->preds2.p;
-        b.todo = (const uint8_t*)h->todo.p;
         b.verdict_only = 0;   // single-candidate lists: nothing to cut short
-        for (int stage = 0; stage < 2; stage++) {
-            if (stage == 0 && !h->llr.fallback_short_reads) continue;
-            if (stage == 1 && !h->llr.fallback_to_llr) continue;
-            la.stage = stage;
-            la.next = counters + 1 + 2 * stage;
-            if (stage == 1 && !h->llr.fallback_short_reads) la.medmad = nullptr;   // stage 0 did not run: compute here
+        const bool hm_on = h->llr.fallback_short_reads, full_on = h->llr.fallback_to_llr;
+        if (hm_on) {
+            la.stage = 0;
+            la.in_list = L[0]; la.in_count = lc + 0;
+            la.todo_list = L[1]; la.todo_count = lc + 1;
+            la.pass_list = L[2]; la.pass_count = lc + 2;
+            la.next = counters + 1;
             llr_kernel<<<llr_grid, FP_THREADS, h->llr_smem, st>>>(la, h->llr);
             CUDA_TRY(cudaGetLastError());
-            b.next = counters + 2 + 2 * stage;
-            b.commit_on_success = stage == 1;
-            b.src_tag = stage == 0 ? LLR_SRC_HAIL_MARY : LLR_SRC_LLR;
-            validate_kernel<<<grid, FP_THREADS, smem, st>>>(b, h->cfg);
+            b.list = L[1]; b.list_count = lc + 1;
+            b.fail_list = L[2]; b.fail_count = lc + 2;
+            b.next = counters + 2;
+            b.commit_on_success = 0;
+            b.src_tag = LLR_SRC_HAIL_MARY;
+            validate_kernel<<<std::min(grid, llr_grid), FP_THREADS, smem, st>>>(b, h->cfg);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 2;
+        }
+        if (full_on) {
+            la.stage = 1;
+            la.in_list = hm_on ? L[2] : L[0]; la.in_count = hm_on ? lc + 2 : lc + 0;
+            la.todo_list = L[3]; la.todo_count = lc + 3;
+            la.pass_list = nullptr; la.pass_count = nullptr;
+            if (!hm_on) la.medmad = nullptr;   // stage 0 did not run: the median / MAD are computed here
+            la.next = counters + 3;
+            llr_kernel<<<llr_grid, FP_THREADS, h->llr_smem, st>>>(la, h->llr);
+            CUDA_TRY(cudaGetLastError());
+            b.list = L[3]; b.list_count = lc + 3;
+            b.fail_list = nullptr; b.fail_count = nullptr;
+            b.next = counters + 4;
+            b.commit_on_success = 1;
+            b.src_tag = LLR_SRC_LLR;
+            validate_kernel<<<std::min(grid, llr_grid), FP_THREADS, smem, st>>>(b, h->cfg);
             CUDA_TRY(cudaGetLastError());
             g_launches += 2;
         }

@@ -448,6 +448,124 @@ __device__ void val_partition(const float* vsig, int L, int64_t start, int64_t e
     }
 }
 
+// ---- median of a moving-window statistic, exactly, without evaluating the statistic exactly everywhere ---------------
+// mean_var_shift_polyA_check takes np.nanmedian over bottleneck.move_var(seg, 100) / move_mean(seg, 20) (mvs.py:93-107): one
+// value per window position, each an O(window) float64 reduction in numpy's pairwise order (two passes for the variance).
+// On real reads the poly(A) stretch is ~4 800 samples, i.e. ~1.9 M float64 operations + 0.9 M float32->float64
+// conversions per read for a single median — half of this kernel's time.  Only the MIDDLE order statistics are needed:
+//  (1) every window gets a cheap approximation A[p] (sliding sums of the centred samples in float64, restarted every
+//      VAL_WIN_CHUNK windows; relative error < 1e-8, stored as float32),
+//  (2) the approximate middle values a are selected from A,
+//  (3) windows with A outside a band of relative half-width 1e-6 around a are certainly below / above the exact middle
+//      values (an order statistic moves by at most the largest perturbation of the data, and float32 rounding of the exact
+//      value is monotone); only the few windows inside the band are evaluated exactly,
+//  (4) the exact middle values are the (k - #below)-th smallest exact values inside the band.
+// The result is bit-identical to selecting from the exactly evaluated array (tests: tests/test_validate.py against the
+// reference-generated fixture and the numpy oracle).  Degenerate data (band overflows VAL_BAND_CAP, non-finite
+// approximations) falls back to evaluating every window exactly.
+constexpr int VAL_WIN_CHUNK = 8;
+constexpr int VAL_BAND_CAP = 384;
+struct ValBand {
+    int idx[VAL_BAND_CAP];
+    float val[VAL_BAND_CAP];
+    int n, below;
+    float out[2];
+};
+
+template <bool VAR>
+__device__ __forceinline__ float val_window_exact(const float* vsig, int lo, int w) {
+    const double mu = __ddiv_rn(np_pairwise<double>(lo, w, [&](int i) { return (double)vsig[i]; }), (double)w);
+    if (!VAR) return (float)mu;
+    const double ss = np_pairwise<double>(lo, w, [&](int i) {
+        const double d = __dsub_rn((double)vsig[i], mu);
+        return __dmul_rn(d, d);
+    });
+    return (float)__ddiv_rn(ss, (double)w);
+}
+
+// np.nanmedian(move_var / move_mean (vsig[e : e + m], w)) as float32 (NaN when no window fits).  scratch: >= m floats.
+template <bool VAR>
+__device__ float val_window_median(const float* vsig, int e, int m, int w, float* scratch, ValBand& bd, ValSel& vs, FpScratch& s) {
+    const int tid = threadIdx.x;
+    const int cnt = m - w + 1;
+    if (cnt <= 0) return __int_as_float(0x7fc00000);
+    __syncthreads();
+    bool exact_all = cnt <= 4 * VAL_BAND_CAP / 3 || w < 4;
+    if (!exact_all) {
+        const double cref = (double)vsig[e], wd = (double)w;
+        for (int p0 = tid * VAL_WIN_CHUNK; p0 < cnt; p0 += FP_THREADS * VAL_WIN_CHUNK) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int i = 0; i < w; i++) {
+                const double d = (double)vsig[e + p0 + i] - cref;
+                s1 += d;
+                if (VAR) s2 += d * d;
+            }
+            const int pe = min(p0 + VAL_WIN_CHUNK, cnt);
+            for (int p = p0;; p++) {
+                const double mu = s1 / wd;
+                scratch[p] = VAR ? (float)(s2 / wd - mu * mu) : (float)(cref + mu);
+                if (p + 1 >= pe) break;
+                const double dn = (double)vsig[e + p + w] - cref, dl = (double)vsig[e + p] - cref;
+                s1 += dn - dl;
+                if (VAR) s2 += dn * dn - dl * dl;
+            }
+        }
+        __syncthreads();
+        const uint32_t rk[2] = {(uint32_t)((cnt - 1) / 2), (uint32_t)(cnt / 2)};
+        float am[2];
+        block_ranks(cnt, [&](int i) { return scratch[i]; }, 2, rk, am, vs, s);
+        // half-width of the band: 1e-6 relative — the float32 storage of A (6e-8) and the sliding float64 sums of the centred
+        // samples (< 1e-10 of the statistic for pA-scale data) stay far inside it; a statistic that is ~0 against data
+        // that is not (constant signal) puts every window into the band and takes the exact path below
+        const double a_lo = (double)fminf(am[0], am[1]), a_hi = (double)fmaxf(am[0], am[1]);
+        const double tol = 1e-6 * fmax(fabs(a_lo), fabs(a_hi)) + 1e-12;
+        const double b_lo = a_lo - tol, b_hi = a_hi + tol;
+        if (tid == 0) {
+            bd.n = 0;
+            bd.below = 0;
+        }
+        __syncthreads();
+        int below = 0;
+        for (int p = tid; p < cnt; p += FP_THREADS) {
+            const double A = (double)scratch[p];
+            if (A < b_lo) below++;
+            else if (A <= b_hi) {
+                const int pos = atomicAdd(&bd.n, 1);
+                if (pos < VAL_BAND_CAP) bd.idx[pos] = p;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if ((tid & 31) == 0 && below) atomicAdd(&bd.below, below);
+        __syncthreads();
+        const int nb = bd.n, r0 = (int)rk[0] - bd.below, r1 = (int)rk[1] - bd.below;
+        if (!(a_lo == a_lo) || !(a_hi - a_lo <= 1e300) || nb > VAL_BAND_CAP || r0 < 0 || r1 >= nb) {
+            exact_all = true;    // uniform decision
+        } else {
+            for (int j = tid; j < nb; j += FP_THREADS) bd.val[j] = val_window_exact<VAR>(vsig, e + bd.idx[j], w);
+            __syncthreads();
+            for (int j = tid; j < nb; j += FP_THREADS) {
+                const float x = bd.val[j];
+                int rank = 0;
+                for (int u = 0; u < nb; u++) {
+                    const float y = bd.val[u];
+                    rank += (y < x) || (y == x && u < j);
+                }
+                if (rank == r0) bd.out[0] = x;
+                if (rank == r1) bd.out[1] = x;
+            }
+            __syncthreads();
+            const float res = median_of(cnt, bd.out[0], bd.out[1]);
+            __syncthreads();
+            return res;
+        }
+        __syncthreads();
+    }
+    for (int p = tid; p < cnt; p += FP_THREADS) scratch[p] = val_window_exact<VAR>(vsig, e + p, w);
+    __syncthreads();
+    return val_median(cnt, [&](int i) { return scratch[i]; }, vs, s);
+}
+
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
 
 __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(const ValArgs a, const ValCfg c) {
@@ -457,6 +575,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     __shared__ FpScratch s;
     __shared__ ValSel vs;
     __shared__ ValTree tree;
+    __shared__ ValBand band;
     __shared__ int sh_i[6];
     __shared__ double sh_d[4];
     __shared__ double sh_v[VAL_NVALS];
@@ -646,18 +765,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                             __syncthreads();
                             r_var = sh_d[0];
                         } else {
-                            const int w = c.pa_var_window, cnt = m - w + 1;
-                            __syncthreads();
-                            for (int p = tid; p < cnt; p += FP_THREADS) {
-                                const double mu = __ddiv_rn(np_pairwise<double>(e + p, w, [&](int i) { return (double)vsig[i]; }), (double)w);
-                                const double ss = np_pairwise<double>(e + p, w, [&](int i) {
-                                    const double d = __dsub_rn((double)vsig[i], mu);
-                                    return __dmul_rn(d, d);
-                                });
-                                scratch[p] = (float)__ddiv_rn(ss, (double)w);
-                            }
-                            __syncthreads();
-                            r_var = (double)val_median(cnt, [&](int i) { return scratch[i]; }, vs, s);
+                            r_var = (double)val_window_median<true>(vsig, e, m, c.pa_var_window, scratch, band, vs, s);
                         }
                         // mean
                         if (nominal <= c.pa_mean_window + 2) {
@@ -667,12 +775,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                             __syncthreads();
                             r_mean = sh_d[0];
                         } else {
-                            const int w = c.pa_mean_window, cnt = m - w + 1;
-                            __syncthreads();
-                            for (int p = tid; p < cnt; p += FP_THREADS)
-                                scratch[p] = (float)__ddiv_rn(np_pairwise<double>(e + p, w, [&](int i) { return (double)vsig[i]; }), (double)w);
-                            __syncthreads();
-                            r_mean = (double)val_median(cnt, [&](int i) { return scratch[i]; }, vs, s);
+                            r_mean = (double)val_window_median<false>(vsig, e, m, c.pa_mean_window, scratch, band, vs, s);
                         }
                         float pmed;
                         r_lr = val_local_range(m, [&](int i) { return vsig[e + i]; }, vs, s, &pmed);

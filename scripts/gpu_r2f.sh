@@ -7,13 +7,4 @@ timeout 900 python -m pytest tests/test_validate.py tests/test_gpu_llr.py tests/
 tail -15 $OUT/${TAG}_pytest.log
 timeout 300 python scripts/val_real_probe.py 2>&1 | tail -1 | tee $OUT/${TAG}_val_probe.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_val_launches.csv python scripts/val_real_probe.py > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=list(csv.reader(open('gpurun_out/'+'${TAG}'+'_val_launches.csv')))
-hdr=None; out=[]
-for r in rows:
-    if 'Kernel Name' in r: hdr=r; continue
-    if hdr and len(r)==len(hdr):
-        d=dict(zip(hdr,r)); out.append((d['Kernel Name'][:40], float(d['Metric Value'])/1e3, d.get('Grid Size')))
-for o in [x for x in out if 'wdx' in x[0]][-5:]: print(o)
-PY
+python scripts/launch_tail.py $OUT/${TAG}_val_launches.csv

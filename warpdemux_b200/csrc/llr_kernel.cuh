@@ -92,7 +92,7 @@ __device__ __forceinline__ double llr_var_c(int start, int end, const double* c,
 }
 
 // _gains(start, end, c, c2, offset_head, offset_tail, stride = 1) over an array of n entries (zeros elsewhere).
-__device__ void llr_gains(const double* c, const double* c2, int n, int start, int end, int head, int tail, double* g) {
+__device__ __noinline__ void llr_gains(const double* c, const double* c2, int n, int start, int end, int head, int tail, double* g) {
     const double vs = __dmul_rn((double)(end - start), log(llr_var_c(start, end, c, c2)));
     for (int i = threadIdx.x; i < n; i += FP_THREADS) {
         double v = 0.0;
@@ -108,7 +108,7 @@ __device__ void llr_gains(const double* c, const double* c2, int n, int start, i
 
 // scipy.signal.find_peaks(x[0:n], distance (0 = None), prominence = pmin, width = wmin, rel_height): number of peaks,
 // the first two in sh.first.  All threads call; results are uniform.
-__device__ int llr_find_peaks(const double* x, int n, int distance, double pmin, double wmin, double rel_height, LlrPeaks& w,
+__device__ __noinline__ int llr_find_peaks(const double* x, int n, int distance, double pmin, double wmin, double rel_height, LlrPeaks& w,
                               LlrShared& sh, FpScratch& s) {
     const int tid = threadIdx.x;
     __syncthreads();
@@ -258,7 +258,7 @@ __device__ int llr_find_peaks(const double* x, int n, int distance, double pmin,
 }
 
 // detect_full_polya_trace_peak_with_spike(trace[0:n]) (llr.py:385-455): xn = scratch for nan_to_num(trace).
-__device__ int llr_polya_peak(const double* tr, int n, double* xn, LlrPeaks& w, LlrShared& sh, FpScratch& s) {
+__device__ __noinline__ int llr_polya_peak(const double* tr, int n, double* xn, LlrPeaks& w, LlrShared& sh, FpScratch& s) {
     const int tid = threadIdx.x;
     const double dmax = 1.7976931348623157e308;
     for (int i = tid; i < n; i += FP_THREADS) {
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
             for (int i = tid; i < Lt; i += FP_THREADS) vsig[i] = __ldg(row + i);
             __syncthreads();
             if (Lt > 0) {   // normalize_signal: nanmedian / MAD of the NaN-free float32 slice
-                med = val_median(Lt, [&](int i) { return vsig[i]; }, vs, s);
-                mad = val_median(Lt, [&](int i) { return fabsf(__fsub_rn(vsig[i], med)); }, vs, s);
+                med = val_median(Lt, val_src(vsig), vs, s);
+                mad = val_median(Lt, val_src_absdev(vsig, med), vs, s);
             } else {
                 med = mad = 1.0f;   // an empty slice normalises to an empty array (normalize.py:49-50)
             }

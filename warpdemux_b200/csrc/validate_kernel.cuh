@@ -166,7 +166,7 @@ struct ValSel {
 
 // out[q] = the ranks[q]-th smallest (0-based) value, q < nq <= VAL_MAXQ; ranks < n, n >= 1.  All threads get all results.
 template <typename VAL>
-__device__ void block_ranks(int n, VAL val, int nq, const uint32_t* ranks, float* out, ValSel& vs, FpScratch& s) {
+__device__ __forceinline__ void block_ranks_t(int n, VAL val, int nq, const uint32_t* ranks, float* out, ValSel& vs, FpScratch& s) {
     const int tid = threadIdx.x;
     __syncthreads();
     if (tid == 0) {
@@ -303,19 +303,33 @@ __device__ __forceinline__ double pct_lerp(float a, float b, double g) {
     return r;
 }
 
+// Every selection of this kernel reads either p[i] or |p[i] - med| (float32): ONE out-of-line copy of the selection code
+// serves all call sites.  (Inlined per call site the kernel was 58 800 SASS instructions and stalled on instruction
+// fetch - "no instruction" 3.3 per issue in profiles/r02_ncu_full_validate_real_reads_before.json.)
+struct ValSrc {
+    const float* p;
+    float med;
+    int absdev;
+    __device__ __forceinline__ float operator()(int i) const { return absdev ? fabsf(__fsub_rn(p[i], med)) : p[i]; }
+};
+__device__ __forceinline__ ValSrc val_src(const float* p) { return ValSrc{p, 0.f, 0}; }
+__device__ __forceinline__ ValSrc val_src_absdev(const float* p, float med) { return ValSrc{p, med, 1}; }
+
+__device__ __noinline__ void block_ranks(int n, ValSrc src, int nq, const uint32_t* ranks, float* out, ValSel& vs, FpScratch& s) {
+    block_ranks_t(n, src, nq, ranks, out, vs, s);
+}
+
 // np.median of n NaN-free float32 values (NaN for n == 0, as numpy returns for an empty slice).
-template <typename VAL>
-__device__ float val_median(int n, VAL val, ValSel& vs, FpScratch& s) {
+__device__ __forceinline__ float val_median(int n, ValSrc src, ValSel& vs, FpScratch& s) {
     if (n <= 0) return __int_as_float(0x7fc00000);
     const uint32_t rk[2] = {(uint32_t)((n - 1) / 2), (uint32_t)(n / 2)};
     float o[2];
-    block_ranks(n, val, 2, rk, o, vs, s);
+    block_ranks(n, src, 2, rk, o, vs, s);
     return median_of(n, o[0], o[1]);
 }
 
 // p85 - p15 of n >= 1 values (np.subtract(*np.percentile(x, (85, 15)))), optionally with the median.
-template <typename VAL>
-__device__ double val_local_range(int n, VAL val, ValSel& vs, FpScratch& s, float* median) {
+__device__ __forceinline__ double val_local_range(int n, ValSrc src, ValSel& vs, FpScratch& s, float* median) {
     uint32_t rk[6];
     double g85, g15;
     pct_ranks(n, 85.0, &rk[0], &rk[1], &g85);
@@ -323,7 +337,7 @@ __device__ double val_local_range(int n, VAL val, ValSel& vs, FpScratch& s, floa
     rk[4] = (uint32_t)((n - 1) / 2);
     rk[5] = (uint32_t)(n / 2);
     float o[6];
-    block_ranks(n, val, median ? 6 : 4, rk, o, vs, s);
+    block_ranks(n, src, median ? 6 : 4, rk, o, vs, s);
     if (median) *median = median_of(n, o[4], o[5]);
     return __dsub_rn(pct_lerp(o[0], o[1], g85), pct_lerp(o[2], o[3], g15));
 }
@@ -410,7 +424,7 @@ __device__ float block_np_sum_f32(int lo, int n, F f, ValTree& t) {
 }
 
 // calc_partition_stats (signal_partitions.py:80-96) of sig[start:end] for a row of L samples -> out[6] (thread 0 writes).
-__device__ void val_partition(const float* vsig, int L, int64_t start, int64_t end, double* out, ValTree& t, ValSel& vs, FpScratch& s) {
+__device__ __noinline__ void val_partition(const float* vsig, int L, int64_t start, int64_t end, double* out, ValTree& t, ValSel& vs, FpScratch& s) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int tid = threadIdx.x;
     if (end <= start) {
@@ -435,8 +449,8 @@ __device__ void val_partition(const float* vsig, int L, int64_t start, int64_t e
             return __fmul_rn(d, d);
         }, t);
         sd = __fsqrt_rn(__fdiv_rn(ss, (float)n));
-        med = val_median(n, [&](int i) { return vsig[b + i]; }, vs, s);
-        mad = val_median(n, [&](int i) { return fabsf(__fsub_rn(vsig[b + i], med)); }, vs, s);
+        med = val_median(n, val_src(vsig + b), vs, s);
+        mad = val_median(n, val_src_absdev(vsig + b, med), vs, s);
     }
     if (tid == 0) {
         out[0] = (double)start;
@@ -485,7 +499,7 @@ __device__ __forceinline__ float val_window_exact(const float* vsig, int lo, int
 
 // np.nanmedian(move_var / move_mean (vsig[e : e + m], w)) as float32 (NaN when no window fits).  scratch: >= m floats.
 template <bool VAR>
-__device__ float val_window_median(const float* vsig, int e, int m, int w, float* scratch, ValBand& bd, ValSel& vs, FpScratch& s) {
+__device__ __noinline__ float val_window_median(const float* vsig, int e, int m, int w, float* scratch, ValBand& bd, ValSel& vs, FpScratch& s) {
     const int tid = threadIdx.x;
     const int cnt = m - w + 1;
     if (cnt <= 0) return __int_as_float(0x7fc00000);
@@ -513,7 +527,7 @@ __device__ float val_window_median(const float* vsig, int e, int m, int w, float
         __syncthreads();
         const uint32_t rk[2] = {(uint32_t)((cnt - 1) / 2), (uint32_t)(cnt / 2)};
         float am[2];
-        block_ranks(cnt, [&](int i) { return scratch[i]; }, 2, rk, am, vs, s);
+        block_ranks(cnt, val_src(scratch), 2, rk, am, vs, s);
         // half-width of the band: 1e-6 relative — the float32 storage of A (6e-8) and the sliding float64 sums of the centred
         // samples (< 1e-10 of the statistic for pA-scale data) stay far inside it; a statistic that is ~0 against data
         // that is not (constant signal) puts every window into the band and takes the exact path below
@@ -563,7 +577,7 @@ __device__ float val_window_median(const float* vsig, int e, int m, int w, float
     }
     for (int p = tid; p < cnt; p += FP_THREADS) scratch[p] = val_window_exact<VAR>(vsig, e + p, w);
     __syncthreads();
-    return val_median(cnt, [&](int i) { return scratch[i]; }, vs, s);
+    return val_median(cnt, val_src(scratch), vs, s);
 }
 
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
@@ -648,8 +662,8 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         if (code == VAL_OK) {
             if (a1 == 0) code = VAL_NO_ADAPTER;
             else {
-                med = val_median(hi, [&](int i) { return vsig[i]; }, vs, s);
-                mad = val_median(hi, [&](int i) { return fabsf(__fsub_rn(vsig[i], med)); }, vs, s);
+                med = val_median(hi, val_src(vsig), vs, s);
+                mad = val_median(hi, val_src_absdev(vsig, med), vs, s);
                 if (tid == 0) {
                     sh_v[0] = (double)med;
                     sh_v[1] = (double)mad;
@@ -721,7 +735,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                 if (val_in_range(mean_start, c.mean_start_lo, c.mean_start_hi) && val_in_range(mean_end, c.mean_end_lo, c.mean_end_hi)) {
                     const int nn = min(c.max_obs_local_range, nseg);
                     const int base = hi - nn;
-                    const double lr = val_local_range(nn, [&](int i) { return vsig[base + i]; }, vs, s, nullptr);
+                    const double lr = val_local_range(nn, val_src(vsig + base), vs, s, nullptr);
                     if (tid == 0) sh_v[4] = lr;
                     ok = val_in_range(lr, c.local_range_lo, c.local_range_hi);
                 }
@@ -778,12 +792,12 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                             r_mean = (double)val_window_median<false>(vsig, e, m, c.pa_mean_window, scratch, band, vs, s);
                         }
                         float pmed;
-                        r_lr = val_local_range(m, [&](int i) { return vsig[e + i]; }, vs, s, &pmed);
+                        r_lr = val_local_range(m, val_src(vsig + e), vs, s, &pmed);
                         r_med = (double)pmed;
                         if (!have_shift) {   // depends on the adapter end only: once per read, not per candidate
                             const int up = min(e + c.median_shift_window, L), dn = max(e - c.median_shift_window, 0);
-                            const float m_after = val_median(up - e, [&](int i) { return vsig[e + i]; }, vs, s);
-                            const float m_before = val_median(e - dn, [&](int i) { return vsig[dn + i]; }, vs, s);
+                            const float m_after = val_median(up - e, val_src(vsig + e), vs, s);
+                            const float m_before = val_median(e - dn, val_src(vsig + dn), vs, s);
                             shift_cached = (double)__fsub_rn(m_after, m_before);
                             have_shift = true;
                         }
@@ -821,8 +835,8 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         if (code == VAL_OK && c.detect_med_shift) {
             const int e = (int)min(a1, (int64_t)L);
             const int up = (int)min(min(a1 + c.med_shift_window, fl), (int64_t)L), dn = (int)max(a1 - c.med_shift_window, (int64_t)0);
-            const float m_after = val_median(max(0, up - e), [&](int i) { return vsig[e + i]; }, vs, s);
-            const float m_before = val_median(max(0, e - min(dn, e)), [&](int i) { return vsig[min(dn, e) + i]; }, vs, s);
+            const float m_after = val_median(max(0, up - e), val_src(vsig + e), vs, s);
+            const float m_before = val_median(max(0, e - min(dn, e)), val_src(vsig + min(dn, e)), vs, s);
             const double ms = (double)__fsub_rn(m_after, m_before);
             if (tid == 0) sh_v[10] = ms;
             if (!val_in_range(ms, c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;

@@ -546,7 +546,7 @@ def raw_signal_chain(params_small, local):
     return out
 
 
-def raw_chain_stream_rank(local, minibatches=48, mb=1000, stride=11500):
+def raw_chain_stream_rank(local, minibatches=48, mb=1000, stride=11500, lanes=4):
     """One rank's part of the multi-GPU raw-signal measurement: a stream of production minibatches (1000 reads x 11 500
     int16 ADC samples + calibration, pinned host memory) through MinibatchDemuxer.stream on this rank's GPU.
     Returns (reads, seconds) — the caller takes the max of the seconds over ranks."""
@@ -564,7 +564,7 @@ def raw_chain_stream_rank(local, minibatches=48, mb=1000, stride=11500):
     md = cnn.load_cnn_model(os.path.join(ROOT, "tests", "golden", "models", "cnn_rna004_130bps_v0.2.4.npz"), device=local)
     mp4 = DTW_SVM(small, device=local, mode="guarded")
     dmx = MinibatchDemuxer(mp4, md, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=5), device=local,
-                           llr=combined.LLRConfig())
+                           llr=combined.LLRConfig(), lanes=lanes)
     mbs = []
     for i in range(minibatches):
         a = (i % nb) * mb

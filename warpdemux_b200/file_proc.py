@@ -90,7 +90,7 @@ class MinibatchDemuxer:
                  validate_config: Optional["_combined.ValidateConfig"] = None, fp_config: Optional[FingerprintConfig] = None,
                  device: Optional[int] = None, mode: Optional[str] = None, cnn_mode: Optional[str] = None,
                  llr_fallback: Optional[Callable] = None, consensus_query=None, full_detect_report: bool = False,
-                 llr="auto"):
+                 llr="auto", lanes: int = 4):
         import torch  # device memory and streams only
 
         self._torch = torch
@@ -121,6 +121,14 @@ class MinibatchDemuxer:
                 if cap2 > fcfg.max_slice_len:
                     fcfg = dataclasses.replace(fcfg, long_slice_len=min(cap2, 16000))
         self.fingerprinter = Fingerprinter(fcfg, device=self.device)
+        # Lanes: `stream()` alternates consecutive minibatches between `lanes` compute streams, each with its OWN set of
+        # library handles (their workspaces are per handle), so that the latency-bound tail of one minibatch (the few
+        # reads of the LLR fallback, the finishing kernels) overlaps the wide kernels of the next.  Lane 0 = the objects
+        # given; the others are replicas built from the same host-side parameters (created lazily).
+        self.lanes = max(1, int(lanes))
+        self._lane_objs = [dict(model_predict=model_predict, model_detect=model_detect, validator=self.validator,
+                                fingerprinter=self.fingerprinter, stream=None)]
+        self._lane_cfg = dict(vcfg=vcfg, fcfg=fcfg, llr=llr, verdict_only=not full_detect_report)
         self.mode = mode or model_predict.mode
         self.cnn_mode = cnn_mode or model_detect.mode
         self.llr_fallback = llr_fallback
@@ -149,6 +157,22 @@ class MinibatchDemuxer:
             self._stream = torch.cuda.Stream(device=self._dev())        # kernels + result download
             self._copy_stream = torch.cuda.Stream(device=self._dev())   # minibatch upload
         return self._stream, self._copy_stream
+
+    def _lane(self, i: int) -> dict:
+        """Handles + compute stream of lane i (replicas of lane 0's objects for i > 0)."""
+        torch = self._torch
+        while len(self._lane_objs) <= i:
+            c = self._lane_cfg
+            mp0, md0 = self.model_predict, self.model_detect
+            self._lane_objs.append(dict(
+                model_predict=type(mp0)(mp0.params, device=self.device, mode=mp0.mode),
+                model_detect=_cnn.BoundariesCNN(md0.weights, device=self.device, mode=md0.mode),
+                validator=_combined.Validator(c["vcfg"], device=self.device, verdict_only=c["verdict_only"], llr=c["llr"]),
+                fingerprinter=Fingerprinter(c["fcfg"], device=self.device), stream=None))
+        ln = self._lane_objs[i]
+        if ln["stream"] is None:
+            ln["stream"] = self._streams()[0] if i == 0 else torch.cuda.Stream(device=self._dev())
+        return ln
 
     def _upload(self, slot: int, signals, full_lengths, read_ids) -> dict:
         """Phase 1 (copy stream): the minibatch goes to the device.  Pageable rows are first copied into the slot's
@@ -232,10 +256,11 @@ class MinibatchDemuxer:
         return job
 
     def _launch(self, job: dict, want_fpt: bool) -> None:
-        """Phase 2 (compute stream): CNN -> validation -> fingerprint + DTW/SVC, then the result download."""
+        """Phase 2 (the lane's compute stream): CNN -> validation / LLR -> fingerprint + DTW/SVC, then the result download."""
         torch = self._torch
-        st, _ = self._streams()
-        dm = self.model_predict._device_model()
+        lane = self._lane(job.get("lane", 0))
+        st = lane["stream"]
+        dm = lane["model_predict"]._device_model()
         k, L = self.model_predict.params.k, self.model_predict.params.L
         n, stride, slot, lens = job["n"], job["stride"], job["slot"], job["lens"]
         ld = 1 + self.k_cand
@@ -269,8 +294,8 @@ class MinibatchDemuxer:
             sp = st.cuda_stream
             rescued = np.zeros(n, dtype=bool)
             if n:
-                _cnn.detect_raw(self.model_detect, self.core, self.k_cand, d_sig, n, stride, d_preds, mode=self.cnn_mode, stream=sp)
-                self.validator.run_raw(d_sig, n, stride, d_len, d_preds, ld, d_suc, d_info, d_bounds, None, stream=sp)
+                _cnn.detect_raw(lane["model_detect"], self.core, self.k_cand, d_sig, n, stride, d_preds, mode=self.cnn_mode, stream=sp)
+                lane["validator"].run_raw(d_sig, n, stride, d_len, d_preds, ld, d_suc, d_info, d_bounds, None, stream=sp)
                 if self.llr_fallback is not None:
                     suc_h = d_suc.cpu().numpy()            # synchronises this stream: n bytes
                     failed = np.flatnonzero(suc_h == 0)
@@ -288,7 +313,7 @@ class MinibatchDemuxer:
                         d_suc.copy_(torch.from_numpy(suc_h))
                 d_a0.copy_(d_bounds[:, 0])
                 d_a1.copy_(d_bounds[:, 1])
-                self.fingerprinter.predict_raw(dm, d_sig, n, stride, d_a0, d_a1, _lib.MODES[self.mode], d_lab, d_status,
+                lane["fingerprinter"].predict_raw(dm, d_sig, n, stride, d_a0, d_a1, _lib.MODES[self.mode], d_lab, d_status,
                                                conf=d_conf, prob=d_prob, fpt=d_fpt, detect_ok=d_suc, stream=sp, flags=d_flags)
             h_block[:max(total, 8)].copy_(d_block, non_blocking=True)      # one download, does not block the host
             host = hviews
@@ -308,14 +333,15 @@ class MinibatchDemuxer:
             # their FAST_F32 results; redo them in EXACT_F64 from the fingerprints still on the device
             torch = self._torch
             sel = torch.from_numpy(over).to(self._dev())
-            with torch.cuda.stream(self._streams()[0]):
+            lane = self._lane(job.get("lane", 0))
+            with torch.cuda.stream(lane["stream"]):
                 x = job["d_fpt"].index_select(0, sel).contiguous()
                 k = prob.shape[1]
                 lab2 = torch.empty(over.size, dtype=torch.int64, device=self._dev())
                 conf2 = torch.empty(over.size, dtype=torch.float64, device=self._dev())
                 prob2 = torch.empty((over.size, k), dtype=torch.float64, device=self._dev())
-                self.model_predict._device_model().predict_raw(x, over.size, _lib.WDX_F64, _lib.MODE_EXACT_F64, lab2, conf2, prob2,
-                                                               stream=self._streams()[0].cuda_stream)
+                lane["model_predict"]._device_model().predict_raw(x, over.size, _lib.WDX_F64, _lib.MODE_EXACT_F64, lab2, conf2, prob2,
+                                                                  stream=lane["stream"].cuda_stream)
                 labels[over], conf[over], prob[over] = lab2.cpu().numpy(), conf2.cpu().numpy(), prob2.cpu().numpy()
         # a fingerprint whose decision values are not finite: the reference's predict raises (sklearn check_array); here the
         # read is reported as failed with its own status instead of silently becoming "unclassified"
@@ -357,7 +383,8 @@ class MinibatchDemuxer:
             def up(slot, mb):
                 return self._upload(slot, mb[0], mb[1], mb[2] if len(mb) > 2 else None)
 
-            SLOTS = 3
+            LANES = self.lanes
+            SLOTS = LANES + 2     # buffer sets: one per launched minibatch + the upload ahead of them
             pending = []          # uploaded or launched jobs, oldest first
             i = 0                 # minibatches uploaded so far
 
@@ -366,14 +393,18 @@ class MinibatchDemuxer:
                 mb = next(it, None)
                 if mb is None:
                     return False
-                pending.append([up(i % SLOTS, mb), False])
+                job = up(i % SLOTS, mb)
+                job["lane"] = i % LANES
+                pending.append([job, False])
                 i += 1
                 return True
 
-            more = upload_next() and upload_next()      # two uploads in flight before the first launch
+            more = True
+            for _ in range(LANES + 1):                  # uploads in flight before the first launch
+                more = more and upload_next()
             while pending:
-                for pj in pending[:2]:                  # keep two minibatches launched (the CNN call blocks the host
-                    if not pj[1]:                       # until its own kernels are done; the next upload is already queued)
+                for pj in pending[:LANES + 1]:          # keep one minibatch per lane launched + one queued behind them
+                    if not pj[1]:
                         self._launch(pj[0], want_fpt)
                         pj[1] = True
                 done = pending.pop(0)
@@ -383,6 +414,11 @@ class MinibatchDemuxer:
                 yield res
 
     def close(self):
+        for ln in self._lane_objs[1:]:
+            ln["validator"].close()
+            ln["fingerprinter"].close()
+            ln["model_detect"].close()
+        self._lane_objs = self._lane_objs[:1]
         self.validator.close()
         self.fingerprinter.close()
         self._buf = {}

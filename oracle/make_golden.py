@@ -34,7 +34,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
 sys.path.insert(0, REF)
 sys.path.insert(0, os.path.join(REF, "warpdemux", "adapted"))
 
-MODELS = ["WDX4_rna004_v1_0", "WDX4b_rna004_v1_0", "WDX4c_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0"]   # every shipped DTW_SVM
+MODELS = ["WDX4_rna004_v1_0", "WDX4b_rna004_v1_0", "WDX4c_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0",   # every shipped DTW_SVM
+          "WDX12_rna002_v0_4_4"]   # + the largest deprecated rna002 model (DEPRECATED/model_files: gamma 1.2, 13 classes, 3617 SVs)
 # WDX_GOLDEN_MODELS="a,b": (re)generate only those model / predict fixtures and leave everything else as it is
 ONLY = [m for m in os.environ.get("WDX_GOLDEN_MODELS", "").split(",") if m]
 
@@ -97,6 +98,8 @@ def main():
             manifest = json.load(fh)
     for name in (ONLY or MODELS):
         path = os.path.join(REF, "warpdemux", "models", "model_files", name + ".joblib")
+        if not os.path.exists(path):
+            path = os.path.join(REF, "DEPRECATED", "model_files", name + ".joblib")
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             ref_model = joblib.load(path)  # the real reference class + real sklearn SVC

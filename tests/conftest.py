@@ -33,7 +33,8 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
-MODEL_NAMES = ["WDX4_rna004_v1_0", "WDX4b_rna004_v1_0", "WDX4c_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0"]   # every shipped DTW_SVM
+MODEL_NAMES = ["WDX4_rna004_v1_0", "WDX4b_rna004_v1_0", "WDX4c_rna004_v1_0", "WDX6_rna004_v1_0", "WDX10_rna004_v1_0",   # every shipped DTW_SVM
+               "WDX12_rna002_v0_4_4"]   # + the largest deprecated rna002 model: gamma 1.2, 13 classes (KM1 = 16 kernel variant)
 
 
 @pytest.fixture(scope="session")

@@ -475,7 +475,7 @@ __device__ __noinline__ void val_partition(const float* vsig, int L, int64_t sta
 //      value is monotone); only the few windows inside the band are evaluated exactly,
 //  (4) the exact middle values are the (k - #below)-th smallest exact values inside the band.
 // The result is bit-identical to selecting from the exactly evaluated array (tests: tests/test_validate.py against the
-// reference-generated fixture and the numpy oracle).  Degenerate data (band overflows VAL_BAND_CAP, non-finite
+// reference-generated fixture and the CPU restatement).  Degenerate data (band overflows VAL_BAND_CAP, non-finite
 // approximations) falls back to evaluating every window exactly.
 constexpr int VAL_WIN_CHUNK = 8;
 constexpr int VAL_BAND_CAP = 384;

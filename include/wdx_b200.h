@@ -392,6 +392,15 @@ int wdx_validate_run(wdx_validate* v, const float* signals, int64_t n, int64_t s
 int wdx_validate_run_ex(wdx_validate* v, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
                         const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
                         double* parts, void* stream);
+/* As wdx_validate_run_ex, plus DetectResults.open_pores when `open_pores` is not NULL (the column of the reference's
+ * detected_boundaries_*.csv.gz / failed_reads_*.csv.gz, adapted/output.py:26-51):
+ *   open_pores [n, WDX_VAL_PORES_LD] int32: [0] = number of positions find_open_pores(...).ravel() returns
+ *   (anomalies.py:16-35, combined.py:469-477; -1 = None: the step did not run for this read), [1 ..] the positions in
+ *   ascending order (at most WDX_VAL_PORES_LD - 1 of them are stored). */
+#define WDX_VAL_PORES_LD 64
+int wdx_validate_run_report(wdx_validate* v, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
+                            const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
+                            double* parts, int32_t* open_pores, void* stream);
 /* on != 0: stop at the first failing poly(A) candidate.  success and bounds are unchanged (the reference never sets
  * `success` back to True after a failed candidate, combined.py:540-610); the fail code, check bits and mvs_* values are
  * those of the FIRST failing candidate instead of the last one evaluated.  For callers that only need the verdict (the

@@ -216,6 +216,7 @@ def validate_one(row: np.ndarray, full_signal_len: int, adapter_end: int, polya_
         if code == OK and cfg.detect_open_pores:                    # :469-481
             pores = find_open_pores(sig[a0:a1], cfg.open_pore_min, cfg.open_pore_min_obs_diff)
             out["n_open_pores"] = int(pores.size)
+            out["open_pores"] = pores + a0                         # DetectResults.open_pores (None when the step is skipped)
             if pores.size > 0:
                 a0 = int(pores[-1]) + a0
                 if a1 - a0 < cfg.min_obs_adapter:
@@ -320,6 +321,12 @@ def validate_batch(signals: np.ndarray, full_lens, preds: np.ndarray, cfg: Valid
         vals[i] = r["vals"]
         pores[i] = r["n_open_pores"]
     return success, code, checks, bounds, vals, pores
+
+
+def open_pores_batch(signals: np.ndarray, full_lens, preds: np.ndarray, cfg: ValidateConfig):
+    """DetectResults.open_pores of every row (combined.py:469-477, 676): None or the int64 positions."""
+    return [validate_one(signals[i], int(full_lens[i]), int(preds[i, 0]), preds[i, 1:], cfg).get("open_pores")
+            for i in range(signals.shape[0])]
 
 
 def synthetic_case(seed: int, stride: int = 12000, k: int = 5):

@@ -101,6 +101,7 @@ def test_gpu_validate_matches_reference_and_oracle(gold, inputs):
     assert np.array_equal(vb.success, osuc) and np.array_equal(vb.code, ocode) and np.array_equal(vb.checks, ochk)
     assert np.array_equal(vb.bounds, obounds) and np.array_equal(vb.n_open_pores, opores)
     assert np.array_equal(vb.vals, ovals, equal_nan=True)
+    _check_open_pores(vb, ov.open_pores_batch(sig, lens, preds, cfg), "fixture")
     v.close()
     # verdict-only mode (what the chained pipeline uses): same success and boundaries, report of the first failing candidate
     v1 = combined.Validator(v.cfg, device=0, verdict_only=True)
@@ -203,6 +204,7 @@ def test_gpu_validate_fuzz_against_oracle():
                               open_pore_min_obs_diff=3, detect_med_shift=True, med_shift_window=77, med_shift_range=(-5.0, 60.0)),
             ov.ValidateConfig(detect_open_pores=False, real_signal_check=False, min_obs_adapter=0, adapter_mad_range=(0.0, 1e9),
                               pA_mean_adapter_med_scale_range=(0.5, ov.INF), median_shift_window=200)]
+    n_lists = 0
     for ci, cfg in enumerate(cfgs):
         pcfg = combined.ValidateConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)})
         for verdict_only in (False, True):
@@ -221,8 +223,33 @@ def test_gpu_validate_fuzz_against_oracle():
                 assert np.array_equal(vb.bounds, o[3]) and np.array_equal(vb.n_open_pores, o[5]), tag
                 bad = np.flatnonzero(~np.all((vb.vals == o[4]) | (np.isnan(vb.vals) & np.isnan(o[4])), axis=1))
                 assert bad.size == 0, (tag, bad[:5], vb.vals[bad[:2]], o[4][bad[:2]])
+                if cols == 2:   # DetectResults.open_pores: every kept position, None where the step did not run
+                    n_lists += _check_open_pores(vb, ov.open_pores_batch(sig, lens, pr, cfg), tag)
             v.close()
+    assert n_lists > 20
     assert len(set(o[1].tolist())) >= 3
+
+
+def _check_open_pores(vb, expected, tag):
+    """vb.open_pores rows against the oracle's lists; returns how many reads had more than one position."""
+    from warpdemux_b200.detect import combined
+
+    multi = 0
+    for i, exp in enumerate(expected):
+        if int(vb.code[i]) == 9:      # NaN error: the reference raises, no DetectResults fields at all
+            continue
+        if exp is not None and len(exp) > combined.PORES_LD - 1:      # more than a row lists: the count is still exact
+            assert int(vb.open_pores[i, 0]) == len(exp), (tag, i)
+            with pytest.raises(ValueError):
+                combined.open_pores_array(vb.open_pores[i])
+            continue
+        got = combined.open_pores_array(vb.open_pores[i])
+        if exp is None:
+            assert got is None, (tag, i, got)
+        else:
+            assert got is not None and got.tolist() == [int(x) for x in exp], (tag, i, got, exp)
+            multi += len(exp) > 1
+    return multi
 
 
 def test_detect_results_mirror_has_the_reference_fields():

@@ -25,7 +25,7 @@ EXPORTS = [
     "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_extract_ex", "wdx_fp_set_consensus", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms", "wdx_fp_set_long_slice_len", "wdx_fp_set_numpy1_promotion",
     "wdx_cnn_create", "wdx_cnn_destroy", "wdx_cnn_detect", "wdx_cnn_prepare", "wdx_cnn_predict", "wdx_cnn_score_len", "wdx_cnn_set_guard", "wdx_cnn_enable_timing",
     "wdx_cnn_last_kernel_ms",
-    "wdx_validate_create", "wdx_validate_destroy", "wdx_validate_run", "wdx_validate_enable_timing", "wdx_validate_last_kernel_ms", "wdx_validate_set_verdict_only", "wdx_validate_run_ex", "wdx_calibrate_rows", "wdx_validate_set_llr",
+    "wdx_validate_create", "wdx_validate_destroy", "wdx_validate_run", "wdx_validate_enable_timing", "wdx_validate_last_kernel_ms", "wdx_validate_set_verdict_only", "wdx_validate_run_ex", "wdx_validate_run_report", "wdx_calibrate_rows", "wdx_validate_set_llr",
 ]
 
 _lib = None
@@ -145,6 +145,8 @@ def load():
         L.wdx_validate_run.argtypes = [vp, vp, i64, i64, vp, vp, i32, vp, vp, vp, vp, vp]
         L.wdx_validate_run_ex.restype = i32
         L.wdx_validate_run_ex.argtypes = [vp, vp, i64, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.wdx_validate_run_report.restype = i32
+        L.wdx_validate_run_report.argtypes = [vp, vp, i64, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.wdx_calibrate_rows.restype = i32
         L.wdx_calibrate_rows.argtypes = [vp, i64, i64, vp, vp, vp, vp, i64, i32, vp]
         L.wdx_validate_set_verdict_only.restype = i32

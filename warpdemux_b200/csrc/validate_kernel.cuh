@@ -43,6 +43,7 @@ enum {
 };
 constexpr int VAL_NVALS = 12;
 constexpr int VAL_NPART = 18;  // adapter, polya, rna_preloaded x (start, len, mean, std, med, mad)
+constexpr int VAL_PORES_LD = 64;  // DetectResults.open_pores row: count (-1 = None), then up to 63 positions
 
 struct ValCfg {
     int min_obs_adapter;
@@ -69,6 +70,7 @@ struct ValArgs {
     int64_t* bounds;           // [n][3] adapter_start, adapter_end, polya_end
     double* vals;              // [n][VAL_NVALS] or nullptr
     double* parts;             // [n][VAL_NPART] partition statistics (signal_partitions.py:65-96) or nullptr
+    int32_t* pores;            // [n][VAL_PORES_LD] DetectResults.open_pores (count, positions ascending) or nullptr
     float* scratch;            // [gridDim.x][stride] moving-window statistics
     int verdict_only;          // stop at the first failing poly(A) candidate: same success / boundaries (success is never
                                // set back once a candidate failed), fail code and statistics of THAT candidate instead of the last
@@ -591,6 +593,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     __shared__ ValTree tree;
     __shared__ ValBand band;
     __shared__ int sh_i[6];
+    __shared__ int sh_pores[VAL_PORES_LD];
     __shared__ double sh_d[4];
     __shared__ double sh_v[VAL_NVALS];
     const int tid = threadIdx.x;
@@ -653,6 +656,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         int64_t a0 = 0;
         int64_t pe_best = a.ld > 1 ? pr[1] : 0;
         int code = VAL_OK, checks = 0, n_pores = 0;
+        int pores_cnt = -1, pores_single = 0;   // open_pores as the reference reports it: None / the kept positions
         // reported statistics live in shared memory (thread 0 writes them as they are found); the fill above is
         // ordered before those writes by the barrier of the NaN vote
 
@@ -699,7 +703,8 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                     for (int q = max(0, i - D + 1); q < i; q++) near |= (vsig[q] >= lo);
                     if (!near) {
                         atomicMax(&sh_i[3], i);
-                        atomicAdd(&sh_i[4], 1);
+                        const int slot = atomicAdd(&sh_i[4], 1);
+                        if (slot < VAL_PORES_LD - 1) sh_pores[1 + slot] = i;
                     }
                 }
             }
@@ -713,6 +718,10 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                 a0 = first;
             }
             if (cnt > 0 && a1 - a0 < c.min_obs_adapter) code = VAL_OPEN_PORE;
+            // find_open_pores(...).ravel() (anomalies.py:16-35): the kept positions, else the last open-pore sample, else
+            // the single one, else an empty array
+            pores_cnt = cnt > 1 ? (sh_i[4] > 0 ? sh_i[4] : 1) : cnt;
+            pores_single = (cnt > 1 && sh_i[4] > 0) ? -1 : (int)a0;
         }
 
         if (code == VAL_OK && c.real_signal_check) {
@@ -852,6 +861,24 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                 val_partition(vsig, L, a0, a1, po, tree, vs, s);
                 val_partition(vsig, L, a1, pe_best, po + 6, tree, vs, s);
                 val_partition(vsig, L, pe_best, (int64_t)L, po + 12, tree, vs, s);
+            }
+        }
+        if (a.pores) {
+            __syncthreads();
+            if (tid == 0) {
+                int32_t* po = a.pores + r * VAL_PORES_LD;
+                po[0] = pores_cnt;
+                if (pores_cnt > 0 && pores_single >= 0) po[1] = pores_single;
+                else if (pores_cnt > 0) {   // found in parallel: a handful of entries, insertion sort
+                    const int m = min(pores_cnt, VAL_PORES_LD - 1);
+                    for (int i = 1; i < m; i++) {
+                        const int v = sh_pores[1 + i];
+                        int j = i - 1;
+                        for (; j >= 0 && sh_pores[1 + j] > v; j--) sh_pores[2 + j] = sh_pores[1 + j];
+                        sh_pores[2 + j] = v;
+                    }
+                    for (int i = 0; i < m; i++) po[1 + i] = sh_pores[1 + i];
+                }
             }
         }
         if (tid == 0) {

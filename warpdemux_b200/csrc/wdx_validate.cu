@@ -17,7 +17,7 @@ struct wdx_validate {
     int smem_max = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr;
-    DevBuf sig, len, preds, success, info, bounds, vals, parts, scratch, counter;
+    DevBuf sig, len, preds, success, info, bounds, vals, parts, pores, scratch, counter;
     // LLR fallback (wdx_validate_set_llr): proposed boundaries, mask, per-read median / MAD
     bool llr_on = false;
     LlrCfg llr{};
@@ -143,7 +143,7 @@ int wdx_validate_create(const wdx_validate_config* cfg, int device, wdx_validate
 void wdx_validate_destroy(wdx_validate* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->parts, &h->scratch, &h->counter,
+    for (DevBuf* b : {&h->sig, &h->len, &h->preds, &h->success, &h->info, &h->bounds, &h->vals, &h->parts, &h->pores, &h->scratch, &h->counter,
                       &h->preds2, &h->todo, &h->medmad})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -218,9 +218,15 @@ int wdx_validate_last_kernel_ms(wdx_validate* h, double* ms, int* launches) {
     return WDX_OK;
 }
 
+int wdx_validate_run_report(wdx_validate* h, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
+                            const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
+                            double* parts, int32_t* open_pores, void* stream);
+
 int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
                         const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
-                        double* parts, void* stream);
+                        double* parts, void* stream) {
+    return wdx_validate_run_report(h, signals, n, stride, full_len, preds, ld, success, info, bounds, vals, parts, nullptr, stream);
+}
 
 int wdx_validate_run(wdx_validate* h, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
                      const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
@@ -228,9 +234,9 @@ int wdx_validate_run(wdx_validate* h, const float* signals, int64_t n, int64_t s
     return wdx_validate_run_ex(h, signals, n, stride, full_len, preds, ld, success, info, bounds, vals, nullptr, stream);
 }
 
-int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
-                        const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
-                        double* parts, void* stream) {
+int wdx_validate_run_report(wdx_validate* h, const float* signals, int64_t n, int64_t stride, const int32_t* full_len,
+                            const int64_t* preds, int32_t ld, uint8_t* success, int32_t* info, int64_t* bounds, double* vals,
+                            double* parts, int32_t* open_pores, void* stream) {
     if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
     if (n < 0 || stride < 1 || ld < 1) return fail(WDX_ERR_INVALID, "n=%lld stride=%lld ld=%d", (long long)n, (long long)stride, ld);
     if (n == 0) return WDX_OK;
@@ -278,12 +284,14 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
         preds_d = (const int64_t*)h->preds.p;
     }
     const bool suc_dev = mem_kind(success) == 2, info_dev = mem_kind(info) == 2, bnd_dev = mem_kind(bounds) == 2,
-               val_dev = vals && mem_kind(vals) == 2, part_dev = parts && mem_kind(parts) == 2;
+               val_dev = vals && mem_kind(vals) == 2, part_dev = parts && mem_kind(parts) == 2,
+               pore_dev = open_pores && mem_kind(open_pores) == 2;
     if (!suc_dev && (rc = h->success.reserve((size_t)n))) return rc;
     if (!info_dev && (rc = h->info.reserve((size_t)n * 16))) return rc;
     if (!bnd_dev && (rc = h->bounds.reserve((size_t)n * 24))) return rc;
     if (vals && !val_dev && (rc = h->vals.reserve((size_t)n * VAL_NVALS * 8))) return rc;
     if (parts && !part_dev && (rc = h->parts.reserve((size_t)n * VAL_NPART * 8))) return rc;
+    if (open_pores && !pore_dev && (rc = h->pores.reserve((size_t)n * VAL_PORES_LD * 4))) return rc;
 
     // persistent grid: as many CTAs as fit (shared memory bound), each owning one scratch row
     int per_sm = 1;
@@ -304,6 +312,7 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
     a.bounds = bnd_dev ? bounds : (int64_t*)h->bounds.p;
     a.vals = vals ? (val_dev ? vals : (double*)h->vals.p) : nullptr;
     a.parts = parts ? (part_dev ? parts : (double*)h->parts.p) : nullptr;
+    a.pores = open_pores ? (pore_dev ? open_pores : (int32_t*)h->pores.p) : nullptr;
     a.scratch = (float*)h->scratch.p;
     a.verdict_only = h->verdict_only ? 1 : 0;
     if ((rc = h->counter.reserve(64))) return rc;
@@ -395,6 +404,7 @@ int wdx_validate_run_ex(wdx_validate* h, const float* signals, int64_t n, int64_
     if (!bnd_dev) { CUDA_TRY(cudaMemcpyAsync(bounds, a.bounds, (size_t)n * 24, cudaMemcpyDeviceToHost, st)); any_host = true; }
     if (vals && !val_dev) { CUDA_TRY(cudaMemcpyAsync(vals, a.vals, (size_t)n * VAL_NVALS * 8, cudaMemcpyDeviceToHost, st)); any_host = true; }
     if (parts && !part_dev) { CUDA_TRY(cudaMemcpyAsync(parts, a.parts, (size_t)n * VAL_NPART * 8, cudaMemcpyDeviceToHost, st)); any_host = true; }
+    if (open_pores && !pore_dev) { CUDA_TRY(cudaMemcpyAsync(open_pores, a.pores, (size_t)n * VAL_PORES_LD * 4, cudaMemcpyDeviceToHost, st)); any_host = true; }
     // host buffers (inputs staged from pageable memory, results) are only safe to touch after the stream drained
     if (any_host || sig_kind != 2 || len_d != full_len || preds_d != preds) CUDA_TRY(cudaStreamSynchronize(st));
     return WDX_OK;

@@ -26,6 +26,7 @@ from . import cnn as _cnn
 INF = float("inf")
 N_VALS = 12
 N_PART = 18
+PORES_LD = 64     # WDX_VAL_PORES_LD
 PART_FIELDS = tuple(f"{p}_{f}" for p in ("adapter", "polya", "rna_preloaded") for f in ("start", "len", "mean", "std", "med", "mad"))
 FAIL_REASONS = {
     0: None,
@@ -172,9 +173,8 @@ def _c_config(cfg: ValidateConfig) -> _CValidateConfig:
 @dataclass
 class DetectResults:
     """adapted/container_types.py:14-77: the reference's fields in the reference's order (so `to_dict()` yields the
-    columns of its detected_boundaries table), then this package's extras.  Not reproduced: `open_pores` holds only the
-    position adapter_start moved to (the reference lists every kept open-pore sample), `llr_trace` / start-peak fields
-    belong to detectors that are not on the GPU path."""
+    columns of its detected_boundaries table), then this package's extras.  Not reproduced: `llr_trace` (dropped by the
+    reference's writer) and the start-peak fields, which belong to a detector that is not on the GPU path."""
     success: bool
 
     signal_len: Optional[int] = None
@@ -263,6 +263,7 @@ class ValidationBatch:
     vals: np.ndarray           # float64 [n, N_VALS]
     kernel_ms: Optional[float] = field(default=None)
     parts: Optional[np.ndarray] = field(default=None)   # float64 [n, N_PART] partition statistics (PART_FIELDS), NaN = None
+    open_pores: Optional[np.ndarray] = field(default=None)   # int32 [n, PORES_LD]: count (-1 = None), positions
     source: Optional[np.ndarray] = field(default=None)  # int32 [n] info[.][3]: bits 0-1 boundaries validated (0 cnn, 1 hail mary,
                                                         # 2 llr), bit 2 hail mary ran, bit 3 full LLR ran
 
@@ -312,12 +313,12 @@ class Validator:
         return self._h
 
     def run_raw(self, signals, n: int, stride: int, full_lens, preds, ld: int, success, info, bounds, vals=None, stream: int = 0,
-                parts=None):
+                parts=None, open_pores=None):
         """Pointer-level call (numpy arrays, torch tensors or addresses; host or device memory)."""
         p = _cnn._ptr
-        rc = _lib.load().wdx_validate_run_ex(self._handle(), p(signals), int(n), int(stride), p(full_lens), p(preds), int(ld),
-                                             p(success), p(info), p(bounds), p(vals), p(parts), stream or None)
-        _lib.check(rc, "wdx_validate_run_ex")
+        rc = _lib.load().wdx_validate_run_report(self._handle(), p(signals), int(n), int(stride), p(full_lens), p(preds), int(ld),
+                                                 p(success), p(info), p(bounds), p(vals), p(parts), p(open_pores), stream or None)
+        _lib.check(rc, "wdx_validate_run_report")
 
     def enable_timing(self, on: bool = True):
         _lib.check(_lib.load().wdx_validate_enable_timing(self._handle(), int(on)), "wdx_validate_enable_timing")
@@ -339,10 +340,11 @@ class Validator:
         bounds = np.zeros((n, 3), np.int64)
         vals = np.full((n, N_VALS), np.nan)
         parts = np.full((n, N_PART), np.nan) if partitions else None
+        pores = np.full((n, PORES_LD), -1, np.int32)
         if n:
-            self.run_raw(sig, n, stride, lens, pr, pr.shape[1], success, info, bounds, vals, parts=parts)
+            self.run_raw(sig, n, stride, lens, pr, pr.shape[1], success, info, bounds, vals, parts=parts, open_pores=pores)
         return ValidationBatch(success, info[:, 0].copy(), info[:, 1].copy(), info[:, 2].copy(), bounds, vals, parts=parts,
-                               source=info[:, 3].copy())
+                               open_pores=pores, source=info[:, 3].copy())
 
     def close(self):
         if self._h is not None:
@@ -378,6 +380,17 @@ def _opt(x: float) -> Optional[float]:
     return None if x != x else float(x)
 
 
+def open_pores_array(row: Optional[np.ndarray]) -> Optional[np.ndarray]:
+    """One row of `ValidationBatch.open_pores` -> what the reference stores in DetectResults.open_pores: None when
+    the open-pore step did not run, else the int64 positions (combined.py:469-477)."""
+    if row is None or row[0] < 0:
+        return None
+    m = int(row[0])
+    if m > PORES_LD - 1:
+        raise ValueError(f"{m} open pores in one adapter: more than the {PORES_LD - 1} the validation kernel lists")
+    return row[1:1 + m].astype(np.int64)
+
+
 def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, stride: int, primary_method: str = "cnn",
                       llr_ran: bool = False) -> List[DetectResults]:
     out = []
@@ -395,10 +408,14 @@ def to_detect_results(vb: ValidationBatch, preds: np.ndarray, full_signal_lens, 
             polya_candidates=np.asarray(preds[i, 1:]).copy() if src == 0 else np.array([int(vb.bounds[i, 2])]),
             mvs_detect_mean_at_loc=_opt(v[5]), mvs_detect_var_at_loc=_opt(v[6]), mvs_detect_polya_med=_opt(v[7]),
             mvs_detect_polya_local_range=_opt(v[8]), mvs_detect_med_shift=_opt(v[9]), adapter_rna_median_shift=_opt(v[10]),
-            real_adapter_mean_start=_opt(v[2]), real_adapter_mean_end=_opt(v[3]), real_adapter_local_range=_opt(v[4]),
+            # np.float32 like the reference's np.mean over float32 samples (real_range.py:47-48): a table whose rows all
+            # carry the value gets a float32 column, which pandas rounds and prints differently from float64
+            real_adapter_mean_start=None if v[2] != v[2] else np.float32(v[2]),
+            real_adapter_mean_end=None if v[3] != v[3] else np.float32(v[3]), real_adapter_local_range=_opt(v[4]),
             n_open_pores=int(vb.n_open_pores[i]), fail_reason=vb.fail_reason(i),
             needs_llr_fallback=not bool(vb.success[i]) and not llr_ran, detect_source=src,
-            open_pores=np.array([int(vb.bounds[i, 0])]) if vb.n_open_pores[i] > 0 else None,
+            open_pores=(open_pores_array(vb.open_pores[i]) if vb.open_pores is not None
+                        else (np.array([int(vb.bounds[i, 0])]) if vb.n_open_pores[i] > 0 else None)),
         )
         if vb.parts is not None:
             for name, x in zip(PART_FIELDS, vb.parts[i]):

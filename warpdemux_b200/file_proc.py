@@ -439,3 +439,47 @@ def detect_and_predict_on_preloaded_signals(preloaded_minibatch, model_predict, 
     finally:
         if demuxer is None:
             d.close()
+
+
+def demux_minibatches_to_dir(minibatches, model_predict, model_detect, spc, writer, predict: bool = True,
+                             validator: Optional["_combined.Validator"] = None, fp_config: Optional[FingerprintConfig] = None) -> dict:
+    """The reference's demux / prep run over an iterable of preloaded minibatches `(signals, full_lengths, read_ids)`
+    with its four outputs written as it writes them (file_proc.py:380-455 per minibatch, :627-724 writers):
+    detected_boundaries_*.csv.gz, failed_reads_*.csv.gz, barcode_fpts_*.npz, barcode_predictions_*.csv.gz through
+    `writer` (io.results.RunDirWriter; reads it already holds from `continue_from` are skipped, file_proc.py:205-214).
+    The full-report path: every DetectResults field of the reference's tables is produced (partition statistics, open
+    pores, fail reasons of the last poly(A) candidate), so it runs the three stages as separate calls instead of the
+    fused `MinibatchDemuxer` chain."""
+    from .sig_proc import batch_detect_results_to_fpt
+
+    v = validator or _combined.Validator(spc, device=getattr(model_detect, "device", None))
+    counts = {"reads": 0, "pass": 0, "fail": 0, "skipped": 0}
+    try:
+        for mb in minibatches:
+            signals, full_lengths, read_ids = mb[0], mb[1], mb[2]
+            signals = _cnn._as_batch(signals)
+            keep = np.array([rid not in writer.processed for rid in read_ids], dtype=bool)
+            counts["skipped"] += int((~keep).sum())
+            if not keep.all():
+                signals, full_lengths = signals[keep], np.asarray(full_lengths)[keep]
+                read_ids = [rid for rid, k in zip(read_ids, keep) if k]
+            if len(read_ids) == 0:
+                continue
+            dets = _combined.combined_detect_cnn(signals, full_lengths, model_detect, spc, validator=v, partitions=True)
+            results = batch_detect_results_to_fpt(signals, fp_config if fp_config is not None else spc, dets)
+            for r, rid in zip(results, read_ids):
+                r.set_read_id(rid)
+            ok = [r for r in results if r.success]
+            predictions = None
+            if predict and ok:
+                predictions = model_predict.predict(np.vstack([r.barcode_fpt for r in ok]), pbar=False, nproc=1, return_df=True)
+                predictions = add_read_id_col_to_predictions(predictions, [r.read_id for r in ok])
+            writer.add(results, predictions)
+            counts["reads"] += len(results)
+            counts["pass"] += len(ok)
+            counts["fail"] += len(results) - len(ok)
+    finally:
+        if validator is None:
+            v.close()
+    writer.close()
+    return counts

@@ -7,6 +7,10 @@ reference's functions of the same names in warpdemux/file_proc.py, so that the G
     predictions/barcode_predictions_{i}.csv.gz save_predictions          file_proc.py:757-766
         header  #read_id,predicted_barcode,confidence_score,pXX...,p-1   (models/utils.py:36-43)
     add_read_id_col_to_predictions                                       file_proc.py:769-780
+    boundaries/detected_boundaries_{i}.csv.gz  save_detect_results("pass") file_proc.py:682-724 -> adapted/output.py:26-51
+    failed_reads/failed_reads_{i}.csv.gz       save_batch_outputs_fail     file_proc.py:650-665
+        one row per read: read_id, the DetectResults fields (container_types.py:14-77 minus success / llr_trace),
+        [fail_reason,] the fingerprint stage's adapter statistics (sig_proc.py:44-59); floats rounded to 3 decimals
     scan_processed_reads (resume)                                        file_proc.py:129-169
     yield_fpts_from_npz (input of `warpdemux predict`)                   file_proc.py:282-330
 
@@ -52,6 +56,123 @@ def save_fpts_arrays(read_ids: np.ndarray, barcode_fpts: np.ndarray, filename: s
     if dwell_times is not None:
         kw["dwell_times"] = np.asarray(dwell_times)
     np.savez(filename, **kw)
+
+
+def save_detected_boundaries(processing_results: Sequence, filename: str, save_fail_reasons: bool = False) -> None:
+    """adapted/output.py:26-51: `ReadResult.to_summary_dict()` rows -> csv(.gz), floats rounded to 3 decimals.  The table's
+    columns, their order and the text of every cell are fixed by the reference's dataclasses and by pandas."""
+    df = pd.DataFrame([pr.to_summary_dict() for pr in processing_results])
+    if not df.empty:
+        drop = ["success", "llr_trace"] + ([] if save_fail_reasons else ["fail_reason"])
+        df = df.drop(columns=[c for c in drop if c in df.columns])
+    df.round(3).to_csv(filename, index=False)
+
+
+def save_detect_results(pass_or_fail: str, results: Sequence, batch_idx: int, save_fpts: bool = True, save_dwell_time: bool = False,
+                        save_boundaries: bool = True, output_dir_boundaries: str = "", output_dir_fpts: str = "",
+                        output_dir_fail: str = "", **kwargs):
+    """file_proc.py:682-724: detected_boundaries_{i}.csv.gz (+ barcode_fpts_{i}.npz) for passed reads,
+    failed_reads_{i}.csv.gz (with the fail reasons) for failed ones."""
+    if pass_or_fail == "pass":
+        fn, dirn = "detected_boundaries", output_dir_boundaries
+    elif pass_or_fail == "fail":
+        fn, dirn = "failed_reads", output_dir_fail
+    else:
+        raise ValueError(f"Invalid pass_or_fail: {pass_or_fail}. Must be 'pass' or 'fail'.")
+    if save_boundaries:
+        save_detected_boundaries(results, os.path.join(dirn, f"{fn}_{batch_idx}.csv.gz"), save_fail_reasons=pass_or_fail == "fail")
+    if pass_or_fail == "pass" and save_fpts:
+        read_ids, signals, _ = save_fpts_signals(results, os.path.join(output_dir_fpts, f"barcode_fpts_{batch_idx}.npz"),
+                                                 save_dwell_time=save_dwell_time)
+        return read_ids, signals
+    return None
+
+
+class RunDirWriter:
+    """The three output collectors of the reference's demux / prep run (file_proc.py:500-584 `queue_batch_processor` with
+    save_batch_outputs_pass / _fail / save_batch_predictions, :627-679) without the queues: results are re-cut into files
+    of `batch_size_output` rows, batch indices continue after the ones `continue_from` already holds
+    (handle_previous_results, file_proc.py:172-185), directory names are OutputConfig's (config/file_proc.py:18-49)."""
+
+    def __init__(self, output_dir: str, batch_size_output: int = 4000, save_predictions: bool = True, save_fpts: bool = False,
+                 save_dwell_time: bool = False, save_boundaries: bool = True, continue_from: Optional[str] = None):
+        self.dir_pred = os.path.join(output_dir, "predictions")
+        self.dir_fail = os.path.join(output_dir, "failed_reads")
+        self.dir_fpts = os.path.join(output_dir, "fingerprints")
+        self.dir_boundaries = os.path.join(output_dir, "boundaries")
+        self.batch = int(batch_size_output)
+        self.opt = dict(save_predictions=save_predictions, save_fpts=save_fpts, save_dwell_time=save_dwell_time,
+                        save_boundaries=save_boundaries)
+        os.makedirs(self.dir_fail, exist_ok=True)
+        for on, d in ((save_predictions, self.dir_pred), (save_boundaries, self.dir_boundaries), (save_fpts, self.dir_fpts)):
+            if on:
+                os.makedirs(d, exist_ok=True)
+        self.processed: Set[str] = set()
+        self.bidx = {"pass": 0, "fail": 0, "predict": 0}
+        if continue_from:
+            result_type = "predictions" if save_predictions else "fingerprints"
+            self.processed, max_pass, max_fail = scan_processed_reads(continue_from, scan_failed=True, result_type=result_type)
+            self.bidx = {"pass": max_pass + 1, "fail": max_fail + 1, "predict": max_pass + 1}
+        self._pass: List = []
+        self._fail: List = []
+        self._pred: List[pd.DataFrame] = []
+        self._pred_rows = 0
+        self.files_written: List[str] = []
+
+    def _flush_pass(self, rows: Sequence) -> None:
+        i = self.bidx["pass"]
+        if self.opt["save_boundaries"] or self.opt["save_fpts"]:
+            save_detect_results("pass", rows, i, save_fpts=self.opt["save_fpts"], save_dwell_time=self.opt["save_dwell_time"],
+                                save_boundaries=self.opt["save_boundaries"], output_dir_boundaries=self.dir_boundaries,
+                                output_dir_fpts=self.dir_fpts)
+            if self.opt["save_boundaries"]:
+                self.files_written.append(os.path.join(self.dir_boundaries, f"detected_boundaries_{i}.csv.gz"))
+            if self.opt["save_fpts"]:
+                self.files_written.append(os.path.join(self.dir_fpts, f"barcode_fpts_{i}.npz"))
+        self.bidx["pass"] += 1
+
+    def _flush_fail(self, rows: Sequence) -> None:
+        i = self.bidx["fail"]
+        save_detect_results("fail", rows, i, output_dir_fail=self.dir_fail, save_fpts=False, save_dwell_time=False, save_boundaries=True)
+        self.files_written.append(os.path.join(self.dir_fail, f"failed_reads_{i}.csv.gz"))
+        self.bidx["fail"] += 1
+
+    def _flush_pred(self, df: pd.DataFrame) -> None:
+        i = self.bidx["predict"]
+        path = os.path.join(self.dir_pred, f"barcode_predictions_{i}.csv.gz")
+        save_predictions(df, path)
+        self.files_written.append(path)
+        self.bidx["predict"] += 1
+
+    def add(self, read_results: Sequence, predictions: Optional[pd.DataFrame] = None) -> None:
+        """One minibatch: `ReadResult`s (split here into pass / fail like file_proc.py:418-440) and the predictions table of
+        its passed reads ('#read_id' column first)."""
+        for r in read_results:
+            (self._pass if r.success else self._fail).append(r)
+        while len(self._pass) >= self.batch:                       # _queue_batch_processor_list
+            self._flush_pass(self._pass[:self.batch])
+            self._pass = self._pass[self.batch:]
+        while len(self._fail) >= self.batch:
+            self._flush_fail(self._fail[:self.batch])
+            self._fail = self._fail[self.batch:]
+        if predictions is not None and self.opt["save_predictions"] and len(predictions):
+            self._pred.append(predictions)
+            self._pred_rows += len(predictions)
+            while self._pred_rows >= self.batch:                   # _queue_batch_processor_df
+                cur = pd.concat(self._pred, axis=0)
+                self._flush_pred(cur.iloc[:self.batch].copy())
+                self._pred = [cur.iloc[self.batch:]]
+                self._pred_rows -= self.batch
+
+    def close(self) -> None:
+        """The remainders (file_proc.py:577-584)."""
+        if self._pass:
+            self._flush_pass(self._pass)
+        if self._fail:
+            self._flush_fail(self._fail)
+        if self._pred_rows > 0:
+            self._flush_pred(pd.concat(self._pred, axis=0))
+        self._pass, self._fail, self._pred, self._pred_rows = [], [], [], 0
 
 
 def save_predictions(predictions: pd.DataFrame, filename: str) -> None:

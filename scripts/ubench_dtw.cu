@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cmath>
+#include <cstring>
 #include "dtw_band.cuh"
 #include "dtw_band_x2.cuh"
 using namespace wdx;
@@ -59,6 +60,32 @@ __global__ void __launch_bounds__(128, MINB) k_x2(const float* __restrict__ X, c
     out[r] = acc;
 }
 
+// offset ("E") form, the production default; MI = 1: 3-input minimum as VIMNMX3 on the bit patterns
+template <int MINB, int MI>
+__global__ void __launch_bounds__(128, MINB) k_x2e(const float* __restrict__ X, const float* __restrict__ SVP, float* out, int n, float p2rt) {
+    extern __shared__ float sm[];
+    for (int q = threadIdx.x; q < NSV * 48; q += blockDim.x) sm[q] = SVP[q];
+    __syncthreads();
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 ap[(L + 1) / 2];
+#pragma unroll
+    for (int q = 0; q < (L + 1) / 2; q++) ap[q] = pack2(X[(size_t)r * L + 2 * q], (2 * q + 1 < L) ? X[(size_t)r * L + 2 * q + 1] : 0.f);
+    float acc = 0.f;
+    for (int s = 0; s < NSV; s++) {
+        u64 sp[L];
+        const float* row = sm + s * 48;
+#pragma unroll
+        for (int t = 1; t < L; t += 2) {
+            float4 w = *reinterpret_cast<const float4*>(row + (t - 1) * 2);
+            sp[t] = pack2(w.x, w.y);
+            if (t + 1 < L) sp[t + 1] = pack2(w.z, w.w);
+        }
+        sp[0] = 0;
+        acc += dtw_band_f32_x2e<L, W, MI>(ap, sp, p2rt);
+    }
+    out[r] = acc;
+}
+
 int main(int argc, char** argv) {
     int n = 148 * 4 * 128 * 4;
     std::vector<float> X((size_t)n * L), SV(NSV * 28, 0.f), SVP(NSV * 48, 0.f);
@@ -98,6 +125,18 @@ int main(int argc, char** argv) {
     timeit("x2_occ2_imm", k_x2<2, 0, 1>, NSV * 48 * 4, o2);
     timeit("x2_occ3_2min", k_x2<3, 2, 0>, NSV * 48 * 4, o2);
     timeit("x2_occ2_2min", k_x2<2, 2, 0>, NSV * 48 * 4, o2);
+    timeit("x2e_occ4_fmnmx3", k_x2e<4, 0>, NSV * 48 * 4, o2);
+    timeit("x2e_occ4_vimnmx3", k_x2e<4, 1>, NSV * 48 * 4, o2);
+    timeit("x2e_occ3_vimnmx3", k_x2e<3, 1>, NSV * 48 * 4, o2);
+    timeit("x2_occ3_vimnmx3", k_x2<3, 1, 0>, NSV * 48 * 4, o2);
+    {
+        k_x2e<4, 0><<<n / 128, 128, NSV * 48 * 4>>>(dX, dSVP, o1, n, 0.01f);
+        k_x2e<4, 1><<<n / 128, 128, NSV * 48 * 4>>>(dX, dSVP, o2, n, 0.01f);
+        std::vector<float> g1(n), g2(n);
+        cudaMemcpy(g1.data(), o1, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(g2.data(), o2, n * 4, cudaMemcpyDeviceToHost);
+        int bad = 0; for (int i = 0; i < n; i++) if (memcmp(&g1[i], &g2[i], 4)) bad++;
+        printf("E form, VIMNMX3 vs FMNMX3 bitwise mismatches: %d of %d\n", bad, n);
+    }
     k_scalar<4, 0><<<n / 128, 128, NSV * 28 * 4>>>(dX, dSV, o1, n, 0.01f);
     k_x2<3, 2><<<n / 128, 128, NSV * 48 * 4>>>(dX, dSVP, o2, n, 0.01f);
     std::vector<float> h1(n), h2(n);

@@ -31,6 +31,12 @@ DEF_KERNEL(k_iadd, int a[NCH]; int b = (int)seed; int c = b + 3, _Pragma("unroll
            _Pragma("unroll") for (int i = 0; i < NCH; i++) asm volatile("add.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)),
            int s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(s + c))
 
+// 3-input integer minimum (VIMNMX3): what a DTW cell could use on the bit patterns of non-negative floats instead of
+// FMNMX3.  No PTX spelling: the intrinsic; the empty asm keeps the compiler from folding the idempotent chain.
+DEF_KERNEL(k_vimnmx3, int a[NCH]; int b = (int)seed + 7; int c = b + 3, _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = b + i + threadIdx.x,
+           _Pragma("unroll") for (int i = 0; i < NCH; i++) { a[i] = __vimin3_s32(a[i], b, c); asm volatile("" : "+r"(a[i])); },
+           int s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(s + c))
+
 #define PDECL u64 a[NCH], b, c
 #define PINIT b = __float_as_uint(seed) | ((u64)__float_as_uint(seed * 2) << 32); c = b + 5; _Pragma("unroll") for (int i = 0; i < NCH; i++) a[i] = b + i + threadIdx.x
 #define PFINI u64 s = 0; _Pragma("unroll") for (int i = 0; i < NCH; i++) s += a[i]; out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s
@@ -93,6 +99,18 @@ DEF_KERNEL(k_mix_x2_min2, PDECL; float m[NCH]; float fb = seed; float fc = seed 
            },
            PFINI; out[0] += m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7])
 
+DEF_KERNEL(k_mix_x2_imin3, PDECL; int m[NCH]; int fb = (int)seed + 11; int fc = fb * 3, PINIT; _Pragma("unroll") for (int i = 0; i < NCH; i++) m[i] = fb * i + threadIdx.x,
+           _Pragma("unroll") for (int i = 0; i < NCH; i += 2) {
+               asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(b));
+               asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c));
+               asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(c));
+               m[i] = __vimin3_s32(m[i], fb, fc); asm volatile("" : "+r"(m[i]));
+               m[i + 1] = __vimin3_s32(m[i + 1], fb, fc); asm volatile("" : "+r"(m[i + 1]));
+           },
+           PFINI; out[0] += (float)(m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7]))
+// one packed-half alternative: the two minima of a cell pair as ONE instruction on packed 16-bit halves is not
+// applicable (values are float32), listed only for completeness of the search in DESIGN.md
+
 template <typename K>
 void run(const char* name, K kern, double instr_per_body, float* out) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -114,6 +132,7 @@ int main() {
     run("FMNMX", k_fmnmx, NCH, out);
     run("FMNMX3", k_fmnmx3, NCH, out);
     run("IMNMX", k_imnmx, NCH, out);
+    run("VIMNMX3", k_vimnmx3, NCH, out);
     run("IADD", k_iadd, NCH, out);
     run("FFMA2", k_ffma2, NCH, out);
     run("FADD2", k_fadd2, NCH, out);
@@ -127,5 +146,6 @@ int main() {
     run("mix 3FFMA,MIN3", k_mix_3fma_min3, NCH * 4, out);
     run("mix x2 (5 per 2 cells)", k_mix_x2, NCH / 2 * 5, out);
     run("mix x2 min2", k_mix_x2_min2, NCH / 2 * 5, out);
+    run("mix x2 VIMNMX3", k_mix_x2_imin3, NCH / 2 * 5, out);
     return 0;
 }

@@ -584,21 +584,888 @@ __device__ __noinline__ float val_window_median(const float* vsig, int e, int m,
 
 __device__ __forceinline__ bool val_in_range(double v, double lo, double hi) { return lo <= v && v <= hi; }
 
+// ---- several selections at once -------------------------------------------------------------------------------------
+// The checks of one read need ~10 exact order statistics over different ranges of the same row.  Run one after the
+// other (block_ranks) each costs ~10 CTA-wide barriers for a few microseconds of work: the kernel was barrier- and
+// latency-bound (profiles/r02_ncu_full_validate_real_reads_before.json).  Here the independent selections of a read
+// are JOBS of one round: every pass (histogram, gather) walks all jobs back to back with no barrier in between, the
+// per-job histogram scans and the per-rank exact rankings run on different warps at the same time.  A job is a range
+// of samples, |sample - median|, 16-bit codes, or the exact moving mean of the range; bins are a monotone map of the
+// value (linear over bounds of the range known beforehand, so no min / max pass), the members of the bins that hold the
+// wanted ranks are gathered and ranked exactly on their order keys.  Crowded bins fall back to radix selection.
+constexpr int MS_BINS = 1024;          // 16-bit counters, two per word
+constexpr int MS_MAXJ = 9;             // jobs per round
+constexpr int MS_MAXQ = 24;            // ranks per round
+constexpr int MS_MAXS = 16;            // distinct (job, bin) candidate lists per round
+constexpr int MS_CAND = 224;           // members kept per list
+constexpr int MS_CHUNKS = (MS_MAXS * MS_CAND * 4) / 16;   // chunk sums (two doubles each) of the moving variance alias the candidate lists
+
+struct MsJob {
+    const float* p;               // modes 0, 1, 3: first sample of the range
+    const unsigned short* c;      // mode 2: codes
+    int n;                        // values
+    int mode;                     // 0 sample, 1 |sample - med|, 2 stored code, 3 code of the moving mean over w samples, made on the fly
+    int w;
+    float med, vmin, scale;       // modes 0, 1: bin = (value - vmin) * scale
+    int flo, fsh;                 // modes 2, 3: bin = 0 below flo, else 1 + ((code - flo) >> fsh) (the focus of the histogram)
+    int chunk;                    // mode 3: consecutive windows per thread (sliding sums)
+    uint32_t kb;                  // mode 3: code = order key of the float32 mean - kb
+    int q0, nq;                   // ranks q0 .. q0 + nq - 1
+};
+
+struct MsState {
+    uint32_t hist[MS_MAXJ][MS_BINS / 2];
+    uint32_t cand[MS_MAXS][MS_CAND];
+    MsJob job[MS_MAXJ];
+    uint32_t slot_n[MS_MAXS];
+    uint32_t q_rank[MS_MAXQ], q_r[MS_MAXQ], q_cnt[MS_MAXQ], q_key[MS_MAXQ];
+    int q_job[MS_MAXQ], q_bin[MS_MAXQ], q_slot[MS_MAXQ];    // q_slot: candidate list, -1 = crowded (radix fallback)
+    int nj, nq, n_slots, crowded;
+};
+
+__device__ __forceinline__ int ms_code_bin(const MsJob& j, int cv) {
+    return cv < j.flo ? 0 : min(MS_BINS - 1, 1 + ((cv - j.flo) >> j.fsh));
+}
+
+template <int MODE>
+__device__ __forceinline__ void ms_eval(const MsJob& j, int i, uint32_t& key, int& bin) {
+    if (MODE == 2) {
+        const int cv = (int)j.c[i];
+        key = (uint32_t)cv;
+        bin = ms_code_bin(j, cv);
+    } else {
+        float x = j.p[i];
+        if (MODE == 1) x = fabsf(__fsub_rn(x, j.med));
+        key = f32_key(x);
+        bin = max(0, min(MS_BINS - 1, (int)__fmul_rn(__fsub_rn(x, j.vmin), j.scale)));
+    }
+}
+
+// Code of an (approximate) moving mean: the distance of its float32 order key from the key of a lower bound of the means.
+__device__ __forceinline__ int ms_mean_code(double mean, uint32_t kb) {
+    const uint32_t k = f32_key((float)mean);
+    return k > kb ? (int)min(k - kb, 0x7ffffff0u) : 0;
+}
+
+// Mode 3: thread t owns the windows [t * chunk, (t + 1) * chunk) and slides a float64 sum of the centred samples over them;
+// f(window, code) is called for each.  The same few flops again in every pass instead of an array of n codes.
+template <typename F>
+__device__ __forceinline__ void ms_mean_windows(const MsJob& j, F f) {
+    const int p0 = threadIdx.x * j.chunk;
+    if (p0 >= j.n) return;
+    const double cref = (double)j.p[0], inv_w = 1.0 / (double)j.w;
+    double s1 = 0.0;
+    for (int i = 0; i < j.w; i++) s1 += (double)j.p[p0 + i] - cref;
+    const int pe = min(p0 + j.chunk, j.n);
+    for (int p = p0;; p++) {
+        f(p, ms_mean_code(cref + s1 * inv_w, j.kb));
+        if (p + 1 >= pe) break;
+        s1 += ((double)j.p[p + j.w] - cref) - ((double)j.p[p] - cref);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void ms_hist_pass(const MsJob& j, uint32_t* hist) {
+    if (MODE == 3) {
+        ms_mean_windows(j, [&](int, int cv) {
+            const int bin = ms_code_bin(j, cv);
+            atomicAdd(&hist[bin >> 1], (bin & 1) ? 0x10000u : 1u);
+        });
+        return;
+    }
+    for (int i = threadIdx.x; i < j.n; i += FP_THREADS) {
+        uint32_t key;
+        int bin;
+        ms_eval<MODE>(j, i, key, bin);
+        atomicAdd(&hist[bin >> 1], (bin & 1) ? 0x10000u : 1u);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void ms_gather_pass(const MsJob& j, MsState& ms) {
+    int qb[6], qs[6], nd = 0;      // the job's distinct lists
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        qb[d] = -1;
+        qs[d] = 0;
+    }
+    for (int q = j.q0; q < j.q0 + j.nq; q++) {
+        const int sl = ms.q_slot[q];
+        if (sl < 0) continue;
+        bool seen = false;
+#pragma unroll
+        for (int d = 0; d < 6; d++) seen |= (d < nd && qs[d] == sl);
+        if (!seen) {
+#pragma unroll
+            for (int d = 0; d < 6; d++)
+                if (d == nd) {
+                    qb[d] = ms.q_bin[q];
+                    qs[d] = sl;
+                }
+            nd++;
+        }
+    }
+    if (nd == 0) return;
+    auto put = [&](uint32_t key, int bin) {
+#pragma unroll
+        for (int d = 0; d < 6; d++)
+            if (bin == qb[d]) {
+                const uint32_t pos = atomicAdd(&ms.slot_n[qs[d]], 1u);
+                if (pos < (uint32_t)MS_CAND) ms.cand[qs[d]][pos] = key;
+            }
+    };
+    if (MODE == 3) {
+        ms_mean_windows(j, [&](int, int cv) { put((uint32_t)cv, ms_code_bin(j, cv)); });
+        return;
+    }
+    for (int i = threadIdx.x; i < j.n; i += FP_THREADS) {
+        uint32_t key;
+        int bin;
+        ms_eval<MODE>(j, i, key, bin);
+        put(key, bin);
+    }
+}
+
+// One warp: exclusive scan of a job's histogram, the bin / rank inside the bin / population of every wanted rank, and
+// the candidate lists (ranks of one job that fall into the same bin share a list).
+__device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
+    const int lane = threadIdx.x & 31;
+    const MsJob& j = ms.job[jj];
+    constexpr int WPL = MS_BINS / 2 / 32;     // words per lane
+    const uint32_t* h = ms.hist[jj] + lane * WPL;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int t = 0; t < WPL; t++) sum += (h[t] & 0xffffu) + (h[t] >> 16);
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t run0 = inc - sum;
+    for (int q = j.q0; q < j.q0 + j.nq; q++) {
+        const uint32_t k = ms.q_rank[q];
+        if (k >= run0 && k < run0 + sum) {    // exactly one lane
+            uint32_t run = run0;
+#pragma unroll
+            for (int t = 0; t < WPL; t++) {
+                const uint32_t c0 = h[t] & 0xffffu, c1 = h[t] >> 16;
+                if (k >= run && k < run + c0) {
+                    ms.q_bin[q] = (lane * WPL + t) * 2;
+                    ms.q_r[q] = k - run;
+                    ms.q_cnt[q] = c0;
+                }
+                run += c0;
+                if (k >= run && k < run + c1) {
+                    ms.q_bin[q] = (lane * WPL + t) * 2 + 1;
+                    ms.q_r[q] = k - run;
+                    ms.q_cnt[q] = c1;
+                }
+                run += c1;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int q = j.q0; q < j.q0 + j.nq; q++) {
+            int sl = -2;
+            for (int u = j.q0; u < q; u++)
+                if (ms.q_bin[u] == ms.q_bin[q]) sl = ms.q_slot[u];
+            if (sl == -2) {
+                sl = -1;
+                if (ms.q_cnt[q] <= (uint32_t)MS_CAND) {
+                    sl = atomicAdd(&ms.n_slots, 1);
+                    if (sl >= MS_MAXS) sl = -1;
+                }
+            }
+            if (sl < 0) ms.crowded = 1;
+            ms.q_slot[q] = sl;
+        }
+    }
+}
+
+// The q_r-th smallest key of every rank's candidate list: the (rank, candidate) pairs are dealt out over the whole CTA.
+__device__ __forceinline__ void ms_rank_all(MsState& ms) {
+    const int nq = ms.nq;
+    int total = 0;
+    for (int q = 0; q < nq; q++) total += (ms.q_slot[q] >= 0) ? (int)ms.q_cnt[q] : 0;
+    for (int idx = threadIdx.x; idx < total; idx += FP_THREADS) {
+        int q = 0, t = idx;
+        for (;; q++) {
+            const int m = (ms.q_slot[q] >= 0) ? (int)ms.q_cnt[q] : 0;
+            if (t < m) break;
+            t -= m;
+        }
+        const uint32_t m = ms.q_cnt[q], r = ms.q_r[q];
+        const uint32_t* cd = ms.cand[ms.q_slot[q]];
+        const uint32_t x = cd[t];
+        uint32_t rank = 0;
+        for (uint32_t u = 0; u < m; u++) {
+            const uint32_t y = cd[u];
+            rank += (y < x) || (y == x && u < (uint32_t)t);
+        }
+        if (rank == r) ms.q_key[q] = x;
+    }
+}
+
+// A round: jobs and ranks are in `ms` (written before the caller's last barrier), histograms / list counters are zero.
+// On return (after a barrier) ms.q_key[q] holds the order key (or the code) of every rank.  `extra_*` let the caller run
+// its own work inside the phases of the round (no barrier of its own needed).
+template <typename F1, typename F2, typename F3>
+__device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_hist, F2 extra_scan, F3 extra_gather) {
+    const int warp = threadIdx.x >> 5;
+    const int nj = ms.nj, nq = ms.nq;
+    for (int jj = 0; jj < nj; jj++) {
+        const MsJob& j = ms.job[jj];
+        switch (j.mode) {
+            case 0: ms_hist_pass<0>(j, ms.hist[jj]); break;
+            case 1: ms_hist_pass<1>(j, ms.hist[jj]); break;
+            case 2: ms_hist_pass<2>(j, ms.hist[jj]); break;
+            default: ms_hist_pass<3>(j, ms.hist[jj]); break;
+        }
+    }
+    extra_hist();
+    __syncthreads();
+    if (warp < nj) ms_scan_job(ms, warp);
+    extra_scan();
+    __syncthreads();
+    for (int jj = 0; jj < nj; jj++) {
+        const MsJob& j = ms.job[jj];
+        switch (j.mode) {
+            case 0: ms_gather_pass<0>(j, ms); break;
+            case 1: ms_gather_pass<1>(j, ms); break;
+            case 2: ms_gather_pass<2>(j, ms); break;
+            default: ms_gather_pass<3>(j, ms); break;
+        }
+    }
+    extra_gather();
+    __syncthreads();
+    ms_rank_all(ms);
+    __syncthreads();
+    if (ms.crowded) {     // uniform; degenerate data only
+        for (int q = 0; q < nq; q++) {
+            if (ms.q_slot[q] >= 0) continue;
+            const MsJob j = ms.job[ms.q_job[q]];
+            const uint32_t k = ms.q_rank[q];
+            auto key_of = [&](int i) {
+                uint32_t key = 0;
+                int bin;
+                switch (j.mode) {
+                    case 0: ms_eval<0>(j, i, key, bin); break;
+                    case 1: ms_eval<1>(j, i, key, bin); break;
+                    case 2: ms_eval<2>(j, i, key, bin); break;
+                    default: {      // the window's own sum (no sliding): the same code up to the last bits, which the band absorbs
+                        const double cref = (double)j.p[0];
+                        double s1 = 0.0;
+                        for (int u = 0; u < j.w; u++) s1 += (double)j.p[i + u] - cref;
+                        key = (uint32_t)ms_mean_code(cref + s1 / (double)j.w, j.kb);
+                    }
+                }
+                return key;
+            };
+            const uint32_t key = block_select_u32(j.n, k, key_of, s);
+            __syncthreads();
+            if (threadIdx.x == 0) ms.q_key[q] = key;
+        }
+        __syncthreads();
+    }
+}
+
+// job / rank bookkeeping (one thread)
+__device__ __forceinline__ int ms_add_job(MsState& ms, const float* p, int n, int mode, float vmin, float vmax) {
+    const int jj = ms.nj++;
+    MsJob& j = ms.job[jj];
+    j.p = p;
+    j.c = nullptr;
+    j.n = n;
+    j.mode = mode;
+    j.w = 0;
+    j.med = 0.f;
+    j.vmin = vmin;
+    const float d = __fsub_rn(vmax, vmin);
+    float sc = (d > 0.f) ? __fdiv_rn((float)MS_BINS, d) : 0.f;
+    if (!(sc < 1e30f)) sc = 0.f;       // a point range or an overflowing scale: everything lands in bin 0 (radix fallback)
+    j.scale = sc;
+    j.flo = 0;
+    j.fsh = 0;
+    j.chunk = 1;
+    j.kb = 0;
+    j.q0 = ms.nq;
+    j.nq = 0;
+    return jj;
+}
+__device__ __forceinline__ int ms_add_rank(MsState& ms, int jj, uint32_t rank) {
+    const int q = ms.nq++;
+    ms.q_rank[q] = rank;
+    ms.q_job[q] = jj;
+    ms.q_slot[q] = -1;
+    ms.q_key[q] = 0;
+    ms.job[jj].nq++;
+    return q;
+}
+
+
+// np.add.reduce of n <= 512 float32 values in numpy's pairwise order by ONE warp: the recursion splits down to at most
+// four blocks of <= 128 elements, each summed with numpy's eight strided accumulators (eight lanes per block), combined
+// in numpy's tree, then the sequential tail.  All lanes get the result.  (One thread: 300 dependent additions.)
+template <typename F>
+__device__ __forceinline__ float warp_np_sum_f32(int lo, int n, F at) {
+    const int lane = threadIdx.x & 31, blk = lane >> 3, k = lane & 7;
+    // blocks 0, 1 = the left half (block 1 empty unless the half is longer than 128), blocks 2, 3 = the right half
+    int off[4] = {0, 0, 0, 0}, len[4] = {0, 0, 0, 0};
+    if (n <= 128) {
+        len[0] = n;
+    } else {
+        int h = n / 2;
+        h -= h % 8;
+        if (h <= 128) {
+            len[0] = h;
+        } else {
+            int q = h / 2;
+            q -= q % 8;
+            len[0] = q;
+            off[1] = q;
+            len[1] = h - q;
+        }
+        const int r = n - h;
+        off[2] = h;
+        if (r <= 128) {
+            len[2] = r;
+        } else {
+            int q2 = r / 2;
+            q2 -= q2 % 8;
+            len[2] = q2;
+            off[3] = h + q2;
+            len[3] = r - q2;
+        }
+    }
+    const int b0 = lo + (blk == 0 ? off[0] : blk == 1 ? off[1] : blk == 2 ? off[2] : off[3]);
+    const int m = blk == 0 ? len[0] : blk == 1 ? len[1] : blk == 2 ? len[2] : len[3];
+    const int m8 = (m < 8) ? 0 : m - (m % 8);
+    float r = 0.f;
+    if (m8 > 0) {
+        r = at(b0 + k);
+        for (int i = 8; i < m8; i += 8) r = __fadd_rn(r, at(b0 + i + k));
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));      // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7))
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    float res = r;                                             // 0 for a block of fewer than eight elements
+    for (int i = m8; i < m; i++) res = __fadd_rn(res, at(b0 + i));
+    const float s0 = __shfl_sync(0xffffffffu, res, 0), s1 = __shfl_sync(0xffffffffu, res, 8), s2 = __shfl_sync(0xffffffffu, res, 16),
+                s3 = __shfl_sync(0xffffffffu, res, 24);
+    const float left = len[1] ? __fadd_rn(s0, s1) : s0;
+    if (n <= 128) return left;
+    const float right = len[3] ? __fadd_rn(s2, s3) : s2;
+    return __fadd_rn(left, right);
+}
+
+// ---- the common read, all checks in two rounds --------------------------------------------------------------------
+// A read whose CNN boundaries allow every check to run (adapter end inside the row, first poly(A) candidate long
+// enough for the windowed statistics) is validated speculatively: all statistics of the checks are computed in two
+// rounds of concurrent selections, then the verdict is derived in the reference's order, so that code / check bits /
+// reported values are those of the sequential evaluation.  Anything else (and further poly(A) candidates after a failed
+// first one) takes the sequential path of validate_kernel.
+struct ValFastOut {      // written by thread 0, read by every thread after the closing barrier
+    int code, checks, n_pores, pores_cnt, pores_single, resume;
+    long long a0, pe_best;
+    float med;
+    double shift;
+};
+
+struct ValSeg {          // order keys of the minimum / maximum of [0, a1), [a1, pend), [pend, L): filled while the row is loaded
+    uint32_t mn[3], mx[3];
+};
+
+__device__ __forceinline__ bool val_fast_eligible(const ValCfg& c, int L, const int64_t* pr, int ld) {
+    if (!c.mvs_detect_check || ld < 2) return false;
+    const int64_t a1 = pr[0], pe = pr[1];
+    if (a1 <= 0 || pe == 0 || a1 > (int64_t)L) return false;
+    if (pe < a1 || pe - a1 <= 2 || (int64_t)L < a1 + c.median_shift_window) return false;        // "early" candidate
+    const int64_t nominal = pe - a1;
+    if (nominal <= c.pa_var_window + 2 || nominal <= c.pa_mean_window + 2) return false;
+    const int m = (int)(min(pe, (int64_t)L) - a1);
+    const int cntv = m - c.pa_var_window + 1, cntm = m - c.pa_mean_window + 1;
+    if (c.pa_var_window < 4 || cntv <= 4 * VAL_BAND_CAP / 3 || cntm <= 4 * VAL_BAND_CAP / 3) return false;
+    const int C = (cntv + FP_THREADS - 1) / FP_THREADS;
+    if ((m + C - 1) / C > MS_CHUNKS) return false;
+    return true;
+}
+
+__device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const float* vsig, unsigned short* codes, int L, int64_t fl,
+                                      const int64_t* pr, const ValSeg& seg, MsState& ms, ValBand& bd, ValBand& bdm, FpScratch& s, int* sh_i,
+                                      int* sh_pores, double* sh_d, double* sh_v, float* scratch, ValSel& vs_old, ValFastOut& fo) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a1 = (int)pr[0], e = a1, hi = a1;
+    const int64_t pe = pr[1];
+    const int pend = (int)min(pe, (int64_t)L);
+    const int m = pend - e;
+    const int wv = c.pa_var_window, wm = c.pa_mean_window;
+    const int cntv = m - wv + 1, cntm = m - wm + 1;
+    const float mnA = f32_unkey(seg.mn[0]), mxA = f32_unkey(seg.mx[0]);
+    const float mnP = f32_unkey(seg.mn[1]), mxP = f32_unkey(seg.mx[1]);
+    const float mnR = (pend < L) ? fminf(mnP, f32_unkey(seg.mn[2])) : mnP, mxR = (pend < L) ? fmaxf(mxP, f32_unkey(seg.mx[2])) : mxP;
+
+    // ---- phase 1a: chunk sums of the centred poly(A) samples (for the sliding sums of the moving variance), open pores
+    const int C = (cntv + FP_THREADS - 1) / FP_THREADS;     // windows per thread
+    const int nch = (m + C - 1) / C;
+    const int Cm = (cntm + FP_THREADS - 1) / FP_THREADS;    // the same for the moving mean
+    const uint32_t kbm = f32_key(mnP);                      // every mean of poly(A) samples is >= their minimum
+    int* smp = bdm.idx;                                     // 2 x 128 sample codes (the mean's band list is free until round B)
+    double* S = reinterpret_cast<double*>(&ms.cand[0][0]);
+    double* Q = S + MS_CHUNKS;
+    const double cref = (double)vsig[e];
+    for (int ch = tid; ch < nch; ch += FP_THREADS) {
+        const int i1 = min((ch + 1) * C, m);
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = ch * C; i < i1; i++) {
+            const double d = (double)vsig[e + i] - cref;
+            s1 += d;
+            s2 += d * d;
+        }
+        S[ch] = s1;
+        Q[ch] = s2;
+    }
+    if (c.detect_open_pores) {
+        // one pass: position i is kept iff it is an open-pore sample with none within min_obs_diff - 1 samples before it and
+        // it is not the first one (find_open_pores starts at the second position); the first one is removed afterwards
+        const float lo = c.open_pore_min;
+        const int D = c.open_pore_min_obs_diff;
+        for (int i = tid; i < hi; i += FP_THREADS) {
+            if (vsig[i] >= lo) {
+                atomicAdd(&sh_i[0], 1);
+                atomicMin(&sh_i[1], i);
+                atomicMax(&sh_i[2], i);
+                bool near = false;
+                for (int q = max(0, i - D + 1); q < i; q++) near |= (vsig[q] >= lo);
+                if (!near) {
+                    atomicMax(&sh_i[3], i);
+                    const int slot = atomicAdd(&sh_i[4], 1);
+                    if (slot < VAL_PORES_LD - 1) sh_pores[1 + slot] = i;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // open pores -> adapter start
+    int64_t a0 = 0;
+    int n_pores = 0, pores_cnt = -1, pores_single = 0;
+    bool pore_fail = false;
+    if (c.detect_open_pores) {
+        const int cnt = sh_i[0], first = sh_i[1], last = sh_i[2], kept = max(0, sh_i[4] - 1);   // sh_i[4] counts the first one too
+        if (cnt > 1) {
+            n_pores = kept > 0 ? kept : 1;
+            a0 = kept > 0 ? sh_i[3] : last;
+        } else if (cnt == 1) {
+            n_pores = 1;
+            a0 = first;
+        }
+        pore_fail = cnt > 0 && a1 - a0 < c.min_obs_adapter;
+        pores_cnt = cnt > 1 ? n_pores : cnt;
+        pores_single = (cnt > 1 && kept > 0) ? -2 : (int)a0;    // -2: the list in sh_pores, minus its smallest entry
+    }
+    const int b0 = (int)min(a0, (int64_t)hi);
+    const int nseg = hi - b0;
+    const bool have_means = c.real_signal_check && nseg >= 2 * c.mean_window;
+
+    // ---- phase 1b: moving variance of every window, approximately (sliding float64 sums seeded from the chunk sums),
+    // stored as a 16-bit code: the float32 bit pattern >> 12 relative to a bound of the variance (monotone; 2048 codes per octave)
+    {
+        const float rng = __fsub_rn(mxP, mnP);
+        const float vb = rng * rng * 0.2503f + 1e-30f;
+        const int base = max(0, (int)(__float_as_uint(vb) >> 12) - 65534);
+        const double inv_w = 1.0 / (double)wv;
+        int cmn = 65535, cmx = 0;
+        const int p0 = tid * C;
+        if (p0 < cntv) {
+            const int k = wv / C;
+            double s1 = 0.0, s2 = 0.0;
+            for (int q = 0; q < k; q++) {
+                s1 += S[tid + q];
+                s2 += Q[tid + q];
+            }
+            for (int i = p0 + k * C; i < p0 + wv; i++) {
+                const double d = (double)vsig[e + i] - cref;
+                s1 += d;
+                s2 += d * d;
+            }
+            const int pe_ = min(p0 + C, cntv);
+            for (int p = p0;; p++) {
+                const double mu = s1 * inv_w;
+                float v32 = (float)(s2 * inv_w - mu * mu);
+                if (!(v32 > 0.f)) v32 = 0.f;
+                const int code = max(0, min(65535, (int)(__float_as_uint(v32) >> 12) - base));
+                codes[p] = (unsigned short)code;
+                cmn = min(cmn, code);
+                cmx = max(cmx, code);
+                if (p + 1 >= pe_) break;
+                const double dn = (double)vsig[e + p + wv] - cref, dl = (double)vsig[e + p] - cref;
+                s1 += dn - dl;
+                s2 += dn * dn - dl * dl;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            cmn = min(cmn, __shfl_xor_sync(0xffffffffu, cmn, o));
+            cmx = max(cmx, __shfl_xor_sync(0xffffffffu, cmx, o));
+        }
+        if (lane == 0) {
+            atomicMin(&sh_i[5], cmn);
+            atomicMax(&sh_i[6], cmx);
+        }
+        // samples for the focus of the two code histograms: the code of every fourth thread's first window
+        if ((tid & 3) == 0) {
+            smp[tid >> 2] = (p0 < cntv) ? (int)codes[p0] : -1;
+            const int q0 = tid * Cm;
+            int cm = -1;
+            if (q0 < cntm) {
+                double s1 = 0.0;
+                for (int i = 0; i < wm; i++) s1 += (double)vsig[e + q0 + i] - cref;
+                cm = ms_mean_code(cref + s1 / (double)wm, kbm);
+            }
+            smp[128 + (tid >> 2)] = cm;
+        }
+        // real_range_check's two means (float32, numpy's pairwise order): one warp each
+        if (have_means && (warp == FP_WARPS - 1 || warp == FP_WARPS - 2)) {
+            const bool first_one = warp == FP_WARPS - 1;
+            const int base_i = first_one ? b0 : hi - c.mean_window;
+            const float sm = (c.mean_window <= 512) ? warp_np_sum_f32(base_i, c.mean_window, [&](int i) { return vsig[i]; })
+                                                    : np_pairwise<float>(base_i, c.mean_window, [&](int i) { return vsig[i]; });
+            if (lane == 0) sh_d[first_one ? 0 : 1] = (double)__fdiv_rn(sm, (float)c.mean_window);
+        }
+    }
+    __syncthreads();
+
+    // focus of the code histograms: the 30 % / 70 % quantiles of the samples (128 each; the middle ranks asked for lie
+    // 4 sigma inside).  Warps 0-3: moving variance, warps 4-7: moving mean.  Next to it the histograms are cleared.
+    uint32_t* hz = &ms.hist[0][0];
+    for (int i = tid; i < MS_MAXJ * MS_BINS / 2; i += FP_THREADS) hz[i] = 0;
+    if (tid < MS_MAXS) ms.slot_n[tid] = 0;
+    if (tid < 256) {
+        const int* sp = smp + (tid & 128);
+        const int t = tid & 127, x = sp[t];
+        int ns = 0, rank = 0;
+        for (int u = 0; u < 128; u++) {
+            const int y = sp[u];
+            ns += (y >= 0);
+            rank += (y >= 0) && ((y < x) || (y == x && u < t));
+        }
+        if (x >= 0) {
+            if (rank == (ns * 3) / 10) sh_i[8 + (tid >> 7) * 2] = x;
+            if (rank == (ns * 7) / 10) sh_i[9 + (tid >> 7) * 2] = x;
+        }
+    }
+    __syncthreads();
+
+    // ---- round A: every selection that does not need another one's result
+    int qa = -1, ql = -1, qp = -1, qs1 = -1, qs2 = -1, qv = -1, qm = -1, qm1 = -1, qm2 = -1;   // first rank of each job
+    double g85l = 0, g15l = 0, g85p = 0, g15p = 0;
+    const int nn = min(c.max_obs_local_range, nseg);
+    const int up = min(e + c.median_shift_window, L), dn = max(e - c.median_shift_window, 0);
+    const int ms_e = min(a1, L);
+    const int ms_up = (int)min(min((int64_t)a1 + c.med_shift_window, fl), (int64_t)L), ms_dn = (int)max((int64_t)a1 - c.med_shift_window, (int64_t)0);
+    const int ms_n1 = max(0, ms_up - ms_e), ms_n2 = max(0, ms_e - min(ms_dn, ms_e));
+    // every thread derives the rank layout (needed to read the results); thread 0 writes it
+    {
+        int q = 0;
+        qa = q; q += 2;                                 // adapter median
+        if (c.real_signal_check && nn >= 1) { ql = q; q += 4; }
+        qp = q; q += 6;                                 // poly(A): p85 pair, p15 pair, median pair
+        qs1 = q; q += 2;
+        qs2 = q; q += 2;
+        qv = q; q += 2;
+        qm = q; q += 2;
+        if (c.detect_med_shift && ms_n1 >= 1) { qm1 = q; q += 2; }
+        if (c.detect_med_shift && ms_n2 >= 1) { qm2 = q; q += 2; }
+    }
+    {
+        uint32_t r0, r1;
+        if (ql >= 0) {
+            pct_ranks(nn, 85.0, &r0, &r1, &g85l);
+            pct_ranks(nn, 15.0, &r0, &r1, &g15l);
+        }
+        pct_ranks(m, 85.0, &r0, &r1, &g85p);
+        pct_ranks(m, 15.0, &r0, &r1, &g15p);
+    }
+    if (tid == 0) {
+        ms.nj = 0;
+        ms.nq = 0;
+        ms.n_slots = 0;
+        ms.crowded = 0;
+        auto median_job = [&](const float* p, int n, float lo, float hi_) {
+            const int jj = ms_add_job(ms, p, n, 0, lo, hi_);
+            ms_add_rank(ms, jj, (uint32_t)((n - 1) / 2));
+            ms_add_rank(ms, jj, (uint32_t)(n / 2));
+            return jj;
+        };
+        median_job(vsig, hi, mnA, mxA);
+        if (ql >= 0) {
+            const int jj = ms_add_job(ms, vsig + (hi - nn), nn, 0, mnA, mxA);
+            uint32_t r0, r1;
+            double g;
+            pct_ranks(nn, 85.0, &r0, &r1, &g);
+            ms_add_rank(ms, jj, r0);
+            ms_add_rank(ms, jj, r1);
+            pct_ranks(nn, 15.0, &r0, &r1, &g);
+            ms_add_rank(ms, jj, r0);
+            ms_add_rank(ms, jj, r1);
+        }
+        {
+            const int jj = ms_add_job(ms, vsig + e, m, 0, mnP, mxP);
+            uint32_t r0, r1;
+            double g;
+            pct_ranks(m, 85.0, &r0, &r1, &g);
+            ms_add_rank(ms, jj, r0);
+            ms_add_rank(ms, jj, r1);
+            pct_ranks(m, 15.0, &r0, &r1, &g);
+            ms_add_rank(ms, jj, r0);
+            ms_add_rank(ms, jj, r1);
+            ms_add_rank(ms, jj, (uint32_t)((m - 1) / 2));
+            ms_add_rank(ms, jj, (uint32_t)(m / 2));
+        }
+        median_job(vsig + e, up - e, mnR, mxR);
+        median_job(vsig + dn, e - dn, mnA, mxA);
+        auto focus = [&](MsJob& j, int flo, int fhi) {
+            j.flo = flo;
+            int sh = 0;
+            while ((((long long)fhi - flo) >> sh) > MS_BINS - 3) sh++;
+            j.fsh = sh;
+        };
+        {   // moving variance: stored codes
+            const int jj = ms_add_job(ms, nullptr, cntv, 2, 0.f, 0.f);
+            MsJob& j = ms.job[jj];
+            j.c = codes;
+            focus(j, sh_i[8], sh_i[9]);
+            ms_add_rank(ms, jj, (uint32_t)((cntv - 1) / 2));
+            ms_add_rank(ms, jj, (uint32_t)(cntv / 2));
+        }
+        {   // moving mean: codes made on the fly
+            const int jj = ms_add_job(ms, vsig + e, cntm, 3, 0.f, 0.f);
+            MsJob& j = ms.job[jj];
+            j.w = wm;
+            j.chunk = Cm;
+            j.kb = kbm;
+            focus(j, sh_i[10], sh_i[11]);
+            ms_add_rank(ms, jj, (uint32_t)((cntm - 1) / 2));
+            ms_add_rank(ms, jj, (uint32_t)(cntm / 2));
+        }
+        if (qm1 >= 0) median_job(vsig + ms_e, ms_n1, mnR, mxR);
+        if (qm2 >= 0) median_job(vsig + min(ms_dn, ms_e), ms_n2, mnA, mxA);
+        bd.n = 0;
+        bd.below = 0;
+        bdm.n = 0;
+        bdm.below = 0;
+    }
+    __syncthreads();
+    ms_round(ms, s, [] {}, [] {}, [] {});
+    auto qf = [&](int q) { return f32_unkey(ms.q_key[q]); };
+    const float med = median_of(hi, qf(qa), qf(qa + 1));
+    const double lr = (ql >= 0) ? __dsub_rn(pct_lerp(qf(ql), qf(ql + 1), g85l), pct_lerp(qf(ql + 2), qf(ql + 3), g15l)) : 0.0;
+    const double r_lr = __dsub_rn(pct_lerp(qf(qp), qf(qp + 1), g85p), pct_lerp(qf(qp + 2), qf(qp + 3), g15p));
+    const double r_med = (double)median_of(m, qf(qp + 4), qf(qp + 5));
+    const double r_shift = (double)__fsub_rn(median_of(up - e, qf(qs1), qf(qs1 + 1)), median_of(e - dn, qf(qs2), qf(qs2 + 1)));
+    const int code_k0 = (int)ms.q_key[qv], code_k1 = (int)ms.q_key[qv + 1];
+    const int mcode_k0 = (int)ms.q_key[qm], mcode_k1 = (int)ms.q_key[qm + 1];
+    const uint32_t rkv0 = (uint32_t)((cntv - 1) / 2), rkv1 = (uint32_t)(cntv / 2);
+    const uint32_t rkm0 = (uint32_t)((cntm - 1) / 2), rkm1 = (uint32_t)(cntm / 2);
+    const MsJob mjob = ms.job[ms.q_job[qm]];      // the moving-mean job, for the band pass of round B
+    const float qnan32 = __int_as_float(0x7fc00000);
+    const double msv = c.detect_med_shift ? (double)__fsub_rn(qm1 >= 0 ? median_of(ms_n1, qf(qm1), qf(qm1 + 1)) : qnan32,
+                                                              qm2 >= 0 ? median_of(ms_n2, qf(qm2), qf(qm2 + 1)) : qnan32) : 0.0;
+    const double mean_start = sh_d[0], mean_end = sh_d[1];
+    __syncthreads();      // everyone has read the results of round A
+
+    // ---- round B: the adapter MAD (needs the median) and the exact evaluation of the variance windows around the middle
+    for (int i = tid; i < MS_BINS / 2; i += FP_THREADS) hz[i] = 0;
+    if (tid < MS_MAXS) ms.slot_n[tid] = 0;
+    const int c_lo = max(0, code_k0 - 1), c_hi = code_k1 + 1;
+    // the mean's codes are float32 order keys (1 ulp apart): three codes of margin keep every window outside the band
+    // strictly below / above the exact middle values even when exact and approximate mean round to neighbouring floats
+    const int cm_lo = max(0, mcode_k0 - 3), cm_hi = mcode_k1 + 3;
+    if (tid == 0) {
+        ms.nj = 0;
+        ms.nq = 0;
+        ms.n_slots = 0;
+        ms.crowded = 0;
+        const float dmax = fmaxf(__fsub_rn(mxA, med), __fsub_rn(med, mnA));
+        const int jj = ms_add_job(ms, vsig, hi, 1, 0.f, dmax);
+        ms.job[jj].med = med;
+        ms_add_rank(ms, jj, (uint32_t)((hi - 1) / 2));
+        ms_add_rank(ms, jj, (uint32_t)(hi / 2));
+    }
+    __syncthreads();
+    bool band_ok = true;
+    ms_round(ms, s,
+        [&] {   // next to the histogram pass: windows certainly below the middle, windows inside the band
+            int below = 0;
+            for (int p = tid; p < cntv; p += FP_THREADS) {
+                const int cv = (int)codes[p];
+                if (cv < c_lo) below++;
+                else if (cv <= c_hi) {
+                    const int pos = atomicAdd(&bd.n, 1);
+                    if (pos < VAL_BAND_CAP) bd.idx[pos] = p;
+                }
+            }
+            int below_m = 0;
+            ms_mean_windows(mjob, [&](int p, int cv) {
+                if (cv < cm_lo) below_m++;
+                else if (cv <= cm_hi) {
+                    const int pos = atomicAdd(&bdm.n, 1);
+                    if (pos < VAL_BAND_CAP) bdm.idx[pos] = p;
+                }
+            });
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                below += __shfl_xor_sync(0xffffffffu, below, o);
+                below_m += __shfl_xor_sync(0xffffffffu, below_m, o);
+            }
+            if (lane == 0 && below) atomicAdd(&bd.below, below);
+            if (lane == 0 && below_m) atomicAdd(&bdm.below, below_m);
+        },
+        [&] {   // next to the scan: exact variance of the band's windows
+            const int nb = bd.n;
+            if (nb <= VAL_BAND_CAP && tid >= 32)      // warp 0 scans the histogram meanwhile
+                for (int j = tid - 32; j < nb; j += FP_THREADS - 32) bd.val[j] = val_window_exact<true>(vsig, e + bd.idx[j], wv);
+            const int nbm = bdm.n;
+            if (nbm <= VAL_BAND_CAP && tid >= 32)
+                for (int j = FP_THREADS - 1 - tid; j < nbm; j += FP_THREADS - 32) bdm.val[j] = val_window_exact<false>(vsig, e + bdm.idx[j], wm);
+        },
+        [&] {   // next to the gather: exact ranking inside the band
+            const int nb = bd.n, r0 = (int)rkv0 - bd.below, r1 = (int)rkv1 - bd.below;
+            if (nb <= VAL_BAND_CAP && r0 >= 0 && r1 < nb) {
+                for (int j = tid; j < nb; j += FP_THREADS) {
+                    const float x = bd.val[j];
+                    int rank = 0;
+                    for (int u = 0; u < nb; u++) {
+                        const float y = bd.val[u];
+                        rank += (y < x) || (y == x && u < j);
+                    }
+                    if (rank == r0) bd.out[0] = x;
+                    if (rank == r1) bd.out[1] = x;
+                }
+            }
+            const int nbm = bdm.n, m0 = (int)rkm0 - bdm.below, m1 = (int)rkm1 - bdm.below;
+            if (nbm <= VAL_BAND_CAP && m0 >= 0 && m1 < nbm) {
+                for (int j = FP_THREADS - 1 - tid; j < nbm; j += FP_THREADS) {
+                    const float x = bdm.val[j];
+                    int rank = 0;
+                    for (int u = 0; u < nbm; u++) {
+                        const float y = bdm.val[u];
+                        rank += (y < x) || (y == x && u < j);
+                    }
+                    if (rank == m0) bdm.out[0] = x;
+                    if (rank == m1) bdm.out[1] = x;
+                }
+            }
+        });
+    {
+        const int nb = bd.n, r0 = (int)rkv0 - bd.below, r1 = (int)rkv1 - bd.below;
+        band_ok = nb <= VAL_BAND_CAP && r0 >= 0 && r1 < nb;
+    }
+    bool mband_ok;
+    {
+        const int nbm = bdm.n, m0 = (int)rkm0 - bdm.below, m1 = (int)rkm1 - bdm.below;
+        mband_ok = nbm <= VAL_BAND_CAP && m0 >= 0 && m1 < nbm;
+    }
+    const float mad = median_of(hi, qf(0), qf(1));
+    double r_var = band_ok ? (double)median_of(cntv, bd.out[0], bd.out[1]) : 0.0;
+    double r_mean = mband_ok ? (double)median_of(cntm, bdm.out[0], bdm.out[1]) : 0.0;
+    __syncthreads();
+    // uniform; a crowded band (e.g. a constant stretch): every window exactly, as the sequential path does
+    if (!band_ok) r_var = (double)val_window_median<true>(vsig, e, m, wv, scratch, bd, vs_old, s);
+    if (!mband_ok) r_mean = (double)val_window_median<false>(vsig, e, m, wm, scratch, bd, vs_old, s);
+
+    // ---- the verdict, in the reference's order (combined.py:452-629)
+    if (tid == 0) {
+        int code = VAL_OK, checks = 0, resume = 0;
+        long long pe_best = pe;
+        sh_v[0] = (double)med;
+        sh_v[1] = (double)mad;
+        if (mad != 0.f && !val_in_range((double)mad, c.mad_lo, c.mad_hi)) code = VAL_ADAPTER_MAD;
+        const bool pores_ran = code == VAL_OK && c.detect_open_pores;
+        if (pores_ran && pore_fail) code = VAL_OPEN_PORE;
+        if (code == VAL_OK && c.real_signal_check) {
+            bool ok = false;
+            if (have_means) {
+                sh_v[2] = mean_start;
+                sh_v[3] = mean_end;
+                if (val_in_range(mean_start, c.mean_start_lo, c.mean_start_hi) && val_in_range(mean_end, c.mean_end_lo, c.mean_end_hi)) {
+                    sh_v[4] = lr;
+                    ok = val_in_range(lr, c.local_range_lo, c.local_range_hi);
+                }
+            }
+            if (!ok) code = VAL_REAL_RANGE;
+        }
+        if (code == VAL_OK) {
+            double mlo = c.mean_lo, mhi = c.mean_hi;
+            if (c.mean_from_scale) {
+                mlo = __dmul_rn(c.scale_lo, (double)med);
+                mhi = __dmul_rn(c.scale_hi, (double)med);
+            }
+            const int bits = (val_in_range(r_mean, mlo, mhi) ? 1 : 0) | (val_in_range(r_var, c.var_lo, c.var_hi) ? 2 : 0) |
+                             (val_in_range(r_med, c.pmed_lo, c.pmed_hi) ? 4 : 0) | (val_in_range(r_lr, c.plr_lo, c.plr_hi) ? 8 : 0) |
+                             (val_in_range(r_shift, c.shift_lo, c.shift_hi) ? 16 : 0);
+            sh_v[5] = r_mean;
+            sh_v[6] = r_var;
+            sh_v[7] = r_med;
+            sh_v[8] = r_lr;
+            sh_v[9] = r_shift;
+            if (bits != 31) {
+                if (r_mean == 0.0) {
+                    code = VAL_MVS_NO_SIGNAL;
+                    checks = 0;
+                } else {
+                    code = VAL_MVS_CHECKS;
+                    checks = bits;
+                }
+                resume = !a.verdict_only;     // the reference goes on to the next candidates (their report overwrites this one)
+            }
+        }
+        if (code == VAL_OK && c.detect_med_shift) {
+            sh_v[10] = msv;
+            if (!val_in_range(msv, c.ms_lo, c.ms_hi)) code = VAL_MED_SHIFT;
+        }
+        fo.code = code;
+        fo.checks = checks;
+        fo.resume = resume;
+        fo.pe_best = pe_best;
+        fo.a0 = pores_ran ? a0 : 0;
+        fo.n_pores = pores_ran ? n_pores : 0;
+        fo.pores_cnt = pores_ran ? pores_cnt : -1;
+        fo.pores_single = pores_single;
+        fo.med = med;
+        fo.shift = r_shift;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(const ValArgs a, const ValCfg c) {
-#ifndef WDX_VAL_GLOBAL_ROW
-    extern __shared__ float vsig[];
-#endif
+    extern __shared__ float vsig[];     // the row, then [stride] 16-bit codes of the moving variance
     __shared__ FpScratch s;
-    __shared__ ValSel vs;
-    __shared__ ValTree tree;
-    __shared__ ValBand band;
-    __shared__ int sh_i[6];
+    // the concurrent selections of the common read and the selection / pairwise-sum state of the sequential path are
+    // never live at the same time
+    __shared__ union ValShared {
+        MsState ms;
+        struct {
+            ValSel vs;
+            ValTree tree;
+        } seq;
+        __device__ ValShared() {}
+    } shu;
+    ValSel& vs = shu.seq.vs;
+    ValTree& tree = shu.seq.tree;
+    __shared__ ValBand band, band2;
+    __shared__ ValSeg seg;
+    __shared__ ValFastOut fo;
+    __shared__ int sh_i[12];
     __shared__ int sh_pores[VAL_PORES_LD];
     __shared__ double sh_d[4];
     __shared__ double sh_v[VAL_NVALS];
     const int tid = threadIdx.x;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     float* scratch = a.scratch + (size_t)blockIdx.x * a.stride;
+    unsigned short* codes = reinterpret_cast<unsigned short*>(vsig + ((a.stride + 3) & ~(int64_t)3));
 
     __shared__ unsigned long long sh_next;
     for (;;) {
@@ -607,6 +1474,19 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             unsigned long long nx = atomicAdd(a.next, 1ULL);
             if (a.list) nx = (nx < (unsigned long long)*a.list_count) ? (unsigned long long)a.list[nx] : (unsigned long long)a.n;
             sh_next = nx;
+            sh_i[0] = 0;           // open-pore samples
+            sh_i[1] = 0x7fffffff;  // first
+            sh_i[2] = -1;          // last
+            sh_i[3] = -1;          // last kept
+            sh_i[4] = 0;           // kept
+            sh_i[5] = 65535;       // smallest / largest code of the moving variance
+            sh_i[6] = 0;
+            sh_i[8] = sh_i[10] = 0;                 // focus of the code histograms (30 % / 70 % sample quantiles)
+            sh_i[9] = sh_i[11] = 0x7ffffff0;
+        }
+        if (tid < 3) {
+            seg.mn[tid] = 0xffffffffu;
+            seg.mx[tid] = 0u;
         }
         __syncthreads();
         const int64_t r = (int64_t)sh_next;
@@ -616,54 +1496,88 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         const int L = (int)max((int64_t)0, min(fl, a.stride));
         int has_nan = 0;
         if (tid < VAL_NVALS) sh_v[tid] = qnan;
-#ifdef WDX_VAL_GLOBAL_ROW
-        // The row stays in global memory: this NaN scan is its one trip from HBM (coalesced), every later pass finds it in
-        // L2 (46 KB per read, ~1200 reads in flight).  No shared-memory staging = small CTAs, eight per SM, and the many
-        // short barrier-separated phases of one read overlap with those of seven others.
-        const float* vsig = row;
-        for (int i0 = tid; i0 < L; i0 += 8 * FP_THREADS) {
-            float xv[8];
+        const int64_t* pr = a.preds + (size_t)r * a.ld;
+        const bool fast = val_fast_eligible(c, L, pr, a.ld);
+        {
+            // minimum / maximum of the adapter, the first poly(A) candidate and the rest of the row, for the bin maps of
+            // the concurrent selections (order keys; a NaN poisons nothing: such a row fails before they are used)
+            const int sa = fast ? (int)pr[0] : 0, sp = fast ? (int)min(pr[1], (int64_t)L) : 0;
+            uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0u, mx1 = 0u, mx2 = 0u;
+            for (int i0 = tid; i0 < L; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
+                float xv[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = i0 + u * FP_THREADS;
-                xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * FP_THREADS;
+                    xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * FP_THREADS;
+                    if (i < L) {
+                        vsig[i] = xv[u];
+                        has_nan |= (xv[u] != xv[u]);
+                        const uint32_t kv = f32_key(xv[u]);
+                        if (i < sa) {
+                            mn0 = min(mn0, kv);
+                            mx0 = max(mx0, kv);
+                        } else if (i < sp) {
+                            mn1 = min(mn1, kv);
+                            mx1 = max(mx1, kv);
+                        } else {
+                            mn2 = min(mn2, kv);
+                            mx2 = max(mx2, kv);
+                        }
+                    }
+                }
             }
+            if (fast) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) has_nan |= (xv[u] != xv[u]);
-        }
-#else
-        for (int i0 = tid; i0 < L; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
-            float xv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * FP_THREADS;
-                xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * FP_THREADS;
-                if (i < L) {
-                    vsig[i] = xv[u];
-                    has_nan |= (xv[u] != xv[u]);
+                for (int o = 16; o; o >>= 1) {
+                    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+                    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+                    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
+                    mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+                    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+                    mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+                }
+                if ((tid & 31) == 0) {
+                    atomicMin(&seg.mn[0], mn0);
+                    atomicMin(&seg.mn[1], mn1);
+                    atomicMin(&seg.mn[2], mn2);
+                    atomicMax(&seg.mx[0], mx0);
+                    atomicMax(&seg.mx[1], mx1);
+                    atomicMax(&seg.mx[2], mx2);
                 }
             }
         }
-#endif
         has_nan = __syncthreads_or(has_nan);
 
-        const int64_t* pr = a.preds + (size_t)r * a.ld;
         const int64_t a1 = pr[0];
         int64_t a0 = 0;
         int64_t pe_best = a.ld > 1 ? pr[1] : 0;
         int code = VAL_OK, checks = 0, n_pores = 0;
-        int pores_cnt = -1, pores_single = 0;   // open_pores as the reference reports it: None / the kept positions
         // reported statistics live in shared memory (thread 0 writes them as they are found); the fill above is
         // ordered before those writes by the barrier of the NaN vote
 
         if (has_nan) code = VAL_HAS_NAN;
         const int hi = (int)max((int64_t)0, min(a1, (int64_t)L));   // sig[a0:a1] ends here
         float med = 0.f, mad = 0.f;
-        if (code == VAL_OK) {
+        int pores_cnt = -1, pores_single = 0;   // open_pores as the reference reports it: None / the kept positions
+        const bool use_fast = fast && code == VAL_OK;
+        int resume = 0;                        // poly(A) candidates from here on go through the sequential loop
+        if (use_fast) {
+            val_fast(a, c, vsig, codes, L, fl, pr, seg, shu.ms, band, band2, s, sh_i, sh_pores, sh_d, sh_v, scratch, vs, fo);
+            code = fo.code;
+            checks = fo.checks;
+            n_pores = fo.n_pores;
+            pores_cnt = fo.pores_cnt;
+            pores_single = fo.pores_single;
+            a0 = fo.a0;
+            pe_best = fo.pe_best;
+            med = fo.med;
+            resume = fo.resume;
+        }
+        if (!use_fast && code == VAL_OK) {
             if (a1 == 0) code = VAL_NO_ADAPTER;
             else {
                 med = val_median(hi, val_src(vsig), vs, s);
@@ -674,18 +1588,9 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                 }
             }
         }
-        if (code == VAL_OK && mad != 0.f && !val_in_range((double)mad, c.mad_lo, c.mad_hi)) code = VAL_ADAPTER_MAD;
+        if (!use_fast && code == VAL_OK && mad != 0.f && !val_in_range((double)mad, c.mad_lo, c.mad_hi)) code = VAL_ADAPTER_MAD;
 
-        if (code == VAL_OK && c.detect_open_pores) {
-            __syncthreads();
-            if (tid == 0) {
-                sh_i[0] = 0;           // open-pore samples
-                sh_i[1] = 0x7fffffff;  // first
-                sh_i[2] = -1;          // last
-                sh_i[3] = -1;          // last kept
-                sh_i[4] = 0;           // kept
-            }
-            __syncthreads();
+        if (!use_fast && code == VAL_OK && c.detect_open_pores) {
             const float lo = c.open_pore_min;
             for (int i = tid; i < hi; i += FP_THREADS) {
                 if (vsig[i] >= lo) {
@@ -724,7 +1629,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             pores_single = (cnt > 1 && sh_i[4] > 0) ? -1 : (int)a0;
         }
 
-        if (code == VAL_OK && c.real_signal_check) {
+        if (!use_fast && code == VAL_OK && c.real_signal_check) {
             const int b0 = (int)min(a0, (int64_t)hi);
             const int nseg = hi - b0;
             bool ok = false;
@@ -752,7 +1657,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             if (!ok) code = VAL_REAL_RANGE;
         }
 
-        if (code == VAL_OK && c.mvs_detect_check) {
+        if ((use_fast ? resume != 0 : code == VAL_OK) && c.mvs_detect_check) {
             if (pe_best == 0) code = VAL_NO_POLYA;
             else {
                 double mlo = c.mean_lo, mhi = c.mean_hi;
@@ -761,9 +1666,9 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                     mhi = __dmul_rn(c.scale_hi, (double)med);
                 }
                 const int e = (int)a1;   // a1 <= L here or the size test below fails first
-                bool have_shift = false;
-                double shift_cached = 0.0;
-                for (int j = 1; j < a.ld; j++) {
+                bool have_shift = use_fast;
+                double shift_cached = use_fast ? fo.shift : 0.0;
+                for (int j = use_fast ? 2 : 1; j < a.ld; j++) {
                     const int64_t pe = pr[j];
                     if (pe == 0) break;
                     double r_mean = 0.0, r_var = 0.0, r_med = 0.0, r_lr = 0.0, r_shift = 0.0;
@@ -841,7 +1746,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
             }
         }
 
-        if (code == VAL_OK && c.detect_med_shift) {
+        if (!use_fast && code == VAL_OK && c.detect_med_shift) {
             const int e = (int)min(a1, (int64_t)L);
             const int up = (int)min(min(a1 + c.med_shift_window, fl), (int64_t)L), dn = (int)max(a1 - c.med_shift_window, (int64_t)0);
             const float m_after = val_median(max(0, up - e), val_src(vsig + e), vs, s);
@@ -870,14 +1775,15 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
                 po[0] = pores_cnt;
                 if (pores_cnt > 0 && pores_single >= 0) po[1] = pores_single;
                 else if (pores_cnt > 0) {   // found in parallel: a handful of entries, insertion sort
-                    const int m = min(pores_cnt, VAL_PORES_LD - 1);
+                    const int extra = pores_single == -2 ? 1 : 0;    // single-pass scan: the list still holds the first open-pore sample
+                    const int m = min(pores_cnt + extra, VAL_PORES_LD - 1);
                     for (int i = 1; i < m; i++) {
                         const int v = sh_pores[1 + i];
                         int j = i - 1;
                         for (; j >= 0 && sh_pores[1 + j] > v; j--) sh_pores[2 + j] = sh_pores[1 + j];
                         sh_pores[2 + j] = v;
                     }
-                    for (int i = 0; i < m; i++) po[1 + i] = sh_pores[1 + i];
+                    for (int i = extra; i < m; i++) po[1 + i - extra] = sh_pores[1 + i];
                 }
             }
         }

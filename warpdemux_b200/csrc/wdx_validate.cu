@@ -242,11 +242,8 @@ int wdx_validate_run_report(wdx_validate* h, const float* signals, int64_t n, in
     if (n == 0) return WDX_OK;
     if (!signals || !full_len || !preds || !success || !info || !bounds)
         return fail(WDX_ERR_INVALID, "signals, full_len, preds, success, info and bounds are required");
-#ifdef WDX_VAL_GLOBAL_ROW
-    const size_t smem = 0;
-#else
-    const size_t smem = (size_t)stride * 4;
-#endif
+    // the row (float32) + one 16-bit code per sample (moving variance of the poly(A) windows, validate_kernel.cuh)
+    const size_t smem = (size_t)((stride + 3) & ~(int64_t)3) * 4 + (((size_t)stride * 2 + 15) & ~(size_t)15);
     if ((int64_t)smem > h->smem_max)
         return fail(WDX_ERR_UNSUPPORTED, "rows of %lld samples need %zu B of shared memory, device allows %d", (long long)stride, smem, h->smem_max);
     std::lock_guard<std::mutex> lk(h->mu);

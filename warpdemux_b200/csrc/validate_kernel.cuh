@@ -673,56 +673,50 @@ __device__ __forceinline__ void ms_hist_pass(const MsJob& j, uint32_t* hist) {
         });
         return;
     }
-    for (int i = threadIdx.x; i < j.n; i += FP_THREADS) {
-        uint32_t key;
-        int bin;
-        ms_eval<MODE>(j, i, key, bin);
-        atomicAdd(&hist[bin >> 1], (bin & 1) ? 0x10000u : 1u);
+    const int n = j.n;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * FP_THREADS) {     // four independent elements per trip
+        int bin[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = min(i0 + u * FP_THREADS, n - 1);
+            uint32_t key;
+            ms_eval<MODE>(j, i, key, bin[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * FP_THREADS < n) atomicAdd(&hist[bin[u] >> 1], (bin[u] & 1) ? 0x10000u : 1u);
     }
 }
 
+// After the scan a job's histogram holds, per bin, 0 or 1 + the candidate list its members go to.
 template <int MODE>
-__device__ __forceinline__ void ms_gather_pass(const MsJob& j, MsState& ms) {
-    int qb[6], qs[6], nd = 0;      // the job's distinct lists
-#pragma unroll
-    for (int d = 0; d < 6; d++) {
-        qb[d] = -1;
-        qs[d] = 0;
-    }
-    for (int q = j.q0; q < j.q0 + j.nq; q++) {
-        const int sl = ms.q_slot[q];
-        if (sl < 0) continue;
-        bool seen = false;
-#pragma unroll
-        for (int d = 0; d < 6; d++) seen |= (d < nd && qs[d] == sl);
-        if (!seen) {
-#pragma unroll
-            for (int d = 0; d < 6; d++)
-                if (d == nd) {
-                    qb[d] = ms.q_bin[q];
-                    qs[d] = sl;
-                }
-            nd++;
-        }
-    }
-    if (nd == 0) return;
-    auto put = [&](uint32_t key, int bin) {
-#pragma unroll
-        for (int d = 0; d < 6; d++)
-            if (bin == qb[d]) {
-                const uint32_t pos = atomicAdd(&ms.slot_n[qs[d]], 1u);
-                if (pos < (uint32_t)MS_CAND) ms.cand[qs[d]][pos] = key;
-            }
+__device__ __forceinline__ void ms_gather_pass(const MsJob& j, MsState& ms, const uint32_t* hist) {
+    const unsigned short* to_list = reinterpret_cast<const unsigned short*>(hist);
+    auto put = [&](uint32_t key, int sl) {
+        const uint32_t pos = atomicAdd(&ms.slot_n[sl], 1u);
+        if (pos < (uint32_t)MS_CAND) ms.cand[sl][pos] = key;
     };
     if (MODE == 3) {
-        ms_mean_windows(j, [&](int, int cv) { put((uint32_t)cv, ms_code_bin(j, cv)); });
+        ms_mean_windows(j, [&](int, int cv) {
+            const int sl = to_list[ms_code_bin(j, cv)];
+            if (sl) put((uint32_t)cv, sl - 1);
+        });
         return;
     }
-    for (int i = threadIdx.x; i < j.n; i += FP_THREADS) {
-        uint32_t key;
-        int bin;
-        ms_eval<MODE>(j, i, key, bin);
-        put(key, bin);
+    const int n = j.n;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * FP_THREADS) {
+        int sl[4];
+        uint32_t key[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = min(i0 + u * FP_THREADS, n - 1);
+            int bin;
+            ms_eval<MODE>(j, i, key[u], bin);
+            sl[u] = (i0 + u * FP_THREADS < n) ? to_list[bin] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (sl[u]) put(key[u], sl[u] - 1);
     }
 }
 
@@ -766,7 +760,12 @@ __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
         }
     }
     __syncwarp();
+    uint32_t* hw = ms.hist[jj] + lane * WPL;
+#pragma unroll
+    for (int t = 0; t < WPL; t++) hw[t] = 0;       // from here on: bin -> 1 + candidate list (ms_gather_pass)
+    __syncwarp();
     if (lane == 0) {
+        unsigned short* to_list = reinterpret_cast<unsigned short*>(ms.hist[jj]);
         for (int q = j.q0; q < j.q0 + j.nq; q++) {
             int sl = -2;
             for (int u = j.q0; u < q; u++)
@@ -779,32 +778,36 @@ __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
                 }
             }
             if (sl < 0) ms.crowded = 1;
+            else to_list[ms.q_bin[q]] = (unsigned short)(sl + 1);
             ms.q_slot[q] = sl;
         }
     }
 }
 
-// The q_r-th smallest key of every rank's candidate list: the (rank, candidate) pairs are dealt out over the whole CTA.
+// The q_r-th smallest key of every rank's candidate list: the (list, candidate) pairs are dealt out over the whole CTA,
+// a candidate's rank inside its list is matched against every rank that reads the list.
 __device__ __forceinline__ void ms_rank_all(MsState& ms) {
-    const int nq = ms.nq;
+    const int nq = ms.nq, ns = min(ms.n_slots, MS_MAXS);
     int total = 0;
-    for (int q = 0; q < nq; q++) total += (ms.q_slot[q] >= 0) ? (int)ms.q_cnt[q] : 0;
+    for (int sl = 0; sl < ns; sl++) total += (int)min(ms.slot_n[sl], (uint32_t)MS_CAND);
     for (int idx = threadIdx.x; idx < total; idx += FP_THREADS) {
-        int q = 0, t = idx;
-        for (;; q++) {
-            const int m = (ms.q_slot[q] >= 0) ? (int)ms.q_cnt[q] : 0;
+        int sl = 0, t = idx;
+        for (;; sl++) {
+            const int m = (int)min(ms.slot_n[sl], (uint32_t)MS_CAND);
             if (t < m) break;
             t -= m;
         }
-        const uint32_t m = ms.q_cnt[q], r = ms.q_r[q];
-        const uint32_t* cd = ms.cand[ms.q_slot[q]];
+        const uint32_t m = min(ms.slot_n[sl], (uint32_t)MS_CAND);
+        const uint32_t* cd = ms.cand[sl];
         const uint32_t x = cd[t];
         uint32_t rank = 0;
+#pragma unroll 4
         for (uint32_t u = 0; u < m; u++) {
             const uint32_t y = cd[u];
             rank += (y < x) || (y == x && u < (uint32_t)t);
         }
-        if (rank == r) ms.q_key[q] = x;
+        for (int q = 0; q < nq; q++)
+            if (ms.q_slot[q] == sl && ms.q_r[q] == rank) ms.q_key[q] = x;
     }
 }
 
@@ -832,10 +835,10 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
     for (int jj = 0; jj < nj; jj++) {
         const MsJob& j = ms.job[jj];
         switch (j.mode) {
-            case 0: ms_gather_pass<0>(j, ms); break;
-            case 1: ms_gather_pass<1>(j, ms); break;
-            case 2: ms_gather_pass<2>(j, ms); break;
-            default: ms_gather_pass<3>(j, ms); break;
+            case 0: ms_gather_pass<0>(j, ms, ms.hist[jj]); break;
+            case 1: ms_gather_pass<1>(j, ms, ms.hist[jj]); break;
+            case 2: ms_gather_pass<2>(j, ms, ms.hist[jj]); break;
+            default: ms_gather_pass<3>(j, ms, ms.hist[jj]); break;
         }
     }
     extra_gather();
@@ -1011,7 +1014,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     const int nch = (m + C - 1) / C;
     const int Cm = (cntm + FP_THREADS - 1) / FP_THREADS;    // the same for the moving mean
     const uint32_t kbm = f32_key(mnP);                      // every mean of poly(A) samples is >= their minimum
-    int* smp = bdm.idx;                                     // 2 x 128 sample codes (the mean's band list is free until round B)
+    int* smp = bdm.idx;                                     // 2 x 64 sample codes (the mean's band list is free until round B)
     double* S = reinterpret_cast<double*>(&ms.cand[0][0]);
     double* Q = S + MS_CHUNKS;
     const double cref = (double)vsig[e];
@@ -1114,9 +1117,9 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
             atomicMin(&sh_i[5], cmn);
             atomicMax(&sh_i[6], cmx);
         }
-        // samples for the focus of the two code histograms: the code of every fourth thread's first window
-        if ((tid & 3) == 0) {
-            smp[tid >> 2] = (p0 < cntv) ? (int)codes[p0] : -1;
+        // samples for the focus of the two code histograms: the code of every eighth thread's first window
+        if ((tid & 7) == 0) {
+            smp[tid >> 3] = (p0 < cntv) ? (int)codes[p0] : -1;
             const int q0 = tid * Cm;
             int cm = -1;
             if (q0 < cntm) {
@@ -1124,7 +1127,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
                 for (int i = 0; i < wm; i++) s1 += (double)vsig[e + q0 + i] - cref;
                 cm = ms_mean_code(cref + s1 / (double)wm, kbm);
             }
-            smp[128 + (tid >> 2)] = cm;
+            smp[64 + (tid >> 3)] = cm;
         }
         // real_range_check's two means (float32, numpy's pairwise order): one warp each
         if (have_means && (warp == FP_WARPS - 1 || warp == FP_WARPS - 2)) {
@@ -1137,23 +1140,25 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     }
     __syncthreads();
 
-    // focus of the code histograms: the 30 % / 70 % quantiles of the samples (128 each; the middle ranks asked for lie
-    // 4 sigma inside).  Warps 0-3: moving variance, warps 4-7: moving mean.  Next to it the histograms are cleared.
+    // focus of the code histograms: the 25 % / 75 % quantiles of the samples (64 each; the middle ranks asked for lie
+    // 4 sigma inside, and a miss only costs the radix fallback).  Warps 0-1: moving variance, warps 2-3: moving mean.
+    // Next to it the histograms are cleared.
     uint32_t* hz = &ms.hist[0][0];
     for (int i = tid; i < MS_MAXJ * MS_BINS / 2; i += FP_THREADS) hz[i] = 0;
     if (tid < MS_MAXS) ms.slot_n[tid] = 0;
-    if (tid < 256) {
-        const int* sp = smp + (tid & 128);
-        const int t = tid & 127, x = sp[t];
+    if (tid < 128) {
+        const int* sp = smp + (tid & 64);
+        const int t = tid & 63, x = sp[t];
         int ns = 0, rank = 0;
-        for (int u = 0; u < 128; u++) {
+#pragma unroll 8
+        for (int u = 0; u < 64; u++) {
             const int y = sp[u];
             ns += (y >= 0);
             rank += (y >= 0) && ((y < x) || (y == x && u < t));
         }
         if (x >= 0) {
-            if (rank == (ns * 3) / 10) sh_i[8 + (tid >> 7) * 2] = x;
-            if (rank == (ns * 7) / 10) sh_i[9 + (tid >> 7) * 2] = x;
+            if (rank == ns / 4) sh_i[8 + (tid >> 6) * 2] = x;
+            if (rank == (ns * 3) / 4) sh_i[9 + (tid >> 6) * 2] = x;
         }
     }
     __syncthreads();

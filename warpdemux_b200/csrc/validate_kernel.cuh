@@ -601,15 +601,10 @@ constexpr int MS_CAND = 224;           // members kept per list
 constexpr int MS_CHUNKS = (MS_MAXS * MS_CAND * 4) / 16;   // chunk sums (two doubles each) of the moving variance alias the candidate lists
 
 struct MsJob {
-    const float* p;               // modes 0, 1, 3: first sample of the range
-    const unsigned short* c;      // mode 2: codes
+    const float* p;               // first sample of the range
     int n;                        // values
-    int mode;                     // 0 sample, 1 |sample - med|, 2 stored code, 3 code of the moving mean over w samples, made on the fly
-    int w;
-    float med, vmin, scale;       // modes 0, 1: bin = (value - vmin) * scale
-    int flo, fsh;                 // modes 2, 3: bin = 0 below flo, else 1 + ((code - flo) >> fsh) (the focus of the histogram)
-    int chunk;                    // mode 3: consecutive windows per thread (sliding sums)
-    uint32_t kb;                  // mode 3: code = order key of the float32 mean - kb
+    int mode;                     // 0 sample, 1 |sample - med|
+    float med, vmin, scale;       // bin = (value - vmin) * scale
     int q0, nq;                   // ranks q0 .. q0 + nq - 1
 };
 
@@ -623,65 +618,22 @@ struct MsState {
     int nj, nq, n_slots, crowded;
 };
 
-__device__ __forceinline__ int ms_code_bin(const MsJob& j, int cv) {
-    return cv < j.flo ? 0 : min(MS_BINS - 1, 1 + ((cv - j.flo) >> j.fsh));
-}
-
 template <int MODE>
-__device__ __forceinline__ void ms_eval(const MsJob& j, int i, uint32_t& key, int& bin) {
-    if (MODE == 2) {
-        const int cv = (int)j.c[i];
-        key = (uint32_t)cv;
-        bin = ms_code_bin(j, cv);
-    } else {
-        float x = j.p[i];
-        if (MODE == 1) x = fabsf(__fsub_rn(x, j.med));
-        key = f32_key(x);
-        bin = max(0, min(MS_BINS - 1, (int)__fmul_rn(__fsub_rn(x, j.vmin), j.scale)));
-    }
+__device__ __forceinline__ float ms_value(const MsJob& j, int i) {
+    const float x = j.p[i];
+    return (MODE == 1) ? fabsf(__fsub_rn(x, j.med)) : x;
 }
-
-// Code of an (approximate) moving mean: the distance of its float32 order key from the key of a lower bound of the means.
-__device__ __forceinline__ int ms_mean_code(double mean, uint32_t kb) {
-    const uint32_t k = f32_key((float)mean);
-    return k > kb ? (int)min(k - kb, 0x7ffffff0u) : 0;
-}
-
-// Mode 3: thread t owns the windows [t * chunk, (t + 1) * chunk) and slides a float64 sum of the centred samples over them;
-// f(window, code) is called for each.  The same few flops again in every pass instead of an array of n codes.
-template <typename F>
-__device__ __forceinline__ void ms_mean_windows(const MsJob& j, F f) {
-    const int p0 = threadIdx.x * j.chunk;
-    if (p0 >= j.n) return;
-    const double cref = (double)j.p[0], inv_w = 1.0 / (double)j.w;
-    double s1 = 0.0;
-    for (int i = 0; i < j.w; i++) s1 += (double)j.p[p0 + i] - cref;
-    const int pe = min(p0 + j.chunk, j.n);
-    for (int p = p0;; p++) {
-        f(p, ms_mean_code(cref + s1 * inv_w, j.kb));
-        if (p + 1 >= pe) break;
-        s1 += ((double)j.p[p + j.w] - cref) - ((double)j.p[p] - cref);
-    }
+__device__ __forceinline__ int ms_bin(const MsJob& j, float x) {
+    return max(0, min(MS_BINS - 1, (int)__fmul_rn(__fsub_rn(x, j.vmin), j.scale)));
 }
 
 template <int MODE>
 __device__ __forceinline__ void ms_hist_pass(const MsJob& j, uint32_t* hist) {
-    if (MODE == 3) {
-        ms_mean_windows(j, [&](int, int cv) {
-            const int bin = ms_code_bin(j, cv);
-            atomicAdd(&hist[bin >> 1], (bin & 1) ? 0x10000u : 1u);
-        });
-        return;
-    }
     const int n = j.n;
     for (int i0 = threadIdx.x; i0 < n; i0 += 4 * FP_THREADS) {     // four independent elements per trip
         int bin[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = min(i0 + u * FP_THREADS, n - 1);
-            uint32_t key;
-            ms_eval<MODE>(j, i, key, bin[u]);
-        }
+        for (int u = 0; u < 4; u++) bin[u] = ms_bin(j, ms_value<MODE>(j, min(i0 + u * FP_THREADS, n - 1)));
 #pragma unroll
         for (int u = 0; u < 4; u++)
             if (i0 + u * FP_THREADS < n) atomicAdd(&hist[bin[u] >> 1], (bin[u] & 1) ? 0x10000u : 1u);
@@ -692,31 +644,21 @@ __device__ __forceinline__ void ms_hist_pass(const MsJob& j, uint32_t* hist) {
 template <int MODE>
 __device__ __forceinline__ void ms_gather_pass(const MsJob& j, MsState& ms, const uint32_t* hist) {
     const unsigned short* to_list = reinterpret_cast<const unsigned short*>(hist);
-    auto put = [&](uint32_t key, int sl) {
-        const uint32_t pos = atomicAdd(&ms.slot_n[sl], 1u);
-        if (pos < (uint32_t)MS_CAND) ms.cand[sl][pos] = key;
-    };
-    if (MODE == 3) {
-        ms_mean_windows(j, [&](int, int cv) {
-            const int sl = to_list[ms_code_bin(j, cv)];
-            if (sl) put((uint32_t)cv, sl - 1);
-        });
-        return;
-    }
     const int n = j.n;
     for (int i0 = threadIdx.x; i0 < n; i0 += 4 * FP_THREADS) {
+        float x[4];
         int sl[4];
-        uint32_t key[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int i = min(i0 + u * FP_THREADS, n - 1);
-            int bin;
-            ms_eval<MODE>(j, i, key[u], bin);
-            sl[u] = (i0 + u * FP_THREADS < n) ? to_list[bin] : 0;
+            x[u] = ms_value<MODE>(j, min(i0 + u * FP_THREADS, n - 1));
+            sl[u] = (i0 + u * FP_THREADS < n) ? to_list[ms_bin(j, x[u])] : 0;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-            if (sl[u]) put(key[u], sl[u] - 1);
+            if (sl[u]) {
+                const uint32_t pos = atomicAdd(&ms.slot_n[sl[u] - 1], 1u);
+                if (pos < (uint32_t)MS_CAND) ms.cand[sl[u] - 1][pos] = f32_key(x[u]);
+            }
     }
 }
 
@@ -820,12 +762,8 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
     const int nj = ms.nj, nq = ms.nq;
     for (int jj = 0; jj < nj; jj++) {
         const MsJob& j = ms.job[jj];
-        switch (j.mode) {
-            case 0: ms_hist_pass<0>(j, ms.hist[jj]); break;
-            case 1: ms_hist_pass<1>(j, ms.hist[jj]); break;
-            case 2: ms_hist_pass<2>(j, ms.hist[jj]); break;
-            default: ms_hist_pass<3>(j, ms.hist[jj]); break;
-        }
+        if (j.mode == 0) ms_hist_pass<0>(j, ms.hist[jj]);
+        else ms_hist_pass<1>(j, ms.hist[jj]);
     }
     extra_hist();
     __syncthreads();
@@ -834,12 +772,8 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
     __syncthreads();
     for (int jj = 0; jj < nj; jj++) {
         const MsJob& j = ms.job[jj];
-        switch (j.mode) {
-            case 0: ms_gather_pass<0>(j, ms, ms.hist[jj]); break;
-            case 1: ms_gather_pass<1>(j, ms, ms.hist[jj]); break;
-            case 2: ms_gather_pass<2>(j, ms, ms.hist[jj]); break;
-            default: ms_gather_pass<3>(j, ms, ms.hist[jj]); break;
-        }
+        if (j.mode == 0) ms_gather_pass<0>(j, ms, ms.hist[jj]);
+        else ms_gather_pass<1>(j, ms, ms.hist[jj]);
     }
     extra_gather();
     __syncthreads();
@@ -850,22 +784,7 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
             if (ms.q_slot[q] >= 0) continue;
             const MsJob j = ms.job[ms.q_job[q]];
             const uint32_t k = ms.q_rank[q];
-            auto key_of = [&](int i) {
-                uint32_t key = 0;
-                int bin;
-                switch (j.mode) {
-                    case 0: ms_eval<0>(j, i, key, bin); break;
-                    case 1: ms_eval<1>(j, i, key, bin); break;
-                    case 2: ms_eval<2>(j, i, key, bin); break;
-                    default: {      // the window's own sum (no sliding): the same code up to the last bits, which the band absorbs
-                        const double cref = (double)j.p[0];
-                        double s1 = 0.0;
-                        for (int u = 0; u < j.w; u++) s1 += (double)j.p[i + u] - cref;
-                        key = (uint32_t)ms_mean_code(cref + s1 / (double)j.w, j.kb);
-                    }
-                }
-                return key;
-            };
+            auto key_of = [&](int i) { return f32_key(j.mode == 0 ? ms_value<0>(j, i) : ms_value<1>(j, i)); };
             const uint32_t key = block_select_u32(j.n, k, key_of, s);
             __syncthreads();
             if (threadIdx.x == 0) ms.q_key[q] = key;
@@ -874,39 +793,28 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
     }
 }
 
-// job / rank bookkeeping (one thread)
-__device__ __forceinline__ int ms_add_job(MsState& ms, const float* p, int n, int mode, float vmin, float vmax) {
-    const int jj = ms.nj++;
+// job / rank bookkeeping: job jj with its ranks at q0 .. (one thread per job; the layout is known to every thread)
+__device__ __forceinline__ void ms_set_job(MsState& ms, int jj, const float* p, int n, int mode, float med, float vmin, float vmax,
+                                           int q0, int nq, const uint32_t* ranks) {
     MsJob& j = ms.job[jj];
     j.p = p;
-    j.c = nullptr;
     j.n = n;
     j.mode = mode;
-    j.w = 0;
-    j.med = 0.f;
+    j.med = med;
     j.vmin = vmin;
     const float d = __fsub_rn(vmax, vmin);
     float sc = (d > 0.f) ? __fdiv_rn((float)MS_BINS, d) : 0.f;
     if (!(sc < 1e30f)) sc = 0.f;       // a point range or an overflowing scale: everything lands in bin 0 (radix fallback)
     j.scale = sc;
-    j.flo = 0;
-    j.fsh = 0;
-    j.chunk = 1;
-    j.kb = 0;
-    j.q0 = ms.nq;
-    j.nq = 0;
-    return jj;
+    j.q0 = q0;
+    j.nq = nq;
+    for (int t = 0; t < nq; t++) {
+        ms.q_rank[q0 + t] = ranks[t];
+        ms.q_job[q0 + t] = jj;
+        ms.q_slot[q0 + t] = -1;
+        ms.q_key[q0 + t] = 0;
+    }
 }
-__device__ __forceinline__ int ms_add_rank(MsState& ms, int jj, uint32_t rank) {
-    const int q = ms.nq++;
-    ms.q_rank[q] = rank;
-    ms.q_job[q] = jj;
-    ms.q_slot[q] = -1;
-    ms.q_key[q] = 0;
-    ms.job[jj].nq++;
-    return q;
-}
-
 
 // np.add.reduce of n <= 512 float32 values in numpy's pairwise order by ONE warp: the recursion splits down to at most
 // four blocks of <= 128 elements, each summed with numpy's eight strided accumulators (eight lanes per block), combined
@@ -969,6 +877,14 @@ __device__ __forceinline__ float warp_np_sum_f32(int lo, int n, F at) {
 // rounds of concurrent selections, then the verdict is derived in the reference's order, so that code / check bits /
 // reported values are those of the sequential evaluation.  Anything else (and further poly(A) candidates after a failed
 // first one) takes the sequential path of validate_kernel.
+//
+// The medians of the moving variance / moving mean (mvs.py:93-107): every window gets a cheap approximation (sliding
+// float64 sums; the variance's seeded from chunk sums), reduced to an 8-BIT BIN that is kept on chip: bin 0 / 255 =
+// below / above the FOCUS, the range between the 25 % and 75 % quantiles of 64 sampled windows, bins 1..254 linear inside
+// it.  A 256-bin histogram (filled while the bins are made) gives the bins of the middle ranks; the windows of those
+// bins +- 1 are the band that is evaluated exactly and ranked, everything else is certainly below / above (a bin is
+// orders of magnitude wider than the approximation error; same argument as val_window_median).  Result = the exact
+// float32 order statistic, bit for bit.
 struct ValFastOut {      // written by thread 0, read by every thread after the closing barrier
     int code, checks, n_pores, pores_cnt, pores_single, resume;
     long long a0, pe_best;
@@ -976,11 +892,16 @@ struct ValFastOut {      // written by thread 0, read by every thread after the 
     double shift;
 };
 
-struct ValSeg {          // order keys of the minimum / maximum of [0, a1), [a1, pend), [pend, L): filled while the row is loaded
+struct ValSeg {          // order keys of the minimum / maximum of [0, a1), [a1, pend), [pend, L)
     uint32_t mn[3], mx[3];
 };
 
-__device__ __forceinline__ bool val_fast_eligible(const ValCfg& c, int L, const int64_t* pr, int ld) {
+struct ValCode8 {        // per code job (0 moving variance, 1 moving mean)
+    uint32_t hist[2][128];          // 256 bins, 16-bit counters
+    int b_lo[2], b_hi[2], below[2]; // bins of the two middle ranks; windows in bins below b_lo - 1
+};
+
+__device__ __forceinline__ bool val_fast_eligible(const ValCfg& c, int L, int64_t stride, const int64_t* pr, int ld) {
     if (!c.mvs_detect_check || ld < 2) return false;
     const int64_t a1 = pr[0], pe = pr[1];
     if (a1 <= 0 || pe == 0 || a1 > (int64_t)L) return false;
@@ -989,15 +910,26 @@ __device__ __forceinline__ bool val_fast_eligible(const ValCfg& c, int L, const 
     if (nominal <= c.pa_var_window + 2 || nominal <= c.pa_mean_window + 2) return false;
     const int m = (int)(min(pe, (int64_t)L) - a1);
     const int cntv = m - c.pa_var_window + 1, cntm = m - c.pa_mean_window + 1;
-    if (c.pa_var_window < 4 || cntv <= 4 * VAL_BAND_CAP / 3 || cntm <= 4 * VAL_BAND_CAP / 3) return false;
+    if (cntv < 1 || cntm < 1 || (int64_t)cntv + cntm > 2 * stride) return false;
     const int C = (cntv + FP_THREADS - 1) / FP_THREADS;
     if ((m + C - 1) / C > MS_CHUNKS) return false;
     return true;
 }
 
-__device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const float* vsig, unsigned short* codes, int L, int64_t fl,
-                                      const int64_t* pr, const ValSeg& seg, MsState& ms, ValBand& bd, ValBand& bdm, FpScratch& s, int* sh_i,
-                                      int* sh_pores, double* sh_d, double* sh_v, float* scratch, ValSel& vs_old, ValFastOut& fo) {
+__device__ __forceinline__ int val_var_code(double var) {     // float32 bit pattern >> 12: 2048 codes per octave, monotone
+    float v32 = (float)var;
+    if (!(v32 > 0.f)) v32 = 0.f;
+    return (int)(__float_as_uint(v32) >> 12);
+}
+__device__ __forceinline__ int val_mean_code(double mean, uint32_t kb) {   // distance of the float32 order key from a lower bound's
+    const uint32_t k = f32_key((float)mean);
+    return k > kb ? (int)min(k - kb, 0x7ffffff0u) : 0;
+}
+__device__ __forceinline__ int val_bin8(int code, int flo, int fsh) { return code < flo ? 0 : min(255, 1 + ((code - flo) >> fsh)); }
+
+__device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const float* vsig, unsigned char* bins8, int L, int64_t fl,
+                                      const int64_t* pr, ValSeg& seg, MsState& ms, ValCode8& c8, ValBand& bd, ValBand& bdm, FpScratch& s,
+                                      int* sh_i, int* sh_pores, double* sh_d, double* sh_v, float* scratch, ValSel& vs_old, ValFastOut& fo) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a1 = (int)pr[0], e = a1, hi = a1;
     const int64_t pe = pr[1];
@@ -1005,16 +937,15 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     const int m = pend - e;
     const int wv = c.pa_var_window, wm = c.pa_mean_window;
     const int cntv = m - wv + 1, cntm = m - wm + 1;
-    const float mnA = f32_unkey(seg.mn[0]), mxA = f32_unkey(seg.mx[0]);
-    const float mnP = f32_unkey(seg.mn[1]), mxP = f32_unkey(seg.mx[1]);
-    const float mnR = (pend < L) ? fminf(mnP, f32_unkey(seg.mn[2])) : mnP, mxR = (pend < L) ? fmaxf(mxP, f32_unkey(seg.mx[2])) : mxP;
+    unsigned char* bv = bins8;             // [cntv] bins of the moving variance
+    unsigned char* bm = bins8 + cntv;      // [cntm] bins of the moving mean
+    const bool all_v = cntv <= VAL_BAND_CAP, all_m = cntm <= VAL_BAND_CAP;     // few windows: all of them are "the band"
 
-    // ---- phase 1a: chunk sums of the centred poly(A) samples (for the sliding sums of the moving variance), open pores
+    // ---- phase 1a: chunk sums of the centred poly(A) samples (seeds of the sliding sums of the moving variance), open
+    // pores, minimum / maximum of the three ranges of the row (bounds of the bin maps)
     const int C = (cntv + FP_THREADS - 1) / FP_THREADS;     // windows per thread
     const int nch = (m + C - 1) / C;
-    const int Cm = (cntm + FP_THREADS - 1) / FP_THREADS;    // the same for the moving mean
-    const uint32_t kbm = f32_key(mnP);                      // every mean of poly(A) samples is >= their minimum
-    int* smp = bdm.idx;                                     // 2 x 64 sample codes (the mean's band list is free until round B)
+    const int Cm = (cntm + FP_THREADS - 1) / FP_THREADS;
     double* S = reinterpret_cast<double*>(&ms.cand[0][0]);
     double* Q = S + MS_CHUNKS;
     const double cref = (double)vsig[e];
@@ -1028,6 +959,27 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
         }
         S[ch] = s1;
         Q[ch] = s2;
+    }
+    {
+        const int lo3[3] = {0, a1, pend}, hi3[3] = {a1, pend, L};
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+            for (int i = lo3[r] + tid; i < hi3[r]; i += FP_THREADS) {
+                const float x = vsig[i];
+                mn = fminf(mn, x);
+                mx = fmaxf(mx, x);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (lane == 0) {
+                atomicMin(&seg.mn[r], f32_key(mn));
+                atomicMax(&seg.mx[r], f32_key(mx));
+            }
+        }
     }
     if (c.detect_open_pores) {
         // one pass: position i is kept iff it is an open-pore sample with none within min_obs_diff - 1 samples before it and
@@ -1051,6 +1003,10 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     }
     __syncthreads();
 
+    const float mnA = f32_unkey(seg.mn[0]), mxA = f32_unkey(seg.mx[0]);
+    const float mnP = f32_unkey(seg.mn[1]), mxP = f32_unkey(seg.mx[1]);
+    const float mnR = (pend < L) ? fminf(mnP, f32_unkey(seg.mn[2])) : mnP, mxR = (pend < L) ? fmaxf(mxP, f32_unkey(seg.mx[2])) : mxP;
+    const uint32_t kbm = f32_key(mnP);                      // every mean of poly(A) samples is >= their minimum
     // open pores -> adapter start
     int64_t a0 = 0;
     int n_pores = 0, pores_cnt = -1, pores_single = 0;
@@ -1071,84 +1027,60 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     const int b0 = (int)min(a0, (int64_t)hi);
     const int nseg = hi - b0;
     const bool have_means = c.real_signal_check && nseg >= 2 * c.mean_window;
+    int* smp = bdm.idx;                    // 2 x 64 sample codes (the mean's band list is free until round B)
 
-    // ---- phase 1b: moving variance of every window, approximately (sliding float64 sums seeded from the chunk sums),
-    // stored as a 16-bit code: the float32 bit pattern >> 12 relative to a bound of the variance (monotone; 2048 codes per octave)
-    {
-        const float rng = __fsub_rn(mxP, mnP);
-        const float vb = rng * rng * 0.2503f + 1e-30f;
-        const int base = max(0, (int)(__float_as_uint(vb) >> 12) - 65534);
-        const double inv_w = 1.0 / (double)wv;
-        int cmn = 65535, cmx = 0;
-        const int p0 = tid * C;
-        if (p0 < cntv) {
-            const int k = wv / C;
-            double s1 = 0.0, s2 = 0.0;
-            for (int q = 0; q < k; q++) {
-                s1 += S[tid + q];
-                s2 += Q[tid + q];
-            }
-            for (int i = p0 + k * C; i < p0 + wv; i++) {
-                const double d = (double)vsig[e + i] - cref;
-                s1 += d;
-                s2 += d * d;
-            }
-            const int pe_ = min(p0 + C, cntv);
-            for (int p = p0;; p++) {
-                const double mu = s1 * inv_w;
-                float v32 = (float)(s2 * inv_w - mu * mu);
-                if (!(v32 > 0.f)) v32 = 0.f;
-                const int code = max(0, min(65535, (int)(__float_as_uint(v32) >> 12) - base));
-                codes[p] = (unsigned short)code;
-                cmn = min(cmn, code);
-                cmx = max(cmx, code);
-                if (p + 1 >= pe_) break;
-                const double dn = (double)vsig[e + p + wv] - cref, dl = (double)vsig[e + p] - cref;
-                s1 += dn - dl;
-                s2 += dn * dn - dl * dl;
-            }
+    // the sums of a thread's first variance window from the chunk sums
+    auto var_seed = [&](int p0, double& s1, double& s2) {
+        const int k = wv / C;
+        s1 = 0.0;
+        s2 = 0.0;
+        for (int q = 0; q < k; q++) {
+            s1 += S[p0 / C + q];
+            s2 += Q[p0 / C + q];
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            cmn = min(cmn, __shfl_xor_sync(0xffffffffu, cmn, o));
-            cmx = max(cmx, __shfl_xor_sync(0xffffffffu, cmx, o));
+        for (int i = p0 + k * C; i < p0 + wv; i++) {
+            const double d = (double)vsig[e + i] - cref;
+            s1 += d;
+            s2 += d * d;
         }
-        if (lane == 0) {
-            atomicMin(&sh_i[5], cmn);
-            atomicMax(&sh_i[6], cmx);
+    };
+    const double inv_wv = 1.0 / (double)wv, inv_wm = 1.0 / (double)wm;
+
+    // ---- phase 1b: samples for the focus (every eighth thread's first window), real_range_check's two means
+    if ((tid & 7) == 0) {
+        int cv = -1, cm = -1;
+        if (tid * C < cntv) {
+            double s1, s2;
+            var_seed(tid * C, s1, s2);
+            const double mu = s1 * inv_wv;
+            cv = val_var_code(s2 * inv_wv - mu * mu);
         }
-        // samples for the focus of the two code histograms: the code of every eighth thread's first window
-        if ((tid & 7) == 0) {
-            smp[tid >> 3] = (p0 < cntv) ? (int)codes[p0] : -1;
-            const int q0 = tid * Cm;
-            int cm = -1;
-            if (q0 < cntm) {
-                double s1 = 0.0;
-                for (int i = 0; i < wm; i++) s1 += (double)vsig[e + q0 + i] - cref;
-                cm = ms_mean_code(cref + s1 / (double)wm, kbm);
-            }
-            smp[64 + (tid >> 3)] = cm;
+        if (tid * Cm < cntm) {
+            double s1 = 0.0;
+            for (int i = 0; i < wm; i++) s1 += (double)vsig[e + tid * Cm + i] - cref;
+            cm = val_mean_code(cref + s1 * inv_wm, kbm);
         }
-        // real_range_check's two means (float32, numpy's pairwise order): one warp each
-        if (have_means && (warp == FP_WARPS - 1 || warp == FP_WARPS - 2)) {
-            const bool first_one = warp == FP_WARPS - 1;
-            const int base_i = first_one ? b0 : hi - c.mean_window;
-            const float sm = (c.mean_window <= 512) ? warp_np_sum_f32(base_i, c.mean_window, [&](int i) { return vsig[i]; })
-                                                    : np_pairwise<float>(base_i, c.mean_window, [&](int i) { return vsig[i]; });
-            if (lane == 0) sh_d[first_one ? 0 : 1] = (double)__fdiv_rn(sm, (float)c.mean_window);
-        }
+        smp[tid >> 3] = cv;
+        smp[64 + (tid >> 3)] = cm;
+    }
+    if (have_means && (warp == FP_WARPS - 1 || warp == FP_WARPS - 2)) {     // float32, numpy's pairwise order: one warp each
+        const bool first_one = warp == FP_WARPS - 1;
+        const int base_i = first_one ? b0 : hi - c.mean_window;
+        const float sm = (c.mean_window <= 512) ? warp_np_sum_f32(base_i, c.mean_window, [&](int i) { return vsig[i]; })
+                                                : np_pairwise<float>(base_i, c.mean_window, [&](int i) { return vsig[i]; });
+        if (lane == 0) sh_d[first_one ? 0 : 1] = (double)__fdiv_rn(sm, (float)c.mean_window);
     }
     __syncthreads();
 
-    // focus of the code histograms: the 25 % / 75 % quantiles of the samples (64 each; the middle ranks asked for lie
-    // 4 sigma inside, and a miss only costs the radix fallback).  Warps 0-1: moving variance, warps 2-3: moving mean.
-    // Next to it the histograms are cleared.
+    // ---- focus of the two code histograms: the 25 % / 75 % quantiles of the samples (the middle ranks lie 4 sigma inside;
+    // a miss only costs the exact evaluation of every window).  Warps 0-1: variance, warps 2-3: mean.  Histograms cleared.
     uint32_t* hz = &ms.hist[0][0];
     for (int i = tid; i < MS_MAXJ * MS_BINS / 2; i += FP_THREADS) hz[i] = 0;
     if (tid < MS_MAXS) ms.slot_n[tid] = 0;
+    if (tid < 256) (&c8.hist[0][0])[tid] = 0;
     if (tid < 128) {
         const int* sp = smp + (tid & 64);
-        const int t = tid & 63, x = sp[t];
+        const int t = tid & 63, x = sp[t], which = tid >> 6;
         int ns = 0, rank = 0;
 #pragma unroll 8
         for (int u = 0; u < 64; u++) {
@@ -1157,219 +1089,237 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
             rank += (y >= 0) && ((y < x) || (y == x && u < t));
         }
         if (x >= 0) {
-            if (rank == ns / 4) sh_i[8 + (tid >> 6) * 2] = x;
-            if (rank == (ns * 3) / 4) sh_i[9 + (tid >> 6) * 2] = x;
+            if (rank == ns / 4) sh_i[8 + which * 2] = x;
+            if (rank == (ns * 3) / 4) sh_i[9 + which * 2] = x;
         }
     }
     __syncthreads();
 
-    // ---- round A: every selection that does not need another one's result
-    int qa = -1, ql = -1, qp = -1, qs1 = -1, qs2 = -1, qv = -1, qm = -1, qm1 = -1, qm2 = -1;   // first rank of each job
-    double g85l = 0, g15l = 0, g85p = 0, g15p = 0;
+    // ---- phase 1c: every window's approximation -> bin -> histogram; the jobs of round A are set up next to it
+    const int flo_v = sh_i[8], flo_m = sh_i[10];
+    int fsh_v = 0, fsh_m = 2;               // the mean's codes are 1 ulp apart: a bin of >= 4 ulp keeps the +-1-bin band safe
+    while ((((long long)sh_i[9] - flo_v) >> fsh_v) > 253) fsh_v++;
+    while ((((long long)sh_i[11] - flo_m) >> fsh_m) > 253) fsh_m++;
+    // rank layout of round A (every thread derives it; the lane 0 of warp jj writes job jj)
     const int nn = min(c.max_obs_local_range, nseg);
+    const bool lr_on = c.real_signal_check && nn >= 1;
+    const bool lr_merged = lr_on && nn == hi;          // real_range_check's percentiles over the whole adapter: ranks of the same job
     const int up = min(e + c.median_shift_window, L), dn = max(e - c.median_shift_window, 0);
     const int ms_e = min(a1, L);
     const int ms_up = (int)min(min((int64_t)a1 + c.med_shift_window, fl), (int64_t)L), ms_dn = (int)max((int64_t)a1 - c.med_shift_window, (int64_t)0);
     const int ms_n1 = max(0, ms_up - ms_e), ms_n2 = max(0, ms_e - min(ms_dn, ms_e));
-    // every thread derives the rank layout (needed to read the results); thread 0 writes it
-    {
-        int q = 0;
-        qa = q; q += 2;                                 // adapter median
-        if (c.real_signal_check && nn >= 1) { ql = q; q += 4; }
-        qp = q; q += 6;                                 // poly(A): p85 pair, p15 pair, median pair
-        qs1 = q; q += 2;
-        qs2 = q; q += 2;
-        qv = q; q += 2;
-        qm = q; q += 2;
-        if (c.detect_med_shift && ms_n1 >= 1) { qm1 = q; q += 2; }
-        if (c.detect_med_shift && ms_n2 >= 1) { qm2 = q; q += 2; }
+    int jn = 0, qn = 0;
+    const int ja = jn++, qa = qn;
+    qn += 2;
+    int jl = -1, ql = -1;
+    if (lr_on) {
+        ql = qn;
+        qn += 4;
+        if (!lr_merged) jl = jn++;
+    }
+    const int jp = jn++, qp = qn;
+    qn += 6;
+    const int js1 = jn++, qs1 = qn;
+    qn += 2;
+    const int js2 = jn++, qs2 = qn;
+    qn += 2;
+    int jm1 = -1, qm1 = -1, jm2 = -1, qm2 = -1;
+    if (c.detect_med_shift && ms_n1 >= 1) {
+        jm1 = jn++;
+        qm1 = qn;
+        qn += 2;
+    }
+    if (c.detect_med_shift && ms_n2 >= 1) {
+        jm2 = jn++;
+        qm2 = qn;
+        qn += 2;
+    }
+    double g85l = 0, g15l = 0, g85p = 0, g15p = 0;
+    uint32_t rl[4] = {0, 0, 0, 0}, rp[6];
+    if (lr_on) {
+        pct_ranks(nn, 85.0, &rl[0], &rl[1], &g85l);
+        pct_ranks(nn, 15.0, &rl[2], &rl[3], &g15l);
+    }
+    pct_ranks(m, 85.0, &rp[0], &rp[1], &g85p);
+    pct_ranks(m, 15.0, &rp[2], &rp[3], &g15p);
+    rp[4] = (uint32_t)((m - 1) / 2);
+    rp[5] = (uint32_t)(m / 2);
+    if (lane == 0 && warp < jn) {
+        auto median_job = [&](int jj, int q0, const float* p, int n, float lo, float hi_) {
+            const uint32_t rk[2] = {(uint32_t)((n - 1) / 2), (uint32_t)(n / 2)};
+            ms_set_job(ms, jj, p, n, 0, 0.f, lo, hi_, q0, 2, rk);
+        };
+        if (warp == ja) {
+            if (lr_merged) {
+                const uint32_t rk[6] = {(uint32_t)((hi - 1) / 2), (uint32_t)(hi / 2), rl[0], rl[1], rl[2], rl[3]};
+                ms_set_job(ms, ja, vsig, hi, 0, 0.f, mnA, mxA, qa, 6, rk);
+            } else {
+                median_job(ja, qa, vsig, hi, mnA, mxA);
+            }
+        }
+        if (warp == jl) ms_set_job(ms, jl, vsig + (hi - nn), nn, 0, 0.f, mnA, mxA, ql, 4, rl);
+        if (warp == jp) ms_set_job(ms, jp, vsig + e, m, 0, 0.f, mnP, mxP, qp, 6, rp);
+        if (warp == js1) median_job(js1, qs1, vsig + e, up - e, mnR, mxR);
+        if (warp == js2) median_job(js2, qs2, vsig + dn, e - dn, mnA, mxA);
+        if (warp == jm1) median_job(jm1, qm1, vsig + ms_e, ms_n1, mnR, mxR);
+        if (warp == jm2) median_job(jm2, qm2, vsig + min(ms_dn, ms_e), ms_n2, mnA, mxA);
+        if (warp == 0) {
+            ms.nj = jn;
+            ms.nq = qn;
+            ms.n_slots = 0;
+            ms.crowded = 0;
+            bd.n = 0;
+            bd.below = 0;
+            bdm.n = 0;
+            bdm.below = 0;
+        }
     }
     {
-        uint32_t r0, r1;
-        if (ql >= 0) {
-            pct_ranks(nn, 85.0, &r0, &r1, &g85l);
-            pct_ranks(nn, 15.0, &r0, &r1, &g15l);
+        if (!all_v && tid * C < cntv) {
+            const int p0 = tid * C, pe_ = min(p0 + C, cntv);
+            double s1, s2;
+            var_seed(p0, s1, s2);
+            for (int p = p0;; p++) {
+                const double mu = s1 * inv_wv;
+                const int b = val_bin8(val_var_code(s2 * inv_wv - mu * mu), flo_v, fsh_v);
+                bv[p] = (unsigned char)b;
+                atomicAdd(&c8.hist[0][b >> 1], (b & 1) ? 0x10000u : 1u);
+                if (p + 1 >= pe_) break;
+                const double dn_ = (double)vsig[e + p + wv] - cref, dl = (double)vsig[e + p] - cref;
+                s1 += dn_ - dl;
+                s2 += dn_ * dn_ - dl * dl;
+            }
         }
-        pct_ranks(m, 85.0, &r0, &r1, &g85p);
-        pct_ranks(m, 15.0, &r0, &r1, &g15p);
-    }
-    if (tid == 0) {
-        ms.nj = 0;
-        ms.nq = 0;
-        ms.n_slots = 0;
-        ms.crowded = 0;
-        auto median_job = [&](const float* p, int n, float lo, float hi_) {
-            const int jj = ms_add_job(ms, p, n, 0, lo, hi_);
-            ms_add_rank(ms, jj, (uint32_t)((n - 1) / 2));
-            ms_add_rank(ms, jj, (uint32_t)(n / 2));
-            return jj;
-        };
-        median_job(vsig, hi, mnA, mxA);
-        if (ql >= 0) {
-            const int jj = ms_add_job(ms, vsig + (hi - nn), nn, 0, mnA, mxA);
-            uint32_t r0, r1;
-            double g;
-            pct_ranks(nn, 85.0, &r0, &r1, &g);
-            ms_add_rank(ms, jj, r0);
-            ms_add_rank(ms, jj, r1);
-            pct_ranks(nn, 15.0, &r0, &r1, &g);
-            ms_add_rank(ms, jj, r0);
-            ms_add_rank(ms, jj, r1);
+        if (!all_m && tid * Cm < cntm) {
+            const int p0 = tid * Cm, pe_ = min(p0 + Cm, cntm);
+            double s1 = 0.0;
+            for (int i = 0; i < wm; i++) s1 += (double)vsig[e + p0 + i] - cref;
+            for (int p = p0;; p++) {
+                const int b = val_bin8(val_mean_code(cref + s1 * inv_wm, kbm), flo_m, fsh_m);
+                bm[p] = (unsigned char)b;
+                atomicAdd(&c8.hist[1][b >> 1], (b & 1) ? 0x10000u : 1u);
+                if (p + 1 >= pe_) break;
+                s1 += (double)vsig[e + p + wm] - (double)vsig[e + p];
+            }
         }
-        {
-            const int jj = ms_add_job(ms, vsig + e, m, 0, mnP, mxP);
-            uint32_t r0, r1;
-            double g;
-            pct_ranks(m, 85.0, &r0, &r1, &g);
-            ms_add_rank(ms, jj, r0);
-            ms_add_rank(ms, jj, r1);
-            pct_ranks(m, 15.0, &r0, &r1, &g);
-            ms_add_rank(ms, jj, r0);
-            ms_add_rank(ms, jj, r1);
-            ms_add_rank(ms, jj, (uint32_t)((m - 1) / 2));
-            ms_add_rank(ms, jj, (uint32_t)(m / 2));
-        }
-        median_job(vsig + e, up - e, mnR, mxR);
-        median_job(vsig + dn, e - dn, mnA, mxA);
-        auto focus = [&](MsJob& j, int flo, int fhi) {
-            j.flo = flo;
-            int sh = 0;
-            while ((((long long)fhi - flo) >> sh) > MS_BINS - 3) sh++;
-            j.fsh = sh;
-        };
-        {   // moving variance: stored codes
-            const int jj = ms_add_job(ms, nullptr, cntv, 2, 0.f, 0.f);
-            MsJob& j = ms.job[jj];
-            j.c = codes;
-            focus(j, sh_i[8], sh_i[9]);
-            ms_add_rank(ms, jj, (uint32_t)((cntv - 1) / 2));
-            ms_add_rank(ms, jj, (uint32_t)(cntv / 2));
-        }
-        {   // moving mean: codes made on the fly
-            const int jj = ms_add_job(ms, vsig + e, cntm, 3, 0.f, 0.f);
-            MsJob& j = ms.job[jj];
-            j.w = wm;
-            j.chunk = Cm;
-            j.kb = kbm;
-            focus(j, sh_i[10], sh_i[11]);
-            ms_add_rank(ms, jj, (uint32_t)((cntm - 1) / 2));
-            ms_add_rank(ms, jj, (uint32_t)(cntm / 2));
-        }
-        if (qm1 >= 0) median_job(vsig + ms_e, ms_n1, mnR, mxR);
-        if (qm2 >= 0) median_job(vsig + min(ms_dn, ms_e), ms_n2, mnA, mxA);
-        bd.n = 0;
-        bd.below = 0;
-        bdm.n = 0;
-        bdm.below = 0;
     }
     __syncthreads();
-    ms_round(ms, s, [] {}, [] {}, [] {});
+
+    // ---- round A: every selection on samples that does not need another one's result; two more warps find the bins of
+    // the middle ranks of the two code histograms
+    const uint32_t rkv0 = (uint32_t)((cntv - 1) / 2), rkv1 = (uint32_t)(cntv / 2);
+    const uint32_t rkm0 = (uint32_t)((cntm - 1) / 2), rkm1 = (uint32_t)(cntm / 2);
+    ms_round(ms, s, [] {},
+        [&] {
+            const int which = warp - (FP_WARPS - 2);      // warps 14, 15
+            if (which < 0) return;
+            const uint32_t* h = c8.hist[which] + lane * 4;     // 8 bins per lane
+            uint32_t cnt8[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                cnt8[2 * t] = h[t] & 0xffffu;
+                cnt8[2 * t + 1] = h[t] >> 16;
+                sum += cnt8[2 * t] + cnt8[2 * t + 1];
+            }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            uint32_t run = inc - sum;
+            const uint32_t k0 = which ? rkm0 : rkv0, k1 = which ? rkm1 : rkv1;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                if (k0 >= run && k0 < run + cnt8[t]) c8.b_lo[which] = lane * 8 + t;
+                if (k1 >= run && k1 < run + cnt8[t]) c8.b_hi[which] = lane * 8 + t;
+                run += cnt8[t];
+            }
+        },
+        [] {});
     auto qf = [&](int q) { return f32_unkey(ms.q_key[q]); };
     const float med = median_of(hi, qf(qa), qf(qa + 1));
-    const double lr = (ql >= 0) ? __dsub_rn(pct_lerp(qf(ql), qf(ql + 1), g85l), pct_lerp(qf(ql + 2), qf(ql + 3), g15l)) : 0.0;
+    const double lr = lr_on ? __dsub_rn(pct_lerp(qf(ql), qf(ql + 1), g85l), pct_lerp(qf(ql + 2), qf(ql + 3), g15l)) : 0.0;
     const double r_lr = __dsub_rn(pct_lerp(qf(qp), qf(qp + 1), g85p), pct_lerp(qf(qp + 2), qf(qp + 3), g15p));
     const double r_med = (double)median_of(m, qf(qp + 4), qf(qp + 5));
     const double r_shift = (double)__fsub_rn(median_of(up - e, qf(qs1), qf(qs1 + 1)), median_of(e - dn, qf(qs2), qf(qs2 + 1)));
-    const int code_k0 = (int)ms.q_key[qv], code_k1 = (int)ms.q_key[qv + 1];
-    const int mcode_k0 = (int)ms.q_key[qm], mcode_k1 = (int)ms.q_key[qm + 1];
-    const uint32_t rkv0 = (uint32_t)((cntv - 1) / 2), rkv1 = (uint32_t)(cntv / 2);
-    const uint32_t rkm0 = (uint32_t)((cntm - 1) / 2), rkm1 = (uint32_t)(cntm / 2);
-    const MsJob mjob = ms.job[ms.q_job[qm]];      // the moving-mean job, for the band pass of round B
     const float qnan32 = __int_as_float(0x7fc00000);
     const double msv = c.detect_med_shift ? (double)__fsub_rn(qm1 >= 0 ? median_of(ms_n1, qf(qm1), qf(qm1 + 1)) : qnan32,
                                                               qm2 >= 0 ? median_of(ms_n2, qf(qm2), qf(qm2 + 1)) : qnan32) : 0.0;
     const double mean_start = sh_d[0], mean_end = sh_d[1];
+    // the bands of the two code jobs: bins of the middle ranks +- 1 (bins 0 / 255 = outside the focus: taken whole, which
+    // overflows the band and sends the read to the exact evaluation of every window)
+    const int bv_lo = all_v ? 0 : max(0, c8.b_lo[0] - 1), bv_hi = all_v ? 255 : min(255, c8.b_hi[0] + 1);
+    const int bm_lo = all_m ? 0 : max(0, c8.b_lo[1] - 1), bm_hi = all_m ? 255 : min(255, c8.b_hi[1] + 1);
     __syncthreads();      // everyone has read the results of round A
 
-    // ---- round B: the adapter MAD (needs the median) and the exact evaluation of the variance windows around the middle
+    // ---- round B: the adapter MAD (needs the median) and the exact evaluation of the windows around the middle
     for (int i = tid; i < MS_BINS / 2; i += FP_THREADS) hz[i] = 0;
     if (tid < MS_MAXS) ms.slot_n[tid] = 0;
-    const int c_lo = max(0, code_k0 - 1), c_hi = code_k1 + 1;
-    // the mean's codes are float32 order keys (1 ulp apart): three codes of margin keep every window outside the band
-    // strictly below / above the exact middle values even when exact and approximate mean round to neighbouring floats
-    const int cm_lo = max(0, mcode_k0 - 3), cm_hi = mcode_k1 + 3;
     if (tid == 0) {
-        ms.nj = 0;
-        ms.nq = 0;
+        ms.nj = 1;
+        ms.nq = 2;
         ms.n_slots = 0;
         ms.crowded = 0;
         const float dmax = fmaxf(__fsub_rn(mxA, med), __fsub_rn(med, mnA));
-        const int jj = ms_add_job(ms, vsig, hi, 1, 0.f, dmax);
-        ms.job[jj].med = med;
-        ms_add_rank(ms, jj, (uint32_t)((hi - 1) / 2));
-        ms_add_rank(ms, jj, (uint32_t)(hi / 2));
+        const uint32_t rk[2] = {(uint32_t)((hi - 1) / 2), (uint32_t)(hi / 2)};
+        ms_set_job(ms, 0, vsig, hi, 1, med, 0.f, dmax, 0, 2, rk);
     }
     __syncthreads();
-    bool band_ok = true;
+    auto band_pass = [&](const unsigned char* b8, int cnt, bool all, int lo8, int hi8, ValBand& B) {
+        if (all) {
+            for (int p = tid; p < cnt; p += FP_THREADS) B.idx[p] = p;
+            if (tid == 0) B.n = cnt;
+            return;
+        }
+        int below = 0;
+        for (int p = tid; p < cnt; p += FP_THREADS) {
+            const int b = (int)b8[p];
+            if (b < lo8) below++;
+            else if (b <= hi8) {
+                const int pos = atomicAdd(&B.n, 1);
+                if (pos < VAL_BAND_CAP) B.idx[pos] = p;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if (lane == 0 && below) atomicAdd(&B.below, below);
+    };
+    auto band_rank = [&](ValBand& B, uint32_t k0, uint32_t k1, int first, int step) {
+        const int nb = B.n, r0 = (int)k0 - B.below, r1 = (int)k1 - B.below;
+        if (nb > VAL_BAND_CAP || r0 < 0 || r1 >= nb) return;
+        for (int j = first; j < nb; j += step) {
+            const float x = B.val[j];
+            int rank = 0;
+            for (int u = 0; u < nb; u++) {
+                const float y = B.val[u];
+                rank += (y < x) || (y == x && u < j);
+            }
+            if (rank == r0) B.out[0] = x;
+            if (rank == r1) B.out[1] = x;
+        }
+    };
     ms_round(ms, s,
         [&] {   // next to the histogram pass: windows certainly below the middle, windows inside the band
-            int below = 0;
-            for (int p = tid; p < cntv; p += FP_THREADS) {
-                const int cv = (int)codes[p];
-                if (cv < c_lo) below++;
-                else if (cv <= c_hi) {
-                    const int pos = atomicAdd(&bd.n, 1);
-                    if (pos < VAL_BAND_CAP) bd.idx[pos] = p;
-                }
-            }
-            int below_m = 0;
-            ms_mean_windows(mjob, [&](int p, int cv) {
-                if (cv < cm_lo) below_m++;
-                else if (cv <= cm_hi) {
-                    const int pos = atomicAdd(&bdm.n, 1);
-                    if (pos < VAL_BAND_CAP) bdm.idx[pos] = p;
-                }
-            });
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                below += __shfl_xor_sync(0xffffffffu, below, o);
-                below_m += __shfl_xor_sync(0xffffffffu, below_m, o);
-            }
-            if (lane == 0 && below) atomicAdd(&bd.below, below);
-            if (lane == 0 && below_m) atomicAdd(&bdm.below, below_m);
+            band_pass(bv, cntv, all_v, bv_lo, bv_hi, bd);
+            band_pass(bm, cntm, all_m, bm_lo, bm_hi, bdm);
         },
-        [&] {   // next to the scan: exact variance of the band's windows
-            const int nb = bd.n;
-            if (nb <= VAL_BAND_CAP && tid >= 32)      // warp 0 scans the histogram meanwhile
+        [&] {   // next to the scan (warp 0): exact statistic of the bands' windows
+            if (tid < 32) return;
+            const int nb = bd.n, nbm = bdm.n;
+            if (nb <= VAL_BAND_CAP)
                 for (int j = tid - 32; j < nb; j += FP_THREADS - 32) bd.val[j] = val_window_exact<true>(vsig, e + bd.idx[j], wv);
-            const int nbm = bdm.n;
-            if (nbm <= VAL_BAND_CAP && tid >= 32)
+            if (nbm <= VAL_BAND_CAP)
                 for (int j = FP_THREADS - 1 - tid; j < nbm; j += FP_THREADS - 32) bdm.val[j] = val_window_exact<false>(vsig, e + bdm.idx[j], wm);
         },
-        [&] {   // next to the gather: exact ranking inside the band
-            const int nb = bd.n, r0 = (int)rkv0 - bd.below, r1 = (int)rkv1 - bd.below;
-            if (nb <= VAL_BAND_CAP && r0 >= 0 && r1 < nb) {
-                for (int j = tid; j < nb; j += FP_THREADS) {
-                    const float x = bd.val[j];
-                    int rank = 0;
-                    for (int u = 0; u < nb; u++) {
-                        const float y = bd.val[u];
-                        rank += (y < x) || (y == x && u < j);
-                    }
-                    if (rank == r0) bd.out[0] = x;
-                    if (rank == r1) bd.out[1] = x;
-                }
-            }
-            const int nbm = bdm.n, m0 = (int)rkm0 - bdm.below, m1 = (int)rkm1 - bdm.below;
-            if (nbm <= VAL_BAND_CAP && m0 >= 0 && m1 < nbm) {
-                for (int j = FP_THREADS - 1 - tid; j < nbm; j += FP_THREADS) {
-                    const float x = bdm.val[j];
-                    int rank = 0;
-                    for (int u = 0; u < nbm; u++) {
-                        const float y = bdm.val[u];
-                        rank += (y < x) || (y == x && u < j);
-                    }
-                    if (rank == m0) bdm.out[0] = x;
-                    if (rank == m1) bdm.out[1] = x;
-                }
-            }
+        [&] {   // next to the gather: exact ranking inside the bands
+            band_rank(bd, rkv0, rkv1, tid, FP_THREADS);
+            band_rank(bdm, rkm0, rkm1, FP_THREADS - 1 - tid, FP_THREADS);
         });
+    bool band_ok, mband_ok;
     {
         const int nb = bd.n, r0 = (int)rkv0 - bd.below, r1 = (int)rkv1 - bd.below;
         band_ok = nb <= VAL_BAND_CAP && r0 >= 0 && r1 < nb;
-    }
-    bool mband_ok;
-    {
         const int nbm = bdm.n, m0 = (int)rkm0 - bdm.below, m1 = (int)rkm1 - bdm.below;
         mband_ok = nbm <= VAL_BAND_CAP && m0 >= 0 && m1 < nbm;
     }
@@ -1377,7 +1327,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     double r_var = band_ok ? (double)median_of(cntv, bd.out[0], bd.out[1]) : 0.0;
     double r_mean = mband_ok ? (double)median_of(cntm, bdm.out[0], bdm.out[1]) : 0.0;
     __syncthreads();
-    // uniform; a crowded band (e.g. a constant stretch): every window exactly, as the sequential path does
+    // uniform; a crowded band (a constant stretch, a middle rank outside the focus): every window exactly, as the sequential path does
     if (!band_ok) r_var = (double)val_window_median<true>(vsig, e, m, wv, scratch, bd, vs_old, s);
     if (!mband_ok) r_mean = (double)val_window_median<false>(vsig, e, m, wm, scratch, bd, vs_old, s);
 
@@ -1446,7 +1396,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
 }
 
 __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(const ValArgs a, const ValCfg c) {
-    extern __shared__ float vsig[];     // the row, then [stride] 16-bit codes of the moving variance
+    extern __shared__ float vsig[];     // the row, then [2 * stride] 8-bit bins of the moving variance / mean windows
     __shared__ FpScratch s;
     // the concurrent selections of the common read and the selection / pairwise-sum state of the sequential path are
     // never live at the same time
@@ -1462,6 +1412,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     ValTree& tree = shu.seq.tree;
     __shared__ ValBand band, band2;
     __shared__ ValSeg seg;
+    __shared__ ValCode8 c8;
     __shared__ ValFastOut fo;
     __shared__ int sh_i[12];
     __shared__ int sh_pores[VAL_PORES_LD];
@@ -1470,7 +1421,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     const int tid = threadIdx.x;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     float* scratch = a.scratch + (size_t)blockIdx.x * a.stride;
-    unsigned short* codes = reinterpret_cast<unsigned short*>(vsig + ((a.stride + 3) & ~(int64_t)3));
+    unsigned char* bins8 = reinterpret_cast<unsigned char*>(vsig + ((a.stride + 3) & ~(int64_t)3));   // [2 * stride]
 
     __shared__ unsigned long long sh_next;
     for (;;) {
@@ -1502,56 +1453,20 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         int has_nan = 0;
         if (tid < VAL_NVALS) sh_v[tid] = qnan;
         const int64_t* pr = a.preds + (size_t)r * a.ld;
-        const bool fast = val_fast_eligible(c, L, pr, a.ld);
-        {
-            // minimum / maximum of the adapter, the first poly(A) candidate and the rest of the row, for the bin maps of
-            // the concurrent selections (order keys; a NaN poisons nothing: such a row fails before they are used)
-            const int sa = fast ? (int)pr[0] : 0, sp = fast ? (int)min(pr[1], (int64_t)L) : 0;
-            uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0u, mx1 = 0u, mx2 = 0u;
-            for (int i0 = tid; i0 < L; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
-                float xv[4];
+        const bool fast = val_fast_eligible(c, L, a.stride, pr, a.ld);
+        for (int i0 = tid; i0 < L; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
+            float xv[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * FP_THREADS;
-                    xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * FP_THREADS;
-                    if (i < L) {
-                        vsig[i] = xv[u];
-                        has_nan |= (xv[u] != xv[u]);
-                        const uint32_t kv = f32_key(xv[u]);
-                        if (i < sa) {
-                            mn0 = min(mn0, kv);
-                            mx0 = max(mx0, kv);
-                        } else if (i < sp) {
-                            mn1 = min(mn1, kv);
-                            mx1 = max(mx1, kv);
-                        } else {
-                            mn2 = min(mn2, kv);
-                            mx2 = max(mx2, kv);
-                        }
-                    }
-                }
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * FP_THREADS;
+                xv[u] = (i < L) ? __ldg(row + i) : 0.0f;
             }
-            if (fast) {
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
-                    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
-                    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
-                    mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
-                    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
-                    mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
-                }
-                if ((tid & 31) == 0) {
-                    atomicMin(&seg.mn[0], mn0);
-                    atomicMin(&seg.mn[1], mn1);
-                    atomicMin(&seg.mn[2], mn2);
-                    atomicMax(&seg.mx[0], mx0);
-                    atomicMax(&seg.mx[1], mx1);
-                    atomicMax(&seg.mx[2], mx2);
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * FP_THREADS;
+                if (i < L) {
+                    vsig[i] = xv[u];
+                    has_nan |= (xv[u] != xv[u]);
                 }
             }
         }
@@ -1571,7 +1486,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         const bool use_fast = fast && code == VAL_OK;
         int resume = 0;                        // poly(A) candidates from here on go through the sequential loop
         if (use_fast) {
-            val_fast(a, c, vsig, codes, L, fl, pr, seg, shu.ms, band, band2, s, sh_i, sh_pores, sh_d, sh_v, scratch, vs, fo);
+            val_fast(a, c, vsig, bins8, L, fl, pr, seg, shu.ms, c8, band, band2, s, sh_i, sh_pores, sh_d, sh_v, scratch, vs, fo);
             code = fo.code;
             checks = fo.checks;
             n_pores = fo.n_pores;

@@ -663,15 +663,19 @@ __device__ __forceinline__ void ms_gather_pass(const MsJob& j, MsState& ms, cons
 }
 
 // One warp: exclusive scan of a job's histogram, the bin / rank inside the bin / population of every wanted rank, and
-// the candidate lists (ranks of one job that fall into the same bin share a list).
+// the candidate lists (ranks of one job that fall into the same bin share a list).  A job has at most six ranks.
 __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
     const int lane = threadIdx.x & 31;
     const MsJob& j = ms.job[jj];
     constexpr int WPL = MS_BINS / 2 / 32;     // words per lane
-    const uint32_t* h = ms.hist[jj] + lane * WPL;
-    uint32_t sum = 0;
+    uint32_t* h = ms.hist[jj] + lane * WPL;
+    uint32_t w[WPL], sum = 0;
 #pragma unroll
-    for (int t = 0; t < WPL; t++) sum += (h[t] & 0xffffu) + (h[t] >> 16);
+    for (int t = 0; t < WPL; t++) {
+        w[t] = h[t];
+        h[t] = 0;                            // from here on: bin -> 1 + candidate list (ms_gather_pass)
+        sum += (w[t] & 0xffffu) + (w[t] >> 16);
+    }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -679,50 +683,70 @@ __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
         if (lane >= o) inc += t;
     }
     const uint32_t run0 = inc - sum;
-    for (int q = j.q0; q < j.q0 + j.nq; q++) {
-        const uint32_t k = ms.q_rank[q];
-        if (k >= run0 && k < run0 + sum) {    // exactly one lane
+    const int q0 = j.q0, nq = j.nq;
+    // lane q < nq owns rank q: which lane's bins hold it, then that lane's walk (all lanes walk at once, one rank each)
+    const uint32_t myk = (lane < nq) ? ms.q_rank[q0 + lane] : 0xffffffffu;
+    int mybin = -1;
+    uint32_t myr = 0, mycnt = 0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        const uint32_t k = __shfl_sync(0xffffffffu, myk, q);
+        if (q >= nq) continue;              // uniform
+        const bool hit = k >= run0 && k < run0 + sum;
+        const unsigned who = __ballot_sync(0xffffffffu, hit);
+        int bin = -1;
+        uint32_t r = 0, cnt = 0;
+        if (hit) {
             uint32_t run = run0;
 #pragma unroll
             for (int t = 0; t < WPL; t++) {
-                const uint32_t c0 = h[t] & 0xffffu, c1 = h[t] >> 16;
+                const uint32_t c0 = w[t] & 0xffffu, c1 = w[t] >> 16;
                 if (k >= run && k < run + c0) {
-                    ms.q_bin[q] = (lane * WPL + t) * 2;
-                    ms.q_r[q] = k - run;
-                    ms.q_cnt[q] = c0;
+                    bin = (lane * WPL + t) * 2;
+                    r = k - run;
+                    cnt = c0;
                 }
                 run += c0;
                 if (k >= run && k < run + c1) {
-                    ms.q_bin[q] = (lane * WPL + t) * 2 + 1;
-                    ms.q_r[q] = k - run;
-                    ms.q_cnt[q] = c1;
+                    bin = (lane * WPL + t) * 2 + 1;
+                    r = k - run;
+                    cnt = c1;
                 }
                 run += c1;
             }
         }
-    }
-    __syncwarp();
-    uint32_t* hw = ms.hist[jj] + lane * WPL;
-#pragma unroll
-    for (int t = 0; t < WPL; t++) hw[t] = 0;       // from here on: bin -> 1 + candidate list (ms_gather_pass)
-    __syncwarp();
-    if (lane == 0) {
-        unsigned short* to_list = reinterpret_cast<unsigned short*>(ms.hist[jj]);
-        for (int q = j.q0; q < j.q0 + j.nq; q++) {
-            int sl = -2;
-            for (int u = j.q0; u < q; u++)
-                if (ms.q_bin[u] == ms.q_bin[q]) sl = ms.q_slot[u];
-            if (sl == -2) {
-                sl = -1;
-                if (ms.q_cnt[q] <= (uint32_t)MS_CAND) {
-                    sl = atomicAdd(&ms.n_slots, 1);
-                    if (sl >= MS_MAXS) sl = -1;
-                }
-            }
-            if (sl < 0) ms.crowded = 1;
-            else to_list[ms.q_bin[q]] = (unsigned short)(sl + 1);
-            ms.q_slot[q] = sl;
+        const int src = who ? __ffs(who) - 1 : 0;
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        r = __shfl_sync(0xffffffffu, r, src);
+        cnt = __shfl_sync(0xffffffffu, cnt, src);
+        if (lane == q) {
+            mybin = bin;
+            myr = r;
+            mycnt = cnt;
         }
+    }
+    // candidate lists: the first rank of a bin allocates, the others share
+    int first = -1;
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+        const int b = __shfl_sync(0xffffffffu, mybin, u);
+        if (u < lane && lane < nq && b == mybin && first < 0) first = u;
+    }
+    int sl = -1;
+    if (lane < nq && first < 0 && mybin >= 0 && mycnt <= (uint32_t)MS_CAND) {
+        sl = atomicAdd(&ms.n_slots, 1);
+        if (sl >= MS_MAXS) sl = -1;
+    }
+    const int shared_sl = __shfl_sync(0xffffffffu, sl, first < 0 ? 0 : first);
+    if (first >= 0) sl = shared_sl;
+    __syncwarp();                            // the histogram words are cleared
+    if (lane < nq) {
+        ms.q_bin[q0 + lane] = mybin;
+        ms.q_r[q0 + lane] = myr;
+        ms.q_cnt[q0 + lane] = mycnt;
+        ms.q_slot[q0 + lane] = sl;
+        if (sl < 0) ms.crowded = 1;
+        else if (first < 0) reinterpret_cast<unsigned short*>(ms.hist[jj])[mybin] = (unsigned short)(sl + 1);
     }
 }
 
@@ -1326,10 +1350,12 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     const float mad = median_of(hi, qf(0), qf(1));
     double r_var = band_ok ? (double)median_of(cntv, bd.out[0], bd.out[1]) : 0.0;
     double r_mean = mband_ok ? (double)median_of(cntm, bdm.out[0], bdm.out[1]) : 0.0;
-    __syncthreads();
     // uniform; a crowded band (a constant stretch, a middle rank outside the focus): every window exactly, as the sequential path does
-    if (!band_ok) r_var = (double)val_window_median<true>(vsig, e, m, wv, scratch, bd, vs_old, s);
-    if (!mband_ok) r_mean = (double)val_window_median<false>(vsig, e, m, wm, scratch, bd, vs_old, s);
+    if (!band_ok || !mband_ok) {
+        __syncthreads();
+        if (!band_ok) r_var = (double)val_window_median<true>(vsig, e, m, wv, scratch, bd, vs_old, s);
+        if (!mband_ok) r_mean = (double)val_window_median<false>(vsig, e, m, wm, scratch, bd, vs_old, s);
+    }
 
     // ---- the verdict, in the reference's order (combined.py:452-629)
     if (tid == 0) {

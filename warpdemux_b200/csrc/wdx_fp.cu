@@ -167,7 +167,10 @@ int run(wdx_fp* f, const FpCall& c) {
     cap64 = std::min<int64_t>(FP_MAX_LEN, std::max<int64_t>(64, (cap64 + 63) & ~(int64_t)63));
     const int cap = (int)cap64;
 
+    // host rows are staged in 256 MB pieces (the next piece copying while this one computes); rows already on the device
+    // need no staging, so the batch is cut only where the result buffers of a host caller would grow without bound
     int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / (c.stride * 4));
+    if (sig_dev) chunk = (int64_t)1 << 20;
     if (c.m) chunk = std::min<int64_t>(chunk, c.m->chunk_reads);
     chunk = std::min(chunk, c.n);
     const int64_t n_chunks = (c.n + chunk - 1) / chunk;

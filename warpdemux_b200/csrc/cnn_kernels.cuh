@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
     __shared__ int32_t pk[PK_MAXPK];
     __shared__ uint8_t st[PK_MAXPK];
     __shared__ int extra_lo, kept_total;
+    __shared__ int def_n, def_i[8], def_p[8];
+    __shared__ long long scan_hit;
     __shared__ uint32_t wtot[PK_THREADS / 32];
     const int tid = threadIdx.x;
     const int64_t read = blockIdx.x;
@@ -417,17 +419,57 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
         g = min(max(g, (int64_t)0), N - 1);
         v[i] = masked[g];
     }
-    if (tid == 0) extra_lo = -1;
+    if (tid == 0) {
+        extra_lo = -1;
+        def_n = 0;
+        scan_hit = 0x7fffffffffffffffLL;
+    }
     __syncthreads();
-    // A plateau that starts left of the window but whose midpoint may fall inside: walk back (rare).
-    if (tid == 0 && lo > 0 && v[0] == v[1]) {
-        int64_t j = lo - 1;
+    // The masked scores are flat (SCORE_EXCL) from one read's poly(A) end to the next read's adapter end: hundreds of equal
+    // samples, and a rising edge into such a plateau (a score below SCORE_EXCL before it) or a window that starts inside one
+    // sends scipy's plateau walk across them.  One thread doing that walk through global memory took 3/4 of this kernel's
+    // time; the CTA does it together: first position != x at or after `from` (forward) / at or before `from` (backward).
+    auto scan_forward = [&](int64_t from, float x) -> int64_t {      // first a >= from with flat[a] != x, or N - 1 (all threads)
+        int64_t base = from;
+        for (;;) {
+            const int64_t a = base + tid;
+            const bool hit = a >= N - 1 || masked[a] != x;
+            if (hit) atomicMin((unsigned long long*)&scan_hit, (unsigned long long)min(a, N - 1));
+            __syncthreads();
+            const int64_t h = scan_hit;
+            __syncthreads();
+            if (h != 0x7fffffffffffffffLL) {
+                if (tid == 0) scan_hit = 0x7fffffffffffffffLL;
+                __syncthreads();
+                return h;
+            }
+            base += PK_THREADS;
+        }
+    };
+    // A plateau that starts left of the window but whose midpoint may fall inside.
+    if (lo > 0 && v[0] == v[1]) {      // uniform
         const float x = v[1];
-        while (j > 0 && masked[j - 1] == x) j--;
-        if (j > 0 && masked[j - 1] < x) {  // a rising edge at j: find the end
-            int64_t e = lo;
-            while (e < N - 1 && masked[e] == x) e++;
-            if (masked[e] < x) {
+        // backward: last position b < lo with flat[b] != x (or -1): the plateau starts at b + 1
+        int64_t base = lo - 1, b = -2;
+        for (;;) {
+            const int64_t q = base - tid;
+            const bool hit = q < 0 || masked[q] != x;
+            if (hit) atomicMin((unsigned long long*)&scan_hit, (unsigned long long)(lo - 1 - max(q, (int64_t)-1)));   // distance back
+            __syncthreads();
+            const int64_t h = scan_hit;
+            __syncthreads();
+            if (h != 0x7fffffffffffffffLL) {
+                if (tid == 0) scan_hit = 0x7fffffffffffffffLL;
+                __syncthreads();
+                b = lo - 1 - h;
+                break;
+            }
+            base -= PK_THREADS;
+        }
+        const int64_t j = b + 1;
+        if (j > 0 && masked[j - 1] < x) {  // a rising edge at j (uniform: every thread reads the same element): find the end
+            const int64_t e = scan_forward(lo, x);
+            if (tid == 0 && masked[e] < x) {
                 const int64_t mid = (j + e - 1) / 2;
                 if (mid >= lo && mid < hi) extra_lo = (int)(mid - lo);
             }
@@ -441,6 +483,39 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
         const int64_t w = g - lo + 1;
         return (w >= 0 && w <= len + 1) ? v[w] : masked[g];
     };
+    // rising edges whose plateau is longer than a few samples are set aside and resolved by the whole CTA
+    constexpr int PK_SHORT = 6, PK_DEFER = 8;
+    for (int i = i0; i < i1; i++) {
+        const int64_t g = lo + i;
+        if (g < 1 || g > N - 2) continue;
+        const float x = v[1 + i];
+        if (!(v[i] < x)) continue;
+        int64_t a = g + 1;
+        while (a < N - 1 && a - g <= PK_SHORT && at(a) == x) a++;
+        if (a < N - 1 && a - g > PK_SHORT && at(a) == x) {
+            const int slot = atomicAdd(&def_n, 1);
+            if (slot < PK_DEFER) def_i[slot] = i;
+        }
+    }
+    __syncthreads();
+    {
+        const int nd = min(def_n, PK_DEFER);
+        for (int k = 0; k < nd; k++) {      // uniform
+            const int i = def_i[k];
+            const int64_t g = lo + i;
+            const float x = v[1 + i];
+            const int64_t a = scan_forward(g + 1, x);
+            if (tid == 0) {
+                int p = -1;
+                if (masked[a] < x) {
+                    const int64_t mid = (g + a - 1) / 2;
+                    if (mid < hi) p = (int)(mid - lo);
+                }
+                def_p[k] = p;
+            }
+        }
+        __syncthreads();
+    }
     // scipy _local_maxima_1d: a rising edge at g, the plateau [g, a), a falling edge at a -> midpoint
     auto peak_from = [&](int i) -> int {
         const int64_t g = lo + i;
@@ -448,7 +523,13 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
         const float x = v[1 + i];
         if (!(v[i] < x)) return -1;
         int64_t a = g + 1;
-        while (a < N - 1 && at(a) == x) a++;
+        while (a < N - 1 && a - g <= PK_SHORT && at(a) == x) a++;
+        if (a < N - 1 && a - g > PK_SHORT && at(a) == x) {      // a long plateau: resolved above (the serial walk only past the list's end)
+            const int nd = min(def_n, PK_DEFER);
+            for (int k = 0; k < nd; k++)
+                if (def_i[k] == i) return def_p[k];
+            while (a < N - 1 && at(a) == x) a++;
+        }
         if (!(at(a) < x)) return -1;
         const int64_t mid = (g + a - 1) / 2;
         return (mid < hi) ? (int)(mid - lo) : -1;

@@ -16,6 +16,9 @@ from warpdemux_b200.sig_proc import Fingerprinter  # noqa: E402
 
 def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
     sig, a0, a1 = synth_adapter_signals(n_base, seed=21, width=9000)
+    short = int(os.environ.get("FP_SHORT", "0"))
+    if short:   # adapters cut to `short` samples (CTA-shape experiments: more CTAs fit an SM with smaller slices)
+        a1 = np.minimum(a1, a0 + short)
     n = n_base * reps
     sd = torch.from_numpy(sig).cuda().repeat(reps, 1).contiguous()
     a0d = torch.from_numpy(a0).cuda().repeat(reps).contiguous()
@@ -37,6 +40,19 @@ def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
         if r:
             best = min(best, ms)
     ok = int((st == 0).sum().item())
+    from warpdemux_b200 import _lib
+    L = _lib.load()
+    if hasattr(L, "wdx_fp_prof_dump"):   # -DWDX_FP_PROF build: cycles per phase and read (thread 0 of every CTA)
+        import ctypes as C
+        buf = (C.c_uint64 * 32)()
+        L.wdx_fp_prof_dump(None, 1)
+        fp.extract_raw(sd, n, sig.shape[1], a0d, a1d, fpt, st, stream=stream)
+        torch.cuda.synchronize()
+        L.wdx_fp_prof_dump(buf, 0)
+        names = ["load", "medians", "clip", "ttest", "localmax", "nbr_sets", "rounds", "-", "scan+list", "topk", "means", "normalize", "out"]
+        ph = {nm: round(buf[i] / n) for i, nm in enumerate(names) if nm != "-"}
+        ph["sum"] = sum(ph.values())
+        print(json.dumps({"cycles_per_read": ph}), flush=True)
     print(json.dumps(dict(reads=n, ok=ok, mean_slice=float(sl.mean()), kernel_ms=round(best, 3), launches=nl,
                           reads_per_s=round(n / best * 1e3), alg_GBps=round(bytes_alg / best / 1e6, 1))), flush=True)
 

@@ -13,7 +13,10 @@ namespace wdx {
 constexpr int FP_THREADS = WDX_FP_THREADS;  // 512 x 2 CTAs/SM = 32 warps/SM at <= 64 registers
 constexpr int FP_WARPS = FP_THREADS / 32;
 constexpr int FP_MAX_EVENTS = 254;   // num_events bound (cpts has num_events + 2 entries)
-constexpr int FP_MAX_LEN = 16000;    // longest adapter slice a CTA can hold in shared memory (14 B per sample)
+#ifndef WDX_FP_MAX_LEN
+#define WDX_FP_MAX_LEN 16000
+#endif
+constexpr int FP_MAX_LEN = WDX_FP_MAX_LEN;    // longest adapter slice a CTA can hold in shared memory (14 B per sample)
 
 
 // ---- order-preserving keys ---------------------------------------------------
@@ -26,6 +29,22 @@ __device__ __forceinline__ float f32_unkey(uint32_t k) {
 }
 
 // ---- block helpers -------------------------------------------------------------
+// Phase clock of the fingerprint kernel (experiments: -DWDX_FP_PROF): thread 0 adds the cycles since its previous mark
+// to counter i; read back with wdx_fp_prof_dump.
+#ifdef WDX_FP_PROF
+__device__ unsigned long long g_fp_prof[32];
+#define FP_T(s_, i_)                                                                  \
+    do {                                                                              \
+        if (threadIdx.x == 0) {                                                       \
+            const long long t__ = clock64();                                          \
+            atomicAdd(&g_fp_prof[i_], (unsigned long long)(t__ - (s_).t_prev));       \
+            (s_).t_prev = t__;                                                        \
+        }                                                                             \
+    } while (0)
+#else
+#define FP_T(s_, i_) do { } while (0)
+#endif
+
 struct FpScratch {
     uint32_t hist[256];
     uint32_t warp_tmp[FP_WARPS];
@@ -39,6 +58,8 @@ struct FpScratch {
     int sel_bin;                       // linear-bin median: bin holding the wanted rank
     uint32_t sel_below, sel_count;     //   elements in lower bins / in that bin
     uint32_t ncand;                    //   gathered candidates
+    uint32_t amin, amax;               // smallest non-zero / largest |x| (float bit patterns) of the winsorised slice
+    long long t_prev;                  // WDX_FP_PROF builds: clock of the previous phase mark (thread 0)
     uint32_t key_lo, key_hi;
 };
 
@@ -58,13 +79,16 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, FpScratch& s, uint3
     __syncthreads();  // warp_tmp free
     if (lane == 31) s.warp_tmp[warp] = inc;
     __syncthreads();
-    uint32_t base = 0, tot = 0;
+    // every warp scans the FP_WARPS warp totals itself (one value per lane) instead of every thread adding them up
+    const uint32_t t = (lane < FP_WARPS) ? s.warp_tmp[lane] : 0u;
+    uint32_t ti = t;
 #pragma unroll
-    for (int w = 0; w < FP_WARPS; w++) {
-        const uint32_t t = s.warp_tmp[w];
-        if (w < warp) base += t;
-        tot += t;
+    for (int o = 1; o < FP_WARPS; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
     }
+    const uint32_t tot = __shfl_sync(0xffffffffu, ti, FP_WARPS - 1);
+    const uint32_t base = __shfl_sync(0xffffffffu, ti - t, warp);
     *total = tot;
     return base + inc - v;
 }

@@ -239,7 +239,12 @@ __device__ double np_pairwise_sum_warp(int n, F at) {
     const int n8 = n - (n % 8);
     if (lane < 8) {
         r = at(lane);
-        for (int i = 8 + lane; i < n8; i += 8) r = __dadd_rn(r, at(i));
+        int i = 8 + lane;
+        for (; i + 24 < n8; i += 32) {   // four operands in flight ahead of the dependent additions
+            const double v0 = at(i), v1 = at(i + 8), v2 = at(i + 16), v3 = at(i + 24);
+            r = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r, v0), v1), v2), v3);
+        }
+        for (; i < n8; i += 8) r = __dadd_rn(r, at(i));
     }
     const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2),
                  r3 = __shfl_sync(0xffffffffu, r, 3), r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5),
@@ -277,91 +282,184 @@ __device__ void small_median(const double* v, int n, double* out, double* tmp2) 
 // Works on the positions (lo, nc - 1) of score[] (find_peaks of the sub-array scores[lo:]: its first
 // and last samples are never peaks and a plateau is judged by the same neighbours, so the maxima of
 // the sub-array are the maxima of the full array whose plateau starts after lo).  Leaves the kept
-// peaks, in order, in kp[0..P) and returns P.  kp / state: scratch of (nc - lo)/2 + 8 entries.
-__device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint8_t* state,
+// peaks, in order, in kp[0..P) and returns P; also prepares select_top_k's scratch (histogram zeroed,
+// float range of the kept peaks' scores in s.vmin_key / s.vmax_key).
+//   bm:  three bitmaps (peak / kept / removed), FP_BM_WORDS(cap) words each, position i = bit i + 32
+//        (a 32-bit window around any position needs no bounds checks);
+//   kp:  (nc - lo)/2 + 8 entries; until the list is written it holds, per peak, the set of its
+//        higher-priority neighbours (two peaks are never adjacent, so position >> 1 is a unique slot).
+static_assert((FP_MAX_LEN + FP_THREADS - 1) / FP_THREADS <= 64, "a thread's positions must fit a 64-bit mask");
+static_assert(FP_THREADS >= 256, "the 256-bin histograms are zeroed by one thread per bin");
+constexpr int FP_NEAR = 7;   // neighbour distances that fit the 15-bit windows (m_obs <= FP_NEAR + 1)
+__host__ __device__ constexpr int FP_BM_WORDS(int cap) { return cap / 32 + 4; }
+
+// bits pos .. pos + 31 of a bitmap (pos >= -32)
+template <typename W>
+__device__ __forceinline__ uint32_t bm_window32(const W* bm, int pos) {
+    const int bi = pos + 32;
+    return __funnelshift_r(bm[bi >> 5], bm[(bi >> 5) + 1], bi & 31);
+}
+__device__ __forceinline__ void bm_set(uint32_t* bm, int pos) { atomicOr(&bm[(pos + 32) >> 5], 1u << (pos & 31)); }
+
+__device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint32_t* bm, int cap,
                                FpScratch& s) {
     const int tid = threadIdx.x;
-    // scipy _local_maxima_1d (strict maxima, plateaus -> midpoint), compacted in order:
-    // thread t scans the contiguous positions [lo + t*chunk, lo + (t+1)*chunk); a plateau belongs to the
-    // thread that owns its first sample, which keeps the list sorted by position.
+    const int bw = FP_BM_WORDS(cap);
+    uint32_t* pk = bm;
+    uint32_t* kept_bm = bm + bw;
+    uint32_t* rem_bm = bm + 2 * bw;
+    for (int i = tid; i < 3 * bw; i += FP_THREADS) bm[i] = 0u;
+    if (tid < 256) s.hist[tid] = 0;
+    if (tid == 0) {
+        s.vmin_key = 0xffffffffu;
+        s.vmax_key = 0u;
+        s.ncand = 0;
+        s.flag = 0;
+    }
+    __syncthreads();
+    // scipy _local_maxima_1d (strict maxima, plateaus -> midpoint): thread t walks the contiguous positions
+    // [lo + t*chunk, lo + (t+1)*chunk) once (one load per position) and marks the midpoint of every maximum
+    // that STARTS there.
     const int chunk = (nc - lo + FP_THREADS - 1) / FP_THREADS;
-    const int p_begin = min(nc - 1, max(lo + 1, lo + tid * chunk)), p_end = min(nc - 1, lo + (tid + 1) * chunk);
-    auto peak_at = [&](int i) -> int {  // midpoint of the maximum that starts at i, or -1
-        const double x = score[i];
-        if (!(score[i - 1] < x)) return -1;
-        int ahead = i + 1;
-        while (ahead < nc - 1 && score[ahead] == x) ahead++;
-        return (score[ahead] < x) ? ((i + ahead - 1) >> 1) : -1;
-    };
-    uint32_t my = 0;
-    for (int i = p_begin; i < p_end; i++) my += (peak_at(i) >= 0);
-    uint32_t total = 0;
-    uint32_t off = block_exscan(my, s, &total);
-    for (int i = p_begin; i < p_end; i++) {
-        const int pk = peak_at(i);
-        if (pk >= 0) {
-            kp[off] = (uint16_t)pk;
-            state[off] = 1;  // per-peak state: 1 undecided, 2 kept, 3 removed
-            off++;
+    const int o_begin = min(nc, lo + tid * chunk), o_end = min(nc, o_begin + chunk);
+    {
+        const int p_begin = max(lo + 1, o_begin), p_end = min(nc - 1, o_end);
+        if (p_begin < p_end) {
+            double prev = score[p_begin - 1];
+            for (int i = p_begin; i < p_end; i++) {
+                const double x = score[i];
+                if (prev < x) {
+                    int ahead = i + 1;
+                    while (ahead < nc - 1 && score[ahead] == x) ahead++;
+                    if (score[ahead] < x) bm_set(pk, (i + ahead - 1) >> 1);
+                }
+                prev = x;
+            }
         }
     }
     __syncthreads();
-    const int P0 = (int)total;
-
-    // ---- scipy _select_by_peak_distance as a fixed point over the peak list ---------
-    // A peak stays iff no STAYING peak of higher priority (score, then index) lies closer than
-    // m_obs samples; the greedy highest-first sweep of scipy computes exactly this set.
-    if (m_obs > 1) {
-        for (;;) {
-            int undecided = 0;
-            for (int j = tid; j < P0; j += FP_THREADS) {
-                if ((state[j] & 15) != 1) continue;
-                const int pj = kp[j];
-                const double x = score[pj];
-                bool killed = false, blocked = false;
-                for (int q = j - 1; q >= 0 && pj - (int)kp[q] < m_obs; q--) {
-                    const int st = state[q] & 15;
-                    if (st == 3) continue;
-                    if (score[kp[q]] > x) {  // equal scores: the higher index wins, q < j loses
-                        if (st == 2) killed = true;
-                        else blocked = true;
-                    }
-                }
-                for (int q = j + 1; q < P0 && (int)kp[q] - pj < m_obs; q++) {
-                    const int st = state[q] & 15;
-                    if (st == 3) continue;
-                    if (score[kp[q]] >= x) {
-                        if (st == 2) killed = true;
-                        else blocked = true;
-                    }
-                }
-                const int ns = killed ? 3 : (blocked ? 1 : 2);
-                if (ns == 1) undecided = 1;
-                state[j] = (uint8_t)(1 | (ns << 4));  // verdict parked in the high nibble (nobody else reads it)
-            }
-            const int any = __syncthreads_or(undecided);
-            for (int j = tid; j < P0; j += FP_THREADS)
-                if (state[j] >> 4) state[j] = state[j] >> 4;
-            __syncthreads();
-            if (!any) break;
-        }
-    } else {
-        for (int j = tid; j < P0; j += FP_THREADS) state[j] = 2;
-        __syncthreads();
+    FP_T(s, 4);   // local maxima
+    // the peaks at this thread's positions
+    unsigned long long mine = 0ull;
+    if (o_begin < o_end) {
+        mine = (unsigned long long)bm_window32(pk, o_begin) | ((unsigned long long)bm_window32(pk, o_begin + 32) << 32);
+        const int len = o_end - o_begin;
+        if (len < 64) mine &= (1ull << len) - 1ull;
     }
 
-    // ---- kept peaks, in order (in place: the write index never passes the read index)
-    const int pchunk0 = (P0 + FP_THREADS - 1) / FP_THREADS;
-    const int j0 = min(P0, tid * pchunk0), j1 = min(P0, j0 + pchunk0);
-    uint32_t mk = 0;
-    for (int j = j0; j < j1; j++) mk += (state[j] == 2);
-    uint32_t koff = block_exscan(mk, s, &total);
-    uint16_t keep_local[FP_MAX_LEN / 2 / FP_THREADS + 2];
-    int nk = 0;
-    for (int j = j0; j < j1; j++)
-        if (state[j] == 2) keep_local[nk++] = kp[j];
-    __syncthreads();  // everybody has read its part of the list
-    for (int q = 0; q < nk; q++) kp[koff + q] = keep_local[q];
+    // ---- scipy _select_by_peak_distance ------------------------------------------------------------
+    // A peak stays iff no STAYING peak of higher priority (score, then index) lies closer than m_obs
+    // samples; the greedy highest-first sweep of scipy computes exactly this set, and the set is unique.
+    // A verdict is written only when it is final (removed: a higher KEPT peak is near; kept: every higher
+    // peak near is REMOVED) and the kept / removed sets only grow, so it does not matter how fresh they are
+    // when they are read: no barrier between the rounds, every warp iterates over its own undecided peaks
+    // until none is left (the highest undecided peak of the read can always be decided, so the loops end).
+    unsigned long long kept = mine;
+    if (m_obs > 1) {
+        unsigned long long und = mine;
+        kept = 0ull;
+        if (m_obs <= FP_NEAR + 1) {
+            // the higher-priority neighbours of every peak, once (scores are not looked at again), as a window:
+            // bit b = the peak at position p - FP_NEAR + b; none -> kept at once
+            const uint32_t near_mask = ((1u << (2 * m_obs - 1)) - 1u) << (FP_NEAR - (m_obs - 1)) & ~(1u << FP_NEAR);
+            unsigned long long m = mine;
+            while (m) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int p = o_begin + k;
+                const double x = score[p];
+                uint32_t nb = bm_window32(pk, p - FP_NEAR) & near_mask, h = 0;
+                while (nb) {
+                    const int b = __ffs((int)nb) - 1;
+                    nb &= nb - 1;
+                    const double y = score[p - FP_NEAR + b];
+                    if (b < FP_NEAR ? (y > x) : (y >= x)) h |= 1u << b;   // equal scores: the higher index wins
+                }
+                if (h == 0) {
+                    bm_set(kept_bm, p);
+                    und &= ~(1ull << k);
+                    kept |= 1ull << k;
+                } else {
+                    kp[p >> 1] = (uint16_t)h;
+                }
+            }
+            FP_T(s, 5);   // neighbour sets
+            const volatile uint32_t* vkept = kept_bm;
+            const volatile uint32_t* vrem = rem_bm;
+            while (__any_sync(0xffffffffu, und != 0ull)) {
+                m = und;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int p = o_begin + k;
+                    const uint32_t h = kp[p >> 1];
+                    if (bm_window32(vkept, p - FP_NEAR) & h) {
+                        bm_set(rem_bm, p);
+                        und &= ~(1ull << k);
+                    } else if ((h & ~bm_window32(vrem, p - FP_NEAR)) == 0u) {
+                        bm_set(kept_bm, p);
+                        und &= ~(1ull << k);
+                        kept |= 1ull << k;
+                    }
+                }
+            }
+        } else {
+            const volatile uint32_t* vkept = kept_bm;
+            const volatile uint32_t* vrem = rem_bm;
+            while (__any_sync(0xffffffffu, und != 0ull)) {
+                unsigned long long m = und;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int p = o_begin + k;
+                    const double x = score[p];
+                    bool killed = false, blocked = false;
+                    const int qlo = max(lo, p - m_obs + 1), qhi = min(nc - 1, p + m_obs - 1);
+                    for (int q = qlo; q <= qhi; q++) {
+                        if (q == p || !((pk[(q + 32) >> 5] >> (q & 31)) & 1u)) continue;
+                        if ((vrem[(q + 32) >> 5] >> (q & 31)) & 1u) continue;
+                        const double y = score[q];
+                        if (q < p ? (y > x) : (y >= x)) {  // equal scores: the higher index wins
+                            if ((vkept[(q + 32) >> 5] >> (q & 31)) & 1u) killed = true;
+                            else blocked = true;
+                        }
+                    }
+                    if (killed) {
+                        bm_set(rem_bm, p);
+                        und &= ~(1ull << k);
+                    } else if (!blocked) {
+                        bm_set(kept_bm, p);
+                        und &= ~(1ull << k);
+                        kept |= 1ull << k;
+                    }
+                }
+            }
+        }
+    }
+    FP_T(s, 6);   // suppression rounds (thread 0's warp)
+
+    // ---- kept peaks, in order (the neighbour sets in kp are dead once every thread is past its rounds: the
+    // barriers of the scan lie in between); float range of their scores for select_top_k on the way
+    uint32_t total = 0;
+    uint32_t koff = block_exscan((uint32_t)__popcll(kept), s, &total);
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    while (kept) {
+        const int k = __ffsll((long long)kept) - 1;
+        kept &= kept - 1;
+        kp[koff++] = (uint16_t)(o_begin + k);
+        const uint32_t kf = f32_key((float)score[o_begin + k]);
+        kmin = min(kmin, kf);
+        kmax = max(kmax, kf);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((tid & 31) == 0 && kmax >= kmin) {
+        atomicMin(&s.vmin_key, kmin);
+        atomicMax(&s.vmax_key, kmax);
+    }
     __syncthreads();
     return (int)total;
 }
@@ -401,37 +499,12 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
         return;
     }
     unsigned long long thr_key;
-    bool have_thr = false;
+    bool have_thr = false, all_ties = false;
     {
-        // The k-th largest score in three light passes: float minimum / maximum of the peaks' scores, a 256-bin histogram
-        // over that range (float(x) and the binning are monotone, so a higher bin holds only larger scores), and the
-        // exact ranking of the few members of the bin that holds rank k on their 64-bit keys.  Falls through to the
-        // radix selection below for degenerate score sets.
-        __syncthreads();
-        if (tid < 256) s.hist[tid] = 0;
-        if (tid == 0) {
-            s.vmin_key = 0xffffffffu;
-            s.vmax_key = 0u;
-            s.ncand = 0;
-            s.flag = 0;
-        }
-        __syncthreads();
-        uint32_t kmin = 0xffffffffu, kmax = 0u;
-        for (int i = tid; i < P; i += FP_THREADS) {
-            const uint32_t kf = f32_key((float)score[kp[i]]);
-            kmin = min(kmin, kf);
-            kmax = max(kmax, kf);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-        }
-        if ((tid & 31) == 0) {
-            atomicMin(&s.vmin_key, kmin);
-            atomicMax(&s.vmax_key, kmax);
-        }
-        __syncthreads();
+        // The k-th largest score in two light passes: a 256-bin histogram over the float range of the peaks' scores
+        // (minimum / maximum and the zeroed histogram come from find_kept_peaks; float(x) and the binning are monotone,
+        // so a higher bin holds only larger scores), and the exact ranking of the few members of the bin that holds
+        // rank k on their 64-bit keys.  Falls through to the radix selection below for degenerate score sets.
         const float vmin = f32_unkey(s.vmin_key), vmax = f32_unkey(s.vmax_key);
         const float scale = __fdiv_rn(256.0f, __fsub_rn(vmax, vmin));
         if (vmax > vmin && scale < 1e30f) {   // uniform
@@ -485,11 +558,12 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
                     if (r_in >= g && r_in < g + e) {   // every copy of the threshold key writes the same values
                         s.sel_prefix64 = x;
                         s.sel_k = r_in - g;            // ties ranked above the selected one
-                        s.flag = 1;
+                        s.flag = (r_in - g + 1 == e) ? 2 : 1;   // 2: every copy of the threshold is selected (no tie ranking)
                     }
                 }
                 __syncthreads();
                 have_thr = s.flag != 0;
+                all_ties = s.flag == 2;
             }
         }
     }
@@ -546,10 +620,14 @@ __device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* s
     // mark the selection, then compact in order
     const int pchunk = (P + FP_THREADS - 1) / FP_THREADS;
     const int i0 = min(P, tid * pchunk), i1 = min(P, i0 + pchunk);
-    uint32_t my_ties = 0;
-    for (int i = i0; i < i1; i++) my_ties += ((unsigned long long)__double_as_longlong(score[kp[i]]) == thr_key);
-    uint32_t tot_ties = 0;
-    uint32_t tie_off = block_exscan(my_ties, s, &tot_ties);  // ties before this thread's chunk
+    uint32_t tot_ties = 0, tie_off = 0;
+    if (all_ties) {   // uniform: the usual case (one copy of the threshold score) needs no ranking of the ties
+        tot_ties = ties_needed;
+    } else {
+        uint32_t my_ties = 0;
+        for (int i = i0; i < i1; i++) my_ties += ((unsigned long long)__double_as_longlong(score[kp[i]]) == thr_key);
+        tie_off = block_exscan(my_ties, s, &tot_ties);  // ties before this thread's chunk
+    }
     uint32_t mysel = 0;
     for (int i = i0; i < i1; i++) {
         const unsigned long long kv = (unsigned long long)__double_as_longlong(score[kp[i]]);
@@ -685,14 +763,18 @@ __device__ void consensus_match_rows(const double* __restrict__ query, int Q, co
 
 // CONS = consensus-guided barcode refinement (tRNA configurations, sig_proc.py:257-378, 451-521).
 template <bool CONS>
-__global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_kernel(const __grid_constant__ FpConfig c,
+#ifndef WDX_FP_MIN_CTAS
+#define WDX_FP_MIN_CTAS (1024 / FP_THREADS)
+#endif
+__global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kernel(const __grid_constant__ FpConfig c,
                                                                    const __grid_constant__ FpArgs a) {
     extern __shared__ __align__(16) unsigned char fp_smem[];
     const int cap = a.cap;
     double* score = reinterpret_cast<double*>(fp_smem);                       // [cap]
-    float* sig = reinterpret_cast<float*>(fp_smem + (size_t)cap * 8);         // [cap]
-    uint16_t* kp = reinterpret_cast<uint16_t*>(fp_smem + (size_t)cap * 12);   // [cap/2 + 8] kept peak positions
-    uint8_t* state = fp_smem + (size_t)cap * 12 + ((size_t)(cap / 2 + 8) * 2);  // [cap]
+    float* sig_al = reinterpret_cast<float*>(fp_smem + (size_t)cap * 8);      // [cap + 8]: the slice starts at sig_al + (0..3)
+    uint16_t* kp = reinterpret_cast<uint16_t*>(fp_smem + (size_t)cap * 12 + 32);   // [cap/2 + 8] kept peak positions
+    uint8_t* state = fp_smem + (size_t)cap * 12 + 32 + ((size_t)(cap / 2 + 8) * 2);  // [cap/2 + 8] one byte per kept peak (top-k)
+    uint32_t* bm = reinterpret_cast<uint32_t*>(fp_smem + (size_t)cap * 12 + 32 + ((size_t)(cap / 2 + 8) * 3));  // peak / kept / removed bitmaps
     __shared__ FpScratch s;
     __shared__ int cpts[FP_MAX_EVENTS + 2];
     __shared__ double ev[FP_MAX_EVENTS + 2];   // event means, later normalised
@@ -703,6 +785,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     const int64_t read = blockIdx.x;
     if (read >= a.n) return;
     if (a.retry_status && a.status[read] != a.retry_status) return;
+#ifdef WDX_FP_PROF
+    if (tid == 0) s.t_prev = clock64();
+#endif
     const int nb = c.barcode_num_events;
     double* fpt_out = a.fpt + read * nb;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -740,29 +825,45 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         s.first_nan = n;
         s.vmin_key = 0xffffffffu;
         s.vmax_key = 0u;
+        s.amin = 0xffffffffu;
+        s.amax = 0u;
     }
     __syncthreads();
-    {   // the one HBM read of the slice, coalesced; minimum / maximum on the way
+    // The one HBM read of the slice: 16-byte loads from the aligned address below the slice's first sample (the
+    // staging buffer keeps the same misalignment, so the shared-memory stores are whole vectors too; the up to three
+    // samples in front of and behind the slice that come along are never looked at), minimum / maximum on the way.
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    float* sig = sig_al + mis;
+    {
+        const float4* src4 = reinterpret_cast<const float4*>(src - mis);
+        float4* dst4 = reinterpret_cast<float4*>(sig_al);
+        const int nv = (n + mis + 3) >> 2;
         uint32_t kmin = 0xffffffffu, kmax = 0u;
-        for (int i0 = tid; i0 < n; i0 += 4 * FP_THREADS) {   // four loads in flight per thread before the first use
-            float xv[4];
+        for (int v0 = tid; v0 < nv; v0 += 2 * FP_THREADS) {   // two vectors in flight per thread before the first use
+            float4 xv[2];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * FP_THREADS;
-                xv[u] = (i < n) ? __ldg(src + i) : 0.0f;
+            for (int u = 0; u < 2; u++) {
+                const int v = v0 + u * FP_THREADS;
+                xv[u] = (v < nv) ? __ldg(src4 + v) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * FP_THREADS;
-                if (i >= n) break;
-                const float x = xv[u];
-                sig[i] = x;
-                if (x != x) {
-                    atomicMin(&s.first_nan, i);
-                } else {
-                    const uint32_t kx = f32_key(x);
-                    kmin = min(kmin, kx);
-                    kmax = max(kmax, kx);
+            for (int u = 0; u < 2; u++) {
+                const int v = v0 + u * FP_THREADS;
+                if (v >= nv) break;
+                dst4[v] = xv[u];
+                const float xe[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int i = 4 * v + e - mis;
+                    if (i < 0 || i >= n) continue;
+                    const float x = xe[e];
+                    if (x != x) {
+                        atomicMin(&s.first_nan, i);
+                    } else {
+                        const uint32_t kx = f32_key(x);
+                        kmin = min(kmin, kx);
+                        kmax = max(kmax, kx);
+                    }
                 }
             }
         }
@@ -777,6 +878,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         }
     }
     __syncthreads();
+    FP_T(s, 0);   // load
     // NaN padding inside the slice (a read that ends less than `padding` samples after its adapter):
     // the reference hands the padded minibatch row to detect_results_to_fpt (file_proc.py:418-428), so
     // the slice keeps its full length for the segmentation parameters, medians ignore the NaNs
@@ -810,6 +912,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         med = block_median_f32(n, [&](int i) { return f32_key(sig[i]); }, s);
         mad = block_median_f32(n, [&](int i) { return f32_key(fabsf(__fsub_rn(sig[i], med))); }, s);
     }
+    FP_T(s, 1);   // medians
     float lo, hi;
     if (c.numpy1_promotion) {
         const double tmd = __dmul_rn(c.outlier_thresh_d, (double)mad);
@@ -821,36 +924,88 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         hi = __fadd_rn(med, tm);
     }
     __syncthreads();
-    for (int i = tid; i < n; i += FP_THREADS) {
-        float x = sig[i];
-        x = (x < lo) ? lo : x;  // np.clip = min(max(x, lo), hi)
-        x = (x > hi) ? hi : x;
-        sig[i] = x;
-        if (a.signals_mut) a.signals_mut[read * a.stride + start + i] = x;  // the reference clips its view in place
+    {
+        uint32_t amin = 0xffffffffu, amax = 0u;   // |x| range of the winsorised slice (non-zero values), as bit patterns
+        for (int i = tid; i < n; i += FP_THREADS) {
+            float x = sig[i];
+            x = (x < lo) ? lo : x;  // np.clip = min(max(x, lo), hi)
+            x = (x > hi) ? hi : x;
+            sig[i] = x;
+            if (a.signals_mut) a.signals_mut[read * a.stride + start + i] = x;  // the reference clips its view in place
+            const uint32_t ab = __float_as_uint(x) & 0x7fffffffu;
+            if (ab) {
+                amin = min(amin, ab);
+                amax = max(amax, ab);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&s.amin, amin);
+            atomicMax(&s.amax, amax);
+        }
     }
     __syncthreads();
+    // Sums of these samples in float64 are EXACT — and therefore independent of the order of the additions — when the
+    // binary exponents of the non-zero samples span at most 14: every sample is a multiple of u = 2^(e_lo - 23), every
+    // partial sum of fewer than 2^14 samples is a multiple of u below 2^(e_hi + 15), i.e. an integer of fewer than
+    // 53 bits times u.  (pA signals: 40 .. 200.)  The reference's sequential sums (window means of the t-test, event
+    // means) may then be formed in any order, bit for bit; otherwise they are formed in the reference's order.
+    bool exact_sums;
+    {
+        const int e_lo = (int)(s.amin >> 23), e_hi = (int)(s.amax >> 23);
+        exact_sums = s.amax == 0u || (e_lo >= 1 && e_hi <= 254 && e_hi - e_lo <= 14);
+    }
+    static_assert(FP_MAX_LEN <= (1 << 14), "exact-sum bound");
 
+    FP_T(s, 2);   // clip
     // ---- c_windowed_t_test (_c_segmentation.pyx:124-161), float64, reference order
     const double wd = (double)w;
     if (w == 12) {  // the capped width (every adapter of >= 1265 samples): unrolled, window in registers
-        // Positions r, r+12, r+24, ... share windows: a thread owns `seg_len` consecutive positions of one
-        // residue class r and carries the second window's statistics over as the next position's first.
+        // A lane owns the twelve consecutive window starts 12*blk .. 12*blk + 11: the window slides through its registers
+        // (one new sample per window), and the second window of position pos — the window that starts at pos + 12 — is
+        // the one its right-hand neighbour lane holds at the same step (same operands, same order: bit for bit the
+        // statistics the reference computes twice).  A warp covers 31 blocks of positions per pass; lane 31 only supplies
+        // second windows.  With exact sums the window sum slides too (minus the sample that leaves, plus the one
+        // that enters).
         const double wr = 1.0 / 12.0;
-        const int chain_len = (nc + 11) / 12;
-        const int seg_len = (chain_len + FP_THREADS / 12 - 1) / (FP_THREADS / 12);
-        const int n_seg = (chain_len + seg_len - 1) / seg_len;  // <= FP_THREADS / 12: one item per thread
-        if (tid < 12 * n_seg) {
-            int pos = tid % 12 + 12 * seg_len * (tid / 12);
-            if (pos < nc) {
-                double m1, v1;
-                window_stat_fixed<12>(sig + pos, 12.0, wr, m1, v1);
-                for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
-                    double m2, v2;
-                    window_stat_fixed<12>(sig + pos + 12, 12.0, wr, m2, v2);
-                    score[pos] = ttest_combine(m1, v1, m2, v2);
-                    m1 = m2;
-                    v1 = v2;
+        const int nblk = (nc + 11) / 12;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int g = warp * 31; g < nblk; g += FP_WARPS * 31) {
+            const int s0 = 12 * (g + lane);
+            double x[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) x[i] = (double)sig[min(s0 + i, n - 1)];
+            double msum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) msum = __dadd_rn(msum, x[i]);
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                if (k > 0) {   // window start s0 + k: x[(k + i) % 12], i = 0..11, oldest first
+                    const double xn = (double)sig[min(s0 + k + 11, n - 1)];
+                    if (exact_sums) {
+                        msum = __dadd_rn(__dsub_rn(msum, x[k - 1]), xn);
+                        x[k - 1] = xn;
+                    } else {
+                        x[k - 1] = xn;
+                        msum = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 12; i++) msum = __dadd_rn(msum, x[(k + i) % 12]);
+                    }
                 }
+                const double m = div_small_int(msum, 12.0, wr);
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const double pd = __dsub_rn(x[(k + i) % 12], m);
+                    v = __dadd_rn(v, __dmul_rn(pd, pd));
+                }
+                const double m2 = __shfl_down_sync(0xffffffffu, m, 1), v2 = __shfl_down_sync(0xffffffffu, v, 1);
+                const int pos = s0 + k;
+                if (lane < 31 && pos < nc) score[pos] = ttest_combine(m, v, m2, v2);
             }
         }
     } else {
@@ -879,8 +1034,10 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     __syncthreads();
 
 
+    FP_T(s, 3);   // t-test
     // ---- change points: find_peaks + the num_events highest scores (sig_proc.py:176-198) ------------
-    const int P = find_kept_peaks(score, 0, nc, m_obs, kp, state, s);
+    const int P = find_kept_peaks(score, 0, nc, m_obs, kp, bm, cap, s);
+    FP_T(s, 8);   // rest of find_kept_peaks
     if (P < c.num_events) {  // sig_proc.py:185-186 -> "event segmentation failed"
         fail(FP_FAIL_SEGMENTATION);
         return;
@@ -895,17 +1052,36 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         cpts[c.num_events + 1] = n;
     }
     __syncthreads();
+    FP_T(s, 9);   // top-k
     const int n_seg = c.num_events + 1;
 
-    // ---- c_new_means (_c_segmentation.pyx:41-53): sequential float64 sums ----------
-    for (int q = tid; q < n_seg; q += FP_THREADS) {
-        double sum = 0.0;
-        const int b = cpts[q], e = cpts[q + 1];
-        for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)sig[i]);
-        ev[q] = __ddiv_rn(sum, (double)(e - b));
-    }
+    // ---- c_new_means (_c_segmentation.pyx:41-53): sequential float64 sums; one warp per segment when the sums are exact
+    auto segment_means = [&](const float* base, int nseg) {
+        if (exact_sums) {
+            // four segments per warp and trip, eight lanes each
+            const int lane = tid & 31, warp = tid >> 5, sub = lane >> 3, sl = lane & 7;
+            for (int q0 = warp * 4; q0 < nseg; q0 += FP_WARPS * 4) {
+                const int q = q0 + sub;
+                const int b = (q < nseg) ? cpts[q] : 0, e = (q < nseg) ? cpts[q + 1] : 0;
+                double sum = 0.0;
+                for (int i = b + sl; i < e; i += 8) sum = __dadd_rn(sum, (double)base[i]);
+#pragma unroll
+                for (int o = 4; o; o >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+                if (sl == 0 && q < nseg) ev[q] = __ddiv_rn(sum, (double)(e - b));
+            }
+        } else {
+            for (int q = tid; q < nseg; q += FP_THREADS) {
+                double sum = 0.0;
+                const int b = cpts[q], e = cpts[q + 1];
+                for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)base[i]);
+                ev[q] = __ddiv_rn(sum, (double)(e - b));
+            }
+        }
+    };
+    segment_means(sig, n_seg);
     __syncthreads();
 
+    FP_T(s, 10);  // means
     // ---- mean_normalize (sig_proc.py:99-111) with numpy's summation order -----------
     if (tid < 32) {   // warp 0: the eight accumulators of numpy's block sum live in lanes 0..7
         const double mean = __ddiv_rn(np_pairwise_sum_warp(n_seg, [&](int i) { return ev[i]; }), (double)n_seg);
@@ -921,6 +1097,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
     __syncthreads();
     const double ev_mean = red[0], ev_std = red[1];
 
+    FP_T(s, 11);  // normalize
     // ---- statistics (sig_proc.py:562-567 / 490-498: always over the ADAPTER events) ---------------
     if (a.stats) {
         if (tid < n_seg) dv[tid] = (double)(cpts[tid + 1] - cpts[tid]);
@@ -973,7 +1150,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         // second segmentation on barcode_scores = adapter_scores[sbs:] with the UNCAPPED min_obs_per_base
         // and running_stat_width (sig_proc.py:336-365)
         const int ke = c.cons_seg_events;
-        const int P2 = (nc - sbs >= 3) ? find_kept_peaks(score, sbs, nc, c.min_obs_per_base, kp, state, s) : 0;
+        const int P2 = (nc - sbs >= 3) ? find_kept_peaks(score, sbs, nc, c.min_obs_per_base, kp, bm, cap, s) : 0;
         if (P2 < ke) {
             fail(FP_FAIL_SEGMENTATION);
             return;
@@ -984,12 +1161,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
             cpts[ke + 1] = n - sbs;   // scores.size + 2 * running_stat_width = (nc - sbs) + 2 w
         }
         __syncthreads();
-        for (int q = tid; q < ke + 1; q += FP_THREADS) {  // compute_base_means(raw_signal[sbs:], cpts) (:368)
-            double sum = 0.0;
-            const int b = cpts[q], e = cpts[q + 1];
-            for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)sig[sbs + i]);
-            ev[q] = __ddiv_rn(sum, (double)(e - b));
-        }
+        segment_means(sig + sbs, ke + 1);  // compute_base_means(raw_signal[sbs:], cpts) (:368)
         __syncthreads();
         n_out_seg = ke + 1;
         if (a.cons && tid == 0) {
@@ -1023,6 +1195,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1024 / FP_THREADS) fingerprint_ker
         fpt_out[q] = v;
         if (a.dwell) a.dwell[read * nb + q] = dw;
     }
+    FP_T(s, 12);  // stats + output
     if (tid == 0) a.status[read] = FP_OK;
 }
 
@@ -1043,7 +1216,7 @@ __global__ void max_slice_kernel(const int64_t* __restrict__ a0, const int64_t* 
 }
 
 inline size_t fingerprint_smem_bytes(int cap) {
-    return (size_t)cap * 12 + (size_t)(cap / 2 + 8) * 2 + (size_t)cap;
+    return (size_t)cap * 12 + 32 + (size_t)(cap / 2 + 8) * 3 + (size_t)FP_BM_WORDS(cap) * 12;
 }
 
 }  // namespace wdx

@@ -470,4 +470,15 @@ int wdx_fp_last_kernel_ms(wdx_fp* f, double* ms, int* launches) {
     return WDX_OK;
 }
 
+#ifdef WDX_FP_PROF
+// experiments only: cycles per phase summed over all CTAs since the last reset
+int wdx_fp_prof_dump(unsigned long long* out32, int reset) {
+    if (out32) CUDA_TRY(cudaMemcpyFromSymbol(out32, wdx::g_fp_prof, 32 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long z[32] = {};
+        CUDA_TRY(cudaMemcpyToSymbol(wdx::g_fp_prof, z, sizeof z));
+    }
+    return WDX_OK;
+}
+#endif
 }  // extern "C"

@@ -49,7 +49,7 @@ def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
         fp.extract_raw(sd, n, sig.shape[1], a0d, a1d, fpt, st, stream=stream)
         torch.cuda.synchronize()
         L.wdx_fp_prof_dump(buf, 0)
-        names = ["load", "medians", "clip", "ttest", "localmax", "nbr_sets", "rounds", "-", "scan+list", "topk", "means", "normalize", "out"]
+        names = ["load", "medians", "clip", "ttest", "localmax", "nbr_sets", "rounds", "-", "scan+list", "topk", "means", "normalize", "out", "n_mean", "n_ss", "n_sqrt"]
         ph = {nm: round(buf[i] / n) for i, nm in enumerate(names) if nm != "-"}
         ph["sum"] = sum(ph.values())
         print(json.dumps({"cycles_per_read": ph}), flush=True)

@@ -54,6 +54,46 @@ def test_synthetic_signals_match_oracle(fp, seed, short):
     _same(b, status, fpt, dwell, stats)
 
 
+@pytest.mark.parametrize("mobs,width_stat,events", [(1, 12, 110), (3, 12, 110), (8, 12, 60), (9, 18, 60), (16, 12, 40),
+                                                     (20, 12, 30), (6, 7, 110)])
+def test_suppression_distance_and_window_width_paths(mobs, width_stat, events):
+    """Every variant of the distance suppression (none, 15-bit neighbour sets up to 8, 31-bit windows up to 16, the
+    per-position loop beyond) and both t-test forms (lane-sliding width 12, generic width) against the oracle."""
+    from warpdemux_b200.sig_proc import Fingerprinter, FingerprintConfig
+
+    cfg = dict(min_obs_per_base=mobs, running_stat_width=width_stat, num_events=events)
+    sig, a0, a1 = synth_adapter_signals(96, seed=40 + mobs, width=9000, short_frac=0.2)
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1, **cfg)
+    assert (status == 0).sum() > 30
+    f = Fingerprinter(FingerprintConfig(**cfg), device=0)
+    try:
+        _same(f.extract(sig, a0, a1), status, fpt, dwell, stats)
+    finally:
+        f.close()
+
+
+def test_samples_whose_sums_are_not_exact(fp):
+    """Signals whose exponents span more than 14 binades (tiny values next to pA-sized ones, zeros, a sign change):
+    float64 sums depend on the order again and the kernel must fall back to the reference's sequential sums."""
+    sig, a0, a1 = synth_adapter_signals(64, seed=51, width=9000)
+    rng = np.random.default_rng(5)
+    sig = sig.copy()
+    for r in range(64):
+        n = int((~np.isnan(sig[r])).sum())
+        kind = r % 4
+        if kind == 0:      # tiny offsets: 1e-7 .. 1e-3 between normal samples
+            idx = rng.integers(0, n, size=n // 7)
+            sig[r, idx] = (10.0 ** rng.uniform(-7, -3, size=idx.size)).astype(np.float32)
+        elif kind == 1:    # centred signal: values of both signs, many near zero
+            sig[r, :n] = (sig[r, :n] - np.float32(80.0)) * np.float32(1e-3)
+        elif kind == 2:    # exact zeros and negative zeros sprinkled in
+            idx = rng.integers(0, n, size=n // 9)
+            sig[r, idx] = np.where(rng.random(idx.size) < 0.5, np.float32(0.0), np.float32(-0.0))
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1)
+    assert (status == 0).sum() > 30
+    _same(fp.extract(sig, a0, a1), status, fpt, dwell, stats)
+
+
 def test_sig_len_detect_ok_and_row_end(fp):
     sig, a0, a1 = synth_adapter_signals(40, seed=13, width=8000)
     lens = (~np.isnan(sig)).sum(axis=1).astype(np.int32)

@@ -57,7 +57,7 @@ struct FpScratch {
     uint32_t vmin_key, vmax_key;      // order keys of the slice minimum / maximum
     int sel_bin;                       // linear-bin median: bin holding the wanted rank
     uint32_t sel_below, sel_count;     //   elements in lower bins / in that bin
-    uint32_t ncand;                    //   gathered candidates
+    uint32_t ncand, ncand2;            //   gathered candidates (first / second median of a pair)
     uint32_t amin, amax;               // smallest non-zero / largest |x| (float bit patterns) of the winsorised slice
     long long t_prev;                  // WDX_FP_PROF builds: clock of the previous phase mark (thread 0)
     uint32_t key_lo, key_hi;

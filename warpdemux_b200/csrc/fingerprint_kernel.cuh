@@ -84,10 +84,12 @@ struct FpArgs {
 // holds rank (n-1)/2 is located by a scan of the histogram, its few members are
 // gathered and ranked exactly on their order keys.  Falls back to the radix
 // selection when the bin is crowded (degenerate signals).
-//   hist: FP_MED_BINS uint32,  cand: FP_MED_CAND uint32  (scratch in shared memory)
+//   cand: FP_MED_CAND uint32 of scratch in shared memory
+//   hist: FP_MED_BINS uint32 ZEROED by the caller, *ncand zeroed too (both behind a barrier; two medians in a row
+//   use two histograms, so neither starts with a clearing pass and its barriers)
 template <typename VAL>
 __device__ float block_median_f32_linear(int n, VAL val, float vmin, float vmax, uint32_t* hist, uint32_t* cand,
-                                         FpScratch& s) {
+                                         uint32_t* ncand, FpScratch& s) {
     if (!(vmax > vmin)) return vmin;  // all values equal
     const float scale = __fdiv_rn((float)FP_MED_BINS, __fsub_rn(vmax, vmin));
     auto key_of = [&](int i) { return f32_key(val(i)); };
@@ -95,10 +97,6 @@ __device__ float block_median_f32_linear(int n, VAL val, float vmin, float vmax,
     auto bin_of = [&](float x) { return min(FP_MED_BINS - 1, (int)__fmul_rn(__fsub_rn(x, vmin), scale)); };
     const int tid = threadIdx.x;
     const uint32_t k_lo = (uint32_t)((n - 1) / 2);
-    __syncthreads();
-    for (int b = tid; b < FP_MED_BINS; b += FP_THREADS) hist[b] = 0;
-    if (tid == 0) s.ncand = 0;
-    __syncthreads();
     for (int i = tid; i < n; i += FP_THREADS) atomicAdd(&hist[bin_of(val(i))], 1u);
     __syncthreads();
     {   // thread t owns bins [t*B, (t+1)*B)
@@ -129,7 +127,7 @@ __device__ float block_median_f32_linear(int n, VAL val, float vmin, float vmax,
     if (m > (uint32_t)FP_MED_CAND) return block_median_f32(n, key_of, s);  // uniform decision
     for (int i = tid; i < n; i += FP_THREADS) {
         const float x = val(i);
-        if (bin_of(x) == sel_bin) cand[atomicAdd(&s.ncand, 1u)] = f32_key(x);
+        if (bin_of(x) == sel_bin) cand[atomicAdd(ncand, 1u)] = f32_key(x);
     }
     __syncthreads();
     const uint32_t r = k_lo - below;  // wanted rank inside the bin
@@ -301,14 +299,10 @@ __device__ __forceinline__ uint32_t bm_window32(const W* bm, int pos) {
 }
 __device__ __forceinline__ void bm_set(uint32_t* bm, int pos) { atomicOr(&bm[(pos + 32) >> 5], 1u << (pos & 31)); }
 
-__device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint32_t* bm, int cap,
-                               FpScratch& s) {
+// Clears the bitmaps and select_top_k's scratch; a barrier must lie between this and find_kept_peaks.
+__device__ __forceinline__ void peaks_scratch_clear(uint32_t* bm, int cap, FpScratch& s) {
     const int tid = threadIdx.x;
-    const int bw = FP_BM_WORDS(cap);
-    uint32_t* pk = bm;
-    uint32_t* kept_bm = bm + bw;
-    uint32_t* rem_bm = bm + 2 * bw;
-    for (int i = tid; i < 3 * bw; i += FP_THREADS) bm[i] = 0u;
+    for (int i = tid; i < 3 * FP_BM_WORDS(cap); i += FP_THREADS) bm[i] = 0u;
     if (tid < 256) s.hist[tid] = 0;
     if (tid == 0) {
         s.vmin_key = 0xffffffffu;
@@ -316,7 +310,15 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
         s.ncand = 0;
         s.flag = 0;
     }
-    __syncthreads();
+}
+
+__device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint32_t* bm, int cap,
+                               FpScratch& s) {
+    const int tid = threadIdx.x;
+    const int bw = FP_BM_WORDS(cap);
+    uint32_t* pk = bm;
+    uint32_t* kept_bm = bm + bw;
+    uint32_t* rem_bm = bm + 2 * bw;
     // scipy _local_maxima_1d (strict maxima, plateaus -> midpoint): thread t walks the contiguous positions
     // [lo + t*chunk, lo + (t+1)*chunk) once (one load per position) and marks the midpoint of every maximum
     // that STARTS there.
@@ -397,6 +399,42 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
                         bm_set(rem_bm, p);
                         und &= ~(1ull << k);
                     } else if ((h & ~bm_window32(vrem, p - FP_NEAR)) == 0u) {
+                        bm_set(kept_bm, p);
+                        und &= ~(1ull << k);
+                        kept |= 1ull << k;
+                    }
+                }
+            }
+        } else if (m_obs <= 16) {
+            // wider neighbourhoods (tRNA: 9): the same rounds on 31-bit windows (bit b = position p - 15 + b); the sets of
+            // higher neighbours do not fit the 16-bit slots, so a visit compares the scores of the neighbours that are
+            // not removed yet again
+            const volatile uint32_t* vkept = kept_bm;
+            const volatile uint32_t* vrem = rem_bm;
+            const uint32_t near_mask = (uint32_t)(((1ull << (2 * m_obs - 1)) - 1ull) << (15 - (m_obs - 1))) & ~(1u << 15);
+            while (__any_sync(0xffffffffu, und != 0ull)) {
+                unsigned long long m = und;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int p = o_begin + k;
+                    const double x = score[p];
+                    uint32_t nb = bm_window32(pk, p - 15) & near_mask & ~bm_window32(vrem, p - 15);
+                    const uint32_t kw = bm_window32(vkept, p - 15);
+                    bool killed = false, blocked = false;
+                    while (nb) {
+                        const int b = __ffs((int)nb) - 1;
+                        nb &= nb - 1;
+                        const double y = score[p - 15 + b];
+                        if (b < 15 ? (y > x) : (y >= x)) {  // equal scores: the higher index wins
+                            if ((kw >> b) & 1u) killed = true;
+                            else blocked = true;
+                        }
+                    }
+                    if (killed) {
+                        bm_set(rem_bm, p);
+                        und &= ~(1ull << k);
+                    } else if (!blocked) {
                         bm_set(kept_bm, p);
                         und &= ~(1ull << k);
                         kept |= 1ull << k;
@@ -827,7 +865,14 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         s.vmax_key = 0u;
         s.amin = 0xffffffffu;
         s.amax = 0u;
+        s.ncand = 0;
+        s.ncand2 = 0;
     }
+    // the two median histograms (the score array is idle until the t-test) are cleared while the slice is on its way
+    uint32_t* med_hist = reinterpret_cast<uint32_t*>(score);
+    const bool lin_fits = cap >= (2 * FP_MED_BINS + FP_MED_CAND) / 2;
+    if (lin_fits)
+        for (int b = tid; b < 2 * FP_MED_BINS; b += FP_THREADS) med_hist[b] = 0u;
     __syncthreads();
     // The one HBM read of the slice: 16-byte loads from the aligned address below the slice's first sample (the
     // staging buffer keeps the same misalignment, so the shared-memory stores are whole vectors too; the up to three
@@ -898,16 +943,15 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
     }
 
     // ---- winsorise at med +- thresh * MAD, float32 (sig_proc.py:421-431) --------
-    uint32_t* med_hist = reinterpret_cast<uint32_t*>(score);  // the score array is idle until the t-test
-    uint32_t* med_cand = med_hist + FP_MED_BINS;
-    const bool lin = !trimmed && cap >= (FP_MED_BINS + FP_MED_CAND) / 2;  // min/max cover exactly the slice; scratch fits
+    uint32_t* med_cand = med_hist + 2 * FP_MED_BINS;
+    const bool lin = !trimmed && lin_fits;  // min/max cover exactly the slice; scratch fits
     float med, mad;
     if (lin) {
         const float vmin = f32_unkey(s.vmin_key), vmax = f32_unkey(s.vmax_key);
-        med = block_median_f32_linear(n, [&](int i) { return sig[i]; }, vmin, vmax, med_hist, med_cand, s);
+        med = block_median_f32_linear(n, [&](int i) { return sig[i]; }, vmin, vmax, med_hist, med_cand, &s.ncand, s);
         const float ymax = fmaxf(__fsub_rn(vmax, med), __fsub_rn(med, vmin));  // >= every |x - med| (rounding is monotone)
-        mad = block_median_f32_linear(n, [&](int i) { return fabsf(__fsub_rn(sig[i], med)); }, 0.0f, ymax, med_hist,
-                                      med_cand, s);
+        mad = block_median_f32_linear(n, [&](int i) { return fabsf(__fsub_rn(sig[i], med)); }, 0.0f, ymax,
+                                      med_hist + FP_MED_BINS, med_cand, &s.ncand2, s);
     } else {
         med = block_median_f32(n, [&](int i) { return f32_key(sig[i]); }, s);
         mad = block_median_f32(n, [&](int i) { return f32_key(fabsf(__fsub_rn(sig[i], med))); }, s);
@@ -963,6 +1007,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
 
     FP_T(s, 2);   // clip
     // ---- c_windowed_t_test (_c_segmentation.pyx:124-161), float64, reference order
+    peaks_scratch_clear(bm, cap, s);   // for find_kept_peaks behind the t-test's barrier (the median scratch is done with)
     const double wd = (double)w;
     if (w == 12) {  // the capped width (every adapter of >= 1265 samples): unrolled, window in registers
         // A lane owns the twelve consecutive window starts 12*blk .. 12*blk + 11: the window slides through its registers
@@ -1085,14 +1130,17 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
     // ---- mean_normalize (sig_proc.py:99-111) with numpy's summation order -----------
     if (tid < 32) {   // warp 0: the eight accumulators of numpy's block sum live in lanes 0..7
         const double mean = __ddiv_rn(np_pairwise_sum_warp(n_seg, [&](int i) { return ev[i]; }), (double)n_seg);
+        FP_T(s, 13);
         const double ss = np_pairwise_sum_warp(n_seg, [&](int i) {
             const double d = __dsub_rn(ev[i], mean);
             return __dmul_rn(d, d);
         });
+        FP_T(s, 14);
         if (tid == 0) {
             red[0] = mean;
             red[1] = __dsqrt_rn(__ddiv_rn(ss, (double)n_seg));
         }
+        FP_T(s, 15);
     }
     __syncthreads();
     const double ev_mean = red[0], ev_std = red[1];
@@ -1146,6 +1194,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         __syncthreads();
         const int q_start = match[0], q_end = match[1];
         const int sbs = cpts[q_end];  // sig_barcode_start = sum(adapter_dwell_times[:q_end]) (sig_proc.py:334)
+        peaks_scratch_clear(bm, cap, s);
         __syncthreads();              // cpts / ev are rewritten below
         // second segmentation on barcode_scores = adapter_scores[sbs:] with the UNCAPPED min_obs_per_base
         // and running_stat_width (sig_proc.py:336-365)

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 python -m warpdemux_b200.build > /dev/null
 L=warpdemux_b200/lib
 mkdir -p $L/var
-rm -f $L/var/*
+rm -f $L/var/*.so $L/var/*.o
 for v in "512 2 16000" "256 4 16000" "256 3 16000" "128 8 8000" "128 6 8000"; do
   set -- $v
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -ccbin /usr/bin/g++ \

@@ -15,7 +15,21 @@ from warpdemux_b200.sig_proc import Fingerprinter  # noqa: E402
 
 
 def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
-    sig, a0, a1 = synth_adapter_signals(n_base, seed=21, width=9000)
+    okd = None
+    if os.environ.get("FP_REAL"):   # the 4000 real reads (rows of bench.chain_dataset) with the reference's own boundaries
+        import bench
+        ds = bench.chain_dataset()
+        with np.load(os.path.join(ROOT, "tests", "golden", "real4000_rna004_WDX4.npz")) as z:
+            bounds, success = z["bounds"], z["success"]
+        sig = ds["sig"]
+        a0, a1 = bounds[:, 0].astype(np.int64).copy(), bounds[:, 1].astype(np.int64).copy()
+        a0[success == 0] = 0
+        a1[success == 0] = 0
+        n_base, reps = sig.shape[0], max(1, reps // 8)
+        okd = torch.from_numpy(np.tile(success.astype(np.uint8), reps)).cuda()
+        os.environ.setdefault("FP_MAX_SLICE", "6720")
+    else:
+        sig, a0, a1 = synth_adapter_signals(n_base, seed=21, width=9000)
     short = int(os.environ.get("FP_SHORT", "0"))
     if short:   # adapters cut to `short` samples (CTA-shape experiments: more CTAs fit an SM with smaller slices)
         a1 = np.minimum(a1, a0 + short)
@@ -34,7 +48,7 @@ def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
     stream = torch.cuda.current_stream().cuda_stream
     best = 1e30
     for r in range(5):
-        fp.extract_raw(sd, n, sig.shape[1], a0d, a1d, fpt, st, stream=stream)
+        fp.extract_raw(sd, n, sig.shape[1], a0d, a1d, fpt, st, detect_ok=okd, stream=stream)
         torch.cuda.synchronize()
         ms, nl = fp.last_kernel_ms()
         if r:
@@ -46,7 +60,7 @@ def main(n_base=512, reps=int(os.environ.get("FP_REPS", "64"))):
         import ctypes as C
         buf = (C.c_uint64 * 32)()
         L.wdx_fp_prof_dump(None, 1)
-        fp.extract_raw(sd, n, sig.shape[1], a0d, a1d, fpt, st, stream=stream)
+        fp.extract_raw(sd, n, sig.shape[1], a0d, a1d, fpt, st, detect_ok=okd, stream=stream)
         torch.cuda.synchronize()
         L.wdx_fp_prof_dump(buf, 0)
         names = ["load", "medians", "clip", "ttest", "localmax", "nbr_sets", "rounds", "-", "scan+list", "topk", "means", "normalize", "out", "n_mean", "n_ss", "n_sqrt"]

@@ -247,31 +247,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
 
     uint32_t p_item = 0, c_item = 0, done_phase = 0;  // ring positions of the producer / MMA thread, phase of layer_done
 
-    for (int64_t read = blockIdx.x; read < a.n; read += gridDim.x) {
-        // ---- input row, conv1 -> activations (fp16 hi + lo) ------------------------------------------
-        const float* xr = a.x + read * d.T;
-        for (int j0 = tid; j0 < 3 * T1 + 8; j0 += 4 * TC_THREADS) {   // four loads in flight per thread before the first use
+    // input row of a read into xs (zero padded), by `nthr` threads of which this one is number `t0`
+    auto load_xs = [&](int64_t rd, int t0, int nthr) {
+        const float* xr = a.x + rd * d.T;
+        for (int j0 = t0; j0 < 3 * T1 + 8; j0 += 4 * nthr) {   // four loads in flight per thread before the first use
             float xv[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int i = j0 + u * TC_THREADS - CNN_P;
+                const int i = j0 + u * nthr - CNN_P;
                 xv[u] = (i >= 0 && i < d.T) ? __ldg(xr + i) : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int j = j0 + u * TC_THREADS;
+                const int j = j0 + u * nthr;
                 if (j < 3 * T1 + 8) xs[j] = xv[u];
             }
         }
+    };
+    // Weight ring, producer side (lane 0 of warp 1): item `it` of a read = tap it % 7 of layer it / 7, item 14 = the
+    // ConvTranspose operand.  The producer runs three items AHEAD of the layer it is in — the first taps of a layer are
+    // requested while the previous layer's last MMAs and its epilogue still run (for layer 0: under the input load and
+    // conv1) — so no layer starts by waiting for its weights.
+    auto issue_item = [&](int it) {
+        const uint32_t s = p_item % TC_STAGES, ph = (p_item / TC_STAGES) & 1;
+        tc_mbar_wait(&empty[s], ph ^ 1);
+        if (it < 2 * CNN_K) {
+            tc_mbar_expect_tx(&full[s], TC_W_TAP);
+            tc_bulk_load(W + s * TC_W_TAP, a.wtc + (size_t)it * (TC_W_TAP / 2), TC_W_TAP, &full[s]);
+        } else {
+            tc_mbar_expect_tx(&full[s], TC_CT_BYTES);
+            tc_bulk_load(W + s * TC_W_TAP, a.wct, TC_CT_BYTES, &full[s]);
+        }
+        p_item++;
+    };
+
+    if ((int64_t)blockIdx.x < a.n) load_xs(blockIdx.x, tid, TC_THREADS);
+    for (int64_t read = blockIdx.x; read < a.n; read += gridDim.x) {
+        // ---- conv1 -> activations (fp16 hi + lo); the input row is in xs already (prefetched under the previous read's MMAs).
+        // The padding rows [0,3) and [T1+3, ROWS) of the activation buffer stay zero from the one-time clearing: conv1
+        // writes rows 3 .. T1+2, the epilogues write zeros to the rows beyond T1 of the tiles they cover.
         if (tid == 0) *range_flag = 0;
-        // padding rows (the previous read's float32 h3 aliased this buffer): rows [0,3) and [T1+3, TC_ROWS)
-        {
-            const int pad_rows = CNN_P + (TC_ROWS - (T1 + CNN_P));
-            for (int i = tid; i < pad_rows * 16; i += TC_THREADS) {
-                const int col = i / pad_rows, pr = i % pad_rows;
-                const int row = pr < CNN_P ? pr : (T1 + CNN_P + (pr - CNN_P));
-                *reinterpret_cast<uint4*>(A + (col >> 3) * TC_A_SPLIT + (col & 7) * TC_LBO + row * 16) = make_uint4(0, 0, 0, 0);
-            }
+        if (warp == 1 && lane == 0) {
+            issue_item(0);
+            issue_item(1);
+            issue_item(2);
         }
         __syncthreads();
         bool range = false;
@@ -306,17 +325,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         __syncthreads();
 
         for (int layer = 0; layer < 2; layer++) {
-            if (warp == 1) {  // ---- weight producer ----
+            if (warp == 1) {  // ---- weight producer: the rest of this layer's taps and the first three items of what follows ----
                 if (lane == 0) {
-                    for (int tap = 0; tap < CNN_K; tap++, p_item++) {
-                        const uint32_t s = p_item % TC_STAGES, ph = (p_item / TC_STAGES) & 1;
-                        tc_mbar_wait(&empty[s], ph ^ 1);
-                        tc_mbar_expect_tx(&full[s], TC_W_TAP);
-                        tc_bulk_load(W + s * TC_W_TAP, a.wtc + (size_t)(layer * CNN_K + tap) * (TC_W_TAP / 2), TC_W_TAP, &full[s]);
-                    }
+                    const int last = min(layer * CNN_K + CNN_K + 2, 2 * CNN_K);
+                    for (int it = layer * CNN_K + 3; it <= last; it++) issue_item(it);
                 }
                 __syncwarp();
-            } else if (warp == 0) {  // ---- MMA issuer: the warp walks the loops, one elected lane issues ----
+            } else if (layer == 1 && warp >= 2) {  // ---- the next read's input row, under this layer's MMAs (xs is idle since conv1) ----
+                if (read + gridDim.x < a.n) load_xs(read + gridDim.x, tid - 64, TC_THREADS - 64);
+            }
+            if (warp == 0) {  // ---- MMA issuer: the warp walks the loops, one elected lane issues ----
                 tc_fence_after();
                 // descriptors advance in 16-byte units inside the 14-bit start-address field (no carry: smem < 256 KB)
                 const uint64_t a_desc0 = tc_desc(a_base, TC_LBO, 128);
@@ -384,16 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         //   out[c][3q - 3 + r] = b[c] + sum_{j = 0..2} sum_ci h[q - j][ci] * w[ci][c][r + 3j]      (tap r + 3j <= 6)
         // = three row-shifted GEMMs  D[q][2r + c] += A[rows q - j] * B_j  with K = 64, N = 16 (6 columns used): the operand of
         // shift j is the activation buffer with the descriptor's start moved back j rows, exactly like a convolution tap.
-        if (warp == 1) {
-            if (lane == 0) {
-                const uint32_t s = p_item % TC_STAGES, ph = (p_item / TC_STAGES) & 1;
-                tc_mbar_wait(&empty[s], ph ^ 1);
-                tc_mbar_expect_tx(&full[s], TC_CT_BYTES);
-                tc_bulk_load(W + s * TC_W_TAP, a.wct, TC_CT_BYTES, &full[s]);
-                p_item++;
-            }
-            __syncwarp();
-        } else if (warp == 0) {
+        if (warp == 0) {   // (the operand B blocks were requested by the producer during layer 1: ring item 14)
             tc_fence_after();
             const uint32_t s = c_item % TC_STAGES, ph = (c_item / TC_STAGES) & 1;
             tc_mbar_wait(&full[s], ph);

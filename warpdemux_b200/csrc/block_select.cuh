@@ -37,12 +37,27 @@ __device__ unsigned long long g_fp_prof[32];
     do {                                                                              \
         if (threadIdx.x == 0) {                                                       \
             const long long t__ = clock64();                                          \
-            atomicAdd(&g_fp_prof[i_], (unsigned long long)(t__ - (s_).t_prev));       \
+            (s_).prof[i_] += (unsigned long long)(t__ - (s_).t_prev);                 \
             (s_).t_prev = t__;                                                        \
         }                                                                             \
     } while (0)
+#define FP_T_BEGIN(s_)                                                                \
+    do {                                                                              \
+        if (threadIdx.x == 0) {                                                       \
+            for (int i__ = 0; i__ < 32; i__++) (s_).prof[i__] = 0;                    \
+            (s_).t_prev = clock64();                                                  \
+        }                                                                             \
+    } while (0)
+#define FP_T_END(s_)                                                                  \
+    do {                                                                              \
+        if (threadIdx.x == 0)                                                         \
+            for (int i__ = 0; i__ < 32; i__++)                                        \
+                if ((s_).prof[i__]) atomicAdd(&g_fp_prof[i__], (s_).prof[i__]);       \
+    } while (0)
 #else
 #define FP_T(s_, i_) do { } while (0)
+#define FP_T_BEGIN(s_) do { } while (0)
+#define FP_T_END(s_) do { } while (0)
 #endif
 
 struct FpScratch {
@@ -59,7 +74,10 @@ struct FpScratch {
     uint32_t sel_below, sel_count;     //   elements in lower bins / in that bin
     uint32_t ncand, ncand2;            //   gathered candidates (first / second median of a pair)
     uint32_t amin, amax;               // smallest non-zero / largest |x| (float bit patterns) of the winsorised slice
-    long long t_prev;                  // WDX_FP_PROF builds: clock of the previous phase mark (thread 0)
+#ifdef WDX_FP_PROF
+    long long t_prev;                  // clock of the previous phase mark (thread 0)
+    unsigned long long prof[32];       // cycles per phase of this read
+#endif
     uint32_t key_lo, key_hi;
 };
 

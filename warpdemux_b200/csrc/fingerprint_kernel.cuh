@@ -312,8 +312,20 @@ __device__ __forceinline__ void peaks_scratch_clear(uint32_t* bm, int cap, FpScr
     }
 }
 
-__device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint32_t* bm, int cap,
-                               FpScratch& s) {
+constexpr int FP_TOPK_CAND = FP_MAX_EVENTS + 2;   // keys of the threshold's histogram bin that can be ranked exactly
+__device__ void select_top_k(const double* score, const uint16_t* kp, uint8_t* state, int P, int k_events, int add, int* out,
+                             FpScratch& s, unsigned long long* cand);
+
+// 256 logarithmic bins (1/8 octave, 2^-12 .. 2^20) of a non-negative score: monotone, needs no minimum / maximum
+__device__ __forceinline__ int topk_bin(double x) {
+    const int b = (int)(__float_as_uint((float)x) >> 20) - ((127 - 12) << 3);
+    return min(255, max(0, b));
+}
+
+// find_peaks + the k_events highest-scoring kept peaks (sig_proc.py:176-198) in one go.  Returns the number P of kept
+// peaks; if P >= k_events, out[0..k_events) = position + add of the selected peaks, in order.
+__device__ int kept_peaks_select(const double* score, int lo, int nc, int m_obs, uint16_t* kp, uint32_t* bm, int cap,
+                                 int k_events, int add, int* out, uint8_t* state, unsigned long long* cand, FpScratch& s) {
     const int tid = threadIdx.x;
     const int bw = FP_BM_WORDS(cap);
     uint32_t* pk = bm;
@@ -388,7 +400,8 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
             FP_T(s, 5);   // neighbour sets
             const volatile uint32_t* vkept = kept_bm;
             const volatile uint32_t* vrem = rem_bm;
-            while (__any_sync(0xffffffffu, und != 0ull)) {
+            for (int spin = 0; __any_sync(0xffffffffu, und != 0ull); spin++) {
+                if (spin > (1 << 22)) __trap();   // a protocol bug must end as a launch failure, never as a hung GPU
                 m = und;
                 while (m) {
                     const int k = __ffsll((long long)m) - 1;
@@ -412,7 +425,8 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
             const volatile uint32_t* vkept = kept_bm;
             const volatile uint32_t* vrem = rem_bm;
             const uint32_t near_mask = (uint32_t)(((1ull << (2 * m_obs - 1)) - 1ull) << (15 - (m_obs - 1))) & ~(1u << 15);
-            while (__any_sync(0xffffffffu, und != 0ull)) {
+            for (int spin = 0; __any_sync(0xffffffffu, und != 0ull); spin++) {
+                if (spin > (1 << 22)) __trap();   // a protocol bug must end as a launch failure, never as a hung GPU
                 unsigned long long m = und;
                 while (m) {
                     const int k = __ffsll((long long)m) - 1;
@@ -444,7 +458,8 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
         } else {
             const volatile uint32_t* vkept = kept_bm;
             const volatile uint32_t* vrem = rem_bm;
-            while (__any_sync(0xffffffffu, und != 0ull)) {
+            for (int spin = 0; __any_sync(0xffffffffu, und != 0ull); spin++) {
+                if (spin > (1 << 22)) __trap();   // a protocol bug must end as a launch failure, never as a hung GPU
                 unsigned long long m = und;
                 while (m) {
                     const int k = __ffsll((long long)m) - 1;
@@ -476,8 +491,108 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
     }
     FP_T(s, 6);   // suppression rounds (thread 0's warp)
 
-    // ---- kept peaks, in order (the neighbour sets in kp are dead once every thread is past its rounds: the
-    // barriers of the scan lie in between); float range of their scores for select_top_k on the way
+    // ---- the k_events highest-scoring kept peaks -------------------------------------------------------
+    // Usual case, without ever listing the kept peaks: every thread adds ITS kept peaks to a histogram over the
+    // logarithmic bins, warp 0 finds the bin that holds rank k from the top (and the number of kept peaks), the few
+    // members of that bin are ranked exactly on their 64-bit keys, and the peaks at or above the threshold key are
+    // written in position order (one scan).  A crowded threshold bin, or a threshold score of which only some copies
+    // are selected (ties -> the higher indices), takes the list-based selection below.
+    {
+        unsigned long long kk = kept;
+        while (kk) {
+            const int k = __ffsll((long long)kk) - 1;
+            kk &= kk - 1;
+            atomicAdd(&s.hist[topk_bin(score[o_begin + k])], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {  // warp 0 scans the 256 bins from the top, 8 per lane (lane 0 = bins 255..248)
+        const uint32_t k = (uint32_t)k_events - 1;  // 0-based rank from the top
+        uint32_t cnt[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            cnt[q] = s.hist[255 - (tid * 8 + q)];
+            sum += cnt[q];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += t;
+        }
+        if (tid == 31) s.n_kept = (int)inc;
+        uint32_t run = inc - sum;  // peaks in higher bins
+        if (k >= run && k < inc) {  // at most one lane
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (k >= run && k < run + cnt[q]) {
+                    s.sel_bin = 255 - (tid * 8 + q);
+                    s.sel_below = k - run;     // rank from the top inside the bin
+                    s.sel_count = cnt[q];
+                }
+                run += cnt[q];
+            }
+        }
+    }
+    __syncthreads();
+    const int P = s.n_kept;
+    if (P < k_events) return P;   // uniform
+    bool fast = s.sel_count <= (uint32_t)FP_TOPK_CAND;
+    if (fast) {
+        const int sel_bin = s.sel_bin;
+        const uint32_t r_in = s.sel_below, m = s.sel_count;
+        unsigned long long kk = kept;
+        while (kk) {
+            const int k = __ffsll((long long)kk) - 1;
+            kk &= kk - 1;
+            const double x = score[o_begin + k];
+            if (topk_bin(x) == sel_bin) cand[atomicAdd(&s.ncand, 1u)] = (unsigned long long)__double_as_longlong(x);
+        }
+        __syncthreads();
+        for (uint32_t t = tid; t < m; t += FP_THREADS) {
+            const unsigned long long x = cand[t];
+            uint32_t g = 0, e = 0;
+            for (uint32_t u = 0; u < m; u++) {
+                const unsigned long long y = cand[u];
+                g += (y > x);
+                e += (y == x);
+            }
+            if (r_in >= g && r_in < g + e) {   // every copy of the threshold key writes the same values
+                s.sel_prefix64 = x;
+                s.flag = (r_in - g + 1 == e) ? 2 : 1;   // 2: every copy of the threshold is selected
+            }
+        }
+        __syncthreads();
+        fast = s.flag == 2;
+    }
+    if (fast) {
+        const unsigned long long thr_key = s.sel_prefix64;
+        unsigned long long sel = 0ull, kk = kept;
+        while (kk) {
+            const int k = __ffsll((long long)kk) - 1;
+            kk &= kk - 1;
+            if ((unsigned long long)__double_as_longlong(score[o_begin + k]) >= thr_key) sel |= 1ull << k;
+        }
+        uint32_t tot_sel = 0;
+        uint32_t so = block_exscan((uint32_t)__popcll(sel), s, &tot_sel);
+        while (sel) {
+            const int k = __ffsll((long long)sel) - 1;
+            sel &= sel - 1;
+            out[so++] = o_begin + k + add;
+        }
+        __syncthreads();
+        return P;
+    }
+
+    // ---- list-based selection: kept peaks in order (the neighbour sets in kp are dead: barriers lie in between),
+    // float range of their scores and a cleared histogram for select_top_k
+    if (tid < 256) s.hist[tid] = 0;
+    if (tid == 0) {
+        s.vmin_key = 0xffffffffu;
+        s.vmax_key = 0u;
+        s.ncand = 0;
+        s.flag = 0;
+    }
     uint32_t total = 0;
     uint32_t koff = block_exscan((uint32_t)__popcll(kept), s, &total);
     uint32_t kmin = 0xffffffffu, kmax = 0u;
@@ -499,11 +614,11 @@ __device__ int find_kept_peaks(const double* score, int lo, int nc, int m_obs, u
         atomicMax(&s.vmax_key, kmax);
     }
     __syncthreads();
-    return (int)total;
+    select_top_k(score, kp, state, P, k_events, add, out, s, cand);
+    return P;
 }
 
 constexpr int FP_RANK_MAX = 192;
-constexpr int FP_TOPK_CAND = FP_MAX_EVENTS + 2;   // keys of the threshold's histogram bin that can be ranked exactly (scratch = dv)   // up to this many kept peaks the top-k is found by all-pairs ranking
 
 // ---- the k highest-scoring of the P kept peaks (sig_proc.py:188), in position order ---------------
 // out[0..k) = kp[i] + add for the selected peaks.  Radix-selects the k-th largest score (scores are
@@ -823,9 +938,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
     const int64_t read = blockIdx.x;
     if (read >= a.n) return;
     if (a.retry_status && a.status[read] != a.retry_status) return;
-#ifdef WDX_FP_PROF
-    if (tid == 0) s.t_prev = clock64();
-#endif
+    FP_T_BEGIN(s);
     const int nb = c.barcode_num_events;
     double* fpt_out = a.fpt + read * nb;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -1103,8 +1216,9 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
 
     FP_T(s, 3);   // t-test
     // ---- change points: find_peaks + the num_events highest scores (sig_proc.py:176-198) ------------
-    const int P = find_kept_peaks(score, 0, nc, m_obs, kp, bm, cap, s);
-    FP_T(s, 8);   // rest of find_kept_peaks
+    const int P = kept_peaks_select(score, 0, nc, m_obs, kp, bm, cap, c.num_events, w /* + running_stat_width */, cpts + 1, state,
+                                    reinterpret_cast<unsigned long long*>(dv), s);
+    FP_T(s, 8);   // kept peaks + top-k
     if (P < c.num_events) {  // sig_proc.py:185-186 -> "event segmentation failed"
         fail(FP_FAIL_SEGMENTATION);
         return;
@@ -1113,7 +1227,6 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         fail(FP_FAIL_NORMALIZE);
         return;
     }
-    select_top_k(score, kp, state, P, c.num_events, w, cpts + 1, s, reinterpret_cast<unsigned long long*>(dv));  // + running_stat_width
     if (tid == 0) {
         cpts[0] = 0;                      // peaks lie in [1, nc-2] and w >= 1: 0 and n are never present
         cpts[c.num_events + 1] = n;
@@ -1151,12 +1264,17 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
     FP_T(s, 10);  // means
     // ---- mean_normalize (sig_proc.py:99-111) with numpy's summation order -----------
     if (tid < 32) {   // warp 0: the eight accumulators of numpy's block sum live in lanes 0..7
+#ifdef WDX_FP_EXPERIMENT_NONORM   // timing experiment only (wrong results): what the two sums cost
+        const double mean = ev[0];
+        const double ss = ev[1];
+#else
         const double mean = __ddiv_rn(np_pairwise_sum_warp(n_seg, [&](int i) { return ev[i]; }), (double)n_seg);
         FP_T(s, 13);
         const double ss = np_pairwise_sum_warp(n_seg, [&](int i) {
             const double d = __dsub_rn(ev[i], mean);
             return __dmul_rn(d, d);
         });
+#endif
         FP_T(s, 14);
         if (tid == 0) {
             red[0] = mean;
@@ -1221,12 +1339,13 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         // second segmentation on barcode_scores = adapter_scores[sbs:] with the UNCAPPED min_obs_per_base
         // and running_stat_width (sig_proc.py:336-365)
         const int ke = c.cons_seg_events;
-        const int P2 = (nc - sbs >= 3) ? find_kept_peaks(score, sbs, nc, c.min_obs_per_base, kp, bm, cap, s) : 0;
+        const int P2 = (nc - sbs >= 3) ? kept_peaks_select(score, sbs, nc, c.min_obs_per_base, kp, bm, cap, ke, w - sbs /* relative to raw_signal[sbs:] */,
+                                                           cpts + 1, state, reinterpret_cast<unsigned long long*>(dv), s)
+                                       : 0;
         if (P2 < ke) {
             fail(FP_FAIL_SEGMENTATION);
             return;
         }
-        select_top_k(score, kp, state, P2, ke, w - sbs, cpts + 1, s, reinterpret_cast<unsigned long long*>(dv));  // relative to raw_signal[sbs:]
         if (tid == 0) {
             cpts[0] = 0;
             cpts[ke + 1] = n - sbs;   // scores.size + 2 * running_stat_width = (nc - sbs) + 2 w
@@ -1267,6 +1386,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         if (a.dwell) a.dwell[read * nb + q] = dw;
     }
     FP_T(s, 12);  // stats + output
+    FP_T_END(s);
     if (tid == 0) a.status[read] = FP_OK;
 }
 

@@ -568,15 +568,22 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
             if ((open_lo && p < distance - 1) || (open_hi && len - 1 - p < distance - 1)) st[j] = 4;
         }
         __syncthreads();
-        for (;;) {
-            int undecided = 0;
+        // A verdict is written only when it is final (removed: a higher KEPT peak is near; kept / unknown: every higher
+        // peak near has its final state), and final states never change, so it does not matter how fresh the neighbours'
+        // states are when they are read: no barrier between the rounds, every warp iterates over its own undecided peaks
+        // until none is left (the highest undecided peak can always be decided, so the loops end).
+        volatile uint8_t* vst = st;
+        bool mine_left = true;
+        for (int spin = 0; __any_sync(0xffffffffu, mine_left); spin++) {
+            if (spin > (1 << 22)) __trap();   // a protocol bug must end as a launch failure, never as a hung GPU
+            mine_left = false;
             for (int j = tid; j < P; j += PK_THREADS) {
-                if ((st[j] & 15) != 1) continue;
+                if (vst[j] != 1) continue;
                 const int pj = pk[j];
                 const float x = v[1 + pj];
                 bool killed = false, blocked = false, unknown = false;
                 for (int q = j - 1; q >= 0 && pj - pk[q] < distance; q--) {
-                    const int sq = st[q] & 15;
+                    const int sq = vst[q];
                     if (sq == 3) continue;
                     if (v[1 + pk[q]] > x) {
                         if (sq == 2) killed = true;
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
                     }
                 }
                 for (int q = j + 1; q < P && pk[q] - pj < distance; q++) {
-                    const int sq = st[q] & 15;
+                    const int sq = vst[q];
                     if (sq == 3) continue;
                     if (v[1 + pk[q]] >= x) {
                         if (sq == 2) killed = true;
@@ -593,38 +600,75 @@ __global__ void __launch_bounds__(PK_THREADS) cnn_peaks_kernel(const float* __re
                         else blocked = true;
                     }
                 }
-                const int ns = killed ? 3 : (blocked ? 1 : (unknown ? 4 : 2));
-                if (ns == 1) undecided = 1;
-                st[j] = (uint8_t)(1 | (ns << 4));
+                if (killed) vst[j] = 3;
+                else if (blocked) mine_left = true;
+                else vst[j] = unknown ? 4 : 2;
             }
-            const int any = __syncthreads_or(undecided);
-            for (int j = tid; j < P; j += PK_THREADS)
-                if (st[j] >> 4) st[j] = st[j] >> 4;
-            __syncthreads();
-            if (!any) break;
         }
+        __syncthreads();
     } else {
         for (int j = tid; j < P; j += PK_THREADS) st[j] = 2;
         __syncthreads();
     }
-    // own surviving peaks, ranked by (height desc, position asc)
+    // own surviving peaks, ranked by (height desc, position asc); only the topk highest are reported.  Every warp
+    // takes its own topk best (topk rounds of a warp maximum over order keys: height, then lower position), the few
+    // warp candidates are ranked against each other — a peak of global rank r < topk is outranked by r peaks, each of
+    // which is among ITS warp's r + 1 best, so the rank among the candidates is the global rank.
     const int w_lo = (int)(own_lo - lo), w_hi = (int)(own_hi - lo);
     int own_kept = 0, own_unknown = 0;
+    constexpr int PK_TOP = 8;
+    __shared__ unsigned long long topc[PK_THREADS / 32][PK_TOP];
+    auto key_of = [&](int p) -> unsigned long long {
+        return ((unsigned long long)f32_key(v[1 + p] + 0.0f) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
+    };
     for (int j = tid; j < P; j += PK_THREADS) {
         const int p = pk[j];
         if (p < w_lo || p >= w_hi) continue;
         if (st[j] == 4) own_unknown = 1;
-        if (st[j] != 2) continue;
-        own_kept++;
-        const float x = v[1 + p];
-        int rank = 0;
-        for (int q = 0; q < P; q++) {
-            const int pq = pk[q];
-            if (st[q] != 2 || pq < w_lo || pq >= w_hi) continue;
-            const float y = v[1 + pq];
-            rank += (y > x) || (y == x && pq < p);
+        if (st[j] == 2) own_kept++;
+    }
+    if (d.topk <= PK_TOP) {
+        unsigned long long prev = ~0ull;
+        for (int r = 0; r < d.topk; r++) {
+            unsigned long long best = 0ull;
+            for (int j = tid; j < P; j += PK_THREADS) {
+                const int p = pk[j];
+                if (p < w_lo || p >= w_hi || st[j] != 2) continue;
+                const unsigned long long key = key_of(p);
+                if (key < prev && key > best) best = key;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if ((tid & 31) == 0) topc[tid >> 5][r] = best;   // 0: the warp has no further peak
+            prev = best;
         }
-        if (rank < d.topk) cand[read * d.topk + rank] = p - w_lo;
+        __syncthreads();
+        if (tid < (PK_THREADS / 32) * d.topk) {
+            const unsigned long long key = topc[tid / d.topk][tid % d.topk];
+            if (key) {
+                int rank = 0;
+                for (int w = 0; w < PK_THREADS / 32; w++)
+                    for (int r = 0; r < d.topk; r++) rank += topc[w][r] > key;
+                if (rank < d.topk) cand[read * d.topk + rank] = (int)(0xffffffffu - (uint32_t)key) - w_lo;
+            }
+        }
+    } else {
+        for (int j = tid; j < P; j += PK_THREADS) {
+            const int p = pk[j];
+            if (p < w_lo || p >= w_hi || st[j] != 2) continue;
+            const float x = v[1 + p];
+            int rank = 0;
+            for (int q = 0; q < P && rank < d.topk; q++) {   // only ranks below topk are used: stop counting there
+                const int pq = pk[q];
+                if (st[q] != 2 || pq < w_lo || pq >= w_hi) continue;
+                const float y = v[1 + pq];
+                rank += (y > x) || (y == x && pq < p);
+            }
+            if (rank < d.topk) cand[read * d.topk + rank] = p - w_lo;
+        }
     }
     own_unknown = __syncthreads_or(own_unknown);
     if (tid == 0) kept_total = 0;

@@ -613,7 +613,7 @@ def raw_chain_stream_rank(local, minibatches=48, mb=1000, stride=11500, lanes=4)
     md = cnn.load_cnn_model(os.path.join(ROOT, "tests", "golden", "models", "cnn_rna004_130bps_v0.2.4.npz"), device=local)
     mp4 = DTW_SVM(small, device=local, mode="guarded")
     dmx = MinibatchDemuxer(mp4, md, core=cnn.CoreConfig(), cnn_boundaries=cnn.CNNBoundariesConfig(polya_cand_k=5), device=local,
-                           llr=combined.LLRConfig(), lanes=lanes)
+                           llr=combined.LLRConfig(), lanes=lanes, overlap_llr_tail=os.environ.get("WDX_OVERLAP_TAIL", "1") != "0")
     mbs = []
     for i in range(minibatches):
         a = (i % nb) * mb

@@ -175,6 +175,12 @@ void wdx_fp_destroy(wdx_fp* f);
  * len > max_slice_len, reads that do not fit the first pass are redone by a second launch with this capacity
  * instead of failing with WDX_FP_FAIL_TOO_LONG; all other reads keep the occupancy of the small capacity.  0 = off. */
 int wdx_fp_set_long_slice_len(wdx_fp* f, int32_t len);
+/* One-shot: the fingerprint pass of the NEXT wdx_fp_extract* / wdx_fp_predict call only revisits the reads whose entry in
+ * `status` (device memory, written by an earlier call over the same batch) equals `status`; all other reads keep their
+ * fingerprints and status.  Lets a caller fingerprint the reads that passed the boundary validation while the LLR
+ * re-detection of the failed ones (combined.py:222-296) still runs, and come back for the rescued reads
+ * (status WDX_FP_FAIL_DETECT = 2) afterwards.  0 = off. */
+int wdx_fp_set_resume_status(wdx_fp* f, int32_t status);
 /* Scalar promotion of the winsorisation bounds med -+ outlier_thresh * mad (warpdemux/sig_proc.py:421-431), where med and
  * mad are np.float32 scalars and outlier_thresh a Python float.  on = 0 (default): numpy >= 2 semantics (NEP 50), every
  * step in float32 — the numpy of this image, which the golden fixtures were written with.  on != 0: numpy < 2 semantics
@@ -406,6 +412,12 @@ int wdx_validate_run_report(wdx_validate* v, const float* signals, int64_t n, in
  * those of the FIRST failing candidate instead of the last one evaluated.  For callers that only need the verdict (the
  * fingerprint stage); default off = reference-identical report. */
 int wdx_validate_set_verdict_only(wdx_validate* v, int on);
+/* One-shot, for the NEXT wdx_validate_run*: right behind the first validation pass — before the LLR re-detection of the
+ * failed reads (wdx_validate_set_llr) is queued — `success` is copied to `success_snapshot` ([n] uint8, device memory) and
+ * `event` (a cudaEvent_t, may be NULL) is recorded on the call's stream.  The reads that passed are final at that point
+ * (the re-detection only revisits failed reads: combined.py:222), so a caller may hand them to the next stage on another
+ * stream while the tail still runs.  NULL, NULL = off. */
+int wdx_validate_set_early(wdx_validate* v, uint8_t* success_snapshot, void* event);
 int wdx_validate_enable_timing(wdx_validate* v, int on);
 int wdx_validate_last_kernel_ms(wdx_validate* v, double* ms, int* launches);
 

@@ -22,10 +22,10 @@ EXPORTS = [
     "wdx_model_create", "wdx_model_destroy", "wdx_model_set_guard", "wdx_model_set_chunk_reads", "wdx_model_set_sv_splits",
     "wdx_predict", "wdx_distance_matrix_to", "wdx_last_error", "wdx_device_count",
     "wdx_kernel_launch_count", "wdx_model_enable_timing", "wdx_model_last_kernel_ms", "wdx_model_last_kernel_ms_mode", "wdx_version",
-    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_extract_ex", "wdx_fp_set_consensus", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms", "wdx_fp_set_long_slice_len", "wdx_fp_set_numpy1_promotion",
+    "wdx_fp_create", "wdx_fp_destroy", "wdx_fp_extract", "wdx_fp_extract_ex", "wdx_fp_set_consensus", "wdx_fp_predict", "wdx_fp_enable_timing", "wdx_fp_last_kernel_ms", "wdx_fp_set_long_slice_len", "wdx_fp_set_numpy1_promotion", "wdx_fp_set_resume_status",
     "wdx_cnn_create", "wdx_cnn_destroy", "wdx_cnn_detect", "wdx_cnn_prepare", "wdx_cnn_predict", "wdx_cnn_score_len", "wdx_cnn_set_guard", "wdx_cnn_enable_timing",
     "wdx_cnn_last_kernel_ms",
-    "wdx_validate_create", "wdx_validate_destroy", "wdx_validate_run", "wdx_validate_enable_timing", "wdx_validate_last_kernel_ms", "wdx_validate_set_verdict_only", "wdx_validate_run_ex", "wdx_validate_run_report", "wdx_calibrate_rows", "wdx_validate_set_llr",
+    "wdx_validate_create", "wdx_validate_destroy", "wdx_validate_run", "wdx_validate_enable_timing", "wdx_validate_last_kernel_ms", "wdx_validate_set_verdict_only", "wdx_validate_set_early", "wdx_validate_run_ex", "wdx_validate_run_report", "wdx_calibrate_rows", "wdx_validate_set_llr",
 ]
 
 _lib = None
@@ -111,6 +111,8 @@ def load():
         L.wdx_fp_set_long_slice_len.argtypes = [vp, C.c_int32]
         L.wdx_fp_set_numpy1_promotion.restype = i32
         L.wdx_fp_set_numpy1_promotion.argtypes = [vp, i32]
+        L.wdx_fp_set_resume_status.restype = i32
+        L.wdx_fp_set_resume_status.argtypes = [vp, C.c_int32]
         L.wdx_fp_set_consensus.restype = i32
         L.wdx_fp_set_consensus.argtypes = [vp, vp]
         L.wdx_fp_predict.restype = i32
@@ -151,6 +153,8 @@ def load():
         L.wdx_calibrate_rows.argtypes = [vp, i64, i64, vp, vp, vp, vp, i64, i32, vp]
         L.wdx_validate_set_verdict_only.restype = i32
         L.wdx_validate_set_verdict_only.argtypes = [vp, i32]
+        L.wdx_validate_set_early.restype = i32
+        L.wdx_validate_set_early.argtypes = [vp, vp, vp]
         L.wdx_validate_set_llr.restype = i32
         L.wdx_validate_set_llr.argtypes = [vp, vp]
         L.wdx_validate_enable_timing.restype = i32

@@ -16,6 +16,7 @@ struct wdx_fp {
     FpConfig cfg{};
     int max_slice_len = 0;
     int long_slice_len = 0;   // > max_slice_len: reads too long for the first pass are redone with this capacity
+    int resume_status = 0;    // one-shot (wdx_fp_set_resume_status): the next call's fingerprint pass only revisits reads with this status
     int device = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr;       // kernels + result copies
@@ -135,6 +136,9 @@ int run(wdx_fp* f, const FpCall& c) {
                           (c.labels && !lab_dev) || (c.conf && !conf_dev) || (c.prob && !prob_dev) ||
                           (c.flags && !flags_dev) || (c.cons && !cons_dev);
 
+    const int resume_status = f->resume_status;
+    f->resume_status = 0;
+    if (resume_status && !status_dev) return fail(WDX_ERR_INVALID, "wdx_fp_set_resume_status needs the status array of the earlier pass on the device");
     // shared-memory capacity per read
     int64_t cap64 = f->max_slice_len;
     if (cap64 <= 0) {
@@ -237,7 +241,9 @@ int run(wdx_fp* f, const FpCall& c) {
         fa.status = status_dev ? c.status + r0 : (int32_t*)f->status[b].p;
         fa.cons_query = (const double*)f->cons_query.p;
         fa.cons = c.cons ? (cons_dev ? c.cons + (size_t)r0 * 3 : (int32_t*)f->cons[b].p) : nullptr;
+        fa.retry_status = resume_status;
         if ((rc = launch_fp(f, fa, st))) return rc;
+        fa.retry_status = 0;
         if (f->max_slice_len > 0 && f->long_slice_len > cap) {   // the few reads longer than the first pass's capacity
             FpArgs fl = fa;
             fl.cap = std::min<int>(FP_MAX_LEN, (f->long_slice_len + 63) & ~63);
@@ -376,6 +382,14 @@ int wdx_fp_set_numpy1_promotion(wdx_fp* f, int on) {
     if (!f) return fail(WDX_ERR_INVALID, "NULL fingerprint handle");
     std::lock_guard<std::mutex> lk(f->mu);
     f->cfg.numpy1_promotion = on != 0;
+    return WDX_OK;
+}
+
+int wdx_fp_set_resume_status(wdx_fp* f, int32_t status) {
+    if (!f) return fail(WDX_ERR_INVALID, "NULL fingerprint handle");
+    if (status < 0 || status > FP_FAIL_CONSENSUS) return fail(WDX_ERR_INVALID, "resume status %d", status);
+    std::lock_guard<std::mutex> lk(f->mu);
+    f->resume_status = status;
     return WDX_OK;
 }
 

@@ -26,6 +26,8 @@ struct wdx_validate {
     DevBuf preds2, todo, medmad;
     bool timing = false;
     bool verdict_only = false;
+    uint8_t* early_ok = nullptr;          // one-shot (wdx_validate_set_early): copy of `success` behind the first validation
+    cudaEvent_t early_ev = nullptr;       //           and the event recorded there
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
 };
@@ -150,6 +152,14 @@ void wdx_validate_destroy(wdx_validate* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int wdx_validate_set_early(wdx_validate* h, uint8_t* success_snapshot, void* event) {
+    if (!h) return fail(WDX_ERR_INVALID, "NULL validation handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->early_ok = success_snapshot;
+    h->early_ev = (cudaEvent_t)event;
+    return WDX_OK;
 }
 
 int wdx_validate_set_verdict_only(wdx_validate* h, int on) {
@@ -332,6 +342,14 @@ int wdx_validate_run_report(wdx_validate* h, const float* signals, int64_t n, in
     validate_kernel<<<grid, FP_THREADS, smem, st>>>(a, h->cfg);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
+    {   // wdx_validate_set_early: the verdicts of the reads that pass are final here — what follows only revisits the failed ones
+        uint8_t* early_ok = h->early_ok;
+        cudaEvent_t early_ev = h->early_ev;
+        h->early_ok = nullptr;
+        h->early_ev = nullptr;
+        if (early_ok) CUDA_TRY(cudaMemcpyAsync(early_ok, a.success, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        if (early_ev) CUDA_TRY(cudaEventRecord(early_ev, st));
+    }
     if (h->llr_on) {
         // combined.py:222-290: the reads that failed get a poly(A) re-detection on the CNN's adapter end ("hail mary",
         // result assigned unconditionally), then a full LLR detection (result assigned only when it validates).

@@ -320,6 +320,15 @@ class Validator:
                                                  p(success), p(info), p(bounds), p(vals), p(parts), p(open_pores), stream or None)
         _lib.check(rc, "wdx_validate_run_report")
 
+    def set_early(self, success_snapshot, event) -> None:
+        """One-shot for the next run: `success` is copied to `success_snapshot` (device uint8 [n]) and `event` (a recorded
+        torch.cuda.Event) is re-recorded right behind the first validation pass, before the LLR re-detection of the failed
+        reads is queued (wdx_validate_set_early)."""
+        ev = int(event.cuda_event) if event is not None else 0
+        if event is not None and not ev:
+            raise ValueError("record the event once before handing it over (torch creates the CUDA event lazily)")
+        _lib.check(_lib.load().wdx_validate_set_early(self._handle(), _cnn._ptr(success_snapshot), ev or None), "wdx_validate_set_early")
+
     def enable_timing(self, on: bool = True):
         _lib.check(_lib.load().wdx_validate_enable_timing(self._handle(), int(on)), "wdx_validate_enable_timing")
 

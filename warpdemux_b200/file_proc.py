@@ -90,7 +90,7 @@ class MinibatchDemuxer:
                  validate_config: Optional["_combined.ValidateConfig"] = None, fp_config: Optional[FingerprintConfig] = None,
                  device: Optional[int] = None, mode: Optional[str] = None, cnn_mode: Optional[str] = None,
                  llr_fallback: Optional[Callable] = None, consensus_query=None, full_detect_report: bool = False,
-                 llr="auto", lanes: int = 4):
+                 llr="auto", lanes: int = 4, overlap_llr_tail: bool = True):
         import torch  # device memory and streams only
 
         self._torch = torch
@@ -126,6 +126,7 @@ class MinibatchDemuxer:
         # reads of the LLR fallback, the finishing kernels) overlaps the wide kernels of the next.  Lane 0 = the objects
         # given; the others are replicas built from the same host-side parameters (created lazily).
         self.lanes = max(1, int(lanes))
+        self.overlap_llr_tail = bool(overlap_llr_tail)   # fingerprints of the validated reads next to the LLR re-detection of the failed ones
         self._lane_objs = [dict(model_predict=model_predict, model_detect=model_detect, validator=self.validator,
                                 fingerprinter=self.fingerprinter, stream=None)]
         self._lane_cfg = dict(vcfg=vcfg, fcfg=fcfg, llr=llr, verdict_only=not full_detect_report)
@@ -154,7 +155,7 @@ class MinibatchDemuxer:
     def _streams(self):
         torch = self._torch
         if self._stream is None:
-            self._stream = torch.cuda.Stream(device=self._dev())        # kernels + result download
+            self._stream = torch.cuda.Stream(device=self._dev(), priority=-1)   # kernels + result download (above the lanes' aux streams)
             self._copy_stream = torch.cuda.Stream(device=self._dev())   # minibatch upload
         return self._stream, self._copy_stream
 
@@ -171,7 +172,7 @@ class MinibatchDemuxer:
                 fingerprinter=Fingerprinter(c["fcfg"], device=self.device), stream=None))
         ln = self._lane_objs[i]
         if ln["stream"] is None:
-            ln["stream"] = self._streams()[0] if i == 0 else torch.cuda.Stream(device=self._dev())
+            ln["stream"] = self._streams()[0] if i == 0 else torch.cuda.Stream(device=self._dev(), priority=-1)
         return ln
 
     def _upload(self, slot: int, signals, full_lengths, read_ids) -> dict:
@@ -295,7 +296,31 @@ class MinibatchDemuxer:
             rescued = np.zeros(n, dtype=bool)
             if n:
                 _cnn.detect_raw(lane["model_detect"], self.core, self.k_cand, d_sig, n, stride, d_preds, mode=self.cnn_mode, stream=sp)
+                # Reads that pass the first validation are final there (the LLR re-detection only revisits failed reads), so
+                # their fingerprints are computed on a second stream WHILE the re-detection tail runs; the fused call below
+                # then only revisits the reads that were failed at that point (status FP_FAIL_DETECT) and may have been rescued.
+                early = self.overlap_llr_tail and self.llr_fallback is None and lane["validator"].llr is not None
+                if early:
+                    if lane.get("aux") is None:
+                        # lowest priority: the few CTAs of the re-detection tail are placed first, the fingerprint pass fills the rest
+                        lane["aux"] = torch.cuda.Stream(device=self._dev(), priority=0)
+                        lane["ev_main"] = torch.cuda.Event()
+                        lane["ev_main"].record(st)      # creates the CUDA event (torch does it lazily)
+                        lane["ev_p1"] = torch.cuda.Event()
+                    d_snap = g("snap_ok", (n,), torch.uint8)
+                    lane["validator"].set_early(d_snap, lane["ev_main"])
                 lane["validator"].run_raw(d_sig, n, stride, d_len, d_preds, ld, d_suc, d_info, d_bounds, None, stream=sp)
+                if early:
+                    aux = lane["aux"]
+                    with torch.cuda.stream(aux):
+                        aux.wait_event(lane["ev_main"])
+                        d_a0.copy_(d_bounds[:, 0])
+                        d_a1.copy_(d_bounds[:, 1])
+                        lane["fingerprinter"].extract_raw(d_sig, n, stride, d_a0, d_a1, d_fpt, d_status, detect_ok=d_snap,
+                                                          stream=aux.cuda_stream)
+                        lane["ev_p1"].record(aux)
+                    st.wait_event(lane["ev_p1"])
+                    lane["fingerprinter"].set_resume_status(2)      # WDX_FP_FAIL_DETECT
                 if self.llr_fallback is not None:
                     suc_h = d_suc.cpu().numpy()            # synchronises this stream: n bytes
                     failed = np.flatnonzero(suc_h == 0)

@@ -252,6 +252,11 @@ class Fingerprinter:
         return ms.value, n.value
 
     # -- pointer-level calls (numpy arrays, torch tensors or addresses) --------
+    def set_resume_status(self, status: int) -> None:
+        """One-shot: the fingerprint pass of the next extract_raw / predict_raw only revisits the reads whose `status` entry
+        (device array written by an earlier call over the same batch) equals `status` (wdx_fp_set_resume_status)."""
+        _lib.check(_lib.load().wdx_fp_set_resume_status(self._handle(), int(status)), "wdx_fp_set_resume_status")
+
     def extract_raw(self, signals, n, stride, adapter_start, adapter_end, fpt, status, sig_len=None, detect_ok=None,
                     dwell=None, stats=None, clip_in_place=False, stream: int = 0, cons=None) -> None:
         rc = _lib.load().wdx_fp_extract_ex(self._handle(), _ptr(signals), int(n), int(stride), _ptr(sig_len),

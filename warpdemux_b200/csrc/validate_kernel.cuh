@@ -673,7 +673,6 @@ __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
 #pragma unroll
     for (int t = 0; t < WPL; t++) {
         w[t] = h[t];
-        h[t] = 0;                            // from here on: bin -> 1 + candidate list (ms_gather_pass)
         sum += (w[t] & 0xffffu) + (w[t] >> 16);
     }
     uint32_t inc = sum;
@@ -683,8 +682,23 @@ __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
         if (lane >= o) inc += t;
     }
     const uint32_t run0 = inc - sum;
+    // The lane's 32 counts become inclusive prefixes IN PLACE (16-bit pairs again: a lane holds fewer than 2^16 values), so
+    // that the bin of a rank is found by the whole warp at once — lane t looks at bin t of the lane whose range holds the
+    // rank — instead of one lane walking its 32 bins through a chain of dependent additions per rank.
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int t = 0; t < WPL; t++) {
+            run += w[t] & 0xffffu;
+            const uint32_t p0 = run;
+            run += w[t] >> 16;
+            h[t] = p0 | (run << 16);
+        }
+    }
+    __syncwarp();
+    const unsigned short* pre = reinterpret_cast<const unsigned short*>(ms.hist[jj]);
     const int q0 = j.q0, nq = j.nq;
-    // lane q < nq owns rank q: which lane's bins hold it, then that lane's walk (all lanes walk at once, one rank each)
+    // lane q < nq owns rank q
     const uint32_t myk = (lane < nq) ? ms.q_rank[q0 + lane] : 0xffffffffu;
     int mybin = -1;
     uint32_t myr = 0, mycnt = 0;
@@ -696,35 +710,26 @@ __device__ __forceinline__ void ms_scan_job(MsState& ms, int jj) {
         const unsigned who = __ballot_sync(0xffffffffu, hit);
         int bin = -1;
         uint32_t r = 0, cnt = 0;
-        if (hit) {
-            uint32_t run = run0;
-#pragma unroll
-            for (int t = 0; t < WPL; t++) {
-                const uint32_t c0 = w[t] & 0xffffu, c1 = w[t] >> 16;
-                if (k >= run && k < run + c0) {
-                    bin = (lane * WPL + t) * 2;
-                    r = k - run;
-                    cnt = c0;
-                }
-                run += c0;
-                if (k >= run && k < run + c1) {
-                    bin = (lane * WPL + t) * 2 + 1;
-                    r = k - run;
-                    cnt = c1;
-                }
-                run += c1;
-            }
+        if (who) {                          // uniform
+            const int src = __ffs(who) - 1;
+            const uint32_t kl = k - __shfl_sync(0xffffffffu, run0, src);    // rank inside that lane's 32 bins
+            const uint32_t incl = pre[src * 2 * WPL + lane];
+            const uint32_t excl = lane ? pre[src * 2 * WPL + lane - 1] : 0u;
+            const unsigned who2 = __ballot_sync(0xffffffffu, kl >= excl && kl < incl);   // exactly one lane (kl < that lane's sum)
+            const int l2 = __ffs(who2) - 1;
+            bin = src * 2 * WPL + l2;
+            r = kl - __shfl_sync(0xffffffffu, excl, l2);
+            cnt = __shfl_sync(0xffffffffu, incl - excl, l2);
         }
-        const int src = who ? __ffs(who) - 1 : 0;
-        bin = __shfl_sync(0xffffffffu, bin, src);
-        r = __shfl_sync(0xffffffffu, r, src);
-        cnt = __shfl_sync(0xffffffffu, cnt, src);
         if (lane == q) {
             mybin = bin;
             myr = r;
             mycnt = cnt;
         }
     }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < WPL; t++) h[t] = 0;  // from here on: bin -> 1 + candidate list (ms_gather_pass)
     // candidate lists: the first rank of a bin allocates, the others share
     int first = -1;
 #pragma unroll

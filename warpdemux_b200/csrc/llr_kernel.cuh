@@ -136,28 +136,57 @@ __device__ __noinline__ int llr_find_peaks(const double* x, int n, int distance,
         __syncthreads();
         return 0;
     }
-    if (distance >= 1) {   // _select_by_peak_distance, priority = height
-        for (int j = tid; j < P; j += FP_THREADS) {
-            const double hj = x[w.pk[j]];
-            int r = 0;
-            for (int k = 0; k < P; k++) {
-                const double hk = x[w.pk[k]];
-                r += (hk < hj) || (hk == hj && k < j);
+    if (distance >= 1) {   // _select_by_peak_distance, priority = (height, then the higher index)
+        // scipy walks the peaks from the highest down and removes the neighbours of every peak still kept; the kept set is
+        // the unique one with "kept iff no kept peak of higher priority lies closer than `distance`".  A verdict is written
+        // only when it is final (removed: a higher KEPT peak is near; kept: every higher peak near is REMOVED) and final
+        // states never change, so stale reads are harmless: every warp iterates over its own undecided peaks without a
+        // barrier between the rounds (before: an all-pairs ranking of the peaks and ONE thread walking them in order).
+        for (int j = tid; j < P; j += FP_THREADS) w.keep[j] = 1;     // 1 undecided, 2 kept, 3 removed
+        __syncthreads();
+        {
+            volatile uint8_t* vk = w.keep;
+            bool mine_left = true;
+            for (int spin = 0; __any_sync(0xffffffffu, mine_left); spin++) {
+                if (spin > (1 << 22)) __trap();   // a protocol bug must end as a launch failure, never as a hung GPU
+                mine_left = false;
+                for (int j = tid; j < P; j += FP_THREADS) {
+                    if (vk[j] != 1) continue;
+                    const int pj = w.pk[j];
+                    const double hj = x[pj];
+                    bool killed = false, blocked = false;
+                    for (int k = j - 1; k >= 0 && pj - w.pk[k] < distance; k--) {
+                        const int st = vk[k];
+                        if (st != 3 && x[w.pk[k]] > hj) {       // equal heights: the higher index wins, k < j loses
+                            if (st == 2) killed = true;
+                            else blocked = true;
+                        }
+                    }
+                    for (int k = j + 1; k < P && w.pk[k] - pj < distance; k++) {
+                        const int st = vk[k];
+                        if (st != 3 && x[w.pk[k]] >= hj) {
+                            if (st == 2) killed = true;
+                            else blocked = true;
+                        }
+                    }
+                    if (killed) vk[j] = 3;
+                    else if (blocked) mine_left = true;
+                    else vk[j] = 2;
+                }
             }
-            w.order[r] = j;
-            w.keep[j] = 1;
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int r = P - 1; r >= 0; r--) {
-                const int j = w.order[r];
-                if (!w.keep[j]) continue;
-                for (int k = j - 1; k >= 0 && w.pk[j] - w.pk[k] < distance; k--) w.keep[k] = 0;
-                for (int k = j + 1; k < P && w.pk[k] - w.pk[j] < distance; k++) w.keep[k] = 0;
-            }
+        if (P <= FP_THREADS) {      // kept peaks, in order (in place: every thread has read its peak before the scan's barriers)
+            const int pj = tid < P ? w.pk[tid] : 0;
+            const uint32_t kf = (tid < P && w.keep[tid] == 2) ? 1u : 0u;
+            uint32_t m = 0;
+            const uint32_t pos = block_exscan(kf, s, &m);
+            if (kf) w.pk[pos] = pj;
+            if (tid == 0) sh.count = (int)m;
+        } else if (tid == 0) {
             int m = 0;
             for (int j = 0; j < P; j++)
-                if (w.keep[j]) w.pk[m++] = w.pk[j];
+                if (w.keep[j] == 2) w.pk[m++] = w.pk[j];
             sh.count = m;
         }
         __syncthreads();

@@ -179,14 +179,23 @@ __device__ __forceinline__ double div_small_int(double x, double w, double r) {
 // (_c_segmentation.pyx:133-149).  The statistics of window [pos+W, pos+2W) at position pos are
 // bit for bit those of window [pos', pos'+W) at pos' = pos + W (same operands, same sequential
 // order), so a thread that walks pos, pos+W, pos+2W, ... computes every window once.
-template <int W>
+// TREE: the sum is known to be exact (see `exact_sums` in the kernel), so it may be formed as a tree — a dependent chain
+// of 4 additions instead of 12.
+template <int W, bool TREE = false>
 __device__ __forceinline__ void window_stat_fixed(const float* p, double wd, double wr, double& m, double& v) {
     double x[W];
 #pragma unroll
     for (int i = 0; i < W; i++) x[i] = (double)p[i];
-    m = 0.0;
+    if (TREE && W == 12) {
+        const double s01 = __dadd_rn(x[0], x[1]), s23 = __dadd_rn(x[2], x[3]), s45 = __dadd_rn(x[4], x[5]);
+        const double s67 = __dadd_rn(x[6], x[7]), s89 = __dadd_rn(x[8], x[9]), sab = __dadd_rn(x[10], x[11]);
+        m = __dadd_rn(__dadd_rn(__dadd_rn(s01, s23), __dadd_rn(s45, s67)), __dadd_rn(s89, sab));
+        m = __dadd_rn(m, 0.0);   // an exact zero sum is +0.0 in the reference (it starts from +0.0); -0.0 + 0.0 = +0.0
+    } else {
+        m = 0.0;
 #pragma unroll
-    for (int i = 0; i < W; i++) m = __dadd_rn(m, x[i]);
+        for (int i = 0; i < W; i++) m = __dadd_rn(m, x[i]);
+    }
     m = div_small_int(m, wd, wr);
     v = 0.0;
 #pragma unroll
@@ -953,16 +962,20 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         if (tid == 0) a.status[read] = code;
     };
 
-    if (a.detect_ok && !a.detect_ok[read]) {  // sig_proc.py:400-407
+    // the read's four scalars are requested together (one round trip to memory instead of three dependent ones)
+    const uint8_t ok_in = a.detect_ok ? a.detect_ok[read] : (uint8_t)1;
+    const int64_t a_start = a.adapter_start[read], a_end = a.adapter_end[read];
+    const int64_t len_in = a.sig_len ? (int64_t)a.sig_len[read] : a.stride;
+    if (!ok_in) {  // sig_proc.py:400-407
         fail(FP_FAIL_DETECT);
         return;
     }
 
     // ---- extract_adapter (sig_proc.py:382-391) --------------------------------
-    const int64_t len_row = a.sig_len ? min((int64_t)a.sig_len[read], a.stride) : a.stride;
-    int64_t start = a.adapter_start[read] - c.padding;
+    const int64_t len_row = min(len_in, a.stride);
+    int64_t start = a_start - c.padding;
     if (start < 0) start = 0;
-    int64_t stop = a.adapter_end[read] + c.padding;
+    int64_t stop = a_end + c.padding;
     if (stop > len_row) stop = len_row;
     int64_t n64 = stop - start;
     if (n64 < 0) n64 = 0;
@@ -1143,13 +1156,24 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
                 int pos = tid % 12 + 12 * seg_len * (tid / 12);
                 if (pos < nc) {
                     double m1, v1;
-                    window_stat_fixed<12>(sig + pos, 12.0, wr, m1, v1);
-                    for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
-                        double m2, v2;
-                        window_stat_fixed<12>(sig + pos + 12, 12.0, wr, m2, v2);
-                        score[pos] = ttest_combine(m1, v1, m2, v2);
-                        m1 = m2;
-                        v1 = v2;
+                    if (exact_sums) {   // uniform
+                        window_stat_fixed<12, true>(sig + pos, 12.0, wr, m1, v1);
+                        for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
+                            double m2, v2;
+                            window_stat_fixed<12, true>(sig + pos + 12, 12.0, wr, m2, v2);
+                            score[pos] = ttest_combine(m1, v1, m2, v2);
+                            m1 = m2;
+                            v1 = v2;
+                        }
+                    } else {
+                        window_stat_fixed<12>(sig + pos, 12.0, wr, m1, v1);
+                        for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
+                            double m2, v2;
+                            window_stat_fixed<12>(sig + pos + 12, 12.0, wr, m2, v2);
+                            score[pos] = ttest_combine(m1, v1, m2, v2);
+                            m1 = m2;
+                            v1 = v2;
+                        }
                     }
                 }
             }

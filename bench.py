@@ -564,6 +564,39 @@ def raw_signal_chain(params_small, local):
                               "validate_reads_per_s": n / (res[1] * 1e-3),
                               "validate_roofline": {"bound": "hbm", "achieved": alg / (res[1] * 1e-3) / 1e9, "unit": "GB/s",
                                                     "note": "algorithmic bytes = 4 x valid samples per row, read once"}}
+    # the tensor-core kernel of the CNN against the measured dense bf16 / fp16 MMA peak: issued MMA flops (M padded to 128-row
+    # tiles, three fp16 products per float32 product) and the useful float32-equivalent flops
+    try:
+        t_in, _t_out = cnn.score_len(model, dmx.core, k, stride)
+        t1 = (t_in - 1) // 3 + 1
+        tiles, qtiles = (t1 + 127) // 128, (t1 + 128) // 128
+        issued = 2 * tiles * 128 * 64 * 64 * 7 * 2 * 3 + qtiles * 128 * 64 * 16 * 3 * 3 * 2
+        useful = 2 * t1 * 64 * 64 * 7 * 2 + t1 * 64 * 2 * 7 * 2
+        cnn.enable_timing(model, dmx.core, k, True)
+        bestc = None
+        with torch.cuda.stream(side):
+            for it in range(3):
+                cnn.detect_raw(model, dmx.core, k, d_sig, n, stride, d_preds, stream=sp)
+                side.synchronize()
+                msc, nl = cnn.last_kernel_ms(model, dmx.core, k)
+                bestc = msc if bestc is None or (it and msc < bestc) else bestc
+        cnn.enable_timing(model, dmx.core, k, False)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak_tf = float(peaks.get("bf16_tflops", 1680.0))
+        out["device_resident"]["cnn_tensor_roofline"] = {
+            "bound": "tensor", "kernel": "cnn_tc_kernel (tcgen05.mma kind::f16 128x64x16, fp16 hi + lo split, TMEM accumulators)",
+            "achieved": issued * n / (bestc * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": issued * n / (bestc * 1e-3) / 1e12 / peak_tf,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1680 TFLOP/s",
+            "useful_f32_equivalent_tflops": useful * n / (bestc * 1e-3) / 1e12, "conv_kernels_ms": bestc, "conv_kernel_launches": nl,
+            "hidden_positions": t1, "issued_mma_flops_per_read": issued,
+            "note": "MMA phases are shared-memory-bound (N = 64: 6 KB of operands per 128x64x16 MMA) and alternate with CUDA-core phases "
+                    "(conv1, epilogues with the fp16 split) of the same read; DESIGN.md 4.6"}
+    except Exception as e:  # noqa: BLE001
+        out["device_resident"]["cnn_tensor_roofline"] = {"error": repr(e)}
     # the whole step through the public call on device-resident rows (stages chained, results downloaded, LLR tail
     # overlapped by the fingerprint pass of the validated reads)
     bestw = 1e30

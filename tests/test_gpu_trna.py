@@ -61,6 +61,30 @@ def test_reference_golden_real_reads(golden_trna, golden_real):
     fp.close()
 
 
+def test_three_launch_form_on_big_batches(golden_trna, golden_real):
+    """Batches of >= 2048 reads take the three-launch consensus form (front part -> alignment kernel of small CTAs ->
+    refinement on the parked state): the same fixture, tiled, must come out bit for bit; the single-launch form
+    (WDX_FP_NO_SPLIT) must agree with it."""
+    g = golden_trna
+    rows = real_fixture_rows(golden_real)
+    reps = -(-2304 // rows.shape[0])
+    tile = lambda x: np.concatenate([x] * reps, axis=0)
+    big = tile(rows)
+    a0, a1, ok = tile(golden_real["adapter_start"]), tile(golden_real["adapter_end"]), tile(golden_real["detect_ok"])
+    assert big.shape[0] >= 2048
+    fp, _ = make_fp(g)
+    b = fp.extract(big, a0, a1, detect_ok=ok)
+    same(b, tile(g["real_status"]), tile(g["real_fpt"]), tile(g["real_dwell"]), tile(g["real_stats"]), tile(g["real_cons"]))
+    os.environ["WDX_FP_NO_SPLIT"] = "1"
+    try:
+        b1 = fp.extract(big, a0, a1, detect_ok=ok)
+    finally:
+        del os.environ["WDX_FP_NO_SPLIT"]
+    assert np.array_equal(b.status, b1.status) and np.array_equal(b.fpt, b1.fpt, equal_nan=True)
+    assert np.array_equal(b.dwell, b1.dwell) and np.array_equal(b.cons, b1.cons) and np.array_equal(b.stats, b1.stats, equal_nan=True)
+    fp.close()
+
+
 def test_reference_golden_synthetic(golden_trna):
     g = golden_trna
     fp, _ = make_fp(g)

@@ -38,7 +38,8 @@
 
 namespace wdx {
 
-enum { FP_OK = 0, FP_FAIL_SEGMENTATION = 1, FP_FAIL_DETECT = 2, FP_FAIL_NORMALIZE = 3, FP_FAIL_TOO_LONG = 4, FP_FAIL_CONSENSUS = 5 };
+enum { FP_OK = 0, FP_FAIL_SEGMENTATION = 1, FP_FAIL_DETECT = 2, FP_FAIL_NORMALIZE = 3, FP_FAIL_TOO_LONG = 4, FP_FAIL_CONSENSUS = 5,
+       FP_PENDING = 100 /* internal: between the kernels of the three-launch consensus form */ };
 constexpr int FP_MAX_QUERY = 128;  // longest consensus query (4 rows per lane of one warp)
 
 struct FpConfig {
@@ -76,7 +77,23 @@ struct FpArgs {
     int32_t* status;            // [n]
     const double* cons_query;   // [cons_len] consensus query (device), consensus mode only
     int32_t* cons;              // [n][3] seg_cons_query_start, seg_cons_query_end, sig_barcode_start, or nullptr
+    unsigned char* park;        // three-launch consensus form: fp_park_bytes(cap) of state per read between the kernels
 };
+
+// State of a read between the kernels of the three-launch consensus form (global memory): the winsorised slice, the
+// t-test scores, the first segmentation's change points, the normalised event series, a few scalars, the match.
+struct FpParkHead {
+    int n, nc, w, n_seg, exact_sums, match[2], pad;
+    double ev_mean, ev_std;
+};
+__host__ __device__ inline size_t fp_park_bytes(int cap) {
+    return sizeof(FpParkHead) + (size_t)cap * 12 + (size_t)(FP_MAX_EVENTS + 2) * 12 + 16;
+}
+__device__ __forceinline__ FpParkHead* park_head(unsigned char* p) { return reinterpret_cast<FpParkHead*>(p); }
+__device__ __forceinline__ double* park_score(unsigned char* p) { return reinterpret_cast<double*>(p + sizeof(FpParkHead)); }
+__device__ __forceinline__ double* park_series(unsigned char* p, int cap) { return park_score(p) + cap; }
+__device__ __forceinline__ float* park_sig(unsigned char* p, int cap) { return reinterpret_cast<float*>(park_series(p, cap) + FP_MAX_EVENTS + 2); }
+__device__ __forceinline__ int* park_cpts(unsigned char* p, int cap) { return reinterpret_cast<int*>(park_sig(p, cap) + cap); }
 
 // Same result as block_median_f32, found with two light passes instead of five
 // heavy ones: values are binned linearly over [vmin, vmax] (a monotone map, so
@@ -196,7 +213,7 @@ __device__ __forceinline__ void window_stat_fixed(const float* p, double wd, dou
 #pragma unroll
         for (int i = 0; i < W; i++) m = __dadd_rn(m, x[i]);
     }
-    m = div_small_int(m, wd, wr);
+    m = (W <= 12) ? div_small_int(m, wd, wr) : __ddiv_rn(m, wd);   // the three-operation division is verified for w <= 12 only
     v = 0.0;
 #pragma unroll
     for (int i = 0; i < W; i++) {
@@ -211,6 +228,29 @@ __device__ __forceinline__ double ttest_combine(double m1, double var1, double m
     if (vs == 0.0) return 0.0;
     const double num = (m1 > m2) ? __dsub_rn(m1, m2) : __dsub_rn(m2, m1);
     return __ddiv_rn(num, __dsqrt_rn(vs));
+}
+
+// The t-test over residue-class chains (see the kernel): thread = (residue r = pos mod W, segment of the chain r, r + W, ...);
+// the second window of one position is the first window of the next.  nblk = ceil(nc / W), seg_len = windows per thread.
+template <int W, bool TREE>
+__device__ __forceinline__ void ttest_residue_chains(const float* sig, double* score, int nc, int nblk, int seg_len) {
+    const int tid = threadIdx.x;
+    const double wd = (double)W, wr = 1.0 / (double)W;
+    const int n_seg = (nblk + seg_len - 1) / seg_len;  // <= FP_THREADS / W: one item per thread
+    if (tid < W * n_seg) {
+        int pos = tid % W + W * seg_len * (tid / W);
+        if (pos < nc) {
+            double m1, v1;
+            window_stat_fixed<W, TREE>(sig + pos, wd, wr, m1, v1);
+            for (int j = 0; j < seg_len && pos < nc; j++, pos += W) {
+                double m2, v2;
+                window_stat_fixed<W, TREE>(sig + pos + W, wd, wr, m2, v2);
+                score[pos] = ttest_combine(m1, v1, m2, v2);
+                m1 = m2;
+                v1 = v2;
+            }
+        }
+    }
 }
 
 // numpy's pairwise summation for n <= 128 contiguous float64 (np.add.reduce):
@@ -923,8 +963,115 @@ __device__ void consensus_match_rows(const double* __restrict__ query, int Q, co
     }
 }
 
+// A read fails: NaN fingerprint, zero dwell times, NaN statistics, its status code (the whole CTA calls this).
+__device__ __forceinline__ void fp_fail(const FpArgs& a, int64_t read, int nb, int code, bool cons) {
+    const int tid = threadIdx.x;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int q = tid; q < nb; q += FP_THREADS) {
+        a.fpt[read * nb + q] = qnan;
+        if (a.dwell) a.dwell[read * nb + q] = 0;
+    }
+    if (a.stats && tid < 6) a.stats[read * 6 + tid] = qnan;
+    if (cons && a.cons && tid < 3) a.cons[read * 3 + tid] = 0;
+    if (tid == 0) a.status[read] = code;
+}
+
+// c_new_means (_c_segmentation.pyx:41-53): sequential float64 sums; eight lanes per segment when the sums are exact
+__device__ __forceinline__ void fp_segment_means(const float* base, int nseg, const int* cpts, double* ev, bool exact_sums) {
+    const int tid = threadIdx.x;
+    if (exact_sums) {
+        // four segments per warp and trip, eight lanes each
+        const int lane = tid & 31, warp = tid >> 5, sub = lane >> 3, sl = lane & 7;
+        for (int q0 = warp * 4; q0 < nseg; q0 += FP_WARPS * 4) {
+            const int q = q0 + sub;
+            const int b = (q < nseg) ? cpts[q] : 0, e = (q < nseg) ? cpts[q + 1] : 0;
+            double sum = 0.0;
+            for (int i = b + sl; i < e; i += 8) sum = __dadd_rn(sum, (double)base[i]);
+#pragma unroll
+            for (int o = 4; o; o >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+            if (sl == 0 && q < nseg) ev[q] = __ddiv_rn(sum, (double)(e - b));
+        }
+    } else {
+        for (int q = tid; q < nseg; q += FP_THREADS) {
+            double sum = 0.0;
+            const int b = cpts[q], e = cpts[q + 1];
+            for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)base[i]);
+            ev[q] = __ddiv_rn(sum, (double)(e - b));
+        }
+    }
+}
+
+// The last barcode_num_events of the n_out_seg segments (bounds in cpts, means in ev), normalised by the mean / std of
+// the adapter events (sig_proc.py:569-594; normalize "mean" :546-552, or normalize_wrt for the refined events :482-484).
+__device__ __forceinline__ void fp_write_fingerprint(const FpArgs& a, int64_t read, int nb, int n_out_seg, const int* cpts, const double* ev,
+                                                     double ev_mean, double ev_std) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const int keep = min(nb, n_out_seg);
+    for (int q = threadIdx.x; q < nb; q += FP_THREADS) {
+        const int srcq = n_out_seg - keep + (q - (nb - keep));
+        double v = qnan;  // front NaN padding if fewer events than asked (unreachable with accept_less_cpts=false)
+        int64_t dw = 0;
+        if (q >= nb - keep) {
+            v = __ddiv_rn(__dsub_rn(ev[srcq], ev_mean), ev_std);
+            dw = (int64_t)(cpts[srcq + 1] - cpts[srcq]);
+        }
+        a.fpt[read * nb + q] = v;
+        if (a.dwell) a.dwell[read * nb + q] = dw;
+    }
+}
+
+// Consensus refinement behind the alignment (sig_proc.py:334-378, 500-521): second segmentation of the scores from the
+// barcode start on, event means, outlier filter, fingerprint.  cpts holds the FIRST segmentation's change points on entry.
+// Returns false when the read failed (status written).  The whole CTA calls this.
+__device__ bool cons_tail(const FpConfig& c, const FpArgs& a, FpScratch& s, int64_t read, int cap, const double* score, const float* sig,
+                          uint16_t* kp, uint8_t* state, uint32_t* bm, int* cpts, double* ev, double* dv, int n, int nc, int w,
+                          bool exact_sums, double ev_mean, double ev_std, int q_start, int q_end) {
+    const int tid = threadIdx.x;
+    const int nb = c.barcode_num_events;
+    const int sbs = cpts[q_end];  // sig_barcode_start = sum(adapter_dwell_times[:q_end]) (sig_proc.py:334)
+    peaks_scratch_clear(bm, cap, s);
+    __syncthreads();              // cpts / ev are rewritten below
+    // second segmentation on barcode_scores = adapter_scores[sbs:] with the UNCAPPED min_obs_per_base
+    // and running_stat_width (sig_proc.py:336-365)
+    const int ke = c.cons_seg_events;
+    const int P2 = (nc - sbs >= 3) ? kept_peaks_select(score, sbs, nc, c.min_obs_per_base, kp, bm, cap, ke, w - sbs /* relative to raw_signal[sbs:] */,
+                                                       cpts + 1, state, reinterpret_cast<unsigned long long*>(dv), s)
+                                   : 0;
+    if (P2 < ke) {
+        fp_fail(a, read, nb, FP_FAIL_SEGMENTATION, true);
+        return false;
+    }
+    if (tid == 0) {
+        cpts[0] = 0;
+        cpts[ke + 1] = n - sbs;   // scores.size + 2 * running_stat_width = (nc - sbs) + 2 w
+    }
+    __syncthreads();
+    fp_segment_means(sig + sbs, ke + 1, cpts, ev, exact_sums);  // compute_base_means(raw_signal[sbs:], cpts) (:368)
+    __syncthreads();
+    if (a.cons && tid == 0) {
+        a.cons[read * 3 + 0] = q_start;
+        a.cons[read * 3 + 1] = q_end;
+        a.cons[read * 3 + 2] = sbs;
+    }
+    if (q_start > c.cons_ub_start || q_end < c.cons_lb_end || q_end > c.cons_ub_end) {  // sig_proc.py:500-521
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int q = tid; q < nb; q += FP_THREADS) {
+            a.fpt[read * nb + q] = qnan;
+            if (a.dwell) a.dwell[read * nb + q] = 0;
+        }
+        if (tid == 0) a.status[read] = FP_FAIL_CONSENSUS;
+        return false;
+    }
+    fp_write_fingerprint(a, read, nb, ke + 1, cpts, ev, ev_mean, ev_std);
+    if (tid == 0) a.status[read] = FP_OK;
+    return true;
+}
+
 // CONS = consensus-guided barcode refinement (tRNA configurations, sig_proc.py:257-378, 451-521).
-template <bool CONS>
+// PHASE 0: the whole chain in one launch.  PHASE 1 (consensus only, big batches): up to the normalised event series, the
+// read's state is parked in global memory and the alignment / refinement follow as fingerprint_cons_align_kernel (many small
+// CTAs per SM: the alignment keeps three warps busy for ~40 % of a read's time here) and fingerprint_cons_tail_kernel.
+template <bool CONS, int PHASE = 0>
 #ifndef WDX_FP_MIN_CTAS
 #define WDX_FP_MIN_CTAS (1024 / FP_THREADS)
 #endif
@@ -952,15 +1099,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
     double* fpt_out = a.fpt + read * nb;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    auto fail = [&](int code) {  // whole CTA calls this (uniform)
-        for (int q = tid; q < nb; q += FP_THREADS) {
-            fpt_out[q] = qnan;
-            if (a.dwell) a.dwell[read * nb + q] = 0;
-        }
-        if (a.stats && tid < 6) a.stats[read * 6 + tid] = qnan;
-        if (CONS && a.cons && tid < 3) a.cons[read * 3 + tid] = 0;
-        if (tid == 0) a.status[read] = code;
-    };
+    auto fail = [&](int code) { fp_fail(a, read, nb, code, CONS); };  // whole CTA calls this (uniform)
 
     // the read's four scalars are requested together (one round trip to memory instead of three dependent ones)
     const uint8_t ok_in = a.detect_ok ? a.detect_ok[read] : (uint8_t)1;
@@ -1151,32 +1290,8 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         // windows over all threads: ceil(chain / 42) + 1 windows each, at ~1.3 x the instructions per window.
         const int seg_len = (nblk + FP_THREADS / 12 - 1) / (FP_THREADS / 12);
         if (seg_len <= 8) {
-            const int n_seg = (nblk + seg_len - 1) / seg_len;  // <= FP_THREADS / 12: one item per thread
-            if (tid < 12 * n_seg) {
-                int pos = tid % 12 + 12 * seg_len * (tid / 12);
-                if (pos < nc) {
-                    double m1, v1;
-                    if (exact_sums) {   // uniform
-                        window_stat_fixed<12, true>(sig + pos, 12.0, wr, m1, v1);
-                        for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
-                            double m2, v2;
-                            window_stat_fixed<12, true>(sig + pos + 12, 12.0, wr, m2, v2);
-                            score[pos] = ttest_combine(m1, v1, m2, v2);
-                            m1 = m2;
-                            v1 = v2;
-                        }
-                    } else {
-                        window_stat_fixed<12>(sig + pos, 12.0, wr, m1, v1);
-                        for (int j = 0; j < seg_len && pos < nc; j++, pos += 12) {
-                            double m2, v2;
-                            window_stat_fixed<12>(sig + pos + 12, 12.0, wr, m2, v2);
-                            score[pos] = ttest_combine(m1, v1, m2, v2);
-                            m1 = m2;
-                            v1 = v2;
-                        }
-                    }
-                }
-            }
+            if (exact_sums) ttest_residue_chains<12, true>(sig, score, nc, nblk, seg_len);   // uniform
+            else ttest_residue_chains<12, false>(sig, score, nc, nblk, seg_len);
         } else
         for (int g = warp * 31; g < nblk; g += FP_WARPS * 31) {
             const int s0 = 12 * (g + lane);
@@ -1212,6 +1327,9 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
                 if (lane < 31 && pos < nc) score[pos] = ttest_combine(m, v, m2, v2);
             }
         }
+    } else if (w == 18) {   // the tRNA configuration's width: residue-class chains (every window's statistics once)
+        const int nblk = (nc + 17) / 18;
+        ttest_residue_chains<18, false>(sig, score, nc, nblk, (nblk + FP_THREADS / 18 - 1) / (FP_THREADS / 18));
     } else {
         for (int pos = tid; pos < nc; pos += FP_THREADS) {
             double m1 = 0.0, m2 = 0.0, var1 = 0.0, var2 = 0.0;
@@ -1260,29 +1378,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
     const int n_seg = c.num_events + 1;
 
     // ---- c_new_means (_c_segmentation.pyx:41-53): sequential float64 sums; one warp per segment when the sums are exact
-    auto segment_means = [&](const float* base, int nseg) {
-        if (exact_sums) {
-            // four segments per warp and trip, eight lanes each
-            const int lane = tid & 31, warp = tid >> 5, sub = lane >> 3, sl = lane & 7;
-            for (int q0 = warp * 4; q0 < nseg; q0 += FP_WARPS * 4) {
-                const int q = q0 + sub;
-                const int b = (q < nseg) ? cpts[q] : 0, e = (q < nseg) ? cpts[q + 1] : 0;
-                double sum = 0.0;
-                for (int i = b + sl; i < e; i += 8) sum = __dadd_rn(sum, (double)base[i]);
-#pragma unroll
-                for (int o = 4; o; o >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
-                if (sl == 0 && q < nseg) ev[q] = __ddiv_rn(sum, (double)(e - b));
-            }
-        } else {
-            for (int q = tid; q < nseg; q += FP_THREADS) {
-                double sum = 0.0;
-                const int b = cpts[q], e = cpts[q + 1];
-                for (int i = b; i < e; i++) sum = __dadd_rn(sum, (double)base[i]);
-                ev[q] = __ddiv_rn(sum, (double)(e - b));
-            }
-        }
-    };
-    segment_means(sig, n_seg);
+    fp_segment_means(sig, n_seg, cpts, ev, exact_sums);
     __syncthreads();
 
     FP_T(s, 10);  // means
@@ -1334,7 +1430,6 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
         }
     };
 
-    int n_out_seg = n_seg;   // segments the fingerprint is cut from (their bounds in cpts, means in ev)
     if constexpr (CONS) {
         // ---- consensus-guided barcode refinement (sig_proc.py:257-378) ------------------------------
         // The second segmentation hands compute_base_means change points up to scores.size + 2 *
@@ -1344,74 +1439,107 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_kerne
             fail(FP_FAIL_SEGMENTATION);
             return;
         }
-        __shared__ double lastrow[FP_MAX_EVENTS + 2];
-        __shared__ int lastorg[FP_MAX_EVENTS + 2];
-        __shared__ int match[2];
         __syncthreads();
         if (tid < n_seg) dv[tid] = __ddiv_rn(__dsub_rn(ev[tid], ev_mean), ev_std);  // normalize(series, "mean")
         __syncthreads();
-        __shared__ double hand_v[2 * (FP_MAX_QUERY / 32)];
-        __shared__ int hand_o[2 * (FP_MAX_QUERY / 32)];
-        if (tid < FP_MAX_QUERY)   // FP_MAX_QUERY / 32 warps, one query row per lane
-            consensus_match_rows<FP_MAX_QUERY / 32>(a.cons_query, c.cons_len, dv, n_seg, c.cons_pen2, c.cons_psi_q, c.cons_psi_s,
-                                                    lastrow, lastorg, match, hand_v, hand_o);
-        __syncthreads();
-        const int q_start = match[0], q_end = match[1];
-        const int sbs = cpts[q_end];  // sig_barcode_start = sum(adapter_dwell_times[:q_end]) (sig_proc.py:334)
-        peaks_scratch_clear(bm, cap, s);
-        __syncthreads();              // cpts / ev are rewritten below
-        // second segmentation on barcode_scores = adapter_scores[sbs:] with the UNCAPPED min_obs_per_base
-        // and running_stat_width (sig_proc.py:336-365)
-        const int ke = c.cons_seg_events;
-        const int P2 = (nc - sbs >= 3) ? kept_peaks_select(score, sbs, nc, c.min_obs_per_base, kp, bm, cap, ke, w - sbs /* relative to raw_signal[sbs:] */,
-                                                           cpts + 1, state, reinterpret_cast<unsigned long long*>(dv), s)
-                                       : 0;
-        if (P2 < ke) {
-            fail(FP_FAIL_SEGMENTATION);
-            return;
-        }
-        if (tid == 0) {
-            cpts[0] = 0;
-            cpts[ke + 1] = n - sbs;   // scores.size + 2 * running_stat_width = (nc - sbs) + 2 w
-        }
-        __syncthreads();
-        segment_means(sig + sbs, ke + 1);  // compute_base_means(raw_signal[sbs:], cpts) (:368)
-        __syncthreads();
-        n_out_seg = ke + 1;
-        if (a.cons && tid == 0) {
-            a.cons[read * 3 + 0] = q_start;
-            a.cons[read * 3 + 1] = q_end;
-            a.cons[read * 3 + 2] = sbs;
-        }
-        if (q_start > c.cons_ub_start || q_end < c.cons_lb_end || q_end > c.cons_ub_end) {  // sig_proc.py:500-521
-            for (int q = tid; q < nb; q += FP_THREADS) {
-                fpt_out[q] = qnan;
-                if (a.dwell) a.dwell[read * nb + q] = 0;
+        write_stats();   // (a read that fails further on overwrites them with NaN, like every failed read)
+        if constexpr (PHASE == 1) {
+            unsigned char* pk_ = a.park + (size_t)read * fp_park_bytes(cap);
+            FpParkHead* hd = park_head(pk_);
+            if (tid == 0) {
+                hd->n = n;
+                hd->nc = nc;
+                hd->w = w;
+                hd->n_seg = n_seg;
+                hd->exact_sums = exact_sums ? 1 : 0;
+                hd->ev_mean = ev_mean;
+                hd->ev_std = ev_std;
+                a.status[read] = FP_PENDING;
             }
-            write_stats();
-            if (tid == 0) a.status[read] = FP_FAIL_CONSENSUS;
+            double* ps = park_score(pk_);
+            for (int i = tid; i < nc; i += FP_THREADS) ps[i] = score[i];
+            float* pg = park_sig(pk_, cap);
+            for (int i = tid; i < n; i += FP_THREADS) pg[i] = sig[i];
+            double* pr = park_series(pk_, cap);
+            int* pc = park_cpts(pk_, cap);
+            for (int i = tid; i < n_seg; i += FP_THREADS) pr[i] = dv[i];
+            for (int i = tid; i <= n_seg; i += FP_THREADS) pc[i] = cpts[i];
+            return;
+        } else {
+            __shared__ double lastrow[FP_MAX_EVENTS + 2];
+            __shared__ int lastorg[FP_MAX_EVENTS + 2];
+            __shared__ int match[2];
+            __shared__ double hand_v[2 * (FP_MAX_QUERY / 32)];
+            __shared__ int hand_o[2 * (FP_MAX_QUERY / 32)];
+            if (tid < FP_MAX_QUERY)   // FP_MAX_QUERY / 32 warps, one query row per lane
+                consensus_match_rows<FP_MAX_QUERY / 32>(a.cons_query, c.cons_len, dv, n_seg, c.cons_pen2, c.cons_psi_q, c.cons_psi_s,
+                                                        lastrow, lastorg, match, hand_v, hand_o);
+            __syncthreads();
+            cons_tail(c, a, s, read, cap, score, sig, kp, state, bm, cpts, ev, dv, n, nc, w, exact_sums, ev_mean, ev_std, match[0], match[1]);
             return;
         }
     }
     write_stats();
-
-    // ---- keep the last barcode_num_events (sig_proc.py:569-594); normalised by the mean / std of the
-    // adapter events (normalize "mean" :546-552, or normalize_wrt for the refined barcode events :482-484)
-    const int keep = min(nb, n_out_seg);
-    for (int q = tid; q < nb; q += FP_THREADS) {
-        const int srcq = n_out_seg - keep + (q - (nb - keep));
-        double v = qnan;  // front NaN padding if fewer events than asked (unreachable with accept_less_cpts=false)
-        int64_t dw = 0;
-        if (q >= nb - keep) {
-            v = __ddiv_rn(__dsub_rn(ev[srcq], ev_mean), ev_std);
-            dw = (int64_t)(cpts[srcq + 1] - cpts[srcq]);
-        }
-        fpt_out[q] = v;
-        if (a.dwell) a.dwell[read * nb + q] = dw;
-    }
+    fp_write_fingerprint(a, read, nb, n_seg, cpts, ev, ev_mean, ev_std);
     FP_T(s, 12);  // stats + output
     FP_T_END(s);
     if (tid == 0) a.status[read] = FP_OK;
+}
+
+// ---- three-launch consensus form, second kernel: the sub-sequence alignment alone.  One small CTA per read (one query row
+// per lane over FP_MAX_QUERY / 32 warps), so that an SM holds many alignments at once: the 200 dependent anti-diagonal
+// steps of one read are latency, not work.
+template <int NW>   // warps = ceil(query length / 32)
+__global__ void __launch_bounds__(NW * 32) fingerprint_cons_align_kernel(const __grid_constant__ FpConfig c, const __grid_constant__ FpArgs a) {
+    __shared__ double series[FP_MAX_EVENTS + 2];
+    __shared__ double lastrow[FP_MAX_EVENTS + 2];
+    __shared__ int lastorg[FP_MAX_EVENTS + 2];
+    __shared__ int match[2];
+    __shared__ double hand_v[2 * NW];
+    __shared__ int hand_o[2 * NW];
+    const int64_t read = blockIdx.x;
+    if (read >= a.n || a.status[read] != FP_PENDING) return;
+    unsigned char* pk_ = a.park + (size_t)read * fp_park_bytes(a.cap);
+    FpParkHead* hd = park_head(pk_);
+    const int n_seg = hd->n_seg;
+    const double* pr = park_series(pk_, a.cap);
+    for (int i = threadIdx.x; i < n_seg; i += NW * 32) series[i] = pr[i];
+    __syncthreads();
+    consensus_match_rows<NW>(a.cons_query, c.cons_len, series, n_seg, c.cons_pen2, c.cons_psi_q, c.cons_psi_s, lastrow, lastorg,
+                                            match, hand_v, hand_o);
+    __syncthreads();
+    if (threadIdx.x < 2) hd->match[threadIdx.x] = match[threadIdx.x];
+}
+
+// ---- third kernel: the refinement behind the alignment on the parked state (same CTA shape and shared-memory layout as
+// fingerprint_kernel).
+__global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_cons_tail_kernel(const __grid_constant__ FpConfig c,
+                                                                                             const __grid_constant__ FpArgs a) {
+    extern __shared__ __align__(16) unsigned char fp_smem[];
+    const int cap = a.cap;
+    double* score = reinterpret_cast<double*>(fp_smem);
+    float* sig = reinterpret_cast<float*>(fp_smem + (size_t)cap * 8);
+    uint16_t* kp = reinterpret_cast<uint16_t*>(fp_smem + (size_t)cap * 12 + 32);
+    uint8_t* state = fp_smem + (size_t)cap * 12 + 32 + ((size_t)(cap / 2 + 8) * 2);
+    uint32_t* bm = reinterpret_cast<uint32_t*>(fp_smem + (size_t)cap * 12 + 32 + ((size_t)(cap / 2 + 8) * 3));
+    __shared__ FpScratch s;
+    __shared__ int cpts[FP_MAX_EVENTS + 2];
+    __shared__ double ev[FP_MAX_EVENTS + 2];
+    __shared__ double dv[FP_MAX_EVENTS + 2];
+    const int tid = threadIdx.x;
+    const int64_t read = blockIdx.x;
+    if (read >= a.n || a.status[read] != FP_PENDING) return;
+    unsigned char* pk_ = a.park + (size_t)read * fp_park_bytes(cap);
+    const FpParkHead hd = *park_head(pk_);
+    const double* ps = park_score(pk_);
+    for (int i = tid; i < hd.nc; i += FP_THREADS) score[i] = ps[i];
+    const float* pg = park_sig(pk_, cap);
+    for (int i = tid; i < hd.n; i += FP_THREADS) sig[i] = pg[i];
+    const int* pc = park_cpts(pk_, cap);
+    for (int i = tid; i <= hd.n_seg; i += FP_THREADS) cpts[i] = pc[i];
+    __syncthreads();
+    cons_tail(c, a, s, read, cap, score, sig, kp, state, bm, cpts, ev, dv, hd.n, hd.nc, hd.w, hd.exact_sums != 0, hd.ev_mean, hd.ev_std,
+              hd.match[0], hd.match[1]);
 }
 
 // Longest adapter slice of a batch whose bounds live in device memory (sizes the shared memory).

@@ -25,6 +25,7 @@ struct wdx_fp {
     DevBuf sig[2], len[2], a0[2], a1[2], ok[2], maxlen;
     DevBuf fpt[2], dwell[2], stats[2], status[2], lab[2], conf[2], prob[2], flags[2], cons[2];
     DevBuf cons_query;                   // consensus query (consensus-guided mode)
+    DevBuf park;                         // three-launch consensus form: the reads' state between the kernels
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;
     size_t tev_used = 0;
@@ -59,6 +60,12 @@ bool zero_copy_disabled() {
     return off;
 }
 
+constexpr int64_t FP_SPLIT_MIN_READS = 2048;   // below: one launch (lower latency); above: the three-launch consensus form
+bool split_disabled() {
+    const char* e = getenv("WDX_FP_NO_SPLIT");
+    return e && *e && *e != '0';
+}
+
 int launch_fp(wdx_fp* f, const FpArgs& fa, cudaStream_t st) {
     const size_t smem = fingerprint_smem_bytes(fa.cap);
     if ((int)smem > f->smem_max) return fail(WDX_ERR_UNSUPPORTED, "adapter slice of %d samples needs %zu B of shared memory, device allows %d", fa.cap, smem, f->smem_max);
@@ -75,8 +82,26 @@ int launch_fp(wdx_fp* f, const FpArgs& fa, cudaStream_t st) {
         f->tev_used++;
         CUDA_TRY(cudaEventRecord(e0, st));
     }
-    if (f->cfg.cons_len > 0) fingerprint_kernel<true><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
-    else fingerprint_kernel<false><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
+    if (f->cfg.cons_len > 0 && fa.park && fa.retry_status == 0) {
+        // big consensus batches: front part, alignment (small CTAs, many per SM), refinement — see fingerprint_kernel
+        fingerprint_kernel<true, 1><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
+        CUDA_TRY(cudaGetLastError());
+        switch ((f->cfg.cons_len + 31) / 32) {
+            case 1: fingerprint_cons_align_kernel<1><<<(unsigned)fa.n, 32, 0, st>>>(f->cfg, fa); break;
+            case 2: fingerprint_cons_align_kernel<2><<<(unsigned)fa.n, 64, 0, st>>>(f->cfg, fa); break;
+            case 3: fingerprint_cons_align_kernel<3><<<(unsigned)fa.n, 96, 0, st>>>(f->cfg, fa); break;
+            default: fingerprint_cons_align_kernel<4><<<(unsigned)fa.n, 128, 0, st>>>(f->cfg, fa); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        fingerprint_cons_tail_kernel<<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
+        g_launches += 2;
+    } else if (f->cfg.cons_len > 0) {
+        FpArgs fw = fa;
+        fw.park = nullptr;
+        fingerprint_kernel<true><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fw);
+    } else {
+        fingerprint_kernel<false><<<(unsigned)fa.n, FP_THREADS, smem, st>>>(f->cfg, fa);
+    }
     CUDA_TRY(cudaGetLastError());
     if (f->timing) CUDA_TRY(cudaEventRecord(e1, st));
     g_launches++;
@@ -176,6 +201,7 @@ int run(wdx_fp* f, const FpCall& c) {
     int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / (c.stride * 4));
     if (sig_dev) chunk = (int64_t)1 << 20;
     if (c.m) chunk = std::min<int64_t>(chunk, c.m->chunk_reads);
+    if (f->cfg.cons_len > 0) chunk = std::min<int64_t>(chunk, (int64_t)1 << 15);   // bounds the parked state (~70 KB per read)
     chunk = std::min(chunk, c.n);
     const int64_t n_chunks = (c.n + chunk - 1) / chunk;
     const int nbuf = n_chunks > 1 ? 2 : 1;
@@ -241,6 +267,11 @@ int run(wdx_fp* f, const FpCall& c) {
         fa.status = status_dev ? c.status + r0 : (int32_t*)f->status[b].p;
         fa.cons_query = (const double*)f->cons_query.p;
         fa.cons = c.cons ? (cons_dev ? c.cons + (size_t)r0 * 3 : (int32_t*)f->cons[b].p) : nullptr;
+        fa.park = nullptr;
+        if (f->cfg.cons_len > 0 && cn >= FP_SPLIT_MIN_READS && !split_disabled()) {
+            if ((rc = f->park.reserve((size_t)cn * fp_park_bytes(cap)))) return rc;
+            fa.park = (unsigned char*)f->park.p;
+        }
         fa.retry_status = resume_status;
         if ((rc = launch_fp(f, fa, st))) return rc;
         fa.retry_status = 0;
@@ -337,6 +368,10 @@ int wdx_fp_create(const wdx_fp_config* cfg, int device, wdx_fp** out) {
         if (cudaFuncSetAttribute((const void*)fingerprint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  f->smem_max) != cudaSuccess ||
             cudaFuncSetAttribute((const void*)fingerprint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 f->smem_max) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)fingerprint_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 f->smem_max) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)fingerprint_cons_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  f->smem_max) != cudaSuccess) {
             delete f;
             return fail(WDX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -1531,12 +1531,15 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_FP_MIN_CTAS) fingerprint_cons_
     if (read >= a.n || a.status[read] != FP_PENDING) return;
     unsigned char* pk_ = a.park + (size_t)read * fp_park_bytes(cap);
     const FpParkHead hd = *park_head(pk_);
-    const double* ps = park_score(pk_);
-    for (int i = tid; i < hd.nc; i += FP_THREADS) score[i] = ps[i];
-    const float* pg = park_sig(pk_, cap);
-    for (int i = tid; i < hd.n; i += FP_THREADS) sig[i] = pg[i];
     const int* pc = park_cpts(pk_, cap);
     for (int i = tid; i <= hd.n_seg; i += FP_THREADS) cpts[i] = pc[i];
+    // only what lies behind the barcode start is looked at again (scores from sbs - 1: the left neighbour of the first candidate)
+    const int q_end_ = min(max(hd.match[1], 0), hd.n_seg);
+    const int from = max(0, min(pc[q_end_], hd.nc) - 1);
+    const double* ps = park_score(pk_);
+    for (int i = from + tid; i < hd.nc; i += FP_THREADS) score[i] = ps[i];
+    const float* pg = park_sig(pk_, cap);
+    for (int i = from + tid; i < hd.n; i += FP_THREADS) sig[i] = pg[i];
     __syncthreads();
     cons_tail(c, a, s, read, cap, score, sig, kp, state, bm, cpts, ev, dv, hd.n, hd.nc, hd.w, hd.exact_sums != 0, hd.ev_mean, hd.ev_std,
               hd.match[0], hd.match[1]);

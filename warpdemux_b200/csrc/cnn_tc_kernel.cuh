@@ -29,7 +29,15 @@
 
 namespace wdx {
 
-constexpr int TC_THREADS = 256;
+// 8 warps.  16 warps (-DWDX_TC_THREADS=512: conv1 interleaved over two warps per channel group, epilogue columns in four groups)
+// make the kernel itself 3 % faster (1.60 -> 1.55 ms per 8 000 reads) but take the whole register file of every SM, so the
+// prepare / argmax kernels of the other chunks no longer run next to it: CNN stage 1.93 -> 2.20 ms.  Measured, kept off.
+#ifndef WDX_TC_THREADS
+#define WDX_TC_THREADS 256
+#endif
+constexpr int TC_THREADS = WDX_TC_THREADS;
+constexpr int TC_WARPS = TC_THREADS / 32;
+static_assert(TC_THREADS == 256 || TC_THREADS == 512, "epilogue column split: 2 or 4 column groups of 32 / 16");
 constexpr int TC_MAX_TILES = 5;                              // 128-row M tiles per read (640 hidden positions: the 18 500-sample preload)
 constexpr int TC_MAX_T1 = TC_MAX_TILES * 128;
 constexpr int TC_W_HALF = CNN_C * CNN_C * 2;                 // 8 192 B: one tap, one split
@@ -171,6 +179,20 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&r)[32]) { tc_ld32(taddr, r); }
+__device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&r)[16]) { tc_ld16(taddr, r); }
+
 // fp16 hi/lo split of 8 consecutive channels -> two 16-byte vectors
 __device__ __forceinline__ void tc_split8(const float (&v)[8], uint4* hi, uint4* lo, bool* range) {
     uint32_t h[4], l[4];
@@ -294,16 +316,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         }
         __syncthreads();
         bool range = false;
-        {   // warp w owns channels 8w..8w+7 (weights in registers); lanes walk the time positions
+        {   // warp w owns channels 8 (w & 7) .. + 7 (weights in registers); lanes walk the time positions, the warps of a
+            // channel group interleaved in blocks of 32
+            const int cg = warp & 7;
             float wr[8][CNN_K], br[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                br[q] = b0_s[warp * 8 + q];
+                br[q] = b0_s[cg * 8 + q];
 #pragma unroll
-                for (int k = 0; k < CNN_K; k++) wr[q][k] = w0_s[(warp * 8 + q) * CNN_K + k];
+                for (int k = 0; k < CNN_K; k++) wr[q][k] = w0_s[(cg * 8 + q) * CNN_K + k];
             }
-            unsigned char* col = A + warp * TC_LBO + CNN_P * 16;
-            for (int t = lane; t < T1; t += 32) {
+            unsigned char* col = A + cg * TC_LBO + CNN_P * 16;
+            for (int t = lane + 32 * (warp >> 3); t < T1; t += 32 * (TC_WARPS / 8)) {
                 float xv[CNN_K];
 #pragma unroll
                 for (int k = 0; k < CNN_K; k++) xv[k] = xs[t * CNN_S + k];
@@ -370,16 +394,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
             tc_fence_after();
 
             // ---- epilogue: TMEM -> registers -> bias, ReLU -> next operand ------------------------------
-            const int g = warp & 3, hc = warp >> 2;  // TMEM lane group of this warp, column half
-            const float* bias = (layer == 0 ? b1_s : b2_s) + hc * 32;
+            constexpr int EC = CNN_C / (TC_WARPS / 4);   // columns per warp: 32 (8 warps) or 16 (16 warps)
+            const int g = warp & 3, hc = warp >> 2;     // TMEM lane group of this warp, column group
+            const float* bias = (layer == 0 ? b1_s : b2_s) + hc * EC;
             const float sc = a.inv_wscale;
 #pragma unroll 1
             for (int m = 0; m < m_tiles; m++) {
-                uint32_t r[32];
-                tc_ld32(tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(m * CNN_C + hc * 32), r);
+                uint32_t r[EC];
+                tc_ld(tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(m * CNN_C + hc * EC), r);
                 const int t = m * 128 + g * 32 + lane;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {   // both layers: the result is the next MMA's operand A (fp16 hi + lo, in place)
+                for (int c4 = 0; c4 < EC / 8; c4++) {   // both layers: the result is the next MMA's operand A (fp16 hi + lo, in place)
                     float v[8];
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
@@ -388,7 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     }
                     uint4 hi, lo;
                     tc_split8(v, &hi, &lo, &range);
-                    unsigned char* p = A + (hc * 4 + c4) * TC_LBO + (t + CNN_P) * 16;
+                    unsigned char* p = A + (hc * (EC / 8) + c4) * TC_LBO + (t + CNN_P) * 16;
                     *reinterpret_cast<uint4*>(p) = hi;
                     *reinterpret_cast<uint4*>(p + TC_A_SPLIT) = lo;
                 }
@@ -443,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
             float* s1 = a.scores + (read * 2 + 1) * d.To;
             const float bb0 = b3_s[0], bb1 = b3_s[1], sct = a.inv_ctscale;
             const int g = warp & 3;
-            for (int m = warp >> 2; m < q_tiles; m += 2) {
+            for (int m = warp >> 2; m < q_tiles; m += TC_WARPS / 4) {
                 uint32_t r[8];
                 tc_ld8(tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(TC_CT_COL0 + m * TC_CT_N), r);
                 const int q = m * 128 + g * 32 + lane;

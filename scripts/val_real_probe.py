@@ -42,6 +42,20 @@ with torch.cuda.stream(side):
             t = ev[0].elapsed_time(ev[1])
             best = t if best is None or (it and t < best) else best
         out[name + "_ms"] = round(best, 4)
+        from warpdemux_b200 import _lib
+        L = _lib.load()
+        if name == "verdict_only" and hasattr(L, "wdx_validate_prof_dump"):   # -DWDX_FP_PROF build: cycles per phase and read
+            import ctypes as C
+            buf = (C.c_uint64 * 32)()
+            L.wdx_validate_prof_dump(None, 1)
+            v.run_raw(d_sig, n, stride, d_len, d_preds, 1 + k, d_suc, d_info, d_bounds, None, stream=sp)
+            side.synchronize()
+            L.wdx_validate_prof_dump(buf, 0)
+            names = ["load", "1a", "1b", "focus", "1c", "A_hist", "A_scan", "A_gather", "A_rank", "A_results", "B_hist", "B_scan", "B_gather",
+                     "B_rank+setup", "verdict", "rest"]
+            ph = {nm: round(buf[i] / n) for i, nm in enumerate(names)}
+            ph["sum"] = sum(ph.values())
+            out["cycles_per_read"] = ph
         out[name + "_ok"] = int(d_suc.sum().item())
         out[name + "_chk"] = int((d_bounds.sum() + d_info[:, 0].sum()).item())
         v.close()

@@ -786,9 +786,10 @@ __device__ __forceinline__ void ms_rank_all(MsState& ms) {
 // On return (after a barrier) ms.q_key[q] holds the order key (or the code) of every rank.  `extra_*` let the caller run
 // its own work inside the phases of the round (no barrier of its own needed).
 template <typename F1, typename F2, typename F3>
-__device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_hist, F2 extra_scan, F3 extra_gather) {
+__device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_hist, F2 extra_scan, F3 extra_gather, int pb = 5) {
     const int warp = threadIdx.x >> 5;
     const int nj = ms.nj, nq = ms.nq;
+    (void)pb;   // phase-clock slots of this round (WDX_FP_PROF builds)
     for (int jj = 0; jj < nj; jj++) {
         const MsJob& j = ms.job[jj];
         if (j.mode == 0) ms_hist_pass<0>(j, ms.hist[jj]);
@@ -796,9 +797,11 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
     }
     extra_hist();
     __syncthreads();
+    FP_T(s, pb + 0);   // histogram pass
     if (warp < nj) ms_scan_job(ms, warp);
     extra_scan();
     __syncthreads();
+    FP_T(s, pb + 1);   // scans
     for (int jj = 0; jj < nj; jj++) {
         const MsJob& j = ms.job[jj];
         if (j.mode == 0) ms_gather_pass<0>(j, ms, ms.hist[jj]);
@@ -806,8 +809,10 @@ __device__ __forceinline__ void ms_round(MsState& ms, FpScratch& s, F1 extra_his
     }
     extra_gather();
     __syncthreads();
+    FP_T(s, pb + 2);   // gather pass
     ms_rank_all(ms);
     __syncthreads();
+    FP_T(s, pb + 3);   // ranking
     if (ms.crowded) {     // uniform; degenerate data only
         for (int q = 0; q < nq; q++) {
             if (ms.q_slot[q] >= 0) continue;
@@ -1075,6 +1080,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     };
     const double inv_wv = 1.0 / (double)wv, inv_wm = 1.0 / (double)wm;
 
+    FP_T(s, 1);   // phase 1a
     // ---- phase 1b: samples for the focus (every eighth thread's first window), real_range_check's two means
     if ((tid & 7) == 0) {
         int cv = -1, cm = -1;
@@ -1101,6 +1107,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     }
     __syncthreads();
 
+    FP_T(s, 2);   // phase 1b
     // ---- focus of the two code histograms: the 25 % / 75 % quantiles of the samples (the middle ranks lie 4 sigma inside;
     // a miss only costs the exact evaluation of every window).  Warps 0-1: variance, warps 2-3: mean.  Histograms cleared.
     uint32_t* hz = &ms.hist[0][0];
@@ -1124,6 +1131,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     }
     __syncthreads();
 
+    FP_T(s, 3);   // focus
     // ---- phase 1c: every window's approximation -> bin -> histogram; the jobs of round A are set up next to it
     const int flo_v = sh_i[8], flo_m = sh_i[10];
     int fsh_v = 0, fsh_m = 2;               // the mean's codes are 1 ulp apart: a bin of >= 4 ulp keeps the +-1-bin band safe
@@ -1234,6 +1242,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     }
     __syncthreads();
 
+    FP_T(s, 4);   // phase 1c
     // ---- round A: every selection on samples that does not need another one's result; two more warps find the bins of
     // the middle ranks of the two code histograms
     const uint32_t rkv0 = (uint32_t)((cntv - 1) / 2), rkv1 = (uint32_t)(cntv / 2);
@@ -1282,6 +1291,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
     const int bm_lo = all_m ? 0 : max(0, c8.b_lo[1] - 1), bm_hi = all_m ? 255 : min(255, c8.b_hi[1] + 1);
     __syncthreads();      // everyone has read the results of round A
 
+    FP_T(s, 9);   // results of round A
     // ---- round B: the adapter MAD (needs the median) and the exact evaluation of the windows around the middle
     for (int i = tid; i < MS_BINS / 2; i += FP_THREADS) hz[i] = 0;
     if (tid < MS_MAXS) ms.slot_n[tid] = 0;
@@ -1344,7 +1354,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
         [&] {   // next to the gather: exact ranking inside the bands
             band_rank(bd, rkv0, rkv1, tid, FP_THREADS);
             band_rank(bdm, rkm0, rkm1, FP_THREADS - 1 - tid, FP_THREADS);
-        });
+        }, 10);
     bool band_ok, mband_ok;
     {
         const int nb = bd.n, r0 = (int)rkv0 - bd.below, r1 = (int)rkv1 - bd.below;
@@ -1362,6 +1372,7 @@ __device__ __noinline__ void val_fast(const ValArgs& a, const ValCfg& c, const f
         if (!mband_ok) r_mean = (double)val_window_median<false>(vsig, e, m, wm, scratch, bd, vs_old, s);
     }
 
+    FP_T(s, 13);  // round B incl. its set-up
     // ---- the verdict, in the reference's order (combined.py:452-629)
     if (tid == 0) {
         int code = VAL_OK, checks = 0, resume = 0;
@@ -1455,7 +1466,10 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
     unsigned char* bins8 = reinterpret_cast<unsigned char*>(vsig + ((a.stride + 3) & ~(int64_t)3));   // [2 * stride]
 
     __shared__ unsigned long long sh_next;
+    FP_T_BEGIN(s);
     for (;;) {
+        FP_T(s, 15);   // rest of the previous read (sequential path, reports)
+        FP_T_END(s);
         __syncthreads();
         if (tid == 0) {
             unsigned long long nx = atomicAdd(a.next, 1ULL);
@@ -1478,6 +1492,7 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         __syncthreads();
         const int64_t r = (int64_t)sh_next;
         if (r >= a.n) break;
+        FP_T_BEGIN(s);
         const float* row = a.signals + (size_t)r * a.stride;
         const int64_t fl = a.full_len[r];
         const int L = (int)max((int64_t)0, min(fl, a.stride));
@@ -1514,10 +1529,12 @@ __global__ void __launch_bounds__(FP_THREADS, WDX_VAL_MIN_CTAS) validate_kernel(
         const int hi = (int)max((int64_t)0, min(a1, (int64_t)L));   // sig[a0:a1] ends here
         float med = 0.f, mad = 0.f;
         int pores_cnt = -1, pores_single = 0;   // open_pores as the reference reports it: None / the kept positions
+        FP_T(s, 0);   // row load + range scan
         const bool use_fast = fast && code == VAL_OK;
         int resume = 0;                        // poly(A) candidates from here on go through the sequential loop
         if (use_fast) {
             val_fast(a, c, vsig, bins8, L, fl, pr, seg, shu.ms, c8, band, band2, s, sh_i, sh_pores, sh_d, sh_v, scratch, vs, fo);
+            FP_T(s, 14);  // verdict
             code = fo.code;
             checks = fo.checks;
             n_pores = fo.n_pores;

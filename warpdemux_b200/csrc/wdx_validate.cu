@@ -425,4 +425,15 @@ int wdx_validate_run_report(wdx_validate* h, const float* signals, int64_t n, in
     return WDX_OK;
 }
 
+#ifdef WDX_FP_PROF
+// experiments only: cycles per phase of validate_kernel summed over all reads since the last reset
+int wdx_validate_prof_dump(unsigned long long* out32, int reset) {
+    if (out32) CUDA_TRY(cudaMemcpyFromSymbol(out32, wdx::g_fp_prof, 32 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long z[32] = {};
+        CUDA_TRY(cudaMemcpyToSymbol(wdx::g_fp_prof, z, sizeof z));
+    }
+    return WDX_OK;
+}
+#endif
 }  // extern "C"

@@ -80,6 +80,109 @@ struct LlrShared {
     double dres[2];
 };
 
+// ---- numpy's pairwise sum of a float64 array of a few hundred elements, in parallel (np.nanstd of the LLR trace) --------
+// np.add.reduce halves the array recursively (left half rounded down to a multiple of 8) until a block has <= 128 elements:
+// thread 0 lists the leaf blocks in order, one WARP sums each leaf (the eight block accumulators in eight lanes), thread 0
+// adds the leaf sums up the same tree.  Same additions in the same order as the serial np_pairwise<double>.
+constexpr int LLR_MAX_LEAVES = 64;
+struct LlrTree {
+    int n_leaves;
+    int off[LLR_MAX_LEAVES];
+    short len[LLR_MAX_LEAVES];
+    double sum[LLR_MAX_LEAVES];
+    double result;
+};
+__device__ void llr_tree_build(int n, LlrTree& t) {   // one thread
+    int lo_s[24], n_s[24], sp = 0, nl = 0;
+    lo_s[sp] = 0;
+    n_s[sp++] = n;
+    while (sp > 0) {
+        const int lo = lo_s[--sp], m = n_s[sp];
+        if (m <= 128) {
+            if (nl < LLR_MAX_LEAVES) {
+                t.off[nl] = lo;
+                t.len[nl] = (short)m;
+            }
+            nl++;
+        } else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            lo_s[sp] = lo + n2;      // right half (popped second)
+            n_s[sp++] = m - n2;
+            lo_s[sp] = lo;           // left half (popped first)
+            n_s[sp++] = n2;
+        }
+    }
+    t.n_leaves = nl;
+}
+__device__ double llr_tree_combine(int n, const LlrTree& t) {   // one thread; same walk, leaf sums consumed in order
+    struct Frame {
+        int n, state;
+        double left;
+    };
+    Frame st[24];
+    int sp = 0, next = 0;
+    st[sp++] = Frame{n, 0, 0.0};
+    double result = 0.0;
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        int n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.n <= 128) {
+            result = t.sum[next++];
+            sp--;
+        } else if (f.state == 0) {
+            f.state = 1;
+            st[sp++] = Frame{n2, 0, 0.0};
+        } else if (f.state == 1) {
+            f.left = result;
+            f.state = 2;
+            st[sp++] = Frame{f.n - n2, 0, 0.0};
+        } else {
+            result = __dadd_rn(f.left, result);
+            sp--;
+        }
+    }
+    return result;
+}
+// np_pairwise_leaf<double> (n <= 128) by one warp: lane j < 8 owns accumulator j; every lane returns the sum
+template <typename F>
+__device__ __forceinline__ double warp_np_leaf_f64(int lo, int n, F at) {
+    const int lane = threadIdx.x & 31;
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r = __dadd_rn(r, at(lo + i));
+        return r;
+    }
+    const int n8 = n - (n % 8);
+    double r = 0.0;
+    if (lane < 8) {
+        r = at(lo + lane);
+        for (int i = 8 + lane; i < n8; i += 8) r = __dadd_rn(r, at(lo + i));
+    }
+    const unsigned full = 0xffffffffu;
+    const double r0 = __shfl_sync(full, r, 0), r1 = __shfl_sync(full, r, 1), r2 = __shfl_sync(full, r, 2), r3 = __shfl_sync(full, r, 3),
+                 r4 = __shfl_sync(full, r, 4), r5 = __shfl_sync(full, r, 5), r6 = __shfl_sync(full, r, 6), r7 = __shfl_sync(full, r, 7);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (int i = n8; i < n; i++) res = __dadd_rn(res, at(lo + i));
+    return res;
+}
+// Sum of f(lo + i), i < n, in numpy's order; the tree for this n must have been built (llr_tree_build + barrier).
+template <typename F>
+__device__ double block_np_sum_f64(int lo, int n, F f, LlrTree& t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < t.n_leaves; k += FP_WARPS) {
+        const double sum = warp_np_leaf_f64(lo + t.off[k], (int)t.len[k], f);
+        if (lane == 0) t.sum[k] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) t.result = llr_tree_combine(n, t);
+    __syncthreads();
+    const double r = t.result;
+    __syncthreads();
+    return r;
+}
+
 __device__ __forceinline__ double llr_var_c(int start, int end, const double* c, const double* c2) {   // _c_llr.pyx:24-38
     if (start == end) return 0.0;
     if (start == 0) {
@@ -508,10 +611,26 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
                 __syncthreads();
                 int cnt = 0;
                 if (nc > 0) {
-                    if (tid == 0) {   // np.nanstd(clip): np.var's two pairwise sums; NaN entries count as absent
-                        int n_nan = 0;
-                        for (int i = 0; i < nc; i++) n_nan += g[t_start + i] != g[t_start + i];
-                        const double cntd = (double)(nc - n_nan);
+                    // np.nanstd(clip): np.var's two pairwise sums; NaN entries count as absent.  By the CTA (leaf blocks of
+                    // numpy's recursion summed by warps) — one thread took ~2 x nc dependent steps here with 511 waiting.
+                    __shared__ LlrTree tree;
+                    int n_nan = 0;
+                    for (int i0 = 0; i0 < nc; i0 += FP_THREADS) {
+                        const int i = i0 + tid;
+                        n_nan += __syncthreads_count(i < nc && g[t_start + i] != g[t_start + i]);
+                    }
+                    const double cntd = (double)(nc - n_nan);
+                    if (tid == 0) llr_tree_build(nc, tree);
+                    __syncthreads();
+                    if (tree.n_leaves <= LLR_MAX_LEAVES) {    // uniform
+                        const double mean = __ddiv_rn(block_np_sum_f64(t_start, nc, [&](int i) { return g[i] != g[i] ? 0.0 : g[i]; }, tree), cntd);
+                        const double ss = block_np_sum_f64(t_start, nc, [&](int i) {
+                            if (g[i] != g[i]) return 0.0;
+                            const double d = __dsub_rn(g[i], mean);
+                            return __dmul_rn(d, d);
+                        }, tree);
+                        if (tid == 0) sh.dres[0] = sqrt(__ddiv_rn(ss, cntd));
+                    } else if (tid == 0) {
                         const double mean = __ddiv_rn(np_pairwise<double>(t_start, nc, [&](int i) { return g[i] != g[i] ? 0.0 : g[i]; }), cntd);
                         const double ss = np_pairwise<double>(t_start, nc, [&](int i) {
                             if (g[i] != g[i]) return 0.0;

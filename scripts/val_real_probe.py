@@ -56,6 +56,16 @@ with torch.cuda.stream(side):
             ph = {nm: round(buf[i] / n) for i, nm in enumerate(names)}
             ph["sum"] = sum(ph.values())
             out["cycles_per_read"] = ph
+        if name == "verdict_only_llr" and hasattr(L, "wdx_validate_prof_dump"):   # slots 16.. : the LLR kernel, per read that reaches it
+            import ctypes as C
+            buf = (C.c_uint64 * 32)()
+            L.wdx_validate_prof_dump(None, 1)
+            v.run_raw(d_sig, n, stride, d_len, d_preds, 1 + k, d_suc, d_info, d_bounds, None, stream=sp)
+            side.synchronize()
+            L.wdx_validate_prof_dump(buf, 0)
+            lnames = ["row+medmad", "downscale", "cumsum", "gains+start_end", "nanstd", "find_peaks", "plateau", "split_peak", "gains2+polya", "rest"]
+            nl = max(1, int(((d_info[:, 3] & 12) != 0).sum().item()))
+            out["llr_cycles_per_llr_read_both_stages"] = {nm: round(buf[16 + i] / nl) for i, nm in enumerate(lnames)}
         out[name + "_ok"] = int(d_suc.sum().item())
         out[name + "_chk"] = int((d_bounds.sum() + d_info[:, 0].sum()).item())
         v.close()

@@ -473,7 +473,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
     w.keep = reinterpret_cast<uint8_t*>(w.order + pcap);
     float* vsig = reinterpret_cast<float*>(llr_smem + ((size_t)a.nmax * 32 + (size_t)pcap * 25 + 15) / 16 * 16);
 
+    FP_T_BEGIN(s);
     for (;;) {
+        FP_T(s, 25);   // rest of the previous read
+        FP_T_END(s);
         __syncthreads();
         if (tid == 0) {
             const unsigned long long i = atomicAdd(a.next, 1ULL);
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
         __syncthreads();
         const int64_t r = (int64_t)sh_next;
         if (r >= a.n) break;
+        FP_T_BEGIN(s);
         const float* row = a.signals + (size_t)r * a.stride;
         const int64_t fl = a.full_len[r];
         const int Lt = (int)max((int64_t)0, min(min((int64_t)c.max_obs_trace, fl), min(a.stride, (int64_t)a.lt_max)));
@@ -525,6 +529,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
             if (tid == 0 && a.pass_list) a.pass_list[atomicAdd(a.pass_count, 1)] = (int)r;
             continue;
         }
+        FP_T(s, 16);   // row + median / MAD
         // clip bounds: python floats (float64), cast once to float32 by np.clip; (clip - med) / mad in float32
         const double tm = __dmul_rn((double)mad, c.outlier_thresh);
         const float lo = (float)__dsub_rn((double)med, tm), hi = (float)__dadd_rn((double)med, tm);
@@ -542,6 +547,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
             xs[j] = (double)__fdiv_rn(sum, (float)c.factor);
         }
         __syncthreads();
+        FP_T(s, 17);   // downscaling
         // c = cumsum(x), c2 = cumsum(x * x): sequential float64 adds (two warps, one each); the loads of eight terms are
         // issued before their dependent chain of adds
         if (tid == 0 || tid == 32) {
@@ -568,6 +574,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
         }
         __syncthreads();
 
+        FP_T(s, 18);   // cumulative sums
         int bits = 0;
         if (hm) {
             bits = LLR_BIT_HM_RAN;
@@ -609,6 +616,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
                 const int t_start = sh.end < 0 ? 0 : sh.start, t_end = sh.end < 0 ? m - 1 : sh.end;
                 const int nc = t_end - t_start;          // trace.signal[start:end]
                 __syncthreads();
+                FP_T(s, 19);   // gains + trace start / end
                 int cnt = 0;
                 if (nc > 0) {
                     // np.nanstd(clip): np.var's two pairwise sums; NaN entries count as absent.  By the CTA (leaf blocks of
@@ -640,9 +648,11 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
                         sh.dres[0] = sqrt(__ddiv_rn(ss, cntd));
                     }
                     __syncthreads();
+                    FP_T(s, 20);   // nanstd
                     const double pmin = __dmul_rn(c.peak_prominence, sh.dres[0]);
                     cnt = llr_find_peaks(g + t_start, nc, 0, pmin, (double)c.peak_width, c.peak_rel_height, w, sh, s);
                 }
+                FP_T(s, 21);   // find_peaks of the trace
                 if (cnt > 0) {
                     int peak = sh.first[0] + t_start;
                     __syncthreads();
@@ -662,6 +672,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
                         if (sh.found >= 0) peak += sh.found + 9;
                         __syncthreads();
                     }
+                    FP_T(s, 22);   // plateau correction
                     {   // correct_for_split_peak(trace, peak, s = 10, t = 0.9, window = 500, prominence = 1.0)
                         const int wl = min(peak + 500, m) - peak;
                         const int c2n = llr_find_peaks(g + peak, wl, 0, 1.0, 10.0, 0.5, w, sh, s);
@@ -671,6 +682,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
                         }
                         __syncthreads();
                     }
+                    FP_T(s, 23);   // split-peak correction
                     if (peak > 0) {
                         a_ds = peak;
                         llr_gains(cs, c2, m, a_ds, m - 1, 1, 1, g);
@@ -678,6 +690,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) llr_kernel(const LlrArgs a, con
                     }
                 }
             }
+            FP_T(s, 24);   // second gains + poly(A) peak
             if (a_ds > 0) {
                 if (tid == 0) {
                     po[0] = (int64_t)a_ds * c.factor;

@@ -94,6 +94,41 @@ def test_samples_whose_sums_are_not_exact(fp):
     _same(fp.extract(sig, a0, a1), status, fpt, dwell, stats)
 
 
+def _tie_signals():
+    """Noise-free periodic level patterns: hundreds of t-test scores repeat bit for bit, so local maxima form plateaus, peaks
+    closer than the distance tie, the top-k threshold falls among equal scores and its histogram bin is crowded."""
+    rows, a0, a1 = [], [], []
+    rng = np.random.default_rng(3)
+    for period, levels in [(16, (60, 90)), (24, (60, 90, 75)), (13, (60, 95)), (40, (55, 80, 100, 70)), (9, (60, 90)), (31, (62, 88, 74))]:
+        for total in (3000, 5200):
+            seg = period // len(levels)
+            pat = np.concatenate([np.full(seg if i < len(levels) - 1 else period - seg * (len(levels) - 1), v, np.float32)
+                                  for i, v in enumerate(levels)])
+            x = np.tile(pat, total // period + 1)[:total].copy()
+            for _ in range(int(rng.integers(5, 15))):      # a few distinct events so that not everything ties
+                p = int(rng.integers(100, total - 100))
+                x[p:p + int(rng.integers(10, 40))] += np.float32(int(rng.integers(-20, 20)))
+            row = np.full(9000, np.nan, np.float32)
+            row[:total + 300] = np.concatenate([x, np.full(300, 95, np.float32)])
+            rows.append(row)
+            a0.append(100)
+            a1.append(total - 100)
+    return np.stack(rows), np.array(a0, np.int64), np.array(a1, np.int64)
+
+
+def test_equal_scores_follow_the_stable_tie_rule(fp):
+    """Ties everywhere (plateaus of equal scores, equal peaks inside the suppression distance, a top-k threshold among
+    equal scores, a crowded threshold bin): the kernel's order-independent forms must give what the reference's sequential
+    code gives with a STABLE sort (the later of two equal peaks wins; numpy's default argsort leaves it unspecified)."""
+    from oracle import wdx_oracle as o
+
+    sig, a0, a1 = _tie_signals()
+    status, fpt, dwell, stats = oracle_fingerprints(sig, a0, a1, stable_ties=True)
+    assert (status == 0).sum() >= 6
+    assert sum(o.fingerprint_has_ties(sig[r], int(a0[r]), int(a1[r])) for r in range(sig.shape[0])) >= 6
+    _same(fp.extract(sig, a0, a1), status, fpt, dwell, stats)
+
+
 def test_sig_len_detect_ok_and_row_end(fp):
     sig, a0, a1 = synth_adapter_signals(40, seed=13, width=8000)
     lens = (~np.isnan(sig)).sum(axis=1).astype(np.int32)

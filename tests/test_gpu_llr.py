@@ -180,10 +180,12 @@ def test_gpu_whole_test_file_raw_signal_to_barcode_calls(g4000, models):
     want_label[g["stable_idx"]] = g["stable_label"]
     assert set(g["stable_idx"].tolist()) <= set(g["tie_reads"].tolist()) and g["stable_idx"].size <= 2
     mismatches = {}
-    for mode, inp in (("guarded", "float"), ("exact", "adc")):
+    # (the third pass: the sequential form of the step, without the fingerprint pass next to the LLR tail)
+    for mode, inp, overlap in (("guarded", "float", True), ("exact", "adc", True), ("guarded", "adc", False)):
         mp = DTW_SVM(models["WDX4_rna004_v1_0"], device=0, mode=mode)
         dmx = MinibatchDemuxer(mp, md, core=spc.core, cnn_boundaries=spc.cnn_boundaries, validate_config=combined.ValidateConfig(),
-                               fp_config=FingerprintConfig(**_fp_cfg(g)), device=0, llr=_llr_cfg(g), full_detect_report=True)
+                               fp_config=FingerprintConfig(**_fp_cfg(g)), device=0, llr=_llr_cfg(g), full_detect_report=True,
+                               overlap_llr_tail=overlap)
         assert dmx.llr_fallback is None
         res = []
         for lo in range(0, n, 1000):
@@ -203,14 +205,15 @@ def test_gpu_whole_test_file_raw_signal_to_barcode_calls(g4000, models):
             "label": np.flatnonzero(good & (labels != want_label)),
             "label_failed_reads": np.flatnonzero(~good & (labels != -1)),
         }
-        mismatches[mode] = {k: v.tolist() for k, v in bad.items() if v.size}
+        key = mode if overlap else mode + "_sequential"
+        mismatches[key] = {k: v.tolist() for k, v in bad.items() if v.size}
         reasons = [res[i // 1000].fail_reason(i % 1000) or "" for i in np.flatnonzero(g["success"] == 0)]
         want = [str(x) for x in g["fail_reason"][g["success"] == 0]]
         if reasons != want:
-            mismatches[mode]["fail_reason"] = [(int(i), a, b) for i, a, b in zip(np.flatnonzero(g["success"] == 0), reasons, want) if a != b][:10]
+            mismatches[key]["fail_reason"] = [(int(i), a, b) for i, a, b in zip(np.flatnonzero(g["success"] == 0), reasons, want) if a != b][:10]
         df = res[0].predictions
         assert list(df["#read_id"]) == [str(x) for x in g["read_ids"][:1000][good[:1000]]]
         dmx.close()
     md.close()
-    assert mismatches == {"guarded": {}, "exact": {}}, mismatches      # the mismatch list must be empty
+    assert mismatches == {"guarded": {}, "exact": {}, "guarded_sequential": {}}, mismatches      # the mismatch list must be empty
     assert (g["path"] == 2).sum() == 30 and (g["path"] == 1).sum() == 5 and g["success"].sum() == 3837

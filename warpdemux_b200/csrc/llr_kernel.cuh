@@ -310,8 +310,12 @@ __device__ __noinline__ int llr_find_peaks(const double* x, int n, int distance,
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             const int dir = side ? 1 : -1;
-            double vmin = xp;
-            int vbase = peak;
+            // every lane keeps the minimum of the samples IT visits (strictly smaller only: its visits move away from the
+            // peak) and how far from the peak it lies; ONE reduction over (value, then distance) behind the walk gives the
+            // minimum and the position closest to the peak where it is reached (lane 0's first visit is the peak itself:
+            // value xp, distance 0).  Before: a five-round (value, index) reduction in every 32-sample step.
+            double lv = INFINITY;
+            int ld = 0x7fffffff;
             for (int base = peak;; base += 32 * dir) {
                 const int idx = base + lane * dir;
                 const bool inside = idx >= 0 && idx < n;
@@ -319,25 +323,23 @@ __device__ __noinline__ int llr_find_peaks(const double* x, int n, int distance,
                 const bool go = inside && (v <= xp);
                 const unsigned stop = __ballot_sync(full, !go);
                 const int first = stop ? (__ffs(stop) - 1) : 32;       // lanes below `first` belong to the walk
-                double cv = (lane < first) ? v : INFINITY;
-                int ci = (lane < first) ? lane : 64;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    const double ov = __shfl_xor_sync(full, cv, o);
-                    const int oi = __shfl_xor_sync(full, ci, o);
-                    if (ov < cv || (ov == cv && oi < ci)) {
-                        cv = ov;
-                        ci = oi;
-                    }
-                }
-                if (cv < vmin) {   // strictly smaller than everything closer to the peak
-                    vmin = cv;
-                    vbase = base + ci * dir;
+                if (lane < first && v < lv) {
+                    lv = v;
+                    ld = (idx - peak) * dir;
                 }
                 if (stop) break;
             }
-            mins[side] = vmin;
-            bases[side] = vbase;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ov = __shfl_xor_sync(full, lv, o);
+                const int od = __shfl_xor_sync(full, ld, o);
+                if (ov < lv || (ov == lv && od < ld)) {
+                    lv = ov;
+                    ld = od;
+                }
+            }
+            mins[side] = lv;
+            bases[side] = peak + ld * dir;
         }
         const double lmin = mins[0], rmin = mins[1];
         const int lb = bases[0], rb = bases[1];

@@ -375,7 +375,13 @@ __device__ __noinline__ int llr_find_peaks(const double* x, int n, int distance,
         if (lane == 0) w.keep[j] = keep;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (P <= FP_THREADS) {      // number of peaks that passed the filters and the first two of them, by a scan
+        const uint32_t kf = (tid < P && w.keep[tid]) ? 1u : 0u;
+        uint32_t tot = 0;
+        const uint32_t pos = block_exscan(kf, s, &tot);
+        if (kf && pos < 2) sh.first[pos] = w.pk[tid];
+        if (tid == 0) sh.count = (int)tot;
+    } else if (tid == 0) {
         int m = 0;
         for (int j = 0; j < P; j++) {
             if (w.keep[j]) {
